@@ -1,0 +1,287 @@
+"""ctypes front-end of the CPU oracle (oracle/oracle.cpp).
+
+TEST INFRASTRUCTURE ONLY: importable from tests/, __graft_entry__.smoke() and
+bench.py's cpu_baseline / --impl reference legs.  The product package
+(legume-rs_b200/) never imports this module.
+
+All dense matrices are column-major f32 like nalgebra's DMatrix; here they are
+numpy arrays of shape (ncols, nrows) in C order, i.e. `proj[j]` is cell j's
+K-vector.  Helper names follow the reference functions they restate.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.path.join(_HERE, "liblegume_oracle.so")
+
+
+def build(force: bool = False) -> str:
+    """Compile the oracle with its committed Makefile (building the checker is not using it)."""
+    src = os.path.join(_HERE, "oracle.cpp")
+    stale = (not os.path.exists(_LIB_PATH)) or os.path.getmtime(_LIB_PATH) < max(
+        os.path.getmtime(src), os.path.getmtime(os.path.join(_HERE, "oracle.h")))
+    if force or stale:
+        subprocess.run(["make", "-C", _HERE], check=True, capture_output=True)
+    return _LIB_PATH
+
+
+_lib = None
+
+_u64p = np.ctypeslib.ndpointer(np.uint64, flags="C_CONTIGUOUS")
+_u32p = np.ctypeslib.ndpointer(np.uint32, flags="C_CONTIGUOUS")
+_u8p = np.ctypeslib.ndpointer(np.uint8, flags="C_CONTIGUOUS")
+_f32p = np.ctypeslib.ndpointer(np.float32, flags="C_CONTIGUOUS")
+_f64p = np.ctypeslib.ndpointer(np.float64, flags="C_CONTIGUOUS")
+
+
+def _ptr(a, ct):
+    return None if a is None else a.ctypes.data_as(C.POINTER(ct))
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        build()
+        _lib = C.CDLL(_LIB_PATH)
+        L = _lib
+        L.orc_digamma.restype = C.c_float
+        L.orc_digamma.argtypes = [C.c_float]
+        L.orc_trigamma.restype = C.c_float
+        L.orc_trigamma.argtypes = [C.c_float]
+        L.orc_l2_sq.restype = C.c_float
+        L.orc_l2_sq.argtypes = [_f32p, _f32p, C.c_int]
+        L.orc_assign_groups.restype = C.c_uint32
+        L.orc_assign_groups_padded.restype = C.c_uint32
+        L.orc_level_sort_dims.restype = C.c_int
+        L.orc_binary_codes.restype = C.c_int
+        L.orc_sim_poisson_csc.restype = C.c_uint64
+    return _lib
+
+
+def _csc(indptr, indices, data):
+    return (np.ascontiguousarray(indptr, np.uint64), np.ascontiguousarray(indices, np.uint64),
+            np.ascontiguousarray(data, np.float32))
+
+
+# ---- stage 1 -------------------------------------------------------------------------------
+def project_raw(indptr, indices, data, basis_kd, nthreads=1):
+    """project_columns_visitor (random_projection.rs:169-199). basis_kd: (D, K) array = K×D col-major."""
+    indptr, indices, data = _csc(indptr, indices, data)
+    basis_kd = np.ascontiguousarray(basis_kd, np.float32)
+    n = len(indptr) - 1
+    K = basis_kd.shape[1]
+    out = np.empty((n, K), np.float32)
+    lib().orc_project_raw(_ptr(indptr, C.c_uint64), _ptr(indices, C.c_uint64), _ptr(data, C.c_float),
+                          C.c_uint64(n), _ptr(basis_kd, C.c_float), C.c_int(K), _ptr(out, C.c_float),
+                          C.c_int(nthreads))
+    return out
+
+
+def project_finish(proj, batch=None, nbatch=0):
+    """batch centring + standardise + clamp (random_projection.rs:378-407); returns a new array."""
+    out = np.ascontiguousarray(proj, np.float32).copy()
+    n, K = out.shape
+    b = None if batch is None else np.ascontiguousarray(batch, np.uint32)
+    lib().orc_project_finish(_ptr(out, C.c_float), C.c_int(K), C.c_uint64(n), _ptr(b, C.c_uint32),
+                             C.c_uint32(nbatch))
+    return out
+
+
+def project(indptr, indices, data, basis_kd, batch=None, nbatch=0, nthreads=1):
+    return project_finish(project_raw(indptr, indices, data, basis_kd, nthreads), batch, nbatch)
+
+
+# ---- stage 2 -------------------------------------------------------------------------------
+def binary_codes(proj, kk, details=False):
+    """binary_sort_columns (random_projection.rs:535-564)."""
+    proj = np.ascontiguousarray(proj, np.float32)
+    n, K = proj.shape
+    codes = np.zeros(n, np.uint64)
+    q = np.zeros((kk, K), np.float32)
+    u = np.zeros((kk, kk), np.float32)
+    sig = np.zeros(kk, np.float32)
+    mean = np.zeros(kk, np.float32)
+    rc = lib().orc_binary_codes(_ptr(proj, C.c_float), C.c_int(K), C.c_uint64(n), C.c_int(kk),
+                                _ptr(codes, C.c_uint64), _ptr(q, C.c_float), _ptr(u, C.c_float),
+                                _ptr(sig, C.c_float), _ptr(mean, C.c_float))
+    if rc != 0:
+        raise ValueError("orc_binary_codes: bad arguments")
+    return (codes, q, u, sig, mean) if details else codes
+
+
+def householder_q(a):
+    """a: (r, K) array = K×r col-major -> thin Q same shape."""
+    a = np.ascontiguousarray(a, np.float32)
+    r, K = a.shape
+    q = np.zeros_like(a)
+    lib().orc_householder_q(_ptr(a, C.c_float), C.c_int(K), C.c_int(r), _ptr(q, C.c_float))
+    return q
+
+
+def jacobi_eig(g):
+    g = np.ascontiguousarray(g, np.float64)
+    n = g.shape[0]
+    ev = np.zeros(n)
+    vec = np.zeros((n, n))
+    lib().orc_jacobi_eig(_ptr(g, C.c_double), C.c_int(n), _ptr(ev, C.c_double), _ptr(vec, C.c_double))
+    return ev, vec  # vec[k] = k-th eigenvector
+
+
+# ---- stage 3 -------------------------------------------------------------------------------
+def assign_groups(codes):
+    codes = np.ascontiguousarray(codes, np.uint64)
+    out = np.zeros(len(codes), np.uint32)
+    ng = lib().orc_assign_groups(_ptr(codes, C.c_uint64), C.c_uint64(len(codes)), _ptr(out, C.c_uint32))
+    return out, int(ng)
+
+
+def assign_groups_padded(labels, k):
+    labels = np.ascontiguousarray(labels, np.uint64)
+    out = np.zeros(len(labels), np.uint32)
+    ng = lib().orc_assign_groups_padded(_ptr(labels, C.c_uint64), C.c_uint64(len(labels)), C.c_uint64(k),
+                                        _ptr(out, C.c_uint32))
+    return out, int(ng)
+
+
+def level_sort_dims(sort_dim, num_levels):
+    out = (C.c_int * max(num_levels, 1))()
+    n = lib().orc_level_sort_dims(C.c_int(sort_dim), C.c_int(num_levels), out)
+    return [out[i] for i in range(n)]
+
+
+# ---- stage 4 -------------------------------------------------------------------------------
+def collapse_basic(indptr, indices, data, nrows, group_of_cell, S, mult=None):
+    indptr, indices, data = _csc(indptr, indices, data)
+    g = np.ascontiguousarray(group_of_cell, np.uint32)
+    m = None if mult is None else np.ascontiguousarray(mult, np.float32)
+    n = len(indptr) - 1
+    sum_ds = np.zeros((S, nrows), np.float32)
+    size_s = np.zeros(S, np.float32)
+    lib().orc_collapse_basic(_ptr(indptr, C.c_uint64), _ptr(indices, C.c_uint64), _ptr(data, C.c_float),
+                             C.c_uint64(nrows), C.c_uint64(n), _ptr(g, C.c_uint32), _ptr(m, C.c_float),
+                             C.c_uint32(S), _ptr(sum_ds, C.c_float), _ptr(size_s, C.c_float))
+    return sum_ds, size_s
+
+
+def collapse_batch(indptr, indices, data, nrows, group_of_cell, batch_of_cell, S, B, mult=None):
+    indptr, indices, data = _csc(indptr, indices, data)
+    g = np.ascontiguousarray(group_of_cell, np.uint32)
+    b = np.ascontiguousarray(batch_of_cell, np.uint32)
+    m = None if mult is None else np.ascontiguousarray(mult, np.float32)
+    n = len(indptr) - 1
+    sum_db = np.zeros((B, nrows), np.float32)
+    n_bs = np.zeros((S, B), np.float32)
+    lib().orc_collapse_batch(_ptr(indptr, C.c_uint64), _ptr(indices, C.c_uint64), _ptr(data, C.c_float),
+                             C.c_uint64(nrows), C.c_uint64(n), _ptr(g, C.c_uint32), _ptr(b, C.c_uint32),
+                             _ptr(m, C.c_float), C.c_uint32(S), C.c_uint32(B), _ptr(sum_db, C.c_float),
+                             _ptr(n_bs, C.c_float))
+    return sum_db, n_bs
+
+
+def merge_stat(fine_ds, fine_to_coarse, ncoarse):
+    fine_ds = np.ascontiguousarray(fine_ds, np.float32)
+    nfine, D = fine_ds.shape
+    f2c = np.ascontiguousarray(fine_to_coarse, np.uint32)
+    out = np.zeros((ncoarse, D), np.float32)
+    lib().orc_merge_stat(_ptr(fine_ds, C.c_float), C.c_uint64(D), C.c_uint32(nfine), _ptr(f2c, C.c_uint32),
+                         C.c_uint32(ncoarse), _ptr(out, C.c_float))
+    return out
+
+
+# ---- stage 5 -------------------------------------------------------------------------------
+TARGET_ALL, TARGET_MEAN_ONLY, TARGET_MEAN_AND_LOG_MEAN = 0, 1, 2
+
+
+def digamma(x):
+    return float(lib().orc_digamma(C.c_float(x)))
+
+
+def trigamma(x):
+    return float(lib().orc_trigamma(C.c_float(x)))
+
+
+def gamma_calibrate(num, den, a0=1.0, b0=1.0, target=TARGET_ALL):
+    num = np.ascontiguousarray(num, np.float32)
+    den = np.ascontiguousarray(den, np.float32)
+    outs = [np.zeros_like(num) for _ in range(4)]
+    lib().orc_gamma_calibrate(_ptr(num, C.c_float), _ptr(den, C.c_float), C.c_uint64(num.size), C.c_float(a0),
+                              C.c_float(b0), C.c_int(target), *[_ptr(o, C.c_float) for o in outs])
+    return dict(mean=outs[0], sd=outs[1], log_mean=outs[2], log_sd=outs[3])
+
+
+def optimize_single(sum_ds, size_s, a0=1.0, b0=1.0, target=TARGET_ALL):
+    sum_ds = np.ascontiguousarray(sum_ds, np.float32)
+    size_s = np.ascontiguousarray(size_s, np.float32)
+    S, D = sum_ds.shape
+    outs = [np.zeros_like(sum_ds) for _ in range(4)]
+    lib().orc_optimize_single(_ptr(sum_ds, C.c_float), _ptr(size_s, C.c_float), C.c_uint64(D), C.c_uint32(S),
+                              C.c_float(a0), C.c_float(b0), C.c_int(target), *[_ptr(o, C.c_float) for o in outs])
+    return dict(mean=outs[0], sd=outs[1], log_mean=outs[2], log_sd=outs[3])
+
+
+def optimize_batched(obs, imp, res, size_s, obs_db, n_bs, a0=1.0, b0=1.0, num_iter=30, target=TARGET_ALL):
+    obs = np.ascontiguousarray(obs, np.float32)
+    imp = np.ascontiguousarray(imp, np.float32)
+    res = np.ascontiguousarray(res, np.float32)
+    size_s = np.ascontiguousarray(size_s, np.float32)
+    obs_db = np.ascontiguousarray(obs_db, np.float32)
+    n_bs = np.ascontiguousarray(n_bs, np.float32)
+    S, D = obs.shape
+    B = obs_db.shape[0]
+    mu_obs, mu_adj, mu_res, gam, lm = [np.zeros_like(obs) for _ in range(5)]
+    delta = np.zeros_like(obs_db)
+    lib().orc_optimize_batched(_ptr(obs, C.c_float), _ptr(imp, C.c_float), _ptr(res, C.c_float),
+                               _ptr(size_s, C.c_float), _ptr(obs_db, C.c_float), _ptr(n_bs, C.c_float),
+                               C.c_uint64(D), C.c_uint32(S), C.c_uint32(B), C.c_float(a0), C.c_float(b0),
+                               C.c_int(num_iter), C.c_int(target), _ptr(mu_obs, C.c_float),
+                               _ptr(mu_adj, C.c_float), _ptr(mu_res, C.c_float), _ptr(gam, C.c_float),
+                               _ptr(delta, C.c_float), _ptr(lm, C.c_float))
+    return dict(mu_observed=mu_obs, mu_adjusted=mu_adj, mu_residual=mu_res, gamma=gam, delta=delta,
+                mu_adjusted_log_mean=lm)
+
+
+# ---- stage 6 -------------------------------------------------------------------------------
+def l2_sq(a, b):
+    a = np.ascontiguousarray(a, np.float32)
+    b = np.ascontiguousarray(b, np.float32)
+    return float(lib().orc_l2_sq(a, b, C.c_int(len(a))))
+
+
+def knn_topk(ref, qry, k, exclude=None, nthreads=1):
+    """ref: (nr, d), qry: (nq, d). Returns (idx (nq,k) uint32, dist (nq,k) f32), nearest first."""
+    ref = np.ascontiguousarray(ref, np.float32)
+    qry = np.ascontiguousarray(qry, np.float32)
+    nr, d = ref.shape
+    nq = qry.shape[0]
+    ex = None if exclude is None else np.ascontiguousarray(exclude, np.uint32)
+    idx = np.zeros((nq, k), np.uint32)
+    dist = np.zeros((nq, k), np.float32)
+    lib().orc_knn_topk(_ptr(ref, C.c_float), C.c_uint64(nr), _ptr(qry, C.c_float), C.c_uint64(nq), C.c_int(d),
+                       C.c_int(k), _ptr(ex, C.c_uint32), _ptr(idx, C.c_uint32), _ptr(dist, C.c_float),
+                       C.c_int(nthreads))
+    return idx, dist
+
+
+# ---- synthetic counts ------------------------------------------------------------------------
+def sim_poisson_csc(seed, D, col_lo, col_hi, topic_of_cell, batch_of_cell, ntopic, nbatch, lam, p0, npiece):
+    """CPU twin of lg_sim_poisson_csc.  topic/batch arrays cover [col_lo, col_hi)."""
+    n = col_hi - col_lo
+    t = np.ascontiguousarray(topic_of_cell, np.uint8)
+    b = np.ascontiguousarray(batch_of_cell, np.uint8)
+    lam = np.ascontiguousarray(lam, np.float32)
+    p0 = np.ascontiguousarray(p0, np.float32)
+    npiece = np.ascontiguousarray(npiece, np.uint8)
+    indptr = np.zeros(n + 1, np.uint64)
+    args = [C.c_uint64(seed), C.c_uint64(D), C.c_uint64(col_lo), C.c_uint64(col_hi), _ptr(t, C.c_uint8),
+            _ptr(b, C.c_uint8), C.c_uint32(ntopic), C.c_uint32(nbatch), _ptr(lam, C.c_float), _ptr(p0, C.c_float),
+            _ptr(npiece, C.c_uint8), _ptr(indptr, C.c_uint64)]
+    nnz = int(lib().orc_sim_poisson_csc(*args, None, None))
+    indices = np.zeros(nnz, np.uint64)
+    data = np.zeros(nnz, np.float32)
+    lib().orc_sim_poisson_csc(*args, _ptr(indices, C.c_uint64), _ptr(data, C.c_float))
+    return indptr, indices, data

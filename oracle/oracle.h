@@ -1,0 +1,105 @@
+/*
+ * oracle.h — C API of the CPU oracle for the legume-rs hot path.
+ *
+ * TEST INFRASTRUCTURE ONLY.  Nothing under legume-rs_b200/ may include, link or
+ * dlopen this.  Only tests/, __graft_entry__.smoke() and bench.py's
+ * cpu_baseline / --impl reference legs may call it, and only as the checker.
+ *
+ * The reference (causalpathlab/legume-rs v0.3.2, Rust) cannot be compiled in
+ * this image (no cargo/rustc, no vendored crates), so this is a RESTATEMENT of
+ * its arithmetic in C++.  Every function cites the reference file:line it
+ * follows.  Layouts follow nalgebra: all dense matrices are column-major f32.
+ *
+ * Pinning status:
+ *   - trigamma / log_sd           pinned by matrix-param/src/dmatrix_gamma_tests.rs:9-32
+ *   - posterior mean (a0+Σy)/(b0+n) pinned by data-beans-alg/tests/weighted_columns.rs:76-121
+ *   - gene-blocked == whole fit    pinned by collapse_data/stats_tests.rs:33-97 (property)
+ *   - exact kNN == brute force     pinned by matrix-util/src/knn/tests.rs:74-150 (property)
+ *   - pad/level bookkeeping        pinned by collapse_data/refine.rs doc examples
+ *   - projection, codes, digamma:  PARITY UNPINNED — the reference's tests hold no
+ *     golden vectors for them and the third-party arithmetic
+ *     (nalgebra 0.34.2 QR/SVD, special 0.13.1 digamma) is not on disk; those are
+ *     restated from their published algorithms.
+ */
+#ifndef LEGUME_ORACLE_H
+#define LEGUME_ORACLE_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- stage 1: projection (random_projection.rs:169-199, 341-415) ---------- */
+/* raw K×N projection: log1p -> L2 normalise -> ascending-row axpy, no centring */
+void orc_project_raw(const uint64_t* indptr, const uint64_t* indices, const float* data,
+                     uint64_t ncols, const float* basis_kd, int K, float* proj_kn, int nthreads);
+/* batch centring + per-cell standardise + clamp + re-standardise, in place.
+ * batch may be NULL (no centring). */
+void orc_project_finish(float* proj_kn, int K, uint64_t ncols, const uint32_t* batch, uint32_t nbatch);
+
+/* ---- stage 2: binary codes (random_projection.rs:535-564, dmatrix_rsvd.rs) - */
+/* returns 0 on success.  scratch outputs may be NULL.
+ * out_q (K×kk), out_b (kk×N), out_u (kk×kk, f32), out_sigma (kk), out_mean (kk). */
+int orc_binary_codes(const float* proj_kn, int K, uint64_t ncols, int kk, uint64_t* codes,
+                     float* out_q, float* out_u, float* out_sigma, float* out_mean);
+/* Householder QR of a K×r block, thin Q (K×r) — nalgebra qr().q() restated */
+void orc_householder_q(const float* a_kr, int K, int r, float* q_kr);
+/* cyclic Jacobi on a symmetric n×n f64 matrix: eigenvalues descending */
+void orc_jacobi_eig(const double* g, int n, double* evals, double* evecs);
+
+/* ---- stage 3: group ids (sparse_io_vector/groups.rs:13-37) ---------------- */
+/* lexicographic rank of code.to_string(); returns number of groups */
+uint32_t orc_assign_groups(const uint64_t* codes, uint64_t n, uint32_t* group_of_cell);
+/* refine.rs:21-35 + groups.rs: zero-padded labels => numeric order */
+uint32_t orc_assign_groups_padded(const uint64_t* labels, uint64_t n, uint64_t k, uint32_t* group_of_cell);
+/* refine.rs:718-734 */
+int orc_level_sort_dims(int sort_dim, int num_levels, int* out_dims);
+
+/* ---- stage 4: collapse (collapse_data/stats.rs:110-164) ------------------- */
+void orc_collapse_basic(const uint64_t* indptr, const uint64_t* indices, const float* data,
+                        uint64_t nrows, uint64_t ncols, const uint32_t* group_of_cell,
+                        const float* mult /*or NULL*/, uint32_t S, float* sum_ds, float* size_s);
+void orc_collapse_batch(const uint64_t* indptr, const uint64_t* indices, const float* data,
+                        uint64_t nrows, uint64_t ncols, const uint32_t* group_of_cell,
+                        const uint32_t* batch_of_cell, const float* mult, uint32_t S, uint32_t B,
+                        float* sum_db, float* n_bs);
+/* stats.rs:790-833 */
+void orc_merge_stat(const float* fine_ds, uint64_t nrows, uint32_t nfine, const uint32_t* fine_to_coarse,
+                    uint32_t ncoarse, float* coarse_ds);
+
+/* ---- stage 5: Poisson-Gamma posterior (dmatrix_gamma.rs, stats.rs:206-368) - */
+float orc_digamma(float x);   /* special 0.13.1 (AS 103), f32 arithmetic */
+float orc_trigamma(float x);  /* special 0.13.1 (AS 121), f32 arithmetic */
+/* target: 0 = All, 1 = MeanOnly, 2 = MeanAndLogMean.  Output planes may be NULL. */
+void orc_gamma_calibrate(const float* num, const float* den, uint64_t n, float a0, float b0, int target,
+                         float* mean, float* sd, float* log_mean, float* log_sd);
+/* single-batch optimize_block (B<=1 arm): denom = size_s broadcast, optional sparsify */
+void orc_optimize_single(const float* sum_ds, const float* size_s, uint64_t D, uint32_t S, float a0, float b0,
+                         int target, float* mean, float* sd, float* log_mean, float* log_sd);
+/* batched optimize_block (B>1 arm), means only + optional log planes of mu_adj.
+ * outs: each D×S (delta D×B); any may be NULL. */
+void orc_optimize_batched(const float* obs_ds, const float* imp_ds, const float* res_ds, const float* size_s,
+                          const float* obs_db, const float* n_bs, uint64_t D, uint32_t S, uint32_t B,
+                          float a0, float b0, int num_iter, int target,
+                          float* mu_obs, float* mu_adj, float* mu_res, float* gamma, float* delta,
+                          float* mu_adj_log_mean);
+
+/* ---- stage 6: exact kNN (knn/metric.rs:19-45, exact.rs:36-55, mod.rs:249-299) */
+float orc_l2_sq(const float* a, const float* b, int d);
+/* ref d×nr, qry d×nq column-major; exclude[q] = reference index to drop or UINT32_MAX.
+ * out_idx/out_dist are k×nq (nearest first, true Euclidean), padded with UINT32_MAX / inf. */
+void orc_knn_topk(const float* ref, uint64_t nr, const float* qry, uint64_t nq, int d, int k,
+                  const uint32_t* exclude, uint32_t* out_idx, float* out_dist, int nthreads);
+
+/* ---- synthetic counts (data-beans-sim/src/core.rs:155-203 restated with a
+ *      counter-based RNG so CPU and GPU produce identical matrices) ---------- */
+/* table entry e = ((k*B + b)*D + g): lam[e], p0[e]=exp(-lam[e]) precomputed by the caller,
+ * npiece[e] >= 1.  Returns nnz; if indices==NULL only counts (fills indptr). */
+uint64_t orc_sim_poisson_csc(uint64_t seed, uint64_t D, uint64_t col_lo, uint64_t col_hi,
+                             const uint8_t* topic_of_cell, const uint8_t* batch_of_cell, uint32_t ntopic,
+                             uint32_t nbatch, const float* lam, const float* p0, const uint8_t* npiece,
+                             uint64_t* indptr, uint64_t* indices, float* data);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
