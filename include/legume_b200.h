@@ -1,0 +1,199 @@
+/*
+ * legume_b200.h — C ABI of liblegume_b200.so: the B200-native replacement for the
+ * data-parallel hot path of causalpathlab/legume-rs (v0.3.2).
+ *
+ * The reference has no FFI of its own; its boundary for this path is the set of Rust
+ * trait methods listed in SURVEY.md §8(b).  Each entry point below names the reference
+ * interface it replaces (file:line relative to the legume-rs tree).  INTEGRATION.md shows
+ * the `legume-b200-sys` Rust binding a maintainer would add.
+ *
+ * Conventions (all follow the reference's own):
+ *   - every call returns an int status (LG_OK == 0); lg_last_error(ctx) gives the message.
+ *     Nothing aborts or throws across the boundary (the reference returns anyhow::Result).
+ *   - dense matrices are column-major f32 (nalgebra DMatrix).  "K x N" means each cell's
+ *     K-vector is contiguous.
+ *   - the caller owns every buffer passed in or out; inputs are borrowed for the call only.
+ *   - EVERY data pointer may be host memory or device memory of ctx's GPU; the library
+ *     detects which (cudaPointerGetAttributes) and stages host buffers itself.  Device
+ *     pointers are used in place, on ctx's stream, with no synchronisation on return;
+ *     when any argument of a call is a host pointer the call synchronises the stream
+ *     before returning so host outputs are valid.
+ *   - one in-flight call per ctx; one ctx per device; callable from any thread.
+ *   - there is no CPU fallback: with no usable CUDA device lg_ctx_create fails.
+ */
+#ifndef LEGUME_B200_H
+#define LEGUME_B200_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LG_OK 0
+#define LG_ERR_INVALID 1   /* bad argument (shape mismatch, null pointer, out-of-range index) */
+#define LG_ERR_CUDA 2      /* a CUDA runtime call failed; message holds cudaGetErrorString */
+#define LG_ERR_NOMEM 3     /* device or host allocation failed */
+#define LG_ERR_INTERNAL 4
+
+#define LG_BLOCK_CELLS 1024 /* granularity of the order-fixed reductions over cells */
+
+/* matrix_param::traits::CalibrateTarget (matrix-param/src/traits.rs:31-39) */
+#define LG_TARGET_ALL 0
+#define LG_TARGET_MEAN_ONLY 1
+#define LG_TARGET_MEAN_AND_LOG_MEAN 2
+
+typedef struct lg_ctx lg_ctx;
+typedef struct lg_csc lg_csc; /* device-resident CSC block: indptr u64, row index u32, value f32 */
+
+/* ---- context -------------------------------------------------------------------------- */
+int lg_ctx_create(int device, lg_ctx** out);
+int lg_ctx_destroy(lg_ctx* ctx);
+const char* lg_last_error(const lg_ctx* ctx);
+/* run on an externally owned cudaStream_t (e.g. torch's current stream); NULL = the legacy
+ * default stream.  A fresh ctx runs on its own non-blocking stream. */
+int lg_ctx_set_stream(lg_ctx* ctx, void* cuda_stream);
+int lg_ctx_sync(lg_ctx* ctx);
+/* number of kernels this library launched through ctx since creation */
+uint64_t lg_ctx_launch_count(const lg_ctx* ctx);
+const char* lg_version(void);
+
+/* ---- data feed --------------------------------------------------------------------------
+ * replaces SparseIo::csc_column_arrays() -> (&[u64] indptr, &[u64] indices, &[f32] data)
+ * (data-beans/src/sparse_io/traits.rs:98-100; zarr impl sparse_backend/zarr.rs:982-994) and the
+ * per-backend row remap of SparseIoVec::read_columns_csc (sparse_io_vector/read.rs:202-219).
+ * Uploads columns [col_lo, col_hi) of the host arrays, narrowing row indices to u32 after a
+ * range check; row_remap (length = nrows_backend, or NULL) maps a backend row to a row of the
+ * shared feature axis, UINT32_MAX = drop the entry.  indptr has (ncols_total + 1) entries. */
+int lg_csc_upload(lg_ctx* ctx, const uint64_t* indptr, const uint64_t* indices, const float* data,
+                  uint64_t nrows, uint64_t col_lo, uint64_t col_hi, const uint32_t* row_remap,
+                  lg_csc** out);
+/* wrap arrays that already live on the device (no copy; the caller keeps them alive) */
+int lg_csc_wrap_device(lg_ctx* ctx, const uint64_t* d_indptr, const uint32_t* d_indices,
+                       const float* d_values, uint64_t nrows, uint64_t ncols, uint64_t nnz,
+                       lg_csc** out);
+int lg_csc_free(lg_ctx* ctx, lg_csc* m);
+int lg_csc_shape(const lg_csc* m, uint64_t* nrows, uint64_t* ncols, uint64_t* nnz);
+/* raw device pointers of a block (for torch interop / tests) */
+int lg_csc_device_arrays(const lg_csc* m, const uint64_t** d_indptr, const uint32_t** d_indices,
+                         const float** d_values);
+/* copy a block back to host arrays in the reference's u64/u64/f32 form */
+int lg_csc_download(lg_ctx* ctx, const lg_csc* m, uint64_t* indptr, uint64_t* indices, float* data);
+
+/* ---- stage 1: random projection -----------------------------------------------------------
+ * replaces RandProjOps::project_columns_with_batch_correction_seeded and
+ * project_columns_weighted_seeded (data-beans-alg/src/random_projection.rs:341-495).  The basis
+ * is an INPUT (identical-projection-matrix contract): basis_kd is K x D column-major, i.e. the
+ * reference's `basis_dk.transpose()` (:360); for the weighted variant the caller zeroes/scales
+ * rows exactly as :438-444 do.  batch_of_cell: u32[ncols] in [0, nbatch) or NULL.
+ * out_proj: K x ncols. */
+int lg_project(lg_ctx* ctx, const lg_csc* m, const float* basis_kd, int K,
+               const uint32_t* batch_of_cell, uint32_t nbatch, float* out_proj);
+/* staged form, for cell-sharded runs (device pointers only):
+ *   raw        project_columns_visitor                         (:169-199)
+ *   partials   per-1024-cell-block f64 sums of proj per (batch, dim) and cell counts:
+ *              out[blk][b*(K+1) + k], k == K holds the count   (:378-388)
+ *   finalize   sums block partials in block order -> out[M] (f64); shards all-gather their
+ *              partials in rank order first, so the result does not depend on the GPU count
+ *   centre_scale  subtract batch means, per-cell standardise, track global (min,max) (:399-401)
+ *   clamp_rescale clamp to [-4,4] and standardise again         (:402-407) */
+int lg_project_raw(lg_ctx* ctx, const lg_csc* m, const float* basis_kd, int K, float* out_proj);
+int lg_proj_batch_partials(lg_ctx* ctx, const float* d_proj, int K, uint64_t ncols,
+                           const uint32_t* d_batch, uint32_t nbatch, double* d_partials);
+int lg_block_partials_finalize(lg_ctx* ctx, const double* d_partials, uint64_t nblocks, uint32_t M,
+                               double* d_out);
+int lg_proj_centre_scale(lg_ctx* ctx, float* d_proj, int K, uint64_t ncols, const uint32_t* d_batch,
+                         uint32_t nbatch, const double* d_batch_sums, float* d_minmax);
+int lg_proj_clamp_rescale(lg_ctx* ctx, float* d_proj, int K, uint64_t ncols);
+
+/* ---- stage 2: binary codes -----------------------------------------------------------------
+ * replaces binary_sort_columns (random_projection.rs:535-564) = rsvd (matrix-util/src/
+ * dmatrix_rsvd.rs:85-180) + per-dimension standardise + sign bits.  codes: u64[ncols] < 2^kk. */
+int lg_binary_codes(lg_ctx* ctx, const float* proj_kn, int K, uint64_t ncols, int kk, uint64_t* out_codes);
+/* staged form (device pointers unless noted):
+ *   basis      host math: Q (K x kk) = first kk columns of qr(X[:, 0..r]).q(), r = min(kk+5, N)
+ *   gram       B = Q^T X (kk x ncols) and block partials of the upper triangle of B B^T
+ *              (M = kk(kk+1)/2, entry (a,b), a<=b, at a*kk - a(a-1)/2 + (b-a))
+ *   factor     host math: Jacobi on the Gram sums -> U (kk x kk f32), sigma (kk), sign-fixed
+ *   vproj      V = B^T U / sigma (kk x ncols) and block partials of its column sums (M = kk)
+ *   pack       warp-ballot sign packer: bit k of code_j = [V[k,j] > mean_k] */
+int lg_codes_basis(lg_ctx* ctx, const float* first_cols_kr, int K, int r, int kk, float* out_q);
+int lg_codes_gram(lg_ctx* ctx, const float* d_proj, int K, uint64_t ncols, const float* d_q, int kk,
+                  float* d_b, double* d_partials);
+int lg_codes_factor(lg_ctx* ctx, const double* gram_sums, const float* q, int K, int kk, float* out_u,
+                    float* out_sigma);
+int lg_codes_vproj(lg_ctx* ctx, const float* d_b, int kk, uint64_t ncols, const float* d_u,
+                   const float* d_sigma, float* d_v, double* d_partials);
+int lg_codes_pack(lg_ctx* ctx, const float* d_v, int kk, uint64_t ncols, const float* d_mean,
+                  uint64_t* d_codes);
+
+/* ---- stage 3: group ids --------------------------------------------------------------------
+ * replaces SparseIoVec::assign_groups (data-beans/src/sparse_io_vector/groups.rs:13-37): groups
+ * ordered by the byte-wise order of code.to_string().  padded != 0 selects the refine path's
+ * zero-padded labels (collapse_data/refine.rs:21-35, 393-399) = numeric order. */
+int lg_assign_groups(lg_ctx* ctx, const uint64_t* codes, uint64_t ncols, int kk, int padded,
+                     uint32_t* out_group_of_cell, uint32_t* out_num_groups);
+/* staged: presence flags (u32[2^kk], OR-reducible across shards), host LUT, device map */
+int lg_code_presence(lg_ctx* ctx, const uint64_t* d_codes, uint64_t ncols, int kk, uint32_t* d_present);
+int lg_group_lut(lg_ctx* ctx, const uint32_t* present, int kk, int padded, uint32_t* out_lut,
+                 uint32_t* out_num_groups);
+int lg_codes_to_groups(lg_ctx* ctx, const uint64_t* d_codes, uint64_t ncols, int kk, const uint32_t* d_lut,
+                       uint32_t* d_group_of_cell);
+
+/* ---- stage 4: collapse ---------------------------------------------------------------------
+ * replaces CollapsingOps::collect_basic_stat / collect_batch_stat
+ * (data-beans-alg/src/collapse_data/mod.rs:477-483, stats.rs:110-164).
+ *   sum_ds[g,s] += y*w, size_s[s] += w;  sum_db[g,b] += y*w, n_bs[b,s] += w.
+ * mult = column multiplicity (sparse_io_vector/batch.rs:331-336) or NULL (all ones).
+ * Outputs are OVERWRITTEN (zeroed first).  group ids >= S are skipped.
+ * Sums of integer-valued counts are exact and order-independent below 2^24. */
+int lg_collapse_basic(lg_ctx* ctx, const lg_csc* m, const uint32_t* group_of_cell, const float* mult,
+                      uint32_t S, float* out_sum_ds, float* out_size_s);
+int lg_collapse_batch(lg_ctx* ctx, const lg_csc* m, const uint32_t* group_of_cell,
+                      const uint32_t* batch_of_cell, const float* mult, uint32_t S, uint32_t B,
+                      float* out_sum_db, float* out_n_bs);
+/* merge_stat (stats.rs:790-833): coarse[:, f2c[f]] += fine[:, f] */
+int lg_merge_stat(lg_ctx* ctx, const float* fine_ds, uint64_t nrows, uint32_t nfine,
+                  const uint32_t* fine_to_coarse, uint32_t ncoarse, float* out_coarse_ds);
+
+/* ---- stage 5: Poisson-Gamma posterior --------------------------------------------------------
+ * replaces GammaMatrix::update_stat + calibrate_with (matrix-param/src/dmatrix_gamma.rs:64-123,
+ * traits.rs:61-77) and optimize/optimize_block (collapse_data/stats.rs:206-512).
+ * a = a0 + num, b = b0 + den; mean = a/b; sd = sqrt(a)/b; log_mean = digamma(a) - ln(b);
+ * log_sd = sqrt(trigamma(a)).  Output planes not selected by target, or NULL, are not written. */
+int lg_gamma_calibrate(lg_ctx* ctx, const float* num, const float* den, uint64_t n, float a0, float b0,
+                       int target, float* mean, float* sd, float* log_mean, float* log_sd);
+/* optimize_block, B <= 1 arm (stats.rs:351-368): den[g,s] = size_s[s]; MeanOnly sparsifies */
+int lg_optimize_single(lg_ctx* ctx, const float* sum_ds, const float* size_s, uint64_t D, uint32_t S,
+                       float a0, float b0, int target, float* mean, float* sd, float* log_mean,
+                       float* log_sd);
+/* optimize_block, B > 1 arm (stats.rs:219-350): num_iter sweeps kept on-device.
+ * Outputs are posterior means (delta is D x B); mu_adj_log_mean optional (target All / MeanAndLogMean). */
+int lg_optimize_batched(lg_ctx* ctx, const float* obs_ds, const float* imp_ds, const float* res_ds,
+                        const float* size_s, const float* obs_db, const float* n_bs, uint64_t D,
+                        uint32_t S, uint32_t B, float a0, float b0, int num_iter, int target,
+                        float* mu_obs, float* mu_adj, float* mu_res, float* gamma, float* delta,
+                        float* mu_adj_log_mean);
+
+/* ---- stage 6: exact kNN ----------------------------------------------------------------------
+ * replaces ColumnDict::search_by_query_data / match_by_query_name_against / search_others with the
+ * exact backend (matrix-util/src/knn/mod.rs:152-299, exact.rs:36-55, metric.rs:19-45).
+ * ref: d x nr, qry: d x nq (column-major).  exclude: u32[nq] reference index to drop per query
+ * (UINT32_MAX = none) or NULL.  out_idx/out_dist: k x nq, nearest first, true Euclidean distance;
+ * unused slots hold UINT32_MAX / +inf.  Ranking is by the reference's squared-distance arithmetic;
+ * equal distances are ordered by lower index. */
+int lg_knn_topk(lg_ctx* ctx, const float* ref, uint64_t nr, const float* qry, uint64_t nq, int d, int k,
+                const uint32_t* exclude, uint32_t* out_idx, float* out_dist);
+
+/* ---- synthetic counts (benchmark input; data-beans-sim/src/core.rs:155-203) --------------------
+ * y[g,j] ~ Poisson(lam[(topic_j*nbatch + batch_j)*D + g]) summed over npiece pieces, kept if > 0.5.
+ * topic/batch arrays cover [col_lo, col_hi).  Counter-based RNG: identical to the oracle's twin. */
+int lg_sim_poisson_csc(lg_ctx* ctx, uint64_t seed, uint64_t D, uint64_t col_lo, uint64_t col_hi,
+                       const uint8_t* topic_of_cell, const uint8_t* batch_of_cell, uint32_t ntopic,
+                       uint32_t nbatch, const float* lam, const float* p0, const uint8_t* npiece,
+                       lg_csc** out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LEGUME_B200_H */

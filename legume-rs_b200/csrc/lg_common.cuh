@@ -1,0 +1,180 @@
+// lg_common.cuh — context, error handling and host/device buffer staging shared by all kernels.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/legume_b200.h"
+
+struct lg_ctx {
+    int device = 0;
+    int num_sms = 148;
+    size_t smem_optin = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    uint64_t launches = 0;
+    std::string err;
+    // pinned staging for small host<->device scalars
+    void* pinned = nullptr;
+    size_t pinned_bytes = 0;
+};
+
+struct lg_csc {
+    uint64_t nrows = 0, ncols = 0, nnz = 0;
+    uint64_t* indptr = nullptr;  // device, ncols + 1
+    uint32_t* indices = nullptr; // device, nnz
+    float* values = nullptr;     // device, nnz
+    bool owned = false;
+};
+
+inline int lg_fail(lg_ctx* ctx, int code, const std::string& msg) {
+    if (ctx) ctx->err = msg;
+    return code;
+}
+
+#define LG_CUDA(ctx, call)                                                                         \
+    do {                                                                                           \
+        cudaError_t e__ = (call);                                                                  \
+        if (e__ != cudaSuccess) {                                                                  \
+            char b__[512];                                                                         \
+            snprintf(b__, sizeof(b__), "%s:%d: %s: %s", __FILE__, __LINE__, #call,                 \
+                     cudaGetErrorString(e__));                                                     \
+            return lg_fail(ctx, e__ == cudaErrorMemoryAllocation ? LG_ERR_NOMEM : LG_ERR_CUDA, b__); \
+        }                                                                                          \
+    } while (0)
+
+#define LG_REQUIRE(ctx, cond, msg)                                             \
+    do {                                                                       \
+        if (!(cond)) return lg_fail(ctx, LG_ERR_INVALID, std::string(msg));    \
+    } while (0)
+
+#define LG_TRY(expr)                    \
+    do {                                \
+        int rc__ = (expr);              \
+        if (rc__ != LG_OK) return rc__; \
+    } while (0)
+
+// every kernel launch goes through this so ctx->launches is the library's own count
+#define LG_LAUNCH(ctx, kernel, grid, block, smem, ...)                          \
+    do {                                                                        \
+        kernel<<<(grid), (block), (smem), (ctx)->stream>>>(__VA_ARGS__);        \
+        (ctx)->launches++;                                                      \
+        LG_CUDA(ctx, cudaGetLastError());                                       \
+    } while (0)
+
+inline bool lg_is_device_ptr(const void* p) {
+    if (!p) return false;
+    cudaPointerAttributes a;
+    cudaError_t e = cudaPointerGetAttributes(&a, p);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
+}
+
+// Scope object that gives device views of caller buffers.  Host inputs are copied up on
+// construction; host outputs are copied back by finish().  Device pointers pass through.
+class LgStage {
+   public:
+    explicit LgStage(lg_ctx* c) : ctx_(c) {}
+    ~LgStage() {
+        for (auto& t : tmp_) cudaFreeAsync(t, ctx_->stream);
+    }
+    // read-only input; bytes may be 0 / p may be NULL -> nullptr
+    template <typename T>
+    int in(const T* p, size_t count, const T** dev) {
+        *dev = nullptr;
+        if (!p || count == 0) return LG_OK;
+        if (lg_is_device_ptr(p)) {
+            *dev = p;
+            return LG_OK;
+        }
+        any_host_ = true;
+        void* d = nullptr;
+        LG_CUDA(ctx_, cudaMallocAsync(&d, count * sizeof(T), ctx_->stream));
+        tmp_.push_back(d);
+        LG_CUDA(ctx_, cudaMemcpyAsync(d, p, count * sizeof(T), cudaMemcpyHostToDevice, ctx_->stream));
+        *dev = static_cast<const T*>(d);
+        return LG_OK;
+    }
+    // output; if host, a device scratch is returned and copied back at finish()
+    template <typename T>
+    int out(T* p, size_t count, T** dev, bool copy_in = false) {
+        *dev = nullptr;
+        if (!p || count == 0) return LG_OK;
+        if (lg_is_device_ptr(p)) {
+            *dev = p;
+            return LG_OK;
+        }
+        any_host_ = true;
+        void* d = nullptr;
+        LG_CUDA(ctx_, cudaMallocAsync(&d, count * sizeof(T), ctx_->stream));
+        tmp_.push_back(d);
+        if (copy_in) LG_CUDA(ctx_, cudaMemcpyAsync(d, p, count * sizeof(T), cudaMemcpyHostToDevice, ctx_->stream));
+        outs_.push_back({p, d, count * sizeof(T)});
+        *dev = static_cast<T*>(d);
+        return LG_OK;
+    }
+    // device scratch owned by the stage
+    template <typename T>
+    int scratch(size_t count, T** dev) {
+        void* d = nullptr;
+        LG_CUDA(ctx_, cudaMallocAsync(&d, (count ? count : 1) * sizeof(T), ctx_->stream));
+        tmp_.push_back(d);
+        *dev = static_cast<T*>(d);
+        return LG_OK;
+    }
+    int finish() {
+        for (auto& o : outs_)
+            LG_CUDA(ctx_, cudaMemcpyAsync(o.host, o.dev, o.bytes, cudaMemcpyDeviceToHost, ctx_->stream));
+        if (any_host_) LG_CUDA(ctx_, cudaStreamSynchronize(ctx_->stream));
+        outs_.clear();
+        return LG_OK;
+    }
+    bool any_host() const { return any_host_; }
+    void mark_host() { any_host_ = true; }
+
+   private:
+    struct Out {
+        void* host;
+        void* dev;
+        size_t bytes;
+    };
+    lg_ctx* ctx_;
+    std::vector<void*> tmp_;
+    std::vector<Out> outs_;
+    bool any_host_ = false;
+};
+
+// ---- device helpers -------------------------------------------------------------------------
+__device__ __forceinline__ double lg_butterfly32(double v) {
+    // fixed tree: xor offsets 16, 8, 4, 2, 1 (the oracle mirrors this order)
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) v = v + __shfl_xor_sync(0xffffffffu, v, off);
+    return v;
+}
+
+// Sum one value per thread over a 1024-thread block in the order fixed by LG_BLOCK_CELLS:
+// warp butterflies, then a butterfly over the 32 warp sums.  Result valid in warp 0.
+__device__ __forceinline__ double lg_block_sum_1024(double v, double* smem32) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    v = lg_butterfly32(v);
+    __syncthreads();
+    if (lane == 0) smem32[warp] = v;
+    __syncthreads();
+    double w = 0.0;
+    if (warp == 0) {
+        w = smem32[lane];
+        w = lg_butterfly32(w);
+    }
+    return w;
+}
+
+// host-side small dense math (lg_hostmath.cpp) — plain C++, no CUDA, no oracle
+void lgh_householder_q(const float* a_kr, int K, int r, float* q_kr);
+void lgh_jacobi_eig(const double* g, int n, double* evals, double* evecs);

@@ -1,0 +1,302 @@
+// lg_project.cu — stage 1: random projection of the sparse gene x cell matrix.
+//   K1  project_columns_visitor       data-beans-alg/src/random_projection.rs:169-199
+//   K2  batch centring / standardise / clamp                         :378-407
+#include "lg_common.cuh"
+
+// ---------------------------------------------------------------------------------------------
+// K1 (baseline CUDA-core form): one warp per cell.  Lanes load 32 nnz at a time with coalesced
+// loads, log1p them, then each nnz's (row, x) pair is broadcast and every lane accumulates its
+// NACC dims of the K-vector.  The 1/||x|| factor is applied once at the end (the reference
+// divides every x first; the difference is rounding only, inside the 1e-5 contract).
+// ---------------------------------------------------------------------------------------------
+template <int NACC>
+__global__ void __launch_bounds__(256) k_project_raw_warp(const uint64_t* __restrict__ indptr,
+                                                          const uint32_t* __restrict__ indices,
+                                                          const float* __restrict__ values, uint64_t ncols,
+                                                          const float* __restrict__ basis_kd, int K,
+                                                          float* __restrict__ out) {
+    const int lane = threadIdx.x & 31;
+    const uint64_t warp0 = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint64_t nwarps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+    for (uint64_t j = warp0; j < ncols; j += nwarps) {
+        const uint64_t lo = indptr[j], hi = indptr[j + 1];
+        float acc[NACC];
+#pragma unroll
+        for (int a = 0; a < NACC; ++a) acc[a] = 0.0f;
+        float nsq = 0.0f;
+        for (uint64_t base = lo; base < hi; base += 32) {
+            const uint64_t t = base + lane;
+            uint32_t idx = 0;
+            float x = 0.0f;
+            if (t < hi) {
+                idx = __ldg(indices + t);
+                x = log1pf(__ldg(values + t));
+            }
+            nsq = fmaf(x, x, nsq);
+            const int n = (hi - base) < 32 ? (int)(hi - base) : 32;
+            for (int s = 0; s < n; ++s) {
+                const uint32_t i = __shfl_sync(0xffffffffu, idx, s);
+                const float xs = __shfl_sync(0xffffffffu, x, s);
+                const float* row = basis_kd + (size_t)i * K;
+#pragma unroll
+                for (int a = 0; a < NACC; ++a) {
+                    const int k = lane + 32 * a;
+                    if (k < K) acc[a] = fmaf(xs, __ldg(row + k), acc[a]);
+                }
+            }
+        }
+#pragma unroll
+        for (int off = 16; off >= 1; off >>= 1) nsq += __shfl_xor_sync(0xffffffffu, nsq, off);
+        const float denom = fmaxf(sqrtf(nsq), 1e-8f);
+#pragma unroll
+        for (int a = 0; a < NACC; ++a) {
+            const int k = lane + 32 * a;
+            if (k < K) out[(size_t)j * K + k] = acc[a] / denom;
+        }
+    }
+}
+
+static int launch_project_raw(lg_ctx* ctx, const lg_csc* m, const float* d_basis, int K, float* d_out) {
+    if (m->ncols == 0) return LG_OK;
+    const int nacc = (K + 31) / 32;
+    uint64_t warps = m->ncols;
+    uint64_t blocks = (warps + 7) / 8;
+    const uint64_t cap = (uint64_t)ctx->num_sms * 32;
+    if (blocks > cap) blocks = cap;
+    switch (nacc) {
+        case 1: LG_LAUNCH(ctx, k_project_raw_warp<1>, (unsigned)blocks, 256, 0, m->indptr, m->indices, m->values, m->ncols, d_basis, K, d_out); break;
+        case 2: LG_LAUNCH(ctx, k_project_raw_warp<2>, (unsigned)blocks, 256, 0, m->indptr, m->indices, m->values, m->ncols, d_basis, K, d_out); break;
+        case 3: LG_LAUNCH(ctx, k_project_raw_warp<3>, (unsigned)blocks, 256, 0, m->indptr, m->indices, m->values, m->ncols, d_basis, K, d_out); break;
+        case 4: LG_LAUNCH(ctx, k_project_raw_warp<4>, (unsigned)blocks, 256, 0, m->indptr, m->indices, m->values, m->ncols, d_basis, K, d_out); break;
+        default: return lg_fail(ctx, LG_ERR_INVALID, "lg_project: K must be in [1, 128]");
+    }
+    return LG_OK;
+}
+
+extern "C" int lg_project_raw(lg_ctx* ctx, const lg_csc* m, const float* basis_kd, int K, float* out_proj) {
+    if (!ctx) return LG_ERR_INVALID;
+    LG_REQUIRE(ctx, m && basis_kd && out_proj, "lg_project_raw: null argument");
+    LG_REQUIRE(ctx, K >= 1 && K <= 128, "lg_project_raw: K must be in [1, 128]");
+    cudaSetDevice(ctx->device);
+    LgStage st(ctx);
+    const float* d_basis;
+    float* d_out;
+    LG_TRY(st.in(basis_kd, (size_t)K * m->nrows, &d_basis));
+    LG_TRY(st.out(out_proj, (size_t)K * m->ncols, &d_out));
+    LG_TRY(launch_project_raw(ctx, m, d_basis, K, d_out));
+    return st.finish();
+}
+
+// ---------------------------------------------------------------------------------------------
+// K2a: per-1024-cell-block f64 partial sums of proj per (batch, dim) + cell counts.
+// One block = LG_BLOCK_CELLS threads = one cell each.  partials[blk][b*(K+1) + k].
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024) k_batch_partials(const float* __restrict__ proj, int K, uint64_t ncols,
+                                                         const uint32_t* __restrict__ batch, uint32_t nbatch,
+                                                         double* __restrict__ partials) {
+    __shared__ double red[32];
+    const uint64_t cell = (uint64_t)blockIdx.x * LG_BLOCK_CELLS + threadIdx.x;
+    const bool live = cell < ncols;
+    const uint32_t myb = live ? (batch ? batch[cell] : 0u) : 0xffffffffu;
+    const float* row = proj + (size_t)cell * K;
+    double* outp = partials + (size_t)blockIdx.x * nbatch * (K + 1);
+    for (uint32_t b = 0; b < nbatch; ++b) {
+        const bool mine = live && myb == b;
+        for (int k = 0; k <= K; ++k) {
+            double v = 0.0;
+            if (mine) v = (k < K) ? (double)row[k] : 1.0;
+            const double s = lg_block_sum_1024(v, red);
+            if (threadIdx.x == 0) outp[(size_t)b * (K + 1) + k] = s;
+        }
+    }
+}
+
+extern "C" int lg_proj_batch_partials(lg_ctx* ctx, const float* d_proj, int K, uint64_t ncols, const uint32_t* d_batch,
+                                      uint32_t nbatch, double* d_partials) {
+    if (!ctx) return LG_ERR_INVALID;
+    LG_REQUIRE(ctx, d_proj && d_partials && nbatch >= 1, "lg_proj_batch_partials: null argument");
+    cudaSetDevice(ctx->device);
+    const uint64_t nblk = (ncols + LG_BLOCK_CELLS - 1) / LG_BLOCK_CELLS;
+    if (nblk == 0) return LG_OK;
+    LG_LAUNCH(ctx, k_batch_partials, (unsigned)nblk, LG_BLOCK_CELLS, 0, d_proj, K, ncols, d_batch, nbatch, d_partials);
+    return LG_OK;
+}
+
+// sum block partials in block order: out[m] = ((p[0][m] + p[1][m]) + p[2][m]) + ...
+__global__ void k_partials_finalize(const double* __restrict__ partials, uint64_t nblocks, uint32_t M,
+                                    double* __restrict__ out) {
+    const uint32_t m = blockIdx.x * blockDim.x + threadIdx.x;
+    if (m >= M) return;
+    double s = 0.0;
+    for (uint64_t b = 0; b < nblocks; ++b) s = s + partials[b * M + m];
+    out[m] = s;
+}
+
+extern "C" int lg_block_partials_finalize(lg_ctx* ctx, const double* d_partials, uint64_t nblocks, uint32_t M,
+                                          double* d_out) {
+    if (!ctx) return LG_ERR_INVALID;
+    LG_REQUIRE(ctx, d_partials && d_out && M >= 1, "lg_block_partials_finalize: null argument");
+    cudaSetDevice(ctx->device);
+    LG_LAUNCH(ctx, k_partials_finalize, (M + 127) / 128, 128, 0, d_partials, nblocks, M, d_out);
+    return LG_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// K2b/K2c: per-cell standardise (nalgebra scale_columns_inplace, dmatrix_util.rs:986-995) done by
+// one thread per cell in the reference's own sequential order, on a smem tile so global traffic
+// stays coalesced.  MODE 0: subtract batch mean first, track (min,max).  MODE 1: clamp first.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void atomic_max_f32(float* addr, float v) {
+    if (v >= 0.0f) atomicMax(reinterpret_cast<int*>(addr), __float_as_int(v));
+    else atomicMin(reinterpret_cast<unsigned int*>(addr), __float_as_uint(v));
+}
+__device__ __forceinline__ void atomic_min_f32(float* addr, float v) {
+    if (v >= 0.0f) atomicMin(reinterpret_cast<int*>(addr), __float_as_int(v));
+    else atomicMax(reinterpret_cast<unsigned int*>(addr), __float_as_uint(v));
+}
+
+constexpr int SCALE_CELLS = 128;
+
+template <int MODE>
+__global__ void __launch_bounds__(SCALE_CELLS) k_scale_cells(float* __restrict__ proj, int K, uint64_t ncols,
+                                                             const uint32_t* __restrict__ batch, uint32_t nbatch,
+                                                             const double* __restrict__ batch_sums,
+                                                             float* __restrict__ minmax) {
+    extern __shared__ float tile[];  // SCALE_CELLS rows of stride KS (odd -> conflict-free row walks)
+    const int KS = K | 1;
+    float* neg_mean = tile + SCALE_CELLS * KS;  // nbatch * K
+    const uint64_t cell0 = (uint64_t)blockIdx.x * SCALE_CELLS;
+    const int ncell = (ncols - cell0) < (uint64_t)SCALE_CELLS ? (int)(ncols - cell0) : SCALE_CELLS;
+    const size_t total = (size_t)ncell * K;
+    const float* src = proj + cell0 * K;
+    for (size_t e = threadIdx.x; e < total; e += SCALE_CELLS) tile[(e / K) * KS + (e % K)] = src[e];
+    if (MODE == 0 && batch_sums) {
+        for (uint32_t e = threadIdx.x; e < nbatch * (uint32_t)K; e += SCALE_CELLS) {
+            const uint32_t b = e / K, k = e % K;
+            const double cnt = batch_sums[(size_t)b * (K + 1) + K];
+            neg_mean[e] = cnt > 0.0 ? -(float)(batch_sums[(size_t)b * (K + 1) + k] / cnt) : 0.0f;
+        }
+    }
+    __syncthreads();
+    float lmin = INFINITY, lmax = -INFINITY;
+    if ((int)threadIdx.x < ncell) {
+        float* x = tile + threadIdx.x * KS;
+        if (MODE == 0 && batch_sums) {
+            const float* nm = neg_mean + (size_t)(batch ? batch[cell0 + threadIdx.x] : 0u) * K;
+            for (int k = 0; k < K; ++k) x[k] = x[k] + nm[k];
+        }
+        if (MODE == 1)
+            for (int k = 0; k < K; ++k) x[k] = fminf(fmaxf(x[k], -4.0f), 4.0f);
+        const float nf = (float)K;
+        float s = 0.0f;
+        for (int k = 0; k < K; ++k) s = __fadd_rn(s, x[k]);
+        const float mu = __fdiv_rn(s, nf);
+        float v = 0.0f;
+        for (int k = 0; k < K; ++k) {
+            const float d = __fsub_rn(x[k], mu);
+            v = __fadd_rn(v, __fmul_rn(d, d));
+        }
+        v = __fdiv_rn(v, nf);
+        const float sig = __fsqrt_rn(v);
+        const float nmu = -mu;
+        for (int k = 0; k < K; ++k) {
+            float y = __fadd_rn(x[k], nmu);
+            if (sig > 0.0f) y = __fdiv_rn(y, sig);
+            x[k] = y;
+            lmin = fminf(lmin, y);
+            lmax = fmaxf(lmax, y);
+        }
+    }
+    __syncthreads();
+    float* dst = proj + cell0 * K;
+    for (size_t e = threadIdx.x; e < total; e += SCALE_CELLS) dst[e] = tile[(e / K) * KS + (e % K)];
+    if (MODE == 0 && minmax) {
+#pragma unroll
+        for (int off = 16; off >= 1; off >>= 1) {
+            lmin = fminf(lmin, __shfl_xor_sync(0xffffffffu, lmin, off));
+            lmax = fmaxf(lmax, __shfl_xor_sync(0xffffffffu, lmax, off));
+        }
+        if ((threadIdx.x & 31) == 0) {
+            if (lmin != INFINITY) atomic_min_f32(minmax, lmin);
+            if (lmax != -INFINITY) atomic_max_f32(minmax + 1, lmax);
+        }
+    }
+}
+
+__global__ void k_init_minmax(float* mm) {
+    mm[0] = INFINITY;
+    mm[1] = -INFINITY;
+}
+
+static size_t scale_smem(int K, uint32_t nbatch) {
+    return ((size_t)SCALE_CELLS * (K | 1) + (size_t)nbatch * K) * sizeof(float);
+}
+
+extern "C" int lg_proj_centre_scale(lg_ctx* ctx, float* d_proj, int K, uint64_t ncols, const uint32_t* d_batch,
+                                    uint32_t nbatch, const double* d_batch_sums, float* d_minmax) {
+    if (!ctx) return LG_ERR_INVALID;
+    LG_REQUIRE(ctx, d_proj && K >= 1 && K <= 128, "lg_proj_centre_scale: bad argument");
+    cudaSetDevice(ctx->device);
+    if (d_minmax) LG_LAUNCH(ctx, k_init_minmax, 1, 1, 0, d_minmax);
+    if (ncols == 0) return LG_OK;
+    if (!d_batch_sums) nbatch = 0;
+    const size_t smem = scale_smem(K, nbatch);
+    LG_REQUIRE(ctx, smem <= ctx->smem_optin, "lg_proj_centre_scale: nbatch*K too large for shared memory");
+    LG_CUDA(ctx, cudaFuncSetAttribute(k_scale_cells<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const uint64_t grid = (ncols + SCALE_CELLS - 1) / SCALE_CELLS;
+    LG_LAUNCH(ctx, k_scale_cells<0>, (unsigned)grid, SCALE_CELLS, smem, d_proj, K, ncols, d_batch, nbatch,
+              d_batch_sums, d_minmax);
+    return LG_OK;
+}
+
+extern "C" int lg_proj_clamp_rescale(lg_ctx* ctx, float* d_proj, int K, uint64_t ncols) {
+    if (!ctx) return LG_ERR_INVALID;
+    LG_REQUIRE(ctx, d_proj && K >= 1 && K <= 128, "lg_proj_clamp_rescale: bad argument");
+    cudaSetDevice(ctx->device);
+    if (ncols == 0) return LG_OK;
+    const size_t smem = scale_smem(K, 0);
+    LG_CUDA(ctx, cudaFuncSetAttribute(k_scale_cells<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const uint64_t grid = (ncols + SCALE_CELLS - 1) / SCALE_CELLS;
+    LG_LAUNCH(ctx, k_scale_cells<1>, (unsigned)grid, SCALE_CELLS, smem, d_proj, K, ncols, (const uint32_t*)nullptr, 0u,
+              (const double*)nullptr, (float*)nullptr);
+    return LG_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// composite: project_columns_with_batch_correction_seeded (random_projection.rs:341-415)
+// ---------------------------------------------------------------------------------------------
+extern "C" int lg_project(lg_ctx* ctx, const lg_csc* m, const float* basis_kd, int K, const uint32_t* batch_of_cell,
+                          uint32_t nbatch, float* out_proj) {
+    if (!ctx) return LG_ERR_INVALID;
+    LG_REQUIRE(ctx, m && basis_kd && out_proj, "lg_project: null argument");
+    LG_REQUIRE(ctx, K >= 1 && K <= 128, "lg_project: K must be in [1, 128]");
+    LG_REQUIRE(ctx, !batch_of_cell || nbatch >= 1, "lg_project: nbatch must be >= 1 with batch labels");
+    cudaSetDevice(ctx->device);
+    LgStage st(ctx);
+    const float* d_basis;
+    const uint32_t* d_batch;
+    float* d_out;
+    LG_TRY(st.in(basis_kd, (size_t)K * m->nrows, &d_basis));
+    LG_TRY(st.in(batch_of_cell, (size_t)m->ncols, &d_batch));
+    LG_TRY(st.out(out_proj, (size_t)K * m->ncols, &d_out));
+    LG_TRY(launch_project_raw(ctx, m, d_basis, K, d_out));
+    const uint64_t nblk = (m->ncols + LG_BLOCK_CELLS - 1) / LG_BLOCK_CELLS;
+    double* d_sums = nullptr;
+    if (d_batch && nblk) {
+        const uint32_t M = nbatch * (K + 1);
+        double* d_part;
+        LG_TRY(st.scratch((size_t)nblk * M, &d_part));
+        LG_TRY(st.scratch((size_t)M, &d_sums));
+        LG_TRY(lg_proj_batch_partials(ctx, d_out, K, m->ncols, d_batch, nbatch, d_part));
+        LG_TRY(lg_block_partials_finalize(ctx, d_part, nblk, M, d_sums));
+    }
+    float* d_mm;
+    LG_TRY(st.scratch(2, &d_mm));
+    LG_TRY(lg_proj_centre_scale(ctx, d_out, K, m->ncols, d_batch, nbatch, d_sums, d_mm));
+    // the clamp branch is a global decision (:401): read back (min, max)
+    float* h_mm = static_cast<float*>(ctx->pinned);
+    LG_CUDA(ctx, cudaMemcpyAsync(h_mm, d_mm, 2 * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+    LG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (m->ncols && (h_mm[1] > 4.0f || h_mm[0] < -4.0f)) LG_TRY(lg_proj_clamp_rescale(ctx, d_out, K, m->ncols));
+    return st.finish();
+}

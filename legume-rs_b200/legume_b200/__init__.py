@@ -1,0 +1,600 @@
+"""legume_b200 — host-side mirror of the legume-rs hot-path API over liblegume_b200.so.
+
+The reference's host code is Rust (no toolchain in this image), so this module mirrors the
+reference's operator interface for the path — same names, argument meaning and error behaviour —
+in Python over the C ABI, so that the parity tests read like the reference's own tests:
+
+    RandProjOps            data-beans-alg/src/random_projection.rs:43-162
+    binary_sort_columns    data-beans-alg/src/random_projection.rs:535
+    SparseIoVec.assign_groups / register_batch_membership / register_column_multiplicity
+                           data-beans/src/sparse_io_vector/{groups.rs:13-37, batch.rs:259-336}
+    CollapsingOps          data-beans-alg/src/collapse_data/mod.rs:315-361
+    CollapsedStat/optimize data-beans-alg/src/collapse_data/stats.rs:378-582
+    GammaMatrix            matrix-param/src/dmatrix_gamma.rs, traits.rs
+    ColumnDict             matrix-util/src/knn/mod.rs:62-299
+
+Matrix convention: a nalgebra `DMatrix` of shape R x C (column-major) is represented by an array of
+shape (C, R) in C order, so `proj[j]` is cell j's K-vector and `sum_ds[s]` is group s's gene vector.
+Arrays may be numpy (host) or torch CUDA tensors (device, used in place, no copies).
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from ._lib import (BLOCK_CELLS, EXPORTED, LIB_PATH, TARGET_ALL, TARGET_MEAN_AND_LOG_MEAN, TARGET_MEAN_ONLY,
+                   LegumeError, lib)
+
+DEFAULT_PROJECTION_SEED = 0x50524F4A_50524F4A  # random_projection.rs:41
+DEFAULT_KNN = 10                                # collapse_data/mod.rs:27
+DEFAULT_OPT_ITER = 100                          # collapse_data/mod.rs:28
+
+__all__ = ["Context", "CscBlock", "SparseIoVec", "binary_sort_columns", "GammaMatrix", "CollapsedStat",
+           "CollapsedOut", "optimize", "ColumnDict", "LegumeError", "CalibrateTarget", "compute_level_sort_dims",
+           "pad_numeric_labels", "merge_stat"]
+
+
+class CalibrateTarget:
+    All = TARGET_ALL
+    MeanOnly = TARGET_MEAN_ONLY
+    MeanAndLogMean = TARGET_MEAN_AND_LOG_MEAN
+
+
+def _is_torch(x):
+    return type(x).__module__.startswith("torch")
+
+
+def _ptr(x):
+    if x is None:
+        return None
+    if isinstance(x, int):
+        return x
+    if _is_torch(x):
+        assert x.is_contiguous(), "device tensors must be contiguous"
+        return x.data_ptr()
+    assert x.flags["C_CONTIGUOUS"], "host arrays must be C-contiguous"
+    return x.ctypes.data
+
+
+def _as(x, dtype):
+    """host arrays are converted/copied to the ABI dtype; device tensors must already match"""
+    if x is None:
+        return None
+    if _is_torch(x):
+        import torch
+        want = {np.float32: torch.float32, np.uint32: torch.int32, np.uint64: torch.int64, np.float64: torch.float64,
+                np.uint8: torch.uint8}[dtype]
+        ok = {x.dtype} & {want, getattr(torch, "uint32", want), getattr(torch, "uint64", want)}
+        assert ok or x.element_size() == np.dtype(dtype).itemsize, f"device tensor dtype {x.dtype} != {dtype}"
+        return x.contiguous()
+    return np.ascontiguousarray(x, dtype)
+
+
+class Context:
+    """One per device (lg_ctx).  Fails loudly without a CUDA device: there is no CPU path."""
+
+    def __init__(self, device: int = 0):
+        h = C.c_void_p()
+        rc = lib.lg_ctx_create(device, C.byref(h))
+        if rc != 0:
+            raise LegumeError(rc, f"lg_ctx_create(device={device}) failed: no usable CUDA device (no CPU fallback)")
+        self.h = h
+        self.device = device
+
+    def check(self, rc):
+        if rc != 0:
+            raise LegumeError(rc, lib.lg_last_error(self.h).decode())
+
+    def sync(self):
+        self.check(lib.lg_ctx_sync(self.h))
+
+    def set_stream(self, stream_ptr):
+        self.check(lib.lg_ctx_set_stream(self.h, stream_ptr))
+
+    def use_torch_stream(self):
+        import torch
+        self.set_stream(torch.cuda.current_stream(self.device).cuda_stream)
+
+    @property
+    def launch_count(self) -> int:
+        return int(lib.lg_ctx_launch_count(self.h))
+
+    def empty(self, shape, dtype, device: bool):
+        """allocate an output next to the inputs (torch CUDA tensor or numpy array)"""
+        if device:
+            import torch
+            tdt = {np.float32: torch.float32, np.uint32: torch.int32, np.uint64: torch.int64,
+                   np.float64: torch.float64}[dtype]
+            return torch.empty(shape, dtype=tdt, device=f"cuda:{self.device}")
+        return np.empty(shape, dtype)
+
+    def close(self):
+        if self.h:
+            lib.lg_ctx_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class CscBlock:
+    """Device-resident CSC block (lg_csc): the data feed of the path (SparseIo::csc_column_arrays)."""
+
+    def __init__(self, ctx: Context, handle, keepalive=None):
+        self.ctx, self.h, self._keep = ctx, handle, keepalive
+        a, b, c = C.c_uint64(), C.c_uint64(), C.c_uint64()
+        lib.lg_csc_shape(self.h, C.byref(a), C.byref(b), C.byref(c))
+        self.nrows, self.ncols, self.nnz = a.value, b.value, c.value
+
+    @classmethod
+    def upload(cls, ctx, indptr, indices, data, nrows, col_lo=0, col_hi=None, row_remap=None):
+        indptr = np.ascontiguousarray(indptr, np.uint64)
+        indices = np.ascontiguousarray(indices, np.uint64)
+        data = np.ascontiguousarray(data, np.float32)
+        if col_hi is None:
+            col_hi = len(indptr) - 1
+        rr = None if row_remap is None else np.ascontiguousarray(row_remap, np.uint32)
+        h = C.c_void_p()
+        ctx.check(lib.lg_csc_upload(ctx.h, _ptr(indptr), _ptr(indices), _ptr(data), nrows, col_lo, col_hi, _ptr(rr),
+                                    C.byref(h)))
+        return cls(ctx, h)
+
+    @classmethod
+    def wrap_device(cls, ctx, d_indptr, d_indices, d_values, nrows):
+        """torch CUDA tensors: int64 indptr (ncols+1), int32 indices, float32 values; kept alive by the block"""
+        h = C.c_void_p()
+        ncols, nnz = d_indptr.numel() - 1, d_values.numel()
+        ctx.check(lib.lg_csc_wrap_device(ctx.h, _ptr(d_indptr), _ptr(d_indices), _ptr(d_values), nrows, ncols, nnz,
+                                         C.byref(h)))
+        return cls(ctx, h, keepalive=(d_indptr, d_indices, d_values))
+
+    def download(self):
+        indptr = np.empty(self.ncols + 1, np.uint64)
+        indices = np.empty(self.nnz, np.uint64)
+        data = np.empty(self.nnz, np.float32)
+        self.ctx.check(lib.lg_csc_download(self.ctx.h, self.h, _ptr(indptr), _ptr(indices), _ptr(data)))
+        return indptr, indices, data
+
+    def free(self):
+        if self.h:
+            lib.lg_csc_free(self.ctx.h if self.ctx.h else None, self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+# --------------------------------------------------------------------------------------------------
+# label helpers (host side, exactly the reference's string-rank rules)
+# --------------------------------------------------------------------------------------------------
+def _rank_labels(labels):
+    """index = rank of label.to_string() in byte-wise order (batch.rs:274-275, groups.rs:20-24)"""
+    strs = [str(int(x)) if isinstance(x, (np.integer, int)) else str(x) for x in labels]
+    keys = sorted(set(strs), key=lambda s: s.encode())
+    lut = {k: i for i, k in enumerate(keys)}
+    return np.fromiter((lut[s] for s in strs), np.uint32, len(strs)), keys
+
+
+def pad_numeric_labels(cell_to_group, k):
+    """collapse_data/refine.rs:21-35"""
+    width, n = 1, max(k, 1) - 1
+    while n >= 10:
+        width += 1
+        n //= 10
+    return [f"{int(g):0{width}d}" for g in cell_to_group]
+
+
+def compute_level_sort_dims(finest_sort_dim, num_levels):
+    """collapse_data/refine.rs:718-734 (f32 arithmetic, round half away from zero)"""
+    if num_levels <= 1:
+        return [finest_sort_dim]
+    coarsest = min(7, finest_sort_dim)
+    dims = []
+    for level in range(num_levels):
+        t = np.float32(level) / np.float32(num_levels - 1)
+        dim = np.float32(finest_sort_dim) - t * np.float32(finest_sort_dim - coarsest)
+        d = int(np.floor(abs(float(dim)) + 0.5) * (1 if dim >= 0 else -1))
+        if not dims or dims[-1] != d:
+            dims.append(d)
+    return dims
+
+
+# --------------------------------------------------------------------------------------------------
+# stage 2/3 free functions
+# --------------------------------------------------------------------------------------------------
+def binary_sort_columns(ctx: Context, proj_kn, kk: int):
+    """random_projection.rs:535-564: proj_kn (N, K) -> codes uint64[N] (< 2^kk)"""
+    proj_kn = _as(proj_kn, np.float32)
+    n, K = proj_kn.shape
+    dev = _is_torch(proj_kn)
+    codes = ctx.empty((n,), np.uint64, dev)
+    ctx.check(lib.lg_binary_codes(ctx.h, _ptr(proj_kn), K, n, kk, _ptr(codes)))
+    return codes
+
+
+def assign_groups_from_codes(ctx: Context, codes, kk: int, padded: bool = False):
+    """groups.rs:13-37 on integer codes: returns (group_of_cell uint32[N], num_groups)"""
+    codes = _as(codes, np.uint64)
+    dev = _is_torch(codes)
+    n = codes.shape[0]
+    group = ctx.empty((n,), np.uint32, dev)
+    ng = C.c_uint32()
+    ctx.check(lib.lg_assign_groups(ctx.h, _ptr(codes), n, kk, int(padded), _ptr(group), C.byref(ng)))
+    return group, ng.value
+
+
+def merge_stat(ctx: Context, fine_ds, fine_to_coarse, ncoarse):
+    """stats.rs:790-833 for one D x S plane"""
+    fine_ds = _as(fine_ds, np.float32)
+    nfine, D = fine_ds.shape
+    f2c = _as(fine_to_coarse, np.uint32)
+    out = ctx.empty((ncoarse, D), np.float32, _is_torch(fine_ds))
+    ctx.check(lib.lg_merge_stat(ctx.h, _ptr(fine_ds), D, nfine, _ptr(f2c), ncoarse, _ptr(out)))
+    return out
+
+
+# --------------------------------------------------------------------------------------------------
+# GammaMatrix (matrix-param/src/dmatrix_gamma.rs) — TwoStatParam + Inference
+# --------------------------------------------------------------------------------------------------
+class GammaMatrix:
+    def __init__(self, ctx: Context, dims, a0: float, b0: float):
+        self.ctx = ctx
+        self.num_rows, self.num_columns = dims
+        self.a0, self.b0 = float(a0), float(b0)
+        self.a_stat = np.full((self.num_columns, self.num_rows), a0, np.float32)
+        self.b_stat = np.full((self.num_columns, self.num_rows), b0, np.float32)
+        self.estimated_mean = np.zeros((self.num_columns, self.num_rows), np.float32)  # eager, zero start (:49-52)
+        self.estimated_sd = self.estimated_log_mean = self.estimated_log_sd = None
+
+    @classmethod
+    def new(cls, ctx, dims, a0, b0):
+        return cls(ctx, dims, a0, b0)
+
+    def update_stat(self, update_a, update_b):
+        self.reset_stat()
+        self.add_stat(update_a, update_b)
+
+    def add_stat(self, add_a, add_b):
+        self.a_stat = self.a_stat + np.asarray(add_a, np.float32)
+        self.b_stat = self.b_stat + np.asarray(add_b, np.float32)
+
+    def reset_stat(self):
+        self.a_stat = np.full_like(self.a_stat, self.a0)
+        self.b_stat = np.full_like(self.b_stat, self.b0)
+
+    def calibrate(self):
+        self.calibrate_with(CalibrateTarget.All)
+
+    def calibrate_with(self, target):
+        n = self.a_stat.size
+        mean = np.empty_like(self.a_stat)
+        sd = np.empty_like(self.a_stat) if target == TARGET_ALL else None
+        lm = np.empty_like(self.a_stat) if target != TARGET_MEAN_ONLY else None
+        ls = np.empty_like(self.a_stat) if target == TARGET_ALL else None
+        # a_stat/b_stat already carry the hyper-parameters (fill + add, dmatrix_gamma.rs:64-75)
+        a = np.ascontiguousarray(self.a_stat)
+        b = np.ascontiguousarray(self.b_stat)
+        self.ctx.check(lib.lg_gamma_calibrate(self.ctx.h, _ptr(a), _ptr(b), n, 0.0, 0.0, target,
+                                              _ptr(mean), _ptr(sd), _ptr(lm), _ptr(ls)))
+        self.estimated_mean = mean
+        if sd is not None:
+            self.estimated_sd = sd
+        if lm is not None:
+            self.estimated_log_mean = lm
+        if ls is not None:
+            self.estimated_log_sd = ls
+
+    def posterior_mean(self):
+        return self.estimated_mean
+
+    def posterior_sd(self):
+        return self.estimated_sd
+
+    def posterior_log_mean(self):
+        return self.estimated_log_mean
+
+    def posterior_log_sd(self):
+        return self.estimated_log_sd
+
+    def nrows(self):
+        return self.num_rows
+
+    def ncols(self):
+        return self.num_columns
+
+
+# --------------------------------------------------------------------------------------------------
+# CollapsedStat / optimize (collapse_data/stats.rs)
+# --------------------------------------------------------------------------------------------------
+class CollapsedStat:
+    """stats.rs:546-582: sufficient statistics, all (S, D) / (B, D) / (S, B) in this module's layout"""
+
+    def __init__(self, ngene, nsample, nbatch):
+        z = lambda *s: np.zeros(s, np.float32)
+        self.observed_sum_ds, self.imputed_sum_ds, self.residual_sum_ds = z(nsample, ngene), z(nsample, ngene), z(nsample, ngene)
+        self.size_s = z(nsample)
+        self.observed_sum_db = z(nbatch, ngene)
+        self.n_bs = z(nsample, nbatch)
+
+    def num_genes(self):
+        return self.observed_sum_ds.shape[1]
+
+    def num_samples(self):
+        return self.observed_sum_ds.shape[0]
+
+    def num_batches(self):
+        return self.observed_sum_db.shape[0]
+
+    def select_rows(self, r0, nrows):
+        out = CollapsedStat(nrows, self.num_samples(), self.num_batches())
+        sl = slice(r0, r0 + nrows)
+        out.observed_sum_ds = np.ascontiguousarray(self.observed_sum_ds[:, sl])
+        out.imputed_sum_ds = np.ascontiguousarray(self.imputed_sum_ds[:, sl])
+        out.residual_sum_ds = np.ascontiguousarray(self.residual_sum_ds[:, sl])
+        out.observed_sum_db = np.ascontiguousarray(self.observed_sum_db[:, sl])
+        out.size_s, out.n_bs = self.size_s.copy(), self.n_bs.copy()
+        return out
+
+
+class CollapsedOut(dict):
+    """stats.rs:516-522: mu_observed, mu_adjusted, mu_residual, gamma, delta (dicts of posterior planes)"""
+
+    def __getattr__(self, k):
+        return self[k]
+
+
+def optimize(ctx: Context, stat: CollapsedStat, hyper=(1.0, 1.0), num_iter=DEFAULT_OPT_ITER, out_target=TARGET_ALL):
+    """stats.rs:378-512.  Gene blocking is numerically inert (:370-377), so the fit runs in one launch."""
+    a0, b0 = hyper
+    S, D = stat.observed_sum_ds.shape
+    B = stat.num_batches()
+    dev = _is_torch(stat.observed_sum_ds)
+    new = lambda shape=(S, D): ctx.empty(shape, np.float32, dev)
+    if B <= 1:
+        mean, sd, lm, ls = new(), None, None, None
+        if out_target == TARGET_ALL:
+            sd, ls = new(), new()
+        if out_target != TARGET_MEAN_ONLY:
+            lm = new()
+        ctx.check(lib.lg_optimize_single(ctx.h, _ptr(stat.observed_sum_ds), _ptr(stat.size_s), D, S, a0, b0, out_target,
+                                         _ptr(mean), _ptr(sd), _ptr(lm), _ptr(ls)))
+        return CollapsedOut(mu_observed=dict(mean=mean, sd=sd, log_mean=lm, log_sd=ls), mu_adjusted=None,
+                            mu_residual=None, gamma=None, delta=None)
+    mu_obs, mu_adj, mu_res, gam, delta = new(), new(), new(), new(), new((B, D))
+    lm = new() if out_target != TARGET_MEAN_ONLY else None
+    ctx.check(lib.lg_optimize_batched(ctx.h, _ptr(stat.observed_sum_ds), _ptr(stat.imputed_sum_ds),
+                                      _ptr(stat.residual_sum_ds), _ptr(stat.size_s), _ptr(stat.observed_sum_db),
+                                      _ptr(stat.n_bs), D, S, B, a0, b0, num_iter, out_target, _ptr(mu_obs), _ptr(mu_adj),
+                                      _ptr(mu_res), _ptr(gam), _ptr(delta), _ptr(lm)))
+    return CollapsedOut(mu_observed=dict(mean=mu_obs), mu_adjusted=dict(mean=mu_adj, log_mean=lm),
+                        mu_residual=dict(mean=mu_res), gamma=dict(mean=gam), delta=dict(mean=delta))
+
+
+# --------------------------------------------------------------------------------------------------
+# SparseIoVec: the data handle the reference's traits are implemented on
+# --------------------------------------------------------------------------------------------------
+class SparseIoVec:
+    """One preloaded backend's columns on the device, with the derived caches of
+    data-beans/src/sparse_io_vector/mod.rs:70-85 (groups, batches, multiplicity)."""
+
+    def __init__(self, ctx: Context, block: CscBlock):
+        self.ctx, self.block = ctx, block
+        self.col_to_group = None      # uint32[N]
+        self.group_keys = None
+        self.col_to_batch = None      # uint32[N]
+        self.batch_names = None
+        self.multiplicity = None      # float32[N] or None
+
+    @classmethod
+    def from_csc(cls, ctx, indptr, indices, data, nrows):
+        return cls(ctx, CscBlock.upload(ctx, indptr, indices, data, nrows))
+
+    def num_rows(self):
+        return self.block.nrows
+
+    def num_columns(self):
+        return self.block.ncols
+
+    # ---- batch.rs:259-336 ----
+    def register_batch_membership(self, labels):
+        if len(labels) != self.num_columns():
+            raise LegumeError(1, "batch membership length mismatches the number of columns")
+        self.col_to_batch, self.batch_names = _rank_labels(labels)
+
+    def num_batches(self):
+        return 0 if self.batch_names is None else len(self.batch_names)
+
+    def register_column_multiplicity(self, weights):
+        w = np.ascontiguousarray(weights, np.float32)
+        if len(w) != self.num_columns():
+            raise LegumeError(1, "column multiplicity length mismatches the number of columns")
+        if not np.all(w > 0):
+            raise LegumeError(1, "column multiplicity must be strictly positive")
+        self.multiplicity = w
+
+    # ---- groups.rs:13-37 ----
+    def assign_groups(self, column_to_group, ncolumns_per_group=None):
+        if ncolumns_per_group is not None:
+            raise LegumeError(1, "ncolumns_per_group down-sampling is outside the hot path (utils.rs:48-62)")
+        if len(column_to_group) != self.num_columns():
+            raise LegumeError(1, "group membership length mismatches the number of columns")
+        self.col_to_group, self.group_keys = _rank_labels(column_to_group)
+
+    def num_groups(self):
+        return 0 if self.group_keys is None else len(self.group_keys)
+
+    def get_group_membership(self):
+        if self.col_to_group is None:
+            raise LegumeError(1, "groups were not assigned")
+        return self.col_to_group
+
+    # ---- RandProjOps (random_projection.rs:341-527) ----
+    def _basis(self, target_dim, seed, basis):
+        if basis is None:
+            # NOTE: the reference draws the basis from rand 0.10 StdRng + rand_distr ziggurat
+            # (rand_util.rs:54-76); that stream is not reproducible here, so parity runs pass `basis`.
+            basis = np.random.default_rng(seed & 0xFFFFFFFF).standard_normal((self.num_rows(), target_dim)).astype(np.float32)
+        basis = _as(basis, np.float32)
+        if tuple(basis.shape) != (self.num_rows(), target_dim):
+            raise LegumeError(1, f"basis must be K x D given as shape (D, K) = ({self.num_rows()}, {target_dim})")
+        return basis
+
+    def project_columns(self, target_dim, block_size=None, basis=None):
+        return self.project_columns_with_batch_correction(target_dim, block_size, None, basis=basis)
+
+    def project_columns_with_batch_correction(self, target_dim, block_size=None, batch_membership=None, basis=None,
+                                              seed=DEFAULT_PROJECTION_SEED):
+        """returns (basis_kd as (D, K), proj as (N, K)); block_size is accepted and ignored (the GPU streams
+        whole column ranges)."""
+        basis = self._basis(target_dim, seed, basis)
+        n = self.num_columns()
+        batch, nb = None, 0
+        if batch_membership is not None:
+            if len(batch_membership) == n:
+                batch, names = _rank_labels(batch_membership)
+                nb = len(names)
+            # else: the reference warns and skips the centring (:389-395)
+        dev = _is_torch(basis)
+        proj = self.ctx.empty((n, target_dim), np.float32, dev)
+        if dev and batch is not None:
+            import torch
+            batch = torch.from_numpy(batch.astype(np.int32)).to(basis.device)
+        self.ctx.check(lib.lg_project(self.ctx.h, self.block.h, _ptr(basis), target_dim, _ptr(batch), nb, _ptr(proj)))
+        return basis, proj
+
+    def project_columns_weighted(self, target_dim, block_size, batch_membership, row_weights, basis=None,
+                                 seed=DEFAULT_PROJECTION_SEED):
+        """random_projection.rs:417-495: rows with w <= 0 are zeroed, |w - 1| > 1e-6 scaled"""
+        row_weights = np.asarray(row_weights, np.float32)
+        if len(row_weights) != self.num_rows():
+            raise LegumeError(1, "row_weights length mismatch")
+        basis = np.array(self._basis(target_dim, seed, basis), np.float32, copy=True)
+        for r, w in enumerate(row_weights):
+            if w <= 0.0:
+                basis[r, :] = 0.0
+            elif abs(w - 1.0) > 1e-6:
+                basis[r, :] *= w
+        return self.project_columns_with_batch_correction(target_dim, block_size, batch_membership, basis=basis)
+
+    def partition_columns_to_groups(self, proj_kn, num_features=None, ncols_per_group=None):
+        """random_projection.rs:506-527: returns max code + 1 and assigns groups"""
+        n, K = proj_kn.shape
+        if n != self.num_columns():
+            raise LegumeError(1, "number of columns mismatch")
+        kk = min(K, num_features if num_features is not None else K, n)
+        codes = binary_sort_columns(self.ctx, proj_kn, kk)
+        codes_h = codes.cpu().numpy().astype(np.uint64) if _is_torch(codes) else codes
+        self.binary_codes = codes_h
+        group, ng = assign_groups_from_codes(self.ctx, codes_h, kk)
+        self.col_to_group = group
+        self.group_keys = sorted({str(int(c)) for c in np.unique(codes_h)}, key=lambda s: s.encode())
+        return int(codes_h.max()) + 1
+
+    # ---- CollapsingOps (collapse_data/mod.rs:315-483) ----
+    def collect_basic_stat(self, stat: CollapsedStat):
+        S = stat.num_samples()
+        self.ctx.check(lib.lg_collapse_basic(self.ctx.h, self.block.h, _ptr(self.get_group_membership()),
+                                             _ptr(self.multiplicity), S, _ptr(stat.observed_sum_ds), _ptr(stat.size_s)))
+
+    def collect_batch_stat(self, stat: CollapsedStat):
+        if self.col_to_batch is None:
+            raise LegumeError(1, "batches were not registered")
+        S, B = stat.num_samples(), stat.num_batches()
+        self.ctx.check(lib.lg_collapse_batch(self.ctx.h, self.block.h, _ptr(self.get_group_membership()),
+                                             _ptr(self.col_to_batch), _ptr(self.multiplicity), S, B,
+                                             _ptr(stat.observed_sum_db), _ptr(stat.n_bs)))
+
+    def collapse_columns(self, knn_batches=None, knn_cells=None, reference_batch_names=None, num_opt_iter=None,
+                         out_target=TARGET_ALL):
+        """collapse_data/mod.rs:384-475 for the single-batch arm; the matched-stat arm (B > 1) is staged
+        through ColumnDict + collect_matched_stat once registered batches carry kNN indices."""
+        if self.col_to_group is None:
+            raise LegumeError(1, "groups were not assigned")
+        nb = max(self.num_batches(), 1)
+        stat = CollapsedStat(self.num_rows(), self.num_groups(), nb)
+        self.collect_basic_stat(stat)
+        if nb > 1:
+            self.collect_batch_stat(stat)
+        return optimize(self.ctx, stat, (1.0, 1.0), num_opt_iter or DEFAULT_OPT_ITER, out_target), stat
+
+
+# --------------------------------------------------------------------------------------------------
+# ColumnDict (matrix-util/src/knn/mod.rs) with the exact backend
+# --------------------------------------------------------------------------------------------------
+class ColumnDict:
+    def __init__(self, ctx: Context, data, names):
+        """data: (n, d) array, one point per row here = one column of the reference's DMatrix"""
+        self.ctx = ctx
+        self.data = _as(data, np.float32)
+        self._names = list(names)
+        if len(self._names) != self.data.shape[0]:
+            raise LegumeError(1, "Data and names must have the same length")
+        self.name2index = {k: i for i, k in enumerate(self._names)}
+
+    @classmethod
+    def from_dmatrix(cls, ctx, data, names):
+        return cls(ctx, data, names)
+
+    def names(self):
+        return self._names
+
+    def dim(self):
+        return None if self.data.shape[0] == 0 else self.data.shape[1]
+
+    def num_points(self):
+        return self.data.shape[0]
+
+    def _index_of(self, name):
+        if name not in self.name2index:
+            raise LegumeError(1, f"name {name} not found")
+        return self.name2index[name]
+
+    def search_indices(self, queries, knn, exclude=None):
+        """batched core: queries (nq, d) -> (idx (nq, k'), dist (nq, k')) with k' = min(knn, available)"""
+        queries = _as(queries, np.float32)
+        nq = queries.shape[0]
+        nr = self.num_points()
+        dev = _is_torch(queries) or _is_torch(self.data)
+        if knn == 0 or nr == 0 or nq == 0:
+            return np.zeros((nq, 0), np.uint32), np.zeros((nq, 0), np.float32)
+        ex = None if exclude is None else _as(exclude, np.uint32)
+        idx = self.ctx.empty((nq, knn), np.uint32, dev)
+        dist = self.ctx.empty((nq, knn), np.float32, dev)
+        self.ctx.check(lib.lg_knn_topk(self.ctx.h, _ptr(self.data), nr, _ptr(queries), nq, self.data.shape[1], knn,
+                                       _ptr(ex), _ptr(idx), _ptr(dist)))
+        return idx, dist
+
+    def _trim(self, idx, dist):
+        keep = idx != np.uint32(0xFFFFFFFF)
+        return [int(i) for i in idx[keep]], [float(x) for x in dist[keep]]
+
+    def search_by_query_data(self, query, knn):
+        query = np.asarray(query, np.float32)
+        if (self.dim() or 0) != query.shape[0]:
+            raise LegumeError(1, "query's dim does not match")
+        idx, dist = self.search_indices(query[None, :], knn)
+        ii, dd = self._trim(np.asarray(idx)[0], np.asarray(dist)[0])
+        return [self._names[i] for i in ii], dd
+
+    def search_by_query_name(self, query_name, knn, exclude_same):
+        q = self._index_of(query_name)
+        ex = np.array([q], np.uint32) if exclude_same else None
+        idx, dist = self.search_indices(np.asarray(self.data)[q:q + 1], knn, ex)
+        ii, dd = self._trim(np.asarray(idx)[0], np.asarray(dist)[0])
+        return [self._names[i] for i in ii], dd
+
+    def search_others(self, query_name, knn):
+        return self.search_by_query_name(query_name, knn, True)
+
+    def match_by_query_name_against(self, query_name, knn, against: "ColumnDict"):
+        q = self._index_of(query_name)
+        idx, dist = against.search_indices(np.asarray(self.data)[q:q + 1], knn)
+        ii, dd = against._trim(np.asarray(idx)[0], np.asarray(dist)[0])
+        return [against._names[i] for i in ii], dd

@@ -1,0 +1,83 @@
+"""ctypes binding of liblegume_b200.so (include/legume_b200.h).
+
+There is no fallback: if the CUDA library has not been built, importing fails loudly, and
+creating a Context without a CUDA device raises.  Nothing here touches oracle/.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_PKG = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(os.path.dirname(_PKG), "liblegume_b200.so")
+
+LG_OK = 0
+TARGET_ALL, TARGET_MEAN_ONLY, TARGET_MEAN_AND_LOG_MEAN = 0, 1, 2
+BLOCK_CELLS = 1024
+
+
+class LegumeError(RuntimeError):
+    """Raised for any non-zero status from the C ABI (the reference returns anyhow::Error)."""
+
+    def __init__(self, code, msg):
+        super().__init__(f"legume_b200 error {code}: {msg}")
+        self.code = code
+
+
+if not os.path.exists(LIB_PATH):
+    raise ImportError(
+        f"{LIB_PATH} is missing: build it with `make -C legume-rs_b200/csrc` (or __graft_entry__.build()). "
+        "legume_b200 has no CPU fallback.")
+
+lib = C.CDLL(LIB_PATH)
+
+_vp, _u64, _u32, _i, _f = C.c_void_p, C.c_uint64, C.c_uint32, C.c_int, C.c_float
+_sig = {
+    "lg_ctx_create": [_i, C.POINTER(_vp)],
+    "lg_ctx_destroy": [_vp],
+    "lg_ctx_set_stream": [_vp, _vp],
+    "lg_ctx_sync": [_vp],
+    "lg_csc_upload": [_vp, _vp, _vp, _vp, _u64, _u64, _u64, _vp, C.POINTER(_vp)],
+    "lg_csc_wrap_device": [_vp, _vp, _vp, _vp, _u64, _u64, _u64, C.POINTER(_vp)],
+    "lg_csc_free": [_vp, _vp],
+    "lg_csc_shape": [_vp, C.POINTER(_u64), C.POINTER(_u64), C.POINTER(_u64)],
+    "lg_csc_device_arrays": [_vp, C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp)],
+    "lg_csc_download": [_vp, _vp, _vp, _vp, _vp],
+    "lg_project": [_vp, _vp, _vp, _i, _vp, _u32, _vp],
+    "lg_project_raw": [_vp, _vp, _vp, _i, _vp],
+    "lg_proj_batch_partials": [_vp, _vp, _i, _u64, _vp, _u32, _vp],
+    "lg_block_partials_finalize": [_vp, _vp, _u64, _u32, _vp],
+    "lg_proj_centre_scale": [_vp, _vp, _i, _u64, _vp, _u32, _vp, _vp],
+    "lg_proj_clamp_rescale": [_vp, _vp, _i, _u64],
+    "lg_binary_codes": [_vp, _vp, _i, _u64, _i, _vp],
+    "lg_codes_basis": [_vp, _vp, _i, _i, _i, _vp],
+    "lg_codes_gram": [_vp, _vp, _i, _u64, _vp, _i, _vp, _vp],
+    "lg_codes_factor": [_vp, _vp, _vp, _i, _i, _vp, _vp],
+    "lg_codes_vproj": [_vp, _vp, _i, _u64, _vp, _vp, _vp, _vp],
+    "lg_codes_pack": [_vp, _vp, _i, _u64, _vp, _vp],
+    "lg_assign_groups": [_vp, _vp, _u64, _i, _i, _vp, C.POINTER(_u32)],
+    "lg_code_presence": [_vp, _vp, _u64, _i, _vp],
+    "lg_group_lut": [_vp, _vp, _i, _i, _vp, C.POINTER(_u32)],
+    "lg_codes_to_groups": [_vp, _vp, _u64, _i, _vp, _vp],
+    "lg_collapse_basic": [_vp, _vp, _vp, _vp, _u32, _vp, _vp],
+    "lg_collapse_batch": [_vp, _vp, _vp, _vp, _vp, _u32, _u32, _vp, _vp],
+    "lg_merge_stat": [_vp, _vp, _u64, _u32, _vp, _u32, _vp],
+    "lg_gamma_calibrate": [_vp, _vp, _vp, _u64, _f, _f, _i, _vp, _vp, _vp, _vp],
+    "lg_optimize_single": [_vp, _vp, _vp, _u64, _u32, _f, _f, _i, _vp, _vp, _vp, _vp],
+    "lg_optimize_batched": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _u64, _u32, _u32, _f, _f, _i, _i, _vp, _vp, _vp, _vp,
+                            _vp, _vp],
+    "lg_knn_topk": [_vp, _vp, _u64, _vp, _u64, _i, _i, _vp, _vp, _vp],
+    "lg_sim_poisson_csc": [_vp, _u64, _u64, _u64, _u64, _vp, _vp, _u32, _u32, _vp, _vp, _vp, C.POINTER(_vp)],
+}
+for _name, _args in _sig.items():
+    _fn = getattr(lib, _name)
+    _fn.argtypes = _args
+    _fn.restype = C.c_int
+lib.lg_last_error.argtypes = [_vp]
+lib.lg_last_error.restype = C.c_char_p
+lib.lg_ctx_launch_count.argtypes = [_vp]
+lib.lg_ctx_launch_count.restype = C.c_uint64
+lib.lg_version.argtypes = []
+lib.lg_version.restype = C.c_char_p
+
+EXPORTED = sorted(list(_sig) + ["lg_last_error", "lg_ctx_launch_count", "lg_version"])

@@ -1,0 +1,202 @@
+"""Device-resident, cell-sharded driver of the hot path.
+
+One process per GPU; every rank owns a contiguous range of cells whose start is a multiple of
+BLOCK_CELLS.  All heavy data stays in torch CUDA tensors; the C ABI is called on torch's current
+stream.  Collectives (torch.distributed / NCCL) appear only where the reference reduces over cells:
+
+    after K1   all-gather of per-block (batch, dim) partial sums; all-reduce(min,max) of 2 floats
+    in K3      broadcast of the first r cells' K-vectors; all-gather of Gram / column-sum partials
+    in K4      all-reduce(max) of the 2^kk code-presence flags
+    after K5   all-reduce(sum) of the gene x group sums and group sizes
+
+Order-sensitive reductions are all-gathered block partials summed in global block order, so results
+are bit-identical for any GPU count.  With world size 1 the same code runs without collectives.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import BLOCK_CELLS, Context, CscBlock, LegumeError, _ptr
+from ._lib import TARGET_ALL, TARGET_MEAN_ONLY, lib
+
+
+def shard_range(ncols: int, rank: int, world: int):
+    """contiguous, BLOCK_CELLS-aligned cell range of `rank`"""
+    nblk = (ncols + BLOCK_CELLS - 1) // BLOCK_CELLS
+    per = (nblk + world - 1) // world
+    lo = min(rank * per * BLOCK_CELLS, ncols)
+    hi = min((rank + 1) * per * BLOCK_CELLS, ncols)
+    return lo, hi
+
+
+class HotPath:
+    def __init__(self, ctx: Context, group=None):
+        self.ctx = ctx
+        self.dev = torch.device(f"cuda:{ctx.device}")
+        self.pg = group
+        self.dist = torch.distributed if (group is not None or (torch.distributed.is_available()
+                                                                 and torch.distributed.is_initialized())) else None
+        self.world = self.dist.get_world_size(group) if self.dist else 1
+        self.rank = self.dist.get_rank(group) if self.dist else 0
+        ctx.use_torch_stream()
+
+    # ---- helpers ---------------------------------------------------------------------------------
+    def _nblk(self, n):
+        return (n + BLOCK_CELLS - 1) // BLOCK_CELLS
+
+    def _sum_partials(self, partials: torch.Tensor, nblk_local: int, M: int):
+        """partials (nblk_local, M) f64 -> (M,) f64 summed over ALL ranks' blocks in global block order"""
+        out = torch.empty(M, dtype=torch.float64, device=self.dev)
+        if self.world > 1:
+            cnt = torch.tensor([nblk_local], dtype=torch.int64, device=self.dev)
+            self.dist.all_reduce(cnt, op=self.dist.ReduceOp.MAX, group=self.pg)
+            mx = int(cnt.item())
+            padded = torch.zeros((mx, M), dtype=torch.float64, device=self.dev)  # +0.0 blocks are exact no-ops
+            padded[:nblk_local] = partials[:nblk_local]
+            allp = torch.empty((self.world * mx, M), dtype=torch.float64, device=self.dev)
+            self.dist.all_gather_into_tensor(allp, padded, group=self.pg)
+            self.ctx.check(lib.lg_block_partials_finalize(self.ctx.h, _ptr(allp), self.world * mx, M, _ptr(out)))
+        else:
+            self.ctx.check(lib.lg_block_partials_finalize(self.ctx.h, _ptr(partials), nblk_local, M, _ptr(out)))
+        return out
+
+    def _total(self, n_local: int) -> int:
+        if self.world == 1:
+            return n_local
+        t = torch.tensor([n_local], dtype=torch.int64, device=self.dev)
+        self.dist.all_reduce(t, group=self.pg)
+        return int(t.item())
+
+    # ---- stage 1 -----------------------------------------------------------------------------------
+    def project(self, block: CscBlock, basis_kd: torch.Tensor, batch: torch.Tensor | None, nbatch: int):
+        """random_projection.rs:341-415 on this rank's cells; basis_kd (D, K) f32, batch int32 (n_local,)"""
+        ctx, n = self.ctx, block.ncols
+        K = basis_kd.shape[1]
+        proj = torch.empty((n, K), dtype=torch.float32, device=self.dev)
+        ctx.check(lib.lg_project_raw(ctx.h, block.h, _ptr(basis_kd), K, _ptr(proj)))
+        sums = None
+        if batch is not None and nbatch >= 1:
+            M = nbatch * (K + 1)
+            nblk = self._nblk(n)
+            part = torch.empty((max(nblk, 1), M), dtype=torch.float64, device=self.dev)
+            ctx.check(lib.lg_proj_batch_partials(ctx.h, _ptr(proj), K, n, _ptr(batch), nbatch, _ptr(part)))
+            sums = self._sum_partials(part, nblk, M)
+        mm = torch.empty(2, dtype=torch.float32, device=self.dev)
+        ctx.check(lib.lg_proj_centre_scale(ctx.h, _ptr(proj), K, n, _ptr(batch) if sums is not None else None,
+                                           nbatch if sums is not None else 0, _ptr(sums), _ptr(mm)))
+        if self.world > 1:
+            lo, hi = mm[0:1].clone(), mm[1:2].clone()
+            self.dist.all_reduce(lo, op=self.dist.ReduceOp.MIN, group=self.pg)
+            self.dist.all_reduce(hi, op=self.dist.ReduceOp.MAX, group=self.pg)
+            mn, mx = float(lo.item()), float(hi.item())
+        else:
+            mn, mx = (float(x) for x in mm.tolist())
+        if mx > 4.0 or mn < -4.0:  # global decision, random_projection.rs:401
+            ctx.check(lib.lg_proj_clamp_rescale(ctx.h, _ptr(proj), K, n))
+        return proj
+
+    # ---- stage 2 -----------------------------------------------------------------------------------
+    def binary_codes(self, proj: torch.Tensor, kk: int):
+        """random_projection.rs:535-564 over all ranks' cells; returns int64 codes (n_local,)"""
+        ctx = self.ctx
+        n, K = proj.shape
+        ntot = self._total(n)
+        rank_all = min(K, ntot)
+        r = kk + 5 if rank_all > kk else rank_all
+        r = min(r, ntot)
+        first = torch.zeros((r, K), dtype=torch.float32, device=self.dev)
+        if self.rank == 0:
+            if n < r:
+                raise LegumeError(1, "rank 0 must hold at least kk+5 cells")
+            first.copy_(proj[:r])
+        if self.world > 1:
+            self.dist.broadcast(first, src=0, group=self.pg)
+        first_h = first.cpu().numpy()
+        q_h = np.empty((kk, K), np.float32)
+        ctx.check(lib.lg_codes_basis(ctx.h, _ptr(first_h), K, r, kk, _ptr(q_h)))
+        q = torch.from_numpy(q_h).to(self.dev)
+        nblk = self._nblk(n)
+        M = kk * (kk + 1) // 2
+        b = torch.empty((n, kk), dtype=torch.float32, device=self.dev)
+        part = torch.empty((max(nblk, 1), M), dtype=torch.float64, device=self.dev)
+        ctx.check(lib.lg_codes_gram(ctx.h, _ptr(proj), K, n, _ptr(q), kk, _ptr(b), _ptr(part)))
+        gram_h = self._sum_partials(part, nblk, M).cpu().numpy()
+        u_h, sig_h = np.empty((kk, kk), np.float32), np.empty(kk, np.float32)
+        ctx.check(lib.lg_codes_factor(ctx.h, _ptr(gram_h), _ptr(q_h), K, kk, _ptr(u_h), _ptr(sig_h)))
+        u, sig = torch.from_numpy(u_h).to(self.dev), torch.from_numpy(sig_h).to(self.dev)
+        v = torch.empty((n, kk), dtype=torch.float32, device=self.dev)
+        part2 = torch.empty((max(nblk, 1), kk), dtype=torch.float64, device=self.dev)
+        ctx.check(lib.lg_codes_vproj(ctx.h, _ptr(b), kk, n, _ptr(u), _ptr(sig), _ptr(v), _ptr(part2)))
+        sums_h = self._sum_partials(part2, nblk, kk).cpu().numpy()
+        mean = torch.from_numpy((sums_h / float(ntot)).astype(np.float32)).to(self.dev)
+        codes = torch.empty(n, dtype=torch.int64, device=self.dev)
+        ctx.check(lib.lg_codes_pack(ctx.h, _ptr(v), kk, n, _ptr(mean), _ptr(codes)))
+        return codes
+
+    # ---- stage 3 -----------------------------------------------------------------------------------
+    def assign_groups(self, codes: torch.Tensor, kk: int, padded: bool = False):
+        """groups.rs:13-37 over all ranks' codes; returns (int32 group ids (n_local,), num_groups)"""
+        ctx, n = self.ctx, codes.shape[0]
+        present = torch.empty(1 << kk, dtype=torch.int32, device=self.dev)
+        ctx.check(lib.lg_code_presence(ctx.h, _ptr(codes), n, kk, _ptr(present)))
+        if self.world > 1:
+            self.dist.all_reduce(present, op=self.dist.ReduceOp.MAX, group=self.pg)
+        present_h = present.cpu().numpy().astype(np.uint32)
+        lut_h = np.empty(1 << kk, np.uint32)
+        ng = C.c_uint32()
+        ctx.check(lib.lg_group_lut(ctx.h, _ptr(present_h), kk, int(padded), _ptr(lut_h), C.byref(ng)))
+        lut = torch.from_numpy(lut_h.astype(np.int64).astype(np.int32, casting="unsafe")).to(self.dev)
+        group = torch.empty(n, dtype=torch.int32, device=self.dev)
+        ctx.check(lib.lg_codes_to_groups(ctx.h, _ptr(codes), n, kk, _ptr(lut), _ptr(group)))
+        return group, int(ng.value)
+
+    # ---- stage 4 -----------------------------------------------------------------------------------
+    def collapse_basic(self, block: CscBlock, group: torch.Tensor, S: int, mult: torch.Tensor | None = None):
+        """stats.rs:110-134 + all-reduce of the sums; returns (sum_ds (S, D), size_s (S,))"""
+        ctx = self.ctx
+        sum_ds = torch.empty((S, block.nrows), dtype=torch.float32, device=self.dev)
+        size_s = torch.empty(S, dtype=torch.float32, device=self.dev)
+        ctx.check(lib.lg_collapse_basic(ctx.h, block.h, _ptr(group), _ptr(mult), S, _ptr(sum_ds), _ptr(size_s)))
+        if self.world > 1:
+            self.dist.all_reduce(sum_ds, group=self.pg)
+            self.dist.all_reduce(size_s, group=self.pg)
+        return sum_ds, size_s
+
+    def collapse_batch(self, block: CscBlock, group, batch, S: int, B: int, mult=None):
+        """stats.rs:136-164 + all-reduce; returns (sum_db (B, D), n_bs (S, B))"""
+        ctx = self.ctx
+        sum_db = torch.empty((B, block.nrows), dtype=torch.float32, device=self.dev)
+        n_bs = torch.empty((S, B), dtype=torch.float32, device=self.dev)
+        ctx.check(lib.lg_collapse_batch(ctx.h, block.h, _ptr(group), _ptr(batch), _ptr(mult), S, B, _ptr(sum_db),
+                                        _ptr(n_bs)))
+        if self.world > 1:
+            self.dist.all_reduce(sum_db, group=self.pg)
+            self.dist.all_reduce(n_bs, group=self.pg)
+        return sum_db, n_bs
+
+    # ---- stage 5 -----------------------------------------------------------------------------------
+    def optimize_single(self, sum_ds: torch.Tensor, size_s: torch.Tensor, a0=1.0, b0=1.0, target=TARGET_ALL):
+        """stats.rs:351-368 (replicated on every rank after the all-reduce)"""
+        ctx = self.ctx
+        S, D = sum_ds.shape
+        new = lambda: torch.empty((S, D), dtype=torch.float32, device=self.dev)
+        mean = new()
+        sd = new() if target == TARGET_ALL else None
+        ls = new() if target == TARGET_ALL else None
+        lm = new() if target != TARGET_MEAN_ONLY else None
+        ctx.check(lib.lg_optimize_single(ctx.h, _ptr(sum_ds), _ptr(size_s), D, S, a0, b0, target, _ptr(mean), _ptr(sd),
+                                         _ptr(lm), _ptr(ls)))
+        return dict(mean=mean, sd=sd, log_mean=lm, log_sd=ls)
+
+    # ---- whole path --------------------------------------------------------------------------------
+    def run(self, block: CscBlock, basis_kd: torch.Tensor, batch, nbatch: int, kk: int, target=TARGET_ALL):
+        """projection -> codes -> groups -> collapse -> posterior (single-batch arm of the path)"""
+        proj = self.project(block, basis_kd, batch, nbatch)
+        codes = self.binary_codes(proj, kk)
+        group, ng = self.assign_groups(codes, kk)
+        sum_ds, size_s = self.collapse_basic(block, group, ng)
+        post = self.optimize_single(sum_ds, size_s, 1.0, 1.0, target)
+        return dict(proj=proj, codes=codes, group=group, num_groups=ng, sum_ds=sum_ds, size_s=size_s, posterior=post)

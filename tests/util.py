@@ -1,0 +1,55 @@
+"""shared fixtures for the parity tests (seeded inputs, the reference's tolerance form)"""
+import numpy as np
+
+
+def close(x, y, tol=1e-5):
+    """|x-y| <= tol * (1 + max(|x|,|y|)) — data-beans-alg/src/collapse_data/stats_tests.rs:20-30"""
+    x = np.asarray(x, np.float64)
+    y = np.asarray(y, np.float64)
+    return bool(np.all(np.abs(x - y) <= tol * (1.0 + np.maximum(np.abs(x), np.abs(y)))))
+
+
+def max_err(x, y):
+    x = np.asarray(x, np.float64)
+    y = np.asarray(y, np.float64)
+    return float(np.max(np.abs(x - y) / (1.0 + np.maximum(np.abs(x), np.abs(y))))) if x.size else 0.0
+
+
+def random_csc(rng, D, N, density=0.05, max_count=6, empty_every=0):
+    """integer-valued counts, rows ascending inside a column (canonical CSC)"""
+    indptr, idx, val = [0], [], []
+    for j in range(N):
+        if empty_every and j % empty_every == 0:
+            indptr.append(len(idx))
+            continue
+        n = rng.binomial(D, density)
+        rows = np.sort(rng.choice(D, size=n, replace=False))
+        idx.extend(rows.tolist())
+        val.extend(np.minimum(rng.geometric(0.7, size=n), max_count).astype(np.float32).tolist())
+        indptr.append(len(idx))
+    return np.array(indptr, np.uint64), np.array(idx, np.uint64), np.array(val, np.float32)
+
+
+def tiny_fixture():
+    """data-beans-alg/src/random_projection.rs:578-605: 8 genes x 12 cells"""
+    d, n = 8, 12
+    indptr, idx, val = [0], [], []
+    for j in range(n):
+        for i in range(d):
+            if (i * 7 + j * 3) % 5 < 3:
+                idx.append(i)
+                val.append(1.0 + ((i + j) % 4))
+        indptr.append(len(idx))
+    return d, n, np.array(indptr, np.uint64), np.array(idx, np.uint64), np.array(val, np.float32)
+
+
+def toy_stat(G, S, B):
+    """data-beans-alg/src/collapse_data/stats_tests.rs:6-18, in (S, G) / (B, G) / (S, B) layout"""
+    f = lambda a, b: 1.0 + ((a * 7 + b * 13) % 11)
+    obs = np.array([[f(g, c) for g in range(G)] for c in range(S)], np.float32)
+    imp = np.array([[0.5 * f(g + 1, c + 2) for g in range(G)] for c in range(S)], np.float32)
+    res = np.array([[0.3 * f(g + 2, c + 1) for g in range(G)] for c in range(S)], np.float32)
+    size = np.array([2.0 + (c % 3) for c in range(S)], np.float32)
+    obs_db = np.array([[f(g, b) + 0.7 for g in range(G)] for b in range(B)], np.float32)
+    n_bs = np.array([[1.0 + ((b + c) % 4) for b in range(B)] for c in range(S)], np.float32)
+    return obs, imp, res, size, obs_db, n_bs
