@@ -12,25 +12,58 @@
 
 #include "lg_common.cuh"
 
-constexpr int COLLAPSE_THREADS = 512;
-constexpr int COLLAPSE_CHUNK = 128;  // sorted cells per work item
+constexpr int COLLAPSE_THREADS = 1024;  // one CTA per SM (the accumulator fills most of shared memory)
+constexpr int COLLAPSE_CHUNK = 256;     // sorted cells per work item
+constexpr int COLLAPSE_UNROLL = 4;      // independent 32-nnz loads in flight per warp
 
 __global__ void k_iota_u32(uint32_t* p, uint64_t n) {
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) p[i] = (uint32_t)i;
 }
 
+// 1 if every stored value is a non-negative integer below 2^20 (then sums can be kept as u32)
+__global__ void k_all_integral(const float* __restrict__ v, uint64_t n, int* __restrict__ not_integral) {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    bool bad = false;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const float x = __ldg(v + i);
+        bad |= !(x >= 0.0f && x < 1048576.0f && x == truncf(x));
+    }
+    if (__any_sync(0xffffffffu, bad) && (threadIdx.x & 31) == 0) atomicOr(not_integral, 1);
+}
+
+// Accumulator element: u32 with native shared-memory ATOMS.ADD when the counts are integers
+// (exact, and a third of the shared-memory traffic of the f32 compare-and-swap loop), f32 otherwise.
+template <bool INT>
+struct Acc;
+template <>
+struct Acc<true> {
+    using T = unsigned int;
+    static __device__ __forceinline__ void add(T* a, float v, float) { atomicAdd(a, (unsigned int)v); }
+    static __device__ __forceinline__ float get(T v) { return (float)v; }
+};
+template <>
+struct Acc<false> {
+    using T = float;
+    static __device__ __forceinline__ void add(T* a, float v, float w) { atomicAdd(a, v * w); }
+    static __device__ __forceinline__ float get(T v) { return v; }
+};
+
 // window [g0, g0 + W) of the gene axis lives in shared memory
-__global__ void __launch_bounds__(COLLAPSE_THREADS) k_collapse_sorted(
+template <bool INT>
+__global__ void __launch_bounds__(COLLAPSE_THREADS, 1) k_collapse_sorted(
     const uint64_t* __restrict__ indptr, const uint32_t* __restrict__ indices, const float* __restrict__ values,
     const uint32_t* __restrict__ sorted_label, const uint32_t* __restrict__ sorted_cell, uint64_t ncells,
     const float* __restrict__ mult, uint32_t S, uint64_t D, uint32_t g0, uint32_t W, float* __restrict__ sum_ds,
     float* __restrict__ size_s, unsigned long long* __restrict__ next_chunk) {
-    extern __shared__ float acc[];  // W floats
+    using A = Acc<INT>;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    typename A::T* acc = reinterpret_cast<typename A::T*>(smem_raw);  // W accumulators
     __shared__ unsigned long long s_chunk;
+    __shared__ uint32_t s_label[COLLAPSE_CHUNK];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = COLLAPSE_THREADS / 32;
     const uint64_t nchunks = (ncells + COLLAPSE_CHUNK - 1) / COLLAPSE_CHUNK;
-    for (uint32_t g = threadIdx.x; g < W; g += COLLAPSE_THREADS) acc[g] = 0.0f;
+    for (uint32_t g = threadIdx.x; g < W; g += COLLAPSE_THREADS) acc[g] = 0;
     while (true) {
         __syncthreads();
         if (threadIdx.x == 0) s_chunk = atomicAdd(next_chunk, 1ull);
@@ -38,33 +71,67 @@ __global__ void __launch_bounds__(COLLAPSE_THREADS) k_collapse_sorted(
         const uint64_t chunk = s_chunk;
         if (chunk >= nchunks) break;
         const uint64_t p0 = chunk * COLLAPSE_CHUNK;
-        const uint64_t p1 = (p0 + COLLAPSE_CHUNK) < ncells ? (p0 + COLLAPSE_CHUNK) : ncells;
-        uint64_t seg0 = p0;
-        while (seg0 < p1) {
+        const int np = (int)((p0 + COLLAPSE_CHUNK) < ncells ? COLLAPSE_CHUNK : (ncells - p0));
+        if ((int)threadIdx.x < np) s_label[threadIdx.x] = sorted_label[p0 + threadIdx.x];
+        __syncthreads();
+        int seg0 = 0;
+        while (seg0 < np) {
             // segment of equal labels inside the chunk (labels are sorted)
-            const uint32_t lab = sorted_label[seg0];
-            uint64_t seg1 = seg0 + 1;
-            while (seg1 < p1 && sorted_label[seg1] == lab) ++seg1;
+            const uint32_t lab = s_label[seg0];
+            int seg1 = seg0 + 1;
+            while (seg1 < np && s_label[seg1] == lab) ++seg1;
             if (lab < S) {
                 float wsum = 0.0f;
-                for (uint64_t p = seg0 + warp; p < seg1; p += nwarp) {
-                    const uint32_t cell = sorted_cell[p];
-                    const float w = mult ? mult[cell] : 1.0f;
-                    const uint64_t lo = indptr[cell], hi = indptr[cell + 1];
-                    for (uint64_t t = lo + lane; t < hi; t += 32) {
-                        const uint32_t gi = __ldg(indices + t) - g0;
-                        if (gi < W) atomicAdd(&acc[gi], __ldg(values + t) * w);
+                // software-pipelined walk over this warp's cells: fetch the next cell's extent early
+                int p = seg0 + warp;
+                uint32_t cell = 0;
+                uint64_t lo = 0, hi = 0;
+                if (p < seg1) {
+                    cell = sorted_cell[p0 + p];
+                    lo = indptr[cell];
+                    hi = indptr[cell + 1];
+                }
+                while (p < seg1) {
+                    const int pn = p + nwarp;
+                    uint32_t cell_n = 0;
+                    uint64_t lo_n = 0, hi_n = 0;
+                    if (pn < seg1) {
+                        cell_n = sorted_cell[p0 + pn];
+                        lo_n = indptr[cell_n];
+                        hi_n = indptr[cell_n + 1];
                     }
-                    wsum += w;
+                    const float w = (!INT && mult) ? mult[cell] : 1.0f;
+                    uint64_t t = lo + lane;
+                    for (; t + 32 * (COLLAPSE_UNROLL - 1) < hi; t += 32 * COLLAPSE_UNROLL) {
+                        uint32_t gi[COLLAPSE_UNROLL];
+                        float vv[COLLAPSE_UNROLL];
+#pragma unroll
+                        for (int u = 0; u < COLLAPSE_UNROLL; ++u) {
+                            gi[u] = __ldg(indices + t + 32 * u) - g0;
+                            vv[u] = __ldg(values + t + 32 * u);
+                        }
+#pragma unroll
+                        for (int u = 0; u < COLLAPSE_UNROLL; ++u)
+                            if (gi[u] < W) A::add(&acc[gi[u]], vv[u], w);
+                    }
+                    for (; t < hi; t += 32) {
+                        const uint32_t gi = __ldg(indices + t) - g0;
+                        if (gi < W) A::add(&acc[gi], __ldg(values + t), w);
+                    }
+                    wsum += (mult ? mult[cell] : 1.0f);
+                    p = pn;
+                    cell = cell_n;
+                    lo = lo_n;
+                    hi = hi_n;
                 }
                 if (lane == 0 && g0 == 0 && size_s && wsum != 0.0f) atomicAdd(&size_s[lab], wsum);
                 __syncthreads();
                 float* col = sum_ds + (size_t)lab * D + g0;
                 for (uint32_t g = threadIdx.x; g < W; g += COLLAPSE_THREADS) {
-                    const float v = acc[g];
-                    if (v != 0.0f) {
-                        atomicAdd(col + g, v);
-                        acc[g] = 0.0f;
+                    const typename A::T v = acc[g];
+                    if (v != 0) {
+                        atomicAdd(col + g, A::get(v));
+                        acc[g] = 0;
                     }
                 }
                 __syncthreads();
@@ -105,18 +172,37 @@ static int collapse_by_label(lg_ctx* ctx, LgStage& st, const lg_csc* m, const ui
     LG_CUDA(ctx, cub::DeviceRadixSort::SortPairs(d_tmp, tmp_bytes, d_label, d_lab_out, d_cell_in, d_cell_out, (int)N, 0,
                                                  32, ctx->stream));
     ctx->launches += 4;  // cub's radix passes (histogram + onesweep), counted conservatively
+    // integer-valued counts with unit multiplicity take the exact u32 accumulator
+    bool use_int = false;
+    if (!d_mult && m->nnz && m->int_valued >= 0) use_int = m->int_valued == 1;
+    else if (!d_mult && m->nnz) {
+        int* d_flag;
+        LG_TRY(st.scratch(1, &d_flag));
+        LG_CUDA(ctx, cudaMemsetAsync(d_flag, 0, sizeof(int), ctx->stream));
+        LG_LAUNCH(ctx, k_all_integral, ctx->num_sms * 8, 256, 0, m->values, m->nnz, d_flag);
+        int* h_flag = static_cast<int*>(ctx->pinned);
+        LG_CUDA(ctx, cudaMemcpyAsync(h_flag, d_flag, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+        LG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        use_int = (*h_flag == 0);
+        m->int_valued = use_int ? 1 : 0;
+    }
     unsigned long long* d_next;
     LG_TRY(st.scratch(1, &d_next));
-    const size_t smem_cap = ctx->smem_optin - 1024;
+    const size_t smem_cap = ctx->smem_optin - 4096;
     const uint32_t Wmax = (uint32_t)(smem_cap / sizeof(float));
     for (uint64_t g0 = 0; g0 < D; g0 += Wmax) {
         const uint32_t W = (uint32_t)((D - g0) < Wmax ? (D - g0) : Wmax);
         const size_t smem = (size_t)W * sizeof(float);
         LG_CUDA(ctx, cudaMemsetAsync(d_next, 0, sizeof(unsigned long long), ctx->stream));
-        LG_CUDA(ctx, cudaFuncSetAttribute(k_collapse_sorted, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        const int per_sm = (smem * 2 + 2048 <= ctx->smem_optin) ? 2 : 1;
-        LG_LAUNCH(ctx, k_collapse_sorted, ctx->num_sms * per_sm, COLLAPSE_THREADS, smem, m->indptr, m->indices, m->values,
-                  d_lab_out, d_cell_out, N, d_mult, S, D, (uint32_t)g0, W, d_sum, d_size, d_next);
+        if (use_int) {
+            LG_CUDA(ctx, cudaFuncSetAttribute(k_collapse_sorted<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            LG_LAUNCH(ctx, k_collapse_sorted<true>, ctx->num_sms, COLLAPSE_THREADS, smem, m->indptr, m->indices, m->values,
+                      d_lab_out, d_cell_out, N, d_mult, S, D, (uint32_t)g0, W, d_sum, d_size, d_next);
+        } else {
+            LG_CUDA(ctx, cudaFuncSetAttribute(k_collapse_sorted<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            LG_LAUNCH(ctx, k_collapse_sorted<false>, ctx->num_sms, COLLAPSE_THREADS, smem, m->indptr, m->indices, m->values,
+                      d_lab_out, d_cell_out, N, d_mult, S, D, (uint32_t)g0, W, d_sum, d_size, d_next);
+        }
     }
     return LG_OK;
 }

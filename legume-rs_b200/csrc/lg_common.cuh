@@ -29,6 +29,8 @@ struct lg_csc {
     uint32_t* indices = nullptr; // device, nnz
     float* values = nullptr;     // device, nnz
     bool owned = false;
+    // cached "all values are small non-negative integers" (-1 unknown); blocks are immutable
+    mutable int int_valued = -1;
 };
 
 inline int lg_fail(lg_ctx* ctx, int code, const std::string& msg) {

@@ -27,6 +27,15 @@ extern "C" int lg_ctx_create(int device, lg_ctx** out) {
         return LG_ERR_CUDA;
     }
     c->own_stream = true;
+    // keep stream-ordered scratch cached across synchronisations (the default threshold of 0
+    // hands every freed block back to the driver at each sync, which costs milliseconds per call)
+    {
+        cudaMemPool_t pool;
+        if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+            uint64_t keep = ~0ull;
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+        }
+    }
     c->pinned_bytes = 1 << 16;
     if (cudaMallocHost(&c->pinned, c->pinned_bytes) != cudaSuccess) {
         cudaStreamDestroy(c->stream);

@@ -353,6 +353,8 @@ class CollapsedOut(dict):
 def optimize(ctx: Context, stat: CollapsedStat, hyper=(1.0, 1.0), num_iter=DEFAULT_OPT_ITER, out_target=TARGET_ALL):
     """stats.rs:378-512.  Gene blocking is numerically inert (:370-377), so the fit runs in one launch."""
     a0, b0 = hyper
+    for name in ("observed_sum_ds", "imputed_sum_ds", "residual_sum_ds", "size_s", "observed_sum_db", "n_bs"):
+        setattr(stat, name, _as(getattr(stat, name), np.float32))
     S, D = stat.observed_sum_ds.shape
     B = stat.num_batches()
     dev = _is_torch(stat.observed_sum_ds)
@@ -500,6 +502,7 @@ class SparseIoVec:
     # ---- CollapsingOps (collapse_data/mod.rs:315-483) ----
     def collect_basic_stat(self, stat: CollapsedStat):
         S = stat.num_samples()
+        stat.observed_sum_ds, stat.size_s = _as(stat.observed_sum_ds, np.float32), _as(stat.size_s, np.float32)
         self.ctx.check(lib.lg_collapse_basic(self.ctx.h, self.block.h, _ptr(self.get_group_membership()),
                                              _ptr(self.multiplicity), S, _ptr(stat.observed_sum_ds), _ptr(stat.size_s)))
 

@@ -15,6 +15,8 @@ are bit-identical for any GPU count.  With world size 1 the same code runs witho
 from __future__ import annotations
 
 import ctypes as C
+import os
+import time
 
 import numpy as np
 import torch
@@ -194,9 +196,25 @@ class HotPath:
     # ---- whole path --------------------------------------------------------------------------------
     def run(self, block: CscBlock, basis_kd: torch.Tensor, batch, nbatch: int, kk: int, target=TARGET_ALL):
         """projection -> codes -> groups -> collapse -> posterior (single-batch arm of the path)"""
+        trace = os.environ.get("LG_TRACE")
+        t = [time.perf_counter()]
+
+        def mark():
+            if trace:
+                torch.cuda.synchronize()
+                t.append(time.perf_counter())
+
         proj = self.project(block, basis_kd, batch, nbatch)
+        mark()
         codes = self.binary_codes(proj, kk)
+        mark()
         group, ng = self.assign_groups(codes, kk)
+        mark()
         sum_ds, size_s = self.collapse_basic(block, group, ng)
+        mark()
         post = self.optimize_single(sum_ds, size_s, 1.0, 1.0, target)
+        mark()
+        if trace and self.rank == 0:
+            names = ["project", "codes", "groups", "collapse", "posterior"]
+            print("LG_TRACE " + " ".join(f"{n}={1e3 * (b - a):.2f}ms" for n, a, b in zip(names, t, t[1:])), flush=True)
         return dict(proj=proj, codes=codes, group=group, num_groups=ng, sum_ds=sum_ds, size_s=size_s, posterior=post)
