@@ -1,6 +1,8 @@
 // lg_project.cu — stage 1: random projection of the sparse gene x cell matrix.
 //   K1  project_columns_visitor       data-beans-alg/src/random_projection.rs:169-199
 //   K2  batch centring / standardise / clamp                         :378-407
+#include <cstdlib>
+
 #include "lg_common.cuh"
 
 // ---------------------------------------------------------------------------------------------
@@ -56,8 +58,17 @@ __global__ void __launch_bounds__(256) k_project_raw_warp(const uint64_t* __rest
     }
 }
 
+int lg_project_raw_umma(lg_ctx* ctx, const lg_csc* m, const float* d_basis, int K, float* d_out, int* used);
+
 static int launch_project_raw(lg_ctx* ctx, const lg_csc* m, const float* d_basis, int K, float* d_out) {
     if (m->ncols == 0) return LG_OK;
+    // tensor path first (lg_project_umma.cu); LG_K1_CUDA_CORES=1 forces the warp-per-cell kernel for A/B runs
+    const char* force = getenv("LG_K1_CUDA_CORES");
+    if (!(force && force[0] == '1')) {
+        int used = 0;
+        LG_TRY(lg_project_raw_umma(ctx, m, d_basis, K, d_out, &used));
+        if (used) return LG_OK;
+    }
     const int nacc = (K + 31) / 32;
     uint64_t warps = m->ncols;
     uint64_t blocks = (warps + 7) / 8;

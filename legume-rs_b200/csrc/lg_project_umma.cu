@@ -1,0 +1,398 @@
+// lg_project_umma.cu — K1 on the Blackwell tensor path (project_columns_visitor,
+// data-beans-alg/src/random_projection.rs:169-199).
+//
+// Why tensor cores here: per non-zero the projection needs one 200-byte basis row.  A CUDA-core
+// SpMM has to move that row from shared memory (or L2) to registers for every non-zero, and the
+// 128 B/clk/SM shared-memory pipe caps it near 2-2.5 clk per nnz (~15% of the HBM roofline; the
+// warp-per-cell kernel in lg_project.cu measures 5%).  The tensor core reads a basis tile once per
+// 128 cells instead, so the kernel becomes a dense int8 GEMM against a 0/1 indicator of the CSC
+// pattern, which sm_100a runs at twice the f16 rate with EXACT s32 accumulation:
+//
+//   proj_raw[:, j] = ( ln2 * sum_{i in nnz(j)} B[i, :]  +  sum_{i: y_ij != 1} (ln(1+y_ij) - ln2) B[i, :] ) / ||x_j||
+//                       `---- K1a: tcgen05 kind::i8 ----'   `---- K1b: CUDA cores, the few counts > 1 ----'
+//
+//   * the basis is quantised to 2^-20 fixed point and split into three signed 8-bit digits
+//     (N = 3K columns of the B operand); |B| < 7.97 is required, else the caller falls back.
+//   * K1b (k_project_prep, one warp per cell, one coalesced pass over indices AND values) writes the
+//     sparsity pattern as a bitmap (1 bit per gene: smaller than the u32 index stream above 3% density),
+//     tiled per (256 cells x 2048 genes) so the tensor kernel fetches it with one bulk copy per chunk,
+//     and leaves corr/norm and ln2/norm per cell.
+//   * K1a never materialises the dense A operand in memory: expander warps turn 64-bit bitmap words
+//     into 16 TMEM columns (u8 in {0, 128}) with two ALU ops per register and tcgen05.st them.
+#include "lg_common.cuh"
+#include "lg_umma.cuh"
+
+using namespace umma;
+
+namespace {
+
+constexpr int TILE_M = 128;          // cells per accumulator (UMMA M)
+constexpr int NT = 2;                // accumulators (cell tiles) per CTA
+constexpr int CELLS = TILE_M * NT;   // cells per CTA pass
+constexpr int GS = 64;               // genes per pipeline stage (2 MMAs of K = 32)
+constexpr int GC = 2048;             // genes per bitmap chunk
+constexpr int BM_STRIDE = GC / 32 + 2;  // 66 words per cell row: 8-byte aligned, conflict-free LDS.64
+constexpr int NBST = 4;              // B-operand ring depth (stages)
+constexpr int NAST = 4;              // A-operand ring depth in TMEM (stages per tile)
+constexpr int A_COLS = GS / 4;       // 16 TMEM columns per A stage
+constexpr int N_EXP_WARPS = 4 * NT;  // 8 expander warps (also the epilogue)
+constexpr int WARP_MMA = N_EXP_WARPS;
+constexpr int WARP_LOAD_B = N_EXP_WARPS + 1;   // basis stages
+constexpr int WARP_LOAD_BM = N_EXP_WARPS + 2;  // bitmap chunks
+constexpr int THREADS = (N_EXP_WARPS + 3) * 32;  // 352
+constexpr uint32_t BM_CHUNK_BYTES = CELLS * BM_STRIDE * 4;  // 67584 bytes per (supertile, chunk)
+constexpr int PREP_WARPS = 8;
+constexpr float QSCALE = 1048576.0f;                       // 2^20
+constexpr int QMAX = 127 * 65536 + 127 * 256 + 127;        // largest 3-digit signed base-256 value
+
+struct Barriers {
+    uint64_t b_full[NBST], b_empty[NBST];
+    uint64_t a_full[NT][NAST], a_empty[NT][NAST];
+    uint64_t bm_full[2], bm_empty[2];
+    uint64_t acc_full[NT], acc_empty[NT];
+};
+
+// ---- basis -> three signed base-256 digits, laid out as the UMMA B operand ---------------------
+// chunk = 32 genes x NB columns in the K-major no-swizzle canonical form:
+//   byte(n, k) = (n/8)*256 + (k/16)*128 + (n%8)*16 + (k%16),  n = digit*K + dim
+__global__ void k_quantize_basis(const float* __restrict__ basis_kd, uint64_t D, int K, int NB, uint64_t Dpad,
+                                 int8_t* __restrict__ bq, int* __restrict__ too_large) {
+    const uint64_t e = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= Dpad * (uint64_t)NB) return;
+    const uint64_t gene = e / NB;
+    const int n = (int)(e % NB);
+    const int digit = n / K, dim = n % K;
+    int8_t out = 0;
+    if (gene < D && digit < 3) {
+        const float b = basis_kd[gene * K + dim];
+        const float qf = rintf(b * QSCALE);
+        if (!(fabsf(qf) <= (float)QMAX)) atomicOr(too_large, 1);
+        int q = (int)fminf(fmaxf(qf, -(float)QMAX), (float)QMAX);
+        int d0 = ((q + 128) & 255) - 128;
+        q = (q - d0) >> 8;
+        int d1 = ((q + 128) & 255) - 128;
+        q = (q - d1) >> 8;
+        const int d[3] = {d0, d1, q};
+        out = (int8_t)d[digit];
+    }
+    const uint64_t chunk = gene >> 5;
+    const int k = (int)(gene & 31);
+    bq[chunk * (uint64_t)(NB * 32) + (uint64_t)(n >> 3) * 256 + (k >> 4) * 128 + (n & 7) * 16 + (k & 15)] = out;
+}
+
+// ---- K1b: one pass over the CSC block (CUDA cores, HBM-bound) -----------------------------------
+// per cell: (1) pattern bitmap row -> tiled global scratch, (2) norm, (3) correction for counts != 1.
+// writes out[j*K + k] = corr_k / norm_j and scale[j] = ln2 / norm_j.
+// bitmap word w of a cell covers genes 32w..32w+31; gene offset o sits at bit (o>>2) + 8*(o&3) so that
+// the expander's (w << (7-b)) & 0x80808080 yields the four K-positions 4b..4b+3 of an MMA operand column.
+template <int NACC>
+__global__ void __launch_bounds__(PREP_WARPS * 32, 6) k_project_prep(const uint64_t* __restrict__ indptr,
+                                                                  const uint32_t* __restrict__ indices,
+                                                                  const float* __restrict__ values, uint64_t ncols,
+                                                                  const float* __restrict__ basis_kd, int K, uint32_t nchunks,
+                                                                  uint32_t* __restrict__ bm_global, float* __restrict__ out,
+                                                                  float* __restrict__ scale) {
+    extern __shared__ __align__(16) uint32_t rows[];  // PREP_WARPS rows of nchunks*64 words
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t row_words = nchunks * (GC / 32);
+    uint32_t* row = rows + (size_t)warp * row_words;
+    const uint64_t warp0 = (uint64_t)blockIdx.x * PREP_WARPS + warp;
+    const uint64_t nwarps = (uint64_t)gridDim.x * PREP_WARPS;
+    const float ln2 = log1pf(1.0f);
+    for (uint64_t j = warp0; j < ncols; j += nwarps) {
+        for (uint32_t i = lane; i < row_words / 4; i += 32) reinterpret_cast<uint4*>(row)[i] = make_uint4(0, 0, 0, 0);
+        __syncwarp();
+        const uint64_t lo = indptr[j], hi = indptr[j + 1];
+        float acc[NACC];
+#pragma unroll
+        for (int a = 0; a < NACC; ++a) acc[a] = 0.0f;
+        float nsq = 0.0f;
+        for (uint64_t base = lo; base < hi; base += 128) {
+            uint32_t ix[4];
+            float v[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {  // 8 independent coalesced loads in flight per lane
+                const uint64_t t = base + 32 * u + lane;
+                const bool live = t < hi;
+                ix[u] = live ? __ldg(indices + t) : 0xffffffffu;
+                v[u] = live ? __ldg(values + t) : 0.0f;
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const bool live = ix[u] != 0xffffffffu;
+                if (live) atomicOr(row + (ix[u] >> 5), 1u << (((ix[u] & 31) >> 2) + 8 * (ix[u] & 3)));
+                const float x = live ? log1pf(v[u]) : 0.0f;
+                nsq = fmaf(x, x, nsq);
+                unsigned pend = __ballot_sync(0xffffffffu, live && v[u] != 1.0f);
+                const float w = x - ln2;
+                while (pend) {
+                    const int sl = __ffs(pend) - 1;
+                    pend &= pend - 1;
+                    const uint32_t gi = __shfl_sync(0xffffffffu, ix[u], sl);
+                    const float ws = __shfl_sync(0xffffffffu, w, sl);
+                    const float* brow = basis_kd + (size_t)gi * K;
+#pragma unroll
+                    for (int a = 0; a < NACC; ++a) {
+                        const int k = lane + 32 * a;
+                        if (k < K) acc[a] = fmaf(ws, __ldg(brow + k), acc[a]);
+                    }
+                }
+            }
+        }
+        __syncwarp();
+        // tiled store: (supertile, chunk) blocks of CELLS rows x BM_STRIDE words; one 256-byte chunk row per iteration
+        {
+            const uint64_t sup = j / CELLS;
+            const uint32_t r = (uint32_t)(j % CELLS);
+            for (uint32_t c = 0; c < nchunks; ++c) {
+                const uint2 w2 = reinterpret_cast<const uint2*>(row + (size_t)c * (GC / 32))[lane];
+                uint32_t* dst = bm_global + ((sup * nchunks + c) * CELLS + r) * (uint64_t)BM_STRIDE;
+                reinterpret_cast<uint2*>(dst)[lane] = w2;
+            }
+        }
+#pragma unroll
+        for (int off = 16; off >= 1; off >>= 1) nsq += __shfl_xor_sync(0xffffffffu, nsq, off);
+        const float denom = fmaxf(sqrtf(nsq), 1e-8f);
+#pragma unroll
+        for (int a = 0; a < NACC; ++a) {
+            const int k = lane + 32 * a;
+            if (k < K) out[(size_t)j * K + k] = acc[a] / denom;
+        }
+        if (lane == 0) scale[j] = ln2 / denom;
+        __syncwarp();
+    }
+}
+
+// ---- K1a: the tcgen05 kernel -----------------------------------------------------------------
+__global__ void __launch_bounds__(THREADS, 1) k_project_umma(const uint32_t* __restrict__ bm_global, uint64_t ncols, uint64_t D,
+                                                             const int8_t* __restrict__ bq, int K, int NB, uint32_t nstages,
+                                                             const float* __restrict__ scale, float* __restrict__ out) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    // carve: [B ring][bitmap x2][barriers][tmem base]
+    const uint32_t stage_bytes = (uint32_t)NB * 32u * (GS / 32);
+    uint8_t* smem_b = smem;
+    uint32_t* bitmap = reinterpret_cast<uint32_t*>(smem + (size_t)NBST * stage_bytes);
+    Barriers* bars = reinterpret_cast<Barriers*>(bitmap + 2 * CELLS * BM_STRIDE);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t nchunks = (uint32_t)((D + GC - 1) / GC);
+    const uint64_t nsuper = (ncols + CELLS - 1) / CELLS;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < NBST; ++s) {
+            mbar_init(&bars->b_full[s], 1);
+            mbar_init(&bars->b_empty[s], 1);
+        }
+        for (int t = 0; t < NT; ++t) {
+            for (int s = 0; s < NAST; ++s) {
+                mbar_init(&bars->a_full[t][s], 4);
+                mbar_init(&bars->a_empty[t][s], 1);
+            }
+            mbar_init(&bars->acc_full[t], 1);
+            mbar_init(&bars->acc_empty[t], 4);
+        }
+        for (int b = 0; b < 2; ++b) {
+            mbar_init(&bars->bm_full[b], 1);
+            mbar_init(&bars->bm_empty[b], N_EXP_WARPS);
+        }
+        fence_barrier_init();
+    }
+    if (warp == WARP_MMA) {
+        tmem_alloc(tmem_slot, 512);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tbase = *tmem_slot;
+    const uint32_t a_col0 = (uint32_t)NT * (uint32_t)NB;  // A ring starts after the accumulators
+
+    if (warp < N_EXP_WARPS) {
+        // ===== expanders / epilogue: one thread per cell row =====
+        const int t = warp >> 2;                        // tile of this warp
+        const int row = (warp & 3) * 32 + lane;         // TMEM lane == row inside the tile
+        const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
+        const uint32_t acc_addr = tbase + lane_base + (uint32_t)t * NB;
+        uint32_t a_it = 0, chunk_it = 0, super_it = 0;
+        for (uint64_t sup = blockIdx.x; sup < nsuper; sup += gridDim.x, ++super_it) {
+            uint32_t stage = 0;
+            for (uint32_t c = 0; c < nchunks; ++c, ++chunk_it) {
+                const uint32_t buf = chunk_it & 1;
+                mbar_wait(&bars->bm_full[buf], (chunk_it >> 1) & 1);
+                const uint32_t* my = bitmap + (size_t)buf * CELLS * BM_STRIDE + (size_t)(t * TILE_M + row) * BM_STRIDE;
+                const uint32_t st_end = min(nstages, (c + 1) * (GC / GS));
+                for (uint32_t ls = 0; stage < st_end; ++stage, ++ls, ++a_it) {
+                    const uint32_t slot = a_it % NAST;
+                    mbar_wait(&bars->a_empty[t][slot], ((a_it / NAST) & 1) ^ 1);
+                    tc_fence_after();
+                    const uint2 w = *reinterpret_cast<const uint2*>(my + 2 * ls);
+                    uint32_t r[16];
+#pragma unroll
+                    for (int b = 0; b < 8; ++b) {
+                        r[b] = (w.x << (7 - b)) & 0x80808080u;
+                        r[8 + b] = (w.y << (7 - b)) & 0x80808080u;
+                    }
+                    tmem_st_x16(tbase + lane_base + a_col0 + (uint32_t)(t * NAST + slot) * A_COLS, r);
+                    tmem_wait_st();
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&bars->a_full[t][slot]);
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&bars->bm_empty[buf]);
+            }
+            // ---- epilogue for this tile ----
+            mbar_wait(&bars->acc_full[t], super_it & 1);
+            tc_fence_after();
+            const uint64_t cell = sup * CELLS + (uint64_t)t * TILE_M + row;
+            const bool live = cell < ncols;
+            const float sc = live ? scale[cell] : 0.0f;
+            float* orow = out + (size_t)cell * K;
+            for (int kb = 0; kb < K; kb += 16) {
+                uint32_t d0[16], d1[16], d2[16];
+                tmem_ld_x16(acc_addr + kb, d0);
+                tmem_ld_x16(acc_addr + K + kb, d1);
+                tmem_ld_x16(acc_addr + 2 * K + kb, d2);
+                tmem_wait_ld();
+                if (live) {
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) {
+                        const int k = kb + i;
+                        if (k < K) {
+                            // digits carry the A scale of 128: total = 128 * sum(q_i), q in 2^-20 units
+                            const long long tot = ((long long)(int)d2[i] << 16) + ((long long)(int)d1[i] << 8) + (long long)(int)d0[i];
+                            const float s = (float)((double)tot * (1.0 / (128.0 * 1048576.0)));
+                            orow[k] = fmaf(s, sc, orow[k]);
+                        }
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&bars->acc_empty[t]);
+        }
+    } else if (warp == WARP_MMA) {
+        // ===== MMA issuer =====
+        if (elect_one()) {
+            const uint32_t idesc = make_idesc(CFMT_S32, FMT_U8, FMT_S8, TILE_M, (uint32_t)NB);
+            uint32_t b_it = 0, a_it = 0, super_it = 0;
+            for (uint64_t sup = blockIdx.x; sup < nsuper; sup += gridDim.x, ++super_it) {
+                for (int t = 0; t < NT; ++t) mbar_wait(&bars->acc_empty[t], (super_it & 1) ^ 1);
+                tc_fence_after();
+                for (uint32_t stage = 0; stage < nstages; ++stage, ++b_it, ++a_it) {
+                    const uint32_t bs = b_it % NBST, as = a_it % NAST;
+                    mbar_wait(&bars->b_full[bs], (b_it / NBST) & 1);
+                    const uint32_t b_addr = smem_u32(smem_b + (size_t)bs * stage_bytes);
+                    for (int t = 0; t < NT; ++t) {
+                        mbar_wait(&bars->a_full[t][as], (a_it / NAST) & 1);
+                        tc_fence_after();
+#pragma unroll
+                        for (int j = 0; j < GS / 32; ++j) {
+                            const uint64_t db = make_smem_desc(b_addr + (uint32_t)j * NB * 32u, 128, 256);
+                            mma_i8_ts(tbase + (uint32_t)t * NB, tbase + a_col0 + (uint32_t)(t * NAST + as) * A_COLS + 8u * j, db, idesc,
+                                      stage > 0 || j > 0);
+                        }
+                        tc_commit(&bars->a_empty[t][as]);
+                    }
+                    tc_commit(&bars->b_empty[bs]);
+                }
+                for (int t = 0; t < NT; ++t) tc_commit(&bars->acc_full[t]);
+            }
+        }
+    } else if (warp == WARP_LOAD_B) {
+        // ===== B-operand loader: one bulk copy per stage =====
+        if (elect_one()) {
+            uint32_t b_it = 0;
+            for (uint64_t sup = blockIdx.x; sup < nsuper; sup += gridDim.x) {
+                for (uint32_t stage = 0; stage < nstages; ++stage, ++b_it) {
+                    const uint32_t bs = b_it % NBST;
+                    mbar_wait(&bars->b_empty[bs], ((b_it / NBST) & 1) ^ 1);
+                    mbar_arrive_expect_tx(&bars->b_full[bs], stage_bytes);
+                    bulk_g2s(smem_b + (size_t)bs * stage_bytes, bq + (size_t)stage * stage_bytes, stage_bytes, &bars->b_full[bs]);
+                }
+            }
+        }
+    } else if (warp == WARP_LOAD_BM) {
+        // ===== bitmap loader: one bulk copy per (supertile, chunk) =====
+        if (elect_one()) {
+            uint32_t chunk_it = 0;
+            for (uint64_t sup = blockIdx.x; sup < nsuper; sup += gridDim.x) {
+                for (uint32_t c = 0; c < nchunks; ++c, ++chunk_it) {
+                    const uint32_t buf = chunk_it & 1;
+                    mbar_wait(&bars->bm_empty[buf], ((chunk_it >> 1) & 1) ^ 1);
+                    mbar_arrive_expect_tx(&bars->bm_full[buf], BM_CHUNK_BYTES);
+                    bulk_g2s(bitmap + (size_t)buf * CELLS * BM_STRIDE,
+                             bm_global + (sup * nchunks + c) * (uint64_t)(CELLS * BM_STRIDE), BM_CHUNK_BYTES, &bars->bm_full[buf]);
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == WARP_MMA) tmem_dealloc(tbase, 512);
+}
+
+}  // namespace
+
+// returns LG_OK and sets *used = 1 when the tensor path ran, *used = 0 when the caller must fall back
+int lg_project_raw_umma(lg_ctx* ctx, const lg_csc* m, const float* d_basis, int K, float* d_out, int* used) {
+    *used = 0;
+    const int NB = ((3 * K + 15) / 16) * 16;
+    if (K < 1 || NT * NB + NT * NAST * A_COLS > 512 || m->nrows > 131072 || m->ncols == 0 || m->nrows == 0) return LG_OK;
+    const uint64_t D = m->nrows;
+    const uint64_t Dpad = ((D + GS - 1) / GS) * GS;
+    const uint32_t nstages = (uint32_t)(Dpad / GS);
+    LgStage st(ctx);
+    int8_t* d_bq;
+    int* d_flag;
+    float* d_scale;
+    LG_TRY(st.scratch((size_t)Dpad * NB, &d_bq));
+    LG_TRY(st.scratch(1, &d_flag));
+    LG_TRY(st.scratch((size_t)m->ncols, &d_scale));
+    LG_CUDA(ctx, cudaMemsetAsync(d_flag, 0, sizeof(int), ctx->stream));
+    {
+        const uint64_t tot = Dpad * (uint64_t)NB;
+        LG_LAUNCH(ctx, k_quantize_basis, (unsigned)((tot + 255) / 256), 256, 0, d_basis, D, K, NB, Dpad, d_bq, d_flag);
+    }
+    int* h_flag = static_cast<int*>(ctx->pinned);
+    LG_CUDA(ctx, cudaMemcpyAsync(h_flag, d_flag, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    LG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (*h_flag) return LG_OK;  // basis outside the fixed-point range (e.g. large row weights): fall back
+
+    // K1b first: bitmap + corr/norm in `out` + ln2/norm in `scale`; K1a then adds the tensor part
+    const uint32_t nchunks = (uint32_t)((D + GC - 1) / GC);
+    const uint64_t nsuper = (m->ncols + CELLS - 1) / CELLS;
+    uint32_t* d_bm;
+    LG_TRY(st.scratch((size_t)nsuper * nchunks * CELLS * BM_STRIDE, &d_bm));
+    if (m->ncols % CELLS)  // rows of the ragged last supertile that no cell writes must read as empty
+        LG_CUDA(ctx, cudaMemsetAsync(d_bm + (nsuper - 1) * nchunks * (size_t)(CELLS * BM_STRIDE), 0,
+                                     (size_t)nchunks * BM_CHUNK_BYTES, ctx->stream));
+    {
+        const size_t psmem = (size_t)PREP_WARPS * nchunks * (GC / 32) * 4;
+        int per_sm = (int)(ctx->smem_optin / (psmem + 1024));
+        if (per_sm > 6) per_sm = 6;
+        if (per_sm < 1) return lg_fail(ctx, LG_ERR_INTERNAL, "k_project_prep: shared memory budget exceeded");
+        uint64_t blocks = (m->ncols + PREP_WARPS - 1) / PREP_WARPS;
+        const uint64_t cap = (uint64_t)ctx->num_sms * per_sm;
+        if (blocks > cap) blocks = cap;
+        const int nacc = (K + 31) / 32;
+        if (nacc == 1) {
+            LG_CUDA(ctx, cudaFuncSetAttribute(k_project_prep<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psmem));
+            LG_LAUNCH(ctx, k_project_prep<1>, (unsigned)blocks, PREP_WARPS * 32, psmem, m->indptr, m->indices, m->values, m->ncols,
+                      d_basis, K, nchunks, d_bm, d_out, d_scale);
+        } else {
+            LG_CUDA(ctx, cudaFuncSetAttribute(k_project_prep<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psmem));
+            LG_LAUNCH(ctx, k_project_prep<2>, (unsigned)blocks, PREP_WARPS * 32, psmem, m->indptr, m->indices, m->values, m->ncols,
+                      d_basis, K, nchunks, d_bm, d_out, d_scale);
+        }
+    }
+    const size_t stage_bytes = (size_t)NB * 32 * (GS / 32);
+    const size_t smem = (size_t)NBST * stage_bytes + (size_t)2 * BM_CHUNK_BYTES + sizeof(Barriers) + 16;
+    if (smem > ctx->smem_optin) return lg_fail(ctx, LG_ERR_INTERNAL, "k_project_umma: shared memory budget exceeded");
+    LG_CUDA(ctx, cudaFuncSetAttribute(k_project_umma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const unsigned grid = (unsigned)(nsuper < (uint64_t)ctx->num_sms ? nsuper : (uint64_t)ctx->num_sms);
+    LG_LAUNCH(ctx, k_project_umma, grid, THREADS, smem, d_bm, m->ncols, D, d_bq, K, NB, nstages, d_scale, d_out);
+    *used = 1;
+    return LG_OK;
+}
