@@ -29,12 +29,12 @@ namespace {
 constexpr int TILE_M = 128;          // cells per accumulator (UMMA M)
 constexpr int NT = 2;                // accumulators (cell tiles) per CTA
 constexpr int CELLS = TILE_M * NT;   // cells per CTA pass
-constexpr int GS = 64;               // genes per pipeline stage (2 MMAs of K = 32)
+constexpr int GS = 128;              // genes per pipeline stage (4 MMAs of K = 32)
 constexpr int GC = 2048;             // genes per bitmap chunk
 constexpr int BM_STRIDE = GC / 32 + 2;  // 66 words per cell row: 8-byte aligned, conflict-free LDS.64
-constexpr int NBST = 4;              // B-operand ring depth (stages)
-constexpr int NAST = 4;              // A-operand ring depth in TMEM (stages per tile)
-constexpr int A_COLS = GS / 4;       // 16 TMEM columns per A stage
+constexpr int NBST = 3;              // B-operand ring depth (stages)
+constexpr int NAST = 3;              // A-operand ring depth in TMEM (stages per tile)
+constexpr int A_COLS = GS / 4;       // 32 TMEM columns per A stage
 constexpr int N_EXP_WARPS = 4 * NT;  // 8 expander warps (also the epilogue)
 constexpr int WARP_MMA = N_EXP_WARPS;
 constexpr int WARP_LOAD_B = N_EXP_WARPS + 1;   // basis stages
@@ -85,73 +85,135 @@ __global__ void k_quantize_basis(const float* __restrict__ basis_kd, uint64_t D,
 // writes out[j*K + k] = corr_k / norm_j and scale[j] = ln2 / norm_j.
 // bitmap word w of a cell covers genes 32w..32w+31; gene offset o sits at bit (o>>2) + 8*(o&3) so that
 // the expander's (w << (7-b)) & 0x80808080 yields the four K-positions 4b..4b+3 of an MMA operand column.
+constexpr int PREP_Q = 256;  // exception queue entries per warp (>= 7 + 128)
+constexpr int PREP_LUT = 64;  // log1p look-up for integer counts below this
+
 template <int NACC>
-__global__ void __launch_bounds__(PREP_WARPS * 32, 6) k_project_prep(const uint64_t* __restrict__ indptr,
-                                                                  const uint32_t* __restrict__ indices,
-                                                                  const float* __restrict__ values, uint64_t ncols,
-                                                                  const float* __restrict__ basis_kd, int K, uint32_t nchunks,
-                                                                  uint32_t* __restrict__ bm_global, float* __restrict__ out,
-                                                                  float* __restrict__ scale) {
-    extern __shared__ __align__(16) uint32_t rows[];  // PREP_WARPS rows of nchunks*64 words
+__global__ void __launch_bounds__(PREP_WARPS * 32, 4) k_project_prep(const uint64_t* __restrict__ indptr,
+                                                                     const uint32_t* __restrict__ indices,
+                                                                     const float* __restrict__ values, uint64_t ncols,
+                                                                     const float* __restrict__ basis_kd, int K, uint32_t nchunks,
+                                                                     uint32_t* __restrict__ bm_global, float* __restrict__ out,
+                                                                     float* __restrict__ scale) {
+    extern __shared__ __align__(16) uint32_t rows[];  // PREP_WARPS bitmap rows, then the exception queues
+    __shared__ float lut_x[PREP_LUT];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint32_t row_words = nchunks * (GC / 32);
     uint32_t* row = rows + (size_t)warp * row_words;
+    uint32_t* qg = rows + (size_t)PREP_WARPS * row_words + warp * (2 * PREP_Q);
+    float* qw = reinterpret_cast<float*>(qg + PREP_Q);
+    if (threadIdx.x < PREP_LUT) lut_x[threadIdx.x] = log1pf((float)threadIdx.x);
+    __syncthreads();
     const uint64_t warp0 = (uint64_t)blockIdx.x * PREP_WARPS + warp;
     const uint64_t nwarps = (uint64_t)gridDim.x * PREP_WARPS;
-    const float ln2 = log1pf(1.0f);
+    const float ln2 = lut_x[1];
+    const unsigned lt_mask = (1u << lane) - 1u;
     for (uint64_t j = warp0; j < ncols; j += nwarps) {
         for (uint32_t i = lane; i < row_words / 4; i += 32) reinterpret_cast<uint4*>(row)[i] = make_uint4(0, 0, 0, 0);
         __syncwarp();
-        const uint64_t lo = indptr[j], hi = indptr[j + 1];
+        const uint64_t lo = indptr[j];
+        const uint32_t n = (uint32_t)(indptr[j + 1] - lo);
+        const uint32_t* ip = indices + lo;
+        const float* vp = values + lo;
         float acc[NACC];
 #pragma unroll
         for (int a = 0; a < NACC; ++a) acc[a] = 0.0f;
         float nsq = 0.0f;
-        for (uint64_t base = lo; base < hi; base += 128) {
-            uint32_t ix[4];
-            float v[4];
+        uint32_t n_one = 0;              // warp-uniform count of entries equal to 1
+        uint32_t qhead = 0, qtail = 0;   // warp-uniform ring cursors of the exception queue
+
+        // gather-accumulate `cnt` (<= 8) queued (gene, weight) pairs with all their basis loads in flight at once
+        auto drain = [&](uint32_t cnt) {
+            uint32_t g[8];
+            float w[8], bv[8][NACC];
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {  // 8 independent coalesced loads in flight per lane
-                const uint64_t t = base + 32 * u + lane;
-                const bool live = t < hi;
-                ix[u] = live ? __ldg(indices + t) : 0xffffffffu;
-                v[u] = live ? __ldg(values + t) : 0.0f;
+            for (int e = 0; e < 8; ++e) {
+                const bool on = (uint32_t)e < cnt;
+                g[e] = on ? qg[(qhead + e) & (PREP_Q - 1)] : 0u;
+                w[e] = on ? qw[(qhead + e) & (PREP_Q - 1)] : 0.0f;
+            }
+#pragma unroll
+            for (int e = 0; e < 8; ++e)
+#pragma unroll
+                for (int a = 0; a < NACC; ++a) {
+                    const int k = lane + 32 * a;
+                    bv[e][a] = (k < K) ? __ldg(basis_kd + (size_t)g[e] * K + k) : 0.0f;
+                }
+#pragma unroll
+            for (int e = 0; e < 8; ++e)
+#pragma unroll
+                for (int a = 0; a < NACC; ++a) acc[a] = fmaf(w[e], bv[e][a], acc[a]);
+            qhead += cnt;
+        };
+
+        uint32_t ix[4];
+        float v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const uint32_t t = 32 * u + lane;
+            const bool live = t < n;
+            ix[u] = live ? __ldg(ip + t) : 0xffffffffu;
+            v[u] = live ? __ldg(vp + t) : 1.0f;
+        }
+        for (uint32_t base = 0; base < n; base += 128) {
+            // software pipeline: the next 128 nnz are in flight while this batch is consumed
+            uint32_t nix[4];
+            float nv[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const uint32_t t = base + 128 + 32 * u + lane;
+                const bool live = t < n;
+                nix[u] = live ? __ldg(ip + t) : 0xffffffffu;
+                nv[u] = live ? __ldg(vp + t) : 1.0f;
             }
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
                 const bool live = ix[u] != 0xffffffffu;
-                if (live) atomicOr(row + (ix[u] >> 5), 1u << (((ix[u] & 31) >> 2) + 8 * (ix[u] & 3)));
-                const float x = live ? log1pf(v[u]) : 0.0f;
-                nsq = fmaf(x, x, nsq);
-                unsigned pend = __ballot_sync(0xffffffffu, live && v[u] != 1.0f);
-                const float w = x - ln2;
-                while (pend) {
-                    const int sl = __ffs(pend) - 1;
-                    pend &= pend - 1;
-                    const uint32_t gi = __shfl_sync(0xffffffffu, ix[u], sl);
-                    const float ws = __shfl_sync(0xffffffffu, w, sl);
-                    const float* brow = basis_kd + (size_t)gi * K;
-#pragma unroll
-                    for (int a = 0; a < NACC; ++a) {
-                        const int k = lane + 32 * a;
-                        if (k < K) acc[a] = fmaf(ws, __ldg(brow + k), acc[a]);
+                if (live) atomicOr(row + (ix[u] >> 5), 1u << (((ix[u] >> 2) & 7) | ((ix[u] & 3) << 3)));
+                // dead lanes carry v = 1, so "not one" already implies live
+                const unsigned m = __ballot_sync(0xffffffffu, v[u] != 1.0f);
+                if (m) {
+                    if (v[u] != 1.0f) {
+                        const int vi = (int)v[u];
+                        float x;
+                        if (v[u] == (float)vi && vi >= 0 && vi < PREP_LUT) x = lut_x[vi];
+                        else x = log1pf(v[u]);
+                        nsq = fmaf(x, x, nsq);
+                        const uint32_t slot = (qtail + __popc(m & lt_mask)) & (PREP_Q - 1);
+                        qg[slot] = ix[u];
+                        qw[slot] = x - ln2;
                     }
+                    qtail += __popc(m);
                 }
             }
+            {   // live entries of this batch that equal 1: total live minus the exceptions just queued
+                const uint32_t nlive = min(128u, n - base);
+                n_one += nlive;
+            }
+            __syncwarp();
+            while (qtail - qhead >= 8) drain(8);
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                ix[u] = nix[u];
+                v[u] = nv[u];
+            }
         }
+        n_one -= qtail;  // every queued exception was counted as live above
+        if (qtail != qhead) drain(qtail - qhead);
         __syncwarp();
         // tiled store: (supertile, chunk) blocks of CELLS rows x BM_STRIDE words; one 256-byte chunk row per iteration
         {
             const uint64_t sup = j / CELLS;
             const uint32_t r = (uint32_t)(j % CELLS);
+            uint32_t* dst = bm_global + ((sup * nchunks) * CELLS + r) * (uint64_t)BM_STRIDE;
             for (uint32_t c = 0; c < nchunks; ++c) {
                 const uint2 w2 = reinterpret_cast<const uint2*>(row + (size_t)c * (GC / 32))[lane];
-                uint32_t* dst = bm_global + ((sup * nchunks + c) * CELLS + r) * (uint64_t)BM_STRIDE;
-                reinterpret_cast<uint2*>(dst)[lane] = w2;
+                reinterpret_cast<uint2*>(dst + (size_t)c * (CELLS * BM_STRIDE))[lane] = w2;
             }
         }
 #pragma unroll
         for (int off = 16; off >= 1; off >>= 1) nsq += __shfl_xor_sync(0xffffffffu, nsq, off);
+        nsq = fmaf((float)n_one, ln2 * ln2, nsq);
         const float denom = fmaxf(sqrtf(nsq), 1e-8f);
 #pragma unroll
         for (int a = 0; a < NACC; ++a) {
@@ -226,14 +288,18 @@ __global__ void __launch_bounds__(THREADS, 1) k_project_umma(const uint32_t* __r
                     const uint32_t slot = a_it % NAST;
                     mbar_wait(&bars->a_empty[t][slot], ((a_it / NAST) & 1) ^ 1);
                     tc_fence_after();
-                    const uint2 w = *reinterpret_cast<const uint2*>(my + 2 * ls);
-                    uint32_t r[16];
+                    const uint32_t a_addr = tbase + lane_base + a_col0 + (uint32_t)(t * NAST + slot) * A_COLS;
 #pragma unroll
-                    for (int b = 0; b < 8; ++b) {
-                        r[b] = (w.x << (7 - b)) & 0x80808080u;
-                        r[8 + b] = (w.y << (7 - b)) & 0x80808080u;
+                    for (int hh = 0; hh < GS / 64; ++hh) {
+                        const uint2 w = *reinterpret_cast<const uint2*>(my + (GS / 32) * ls + 2 * hh);
+                        uint32_t r[16];
+#pragma unroll
+                        for (int b = 0; b < 8; ++b) {
+                            r[b] = (w.x << (7 - b)) & 0x80808080u;
+                            r[8 + b] = (w.y << (7 - b)) & 0x80808080u;
+                        }
+                        tmem_st_x16(a_addr + 16u * hh, r);
                     }
-                    tmem_st_x16(tbase + lane_base + a_col0 + (uint32_t)(t * NAST + slot) * A_COLS, r);
                     tmem_wait_st();
                     tc_fence_before();
                     __syncwarp();
@@ -243,27 +309,37 @@ __global__ void __launch_bounds__(THREADS, 1) k_project_umma(const uint32_t* __r
                 if (lane == 0) mbar_arrive(&bars->bm_empty[buf]);
             }
             // ---- epilogue for this tile ----
-            mbar_wait(&bars->acc_full[t], super_it & 1);
-            tc_fence_after();
+            // the correction row and the scale are fetched while the last MMAs still run
             const uint64_t cell = sup * CELLS + (uint64_t)t * TILE_M + row;
             const bool live = cell < ncols;
-            const float sc = live ? scale[cell] : 0.0f;
             float* orow = out + (size_t)cell * K;
-            for (int kb = 0; kb < K; kb += 16) {
-                uint32_t d0[16], d1[16], d2[16];
-                tmem_ld_x16(acc_addr + kb, d0);
-                tmem_ld_x16(acc_addr + K + kb, d1);
-                tmem_ld_x16(acc_addr + 2 * K + kb, d2);
-                tmem_wait_ld();
-                if (live) {
+            float corr[64];
+            float sc = 0.0f;
+            if (live) {
+                sc = __ldg(scale + cell);
 #pragma unroll
-                    for (int i = 0; i < 16; ++i) {
-                        const int k = kb + i;
-                        if (k < K) {
-                            // digits carry the A scale of 128: total = 128 * sum(q_i), q in 2^-20 units
-                            const long long tot = ((long long)(int)d2[i] << 16) + ((long long)(int)d1[i] << 8) + (long long)(int)d0[i];
-                            const float s = (float)((double)tot * (1.0 / (128.0 * 1048576.0)));
-                            orow[k] = fmaf(s, sc, orow[k]);
+                for (int k = 0; k < 64; ++k) corr[k] = (k < K) ? __ldcs(orow + k) : 0.0f;
+            }
+            mbar_wait(&bars->acc_full[t], super_it & 1);
+            tc_fence_after();
+#pragma unroll
+            for (int kb = 0; kb < 64; kb += 16) {
+                if (kb < K) {
+                    uint32_t d0[16], d1[16], d2[16];
+                    tmem_ld_x16(acc_addr + kb, d0);
+                    tmem_ld_x16(acc_addr + K + kb, d1);
+                    tmem_ld_x16(acc_addr + 2 * K + kb, d2);
+                    tmem_wait_ld();
+                    if (live) {
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) {
+                            const int k = kb + i;
+                            if (k < K) {
+                                // digits carry the A scale of 128: total = 128 * sum(q_i), q in 2^-20 units
+                                const long long tot = ((long long)(int)d2[i] << 16) + ((long long)(int)d1[i] << 8) + (long long)(int)d0[i];
+                                const float sv = (float)((double)tot * (1.0 / (128.0 * 1048576.0)));
+                                __stcs(orow + k, fmaf(sv, sc, corr[k]));
+                            }
                         }
                     }
                 }
@@ -369,9 +445,9 @@ int lg_project_raw_umma(lg_ctx* ctx, const lg_csc* m, const float* d_basis, int 
         LG_CUDA(ctx, cudaMemsetAsync(d_bm + (nsuper - 1) * nchunks * (size_t)(CELLS * BM_STRIDE), 0,
                                      (size_t)nchunks * BM_CHUNK_BYTES, ctx->stream));
     {
-        const size_t psmem = (size_t)PREP_WARPS * nchunks * (GC / 32) * 4;
+        const size_t psmem = (size_t)PREP_WARPS * nchunks * (GC / 32) * 4 + (size_t)PREP_WARPS * 2 * PREP_Q * 4;
         int per_sm = (int)(ctx->smem_optin / (psmem + 1024));
-        if (per_sm > 6) per_sm = 6;
+        if (per_sm > 4) per_sm = 4;
         if (per_sm < 1) return lg_fail(ctx, LG_ERR_INTERNAL, "k_project_prep: shared memory budget exceeded");
         uint64_t blocks = (m->ncols + PREP_WARPS - 1) / PREP_WARPS;
         const uint64_t cap = (uint64_t)ctx->num_sms * per_sm;
