@@ -85,7 +85,7 @@ __global__ void k_quantize_basis(const float* __restrict__ basis_kd, uint64_t D,
 // writes out[j*K + k] = corr_k / norm_j and scale[j] = ln2 / norm_j.
 // bitmap word w of a cell covers genes 32w..32w+31; gene offset o sits at bit (o>>2) + 8*(o&3) so that
 // the expander's (w << (7-b)) & 0x80808080 yields the four K-positions 4b..4b+3 of an MMA operand column.
-constexpr int PREP_Q = 256;  // exception queue entries per warp (>= 7 + 128)
+constexpr int PREP_Q = 256;   // exception queue entries per warp (>= 31 + 128)
 constexpr int PREP_LUT = 64;  // log1p look-up for integer counts below this
 
 template <int NACC>
@@ -100,8 +100,8 @@ __global__ void __launch_bounds__(PREP_WARPS * 32, 4) k_project_prep(const uint6
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint32_t row_words = nchunks * (GC / 32);
     uint32_t* row = rows + (size_t)warp * row_words;
-    uint32_t* qg = rows + (size_t)PREP_WARPS * row_words + warp * (2 * PREP_Q);
-    float* qw = reinterpret_cast<float*>(qg + PREP_Q);
+    uint32_t* qg = rows + (size_t)PREP_WARPS * row_words + warp * (2 * PREP_Q);  // queued gene
+    float* qv = reinterpret_cast<float*>(qg + PREP_Q);                            // queued raw value
     if (threadIdx.x < PREP_LUT) lut_x[threadIdx.x] = log1pf((float)threadIdx.x);
     __syncthreads();
     const uint64_t warp0 = (uint64_t)blockIdx.x * PREP_WARPS + warp;
@@ -113,93 +113,101 @@ __global__ void __launch_bounds__(PREP_WARPS * 32, 4) k_project_prep(const uint6
         __syncwarp();
         const uint64_t lo = indptr[j];
         const uint32_t n = (uint32_t)(indptr[j + 1] - lo);
-        const uint32_t* ip = indices + lo;
-        const float* vp = values + lo;
+        const uint32_t* ip = indices + lo + lane;
+        const float* vp = values + lo + lane;
         float acc[NACC];
 #pragma unroll
         for (int a = 0; a < NACC; ++a) acc[a] = 0.0f;
         float nsq = 0.0f;
-        uint32_t n_one = 0;              // warp-uniform count of entries equal to 1
-        uint32_t qhead = 0, qtail = 0;   // warp-uniform ring cursors of the exception queue
+        uint32_t qhead = 0, qtail = 0;  // warp-uniform ring cursors of the exception queue
 
-        // gather-accumulate `cnt` (<= 8) queued (gene, weight) pairs with all their basis loads in flight at once
+        // entries != 1 are rare in count data: they are queued raw and handled 32 at a time, one queue entry per
+        // lane for the log1p / norm part, then broadcast so that all lanes gather the basis row (lanes = dims)
         auto drain = [&](uint32_t cnt) {
-            uint32_t g[8];
-            float w[8], bv[8][NACC];
-#pragma unroll
-            for (int e = 0; e < 8; ++e) {
-                const bool on = (uint32_t)e < cnt;
-                g[e] = on ? qg[(qhead + e) & (PREP_Q - 1)] : 0u;
-                w[e] = on ? qw[(qhead + e) & (PREP_Q - 1)] : 0.0f;
+            const bool on = (uint32_t)lane < cnt;
+            const uint32_t g = on ? qg[(qhead + lane) & (PREP_Q - 1)] : 0u;
+            float w = 0.0f;
+            if (on) {
+                const float val = qv[(qhead + lane) & (PREP_Q - 1)];
+                const int vi = (int)val;
+                const float x = (val == (float)vi && vi >= 0 && vi < PREP_LUT) ? lut_x[vi] : log1pf(val);
+                nsq = fmaf(x, x, nsq);
+                w = x - ln2;
             }
+            for (uint32_t e0 = 0; e0 < cnt; e0 += 8) {
+                float bv[8][NACC], ws[8];
 #pragma unroll
-            for (int e = 0; e < 8; ++e)
+                for (int e = 0; e < 8; ++e) {
+                    const uint32_t ge = __shfl_sync(0xffffffffu, g, e0 + e);
+                    ws[e] = __shfl_sync(0xffffffffu, w, e0 + e);
+                    const float* brow = basis_kd + (size_t)ge * K + lane;
 #pragma unroll
-                for (int a = 0; a < NACC; ++a) {
-                    const int k = lane + 32 * a;
-                    bv[e][a] = (k < K) ? __ldg(basis_kd + (size_t)g[e] * K + k) : 0.0f;
+                    for (int a = 0; a < NACC; ++a) bv[e][a] = (lane + 32 * a < K) ? __ldg(brow + 32 * a) : 0.0f;
                 }
 #pragma unroll
-            for (int e = 0; e < 8; ++e)
+                for (int e = 0; e < 8; ++e)
 #pragma unroll
-                for (int a = 0; a < NACC; ++a) acc[a] = fmaf(w[e], bv[e][a], acc[a]);
+                    for (int a = 0; a < NACC; ++a) acc[a] = fmaf(ws[e], bv[e][a], acc[a]);
+            }
             qhead += cnt;
         };
+        auto consume = [&](uint32_t ixu, float vu, bool live) {
+            if (live) atomicOr(row + (ixu >> 5), 1u << (((ixu >> 2) & 7) | ((ixu & 3) << 3)));
+            const bool exc = vu != 1.0f;  // dead lanes carry 1
+            const unsigned m = __ballot_sync(0xffffffffu, exc);
+            if (m) {
+                if (exc) {
+                    const uint32_t slot = (qtail + __popc(m & lt_mask)) & (PREP_Q - 1);
+                    qg[slot] = ixu;
+                    qv[slot] = vu;
+                }
+                qtail += __popc(m);
+            }
+        };
 
+        const uint32_t nfull = n >> 7;
         uint32_t ix[4];
         float v[4];
+        if (nfull) {
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            const uint32_t t = 32 * u + lane;
-            const bool live = t < n;
-            ix[u] = live ? __ldg(ip + t) : 0xffffffffu;
-            v[u] = live ? __ldg(vp + t) : 1.0f;
+            for (int u = 0; u < 4; ++u) {
+                ix[u] = __ldg(ip + 32 * u);
+                v[u] = __ldg(vp + 32 * u);
+            }
         }
-        for (uint32_t base = 0; base < n; base += 128) {
+        for (uint32_t b = 0; b < nfull; ++b) {
             // software pipeline: the next 128 nnz are in flight while this batch is consumed
             uint32_t nix[4];
             float nv[4];
+            const uint32_t nb = (b + 1 < nfull) ? (b + 1) : b;  // last iteration re-reads its own (cached) batch
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
-                const uint32_t t = base + 128 + 32 * u + lane;
-                const bool live = t < n;
-                nix[u] = live ? __ldg(ip + t) : 0xffffffffu;
-                nv[u] = live ? __ldg(vp + t) : 1.0f;
+                nix[u] = __ldg(ip + 128 * nb + 32 * u);
+                nv[u] = __ldg(vp + 128 * nb + 32 * u);
             }
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                const bool live = ix[u] != 0xffffffffu;
-                if (live) atomicOr(row + (ix[u] >> 5), 1u << (((ix[u] >> 2) & 7) | ((ix[u] & 3) << 3)));
-                // dead lanes carry v = 1, so "not one" already implies live
-                const unsigned m = __ballot_sync(0xffffffffu, v[u] != 1.0f);
-                if (m) {
-                    if (v[u] != 1.0f) {
-                        const int vi = (int)v[u];
-                        float x;
-                        if (v[u] == (float)vi && vi >= 0 && vi < PREP_LUT) x = lut_x[vi];
-                        else x = log1pf(v[u]);
-                        nsq = fmaf(x, x, nsq);
-                        const uint32_t slot = (qtail + __popc(m & lt_mask)) & (PREP_Q - 1);
-                        qg[slot] = ix[u];
-                        qw[slot] = x - ln2;
-                    }
-                    qtail += __popc(m);
-                }
-            }
-            {   // live entries of this batch that equal 1: total live minus the exceptions just queued
-                const uint32_t nlive = min(128u, n - base);
-                n_one += nlive;
-            }
+            for (int u = 0; u < 4; ++u) consume(ix[u], v[u], true);
             __syncwarp();
-            while (qtail - qhead >= 8) drain(8);
+            while (qtail - qhead >= 32) drain(32);
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
                 ix[u] = nix[u];
                 v[u] = nv[u];
             }
         }
-        n_one -= qtail;  // every queued exception was counted as live above
-        if (qtail != qhead) drain(qtail - qhead);
+        if (n & 127) {  // ragged tail
+            const uint32_t base = nfull << 7;
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const bool live = base + 32 * u + lane < n;
+                const uint32_t ixu = live ? __ldg(ip + base + 32 * u) : 0u;
+                const float vu = live ? __ldg(vp + base + 32 * u) : 1.0f;
+                consume(ixu, vu, live);
+            }
+            __syncwarp();
+        }
+        while (qtail != qhead) drain(min(32u, qtail - qhead));
+        const uint32_t n_one = n - qtail;  // qtail counts every queued exception of this cell
         __syncwarp();
         // tiled store: (supertile, chunk) blocks of CELLS rows x BM_STRIDE words; one 256-byte chunk row per iteration
         {
