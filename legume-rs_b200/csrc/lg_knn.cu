@@ -7,7 +7,12 @@
 // tile, every lane evaluates the reference's exact f32 distance arithmetic for its own points and
 // the warp keeps a k-entry candidate list ordered by the 64-bit key (distance bits << 32 | index),
 // which is the reference's (distance, then lower index) order for non-negative distances.
+#include <cstdlib>
+
 #include "lg_common.cuh"
+
+int lg_knn_topk_umma(lg_ctx* ctx, const float* d_ref, uint64_t nr, const float* d_qry, uint64_t nq, int d, int k,
+                     const uint32_t* d_ex, uint32_t* d_idx, float* d_dist, int* used);
 
 constexpr int KNN_WARPS = 8;      // queries per CTA
 constexpr int KNN_TILE = 128;     // reference points per shared-memory tile
@@ -52,6 +57,8 @@ __device__ __forceinline__ unsigned long long warp_max_u64(unsigned long long v,
 __global__ void __launch_bounds__(KNN_WARPS * 32) k_knn_exact(const float* __restrict__ ref, uint64_t nr,
                                                               const float* __restrict__ qry, uint64_t nq, int d, int k,
                                                               const uint32_t* __restrict__ exclude,
+                                                              const uint32_t* __restrict__ qlist,
+                                                              const unsigned int* __restrict__ qcount,
                                                               uint32_t* __restrict__ out_idx, float* __restrict__ out_dist) {
     extern __shared__ unsigned char smem_raw[];
     const int ds = d | 1;  // odd row stride: lanes walking different rows hit different banks
@@ -59,8 +66,12 @@ __global__ void __launch_bounds__(KNN_WARPS * 32) k_knn_exact(const float* __res
     float* qs = tile + (size_t)KNN_TILE * ds;                               // KNN_WARPS * d
     unsigned long long* lists = reinterpret_cast<unsigned long long*>(qs + (size_t)KNN_WARPS * d + ((KNN_WARPS * d) & 1));
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const uint64_t q = (uint64_t)blockIdx.x * KNN_WARPS + warp;
-    const bool live = q < nq;
+    // optional indirection: only the queries listed in qlist[0 .. *qcount) are processed
+    const uint64_t slot = (uint64_t)blockIdx.x * KNN_WARPS + warp;
+    const uint64_t nslots = qlist ? (uint64_t)*qcount : nq;
+    if ((uint64_t)blockIdx.x * KNN_WARPS >= nslots) return;  // CTA-uniform
+    const bool live = slot < nslots;
+    const uint64_t q = live ? (qlist ? (uint64_t)qlist[slot] : slot) : 0;
     unsigned long long* mine = lists + (size_t)warp * k;
     float* myq = qs + (size_t)warp * d;
     if (live)
@@ -150,8 +161,25 @@ extern "C" int lg_knn_topk(lg_ctx* ctx, const float* ref, uint64_t nr, const flo
         const size_t smem = fl * sizeof(float) + (size_t)KNN_WARPS * k * sizeof(unsigned long long);
         LG_REQUIRE(ctx, smem <= ctx->smem_optin, "lg_knn_topk: d and k too large for shared memory");
         LG_CUDA(ctx, cudaFuncSetAttribute(k_knn_exact, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        LG_LAUNCH(ctx, k_knn_exact, (unsigned)((nq + KNN_WARPS - 1) / KNN_WARPS), KNN_WARPS * 32, smem, d_ref, nr, d_qry, nq, d, k,
-                  d_ex, d_idx, d_dist);
+        int used = 0;
+        const char* force = getenv("LG_KNN_CUDA_CORES");
+        if (!(force && force[0] == '1')) LG_TRY(lg_knn_topk_umma(ctx, d_ref, nr, d_qry, nq, d, k, d_ex, d_idx, d_dist, &used));
+        if (!used)
+            LG_LAUNCH(ctx, k_knn_exact, (unsigned)((nq + KNN_WARPS - 1) / KNN_WARPS), KNN_WARPS * 32, smem, d_ref, nr, d_qry, nq, d, k,
+                      d_ex, (const uint32_t*)nullptr, (const unsigned int*)nullptr, d_idx, d_dist);
     }
     return st.finish();
+}
+
+// brute-force pass over the queries listed in d_qlist[0 .. *d_qcount) (used by the tensor path's verified fallback)
+int lg_knn_exact_list(lg_ctx* ctx, const float* d_ref, uint64_t nr, const float* d_qry, uint64_t nq, int d, int k,
+                      const uint32_t* d_exclude, const uint32_t* d_qlist, const unsigned int* d_qcount, uint32_t* d_idx,
+                      float* d_dist) {
+    if (nq == 0) return LG_OK;
+    const size_t fl = (size_t)KNN_TILE * (d | 1) + (size_t)KNN_WARPS * d + ((KNN_WARPS * d) & 1);
+    const size_t smem = fl * sizeof(float) + (size_t)KNN_WARPS * k * sizeof(unsigned long long);
+    LG_CUDA(ctx, cudaFuncSetAttribute(k_knn_exact, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    LG_LAUNCH(ctx, k_knn_exact, (unsigned)((nq + KNN_WARPS - 1) / KNN_WARPS), KNN_WARPS * 32, smem, d_ref, nr, d_qry, nq, d, k,
+              d_exclude, d_qlist, d_qcount, d_idx, d_dist);
+    return LG_OK;
 }

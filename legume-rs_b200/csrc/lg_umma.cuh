@@ -131,6 +131,16 @@ __device__ __forceinline__ void mma_tf32_ss(uint32_t tmem_d, uint64_t desc_a, ui
         : "memory");
 }
 
+// D[tmem] (+)= A[smem] * B[smem], f16 inputs, f32 accumulate, K = 16
+__device__ __forceinline__ void mma_f16_ss(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, bool accumulate) {
+    const uint32_t acc = accumulate ? 1u : 0u;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+        "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(acc)
+        : "memory");
+}
+
 __device__ __forceinline__ bool elect_one() {
     uint32_t pred;
     asm volatile(

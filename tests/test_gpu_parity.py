@@ -411,3 +411,31 @@ def test_composite_and_staged_paths_agree(lg, ctx):
     c1 = lg.binary_sort_columns(ctx, proj, kk)
     c2 = hp.binary_codes(p2, kk).cpu().numpy().astype(np.uint64)
     assert np.array_equal(c1, c2)
+
+
+# ---- stage 6 on the tensor path (lg_knn_umma.cu): large enough to take the tcgen05 filter + exact refine ----
+@pytest.mark.parametrize("nr,nq,d,k,kind", [(20000, 3000, 50, 10, "gauss"), (9000, 6000, 32, 5, "uniform"),
+                                            (16384, 4096, 50, 12, "clustered"), (12000, 5000, 17, 10, "dupes")])
+def test_knn_tensor_path_is_exact(lg, ctx, nr, nq, d, k, kind):
+    rng = np.random.default_rng(nr + d)
+    if kind == "gauss":
+        ref = orc.project_finish(rng.normal(size=(nr, d)).astype(np.float32))
+    elif kind == "uniform":
+        ref = rng.uniform(-1, 1, size=(nr, d)).astype(np.float32)
+    elif kind == "clustered":  # near-degenerate gaps: exercises the verified fallback
+        centres = rng.normal(size=(40, d))
+        ref = (centres[rng.integers(0, 40, nr)] + 1e-4 * rng.normal(size=(nr, d))).astype(np.float32)
+    else:  # exact duplicates: ties must resolve by lower index
+        ref = rng.normal(size=(nr, d)).astype(np.float32)
+        ref[nr // 2:] = ref[: nr - nr // 2]
+    qry = ref[:nq].copy()
+    ex = np.arange(nq, dtype=np.uint32)
+    dct = lg.ColumnDict.from_dmatrix(ctx, ref, list(range(nr)))
+    idx, dist = dct.search_indices(qry, k, ex)
+    widx, wdist = orc.knn_topk(ref, qry, k, ex, nthreads=8)
+    assert np.array_equal(idx, widx), int((idx != widx).sum())
+    assert dist.tobytes() == wdist.tobytes()
+    qry2 = (qry + 0.01 * rng.normal(size=qry.shape)).astype(np.float32)
+    idx, dist = dct.search_indices(qry2, k)
+    widx, wdist = orc.knn_topk(ref, qry2, k, nthreads=8)
+    assert np.array_equal(idx, widx) and dist.tobytes() == wdist.tobytes()
