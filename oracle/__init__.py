@@ -22,9 +22,8 @@ _LIB_PATH = os.path.join(_HERE, "liblegume_oracle.so")
 
 def build(force: bool = False) -> str:
     """Compile the oracle with its committed Makefile (building the checker is not using it)."""
-    src = os.path.join(_HERE, "oracle.cpp")
-    stale = (not os.path.exists(_LIB_PATH)) or os.path.getmtime(_LIB_PATH) < max(
-        os.path.getmtime(src), os.path.getmtime(os.path.join(_HERE, "oracle.h")))
+    srcs = [os.path.join(_HERE, f) for f in ("oracle.cpp", "oracle_adjust.cpp", "oracle.h")]
+    stale = (not os.path.exists(_LIB_PATH)) or os.path.getmtime(_LIB_PATH) < max(os.path.getmtime(f) for f in srcs)
     if force or stale:
         subprocess.run(["make", "-C", _HERE], check=True, capture_output=True)
     return _LIB_PATH
@@ -60,6 +59,8 @@ def lib():
         L.orc_level_sort_dims.restype = C.c_int
         L.orc_binary_codes.restype = C.c_int
         L.orc_sim_poisson_csc.restype = C.c_uint64
+        L.orc_pb_layout.restype = C.c_uint32
+        L.orc_fine_to_coarse.restype = C.c_uint32
     return _lib
 
 
@@ -265,6 +266,107 @@ def knn_topk(ref, qry, k, exclude=None, nthreads=1):
                        C.c_int(k), _ptr(ex, C.c_uint32), _ptr(idx, C.c_uint32), _ptr(dist, C.c_float),
                        C.c_int(nthreads))
     return idx, dist
+
+
+# ---- stage 7: cross-batch neighbourhood adjustment ---------------------------------------------
+def batch_proximity(proj, batch, B):
+    """sort_batch_proximity (batch.rs:182-234): (order (B, B) uint32, centroids (B, K))"""
+    proj = np.ascontiguousarray(proj, np.float32)
+    n, K = proj.shape
+    b = np.ascontiguousarray(batch, np.uint32)
+    order = np.zeros((B, B), np.uint32)
+    cen = np.zeros((B, K), np.float32)
+    lib().orc_batch_proximity(_ptr(proj, C.c_float), C.c_int(K), C.c_uint64(n), _ptr(b, C.c_uint32), C.c_uint32(B),
+                              _ptr(order, C.c_uint32), _ptr(cen, C.c_float))
+    return order, cen
+
+
+def knn_match_batches(proj, batch, B, knn, target_order=None, nthreads=0):
+    """neighbouring_columns_triplets (matched.rs:173-260): (idx (N, nt*knn) uint32 global, dist)"""
+    proj = np.ascontiguousarray(proj, np.float32)
+    n, K = proj.shape
+    b = np.ascontiguousarray(batch, np.uint32)
+    to = None if target_order is None else np.ascontiguousarray(target_order, np.uint32)
+    nt = B if to is None else to.shape[1]
+    idx = np.zeros((n, nt * knn), np.uint32)
+    dist = np.zeros((n, nt * knn), np.float32)
+    lib().orc_knn_match_batches(_ptr(proj, C.c_float), C.c_int(K), C.c_uint64(n), _ptr(b, C.c_uint32), C.c_uint32(B),
+                                C.c_int(knn), _ptr(to, C.c_uint32), C.c_uint32(nt), _ptr(idx, C.c_uint32),
+                                _ptr(dist, C.c_float), C.c_int(nthreads))
+    return idx, dist
+
+
+def collect_matched_stat(indptr, indices, data, nrows, group_of_cell, S, matched_idx, matched_dist):
+    """collect_matched_stat_visitor (stats.rs:26-108): (imputed_sum_ds (S, D), residual_sum_ds (S, D))"""
+    indptr, indices, data = _csc(indptr, indices, data)
+    g = np.ascontiguousarray(group_of_cell, np.uint32)
+    mi = np.ascontiguousarray(matched_idx, np.uint32)
+    md = np.ascontiguousarray(matched_dist, np.float32)
+    n = len(indptr) - 1
+    imp = np.zeros((S, nrows), np.float32)
+    res = np.zeros((S, nrows), np.float32)
+    lib().orc_collect_matched_stat(_ptr(indptr, C.c_uint64), _ptr(indices, C.c_uint64), _ptr(data, C.c_float),
+                                   C.c_uint64(nrows), C.c_uint64(n), _ptr(g, C.c_uint32), C.c_uint32(S),
+                                   _ptr(mi, C.c_uint32), _ptr(md, C.c_float), C.c_uint32(mi.shape[1]),
+                                   _ptr(imp, C.c_float), _ptr(res, C.c_float))
+    return imp, res
+
+
+def pb_layout(proj, group_of_cell, S, batch_of_cell, B, mult=None):
+    """build_pb_sample_layout (pb_samples.rs:94-219): dict(cell_to_pb, pb_group, pb_batch, pb_count, centroids)"""
+    proj = np.ascontiguousarray(proj, np.float32)
+    n, K = proj.shape
+    g = np.ascontiguousarray(group_of_cell, np.uint32)
+    b = np.ascontiguousarray(batch_of_cell, np.uint32)
+    m = None if mult is None else np.ascontiguousarray(mult, np.float32)
+    c2p = np.zeros(n, np.uint32)
+    pg, pbt = np.zeros(S * B, np.uint32), np.zeros(S * B, np.uint32)
+    cnt = np.zeros(S * B, np.float32)
+    cen = np.zeros((S * B, K), np.float32)
+    npb = int(lib().orc_pb_layout(_ptr(proj, C.c_float), C.c_int(K), C.c_uint64(n), _ptr(g, C.c_uint32), C.c_uint32(S),
+                                  _ptr(b, C.c_uint32), C.c_uint32(B), _ptr(m, C.c_float), _ptr(c2p, C.c_uint32),
+                                  _ptr(pg, C.c_uint32), _ptr(pbt, C.c_uint32), _ptr(cnt, C.c_float), _ptr(cen, C.c_float)))
+    return dict(cell_to_pb=c2p, pb_group=pg[:npb].copy(), pb_batch=pbt[:npb].copy(), pb_count=cnt[:npb].copy(),
+                centroids=cen[:npb].copy(), num_pb=npb)
+
+
+def pb_match(proj, batch_of_cell, B, layout, knn, nthreads=0):
+    """per_batch_sc_neighbors (pb_samples.rs:442-459): (matched_pb (npb, B*knn) uint32, dist)"""
+    proj = np.ascontiguousarray(proj, np.float32)
+    n, K = proj.shape
+    b = np.ascontiguousarray(batch_of_cell, np.uint32)
+    npb = layout["num_pb"]
+    mp = np.zeros((npb, B * knn), np.uint32)
+    md = np.zeros((npb, B * knn), np.float32)
+    cen = np.ascontiguousarray(layout["centroids"], np.float32)
+    lib().orc_pb_match(_ptr(proj, C.c_float), C.c_int(K), C.c_uint64(n), _ptr(b, C.c_uint32), C.c_uint32(B),
+                       _ptr(layout["cell_to_pb"], C.c_uint32), _ptr(cen, C.c_float), _ptr(layout["pb_batch"], C.c_uint32),
+                       C.c_uint32(npb), C.c_int(knn), _ptr(mp, C.c_uint32), _ptr(md, C.c_float), C.c_int(nthreads))
+    return mp, md
+
+
+def collect_matched_stat_coarse(gene_sums, pb_count, pb_to_group, S, matched_pb, matched_dist):
+    """collect_matched_stat_coarse (stats.rs:698-784); gene_sums (npb, D) dense"""
+    gs = np.ascontiguousarray(gene_sums, np.float32)
+    npb, D = gs.shape
+    cnt = np.ascontiguousarray(pb_count, np.float32)
+    p2g = np.ascontiguousarray(pb_to_group, np.uint32)
+    mp = np.ascontiguousarray(matched_pb, np.uint32)
+    md = np.ascontiguousarray(matched_dist, np.float32)
+    imp = np.zeros((S, D), np.float32)
+    res = np.zeros((S, D), np.float32)
+    lib().orc_collect_matched_stat_coarse(_ptr(gs, C.c_float), C.c_uint64(D), C.c_uint32(npb), _ptr(cnt, C.c_float),
+                                          _ptr(p2g, C.c_uint32), C.c_uint32(S), _ptr(mp, C.c_uint32), _ptr(md, C.c_float),
+                                          C.c_uint32(mp.shape[1]), _ptr(imp, C.c_float), _ptr(res, C.c_float))
+    return imp, res
+
+
+def fine_to_coarse(group_code, coarse_dim):
+    """compute_fine_to_coarse_mapping (refine.rs:741-769): (fine_to_coarse uint32[nfine], num_coarse)"""
+    gc = np.ascontiguousarray(group_code, np.uint64)
+    out = np.zeros(len(gc), np.uint32)
+    k = int(lib().orc_fine_to_coarse(_ptr(gc, C.c_uint64), C.c_uint32(len(gc)), C.c_int(coarse_dim), _ptr(out, C.c_uint32)))
+    return out, k
 
 
 # ---- synthetic counts ------------------------------------------------------------------------

@@ -90,6 +90,35 @@ float orc_l2_sq(const float* a, const float* b, int d);
 void orc_knn_topk(const float* ref, uint64_t nr, const float* qry, uint64_t nq, int d, int k,
                   const uint32_t* exclude, uint32_t* out_idx, float* out_dist, int nthreads);
 
+
+/* ---- stage 7: cross-batch neighbourhood adjustment (oracle_adjust.cpp) ------
+ * per-cell path: batch.rs:182-234, matched.rs:173-260, collapse_data/stats.rs:26-108 */
+/* order: B x B, row b = all batches by distance from batch b's centroid (itself first);
+ * out_centroids (B x K... stored K-contiguous per batch) may be NULL */
+void orc_batch_proximity(const float* proj_kn, int K, uint64_t ncols, const uint32_t* batch_of_cell, uint32_t B,
+                         uint32_t* order, float* out_centroids);
+/* target_order: B x nt (row = source batch) or NULL (targets 0..nt-1); slots whose target is the
+ * source batch (or >= B) stay empty.  out_idx/out_dist: (nt*knn) x ncols, global cell indices. */
+void orc_knn_match_batches(const float* proj_kn, int K, uint64_t ncols, const uint32_t* batch_of_cell, uint32_t B,
+                           int knn, const uint32_t* target_order, uint32_t nt, uint32_t* out_idx, float* out_dist,
+                           int nthreads);
+/* imputed_sum_ds / residual_sum_ds (D x S), overwritten */
+void orc_collect_matched_stat(const uint64_t* indptr, const uint64_t* indices, const float* data, uint64_t nrows,
+                              uint64_t ncols, const uint32_t* group_of_cell, uint32_t S, const uint32_t* matched_idx,
+                              const float* matched_dist, uint32_t T, float* imputed_ds, float* residual_ds);
+/* pb-sample path: collapse_data/pb_samples.rs:94-459, stats.rs:698-784 */
+uint32_t orc_pb_layout(const float* proj_kn, int K, uint64_t ncols, const uint32_t* group_of_cell, uint32_t S,
+                       const uint32_t* batch_of_cell, uint32_t B, const float* mult, uint32_t* cell_to_pb,
+                       uint32_t* pb_group, uint32_t* pb_batch, float* pb_count, float* centroids);
+void orc_pb_match(const float* proj_kn, int K, uint64_t ncols, const uint32_t* batch_of_cell, uint32_t B,
+                  const uint32_t* cell_to_pb, const float* centroids, const uint32_t* pb_batch, uint32_t npb, int knn,
+                  uint32_t* out_pb, float* out_dist, int nthreads);
+void orc_collect_matched_stat_coarse(const float* gene_sums_dp, uint64_t nrows, uint32_t npb, const float* pb_count,
+                                     const uint32_t* pb_to_group, uint32_t S, const uint32_t* matched_pb,
+                                     const float* matched_dist, uint32_t T, float* imputed_ds, float* residual_ds);
+/* refine.rs:741-769; returns the number of coarse groups */
+uint32_t orc_fine_to_coarse(const uint64_t* group_code, uint32_t nfine, int coarse_dim, uint32_t* fine_to_coarse);
+
 /* ---- synthetic counts (data-beans-sim/src/core.rs:155-203 restated with a
  *      counter-based RNG so CPU and GPU produce identical matrices) ---------- */
 /* table entry e = ((k*B + b)*D + g): lam[e], p0[e]=exp(-lam[e]) precomputed by the caller,
