@@ -185,6 +185,60 @@ int lg_optimize_batched(lg_ctx* ctx, const float* obs_ds, const float* imp_ds, c
 int lg_knn_topk(lg_ctx* ctx, const float* ref, uint64_t nr, const float* qry, uint64_t nq, int d, int k,
                 const uint32_t* exclude, uint32_t* out_idx, float* out_dist);
 
+/* ---- stage 7: cross-batch neighbourhood adjustment ---------------------------------------------
+ * (a) per-cell path = CollapsingOps::collapse_columns with B > 1 (collapse_data/mod.rs:384-475):
+ *     batch dictionaries + sort_batch_proximity (data-beans/src/sparse_io_vector/batch.rs:100-234),
+ *     read_neighbouring_columns_csc / read_matched_columns_csc (sparse_io_vector/matched.rs:173-474),
+ *     collect_matched_stat_visitor (collapse_data/stats.rs:26-108).
+ * (b) pb-sample path = collapse_columns_multilevel_vec with B >= 2 (collapse_data/mod.rs:867-1050):
+ *     build_pb_sample_layout / per_batch_sc_neighbors (collapse_data/pb_samples.rs:94-459),
+ *     collect_matched_stat_coarse (collapse_data/stats.rs:698-784),
+ *     compute_fine_to_coarse_mapping (collapse_data/refine.rs:741-769).                          */
+
+/* sort_batch_proximity: out_order is B x B (row b = every batch by distance from batch b's centroid,
+ * b itself first); out_centroids (K x B, may be NULL) = DMatrix::column_mean of each batch's cells */
+int lg_batch_proximity(lg_ctx* ctx, const float* proj_kn, int K, uint64_t ncols, const uint32_t* batch_of_cell,
+                       uint32_t B, uint32_t* out_order, float* out_centroids);
+/* neighbouring_columns_triplets, kNN part: for source cell j of batch s and slot i < nt the target batch
+ * is target_order[s*nt + i] (NULL: nt = B, targets 0..B-1).  Slots whose target is s itself or >= B stay
+ * empty (skip_same_batch).  out_idx / out_dist: (nt*knn) x ncols; entry i*knn + r = r-th nearest cell of the
+ * target batch as a GLOBAL cell index / Euclidean distance; UINT32_MAX / +inf when absent.  The
+ * reference's knn_batches argument only sizes a Vec (matched.rs:201) and is not part of the result. */
+int lg_knn_match_batches(lg_ctx* ctx, const float* proj_kn, int K, uint64_t ncols, const uint32_t* batch_of_cell,
+                         uint32_t B, int knn, const uint32_t* target_order, uint32_t nt, uint32_t* out_idx,
+                         float* out_dist);
+/* collect_matched_stat_visitor over every group: W = softmax(-d) per source cell, y_hat = Y_matched W,
+ * y1 <- y1 / (y_hat * sum(y1)/sum(y_hat)) where y_hat > 0; imputed[:, s] += y_hat, residual[:, s] += y1.
+ * matched_idx / matched_dist: T x ncols as written by lg_knn_match_batches.  Outputs (D x S) are overwritten.
+ * Sums are accumulated in a fixed order (cells ascending inside a group): bit-identical run to run. */
+int lg_collect_matched_stat(lg_ctx* ctx, const lg_csc* m, const uint32_t* group_of_cell, uint32_t S,
+                            const uint32_t* matched_idx, const float* matched_dist, uint32_t T,
+                            float* out_imputed_ds, float* out_residual_ds);
+
+/* build_pb_sample_layout: pb-sample = non-empty (group, batch) block, numbered group-major with batches
+ * ascending inside a group.  Outputs: cell_to_pb u32[ncols]; pb_group / pb_batch / pb_count: capacity S*B;
+ * centroids K x (S*B) (mean of the block's K-vectors, summed in ascending cell order); *out_num_pb.
+ * mult = column multiplicity or NULL.  anchor / bulk batches are not supported. */
+int lg_pb_layout(lg_ctx* ctx, const float* proj_kn, int K, uint64_t ncols, const uint32_t* group_of_cell, uint32_t S,
+                 const uint32_t* batch_of_cell, uint32_t B, const float* mult, uint32_t* out_cell_to_pb,
+                 uint32_t* out_pb_group, uint32_t* out_pb_batch, float* out_pb_count, float* out_centroids,
+                 uint32_t* out_num_pb);
+/* per_batch_sc_neighbors (pooled matching): for pb-sample p and batch b != pb_batch[p], the knn nearest
+ * DISTINCT foreign pb-samples of batch b (distance of a pb-sample = its closest cell to p's centroid, which is
+ * what the adaptive 4k+1, x4 search of pb_samples.rs:337-363 converges to).  out: (B*knn) x npb. */
+int lg_pb_match(lg_ctx* ctx, const float* proj_kn, int K, uint64_t ncols, const uint32_t* batch_of_cell, uint32_t B,
+                const uint32_t* cell_to_pb, const float* centroids, const uint32_t* pb_batch, uint32_t npb, int knn,
+                uint32_t* out_matched_pb, float* out_matched_dist);
+/* collect_matched_stat_coarse.  gene_sums: D x npb dense (= lg_collapse_basic with cell_to_pb as the label).
+ * pb_to_group: layout.pb_group or a refined assignment.  Outputs (D x S) are overwritten. */
+int lg_collect_matched_stat_coarse(lg_ctx* ctx, const float* gene_sums, uint64_t D, uint32_t npb, const float* pb_count,
+                                   const uint32_t* pb_to_group, uint32_t S, const uint32_t* matched_pb,
+                                   const float* matched_dist, uint32_t T, float* out_imputed_ds,
+                                   float* out_residual_ds);
+/* compute_fine_to_coarse_mapping: coarse code = fine code & (2^coarse_dim - 1), ids by sorted unique code */
+int lg_fine_to_coarse(lg_ctx* ctx, const uint64_t* codes, const uint32_t* group_of_cell, uint64_t ncols, uint32_t nfine,
+                      int coarse_dim, uint32_t* out_fine_to_coarse, uint32_t* out_num_coarse);
+
 /* ---- synthetic counts (benchmark input; data-beans-sim/src/core.rs:155-203) --------------------
  * y[g,j] ~ Poisson(lam[(topic_j*nbatch + batch_j)*D + g]) summed over npiece pieces, kept if > 0.5.
  * topic/batch arrays cover [col_lo, col_hi).  Counter-based RNG: identical to the oracle's twin. */

@@ -1,0 +1,1052 @@
+// lg_adjust.cu — stage 7: cross-batch neighbourhood adjustment (SURVEY.md §8a rows a14–a17).
+//
+//   per-cell path (CollapsingOps::collapse_columns, B > 1; collapse_data/mod.rs:384-475)
+//     sort_batch_proximity            data-beans/src/sparse_io_vector/batch.rs:182-234
+//     neighbouring_columns_triplets   data-beans/src/sparse_io_vector/matched.rs:173-260
+//     collect_matched_stat_visitor    data-beans-alg/src/collapse_data/stats.rs:26-108
+//   pb-sample path (collapse_columns_multilevel_vec, B >= 2; collapse_data/mod.rs:867-1050)
+//     build_pb_sample_layout          collapse_data/pb_samples.rs:94-219
+//     per_batch_sc_neighbors          collapse_data/pb_samples.rs:323-459
+//     collect_matched_stat_coarse     collapse_data/stats.rs:698-784
+//     compute_fine_to_coarse_mapping  collapse_data/refine.rs:741-769
+//
+// Everything that decides an INDEX (centroids, distances, rankings) uses the reference's exact f32
+// arithmetic in the reference's order, so neighbour sets are bit-exact.  The weighted sums are
+// accumulated in a fixed order (no floating-point atomics), so results are bit-identical run to run;
+// they differ from the reference only through expf (last-bit) and stay inside the 1e-5 contract.
+#include <cub/cub.cuh>
+
+#include <algorithm>
+#include <cmath>
+#include <numeric>
+
+#include "lg_common.cuh"
+
+int lg_knn_topk_device(lg_ctx* ctx, const float* d_ref, uint64_t nr, const float* d_qry, uint64_t nq, int d, int k,
+                       const uint32_t* d_ex, uint32_t* d_idx, float* d_dist);
+
+namespace {
+
+constexpr uint32_t NONE = 0xFFFFFFFFu;
+
+// ------------------------------------------------------------------------------------------------
+// helpers shared by the host wrappers
+// ------------------------------------------------------------------------------------------------
+__global__ void k_iota(uint32_t* p, uint64_t n) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = (uint32_t)i;
+}
+__global__ void k_fill_u32(uint32_t* p, uint64_t n, uint32_t v) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = v;
+}
+__global__ void k_fill_f32(float* p, uint64_t n, float v) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = v;
+}
+__global__ void k_label_counts(const uint32_t* __restrict__ label, uint64_t n, uint32_t L, unsigned int* __restrict__ counts) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n && label[i] < L) atomicAdd(&counts[label[i]], 1u);
+}
+
+// stable sort of cell ids by a u32 label: cells stay ascending inside a label (labels >= L sort last)
+int sort_cells_by_label(lg_ctx* ctx, LgStage& st, const uint32_t* d_label, uint64_t N, uint32_t** d_lab_sorted,
+                        uint32_t** d_cell_sorted) {
+    uint32_t* d_in;
+    LG_TRY(st.scratch(N, &d_in));
+    LG_TRY(st.scratch(N, d_lab_sorted));
+    LG_TRY(st.scratch(N, d_cell_sorted));
+    if (N == 0) return LG_OK;
+    LG_LAUNCH(ctx, k_iota, (unsigned)((N + 255) / 256), 256, 0, d_in, N);
+    size_t tmp_bytes = 0;
+    LG_CUDA(ctx, cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, d_label, *d_lab_sorted, d_in, *d_cell_sorted, (int)N, 0, 32,
+                                                 ctx->stream));
+    char* d_tmp;
+    LG_TRY(st.scratch(tmp_bytes, &d_tmp));
+    LG_CUDA(ctx, cub::DeviceRadixSort::SortPairs(d_tmp, tmp_bytes, d_label, *d_lab_sorted, d_in, *d_cell_sorted, (int)N, 0, 32,
+                                                 ctx->stream));
+    ctx->launches += 4;
+    return LG_OK;
+}
+
+// per-label counts on the host (one synchronisation)
+int label_counts_host(lg_ctx* ctx, LgStage& st, const uint32_t* d_label, uint64_t N, uint32_t L, std::vector<uint32_t>& counts) {
+    counts.assign(L, 0);
+    if (L == 0 || N == 0) return LG_OK;
+    unsigned int* d_counts;
+    LG_TRY(st.scratch(L, &d_counts));
+    LG_CUDA(ctx, cudaMemsetAsync(d_counts, 0, sizeof(unsigned int) * L, ctx->stream));
+    LG_LAUNCH(ctx, k_label_counts, (unsigned)((N + 255) / 256), 256, 0, d_label, N, L, d_counts);
+    LG_CUDA(ctx, cudaMemcpyAsync(counts.data(), d_counts, sizeof(uint32_t) * L, cudaMemcpyDeviceToHost, ctx->stream));
+    LG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return LG_OK;
+}
+
+// small caller array (host or device) -> host vector
+template <typename T>
+int to_host(lg_ctx* ctx, const T* p, size_t n, std::vector<T>& out) {
+    out.resize(n);
+    if (n == 0) return LG_OK;
+    if (lg_is_device_ptr(p)) {
+        LG_CUDA(ctx, cudaMemcpyAsync(out.data(), p, sizeof(T) * n, cudaMemcpyDeviceToHost, ctx->stream));
+        LG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    } else {
+        std::copy(p, p + n, out.begin());
+    }
+    return LG_OK;
+}
+template <typename T>
+int upload(lg_ctx* ctx, LgStage& st, const std::vector<T>& h, T** d) {
+    LG_TRY(st.scratch(h.size(), d));
+    if (!h.empty()) {
+        // pageable source: the copy is staged by the runtime before the call returns
+        LG_CUDA(ctx, cudaMemcpyAsync(*d, h.data(), sizeof(T) * h.size(), cudaMemcpyHostToDevice, ctx->stream));
+        LG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    }
+    return LG_OK;
+}
+
+// knn/metric.rs:19-45 — exact f32 arithmetic of the reference's distance
+__device__ __forceinline__ float adj_l2_sq(const float* __restrict__ r, const float* __restrict__ q, int d) {
+    float acc[16];
+#pragma unroll
+    for (int l = 0; l < 16; ++l) acc[l] = 0.0f;
+    int c = 0;
+    for (; c + 16 <= d; c += 16) {
+#pragma unroll
+        for (int l = 0; l < 16; ++l) {
+            const float df = __fsub_rn(r[c + l], q[c + l]);
+            acc[l] = __fadd_rn(acc[l], __fmul_rn(df, df));
+        }
+    }
+    float sum = 0.0f;
+#pragma unroll
+    for (int l = 0; l < 16; ++l) sum = __fadd_rn(sum, acc[l]);
+    for (; c < d; ++c) {
+        const float df = __fsub_rn(r[c], q[c]);
+        sum = __fadd_rn(sum, __fmul_rn(df, df));
+    }
+    return sum;
+}
+
+// ------------------------------------------------------------------------------------------------
+// segment means in the reference's order: one block per segment, one thread per dimension, cells walked
+// in ascending order with the loads unrolled ahead of the (serial) adds
+//   MODE 0: nalgebra column_mean     acc = (1/n) * x + acc                 (batch.rs:196-205)
+//   MODE 1: pb-sample centroid       acc += x * w ; then acc * (1/count)   (pb_samples.rs:141-160)
+// ------------------------------------------------------------------------------------------------
+template <int MODE>
+__global__ void k_segment_mean(const float* __restrict__ proj, int K, const uint32_t* __restrict__ cell_sorted,
+                               const uint64_t* __restrict__ seg_off, const float* __restrict__ mult, float* __restrict__ out_mean,
+                               float* __restrict__ out_count) {
+    const uint32_t s = blockIdx.x;
+    const int k = threadIdx.x;
+    const uint64_t lo = seg_off[s], hi = seg_off[s + 1];
+    float cnt = 0.0f;
+    if (MODE == 1) {
+        // the count is a serial f32 sum of the multiplicities (every thread computes the same value)
+        for (uint64_t i = lo; i < hi; ++i) cnt = __fadd_rn(cnt, mult ? mult[cell_sorted[i]] : 1.0f);
+    }
+    if (k >= K) return;
+    const float denom = (MODE == 0) ? __fdiv_rn(1.0f, (float)(double)(hi - lo)) : 0.0f;
+    float acc = 0.0f;
+    uint64_t i = lo;
+    for (; i + 8 <= hi; i += 8) {
+        float x[8], w[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const uint32_t c = cell_sorted[i + u];
+            x[u] = proj[(size_t)c * K + k];
+            w[u] = (MODE == 1 && mult) ? mult[c] : 1.0f;
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u)
+            acc = (MODE == 0) ? __fadd_rn(__fmul_rn(denom, x[u]), acc) : __fadd_rn(acc, __fmul_rn(x[u], w[u]));
+    }
+    for (; i < hi; ++i) {
+        const uint32_t c = cell_sorted[i];
+        const float x = proj[(size_t)c * K + k];
+        const float w = (MODE == 1 && mult) ? mult[c] : 1.0f;
+        acc = (MODE == 0) ? __fadd_rn(__fmul_rn(denom, x), acc) : __fadd_rn(acc, __fmul_rn(x, w));
+    }
+    if (MODE == 1) {
+        const float inv = __fdiv_rn(1.0f, cnt);
+        acc = __fmul_rn(acc, inv);
+        if (k == 0 && out_count) out_count[s] = cnt;
+    }
+    out_mean[(size_t)s * K + k] = acc;
+}
+
+__global__ void k_gather_rows(const float* __restrict__ src, int K, const uint32_t* __restrict__ rows, uint64_t n,
+                              float* __restrict__ dst) {
+    const uint64_t e = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n * (uint64_t)K) return;
+    const uint64_t r = e / K;
+    dst[e] = src[(size_t)rows[r] * K + (e % K)];
+}
+
+// kNN results of one (target batch, query range) -> global indices in the caller's slot layout
+__global__ void k_scatter_matches(const uint32_t* __restrict__ knn_idx, const float* __restrict__ knn_dist, uint64_t nq, int knn,
+                                  uint64_t q0, uint64_t ref0, const uint32_t* __restrict__ cell_sorted,
+                                  const uint32_t* __restrict__ batch_sorted, const uint32_t* __restrict__ slot_of, uint32_t B,
+                                  uint32_t b, uint32_t T, uint32_t* __restrict__ out_idx, float* __restrict__ out_dist) {
+    const uint64_t e = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= nq * (uint64_t)knn) return;
+    const uint64_t q = e / knn;
+    const int r = (int)(e % knn);
+    const uint32_t s = batch_sorted[q0 + q];
+    if (s >= B) return;
+    const uint32_t slot = slot_of[(size_t)s * B + b];
+    if (slot == NONE) return;
+    const uint32_t c = cell_sorted[q0 + q];
+    const uint32_t local = knn_idx[e];
+    const size_t o = (size_t)c * T + (size_t)slot * knn + r;
+    out_idx[o] = local == NONE ? NONE : cell_sorted[ref0 + local];
+    out_dist[o] = knn_dist[e];
+}
+
+// ------------------------------------------------------------------------------------------------
+// collect_matched_stat_visitor
+// ------------------------------------------------------------------------------------------------
+constexpr int MS_THREADS = 1024;  // one CTA per SM (the accumulators fill shared memory)
+constexpr int MS_U = 2;           // prefetched elements per thread per matched column
+constexpr int MS_PF = 4;          // matched columns in flight
+constexpr int MS_SEG = 128;       // source cells per work item
+constexpr int MS_MAXR = 16;       // gene ranges
+
+struct MatchDesc {
+    unsigned long long lo;  // first nnz of the matched column inside this gene range
+    uint32_t n;             // nnz of the matched column inside this gene range
+    float w;                // softmax weight
+};
+
+// per cell: sum of the column, and the nnz offsets at which the row index crosses each gene-range boundary
+__global__ void k_cell_ranges(const uint64_t* __restrict__ indptr, const uint32_t* __restrict__ indices,
+                              const float* __restrict__ values, uint64_t ncols, uint32_t W, int R, float* __restrict__ colsum,
+                              uint32_t* __restrict__ split, unsigned int* __restrict__ max_part) {
+    const int lane = threadIdx.x & 31;
+    const uint64_t j = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (j >= ncols) return;
+    const uint64_t lo = indptr[j], hi = indptr[j + 1];
+    float s = 0.0f;
+    uint32_t below[MS_MAXR];
+#pragma unroll
+    for (int r = 0; r < MS_MAXR; ++r) below[r] = 0;
+    for (uint64_t t = lo + lane; t < hi; t += 32) {
+        s += values[t];
+        const uint32_t g = indices[t];
+#pragma unroll
+        for (int r = 1; r < MS_MAXR; ++r)
+            if (r < R) below[r] += (g < (uint32_t)r * W) ? 1u : 0u;
+    }
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+    uint32_t prev = 0, mx = 0;
+#pragma unroll
+    for (int r = 1; r < MS_MAXR; ++r) {
+        if (r < R) {
+            uint32_t b = below[r];
+#pragma unroll
+            for (int off = 16; off >= 1; off >>= 1) b += __shfl_xor_sync(0xffffffffu, b, off);
+            if (lane == 0) split[j * (uint64_t)(R + 1) + r] = b;
+            mx = max(mx, b - prev);
+            prev = b;
+        }
+    }
+    if (lane == 0) {
+        split[j * (uint64_t)(R + 1)] = 0;
+        split[j * (uint64_t)(R + 1) + R] = (uint32_t)(hi - lo);
+        mx = max(mx, (uint32_t)(hi - lo) - prev);
+        colsum[j] = s;
+        atomicMax(max_part, mx);
+    }
+}
+
+// per source cell (one warp): softmax(-d) over its matched columns (dmatrix_util.rs:649-671: the MIN logit is
+// subtracted), the division scale sum(y1) / sum(y_hat) (dmatrix_util.rs:145-176), and one descriptor per
+// (gene range, matched column)
+__global__ void k_match_desc(const uint64_t* __restrict__ indptr, const uint32_t* __restrict__ split, const float* __restrict__ colsum,
+                             uint64_t ncols, const uint32_t* __restrict__ midx, const float* __restrict__ mdist, uint32_t T, int R,
+                             MatchDesc* __restrict__ desc, float* __restrict__ scale) {
+    const int lane = threadIdx.x & 31;
+    const uint64_t j = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (j >= ncols) return;
+    const uint32_t* mi = midx + j * T;
+    const float* md = mdist + j * T;
+    float lmin = INFINITY;
+    for (uint32_t t = lane; t < T; t += 32)
+        if (mi[t] < ncols) lmin = fminf(lmin, -md[t]);
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) lmin = fminf(lmin, __shfl_xor_sync(0xffffffffu, lmin, off));
+    float denom = 0.0f;
+    for (uint32_t t = lane; t < T; t += 32)
+        if (mi[t] < ncols) denom += expf(-md[t] - lmin);
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) denom += __shfl_xor_sync(0xffffffffu, denom, off);
+    float dsum = 0.0f;
+    for (uint32_t t = lane; t < T; t += 32) {
+        const uint32_t m = mi[t];
+        const bool ok = m < ncols;
+        const float w = ok ? __fdiv_rn(expf(-md[t] - lmin), denom) : 0.0f;
+        if (ok) dsum += w * colsum[m];
+        for (int r = 0; r < R; ++r) {
+            MatchDesc d;
+            d.lo = 0;
+            d.n = 0;
+            d.w = w;
+            if (ok) {
+                const uint32_t a = split[m * (uint64_t)(R + 1) + r], b = split[m * (uint64_t)(R + 1) + r + 1];
+                d.lo = indptr[m] + a;
+                d.n = b - a;
+            }
+            desc[(j * R + r) * (uint64_t)T + t] = d;
+        }
+    }
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) dsum += __shfl_xor_sync(0xffffffffu, dsum, off);
+    if (lane == 0) scale[j] = dsum > 0.0f ? __fdiv_rn(colsum[j], dsum) : 1.0f;
+}
+
+// grid = (segments, gene ranges).  The CTA walks its source cells in ascending order; for each one it
+// streams the matched columns one at a time (rows are unique inside a column, so plain shared-memory
+// read-modify-writes are race-free and the accumulation order is fixed), with the next MS_PF columns'
+// loads already in flight.
+__global__ void __launch_bounds__(MS_THREADS, 1) k_matched_stat(
+    const uint64_t* __restrict__ indptr, const uint32_t* __restrict__ indices, const float* __restrict__ values,
+    const uint32_t* __restrict__ split, const uint32_t* __restrict__ cell_sorted, const uint32_t* __restrict__ seg_first,
+    const uint32_t* __restrict__ seg_len, const uint32_t* __restrict__ seg_group, const uint8_t* __restrict__ seg_single,
+    const MatchDesc* __restrict__ desc, const float* __restrict__ scale, uint32_t T, int R, uint64_t D, uint32_t W, uint32_t pmax,
+    float* __restrict__ scratch, float* __restrict__ out_imp, float* __restrict__ out_res) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float* imp = reinterpret_cast<float*>(smem_raw);
+    float* res = imp + W;
+    float* yhat = res + W;
+    float* pat_v = yhat + pmax;
+    uint32_t* pat_g = reinterpret_cast<uint32_t*>(pat_v + pmax);
+    MatchDesc* dsc = reinterpret_cast<MatchDesc*>(pat_g + pmax);  // W and pmax are multiples of 4: still 16-byte aligned
+    unsigned short* slot = reinterpret_cast<unsigned short*>(dsc + T);
+    const int tid = threadIdx.x;
+    const uint32_t seg = blockIdx.x;
+    const int r = blockIdx.y;
+    const uint32_t g0 = (uint32_t)r * W;
+    const uint32_t Wr = (uint32_t)min((uint64_t)W, D - g0);
+    for (uint32_t g = tid; g < W; g += MS_THREADS) {
+        imp[g] = 0.0f;
+        res[g] = 0.0f;
+        slot[g] = 0xFFFF;
+    }
+    const uint32_t p0 = seg_first[seg], np_cells = seg_len[seg];
+    for (uint32_t p = 0; p < np_cells; ++p) {
+        const uint32_t j = cell_sorted[p0 + p];
+        const uint64_t own_lo = indptr[j] + split[j * (uint64_t)(R + 1) + r];
+        const uint32_t own_n = split[j * (uint64_t)(R + 1) + r + 1] - split[j * (uint64_t)(R + 1) + r];
+        __syncthreads();  // previous cell fully retired (slots cleared) and, first time, the accumulators zeroed
+        for (uint32_t i = tid; i < own_n; i += MS_THREADS) {
+            const uint32_t g = indices[own_lo + i] - g0;
+            pat_g[i] = g;
+            pat_v[i] = values[own_lo + i];
+            yhat[i] = 0.0f;
+            slot[g] = (unsigned short)i;
+        }
+        for (uint32_t t = tid; t < T; t += MS_THREADS) dsc[t] = desc[((uint64_t)j * R + r) * T + t];
+        const float sc = scale[j];
+        __syncthreads();
+
+        uint32_t pg[MS_PF][MS_U];
+        float pv[MS_PF][MS_U];
+        auto issue = [&](uint32_t t, uint32_t (&g)[MS_U], float (&v)[MS_U]) {
+            const bool on = t < T;
+            const unsigned long long lo = on ? dsc[t].lo : 0ull;
+            const uint32_t n = on ? dsc[t].n : 0u;
+#pragma unroll
+            for (int u = 0; u < MS_U; ++u) {
+                const uint32_t e = tid + u * MS_THREADS;
+                g[u] = NONE;
+                v[u] = 0.0f;
+                if (e < n) {
+                    g[u] = __ldg(indices + lo + e) - g0;
+                    v[u] = __ldg(values + lo + e);
+                }
+            }
+        };
+        auto apply = [&](uint32_t g, float v, float w) {
+            const float term = __fmul_rn(w, v);
+            imp[g] = __fadd_rn(imp[g], term);
+            const unsigned short sl = slot[g];
+            if (sl != 0xFFFF) yhat[sl] = __fadd_rn(yhat[sl], term);
+        };
+#pragma unroll
+        for (int s = 0; s < MS_PF; ++s) issue(s, pg[s], pv[s]);
+        for (uint32_t t0 = 0; t0 < T; t0 += MS_PF) {
+#pragma unroll
+            for (int s = 0; s < MS_PF; ++s) {
+                const uint32_t t = t0 + s;
+                const uint32_t n = t < T ? dsc[t].n : 0u;  // CTA-uniform
+                if (n) {
+                    const float w = dsc[t].w;
+#pragma unroll
+                    for (int u = 0; u < MS_U; ++u)
+                        if (pg[s][u] != NONE) apply(pg[s][u], pv[s][u], w);
+                    const unsigned long long lo = dsc[t].lo;
+                    for (uint32_t e = tid + MS_U * MS_THREADS; e < n; e += MS_THREADS)
+                        apply(__ldg(indices + lo + e) - g0, __ldg(values + lo + e), w);
+                }
+                issue(t + MS_PF, pg[s], pv[s]);
+                if (n) __syncthreads();  // the next column may touch the same genes
+            }
+        }
+        __syncthreads();
+        for (uint32_t i = tid; i < own_n; i += MS_THREADS) {
+            const float d = yhat[i];
+            float x = pat_v[i];
+            if (d > 0.0f) x = __fdiv_rn(x, __fmul_rn(d, sc));
+            const uint32_t g = pat_g[i];
+            res[g] = __fadd_rn(res[g], x);
+            slot[g] = 0xFFFF;
+        }
+    }
+    __syncthreads();
+    float *dst_imp, *dst_res;
+    if (seg_single[seg]) {
+        dst_imp = out_imp + (size_t)seg_group[seg] * D + g0;
+        dst_res = out_res + (size_t)seg_group[seg] * D + g0;
+    } else {
+        dst_imp = scratch + ((size_t)seg * 2) * D + g0;
+        dst_res = scratch + ((size_t)seg * 2 + 1) * D + g0;
+    }
+    for (uint32_t g = tid; g < Wr; g += MS_THREADS) {
+        dst_imp[g] = imp[g];
+        dst_res[g] = res[g];
+    }
+}
+
+// groups that span several segments: partial sums added in segment order
+__global__ void k_segment_reduce(const float* __restrict__ scratch, const uint32_t* __restrict__ group_seg0, uint32_t S, uint64_t D,
+                                 float* __restrict__ out_imp, float* __restrict__ out_res) {
+    const uint64_t e = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= D * S) return;
+    const uint32_t s = (uint32_t)(e / D);
+    const uint64_t g = e % D;
+    const uint32_t a = group_seg0[s], b = group_seg0[s + 1];
+    if (b - a < 2) return;
+    float x = 0.0f, y = 0.0f;
+    for (uint32_t seg = a; seg < b; ++seg) {
+        x = __fadd_rn(x, scratch[((size_t)seg * 2) * D + g]);
+        y = __fadd_rn(y, scratch[((size_t)seg * 2 + 1) * D + g]);
+    }
+    out_imp[e] = x;
+    out_res[e] = y;
+}
+
+// ------------------------------------------------------------------------------------------------
+// pb-sample path
+// ------------------------------------------------------------------------------------------------
+__global__ void k_pair_presence(const uint32_t* __restrict__ grp, const uint32_t* __restrict__ batch, uint64_t n, uint32_t S,
+                                uint32_t B, uint32_t* __restrict__ present) {
+    const uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j < n && grp[j] < S && batch[j] < B) present[(size_t)grp[j] * B + batch[j]] = 1u;
+}
+__global__ void k_cell_to_pb(const uint32_t* __restrict__ grp, const uint32_t* __restrict__ batch, uint64_t n, uint32_t S, uint32_t B,
+                             const uint32_t* __restrict__ id, uint32_t* __restrict__ c2p) {
+    const uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j < n) c2p[j] = (grp[j] < S && batch[j] < B) ? id[(size_t)grp[j] * B + batch[j]] : NONE;
+}
+
+constexpr int PM_Q = 256;     // queries (centroids) per CTA
+constexpr int PM_CELLS = 64;  // cells of the target pb-sample per shared-memory tile
+
+// key[q - q0][p] = min over the cells c of pb-sample p of (l2_sq(centroid_q, c) << 32 | c); ~0 when p is in
+// q's own batch (which covers p == q) or empty.  The minimum key is the first cell of p met when the batch's
+// cells are walked in (distance, index) order, i.e. what the reference's growing search reports for p.
+__global__ void __launch_bounds__(PM_Q) k_pb_min_dist(const float* __restrict__ proj, int K, const uint32_t* __restrict__ cell_sorted,
+                                                      const uint64_t* __restrict__ pb_off, const float* __restrict__ centroids,
+                                                      const uint32_t* __restrict__ pb_batch, uint32_t npb, uint32_t q0, uint32_t nq,
+                                                      unsigned long long* __restrict__ keys) {
+    extern __shared__ float pm_smem[];
+    const int ds = K | 1;
+    float* qs = pm_smem;                        // PM_Q x ds
+    float* cs = pm_smem + (size_t)PM_Q * ds;    // PM_CELLS x K
+    __shared__ uint32_t cell_id[PM_CELLS];
+    const uint32_t p = blockIdx.x;
+    const uint32_t ql = blockIdx.y * PM_Q + threadIdx.x;
+    const bool live = ql < nq;
+    const uint32_t q = q0 + ql;
+    const uint32_t nq_here = min((uint32_t)PM_Q, nq - blockIdx.y * PM_Q);
+    for (uint32_t e = threadIdx.x; e < nq_here * (uint32_t)K; e += PM_Q)
+        qs[(e / K) * ds + (e % K)] = centroids[(size_t)(q0 + blockIdx.y * PM_Q) * K + e];
+    const uint32_t pbatch = pb_batch[p];
+    const bool want = live && pb_batch[q] != pbatch;
+    unsigned long long best = ~0ull;
+    const uint64_t lo = pb_off[p], hi = pb_off[p + 1];
+    for (uint64_t base = lo; base < hi; base += PM_CELLS) {
+        const int nt = (int)min((uint64_t)PM_CELLS, hi - base);
+        __syncthreads();
+        if ((int)threadIdx.x < nt) cell_id[threadIdx.x] = cell_sorted[base + threadIdx.x];
+        __syncthreads();
+        for (int e = threadIdx.x; e < nt * K; e += PM_Q) cs[e] = proj[(size_t)cell_id[e / K] * K + (e % K)];
+        __syncthreads();
+        if (want) {
+            const float* myq = qs + (size_t)threadIdx.x * ds;
+            for (int t = 0; t < nt; ++t) {
+                const float d2 = adj_l2_sq(cs + (size_t)t * K, myq, K);
+                const unsigned long long key = ((unsigned long long)__float_as_uint(d2) << 32) | cell_id[t];
+                best = key < best ? key : best;
+            }
+        }
+    }
+    if (live) keys[(size_t)ql * npb + p] = best;
+}
+
+// one warp per (query, target batch): the knn smallest keys among that batch's pb-samples, ascending
+__global__ void k_pb_topk(const unsigned long long* __restrict__ keys, uint32_t npb, uint32_t q0, uint32_t nq, uint32_t B,
+                          const uint32_t* __restrict__ batch_pb, const uint32_t* __restrict__ batch_off, int knn,
+                          uint32_t* __restrict__ out_pb, float* __restrict__ out_dist) {
+    const int lane = threadIdx.x & 31;
+    const uint64_t wid = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (wid >= (uint64_t)nq * B) return;
+    const uint32_t ql = (uint32_t)(wid / B), b = (uint32_t)(wid % B);
+    const unsigned long long* row = keys + (size_t)ql * npb;
+    const uint32_t lo = batch_off[b], hi = batch_off[b + 1];
+    unsigned long long last = 0;
+    bool first = true;
+    const size_t o = ((size_t)(q0 + ql) * B + b) * knn;
+    for (int r = 0; r < knn; ++r) {
+        unsigned long long best = ~0ull;
+        uint32_t arg = NONE;
+        for (uint32_t i = lo + lane; i < hi; i += 32) {
+            const uint32_t p = batch_pb[i];
+            const unsigned long long k = row[p];
+            if ((first || k > last) && k < best) {
+                best = k;
+                arg = p;
+            }
+        }
+#pragma unroll
+        for (int off = 16; off >= 1; off >>= 1) {
+            const unsigned long long ob = __shfl_xor_sync(0xffffffffu, best, off);
+            const uint32_t oa = __shfl_xor_sync(0xffffffffu, arg, off);
+            if (ob < best) {
+                best = ob;
+                arg = oa;
+            }
+        }
+        if (lane == 0) {
+            const bool empty = best == ~0ull;
+            out_pb[o + r] = empty ? NONE : arg;
+            out_dist[o + r] = empty ? INFINITY : __fsqrt_rn(__uint_as_float((uint32_t)(best >> 32)));
+        }
+        if (best == ~0ull) {
+            // nothing left: the remaining slots stay empty
+            if (lane == 0)
+                for (int rr = r + 1; rr < knn; ++rr) {
+                    out_pb[o + rr] = NONE;
+                    out_dist[o + rr] = INFINITY;
+                }
+            break;
+        }
+        last = best;
+        first = false;
+    }
+}
+
+// stats.rs:715-731: softmax weights (MAX of -d subtracted), one warp per pb-sample
+__global__ void k_pb_weights(const uint32_t* __restrict__ mpb, const float* __restrict__ mdist, uint32_t npb, uint32_t T,
+                             float* __restrict__ w) {
+    const int lane = threadIdx.x & 31;
+    const uint64_t p = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (p >= npb) return;
+    const uint32_t* mi = mpb + p * T;
+    const float* md = mdist + p * T;
+    float mx = -INFINITY;
+    for (uint32_t t = lane; t < T; t += 32)
+        if (mi[t] < npb) mx = fmaxf(mx, -md[t]);
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, off));
+    float sum = 0.0f;
+    for (uint32_t t = lane; t < T; t += 32)
+        if (mi[t] < npb) sum += expf(-md[t] - mx);
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, off);
+    for (uint32_t t = lane; t < T; t += 32) {
+        float x = 0.0f;
+        if (mi[t] < npb) {
+            x = expf(-md[t] - mx);
+            if (sum > 0.0f) x = __fdiv_rn(x, sum);
+        }
+        w[p * T + t] = x;
+    }
+}
+
+// stats.rs:733-779: one thread per (gene, group); the group's pb-samples are folded in ascending order
+__global__ void k_coarse_stat(const float* __restrict__ gene_sums, uint64_t D, uint32_t npb, const float* __restrict__ pb_count,
+                              const uint32_t* __restrict__ group_pb, const uint32_t* __restrict__ group_off, uint32_t S,
+                              const uint32_t* __restrict__ mpb, const float* __restrict__ w, uint32_t T, float* __restrict__ out_imp,
+                              float* __restrict__ out_res) {
+    const uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t s = blockIdx.y;
+    if (g >= D) return;
+    float imp = 0.0f, res = 0.0f;
+    for (uint32_t i = group_off[s]; i < group_off[s + 1]; ++i) {
+        const uint32_t p = group_pb[i];
+        const float cnt = pb_count[p];
+        if (cnt < 1.0f) continue;
+        float yhat = 0.0f;
+        bool present = false, any = false;
+        for (uint32_t t = 0; t < T; ++t) {
+            const uint32_t m = mpb[(size_t)p * T + t];
+            if (m >= npb) continue;
+            any = true;
+            const float mc = pb_count[m];
+            if (mc < 1.0f) continue;
+            const float gs = gene_sums[(size_t)m * D + g];
+            if (gs != 0.0f) {
+                present = true;
+                yhat = __fadd_rn(yhat, __fmul_rn(__fmul_rn(w[(size_t)p * T + t], gs), __fdiv_rn(1.0f, mc)));
+            }
+        }
+        if (!any || !present) continue;
+        imp = __fadd_rn(imp, __fmul_rn(cnt, yhat));
+        const float own = gene_sums[(size_t)p * D + g];
+        if (own != 0.0f && yhat > 0.0f) res = __fadd_rn(res, __fdiv_rn(own, yhat));
+    }
+    out_imp[(size_t)s * D + g] = imp;
+    out_res[(size_t)s * D + g] = res;
+}
+
+__global__ void k_group_code(const uint64_t* __restrict__ codes, const uint32_t* __restrict__ grp, uint64_t n, uint32_t nfine,
+                             unsigned long long* __restrict__ group_code) {
+    const uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j < n && grp[j] < nfine) group_code[grp[j]] = codes[j];  // every cell of a group carries the same code
+}
+
+}  // namespace
+
+// ====================================================================================================
+extern "C" int lg_batch_proximity(lg_ctx* ctx, const float* proj_kn, int K, uint64_t ncols, const uint32_t* batch_of_cell,
+                                  uint32_t B, uint32_t* out_order, float* out_centroids) {
+    if (!ctx) return LG_ERR_INVALID;
+    LG_REQUIRE(ctx, proj_kn && batch_of_cell && out_order, "lg_batch_proximity: null argument");
+    LG_REQUIRE(ctx, K >= 1 && K <= 1024 && B >= 1 && B <= 65535 && ncols < 0xFFFFFFFFull, "lg_batch_proximity: bad shape");
+    cudaSetDevice(ctx->device);
+    LgStage st(ctx);
+    const float* d_proj;
+    const uint32_t* d_batch;
+    LG_TRY(st.in(proj_kn, (size_t)ncols * K, &d_proj));
+    LG_TRY(st.in(batch_of_cell, (size_t)ncols, &d_batch));
+    std::vector<uint32_t> counts;
+    LG_TRY(label_counts_host(ctx, st, d_batch, ncols, B, counts));
+    std::vector<uint64_t> off(B + 1, 0);
+    for (uint32_t b = 0; b < B; ++b) off[b + 1] = off[b] + counts[b];
+    uint32_t *d_lab, *d_cell;
+    LG_TRY(sort_cells_by_label(ctx, st, d_batch, ncols, &d_lab, &d_cell));
+    uint64_t* d_off;
+    LG_TRY(upload(ctx, st, off, &d_off));
+    float* d_cen;
+    LG_TRY(st.scratch((size_t)B * K, &d_cen));
+    LG_LAUNCH(ctx, k_segment_mean<0>, B, ((K + 31) / 32) * 32, 0, d_proj, K, d_cell, d_off, (const float*)nullptr, d_cen,
+              (float*)nullptr);
+    std::vector<float> cen((size_t)B * K);
+    LG_CUDA(ctx, cudaMemcpyAsync(cen.data(), d_cen, sizeof(float) * cen.size(), cudaMemcpyDeviceToHost, ctx->stream));
+    LG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    // B x B exact scan on the host (B is tiny): search_by_query_name(b, nbatches, false)
+    std::vector<uint32_t> order((size_t)B * B);
+    std::vector<std::pair<float, uint32_t>> sc(B);
+    for (uint32_t b = 0; b < B; ++b) {
+        for (uint32_t o = 0; o < B; ++o) sc[o] = {lgh_l2_sq(&cen[(size_t)o * K], &cen[(size_t)b * K], K), o};
+        std::sort(sc.begin(), sc.end());
+        for (uint32_t o = 0; o < B; ++o) order[(size_t)b * B + o] = sc[o].second;
+    }
+    auto put = [&](void* dst, const void* src, size_t bytes) -> int {
+        LG_CUDA(ctx, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDefault, ctx->stream));
+        LG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        return LG_OK;
+    };
+    LG_TRY(put(out_order, order.data(), sizeof(uint32_t) * order.size()));
+    if (out_centroids) LG_TRY(put(out_centroids, cen.data(), sizeof(float) * cen.size()));
+    return st.finish();
+}
+
+extern "C" int lg_knn_match_batches(lg_ctx* ctx, const float* proj_kn, int K, uint64_t ncols, const uint32_t* batch_of_cell,
+                                    uint32_t B, int knn, const uint32_t* target_order, uint32_t nt, uint32_t* out_idx,
+                                    float* out_dist) {
+    if (!ctx) return LG_ERR_INVALID;
+    LG_REQUIRE(ctx, proj_kn && batch_of_cell && out_idx && out_dist, "lg_knn_match_batches: null argument");
+    LG_REQUIRE(ctx, K >= 1 && K <= 256 && knn >= 1 && knn <= 1024 && B >= 1 && B <= 65535 && ncols < 0xFFFFFFFFull,
+               "lg_knn_match_batches: bad shape");
+    if (!target_order) nt = B;
+    LG_REQUIRE(ctx, nt >= 1, "lg_knn_match_batches: no target slots");
+    cudaSetDevice(ctx->device);
+    LgStage st(ctx);
+    const uint64_t N = ncols;
+    const uint32_t T = nt * (uint32_t)knn;
+    const float* d_proj;
+    const uint32_t* d_batch;
+    uint32_t* d_oidx;
+    float* d_odist;
+    LG_TRY(st.in(proj_kn, (size_t)N * K, &d_proj));
+    LG_TRY(st.in(batch_of_cell, (size_t)N, &d_batch));
+    LG_TRY(st.out(out_idx, (size_t)N * T, &d_oidx));
+    LG_TRY(st.out(out_dist, (size_t)N * T, &d_odist));
+    if (N == 0) return st.finish();
+    // slot_of[s][b]: which output slot of a source cell of batch s holds target batch b
+    std::vector<uint32_t> slot_of((size_t)B * B, NONE);
+    {
+        std::vector<uint32_t> order;
+        if (target_order) LG_TRY(to_host(ctx, target_order, (size_t)B * nt, order));
+        for (uint32_t s = 0; s < B; ++s)
+            for (uint32_t i = 0; i < nt; ++i) {
+                const uint32_t b = target_order ? order[(size_t)s * nt + i] : i;
+                if (b < B && b != s && slot_of[(size_t)s * B + b] == NONE) slot_of[(size_t)s * B + b] = i;
+            }
+    }
+    std::vector<uint32_t> counts;
+    LG_TRY(label_counts_host(ctx, st, d_batch, N, B, counts));
+    std::vector<uint64_t> off(B + 1, 0);
+    for (uint32_t b = 0; b < B; ++b) off[b + 1] = off[b] + counts[b];
+    const uint64_t nlive = off[B];  // cells with a valid batch sort first
+    uint32_t *d_lab, *d_cell, *d_slot;
+    LG_TRY(sort_cells_by_label(ctx, st, d_batch, N, &d_lab, &d_cell));
+    LG_TRY(upload(ctx, st, slot_of, &d_slot));
+    float* d_sorted;
+    LG_TRY(st.scratch((size_t)N * K, &d_sorted));
+    LG_LAUNCH(ctx, k_gather_rows, (unsigned)(((uint64_t)N * K + 255) / 256), 256, 0, d_proj, K, d_cell, N, d_sorted);
+    LG_LAUNCH(ctx, k_fill_u32, (unsigned)(((uint64_t)N * T + 255) / 256), 256, 0, d_oidx, (uint64_t)N * T, NONE);
+    LG_LAUNCH(ctx, k_fill_f32, (unsigned)(((uint64_t)N * T + 255) / 256), 256, 0, d_odist, (uint64_t)N * T, INFINITY);
+    uint32_t* d_kidx;
+    float* d_kdist;
+    LG_TRY(st.scratch((size_t)N * knn, &d_kidx));
+    LG_TRY(st.scratch((size_t)N * knn, &d_kdist));
+    for (uint32_t b = 0; b < B; ++b) {
+        const uint64_t nb = counts[b];
+        if (nb == 0) continue;
+        bool wanted = false;
+        for (uint32_t s = 0; s < B && !wanted; ++s) wanted = slot_of[(size_t)s * B + b] != NONE && counts[s] > 0;
+        if (!wanted) continue;
+        // queries: every cell outside batch b = the two ranges around it in batch-sorted order
+        const uint64_t ranges[2][2] = {{0, off[b]}, {off[b + 1], nlive}};
+        for (int h = 0; h < 2; ++h) {
+            const uint64_t q0 = ranges[h][0], nq = ranges[h][1] - ranges[h][0];
+            if (nq == 0) continue;
+            LG_TRY(lg_knn_topk_device(ctx, d_sorted + off[b] * K, nb, d_sorted + q0 * K, nq, K, knn, nullptr, d_kidx, d_kdist));
+            LG_LAUNCH(ctx, k_scatter_matches, (unsigned)((nq * knn + 255) / 256), 256, 0, d_kidx, d_kdist, nq, knn, q0, off[b], d_cell,
+                      d_lab, d_slot, B, b, T, d_oidx, d_odist);
+        }
+    }
+    return st.finish();
+}
+
+extern "C" int lg_collect_matched_stat(lg_ctx* ctx, const lg_csc* m, const uint32_t* group_of_cell, uint32_t S,
+                                       const uint32_t* matched_idx, const float* matched_dist, uint32_t T, float* out_imputed_ds,
+                                       float* out_residual_ds) {
+    if (!ctx) return LG_ERR_INVALID;
+    LG_REQUIRE(ctx, m && group_of_cell && matched_idx && matched_dist && out_imputed_ds && out_residual_ds,
+               "lg_collect_matched_stat: null argument");
+    LG_REQUIRE(ctx, T >= 1 && T <= 4096 && S >= 1, "lg_collect_matched_stat: T must be in [1, 4096] and S >= 1");
+    cudaSetDevice(ctx->device);
+    LgStage st(ctx);
+    const uint64_t N = m->ncols, D = m->nrows;
+    LG_REQUIRE(ctx, N < 0xFFFFFFFFull, "lg_collect_matched_stat: more than 2^32-1 cells in one block");
+    const uint32_t* d_group;
+    const uint32_t* d_midx;
+    const float* d_mdist;
+    float *d_imp, *d_res;
+    LG_TRY(st.in(group_of_cell, (size_t)N, &d_group));
+    LG_TRY(st.in(matched_idx, (size_t)N * T, &d_midx));
+    LG_TRY(st.in(matched_dist, (size_t)N * T, &d_mdist));
+    LG_TRY(st.out(out_imputed_ds, (size_t)D * S, &d_imp));
+    LG_TRY(st.out(out_residual_ds, (size_t)D * S, &d_res));
+    LG_CUDA(ctx, cudaMemsetAsync(d_imp, 0, sizeof(float) * (size_t)D * S, ctx->stream));
+    LG_CUDA(ctx, cudaMemsetAsync(d_res, 0, sizeof(float) * (size_t)D * S, ctx->stream));
+    if (N == 0 || D == 0) return st.finish();
+
+    // gene ranges: per range two f32 accumulators + a u16 slot map (10 B per gene) next to the per-cell pattern
+    // buffers (12 B per own nnz) and the T descriptors
+    const size_t budget = ctx->smem_optin - 2048 - (size_t)T * sizeof(MatchDesc);
+    int R = 1;
+    uint32_t W = (uint32_t)D, pmax = 0;
+    float* d_colsum;
+    uint32_t* d_split = nullptr;
+    unsigned int* d_maxpart;
+    LG_TRY(st.scratch(N, &d_colsum));
+    LG_TRY(st.scratch(1, &d_maxpart));
+    for (;; ++R) {
+        LG_REQUIRE(ctx, R <= MS_MAXR, "lg_collect_matched_stat: too many genes for the shared-memory accumulators");
+        W = (uint32_t)((D + R - 1) / R);
+        W = (W + 3) & ~3u;
+        if ((size_t)W * 10 + 64 > budget) continue;
+        LG_TRY(st.scratch((size_t)N * (R + 1), &d_split));
+        LG_CUDA(ctx, cudaMemsetAsync(d_maxpart, 0, sizeof(unsigned int), ctx->stream));
+        LG_LAUNCH(ctx, k_cell_ranges, (unsigned)((N * 32 + 255) / 256), 256, 0, m->indptr, m->indices, m->values, N, W, R, d_colsum,
+                  d_split, d_maxpart);
+        unsigned int* h = static_cast<unsigned int*>(ctx->pinned);
+        LG_CUDA(ctx, cudaMemcpyAsync(h, d_maxpart, sizeof(unsigned int), cudaMemcpyDeviceToHost, ctx->stream));
+        LG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        pmax = (*h + 3) & ~3u;
+        if (pmax < 4) pmax = 4;
+        if ((size_t)W * 10 + (size_t)pmax * 12 + 64 <= budget) break;
+    }
+    LG_REQUIRE(ctx, pmax < 65535, "lg_collect_matched_stat: a column holds more than 65534 entries in one gene range");
+    const size_t smem = (size_t)W * 10 + (size_t)pmax * 12 + (size_t)T * sizeof(MatchDesc) + 64;
+
+    // segments of at most MS_SEG group-sorted cells, never crossing a group boundary
+    std::vector<uint32_t> counts;
+    LG_TRY(label_counts_host(ctx, st, d_group, N, S, counts));
+    std::vector<uint32_t> seg_first, seg_len, seg_group, group_seg0(S + 1, 0);
+    std::vector<uint8_t> seg_single;
+    {
+        uint64_t pos = 0;
+        for (uint32_t s = 0; s < S; ++s) {
+            group_seg0[s] = (uint32_t)seg_first.size();
+            const uint32_t nseg = (counts[s] + MS_SEG - 1) / MS_SEG;
+            for (uint32_t i = 0; i < nseg; ++i) {
+                seg_first.push_back((uint32_t)(pos + (uint64_t)i * MS_SEG));
+                seg_len.push_back(std::min<uint32_t>(MS_SEG, counts[s] - i * MS_SEG));
+                seg_group.push_back(s);
+                seg_single.push_back(nseg == 1);
+            }
+            pos += counts[s];
+        }
+        group_seg0[S] = (uint32_t)seg_first.size();
+    }
+    const uint32_t nseg = (uint32_t)seg_first.size();
+    if (nseg == 0) return st.finish();
+    uint32_t *d_lab, *d_cell, *d_seg_first, *d_seg_len, *d_seg_group, *d_group_seg0;
+    uint8_t* d_seg_single;
+    LG_TRY(sort_cells_by_label(ctx, st, d_group, N, &d_lab, &d_cell));
+    LG_TRY(upload(ctx, st, seg_first, &d_seg_first));
+    LG_TRY(upload(ctx, st, seg_len, &d_seg_len));
+    LG_TRY(upload(ctx, st, seg_group, &d_seg_group));
+    LG_TRY(upload(ctx, st, seg_single, &d_seg_single));
+    LG_TRY(upload(ctx, st, group_seg0, &d_group_seg0));
+    MatchDesc* d_desc;
+    float *d_scale, *d_scratch;
+    LG_TRY(st.scratch((size_t)N * R * T, &d_desc));
+    LG_TRY(st.scratch(N, &d_scale));
+    const bool multi = std::any_of(seg_single.begin(), seg_single.end(), [](uint8_t x) { return x == 0; });
+    LG_TRY(st.scratch(multi ? (size_t)nseg * 2 * D : 1, &d_scratch));
+    LG_LAUNCH(ctx, k_match_desc, (unsigned)((N * 32 + 255) / 256), 256, 0, m->indptr, d_split, d_colsum, N, d_midx, d_mdist, T, R,
+              d_desc, d_scale);
+    LG_CUDA(ctx, cudaFuncSetAttribute(k_matched_stat, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    {
+        dim3 grid(nseg, (unsigned)R);
+        k_matched_stat<<<grid, MS_THREADS, smem, ctx->stream>>>(m->indptr, m->indices, m->values, d_split, d_cell, d_seg_first, d_seg_len,
+                                                               d_seg_group, d_seg_single, d_desc, d_scale, T, R, D, W, pmax, d_scratch,
+                                                               d_imp, d_res);
+        ctx->launches++;
+        LG_CUDA(ctx, cudaGetLastError());
+    }
+    if (multi) LG_LAUNCH(ctx, k_segment_reduce, (unsigned)((D * S + 255) / 256), 256, 0, d_scratch, d_group_seg0, S, D, d_imp, d_res);
+    return st.finish();
+}
+
+extern "C" int lg_pb_layout(lg_ctx* ctx, const float* proj_kn, int K, uint64_t ncols, const uint32_t* group_of_cell, uint32_t S,
+                            const uint32_t* batch_of_cell, uint32_t B, const float* mult, uint32_t* out_cell_to_pb,
+                            uint32_t* out_pb_group, uint32_t* out_pb_batch, float* out_pb_count, float* out_centroids,
+                            uint32_t* out_num_pb) {
+    if (!ctx) return LG_ERR_INVALID;
+    LG_REQUIRE(ctx, proj_kn && group_of_cell && batch_of_cell && out_cell_to_pb && out_pb_group && out_pb_batch && out_pb_count &&
+                        out_centroids && out_num_pb,
+               "lg_pb_layout: null argument");
+    LG_REQUIRE(ctx, K >= 1 && K <= 1024 && S >= 1 && B >= 1 && (uint64_t)S * B < 0x7FFFFFFFull && ncols < 0xFFFFFFFFull,
+               "lg_pb_layout: bad shape");
+    cudaSetDevice(ctx->device);
+    LgStage st(ctx);
+    const uint64_t N = ncols;
+    const size_t cap = (size_t)S * B;
+    const float *d_proj, *d_mult;
+    const uint32_t *d_group, *d_batch;
+    uint32_t *d_c2p, *d_pg, *d_pb;
+    float *d_cnt, *d_cen;
+    LG_TRY(st.in(proj_kn, (size_t)N * K, &d_proj));
+    LG_TRY(st.in(group_of_cell, (size_t)N, &d_group));
+    LG_TRY(st.in(batch_of_cell, (size_t)N, &d_batch));
+    LG_TRY(st.in(mult, (size_t)N, &d_mult));
+    LG_TRY(st.out(out_cell_to_pb, (size_t)N, &d_c2p));
+    LG_TRY(st.out(out_pb_group, cap, &d_pg));
+    LG_TRY(st.out(out_pb_batch, cap, &d_pb));
+    LG_TRY(st.out(out_pb_count, cap, &d_cnt));
+    LG_TRY(st.out(out_centroids, cap * K, &d_cen));
+    uint32_t* d_present;
+    LG_TRY(st.scratch(cap, &d_present));
+    LG_CUDA(ctx, cudaMemsetAsync(d_present, 0, sizeof(uint32_t) * cap, ctx->stream));
+    LG_CUDA(ctx, cudaMemsetAsync(d_pg, 0, sizeof(uint32_t) * cap, ctx->stream));
+    LG_CUDA(ctx, cudaMemsetAsync(d_pb, 0, sizeof(uint32_t) * cap, ctx->stream));
+    LG_CUDA(ctx, cudaMemsetAsync(d_cnt, 0, sizeof(float) * cap, ctx->stream));
+    LG_CUDA(ctx, cudaMemsetAsync(d_cen, 0, sizeof(float) * cap * K, ctx->stream));
+    if (N) LG_LAUNCH(ctx, k_pair_presence, (unsigned)((N + 255) / 256), 256, 0, d_group, d_batch, N, S, B, d_present);
+    std::vector<uint32_t> present(cap);
+    LG_CUDA(ctx, cudaMemcpyAsync(present.data(), d_present, sizeof(uint32_t) * cap, cudaMemcpyDeviceToHost, ctx->stream));
+    LG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    std::vector<uint32_t> id(cap, NONE), pg, pb;
+    for (size_t e = 0; e < cap; ++e)
+        if (present[e]) {
+            id[e] = (uint32_t)pg.size();
+            pg.push_back((uint32_t)(e / B));
+            pb.push_back((uint32_t)(e % B));
+        }
+    const uint32_t npb = (uint32_t)pg.size();
+    *out_num_pb = npb;
+    if (npb == 0) return lg_fail(ctx, LG_ERR_INVALID, "lg_pb_layout: no pb-samples built");  // pb_samples.rs:179-181
+    uint32_t* d_id;
+    LG_TRY(upload(ctx, st, id, &d_id));
+    LG_CUDA(ctx, cudaMemcpyAsync(d_pg, pg.data(), sizeof(uint32_t) * npb, cudaMemcpyHostToDevice, ctx->stream));
+    LG_CUDA(ctx, cudaMemcpyAsync(d_pb, pb.data(), sizeof(uint32_t) * npb, cudaMemcpyHostToDevice, ctx->stream));
+    LG_LAUNCH(ctx, k_cell_to_pb, (unsigned)((N + 255) / 256), 256, 0, d_group, d_batch, N, S, B, d_id, d_c2p);
+    std::vector<uint32_t> counts;
+    LG_TRY(label_counts_host(ctx, st, d_c2p, N, npb, counts));  // also orders the two small copies above
+    std::vector<uint64_t> off(npb + 1, 0);
+    for (uint32_t p = 0; p < npb; ++p) off[p + 1] = off[p] + counts[p];
+    uint32_t *d_lab, *d_cell;
+    uint64_t* d_off;
+    LG_TRY(sort_cells_by_label(ctx, st, d_c2p, N, &d_lab, &d_cell));
+    LG_TRY(upload(ctx, st, off, &d_off));
+    LG_LAUNCH(ctx, k_segment_mean<1>, npb, ((K + 31) / 32) * 32, 0, d_proj, K, d_cell, d_off, d_mult, d_cen, d_cnt);
+    return st.finish();
+}
+
+extern "C" int lg_pb_match(lg_ctx* ctx, const float* proj_kn, int K, uint64_t ncols, const uint32_t* batch_of_cell, uint32_t B,
+                           const uint32_t* cell_to_pb, const float* centroids, const uint32_t* pb_batch, uint32_t npb, int knn,
+                           uint32_t* out_matched_pb, float* out_matched_dist) {
+    if (!ctx) return LG_ERR_INVALID;
+    LG_REQUIRE(ctx, proj_kn && batch_of_cell && cell_to_pb && centroids && pb_batch && out_matched_pb && out_matched_dist,
+               "lg_pb_match: null argument");
+    LG_REQUIRE(ctx, K >= 1 && K <= 256 && knn >= 1 && B >= 1 && npb >= 1 && ncols < 0xFFFFFFFFull, "lg_pb_match: bad shape");
+    cudaSetDevice(ctx->device);
+    LgStage st(ctx);
+    const uint64_t N = ncols;
+    const uint32_t T = B * (uint32_t)knn;
+    const float *d_proj, *d_cen;
+    const uint32_t *d_c2p, *d_pbb;
+    uint32_t* d_mpb;
+    float* d_md;
+    (void)batch_of_cell;  // a cell's batch is its pb-sample's batch
+    LG_TRY(st.in(proj_kn, (size_t)N * K, &d_proj));
+    LG_TRY(st.in(cell_to_pb, (size_t)N, &d_c2p));
+    LG_TRY(st.in(centroids, (size_t)npb * K, &d_cen));
+    LG_TRY(st.in(pb_batch, (size_t)npb, &d_pbb));
+    LG_TRY(st.out(out_matched_pb, (size_t)npb * T, &d_mpb));
+    LG_TRY(st.out(out_matched_dist, (size_t)npb * T, &d_md));
+    std::vector<uint32_t> pbb;
+    LG_TRY(to_host(ctx, pb_batch, npb, pbb));
+    std::vector<uint32_t> batch_off(B + 1, 0), batch_pb(npb);
+    for (uint32_t p = 0; p < npb; ++p) {
+        LG_REQUIRE(ctx, pbb[p] < B, "lg_pb_match: pb_batch out of range");
+        batch_off[pbb[p] + 1]++;
+    }
+    for (uint32_t b = 0; b < B; ++b) batch_off[b + 1] += batch_off[b];
+    {
+        std::vector<uint32_t> cur(batch_off.begin(), batch_off.end() - 1);
+        for (uint32_t p = 0; p < npb; ++p) batch_pb[cur[pbb[p]]++] = p;
+    }
+    std::vector<uint32_t> counts;
+    LG_TRY(label_counts_host(ctx, st, d_c2p, N, npb, counts));
+    std::vector<uint64_t> off(npb + 1, 0);
+    for (uint32_t p = 0; p < npb; ++p) off[p + 1] = off[p] + counts[p];
+    uint32_t *d_lab, *d_cell, *d_batch_pb, *d_batch_off;
+    uint64_t* d_off;
+    LG_TRY(sort_cells_by_label(ctx, st, d_c2p, N, &d_lab, &d_cell));
+    LG_TRY(upload(ctx, st, off, &d_off));
+    LG_TRY(upload(ctx, st, batch_pb, &d_batch_pb));
+    LG_TRY(upload(ctx, st, batch_off, &d_batch_off));
+    // query chunks keep the key matrix below ~2 GiB
+    uint32_t QC = (uint32_t)std::min<uint64_t>(npb, std::max<uint64_t>(PM_Q, ((uint64_t)1 << 28) / npb));
+    QC = ((QC + PM_Q - 1) / PM_Q) * PM_Q;
+    unsigned long long* d_keys;
+    LG_TRY(st.scratch((size_t)QC * npb, &d_keys));
+    const size_t smem = ((size_t)PM_Q * (K | 1) + (size_t)PM_CELLS * K) * sizeof(float);
+    LG_REQUIRE(ctx, smem <= ctx->smem_optin, "lg_pb_match: K too large for shared memory");
+    LG_CUDA(ctx, cudaFuncSetAttribute(k_pb_min_dist, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    for (uint32_t q0 = 0; q0 < npb; q0 += QC) {
+        const uint32_t nq = std::min(QC, npb - q0);
+        dim3 grid(npb, (nq + PM_Q - 1) / PM_Q);
+        k_pb_min_dist<<<grid, PM_Q, smem, ctx->stream>>>(d_proj, K, d_cell, d_off, d_cen, d_pbb, npb, q0, nq, d_keys);
+        ctx->launches++;
+        LG_CUDA(ctx, cudaGetLastError());
+        LG_LAUNCH(ctx, k_pb_topk, (unsigned)(((uint64_t)nq * B * 32 + 255) / 256), 256, 0, d_keys, npb, q0, nq, B, d_batch_pb, d_batch_off,
+                  knn, d_mpb, d_md);
+    }
+    return st.finish();
+}
+
+extern "C" int lg_collect_matched_stat_coarse(lg_ctx* ctx, const float* gene_sums, uint64_t D, uint32_t npb, const float* pb_count,
+                                              const uint32_t* pb_to_group, uint32_t S, const uint32_t* matched_pb,
+                                              const float* matched_dist, uint32_t T, float* out_imputed_ds, float* out_residual_ds) {
+    if (!ctx) return LG_ERR_INVALID;
+    LG_REQUIRE(ctx, gene_sums && pb_count && pb_to_group && matched_pb && matched_dist && out_imputed_ds && out_residual_ds,
+               "lg_collect_matched_stat_coarse: null argument");
+    LG_REQUIRE(ctx, npb >= 1 && S >= 1 && S <= 65535 && T >= 1, "lg_collect_matched_stat_coarse: bad shape");
+    cudaSetDevice(ctx->device);
+    LgStage st(ctx);
+    const float *d_gs, *d_cnt, *d_md;
+    const uint32_t* d_mpb;
+    float *d_imp, *d_res;
+    LG_TRY(st.in(gene_sums, (size_t)D * npb, &d_gs));
+    LG_TRY(st.in(pb_count, (size_t)npb, &d_cnt));
+    LG_TRY(st.in(matched_pb, (size_t)npb * T, &d_mpb));
+    LG_TRY(st.in(matched_dist, (size_t)npb * T, &d_md));
+    LG_TRY(st.out(out_imputed_ds, (size_t)D * S, &d_imp));
+    LG_TRY(st.out(out_residual_ds, (size_t)D * S, &d_res));
+    std::vector<uint32_t> p2g;
+    LG_TRY(to_host(ctx, pb_to_group, npb, p2g));
+    std::vector<uint32_t> group_off(S + 1, 0), group_pb(npb);
+    uint32_t kept = 0;
+    for (uint32_t p = 0; p < npb; ++p)
+        if (p2g[p] < S) {
+            group_off[p2g[p] + 1]++;
+            ++kept;
+        }
+    for (uint32_t s = 0; s < S; ++s) group_off[s + 1] += group_off[s];
+    {
+        std::vector<uint32_t> cur(group_off.begin(), group_off.end() - 1);
+        for (uint32_t p = 0; p < npb; ++p)
+            if (p2g[p] < S) group_pb[cur[p2g[p]]++] = p;
+    }
+    (void)kept;
+    uint32_t *d_group_pb, *d_group_off;
+    float* d_w;
+    LG_TRY(upload(ctx, st, group_pb, &d_group_pb));
+    LG_TRY(upload(ctx, st, group_off, &d_group_off));
+    LG_TRY(st.scratch((size_t)npb * T, &d_w));
+    LG_LAUNCH(ctx, k_pb_weights, (unsigned)(((uint64_t)npb * 32 + 255) / 256), 256, 0, d_mpb, d_md, npb, T, d_w);
+    if (D) {
+        dim3 grid((unsigned)((D + 255) / 256), S);
+        k_coarse_stat<<<grid, 256, 0, ctx->stream>>>(d_gs, D, npb, d_cnt, d_group_pb, d_group_off, S, d_mpb, d_w, T, d_imp, d_res);
+        ctx->launches++;
+        LG_CUDA(ctx, cudaGetLastError());
+    }
+    return st.finish();
+}
+
+extern "C" int lg_fine_to_coarse(lg_ctx* ctx, const uint64_t* codes, const uint32_t* group_of_cell, uint64_t ncols, uint32_t nfine,
+                                 int coarse_dim, uint32_t* out_fine_to_coarse, uint32_t* out_num_coarse) {
+    if (!ctx) return LG_ERR_INVALID;
+    LG_REQUIRE(ctx, codes && group_of_cell && out_fine_to_coarse && out_num_coarse, "lg_fine_to_coarse: null argument");
+    LG_REQUIRE(ctx, coarse_dim >= 0 && nfine >= 1, "lg_fine_to_coarse: bad shape");
+    cudaSetDevice(ctx->device);
+    LgStage st(ctx);
+    const uint64_t* d_codes;
+    const uint32_t* d_group;
+    LG_TRY(st.in(codes, (size_t)ncols, &d_codes));
+    LG_TRY(st.in(group_of_cell, (size_t)ncols, &d_group));
+    unsigned long long* d_gc;
+    LG_TRY(st.scratch(nfine, &d_gc));
+    LG_CUDA(ctx, cudaMemsetAsync(d_gc, 0xFF, sizeof(unsigned long long) * nfine, ctx->stream));
+    if (ncols) LG_LAUNCH(ctx, k_group_code, (unsigned)((ncols + 255) / 256), 256, 0, d_codes, d_group, ncols, nfine, d_gc);
+    std::vector<unsigned long long> gc(nfine);
+    LG_CUDA(ctx, cudaMemcpyAsync(gc.data(), d_gc, sizeof(unsigned long long) * nfine, cudaMemcpyDeviceToHost, ctx->stream));
+    LG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    const unsigned long long mask = coarse_dim >= 64 ? ~0ull : ((1ull << coarse_dim) - 1ull);
+    std::vector<unsigned long long> uniq(nfine);
+    for (uint32_t f = 0; f < nfine; ++f) {
+        LG_REQUIRE(ctx, gc[f] != ~0ull, "lg_fine_to_coarse: a fine group has no cells");
+        uniq[f] = gc[f] & mask;
+    }
+    std::sort(uniq.begin(), uniq.end());
+    uniq.erase(std::unique(uniq.begin(), uniq.end()), uniq.end());
+    std::vector<uint32_t> f2c(nfine);
+    for (uint32_t f = 0; f < nfine; ++f) f2c[f] = (uint32_t)(std::lower_bound(uniq.begin(), uniq.end(), gc[f] & mask) - uniq.begin());
+    *out_num_coarse = (uint32_t)uniq.size();
+    LG_CUDA(ctx, cudaMemcpyAsync(out_fine_to_coarse, f2c.data(), sizeof(uint32_t) * nfine, cudaMemcpyDefault, ctx->stream));
+    LG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return st.finish();
+}

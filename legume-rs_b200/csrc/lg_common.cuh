@@ -180,3 +180,4 @@ __device__ __forceinline__ double lg_block_sum_1024(double v, double* smem32) {
 // host-side small dense math (lg_hostmath.cpp) — plain C++, no CUDA, no oracle
 void lgh_householder_q(const float* a_kr, int K, int r, float* q_kr);
 void lgh_jacobi_eig(const double* g, int n, double* evals, double* evecs);
+float lgh_l2_sq(const float* a, const float* b, int d);

@@ -117,3 +117,23 @@ void lgh_jacobi_eig(const double* g, int n, double* evals, double* evecs) {
         for (int i = 0; i < n; ++i) evecs[(size_t)k * n + i] = v(i, order[k]);
     }
 }
+
+// knn/metric.rs:19-45 on the host (used for the B x B batch-centroid proximity, batch.rs:182-234):
+// 16 lane accumulators, left fold, sequential tail.  Compiled with -ffp-contract=off.
+float lgh_l2_sq(const float* a, const float* b, int d) {
+    float acc[16];
+    for (int l = 0; l < 16; ++l) acc[l] = 0.0f;
+    int c = 0;
+    for (; c + 16 <= d; c += 16)
+        for (int l = 0; l < 16; ++l) {
+            const float df = a[c + l] - b[c + l];
+            acc[l] += df * df;
+        }
+    float sum = 0.0f;
+    for (int l = 0; l < 16; ++l) sum += acc[l];
+    for (; c < d; ++c) {
+        const float df = a[c] - b[c];
+        sum += df * df;
+    }
+    return sum;
+}

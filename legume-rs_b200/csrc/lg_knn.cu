@@ -138,13 +138,33 @@ __global__ void __launch_bounds__(KNN_WARPS * 32) k_knn_exact(const float* __res
     }
 }
 
+// device-pointer core shared by lg_knn_topk and the cross-batch matching of lg_adjust.cu:
+// tensor-core filter + exact refine when applicable, else the CUDA-core kernel.  Same result either way.
+int lg_knn_topk_device(lg_ctx* ctx, const float* d_ref, uint64_t nr, const float* d_qry, uint64_t nq, int d, int k,
+                       const uint32_t* d_ex, uint32_t* d_idx, float* d_dist) {
+    LG_REQUIRE(ctx, d >= 1 && d <= 256, "lg_knn_topk: d must be in [1, 256]");
+    LG_REQUIRE(ctx, k >= 1 && k <= KNN_KMAX, "lg_knn_topk: k must be in [1, 1024]");
+    LG_REQUIRE(ctx, nr < 0xFFFFFFFFull, "lg_knn_topk: reference set must have < 2^32-1 points");
+    if (nq == 0) return LG_OK;
+    const size_t fl = (size_t)KNN_TILE * (d | 1) + (size_t)KNN_WARPS * d + ((KNN_WARPS * d) & 1);
+    const size_t smem = fl * sizeof(float) + (size_t)KNN_WARPS * k * sizeof(unsigned long long);
+    LG_REQUIRE(ctx, smem <= ctx->smem_optin, "lg_knn_topk: d and k too large for shared memory");
+    LG_CUDA(ctx, cudaFuncSetAttribute(k_knn_exact, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int used = 0;
+    const char* force = getenv("LG_KNN_CUDA_CORES");
+    if (!(force && force[0] == '1')) LG_TRY(lg_knn_topk_umma(ctx, d_ref, nr, d_qry, nq, d, k, d_ex, d_idx, d_dist, &used));
+    if (!used)
+        LG_LAUNCH(ctx, k_knn_exact, (unsigned)((nq + KNN_WARPS - 1) / KNN_WARPS), KNN_WARPS * 32, smem, d_ref, nr, d_qry, nq, d, k,
+                  d_ex, (const uint32_t*)nullptr, (const unsigned int*)nullptr, d_idx, d_dist);
+    return LG_OK;
+}
+
 extern "C" int lg_knn_topk(lg_ctx* ctx, const float* ref, uint64_t nr, const float* qry, uint64_t nq, int d, int k,
                            const uint32_t* exclude, uint32_t* out_idx, float* out_dist) {
     if (!ctx) return LG_ERR_INVALID;
     LG_REQUIRE(ctx, qry && out_idx && out_dist && (ref || nr == 0), "lg_knn_topk: null argument");
     LG_REQUIRE(ctx, d >= 1 && d <= 256, "lg_knn_topk: d must be in [1, 256]");
     LG_REQUIRE(ctx, k >= 1 && k <= KNN_KMAX, "lg_knn_topk: k must be in [1, 1024]");
-    LG_REQUIRE(ctx, nr < 0xFFFFFFFFull, "lg_knn_topk: reference set must have < 2^32-1 points");
     cudaSetDevice(ctx->device);
     LgStage st(ctx);
     const float *d_ref, *d_qry;
@@ -156,18 +176,7 @@ extern "C" int lg_knn_topk(lg_ctx* ctx, const float* ref, uint64_t nr, const flo
     LG_TRY(st.in(exclude, (size_t)nq, &d_ex));
     LG_TRY(st.out(out_idx, (size_t)nq * k, &d_idx));
     LG_TRY(st.out(out_dist, (size_t)nq * k, &d_dist));
-    if (nq) {
-        const size_t fl = (size_t)KNN_TILE * (d | 1) + (size_t)KNN_WARPS * d + ((KNN_WARPS * d) & 1);
-        const size_t smem = fl * sizeof(float) + (size_t)KNN_WARPS * k * sizeof(unsigned long long);
-        LG_REQUIRE(ctx, smem <= ctx->smem_optin, "lg_knn_topk: d and k too large for shared memory");
-        LG_CUDA(ctx, cudaFuncSetAttribute(k_knn_exact, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        int used = 0;
-        const char* force = getenv("LG_KNN_CUDA_CORES");
-        if (!(force && force[0] == '1')) LG_TRY(lg_knn_topk_umma(ctx, d_ref, nr, d_qry, nq, d, k, d_ex, d_idx, d_dist, &used));
-        if (!used)
-            LG_LAUNCH(ctx, k_knn_exact, (unsigned)((nq + KNN_WARPS - 1) / KNN_WARPS), KNN_WARPS * 32, smem, d_ref, nr, d_qry, nq, d, k,
-                      d_ex, (const uint32_t*)nullptr, (const unsigned int*)nullptr, d_idx, d_dist);
-    }
+    LG_TRY(lg_knn_topk_device(ctx, d_ref, nr, d_qry, nq, d, k, d_ex, d_idx, d_dist));
     return st.finish();
 }
 

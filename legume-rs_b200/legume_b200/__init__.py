@@ -32,7 +32,10 @@ DEFAULT_OPT_ITER = 100                          # collapse_data/mod.rs:28
 
 __all__ = ["Context", "CscBlock", "SparseIoVec", "binary_sort_columns", "GammaMatrix", "CollapsedStat",
            "CollapsedOut", "optimize", "ColumnDict", "LegumeError", "CalibrateTarget", "compute_level_sort_dims",
-           "pad_numeric_labels", "merge_stat"]
+           "pad_numeric_labels", "merge_stat", "MultilevelParams", "PbSampleLayout", "build_pb_sample_layout",
+           "per_batch_sc_neighbors", "collect_matched_stat_coarse", "compute_fine_to_coarse_mapping",
+           "sort_batch_proximity", "knn_match_batches"]
+DEFAULT_NUM_LEVELS = 2                          # collapse_data/stats.rs:688
 
 
 class CalibrateTarget:
@@ -241,6 +244,116 @@ def merge_stat(ctx: Context, fine_ds, fine_to_coarse, ncoarse):
 
 
 # --------------------------------------------------------------------------------------------------
+# stage 7: cross-batch neighbourhood adjustment (free functions; SparseIoVec methods wrap them)
+# --------------------------------------------------------------------------------------------------
+def sort_batch_proximity(ctx: Context, proj_kn, col_to_batch, nbatch):
+    """batch.rs:182-234: (order (B, B) uint32 — row b = every batch by centroid distance, b first; centroids (B, K))"""
+    proj_kn = _as(proj_kn, np.float32)
+    n, K = proj_kn.shape
+    batch = _as(col_to_batch, np.uint32)
+    order = np.empty((nbatch, nbatch), np.uint32)
+    cen = np.empty((nbatch, K), np.float32)
+    ctx.check(lib.lg_batch_proximity(ctx.h, _ptr(proj_kn), K, n, _ptr(batch), nbatch, _ptr(order), _ptr(cen)))
+    return order, cen
+
+
+def knn_match_batches(ctx: Context, proj_kn, col_to_batch, nbatch, knn, target_order=None):
+    """matched.rs:173-260 (kNN part): (matched_idx (N, nt*knn) global cell indices, matched_dist)"""
+    proj_kn = _as(proj_kn, np.float32)
+    n, K = proj_kn.shape
+    batch = _as(col_to_batch, np.uint32)
+    to = None if target_order is None else np.ascontiguousarray(target_order, np.uint32)
+    nt = nbatch if to is None else to.shape[1]
+    dev = _is_torch(proj_kn)
+    idx = ctx.empty((n, nt * knn), np.uint32, dev)
+    dist = ctx.empty((n, nt * knn), np.float32, dev)
+    ctx.check(lib.lg_knn_match_batches(ctx.h, _ptr(proj_kn), K, n, _ptr(batch), nbatch, knn, _ptr(to), nt, _ptr(idx),
+                                       _ptr(dist)))
+    return idx, dist
+
+
+class PbSampleLayout(dict):
+    """pb_samples.rs:33-60: centroids (npb, K), cell_counts, pb_sample_to_batch, pb_sample_to_group, cell_to_pbsamp"""
+
+    def __getattr__(self, k):
+        return self[k]
+
+
+def build_pb_sample_layout(ctx: Context, col_to_group, num_groups, col_to_batch, nbatch, proj_kn, col_weight=None,
+                           anchor_batches=(), bulk_batches=()):
+    """pb_samples.rs:94-219 (ordinary (batch, group) blocks; anchored / bulk singletons are outside the hot path)"""
+    if len(anchor_batches) or len(bulk_batches):
+        raise LegumeError(1, "anchor / bulk batches are outside the hot path (pb_samples.rs:75-88)")
+    proj_kn = _as(proj_kn, np.float32)
+    n, K = proj_kn.shape
+    grp, bat = _as(col_to_group, np.uint32), _as(col_to_batch, np.uint32)
+    w = None if col_weight is None else _as(col_weight, np.float32)
+    cap = num_groups * nbatch
+    c2p = np.empty(n, np.uint32)
+    pg, pb = np.empty(cap, np.uint32), np.empty(cap, np.uint32)
+    cnt = np.empty(cap, np.float32)
+    cen = np.empty((cap, K), np.float32)
+    npb = C.c_uint32()
+    ctx.check(lib.lg_pb_layout(ctx.h, _ptr(proj_kn), K, n, _ptr(grp), num_groups, _ptr(bat), nbatch, _ptr(w), _ptr(c2p),
+                               _ptr(pg), _ptr(pb), _ptr(cnt), _ptr(cen), C.byref(npb)))
+    k = npb.value
+    return PbSampleLayout(centroids=cen[:k].copy(), cell_counts=cnt[:k].copy(), pb_sample_to_batch=pb[:k].copy(),
+                          pb_sample_to_group=pg[:k].copy(), cell_to_pbsamp=c2p, num_pb=k)
+
+
+def per_batch_sc_neighbors(ctx: Context, layout: PbSampleLayout, proj_kn, col_to_batch, nbatch, knn, anchor_batches=None):
+    """pb_samples.rs:442-459 with pooled matching: (matched_pb (npb, B*knn) uint32, matched_dist)"""
+    if anchor_batches is not None:
+        raise LegumeError(1, "anchored matching is outside the hot path (pb_samples.rs:407-424)")
+    proj_kn = _as(proj_kn, np.float32)
+    n, K = proj_kn.shape
+    npb = layout.num_pb
+    mp = np.empty((npb, nbatch * knn), np.uint32)
+    md = np.empty((npb, nbatch * knn), np.float32)
+    ctx.check(lib.lg_pb_match(ctx.h, _ptr(proj_kn), K, n, _ptr(_as(col_to_batch, np.uint32)), nbatch,
+                              _ptr(_as(layout.cell_to_pbsamp, np.uint32)), _ptr(_as(layout.centroids, np.float32)),
+                              _ptr(_as(layout.pb_sample_to_batch, np.uint32)), npb, knn, _ptr(mp), _ptr(md)))
+    return mp, md
+
+
+def collect_matched_stat_coarse(ctx: Context, layout: PbSampleLayout, gene_sums, pbsamp_to_group, matched, stat):
+    """stats.rs:698-784: fills stat.imputed_sum_ds / stat.residual_sum_ds; gene_sums (npb, D) dense"""
+    mp, md = matched
+    gs = _as(gene_sums, np.float32)
+    npb, D = gs.shape
+    S = stat.num_samples()
+    dev = _is_torch(gs)
+    imp, res = ctx.empty((S, D), np.float32, dev), ctx.empty((S, D), np.float32, dev)
+    ctx.check(lib.lg_collect_matched_stat_coarse(ctx.h, _ptr(gs), D, npb, _ptr(_as(layout.cell_counts, np.float32)),
+                                                 _ptr(_as(pbsamp_to_group, np.uint32)), S, _ptr(_as(mp, np.uint32)),
+                                                 _ptr(_as(md, np.float32)), mp.shape[1], _ptr(imp), _ptr(res)))
+    stat.imputed_sum_ds, stat.residual_sum_ds = imp, res
+
+
+def compute_fine_to_coarse_mapping(ctx: Context, fine_codes, col_to_group, num_fine, coarse_dim):
+    """refine.rs:741-769: (fine_to_coarse uint32[num_fine], num_coarse)"""
+    codes, grp = _as(fine_codes, np.uint64), _as(col_to_group, np.uint32)
+    f2c = np.empty(num_fine, np.uint32)
+    k = C.c_uint32()
+    ctx.check(lib.lg_fine_to_coarse(ctx.h, _ptr(codes), _ptr(grp), codes.shape[0], num_fine, coarse_dim, _ptr(f2c),
+                                    C.byref(k)))
+    return f2c, k.value
+
+
+class MultilevelParams:
+    """collapse_data/mod.rs:64-130 (the fields the un-refined path reads)"""
+
+    def __init__(self, proj_dim, knn_pb_samples=DEFAULT_KNN, num_levels=DEFAULT_NUM_LEVELS, sort_dim=None,
+                 num_opt_iter=DEFAULT_OPT_ITER, refine=None, output_calibration=TARGET_ALL):
+        self.knn_pb_samples = knn_pb_samples
+        self.num_levels = num_levels
+        self.sort_dim = min(proj_dim, 10) if sort_dim is None else sort_dim
+        self.num_opt_iter = num_opt_iter
+        self.refine = refine
+        self.output_calibration = output_calibration
+
+
+# --------------------------------------------------------------------------------------------------
 # GammaMatrix (matrix-param/src/dmatrix_gamma.rs) — TwoStatParam + Inference
 # --------------------------------------------------------------------------------------------------
 class GammaMatrix:
@@ -393,6 +506,8 @@ class SparseIoVec:
         self.col_to_batch = None      # uint32[N]
         self.batch_names = None
         self.multiplicity = None      # float32[N] or None
+        self.batch_proj = None        # (N, K) features the per-batch kNN dictionaries were built on
+        self.between_batch_proximity = None  # uint32 (B, B) or None (batch.rs:176-178: only when B > 2)
 
     @classmethod
     def from_csc(cls, ctx, indptr, indices, data, nrows):
@@ -514,18 +629,125 @@ class SparseIoVec:
                                              _ptr(self.col_to_batch), _ptr(self.multiplicity), S, B,
                                              _ptr(stat.observed_sum_db), _ptr(stat.n_bs)))
 
+    # ---- batch.rs:46-234 ----
+    def build_hnsw_per_batch(self, proj_kn, batch_membership):
+        """collapse_data/mod.rs:364-383 -> register_batches_dmatrix (batch.rs:46-180).  The per-batch
+        dictionaries are the exact backend at every size: they are not materialised; the
+        features are kept and searched by lg_knn_match_batches / lg_pb_match."""
+        if len(batch_membership) != self.num_columns():
+            raise LegumeError(1, "batch membership length mismatches the number of columns")
+        self.register_batch_membership(batch_membership)
+        self.batch_proj = _as(proj_kn, np.float32)
+        self.between_batch_proximity = None
+        if self.num_batches() > 2:
+            self.between_batch_proximity, _ = sort_batch_proximity(self.ctx, self.batch_proj, self.col_to_batch,
+                                                                   self.num_batches())
+
+    register_batches_dmatrix = build_hnsw_per_batch
+
+    def neighbouring_matches(self, knn_batches, knn_columns, skip_same_batch=True, skip_batches=None,
+                             target_batches=None):
+        """the kNN part of read_neighbouring_columns_csc / read_matched_columns_csc (matched.rs:173-260, 97-158):
+        (matched_columns (N, T) global indices, distances (N, T)); slot i*knn + r = r-th nearest cell of the i-th
+        neighbouring batch.  knn_batches only sizes a Vec in the reference (matched.rs:201) and is ignored."""
+        if self.batch_proj is None:
+            raise LegumeError(1, "no knn lookup")
+        if not skip_same_batch:
+            raise LegumeError(1, "skip_same_batch = false is not used on the hot path")
+        B = self.num_batches()
+        if target_batches is not None:
+            order = np.tile(np.asarray(target_batches, np.uint32)[None, :], (B, 1))
+        elif self.between_batch_proximity is not None:
+            order = np.array(self.between_batch_proximity, np.uint32, copy=True)
+        else:
+            order = np.tile(np.arange(B, dtype=np.uint32)[None, :], (B, 1))
+        if skip_batches is not None:
+            order[np.isin(order, np.asarray(skip_batches, np.uint32))] = 0xFFFFFFFF
+        return knn_match_batches(self.ctx, self.batch_proj, self.col_to_batch, B, knn_columns, order)
+
+    def collect_matched_stat(self, knn_batches, knn_cells, reference_indices, stat: CollapsedStat):
+        """collapse_data/mod.rs:485-500 -> collect_matched_stat_visitor (stats.rs:26-108)"""
+        midx, mdist = self.neighbouring_matches(knn_batches, knn_cells, True, None, reference_indices)
+        S, D = stat.num_samples(), self.num_rows()
+        dev = _is_torch(midx)
+        imp, res = self.ctx.empty((S, D), np.float32, dev), self.ctx.empty((S, D), np.float32, dev)
+        grp = self.get_group_membership()
+        if dev:
+            import torch
+            grp = torch.from_numpy(np.asarray(grp).astype(np.int32)).to(midx.device)
+        self.ctx.check(lib.lg_collect_matched_stat(self.ctx.h, self.block.h, _ptr(grp), S, _ptr(midx), _ptr(mdist),
+                                                   midx.shape[1], _ptr(imp), _ptr(res)))
+        stat.imputed_sum_ds, stat.residual_sum_ds = imp, res
+
     def collapse_columns(self, knn_batches=None, knn_cells=None, reference_batch_names=None, num_opt_iter=None,
                          out_target=TARGET_ALL):
-        """collapse_data/mod.rs:384-475 for the single-batch arm; the matched-stat arm (B > 1) is staged
-        through ColumnDict + collect_matched_stat once registered batches carry kNN indices."""
+        """collapse_data/mod.rs:384-475: basic stats; with B > 1 also batch stats and the per-cell matched stats
+        (cross-batch kNN neighbourhood adjustment), then the Poisson-Gamma fit"""
         if self.col_to_group is None:
-            raise LegumeError(1, "groups were not assigned")
-        nb = max(self.num_batches(), 1)
+            raise LegumeError(1, "The columns were not assigned before. Call `assign_columns_to_groups`")
+        nb = self.num_batches()
         stat = CollapsedStat(self.num_rows(), self.num_groups(), nb)
         self.collect_basic_stat(stat)
         if nb > 1:
+            ref = None
+            if reference_batch_names is not None:
+                lut = {k: i for i, k in enumerate(self.batch_names)}
+                ref = [lut[str(b)] for b in reference_batch_names if str(b) in lut]
+                if not ref:
+                    raise LegumeError(1, "no reference batch names matched!")
             self.collect_batch_stat(stat)
+            self.collect_matched_stat(2 if knn_batches is None else knn_batches,
+                                      DEFAULT_KNN if knn_cells is None else knn_cells, ref, stat)
         return optimize(self.ctx, stat, (1.0, 1.0), num_opt_iter or DEFAULT_OPT_ITER, out_target), stat
+
+    # ---- MultilevelCollapsingOps (collapse_data/mod.rs:867-1050, un-refined path) ----
+    def collapse_columns_multilevel_vec(self, proj_kn, batch_membership, params: MultilevelParams):
+        """returns (levels finest-first: list of CollapsedOut, list of CollapsedStat)"""
+        if params.refine is not None:
+            raise LegumeError(1, "BBKNN + DC-SBM refinement is outside the hot path (SURVEY.md §8f rank 3)")
+        ctx = self.ctx
+        proj_kn = _as(proj_kn, np.float32)
+        n, K = proj_kn.shape
+        self.register_batch_membership(batch_membership)
+        nb = self.num_batches()
+        if nb >= 2:
+            self.build_hnsw_per_batch(proj_kn, batch_membership)
+        level_dims = compute_level_sort_dims(params.sort_dim, params.num_levels)
+        kk = min(K, level_dims[0], n)
+        fine_codes = binary_sort_columns(ctx, proj_kn, kk)
+        codes_h = fine_codes.cpu().numpy().astype(np.uint64) if _is_torch(fine_codes) else fine_codes
+        group, ng = assign_groups_from_codes(ctx, codes_h, kk)
+        self.col_to_group, self.binary_codes = group, codes_h
+        self.group_keys = sorted({str(int(c)) for c in np.unique(codes_h)}, key=lambda s: s.encode())
+        fine_stat = CollapsedStat(self.num_rows(), ng, nb)
+        self.collect_basic_stat(fine_stat)
+        if nb >= 2:
+            self.collect_batch_stat(fine_stat)
+            layout = build_pb_sample_layout(ctx, group, ng, self.col_to_batch, nb, proj_kn, self.multiplicity)
+            gs = CollapsedStat(self.num_rows(), layout.num_pb, 1)
+            ctx.check(lib.lg_collapse_basic(ctx.h, self.block.h, _ptr(layout.cell_to_pbsamp), _ptr(self.multiplicity),
+                                            layout.num_pb, _ptr(gs.observed_sum_ds), _ptr(gs.size_s)))
+            matched = per_batch_sc_neighbors(ctx, layout, proj_kn, self.col_to_batch, nb, params.knn_pb_samples)
+            collect_matched_stat_coarse(ctx, layout, gs.observed_sum_ds, layout.pb_sample_to_group, matched, fine_stat)
+        outs = [optimize(ctx, fine_stat, (1.0, 1.0), params.num_opt_iter, TARGET_ALL)]
+        stats = [fine_stat]
+        prev, prev_group, prev_n = fine_stat, np.asarray(group), ng
+        for dim in level_dims[1:]:
+            f2c, nc = compute_fine_to_coarse_mapping(ctx, codes_h, prev_group, prev_n, dim)
+            coarse = CollapsedStat(self.num_rows(), nc, nb)
+            for name in ("observed_sum_ds", "imputed_sum_ds", "residual_sum_ds"):
+                setattr(coarse, name, merge_stat(ctx, getattr(prev, name), f2c, nc))
+            size, nbs = np.zeros(nc, np.float32), np.zeros((nc, max(nb, 1)), np.float32)
+            psize, pnbs = np.asarray(prev.size_s, np.float32), np.asarray(prev.n_bs, np.float32).reshape(prev_n, -1)
+            for f, c in enumerate(f2c):  # ascending fine index, f32 adds (stats.rs:813-816)
+                size[c] += psize[f]
+                nbs[c] += pnbs[f]
+            coarse.size_s, coarse.n_bs = size, nbs
+            coarse.observed_sum_db = prev.observed_sum_db
+            outs.append(optimize(ctx, coarse, (1.0, 1.0), max(params.num_opt_iter // 2, 10), TARGET_ALL))
+            stats.append(coarse)
+            prev, prev_group, prev_n = coarse, f2c[prev_group], nc
+        return outs, stats
 
 
 # --------------------------------------------------------------------------------------------------

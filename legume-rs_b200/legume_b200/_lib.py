@@ -67,6 +67,13 @@ _sig = {
     "lg_optimize_batched": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _u64, _u32, _u32, _f, _f, _i, _i, _vp, _vp, _vp, _vp,
                             _vp, _vp],
     "lg_knn_topk": [_vp, _vp, _u64, _vp, _u64, _i, _i, _vp, _vp, _vp],
+    "lg_batch_proximity": [_vp, _vp, _i, _u64, _vp, _u32, _vp, _vp],
+    "lg_knn_match_batches": [_vp, _vp, _i, _u64, _vp, _u32, _i, _vp, _u32, _vp, _vp],
+    "lg_collect_matched_stat": [_vp, _vp, _vp, _u32, _vp, _vp, _u32, _vp, _vp],
+    "lg_pb_layout": [_vp, _vp, _i, _u64, _vp, _u32, _vp, _u32, _vp, _vp, _vp, _vp, _vp, _vp, C.POINTER(_u32)],
+    "lg_pb_match": [_vp, _vp, _i, _u64, _vp, _u32, _vp, _vp, _vp, _u32, _i, _vp, _vp],
+    "lg_collect_matched_stat_coarse": [_vp, _vp, _u64, _u32, _vp, _vp, _u32, _vp, _vp, _u32, _vp, _vp],
+    "lg_fine_to_coarse": [_vp, _vp, _vp, _u64, _u32, _i, _vp, C.POINTER(_u32)],
     "lg_sim_poisson_csc": [_vp, _u64, _u64, _u64, _u64, _vp, _vp, _u32, _u32, _vp, _vp, _vp, C.POINTER(_vp)],
 }
 for _name, _args in _sig.items():

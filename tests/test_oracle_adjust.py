@@ -4,7 +4,7 @@ numpy restatements elsewhere."""
 import numpy as np
 
 import oracle as orc
-from util import close, random_csc
+from util import close, matched_stat_f64, random_csc
 
 
 def make_case(seed=0, D=300, N=400, B=3, S=7, K=12):
@@ -65,20 +65,7 @@ def test_collect_matched_stat_against_float64():
     D, N, B, S, K, ip, ix, v, proj, batch, grp = make_case(3)
     idx, dist = orc.knn_match_batches(proj, batch, B, 3)
     imp, res = orc.collect_matched_stat(ip, ix, v, D, grp, S, idx, dist)
-    Y = dense(ip, ix, v, D)
-    wimp, wres = np.zeros((S, D)), np.zeros((S, D))
-    for j in range(N):
-        live = idx[j] != 0xFFFFFFFF
-        m, d = idx[j][live].astype(np.int64), dist[j][live].astype(np.float64)
-        w = np.exp(-d - (-d).min())
-        w /= w.sum()
-        yhat = (w[:, None] * Y[m]).sum(0)
-        scale = Y[j].sum() / yhat.sum() if yhat.sum() > 0 else 1.0
-        y1 = Y[j].copy()
-        pos = (yhat > 0) & (y1 > 0)
-        y1[pos] = y1[pos] / (yhat[pos] * scale)
-        wimp[grp[j]] += yhat
-        wres[grp[j]] += y1
+    wimp, wres = matched_stat_f64(ip, ix, v, D, grp, S, idx, dist)
     assert close(imp, wimp, 1e-5) and close(res, wres, 1e-5)
 
 

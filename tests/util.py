@@ -53,3 +53,32 @@ def toy_stat(G, S, B):
     obs_db = np.array([[f(g, b) + 0.7 for g in range(G)] for b in range(B)], np.float32)
     n_bs = np.array([[1.0 + ((b + c) % 4) for b in range(B)] for c in range(S)], np.float32)
     return obs, imp, res, size, obs_db, n_bs
+
+
+def dense_columns(ip, ix, v, D):
+    n = len(ip) - 1
+    out = np.zeros((n, D))
+    for j in range(n):
+        sl = slice(int(ip[j]), int(ip[j + 1]))
+        out[j, ix[sl].astype(np.int64)] = v[sl]
+    return out
+
+
+def matched_stat_f64(ip, ix, v, D, grp, S, idx, dist):
+    """float64 restatement of collect_matched_stat_visitor (stats.rs:26-108): (imputed (S, D), residual (S, D))"""
+    Y = dense_columns(ip, ix, v, D)
+    imp, res = np.zeros((S, D)), np.zeros((S, D))
+    for j in range(len(ip) - 1):
+        live = idx[j] != 0xFFFFFFFF
+        y1 = Y[j].copy()
+        if live.any():
+            m, d = idx[j][live].astype(np.int64), dist[j][live].astype(np.float64)
+            w = np.exp(-d - (-d).min())
+            w /= w.sum()
+            yhat = (w[:, None] * Y[m]).sum(0)
+            scale = Y[j].sum() / yhat.sum() if yhat.sum() > 0 else 1.0
+            pos = (yhat > 0) & (y1 > 0)
+            y1[pos] = y1[pos] / (yhat[pos] * scale)
+            imp[grp[j]] += yhat
+        res[grp[j]] += y1
+    return imp, res
