@@ -208,11 +208,12 @@ __global__ void k_scatter_matches(const uint32_t* __restrict__ knn_idx, const fl
 // ------------------------------------------------------------------------------------------------
 // collect_matched_stat_visitor
 // ------------------------------------------------------------------------------------------------
-constexpr int MS_THREADS = 1024;  // one CTA per SM (the accumulators fill shared memory)
-constexpr int MS_U = 2;           // prefetched elements per thread per matched column
-constexpr int MS_PF = 4;          // matched columns in flight
+constexpr int MS_THREADS = 256;   // one CTA per SM (the accumulators fill shared memory); 4 nnz per thread per pass
+constexpr int MS_PF = 6;          // matched columns in flight (cp.async ring: 2 x 16 B per thread per stage)
+constexpr size_t MS_RING_BYTES = (size_t)MS_PF * 2 * MS_THREADS * 16;
 constexpr int MS_SEG = 128;       // source cells per work item
 constexpr int MS_MAXR = 16;       // gene ranges
+constexpr int MS_PASS = MS_THREADS * 4;
 
 struct MatchDesc {
     unsigned long long lo;  // first nnz of the matched column inside this gene range
@@ -307,18 +308,31 @@ __global__ void k_match_desc(const uint64_t* __restrict__ indptr, const uint32_t
     if (lane == 0) scale[j] = dsum > 0.0f ? __fdiv_rn(colsum[j], dsum) : 1.0f;
 }
 
+__device__ __forceinline__ void cp_async16(void* dst_smem, const void* src, bool on) {
+    const uint32_t d = (uint32_t)__cvta_generic_to_shared(dst_smem);
+    const int bytes = on ? 16 : 0;  // 0 source bytes = zero fill, nothing is read
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(src), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+    asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+
 // grid = (segments, gene ranges).  The CTA walks its source cells in ascending order; for each one it
 // streams the matched columns one at a time (rows are unique inside a column, so plain shared-memory
-// read-modify-writes are race-free and the accumulation order is fixed), with the next MS_PF columns'
-// loads already in flight.
+// read-modify-writes are race-free and the accumulation order is fixed).  A thread owns one 16-byte-aligned
+// group of 4 nnz per pass; the next MS_PF columns are already on their way into a shared-memory ring through
+// cp.async (each thread only ever reads back its own 32 bytes, so the ring needs no barrier of its own).
 __global__ void __launch_bounds__(MS_THREADS, 1) k_matched_stat(
-    const uint64_t* __restrict__ indptr, const uint32_t* __restrict__ indices, const float* __restrict__ values,
+    const uint64_t* __restrict__ indptr, const uint32_t* __restrict__ indices, const float* __restrict__ values, uint64_t nnz_total,
     const uint32_t* __restrict__ split, const uint32_t* __restrict__ cell_sorted, const uint32_t* __restrict__ seg_first,
     const uint32_t* __restrict__ seg_len, const uint32_t* __restrict__ seg_group, const uint8_t* __restrict__ seg_single,
     const MatchDesc* __restrict__ desc, const float* __restrict__ scale, uint32_t T, int R, uint64_t D, uint32_t W, uint32_t pmax,
     float* __restrict__ scratch, float* __restrict__ out_imp, float* __restrict__ out_res) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    float* imp = reinterpret_cast<float*>(smem_raw);
+    uint4* ring = reinterpret_cast<uint4*>(smem_raw);  // [MS_PF][2][MS_THREADS]
+    float* imp = reinterpret_cast<float*>(smem_raw + MS_RING_BYTES);
     float* res = imp + W;
     float* yhat = res + W;
     float* pat_v = yhat + pmax;
@@ -335,12 +349,66 @@ __global__ void __launch_bounds__(MS_THREADS, 1) k_matched_stat(
         res[g] = 0.0f;
         slot[g] = 0xFFFF;
     }
+    // synchronous fetch of one aligned group of 4 entries starting at element c (long columns, array tail)
+    auto fetch = [&](unsigned long long c, uint4& g, float4& v) {
+        if (c + 4 <= nnz_total) {
+            g = __ldg(reinterpret_cast<const uint4*>(indices + c));
+            v = __ldg(reinterpret_cast<const float4*>(values + c));
+        } else {  // the last, partial group of the whole array
+            uint32_t gg[4] = {0, 0, 0, 0};
+            float vv[4] = {0.f, 0.f, 0.f, 0.f};
+            for (int u = 0; u < 4; ++u)
+                if (c + u < nnz_total) {
+                    gg[u] = indices[c + u];
+                    vv[u] = values[c + u];
+                }
+            g = make_uint4(gg[0], gg[1], gg[2], gg[3]);
+            v = make_float4(vv[0], vv[1], vv[2], vv[3]);
+        }
+    };
+    auto apply4 = [&](unsigned long long c, unsigned long long lo, uint32_t n, float w, const uint4& g, const float4& v) {
+        const uint32_t e0 = (uint32_t)(c - lo);  // position of the group's first entry in the column (wraps below 0: masked)
+        const uint32_t gi[4] = {g.x - g0, g.y - g0, g.z - g0, g.w - g0};
+        const float vi[4] = {v.x, v.y, v.z, v.w};
+        bool ok[4];
+        float a[4], term[4];
+        unsigned short sl[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            ok[u] = (e0 + (uint32_t)u) < n;
+            a[u] = ok[u] ? imp[gi[u]] : 0.0f;  // rows are distinct inside a column: the four updates never alias
+            sl[u] = ok[u] ? slot[gi[u]] : (unsigned short)0xFFFF;
+            term[u] = __fmul_rn(w, vi[u]);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+            if (ok[u]) imp[gi[u]] = __fadd_rn(a[u], term[u]);
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+            if (sl[u] != 0xFFFF) yhat[sl[u]] = __fadd_rn(yhat[sl[u]], term[u]);
+    };
+    // asynchronous copy of this thread's group of column t into ring stage s (always commits, so group counts stay uniform)
+    auto issue = [&](uint32_t t, int s) {
+        if (t < T) {
+            const unsigned long long lo = dsc[t].lo;
+            const unsigned long long c = (lo & ~3ull) + 4ull * tid;
+            const bool on = (c < lo + dsc[t].n) && (c + 4 <= nnz_total);
+            const unsigned long long cs = on ? c : 0ull;
+            cp_async16(&ring[(s * 2 + 0) * MS_THREADS + tid], indices + cs, on);
+            cp_async16(&ring[(s * 2 + 1) * MS_THREADS + tid], values + cs, on);
+        }
+        cp_async_commit();
+    };
     const uint32_t p0 = seg_first[seg], np_cells = seg_len[seg];
     for (uint32_t p = 0; p < np_cells; ++p) {
         const uint32_t j = cell_sorted[p0 + p];
         const uint64_t own_lo = indptr[j] + split[j * (uint64_t)(R + 1) + r];
         const uint32_t own_n = split[j * (uint64_t)(R + 1) + r + 1] - split[j * (uint64_t)(R + 1) + r];
         __syncthreads();  // previous cell fully retired (slots cleared) and, first time, the accumulators zeroed
+        for (uint32_t t = tid; t < T; t += MS_THREADS) dsc[t] = desc[((uint64_t)j * R + r) * T + t];
+        __syncthreads();
+#pragma unroll
+        for (int s = 0; s < MS_PF; ++s) issue(s, s);
         for (uint32_t i = tid; i < own_n; i += MS_THREADS) {
             const uint32_t g = indices[own_lo + i] - g0;
             pat_g[i] = g;
@@ -348,53 +416,37 @@ __global__ void __launch_bounds__(MS_THREADS, 1) k_matched_stat(
             yhat[i] = 0.0f;
             slot[g] = (unsigned short)i;
         }
-        for (uint32_t t = tid; t < T; t += MS_THREADS) dsc[t] = desc[((uint64_t)j * R + r) * T + t];
         const float sc = scale[j];
         __syncthreads();
-
-        uint32_t pg[MS_PF][MS_U];
-        float pv[MS_PF][MS_U];
-        auto issue = [&](uint32_t t, uint32_t (&g)[MS_U], float (&v)[MS_U]) {
-            const bool on = t < T;
-            const unsigned long long lo = on ? dsc[t].lo : 0ull;
-            const uint32_t n = on ? dsc[t].n : 0u;
-#pragma unroll
-            for (int u = 0; u < MS_U; ++u) {
-                const uint32_t e = tid + u * MS_THREADS;
-                g[u] = NONE;
-                v[u] = 0.0f;
-                if (e < n) {
-                    g[u] = __ldg(indices + lo + e) - g0;
-                    v[u] = __ldg(values + lo + e);
-                }
-            }
-        };
-        auto apply = [&](uint32_t g, float v, float w) {
-            const float term = __fmul_rn(w, v);
-            imp[g] = __fadd_rn(imp[g], term);
-            const unsigned short sl = slot[g];
-            if (sl != 0xFFFF) yhat[sl] = __fadd_rn(yhat[sl], term);
-        };
-#pragma unroll
-        for (int s = 0; s < MS_PF; ++s) issue(s, pg[s], pv[s]);
         for (uint32_t t0 = 0; t0 < T; t0 += MS_PF) {
 #pragma unroll
             for (int s = 0; s < MS_PF; ++s) {
                 const uint32_t t = t0 + s;
                 const uint32_t n = t < T ? dsc[t].n : 0u;  // CTA-uniform
+                cp_async_wait<MS_PF - 1>();                // this thread's copies for column t have landed
                 if (n) {
                     const float w = dsc[t].w;
-#pragma unroll
-                    for (int u = 0; u < MS_U; ++u)
-                        if (pg[s][u] != NONE) apply(pg[s][u], pv[s][u], w);
                     const unsigned long long lo = dsc[t].lo;
-                    for (uint32_t e = tid + MS_U * MS_THREADS; e < n; e += MS_THREADS)
-                        apply(__ldg(indices + lo + e) - g0, __ldg(values + lo + e), w);
+                    const unsigned long long c0 = (lo & ~3ull) + 4ull * tid;
+                    if (c0 < lo + n) {
+                        uint4 g = ring[(s * 2 + 0) * MS_THREADS + tid];
+                        uint4 vb = ring[(s * 2 + 1) * MS_THREADS + tid];
+                        float4 v = make_float4(__uint_as_float(vb.x), __uint_as_float(vb.y), __uint_as_float(vb.z), __uint_as_float(vb.w));
+                        if (c0 + 4 > nnz_total) fetch(c0, g, v);
+                        apply4(c0, lo, n, w, g, v);
+                    }
+                    for (unsigned long long c = c0 + MS_PASS; c < lo + n; c += MS_PASS) {  // columns longer than one pass
+                        uint4 g;
+                        float4 v;
+                        fetch(c, g, v);
+                        apply4(c, lo, n, w, g, v);
+                    }
                 }
-                issue(t + MS_PF, pg[s], pv[s]);
+                issue(t + MS_PF, s);
                 if (n) __syncthreads();  // the next column may touch the same genes
             }
         }
+        cp_async_wait<0>();
         __syncthreads();
         for (uint32_t i = tid; i < own_n; i += MS_THREADS) {
             const float d = yhat[i];
@@ -746,6 +798,8 @@ extern "C" int lg_collect_matched_stat(lg_ctx* ctx, const lg_csc* m, const uint3
     LgStage st(ctx);
     const uint64_t N = m->ncols, D = m->nrows;
     LG_REQUIRE(ctx, N < 0xFFFFFFFFull, "lg_collect_matched_stat: more than 2^32-1 cells in one block");
+    LG_REQUIRE(ctx, ((uintptr_t)m->indices & 15) == 0 && ((uintptr_t)m->values & 15) == 0,
+               "lg_collect_matched_stat: the CSC index / value arrays must be 16-byte aligned");
     const uint32_t* d_group;
     const uint32_t* d_midx;
     const float* d_mdist;
@@ -761,7 +815,7 @@ extern "C" int lg_collect_matched_stat(lg_ctx* ctx, const lg_csc* m, const uint3
 
     // gene ranges: per range two f32 accumulators + a u16 slot map (10 B per gene) next to the per-cell pattern
     // buffers (12 B per own nnz) and the T descriptors
-    const size_t budget = ctx->smem_optin - 2048 - (size_t)T * sizeof(MatchDesc);
+    const size_t budget = ctx->smem_optin - 2048 - (size_t)T * sizeof(MatchDesc) - MS_RING_BYTES;
     int R = 1;
     uint32_t W = (uint32_t)D, pmax = 0;
     float* d_colsum;
@@ -772,7 +826,7 @@ extern "C" int lg_collect_matched_stat(lg_ctx* ctx, const lg_csc* m, const uint3
     for (;; ++R) {
         LG_REQUIRE(ctx, R <= MS_MAXR, "lg_collect_matched_stat: too many genes for the shared-memory accumulators");
         W = (uint32_t)((D + R - 1) / R);
-        W = (W + 3) & ~3u;
+        W = (W + 7) & ~7u;
         if ((size_t)W * 10 + 64 > budget) continue;
         LG_TRY(st.scratch((size_t)N * (R + 1), &d_split));
         LG_CUDA(ctx, cudaMemsetAsync(d_maxpart, 0, sizeof(unsigned int), ctx->stream));
@@ -786,7 +840,7 @@ extern "C" int lg_collect_matched_stat(lg_ctx* ctx, const lg_csc* m, const uint3
         if ((size_t)W * 10 + (size_t)pmax * 12 + 64 <= budget) break;
     }
     LG_REQUIRE(ctx, pmax < 65535, "lg_collect_matched_stat: a column holds more than 65534 entries in one gene range");
-    const size_t smem = (size_t)W * 10 + (size_t)pmax * 12 + (size_t)T * sizeof(MatchDesc) + 64;
+    const size_t smem = MS_RING_BYTES + (size_t)W * 10 + (size_t)pmax * 12 + (size_t)T * sizeof(MatchDesc) + 64;
 
     // segments of at most MS_SEG group-sorted cells, never crossing a group boundary
     std::vector<uint32_t> counts;
@@ -829,7 +883,7 @@ extern "C" int lg_collect_matched_stat(lg_ctx* ctx, const lg_csc* m, const uint3
     LG_CUDA(ctx, cudaFuncSetAttribute(k_matched_stat, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     {
         dim3 grid(nseg, (unsigned)R);
-        k_matched_stat<<<grid, MS_THREADS, smem, ctx->stream>>>(m->indptr, m->indices, m->values, d_split, d_cell, d_seg_first, d_seg_len,
+        k_matched_stat<<<grid, MS_THREADS, smem, ctx->stream>>>(m->indptr, m->indices, m->values, m->nnz, d_split, d_cell, d_seg_first, d_seg_len,
                                                                d_seg_group, d_seg_single, d_desc, d_scale, T, R, D, W, pmax, d_scratch,
                                                                d_imp, d_res);
         ctx->launches++;
