@@ -185,6 +185,17 @@ int lg_optimize_batched(lg_ctx* ctx, const float* obs_ds, const float* imp_ds, c
 int lg_knn_topk(lg_ctx* ctx, const float* ref, uint64_t nr, const float* qry, uint64_t nq, int d, int k,
                 const uint32_t* exclude, uint32_t* out_idx, float* out_dist);
 
+/* the same search leaving SQUARED distances (what the ranking is made on): the per-shard half of a search
+ * whose reference cells are sharded over GPUs */
+int lg_knn_topk_sq(lg_ctx* ctx, const float* ref, uint64_t nr, const float* qry, uint64_t nq, int d, int k,
+                   const uint32_t* exclude, uint32_t* out_idx, float* out_sq);
+/* top-k merge across reference-cell shards: shard_idx / shard_sq are nshard x nq x k lists from
+ * lg_knn_topk_sq (local indices); shard s holds the reference cells shard_offset[s] ... of the global numbering.
+ * Merged by (squared distance, lower global index), exactly the order of a single search over all cells;
+ * exclude (u32[nq], global index, or NULL) is applied here, so shards must be searched with k+1 when it is used. */
+int lg_knn_merge_topk(lg_ctx* ctx, const uint32_t* shard_idx, const float* shard_sq, uint32_t nshard, uint64_t nq, int k,
+                      const uint64_t* shard_offset, const uint32_t* exclude, uint32_t* out_idx, float* out_dist);
+
 /* ---- stage 7: cross-batch neighbourhood adjustment ---------------------------------------------
  * (a) per-cell path = CollapsingOps::collapse_columns with B > 1 (collapse_data/mod.rs:384-475):
  *     batch dictionaries + sort_batch_proximity (data-beans/src/sparse_io_vector/batch.rs:100-234),

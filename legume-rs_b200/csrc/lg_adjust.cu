@@ -23,7 +23,7 @@
 #include "lg_common.cuh"
 
 int lg_knn_topk_device(lg_ctx* ctx, const float* d_ref, uint64_t nr, const float* d_qry, uint64_t nq, int d, int k,
-                       const uint32_t* d_ex, uint32_t* d_idx, float* d_dist);
+                       const uint32_t* d_ex, uint32_t* d_idx, float* d_dist, int squared);
 
 namespace {
 
@@ -779,7 +779,7 @@ extern "C" int lg_knn_match_batches(lg_ctx* ctx, const float* proj_kn, int K, ui
         for (int h = 0; h < 2; ++h) {
             const uint64_t q0 = ranges[h][0], nq = ranges[h][1] - ranges[h][0];
             if (nq == 0) continue;
-            LG_TRY(lg_knn_topk_device(ctx, d_sorted + off[b] * K, nb, d_sorted + q0 * K, nq, K, knn, nullptr, d_kidx, d_kdist));
+            LG_TRY(lg_knn_topk_device(ctx, d_sorted + off[b] * K, nb, d_sorted + q0 * K, nq, K, knn, nullptr, d_kidx, d_kdist, 0));
             LG_LAUNCH(ctx, k_scatter_matches, (unsigned)((nq * knn + 255) / 256), 256, 0, d_kidx, d_kdist, nq, knn, q0, off[b], d_cell,
                       d_lab, d_slot, B, b, T, d_oidx, d_odist);
         }

@@ -289,7 +289,7 @@ __global__ void __launch_bounds__(256) k_knn_refine(const float* __restrict__ re
                                                     const float* __restrict__ cand_key, const uint32_t* __restrict__ cand_idx,
                                                     const unsigned int* __restrict__ absmax_bits, uint32_t* __restrict__ out_idx,
                                                     float* __restrict__ out_dist, uint32_t* __restrict__ redo_list,
-                                                    unsigned int* __restrict__ redo_count) {
+                                                    unsigned int* __restrict__ redo_count, int squared) {
     extern __shared__ unsigned long long keys_s[];  // per warp: nlists*CAND keys
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint64_t q = (uint64_t)blockIdx.x * (blockDim.x >> 5) + warp;
@@ -346,7 +346,8 @@ __global__ void __launch_bounds__(256) k_knn_refine(const float* __restrict__ re
         if (lane == 0) {
             const bool empty = best == ~0ull;
             out_idx[q * k + t] = empty ? 0xffffffffu : (uint32_t)(best & 0xffffffffu);
-            out_dist[q * k + t] = empty ? INFINITY : __fsqrt_rn(__uint_as_float((uint32_t)(best >> 32)));
+            const float d2 = __uint_as_float((uint32_t)(best >> 32));
+            out_dist[q * k + t] = empty ? INFINITY : (squared ? d2 : __fsqrt_rn(d2));
             if (!empty) keys[bpos] = ~0ull;
         }
         if (best != ~0ull) {
@@ -368,12 +369,12 @@ __global__ void __launch_bounds__(256) k_knn_refine(const float* __restrict__ re
 
 // brute-force kernel of lg_knn.cu on a list of query ids (device-side count)
 int lg_knn_exact_list(lg_ctx* ctx, const float* d_ref, uint64_t nr, const float* d_qry, uint64_t nq, int d, int k,
-                      const uint32_t* d_exclude, const uint32_t* d_qlist, const unsigned int* d_qcount, uint32_t* d_idx,
-                      float* d_dist);
+                      const uint32_t* d_exclude, const uint32_t* d_qlist, const unsigned int* d_qcount, int squared,
+                      uint32_t* d_idx, float* d_dist);
 
 // returns LG_OK; *used = 0 means "not applicable, run the brute-force kernel"
 int lg_knn_topk_umma(lg_ctx* ctx, const float* d_ref, uint64_t nr, const float* d_qry, uint64_t nq, int d, int k,
-                     const uint32_t* d_ex, uint32_t* d_idx, float* d_dist, int* used) {
+                     const uint32_t* d_ex, uint32_t* d_idx, float* d_dist, int squared, int* used) {
     *used = 0;
     if (k + 4 > CAND || d > 126 || nr < 4096 || nq == 0 || nr >= 0xFFFFFF00ull || (double)nq * (double)nr < 5e7) return LG_OK;
     const int ksteps = (d + 2 + 15) / 16;
@@ -417,7 +418,7 @@ int lg_knn_topk_umma(lg_ctx* ctx, const float* d_ref, uint64_t nr, const float* 
         const size_t rsmem = (size_t)wpb * nlists * CAND * sizeof(unsigned long long);
         LG_CUDA(ctx, cudaFuncSetAttribute(k_knn_refine, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rsmem));
         LG_LAUNCH(ctx, k_knn_refine, (unsigned)((nq + wpb - 1) / wpb), wpb * 32, rsmem, d_ref, d_qry, nq, d, k, d_ex, nlists, d_ckey,
-                  d_cidx, d_absmax, d_idx, d_dist, d_redo, d_redo_count);
+                  d_cidx, d_absmax, d_idx, d_dist, d_redo, d_redo_count, squared);
     }
     if (const char* dbg = getenv("LG_KNN_STATS")) {
         if (dbg[0] == '1') {
@@ -428,7 +429,7 @@ int lg_knn_topk_umma(lg_ctx* ctx, const float* d_ref, uint64_t nr, const float* 
                     (unsigned long long)nq, (unsigned long long)nr, d, k, nsplit, h);
         }
     }
-    LG_TRY(lg_knn_exact_list(ctx, d_ref, nr, d_qry, nq, d, k, d_ex, d_redo, d_redo_count, d_idx, d_dist));
+    LG_TRY(lg_knn_exact_list(ctx, d_ref, nr, d_qry, nq, d, k, d_ex, d_redo, d_redo_count, squared, d_idx, d_dist));
     *used = 1;
     return LG_OK;
 }

@@ -67,6 +67,8 @@ _sig = {
     "lg_optimize_batched": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _u64, _u32, _u32, _f, _f, _i, _i, _vp, _vp, _vp, _vp,
                             _vp, _vp],
     "lg_knn_topk": [_vp, _vp, _u64, _vp, _u64, _i, _i, _vp, _vp, _vp],
+    "lg_knn_topk_sq": [_vp, _vp, _u64, _vp, _u64, _i, _i, _vp, _vp, _vp],
+    "lg_knn_merge_topk": [_vp, _vp, _vp, _u32, _u64, _i, _vp, _vp, _vp, _vp],
     "lg_batch_proximity": [_vp, _vp, _i, _u64, _vp, _u32, _vp, _vp],
     "lg_knn_match_batches": [_vp, _vp, _i, _u64, _vp, _u32, _i, _vp, _u32, _vp, _vp],
     "lg_collect_matched_stat": [_vp, _vp, _vp, _u32, _vp, _vp, _u32, _vp, _vp],

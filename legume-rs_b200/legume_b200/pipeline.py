@@ -23,6 +23,7 @@ import torch
 
 from . import BLOCK_CELLS, Context, CscBlock, LegumeError, _ptr
 from ._lib import TARGET_ALL, TARGET_MEAN_ONLY, lib
+from .exchange import Exchange
 
 
 def shard_range(ncols: int, rank: int, world: int):
@@ -38,11 +39,8 @@ class HotPath:
     def __init__(self, ctx: Context, group=None):
         self.ctx = ctx
         self.dev = torch.device(f"cuda:{ctx.device}")
-        self.pg = group
-        self.dist = torch.distributed if (group is not None or (torch.distributed.is_available()
-                                                                 and torch.distributed.is_initialized())) else None
-        self.world = self.dist.get_world_size(group) if self.dist else 1
-        self.rank = self.dist.get_rank(group) if self.dist else 0
+        self.ex = Exchange(group)
+        self.world, self.rank = self.ex.world, self.ex.rank
         ctx.use_torch_stream()
 
     # ---- helpers ---------------------------------------------------------------------------------
@@ -52,25 +50,12 @@ class HotPath:
     def _sum_partials(self, partials: torch.Tensor, nblk_local: int, M: int):
         """partials (nblk_local, M) f64 -> (M,) f64 summed over ALL ranks' blocks in global block order"""
         out = torch.empty(M, dtype=torch.float64, device=self.dev)
-        if self.world > 1:
-            cnt = torch.tensor([nblk_local], dtype=torch.int64, device=self.dev)
-            self.dist.all_reduce(cnt, op=self.dist.ReduceOp.MAX, group=self.pg)
-            mx = int(cnt.item())
-            padded = torch.zeros((mx, M), dtype=torch.float64, device=self.dev)  # +0.0 blocks are exact no-ops
-            padded[:nblk_local] = partials[:nblk_local]
-            allp = torch.empty((self.world * mx, M), dtype=torch.float64, device=self.dev)
-            self.dist.all_gather_into_tensor(allp, padded, group=self.pg)
-            self.ctx.check(lib.lg_block_partials_finalize(self.ctx.h, _ptr(allp), self.world * mx, M, _ptr(out)))
-        else:
-            self.ctx.check(lib.lg_block_partials_finalize(self.ctx.h, _ptr(partials), nblk_local, M, _ptr(out)))
+        allp = self.ex.gather_block_partials(partials, nblk_local).contiguous()
+        self.ctx.check(lib.lg_block_partials_finalize(self.ctx.h, _ptr(allp), allp.shape[0], M, _ptr(out)))
         return out
 
     def _total(self, n_local: int) -> int:
-        if self.world == 1:
-            return n_local
-        t = torch.tensor([n_local], dtype=torch.int64, device=self.dev)
-        self.dist.all_reduce(t, group=self.pg)
-        return int(t.item())
+        return self.ex.total(n_local, self.dev)
 
     # ---- stage 1 -----------------------------------------------------------------------------------
     def project(self, block: CscBlock, basis_kd: torch.Tensor, batch: torch.Tensor | None, nbatch: int):
@@ -89,13 +74,7 @@ class HotPath:
         mm = torch.empty(2, dtype=torch.float32, device=self.dev)
         ctx.check(lib.lg_proj_centre_scale(ctx.h, _ptr(proj), K, n, _ptr(batch) if sums is not None else None,
                                            nbatch if sums is not None else 0, _ptr(sums), _ptr(mm)))
-        if self.world > 1:
-            lo, hi = mm[0:1].clone(), mm[1:2].clone()
-            self.dist.all_reduce(lo, op=self.dist.ReduceOp.MIN, group=self.pg)
-            self.dist.all_reduce(hi, op=self.dist.ReduceOp.MAX, group=self.pg)
-            mn, mx = float(lo.item()), float(hi.item())
-        else:
-            mn, mx = (float(x) for x in mm.tolist())
+        mn, mx = self.ex.minmax(mm)
         if mx > 4.0 or mn < -4.0:  # global decision, random_projection.rs:401
             ctx.check(lib.lg_proj_clamp_rescale(ctx.h, _ptr(proj), K, n))
         return proj
@@ -114,8 +93,7 @@ class HotPath:
             if n < r:
                 raise LegumeError(1, "rank 0 must hold at least kk+5 cells")
             first.copy_(proj[:r])
-        if self.world > 1:
-            self.dist.broadcast(first, src=0, group=self.pg)
+        self.ex.broadcast_(first, src=0)
         first_h = first.cpu().numpy()
         q_h = np.empty((kk, K), np.float32)
         ctx.check(lib.lg_codes_basis(ctx.h, _ptr(first_h), K, r, kk, _ptr(q_h)))
@@ -144,8 +122,7 @@ class HotPath:
         ctx, n = self.ctx, codes.shape[0]
         present = torch.empty(1 << kk, dtype=torch.int32, device=self.dev)
         ctx.check(lib.lg_code_presence(ctx.h, _ptr(codes), n, kk, _ptr(present)))
-        if self.world > 1:
-            self.dist.all_reduce(present, op=self.dist.ReduceOp.MAX, group=self.pg)
+        self.ex.max_(present)
         present_h = present.cpu().numpy().astype(np.uint32)
         lut_h = np.empty(1 << kk, np.uint32)
         ng = C.c_uint32()
@@ -162,9 +139,8 @@ class HotPath:
         sum_ds = torch.empty((S, block.nrows), dtype=torch.float32, device=self.dev)
         size_s = torch.empty(S, dtype=torch.float32, device=self.dev)
         ctx.check(lib.lg_collapse_basic(ctx.h, block.h, _ptr(group), _ptr(mult), S, _ptr(sum_ds), _ptr(size_s)))
-        if self.world > 1:
-            self.dist.all_reduce(sum_ds, group=self.pg)
-            self.dist.all_reduce(size_s, group=self.pg)
+        self.ex.sum_(sum_ds)
+        self.ex.sum_(size_s)
         return sum_ds, size_s
 
     def collapse_batch(self, block: CscBlock, group, batch, S: int, B: int, mult=None):
@@ -174,9 +150,8 @@ class HotPath:
         n_bs = torch.empty((S, B), dtype=torch.float32, device=self.dev)
         ctx.check(lib.lg_collapse_batch(ctx.h, block.h, _ptr(group), _ptr(batch), _ptr(mult), S, B, _ptr(sum_db),
                                         _ptr(n_bs)))
-        if self.world > 1:
-            self.dist.all_reduce(sum_db, group=self.pg)
-            self.dist.all_reduce(n_bs, group=self.pg)
+        self.ex.sum_(sum_db)
+        self.ex.sum_(n_bs)
         return sum_db, n_bs
 
     # ---- stage 5 -----------------------------------------------------------------------------------
@@ -192,6 +167,42 @@ class HotPath:
         ctx.check(lib.lg_optimize_single(ctx.h, _ptr(sum_ds), _ptr(size_s), D, S, a0, b0, target, _ptr(mean), _ptr(sd),
                                          _ptr(lm), _ptr(ls)))
         return dict(mean=mean, sd=sd, log_mean=lm, log_sd=ls)
+
+    # ---- stage 6 -----------------------------------------------------------------------------------
+    def knn_topk_sharded(self, ref_local: torch.Tensor, qry_local: torch.Tensor, k: int, exclude_global=None):
+        """exact kNN with the REFERENCE cells sharded over ranks: queries are all-gathered, every
+        rank searches its own reference shard (squared distances, local indices), the k-lists travel back to the
+        rank that owns the query and are merged by (squared distance, lower global index).  Returns
+        (idx int32 (nq_local, k) global reference indices, dist f32 (nq_local, k)), identical to one search over
+        all reference cells.  exclude_global: int32 (nq_local,) global index to drop per query, or None."""
+        ctx = self.ctx
+        d = qry_local.shape[1]
+        kq = k + (1 if exclude_global is not None else 0)
+        allq, qcnt = self.ex.all_gather_rows(qry_local.contiguous())
+        nr_cnt = self.ex.counts(ref_local.shape[0], self.dev)
+        NQ = allq.shape[0]
+        idx = torch.empty((NQ, kq), dtype=torch.int32, device=self.dev)
+        sq = torch.empty((NQ, kq), dtype=torch.float32, device=self.dev)
+        ctx.check(lib.lg_knn_topk_sq(ctx.h, _ptr(ref_local.contiguous()), ref_local.shape[0], _ptr(allq.contiguous()), NQ, d, kq,
+                                     None, _ptr(idx), _ptr(sq)))
+        sidx = self.ex.exchange_query_lists(idx, qcnt).contiguous()
+        ssq = self.ex.exchange_query_lists(sq, qcnt).contiguous()
+        off = torch.tensor(np.concatenate([[0], np.cumsum(nr_cnt)[:-1]]).astype(np.int64), device=self.dev)
+        nq = qry_local.shape[0]
+        out_idx = torch.empty((nq, k), dtype=torch.int32, device=self.dev)
+        out_dist = torch.empty((nq, k), dtype=torch.float32, device=self.dev)
+        # the merge reads lists of length kq and writes the k best after the exclusion
+        if kq != k:
+            full_i = torch.empty((nq, kq), dtype=torch.int32, device=self.dev)
+            full_d = torch.empty((nq, kq), dtype=torch.float32, device=self.dev)
+            ctx.check(lib.lg_knn_merge_topk(ctx.h, _ptr(sidx), _ptr(ssq), self.world, nq, kq, _ptr(off), _ptr(exclude_global),
+                                            _ptr(full_i), _ptr(full_d)))
+            out_idx.copy_(full_i[:, :k])
+            out_dist.copy_(full_d[:, :k])
+        else:
+            ctx.check(lib.lg_knn_merge_topk(ctx.h, _ptr(sidx), _ptr(ssq), self.world, nq, k, _ptr(off), None, _ptr(out_idx),
+                                            _ptr(out_dist)))
+        return out_idx, out_dist
 
     # ---- whole path --------------------------------------------------------------------------------
     def run(self, block: CscBlock, basis_kd: torch.Tensor, batch, nbatch: int, kk: int, target=TARGET_ALL):
