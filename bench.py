@@ -45,6 +45,7 @@ def parse():
     ap.add_argument("--cpu-cells", type=int, default=0, help="cells in the bounded CPU sample (0 = auto)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-knn", action="store_true")
     return ap.parse_args()
 
 
@@ -61,6 +62,28 @@ def measured_peak():
             return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json, burst copy)"
     except Exception:
         return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def measured_tensor_peak():
+    """dense 16-bit tensor throughput (the kNN filter runs kind::f16): burst figure, the kernel is timed alone"""
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["bf16_tflops"]), "measured (MEASURED_PEAKS.json, cuBLAS bf16 burst)"
+    except Exception:
+        return 2250.0, "fallback (nominal dense bf16, B200_PROFILING.md)"
+
+
+def k1_traffic(cells, genes, nnz):
+    """dram__bytes_read.sum + dram__bytes_write.sum of the two K1 kernels from the committed ncu --set full capture
+    (profiles/k1_traffic.json), if it was taken on this workload"""
+    try:
+        with open(os.path.join(ROOT, "profiles", "k1_traffic.json")) as f:
+            t = json.load(f)
+        if int(t["cells"]) == int(cells) and int(t["genes"]) == int(genes) and abs(int(t["nnz"]) - int(nnz)) <= 0.001 * nnz:
+            return float(t["dram_bytes_prep"]) + float(t["dram_bytes_umma"])
+    except Exception:
+        pass
+    return None
 
 
 class ClockSampler:
@@ -274,12 +297,34 @@ def main():
     peak, peak_src = measured_peak()
     k1_bytes = 8.0 * nnz_local + 8.0 * (n_local + 1) + 4.0 * K * n_local
     achieved = k1_bytes / (t_k1 * 1e-3) / 1e9
-    roofline = {"bound": "hbm", "kernel": "k_project_raw (K1, nnz stream)", "achieved": achieved, "peak": peak,
-                "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
-                "algorithmic_bytes_per_launch": k1_bytes, "launch_ms": t_k1}
+    roofline = {"bound": "hbm", "kernel": "K1 projection = k_project_prep + k_project_umma (one nnz stream)", "achieved": achieved,
+                "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": k1_traffic(n_local, D, nnz_local),
+                "peak_source": peak_src, "algorithmic_bytes_per_launch": k1_bytes, "launch_ms": t_k1}
     if "collapse_ms" in stages:
         cb = 8.0 * nnz_local + 8.0 * (n_local + 1) + 4.0 * n_local + 4.0 * D * ngroups
         stages["collapse_GBps"] = cb / (stages["collapse_ms"] * 1e-3) / 1e9
+
+    # ---- K7 at the shape of BASELINE configs[2]: one batch's 125k cells as references, 250k queries, d = 50, k = 10 ----
+    roofline_knn = None
+    if rank == 0 and not args.no_knn:
+        nr_k, nq_k, k_k = 125_000, 250_000, 10
+        g = torch.Generator(device=dev).manual_seed(0)
+        std = lambda x: (x - x.mean(1, keepdim=True)) / x.std(1, keepdim=True, unbiased=False)
+        kref, kqry = std(torch.randn((nr_k, K), device=dev, generator=g)), std(torch.randn((nq_k, K), device=dev, generator=g))
+        kidx = torch.empty((nq_k, k_k), dtype=torch.int32, device=dev)
+        kdist = torch.empty((nq_k, k_k), dtype=torch.float32, device=dev)
+        t_knn = timed(lambda: ctx.check(lib.lg_knn_topk(ctx.h, kref.data_ptr(), nr_k, kqry.data_ptr(), nq_k, K, k_k, None, kidx.data_ptr(),
+                                                        kdist.data_ptr())), reps)
+        tpeak, tsrc = measured_tensor_peak()
+        flop = 2.0 * K * nq_k * nr_k
+        ach = flop / (t_knn * 1e-3) / 1e12
+        stages["knn_250k_x_125k_ms"] = t_knn
+        roofline_knn = {"bound": "tensor", "kernel": "K7 exact kNN = k_knn_umma (split-f16 tcgen05 filter) + k_knn_refine", "achieved": ach,
+                        "peak": tpeak, "unit": "TFLOP/s", "frac": ach / tpeak, "traffic": None, "peak_source": tsrc,
+                        "algorithmic_flops_per_launch": flop, "launch_ms": t_knn, "queries_per_s": nq_k / (t_knn * 1e-3),
+                        "note": "algorithmic flops 2*d*Nq*Nr; the filter issues 3 f16 passes over a K axis padded 50 -> 64, i.e. "
+                                "3.84x these flops on the tensor pipe"}
+        del kref, kqry, kidx, kdist
 
     # ---- e2e: host buffers in the reference's form through the C ABI, results read back ----
     e2e = None
@@ -370,7 +415,7 @@ def main():
                        "genes": D, "nnz_per_gpu": int(nnz_local), "proj_dim": K, "sort_dim": kk, "groups": int(ngroups),
                        "l2": "inputs larger than L2 (nnz stream %.1f GB per GPU)" % (8e-9 * nnz_local),
                        "parallelism": f"cells sharded x{world}"},
-            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clk,
+            "roofline": roofline, "roofline_knn": roofline_knn, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clk,
             "stages": stages,
         }
         print(json.dumps(line))

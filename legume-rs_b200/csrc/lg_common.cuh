@@ -29,6 +29,7 @@ struct lg_csc {
     uint32_t* indices = nullptr; // device, nnz
     float* values = nullptr;     // device, nnz
     bool owned = false;
+    bool pooled = false;  // owned arrays came from the stream-ordered pool (cudaMallocAsync): freed with cudaFreeAsync
     // cached "all values are small non-negative integers" (-1 unknown); blocks are immutable
     mutable int int_valued = -1;
 };

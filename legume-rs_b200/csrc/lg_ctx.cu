@@ -144,9 +144,12 @@ extern "C" int lg_csc_upload(lg_ctx* ctx, const uint64_t* indptr, const uint64_t
             return fail(e__ == cudaErrorMemoryAllocation ? LG_ERR_NOMEM : LG_ERR_CUDA); \
         }                                                                              \
     } while (0)
-    UP_CUDA(cudaMalloc(&m->indptr, (ncols + 1) * sizeof(uint64_t)));
-    UP_CUDA(cudaMalloc(&m->indices, (nnz ? nnz : 1) * sizeof(uint32_t)));
-    UP_CUDA(cudaMalloc(&m->values, (nnz ? nnz : 1) * sizeof(float)));
+    // stream-ordered pool: a block freed by lg_csc_free is handed to the next upload without a device-wide
+    // synchronisation or page (un)mapping (cudaMalloc / cudaFree of ~11 GB cost up to 200 ms per call)
+    m->pooled = true;
+    UP_CUDA(cudaMallocAsync(&m->indptr, (ncols + 1) * sizeof(uint64_t), st));
+    UP_CUDA(cudaMallocAsync(&m->indices, (nnz ? nnz : 1) * sizeof(uint32_t), st));
+    UP_CUDA(cudaMallocAsync(&m->values, (nnz ? nnz : 1) * sizeof(float), st));
     // indptr: copy then rebase to 0
     {
         uint64_t* tmp = nullptr;
@@ -237,9 +240,15 @@ extern "C" int lg_csc_free(lg_ctx* ctx, lg_csc* m) {
             cudaSetDevice(ctx->device);
             cudaStreamSynchronize(ctx->stream);
         }
-        if (m->indptr) cudaFree(m->indptr);
-        if (m->indices) cudaFree(m->indices);
-        if (m->values) cudaFree(m->values);
+        if (m->pooled && ctx) {
+            if (m->indptr) cudaFreeAsync(m->indptr, ctx->stream);
+            if (m->indices) cudaFreeAsync(m->indices, ctx->stream);
+            if (m->values) cudaFreeAsync(m->values, ctx->stream);
+        } else {
+            if (m->indptr) cudaFree(m->indptr);
+            if (m->indices) cudaFree(m->indices);
+            if (m->values) cudaFree(m->values);
+        }
     }
     delete m;
     return LG_OK;

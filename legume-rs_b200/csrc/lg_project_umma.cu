@@ -19,6 +19,8 @@
 //     and leaves corr/norm and ln2/norm per cell.
 //   * K1a never materialises the dense A operand in memory: expander warps turn 64-bit bitmap words
 //     into 16 TMEM columns (u8 in {0, 128}) with two ALU ops per register and tcgen05.st them.
+#include <cstdlib>
+
 #include "lg_common.cuh"
 #include "lg_umma.cuh"
 
@@ -30,9 +32,9 @@ constexpr int TILE_M = 128;          // cells per accumulator (UMMA M)
 constexpr int NT = 2;                // accumulators (cell tiles) per CTA
 constexpr int CELLS = TILE_M * NT;   // cells per CTA pass
 constexpr int GS = 128;              // genes per pipeline stage (4 MMAs of K = 32)
-constexpr int GC = 2048;             // genes per bitmap chunk
-constexpr int BM_STRIDE = GC / 32 + 2;  // 66 words per cell row: 8-byte aligned, conflict-free LDS.64
-constexpr int NBST = 3;              // B-operand ring depth (stages)
+constexpr int GC = 1024;             // genes per bitmap chunk (small chunks leave shared memory for a deep B ring)
+constexpr int BM_STRIDE = GC / 32 + 2;  // 34 words per cell row: 8-byte aligned, conflict-free LDS.64
+constexpr int NBST = 5;              // B-operand ring depth (stages)
 constexpr int NAST = 3;              // A-operand ring depth in TMEM (stages per tile)
 constexpr int A_COLS = GS / 4;       // 32 TMEM columns per A stage
 constexpr int N_EXP_WARPS = 4 * NT;  // 8 expander warps (also the epilogue)
@@ -214,9 +216,14 @@ __global__ void __launch_bounds__(PREP_WARPS * 32, 4) k_project_prep(const uint6
             const uint64_t sup = j / CELLS;
             const uint32_t r = (uint32_t)(j % CELLS);
             uint32_t* dst = bm_global + ((sup * nchunks) * CELLS + r) * (uint64_t)BM_STRIDE;
+            static_assert(GC / 32 == 32 || GC / 32 == 64, "one or two bitmap words per lane and chunk");
             for (uint32_t c = 0; c < nchunks; ++c) {
-                const uint2 w2 = reinterpret_cast<const uint2*>(row + (size_t)c * (GC / 32))[lane];
-                reinterpret_cast<uint2*>(dst + (size_t)c * (CELLS * BM_STRIDE))[lane] = w2;
+                if (GC / 32 == 64) {
+                    const uint2 w2 = reinterpret_cast<const uint2*>(row + (size_t)c * (GC / 32))[lane];
+                    reinterpret_cast<uint2*>(dst + (size_t)c * (CELLS * BM_STRIDE))[lane] = w2;
+                } else {
+                    dst[(size_t)c * (CELLS * BM_STRIDE) + lane] = row[(size_t)c * (GC / 32) + lane];
+                }
             }
         }
 #pragma unroll

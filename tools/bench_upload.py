@@ -1,0 +1,35 @@
+"""Where the end-to-end time goes: host CSC (u64/u64/f32, pinned) -> lg_csc_upload -> hot path -> results to host."""
+import ctypes as C, json, os, sys, time
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path[:0] = [ROOT, os.path.join(ROOT, "legume-rs_b200")]
+import numpy as np, torch
+import legume_b200 as lg
+from legume_b200 import sim
+from legume_b200._lib import lib
+from legume_b200.pipeline import HotPath
+N = int(sys.argv[1]) if len(sys.argv) > 1 else 1_000_000
+D, K, kk = 30000, 50, 10
+ctx = lg.Context(0); hp = HotPath(ctx)
+tabs = sim.make_tables(D, ntopic=8, nbatch=1, depth=1500, seed=42)
+blk, _, _ = sim.sim_block(ctx, tabs, 0, N)
+ip, ix, v = blk.download(); blk.free()
+pin = lambda a: torch.from_numpy(a.view(np.int64) if a.dtype == np.uint64 else a).pin_memory()
+h_ip, h_ix, h_v = pin(ip), pin(ix), pin(v); del ip, ix, v
+basis = torch.from_numpy(np.random.default_rng(0).standard_normal((D, K)).astype(np.float32)).cuda()
+batch = torch.zeros(N, dtype=torch.int32, device="cuda")
+def now():
+    torch.cuda.synchronize(); return time.perf_counter()
+res = []
+for it in range(4):
+    t0 = now()
+    h = C.c_void_p()
+    ctx.check(lib.lg_csc_upload(ctx.h, h_ip.data_ptr(), h_ix.data_ptr(), h_v.data_ptr(), D, 0, N, None, C.byref(h)))
+    t1 = now()
+    b = lg.CscBlock(ctx, h)
+    o = hp.run(b, basis, batch, 1, kk)
+    t2 = now()
+    b.free()
+    t3 = now()
+    res.append({"upload_ms": 1e3 * (t1 - t0), "run_ms": 1e3 * (t2 - t1), "free_ms": 1e3 * (t3 - t2)})
+bytes_up = h_ip.numel() * 8 + h_ix.numel() * 8 + h_v.numel() * 4
+print(json.dumps({"cells": N, "h2d_bytes": bytes_up, "iters": res, "upload_GBps_last": bytes_up / res[-1]["upload_ms"] / 1e6}))
