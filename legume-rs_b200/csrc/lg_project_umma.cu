@@ -90,7 +90,10 @@ __global__ void k_quantize_basis(const float* __restrict__ basis_kd, uint64_t D,
 constexpr int PREP_Q = 256;   // exception queue entries per warp (>= 31 + 128)
 constexpr int PREP_LUT = 64;  // log1p look-up for integer counts below this
 
-template <int NACC>
+// HALF2 (K even, basis 8-byte aligned): the basis rows of TWO exceptions are gathered at once, one per half-warp,
+// as float2 (lane l of a half holds dims 2l, 2l+1, 2l+32, 2l+33) — a third of the instructions per exception of the
+// lanes-as-dims form, which stays as the fallback for odd K.
+template <int NACC, bool HALF2>
 __global__ void __launch_bounds__(PREP_WARPS * 32, 4) k_project_prep(const uint64_t* __restrict__ indptr,
                                                                      const uint32_t* __restrict__ indices,
                                                                      const float* __restrict__ values, uint64_t ncols,
@@ -117,9 +120,9 @@ __global__ void __launch_bounds__(PREP_WARPS * 32, 4) k_project_prep(const uint6
         const uint32_t n = (uint32_t)(indptr[j + 1] - lo);
         const uint32_t* ip = indices + lo + lane;
         const float* vp = values + lo + lane;
-        float acc[NACC];
+        float acc[HALF2 ? 4 : NACC];
 #pragma unroll
-        for (int a = 0; a < NACC; ++a) acc[a] = 0.0f;
+        for (int a = 0; a < (HALF2 ? 4 : NACC); ++a) acc[a] = 0.0f;
         float nsq = 0.0f;
         uint32_t qhead = 0, qtail = 0;  // warp-uniform ring cursors of the exception queue
 
@@ -136,6 +139,30 @@ __global__ void __launch_bounds__(PREP_WARPS * 32, 4) k_project_prep(const uint6
                 nsq = fmaf(x, x, nsq);
                 w = x - ln2;
             }
+            if constexpr (HALF2) {
+                const int half = lane >> 4, l = lane & 15;
+                const bool hi_on = 2 * (l + 16) < K;
+                for (uint32_t e0 = 0; e0 < cnt; e0 += 8) {  // 8 exceptions = 4 pairs per round
+                    float2 b0[4], b1[4];
+                    float ws[4];
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        const int src = (int)e0 + 2 * e + half;  // lanes >= cnt carry w = 0 and gene 0
+                        const uint32_t ge = __shfl_sync(0xffffffffu, g, src);
+                        ws[e] = __shfl_sync(0xffffffffu, w, src);
+                        const float2* brow = reinterpret_cast<const float2*>(basis_kd + (size_t)ge * K);
+                        b0[e] = (2 * l < K) ? __ldg(brow + l) : make_float2(0.f, 0.f);
+                        b1[e] = hi_on ? __ldg(brow + l + 16) : make_float2(0.f, 0.f);
+                    }
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        acc[0] = fmaf(ws[e], b0[e].x, acc[0]);
+                        acc[1] = fmaf(ws[e], b0[e].y, acc[1]);
+                        acc[2] = fmaf(ws[e], b1[e].x, acc[2]);
+                        acc[3] = fmaf(ws[e], b1[e].y, acc[3]);
+                    }
+                }
+            } else {
             for (uint32_t e0 = 0; e0 < cnt; e0 += 8) {
                 float bv[8][NACC], ws[8];
 #pragma unroll
@@ -150,6 +177,7 @@ __global__ void __launch_bounds__(PREP_WARPS * 32, 4) k_project_prep(const uint6
                 for (int e = 0; e < 8; ++e)
 #pragma unroll
                     for (int a = 0; a < NACC; ++a) acc[a] = fmaf(ws[e], bv[e][a], acc[a]);
+            }
             }
             qhead += cnt;
         };
@@ -230,10 +258,27 @@ __global__ void __launch_bounds__(PREP_WARPS * 32, 4) k_project_prep(const uint6
         for (int off = 16; off >= 1; off >>= 1) nsq += __shfl_xor_sync(0xffffffffu, nsq, off);
         nsq = fmaf((float)n_one, ln2 * ln2, nsq);
         const float denom = fmaxf(sqrtf(nsq), 1e-8f);
+        if constexpr (HALF2) {
 #pragma unroll
-        for (int a = 0; a < NACC; ++a) {
-            const int k = lane + 32 * a;
-            if (k < K) out[(size_t)j * K + k] = acc[a] / denom;
+            for (int a = 0; a < 4; ++a) acc[a] += __shfl_xor_sync(0xffffffffu, acc[a], 16);  // the two half-warps' shares
+            const int l = lane & 15;
+            if (lane < 16) {
+                float* o = out + (size_t)j * K;
+                if (2 * l < K) {
+                    o[2 * l] = acc[0] / denom;
+                    o[2 * l + 1] = acc[1] / denom;
+                }
+                if (2 * (l + 16) < K) {
+                    o[2 * l + 32] = acc[2] / denom;
+                    o[2 * l + 33] = acc[3] / denom;
+                }
+            }
+        } else {
+#pragma unroll
+            for (int a = 0; a < NACC; ++a) {
+                const int k = lane + 32 * a;
+                if (k < K) out[(size_t)j * K + k] = acc[a] / denom;
+            }
         }
         if (lane == 0) scale[j] = ln2 / denom;
         __syncwarp();
@@ -468,15 +513,17 @@ int lg_project_raw_umma(lg_ctx* ctx, const lg_csc* m, const float* d_basis, int 
         const uint64_t cap = (uint64_t)ctx->num_sms * per_sm;
         if (blocks > cap) blocks = cap;
         const int nacc = (K + 31) / 32;
-        if (nacc == 1) {
-            LG_CUDA(ctx, cudaFuncSetAttribute(k_project_prep<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psmem));
-            LG_LAUNCH(ctx, k_project_prep<1>, (unsigned)blocks, PREP_WARPS * 32, psmem, m->indptr, m->indices, m->values, m->ncols,
-                      d_basis, K, nchunks, d_bm, d_out, d_scale);
-        } else {
-            LG_CUDA(ctx, cudaFuncSetAttribute(k_project_prep<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psmem));
-            LG_LAUNCH(ctx, k_project_prep<2>, (unsigned)blocks, PREP_WARPS * 32, psmem, m->indptr, m->indices, m->values, m->ncols,
-                      d_basis, K, nchunks, d_bm, d_out, d_scale);
-        }
+        const bool half2 = (K % 2 == 0) && (((uintptr_t)d_basis & 7) == 0);
+#define LG_PREP_LAUNCH(NA, H2)                                                                                                      \
+    do {                                                                                                                            \
+        LG_CUDA(ctx, cudaFuncSetAttribute(k_project_prep<NA, H2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psmem));        \
+        LG_LAUNCH(ctx, (k_project_prep<NA, H2>), (unsigned)blocks, PREP_WARPS * 32, psmem, m->indptr, m->indices, m->values,      \
+                  m->ncols, d_basis, K, nchunks, d_bm, d_out, d_scale);                                                             \
+    } while (0)
+        if (half2) LG_PREP_LAUNCH(2, true);
+        else if (nacc == 1) LG_PREP_LAUNCH(1, false);
+        else LG_PREP_LAUNCH(2, false);
+#undef LG_PREP_LAUNCH
     }
     const size_t stage_bytes = (size_t)NB * 32 * (GS / 32);
     const size_t smem = (size_t)NBST * stage_bytes + (size_t)2 * BM_CHUNK_BYTES + sizeof(Barriers) + 16;
