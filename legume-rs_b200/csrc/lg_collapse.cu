@@ -245,16 +245,15 @@ extern "C" int lg_collapse_batch(lg_ctx* ctx, const lg_csc* m, const uint32_t* g
     return st.finish();
 }
 
-__global__ void k_merge_stat(const float* __restrict__ fine, uint64_t D, uint32_t nfine, const uint32_t* __restrict__ f2c,
-                             uint32_t ncoarse, float* __restrict__ coarse) {
+__global__ void k_merge_stat(const float* __restrict__ fine, uint64_t D, const uint32_t* __restrict__ coarse_off,
+                             const uint32_t* __restrict__ coarse_fine, uint32_t ncoarse, float* __restrict__ coarse) {
     // one thread per (gene, coarse) output; fine columns are summed in ascending fine index, as stats.rs:798-812 does
     const uint64_t e = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= D * ncoarse) return;
     const uint64_t g = e % D;
     const uint32_t c = (uint32_t)(e / D);
     float s = 0.0f;
-    for (uint32_t f = 0; f < nfine; ++f)
-        if (f2c[f] == c) s = __fadd_rn(s, fine[(size_t)f * D + g]);
+    for (uint32_t i = coarse_off[c]; i < coarse_off[c + 1]; ++i) s = __fadd_rn(s, fine[(size_t)coarse_fine[i] * D + g]);
     coarse[e] = s;
 }
 
@@ -265,12 +264,32 @@ extern "C" int lg_merge_stat(lg_ctx* ctx, const float* fine_ds, uint64_t nrows, 
     cudaSetDevice(ctx->device);
     LgStage st(ctx);
     const float* d_fine;
-    const uint32_t* d_f2c;
     float* d_coarse;
     LG_TRY(st.in(fine_ds, (size_t)nrows * nfine, &d_fine));
-    LG_TRY(st.in(fine_to_coarse, (size_t)nfine, &d_f2c));
     LG_TRY(st.out(out_coarse_ds, (size_t)nrows * ncoarse, &d_coarse));
+    // the map is tiny (<= 2^kk entries): bucket the fine columns by coarse column on the host, ascending inside a bucket
+    std::vector<uint32_t> f2c(nfine);
+    if (nfine) {
+        LG_CUDA(ctx, cudaMemcpyAsync(f2c.data(), fine_to_coarse, sizeof(uint32_t) * nfine, cudaMemcpyDefault, ctx->stream));
+        LG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    }
+    std::vector<uint32_t> off(ncoarse + 1, 0), lst(nfine);
+    for (uint32_t f = 0; f < nfine; ++f) {
+        LG_REQUIRE(ctx, f2c[f] < ncoarse, "lg_merge_stat: fine_to_coarse out of range");
+        off[f2c[f] + 1]++;
+    }
+    for (uint32_t c = 0; c < ncoarse; ++c) off[c + 1] += off[c];
+    {
+        std::vector<uint32_t> cur(off.begin(), off.end() - 1);
+        for (uint32_t f = 0; f < nfine; ++f) lst[cur[f2c[f]]++] = f;
+    }
+    uint32_t *d_off, *d_lst;
+    LG_TRY(st.scratch(off.size(), &d_off));
+    LG_TRY(st.scratch(lst.size(), &d_lst));
+    LG_CUDA(ctx, cudaMemcpyAsync(d_off, off.data(), sizeof(uint32_t) * off.size(), cudaMemcpyHostToDevice, ctx->stream));
+    if (nfine) LG_CUDA(ctx, cudaMemcpyAsync(d_lst, lst.data(), sizeof(uint32_t) * nfine, cudaMemcpyHostToDevice, ctx->stream));
+    LG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // the host vectors go out of scope below
     const uint64_t total = nrows * ncoarse;
-    if (total) LG_LAUNCH(ctx, k_merge_stat, (unsigned)((total + 255) / 256), 256, 0, d_fine, nrows, nfine, d_f2c, ncoarse, d_coarse);
+    if (total) LG_LAUNCH(ctx, k_merge_stat, (unsigned)((total + 255) / 256), 256, 0, d_fine, nrows, d_off, d_lst, ncoarse, d_coarse);
     return st.finish();
 }

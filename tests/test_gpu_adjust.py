@@ -253,3 +253,53 @@ def test_collapse_columns_multilevel_matches_oracle(lg, ctx):
     assert np.array_equal(stats[1].size_s, csize) and np.array_equal(stats[1].n_bs, cnbs)
     want1 = orc.optimize_batched(cobs, cimp, cres, csize, obs_db, cnbs, 1.0, 1.0, 10, 0)
     assert close(outs[1].mu_adjusted["mean"], want1["mu_adjusted"], 1e-4)
+
+
+# ---- edge cases: empty batches / groups / columns, one batch only ---------------------------------------------------
+def test_adjustment_edge_cases(lg, ctx):
+    D, N, B, S, K, knn = 200, 700, 4, 12, 10, 6
+    rng = np.random.default_rng(12)
+    ip, ix, v = random_csc(rng, D, N, density=0.08, empty_every=9)   # every ninth cell has no counts at all
+    proj = rng.standard_normal((N, K)).astype(np.float32)
+    batch = rng.choice([0, 1, 3], N).astype(np.uint32)                # batch 2 is empty
+    batch[:3] = 3
+    grp = rng.choice([0, 2, 3, 7, 11], N).astype(np.uint32)           # most group ids are empty
+    # per-cell arm
+    order, _ = orc.batch_proximity(proj, batch, B)
+    gorder, _ = lg.sort_batch_proximity(ctx, proj, batch, B)
+    assert np.array_equal(gorder, order)
+    midx, mdist = lg.knn_match_batches(ctx, proj, batch, B, knn, order)
+    widx, wdist = orc.knn_match_batches(proj, batch, B, knn, order)
+    assert np.array_equal(midx, widx) and mdist.tobytes() == wdist.tobytes()
+    wimp, wres = orc.collect_matched_stat(ip, ix, v, D, grp, S, widx, wdist)
+    blk = lg.CscBlock.upload(ctx, ip, ix, v, D)
+    imp, res = np.empty((S, D), np.float32), np.empty((S, D), np.float32)
+    ctx.check(lg.lib.lg_collect_matched_stat(ctx.h, blk.h, lg._ptr(grp), S, lg._ptr(midx), lg._ptr(mdist), midx.shape[1],
+                                             lg._ptr(imp), lg._ptr(res)))
+    assert close(imp, wimp, TOL) and close(res, wres, 1e-4)
+    assert not imp[[1, 4, 5, 6, 8, 9, 10]].any() and not res[[1, 4, 5, 6, 8, 9, 10]].any()  # empty groups stay zero
+    # pb-sample arm
+    lay = lg.build_pb_sample_layout(ctx, grp, S, batch, B, proj)
+    want = orc.pb_layout(proj, grp, S, batch, B)
+    assert lay.num_pb == want["num_pb"] and np.array_equal(lay.cell_to_pbsamp, want["cell_to_pb"])
+    assert lay.centroids.tobytes() == want["centroids"].tobytes()
+    mp, md = lg.per_batch_sc_neighbors(ctx, lay, proj, batch, B, knn)
+    wmp, wmd = orc.pb_match(proj, batch, B, want, knn)
+    assert np.array_equal(mp, wmp) and md.tobytes() == wmd.tobytes()
+    assert np.all(mp[:, 2 * knn:3 * knn] == NONE)  # nothing can be matched in the empty batch
+    # one batch only: no foreign pb-samples, the matched stats stay zero
+    one = np.zeros(N, np.uint32)
+    lay1 = lg.build_pb_sample_layout(ctx, grp, S, one, 1, proj)
+    mp1, md1 = lg.per_batch_sc_neighbors(ctx, lay1, proj, one, 1, knn)
+    assert np.all(mp1 == NONE) and np.all(np.isinf(md1))
+    gs, _ = orc.collapse_basic(ip, ix, v, D, lay1.cell_to_pbsamp, lay1.num_pb)
+    stat = lg.CollapsedStat(D, S, 1)
+    lg.collect_matched_stat_coarse(ctx, lay1, gs, lay1.pb_sample_to_group, (mp1, md1), stat)
+    assert not np.asarray(stat.imputed_sum_ds).any() and not np.asarray(stat.residual_sum_ds).any()
+
+
+def test_merge_stat_many_groups(lg, ctx):
+    rng = np.random.default_rng(13)
+    fine = rng.integers(0, 50, (300, 64)).astype(np.float32)
+    f2c = rng.integers(0, 37, 300).astype(np.uint32)
+    assert np.array_equal(lg.merge_stat(ctx, fine, f2c, 37), orc.merge_stat(fine, f2c, 37))
