@@ -334,10 +334,16 @@ def main():
             avail = psutil.virtual_memory().available
         except Exception:
             avail = 64 << 30
+        # host copies (download + pinned) of this rank's block; every rank of the node draws on the same host memory
         need = nnz_local * 12 * 2.5 + n_local * 8
+        budget = 0.4 * avail / max(world, 1)
         e2e_cells = n_local
-        if need > 0.5 * avail:
-            e2e_cells = max(1024, int(n_local * 0.5 * avail / need) // 1024 * 1024)
+        if need > budget:
+            e2e_cells = max(1024, int(n_local * budget / need) // 1024 * 1024)
+        if world > 1:  # same sample size on every rank
+            t_cells = torch.tensor([e2e_cells], dtype=torch.int64, device=dev)
+            dist.all_reduce(t_cells, op=dist.ReduceOp.MIN)
+            e2e_cells = int(t_cells.item())
         sub, _, _ = (blk, None, None) if e2e_cells == n_local else sim.sim_block(ctx, tabs, lo, lo + e2e_cells)
         ip, ix, v = sub.download()
         if sub is not blk:

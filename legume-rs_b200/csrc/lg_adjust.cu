@@ -506,10 +506,13 @@ __global__ void k_cell_to_pb(const uint32_t* __restrict__ grp, const uint32_t* _
 
 constexpr int PM_Q = 256;     // queries (centroids) per CTA
 constexpr int PM_CELLS = 64;  // cells of the target pb-sample per shared-memory tile
+constexpr int PM_U = 4;       // cells scored per pass over a query's coordinates (register tile)
 
 // key[q - q0][p] = min over the cells c of pb-sample p of (l2_sq(centroid_q, c) << 32 | c); ~0 when p is in
 // q's own batch (which covers p == q) or empty.  The minimum key is the first cell of p met when the batch's
 // cells are walked in (distance, index) order, i.e. what the reference's growing search reports for p.
+// One thread per query; PM_U cells share every load of the query's coordinates, each with the reference's own
+// 16 lane accumulators (knn/metric.rs:19-45), so the distances are bit-exact and the loop is FP-issue bound.
 __global__ void __launch_bounds__(PM_Q) k_pb_min_dist(const float* __restrict__ proj, int K, const uint32_t* __restrict__ cell_sorted,
                                                       const uint64_t* __restrict__ pb_off, const float* __restrict__ centroids,
                                                       const uint32_t* __restrict__ pb_batch, uint32_t npb, uint32_t q0, uint32_t nq,
@@ -530,6 +533,7 @@ __global__ void __launch_bounds__(PM_Q) k_pb_min_dist(const float* __restrict__ 
     const bool want = live && pb_batch[q] != pbatch;
     unsigned long long best = ~0ull;
     const uint64_t lo = pb_off[p], hi = pb_off[p + 1];
+    const float* myq = qs + (size_t)threadIdx.x * ds;
     for (uint64_t base = lo; base < hi; base += PM_CELLS) {
         const int nt = (int)min((uint64_t)PM_CELLS, hi - base);
         __syncthreads();
@@ -537,13 +541,43 @@ __global__ void __launch_bounds__(PM_Q) k_pb_min_dist(const float* __restrict__ 
         __syncthreads();
         for (int e = threadIdx.x; e < nt * K; e += PM_Q) cs[e] = proj[(size_t)cell_id[e / K] * K + (e % K)];
         __syncthreads();
-        if (want) {
-            const float* myq = qs + (size_t)threadIdx.x * ds;
-            for (int t = 0; t < nt; ++t) {
-                const float d2 = adj_l2_sq(cs + (size_t)t * K, myq, K);
-                const unsigned long long key = ((unsigned long long)__float_as_uint(d2) << 32) | cell_id[t];
+        if (!want) continue;
+        int t = 0;
+        for (; t + PM_U <= nt; t += PM_U) {
+            float acc[PM_U][16];
+#pragma unroll
+            for (int u = 0; u < PM_U; ++u)
+#pragma unroll
+                for (int l = 0; l < 16; ++l) acc[u][l] = 0.0f;
+            int c = 0;
+            for (; c + 16 <= K; c += 16) {
+#pragma unroll
+                for (int l = 0; l < 16; ++l) {
+                    const float qv = myq[c + l];
+#pragma unroll
+                    for (int u = 0; u < PM_U; ++u) {
+                        const float df = __fsub_rn(cs[(size_t)(t + u) * K + c + l], qv);
+                        acc[u][l] = __fadd_rn(acc[u][l], __fmul_rn(df, df));
+                    }
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < PM_U; ++u) {
+                float sum = 0.0f;
+#pragma unroll
+                for (int l = 0; l < 16; ++l) sum = __fadd_rn(sum, acc[u][l]);
+                for (int cc = c; cc < K; ++cc) {
+                    const float df = __fsub_rn(cs[(size_t)(t + u) * K + cc], myq[cc]);
+                    sum = __fadd_rn(sum, __fmul_rn(df, df));
+                }
+                const unsigned long long key = ((unsigned long long)__float_as_uint(sum) << 32) | cell_id[t + u];
                 best = key < best ? key : best;
             }
+        }
+        for (; t < nt; ++t) {
+            const float d2 = adj_l2_sq(cs + (size_t)t * K, myq, K);
+            const unsigned long long key = ((unsigned long long)__float_as_uint(d2) << 32) | cell_id[t];
+            best = key < best ? key : best;
         }
     }
     if (live) keys[(size_t)ql * npb + p] = best;
