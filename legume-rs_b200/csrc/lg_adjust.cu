@@ -21,6 +21,7 @@
 #include <numeric>
 
 #include "lg_common.cuh"
+#include "lg_umma.cuh"
 
 int lg_knn_topk_device(lg_ctx* ctx, const float* d_ref, uint64_t nr, const float* d_qry, uint64_t nq, int d, int k,
                        const uint32_t* d_ex, uint32_t* d_idx, float* d_dist, int squared);
@@ -208,67 +209,66 @@ __global__ void k_scatter_matches(const uint32_t* __restrict__ knn_idx, const fl
 // ------------------------------------------------------------------------------------------------
 // collect_matched_stat_visitor
 // ------------------------------------------------------------------------------------------------
-constexpr int MS_THREADS = 256;   // one CTA per SM (the accumulators fill shared memory); 4 nnz per thread per pass
-constexpr int MS_PF = 6;          // matched columns in flight (cp.async ring: 2 x 16 B per thread per stage)
-constexpr size_t MS_RING_BYTES = (size_t)MS_PF * 2 * MS_THREADS * 16;
-constexpr int MS_SEG = 128;       // source cells per work item
-constexpr int MS_MAXR = 16;       // gene ranges
-constexpr int MS_PASS = MS_THREADS * 4;
+constexpr int MS_NW = 8;           // worker warps: each owns one gene sub-range of the CTA's range
+constexpr int MS_THREADS = (MS_NW + 1) * 32;  // + one warp that prepares the next cell's descriptors
+constexpr int MS_PF = 6;           // matched columns in flight per warp (cp.async ring: 2 x 16 B per lane per stage)
+constexpr size_t MS_RING_BYTES = (size_t)MS_NW * MS_PF * 2 * 32 * 16;
+constexpr int MS_SEG = 128;        // source cells per work item
+constexpr int MS_MAXR = 16;        // gene ranges
+constexpr int MS_PASS = 32 * 4;    // nnz per warp and pass
 
-struct MatchDesc {
-    unsigned long long lo;  // first nnz of the matched column inside this gene range
-    uint32_t n;             // nnz of the matched column inside this gene range
-    float w;                // softmax weight
-};
-
-// per cell: sum of the column, and the nnz offsets at which the row index crosses each gene-range boundary
-__global__ void k_cell_ranges(const uint64_t* __restrict__ indptr, const uint32_t* __restrict__ indices,
-                              const float* __restrict__ values, uint64_t ncols, uint32_t W, int R, float* __restrict__ colsum,
-                              uint32_t* __restrict__ split, unsigned int* __restrict__ max_part) {
+// per cell: sum of the column (one warp per cell)
+__global__ void k_cell_colsum(const uint64_t* __restrict__ indptr, const float* __restrict__ values, uint64_t ncols,
+                              float* __restrict__ colsum) {
     const int lane = threadIdx.x & 31;
     const uint64_t j = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (j >= ncols) return;
     const uint64_t lo = indptr[j], hi = indptr[j + 1];
     float s = 0.0f;
-    uint32_t below[MS_MAXR];
-#pragma unroll
-    for (int r = 0; r < MS_MAXR; ++r) below[r] = 0;
-    for (uint64_t t = lo + lane; t < hi; t += 32) {
-        s += values[t];
-        const uint32_t g = indices[t];
-#pragma unroll
-        for (int r = 1; r < MS_MAXR; ++r)
-            if (r < R) below[r] += (g < (uint32_t)r * W) ? 1u : 0u;
-    }
+    for (uint64_t t = lo + lane; t < hi; t += 32) s += values[t];
 #pragma unroll
     for (int off = 16; off >= 1; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
-    uint32_t prev = 0, mx = 0;
-#pragma unroll
-    for (int r = 1; r < MS_MAXR; ++r) {
-        if (r < R) {
-            uint32_t b = below[r];
-#pragma unroll
-            for (int off = 16; off >= 1; off >>= 1) b += __shfl_xor_sync(0xffffffffu, b, off);
-            if (lane == 0) split[j * (uint64_t)(R + 1) + r] = b;
-            mx = max(mx, b - prev);
-            prev = b;
-        }
-    }
-    if (lane == 0) {
-        split[j * (uint64_t)(R + 1)] = 0;
-        split[j * (uint64_t)(R + 1) + R] = (uint32_t)(hi - lo);
-        mx = max(mx, (uint32_t)(hi - lo) - prev);
-        colsum[j] = s;
-        atomicMax(max_part, mx);
-    }
+    if (lane == 0) colsum[j] = s;
 }
 
+// split[j][b] = number of entries of column j with row < b * wsub, b = 0 .. nb (rows are sorted: a binary search)
+__global__ void k_cell_splits(const uint64_t* __restrict__ indptr, const uint32_t* __restrict__ indices, uint64_t ncols, uint32_t wsub,
+                              uint32_t nb, uint32_t* __restrict__ split) {
+    const uint64_t e = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= ncols * (uint64_t)(nb + 1)) return;
+    const uint64_t j = e / (nb + 1);
+    const uint32_t b = (uint32_t)(e % (nb + 1));
+    const uint64_t lo = indptr[j], hi = indptr[j + 1];
+    const uint64_t bound = (uint64_t)b * wsub;
+    uint64_t a = lo, z = hi;
+    while (a < z) {
+        const uint64_t mid = (a + z) >> 1;
+        if ((uint64_t)indices[mid] < bound) a = mid + 1;
+        else z = mid;
+    }
+    split[e] = (uint32_t)(a - lo);
+}
+__global__ void k_max_part(const uint32_t* __restrict__ split, uint64_t ncols, uint32_t nb, unsigned int* __restrict__ max_part) {
+    const uint64_t e = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= ncols * (uint64_t)nb) return;
+    const uint64_t j = e / nb;
+    const uint32_t b = (uint32_t)(e % nb);
+    const unsigned int n = split[j * (nb + 1) + b + 1] - split[j * (nb + 1) + b];
+    unsigned int m = n;
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, off));
+    if ((threadIdx.x & 31) == 0) atomicMax(max_part, m);
+}
+
+struct MatchW {
+    uint32_t m;  // matched cell (>= ncols: empty slot)
+    float w;     // softmax weight
+};
+
 // per source cell (one warp): softmax(-d) over its matched columns (dmatrix_util.rs:649-671: the MIN logit is
-// subtracted), the division scale sum(y1) / sum(y_hat) (dmatrix_util.rs:145-176), and one descriptor per
-// (gene range, matched column)
-__global__ void k_match_desc(const uint64_t* __restrict__ indptr, const uint32_t* __restrict__ split, const float* __restrict__ colsum,
-                             uint64_t ncols, const uint32_t* __restrict__ midx, const float* __restrict__ mdist, uint32_t T, int R,
-                             MatchDesc* __restrict__ desc, float* __restrict__ scale) {
+// subtracted) and the division scale sum(y1) / sum(y_hat) (dmatrix_util.rs:145-176)
+__global__ void k_match_weights(const float* __restrict__ colsum, uint64_t ncols, const uint32_t* __restrict__ midx,
+                                const float* __restrict__ mdist, uint32_t T, MatchW* __restrict__ mw, float* __restrict__ scale) {
     const int lane = threadIdx.x & 31;
     const uint64_t j = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (j >= ncols) return;
@@ -288,20 +288,11 @@ __global__ void k_match_desc(const uint64_t* __restrict__ indptr, const uint32_t
     for (uint32_t t = lane; t < T; t += 32) {
         const uint32_t m = mi[t];
         const bool ok = m < ncols;
-        const float w = ok ? __fdiv_rn(expf(-md[t] - lmin), denom) : 0.0f;
-        if (ok) dsum += w * colsum[m];
-        for (int r = 0; r < R; ++r) {
-            MatchDesc d;
-            d.lo = 0;
-            d.n = 0;
-            d.w = w;
-            if (ok) {
-                const uint32_t a = split[m * (uint64_t)(R + 1) + r], b = split[m * (uint64_t)(R + 1) + r + 1];
-                d.lo = indptr[m] + a;
-                d.n = b - a;
-            }
-            desc[(j * R + r) * (uint64_t)T + t] = d;
-        }
+        MatchW o;
+        o.m = ok ? m : NONE;
+        o.w = ok ? __fdiv_rn(expf(-md[t] - lmin), denom) : 0.0f;
+        if (ok) dsum += o.w * colsum[m];
+        mw[j * T + t] = o;
     }
 #pragma unroll
     for (int off = 16; off >= 1; off >>= 1) dsum += __shfl_xor_sync(0xffffffffu, dsum, off);
@@ -319,142 +310,203 @@ __device__ __forceinline__ void cp_async_wait() {
     asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
 }
 
-// grid = (segments, gene ranges).  The CTA walks its source cells in ascending order; for each one it
-// streams the matched columns one at a time (rows are unique inside a column, so plain shared-memory
-// read-modify-writes are race-free and the accumulation order is fixed).  A thread owns one 16-byte-aligned
-// group of 4 nnz per pass; the next MS_PF columns are already on their way into a shared-memory ring through
-// cp.async (each thread only ever reads back its own 32 bytes, so the ring needs no barrier of its own).
+// what one worker warp needs for one matched column (or for the cell's own column): its sub-range of the column
+struct SubSeg {
+    unsigned long long lo;  // first nnz inside this warp's gene sub-range
+    uint32_t n;             // nnz inside it
+    float w;                // softmax weight (own column: the division scale)
+};
+
+// grid = (segments, gene ranges).  The CTA walks its source cells in ascending order.  The gene range is cut into
+// MS_NW sub-ranges, one per worker warp: rows are sorted inside a column, so a warp's share of any column is one
+// contiguous piece, and because no other warp ever touches its genes the warp streams the matched columns in order
+// with plain shared-memory read-modify-writes — fixed accumulation order, no CTA barrier, no atomics.  Each warp
+// keeps MS_PF columns in flight through its own cp.async ring; a ninth warp resolves the NEXT cell's pieces
+// (indptr + split look-ups) into a double-buffered table while the workers are busy.
 __global__ void __launch_bounds__(MS_THREADS, 1) k_matched_stat(
     const uint64_t* __restrict__ indptr, const uint32_t* __restrict__ indices, const float* __restrict__ values, uint64_t nnz_total,
     const uint32_t* __restrict__ split, const uint32_t* __restrict__ cell_sorted, const uint32_t* __restrict__ seg_first,
     const uint32_t* __restrict__ seg_len, const uint32_t* __restrict__ seg_group, const uint8_t* __restrict__ seg_single,
-    const MatchDesc* __restrict__ desc, const float* __restrict__ scale, uint32_t T, int R, uint64_t D, uint32_t W, uint32_t pmax,
-    float* __restrict__ scratch, float* __restrict__ out_imp, float* __restrict__ out_res) {
+    const MatchW* __restrict__ mw, const float* __restrict__ scale, uint64_t ncols, uint32_t T, int R, uint64_t D, uint32_t W,
+    uint32_t wsub, uint32_t pmax, float* __restrict__ scratch, float* __restrict__ out_imp, float* __restrict__ out_res) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    uint4* ring = reinterpret_cast<uint4*>(smem_raw);  // [MS_PF][2][MS_THREADS]
-    float* imp = reinterpret_cast<float*>(smem_raw + MS_RING_BYTES);
+    uint4* ring = reinterpret_cast<uint4*>(smem_raw);                               // [MS_NW][MS_PF][2][32]
+    SubSeg* tab = reinterpret_cast<SubSeg*>(smem_raw + MS_RING_BYTES);              // [2][T + 1][MS_NW]; entry T = own column
+    float* imp = reinterpret_cast<float*>(tab + (size_t)2 * (T + 1) * MS_NW);
     float* res = imp + W;
-    float* yhat = res + W;
-    float* pat_v = yhat + pmax;
-    uint32_t* pat_g = reinterpret_cast<uint32_t*>(pat_v + pmax);
-    MatchDesc* dsc = reinterpret_cast<MatchDesc*>(pat_g + pmax);  // W and pmax are multiples of 4: still 16-byte aligned
-    unsigned short* slot = reinterpret_cast<unsigned short*>(dsc + T);
-    const int tid = threadIdx.x;
+    float* yhat = res + W;                                                          // [MS_NW][pmax]
+    float* pat_v = yhat + (size_t)MS_NW * pmax;
+    uint32_t* pat_g = reinterpret_cast<uint32_t*>(pat_v + (size_t)MS_NW * pmax);
+    unsigned short* slot = reinterpret_cast<unsigned short*>(pat_g + (size_t)MS_NW * pmax);
+    __shared__ uint64_t bar_full[2], bar_empty[2];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t seg = blockIdx.x;
     const int r = blockIdx.y;
     const uint32_t g0 = (uint32_t)r * W;
-    const uint32_t Wr = (uint32_t)min((uint64_t)W, D - g0);
+    const uint32_t Wr = g0 < D ? (uint32_t)min((uint64_t)W, D - g0) : 0u;
+    const uint32_t nb = (uint32_t)R * MS_NW;
     for (uint32_t g = tid; g < W; g += MS_THREADS) {
         imp[g] = 0.0f;
         res[g] = 0.0f;
         slot[g] = 0xFFFF;
     }
-    // synchronous fetch of one aligned group of 4 entries starting at element c (long columns, array tail)
-    auto fetch = [&](unsigned long long c, uint4& g, float4& v) {
-        if (c + 4 <= nnz_total) {
-            g = __ldg(reinterpret_cast<const uint4*>(indices + c));
-            v = __ldg(reinterpret_cast<const float4*>(values + c));
-        } else {  // the last, partial group of the whole array
-            uint32_t gg[4] = {0, 0, 0, 0};
-            float vv[4] = {0.f, 0.f, 0.f, 0.f};
-            for (int u = 0; u < 4; ++u)
-                if (c + u < nnz_total) {
-                    gg[u] = indices[c + u];
-                    vv[u] = values[c + u];
-                }
-            g = make_uint4(gg[0], gg[1], gg[2], gg[3]);
-            v = make_float4(vv[0], vv[1], vv[2], vv[3]);
+    if (tid == 0) {
+        for (int b = 0; b < 2; ++b) {
+            umma::mbar_init(&bar_full[b], 1);
+            umma::mbar_init(&bar_empty[b], MS_NW);
         }
-    };
-    auto apply4 = [&](unsigned long long c, unsigned long long lo, uint32_t n, float w, const uint4& g, const float4& v) {
-        const uint32_t e0 = (uint32_t)(c - lo);  // position of the group's first entry in the column (wraps below 0: masked)
-        const uint32_t gi[4] = {g.x - g0, g.y - g0, g.z - g0, g.w - g0};
-        const float vi[4] = {v.x, v.y, v.z, v.w};
-        bool ok[4];
-        float a[4], term[4];
-        unsigned short sl[4];
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            ok[u] = (e0 + (uint32_t)u) < n;
-            a[u] = ok[u] ? imp[gi[u]] : 0.0f;  // rows are distinct inside a column: the four updates never alias
-            sl[u] = ok[u] ? slot[gi[u]] : (unsigned short)0xFFFF;
-            term[u] = __fmul_rn(w, vi[u]);
-        }
-#pragma unroll
-        for (int u = 0; u < 4; ++u)
-            if (ok[u]) imp[gi[u]] = __fadd_rn(a[u], term[u]);
-#pragma unroll
-        for (int u = 0; u < 4; ++u)
-            if (sl[u] != 0xFFFF) yhat[sl[u]] = __fadd_rn(yhat[sl[u]], term[u]);
-    };
-    // asynchronous copy of this thread's group of column t into ring stage s (always commits, so group counts stay uniform)
-    auto issue = [&](uint32_t t, int s) {
-        if (t < T) {
-            const unsigned long long lo = dsc[t].lo;
-            const unsigned long long c = (lo & ~3ull) + 4ull * tid;
-            const bool on = (c < lo + dsc[t].n) && (c + 4 <= nnz_total);
-            const unsigned long long cs = on ? c : 0ull;
-            cp_async16(&ring[(s * 2 + 0) * MS_THREADS + tid], indices + cs, on);
-            cp_async16(&ring[(s * 2 + 1) * MS_THREADS + tid], values + cs, on);
-        }
-        cp_async_commit();
-    };
+        umma::fence_barrier_init();
+    }
+    __syncthreads();
     const uint32_t p0 = seg_first[seg], np_cells = seg_len[seg];
-    for (uint32_t p = 0; p < np_cells; ++p) {
-        const uint32_t j = cell_sorted[p0 + p];
-        const uint64_t own_lo = indptr[j] + split[j * (uint64_t)(R + 1) + r];
-        const uint32_t own_n = split[j * (uint64_t)(R + 1) + r + 1] - split[j * (uint64_t)(R + 1) + r];
-        __syncthreads();  // previous cell fully retired (slots cleared) and, first time, the accumulators zeroed
-        for (uint32_t t = tid; t < T; t += MS_THREADS) dsc[t] = desc[((uint64_t)j * R + r) * T + t];
-        __syncthreads();
-#pragma unroll
-        for (int s = 0; s < MS_PF; ++s) issue(s, s);
-        for (uint32_t i = tid; i < own_n; i += MS_THREADS) {
-            const uint32_t g = indices[own_lo + i] - g0;
-            pat_g[i] = g;
-            pat_v[i] = values[own_lo + i];
-            yhat[i] = 0.0f;
-            slot[g] = (unsigned short)i;
-        }
-        const float sc = scale[j];
-        __syncthreads();
-        for (uint32_t t0 = 0; t0 < T; t0 += MS_PF) {
-#pragma unroll
-            for (int s = 0; s < MS_PF; ++s) {
-                const uint32_t t = t0 + s;
-                const uint32_t n = t < T ? dsc[t].n : 0u;  // CTA-uniform
-                cp_async_wait<MS_PF - 1>();                // this thread's copies for column t have landed
-                if (n) {
-                    const float w = dsc[t].w;
-                    const unsigned long long lo = dsc[t].lo;
-                    const unsigned long long c0 = (lo & ~3ull) + 4ull * tid;
-                    if (c0 < lo + n) {
-                        uint4 g = ring[(s * 2 + 0) * MS_THREADS + tid];
-                        uint4 vb = ring[(s * 2 + 1) * MS_THREADS + tid];
-                        float4 v = make_float4(__uint_as_float(vb.x), __uint_as_float(vb.y), __uint_as_float(vb.z), __uint_as_float(vb.w));
-                        if (c0 + 4 > nnz_total) fetch(c0, g, v);
-                        apply4(c0, lo, n, w, g, v);
-                    }
-                    for (unsigned long long c = c0 + MS_PASS; c < lo + n; c += MS_PASS) {  // columns longer than one pass
-                        uint4 g;
-                        float4 v;
-                        fetch(c, g, v);
-                        apply4(c, lo, n, w, g, v);
-                    }
+
+    if (warp == MS_NW) {
+        // ===== descriptor warp: one cell ahead of the workers =====
+        for (uint32_t p = 0; p < np_cells; ++p) {
+            const uint32_t buf = p & 1;
+            if (p >= 2) umma::mbar_wait(&bar_empty[buf], ((p >> 1) - 1) & 1);
+            const uint32_t j = cell_sorted[p0 + p];
+            SubSeg* tb = tab + (size_t)buf * (T + 1) * MS_NW;
+            for (uint32_t t = lane; t <= T; t += 32) {
+                uint32_t m;
+                float w;
+                if (t < T) {
+                    const MatchW x = mw[(uint64_t)j * T + t];
+                    m = x.m;
+                    w = x.w;
+                } else {
+                    m = j;
+                    w = scale[j];
                 }
-                issue(t + MS_PF, s);
-                if (n) __syncthreads();  // the next column may touch the same genes
+                const bool ok = m < ncols;
+                const unsigned long long base = ok ? indptr[m] : 0ull;
+                const uint32_t* sp = split + (uint64_t)(ok ? m : 0) * (nb + 1) + (uint32_t)r * MS_NW;
+                uint32_t prev = ok ? sp[0] : 0u;
+#pragma unroll
+                for (int w8 = 0; w8 < MS_NW; ++w8) {
+                    const uint32_t nxt = ok ? sp[w8 + 1] : 0u;
+                    SubSeg s;
+                    s.lo = base + prev;
+                    s.n = nxt - prev;
+                    s.w = w;
+                    tb[(size_t)t * MS_NW + w8] = s;
+                    prev = nxt;
+                }
             }
+            __syncwarp();
+            if (lane == 0) umma::mbar_arrive(&bar_full[buf]);
         }
-        cp_async_wait<0>();
-        __syncthreads();
-        for (uint32_t i = tid; i < own_n; i += MS_THREADS) {
-            const float d = yhat[i];
-            float x = pat_v[i];
-            if (d > 0.0f) x = __fdiv_rn(x, __fmul_rn(d, sc));
-            const uint32_t g = pat_g[i];
-            res[g] = __fadd_rn(res[g], x);
-            slot[g] = 0xFFFF;
+    } else {
+        // ===== worker warp: owns genes [g0 + warp * wsub, g0 + (warp + 1) * wsub) =====
+        uint4* myring = ring + (size_t)warp * MS_PF * 2 * 32;
+        float* my_yhat = yhat + (size_t)warp * pmax;
+        float* my_pv = pat_v + (size_t)warp * pmax;
+        uint32_t* my_pg = pat_g + (size_t)warp * pmax;
+        auto fetch = [&](unsigned long long c, uint4& g, float4& v) {  // synchronous: long pieces and the array tail
+            if (c + 4 <= nnz_total) {
+                g = __ldg(reinterpret_cast<const uint4*>(indices + c));
+                v = __ldg(reinterpret_cast<const float4*>(values + c));
+            } else {
+                uint32_t gg[4] = {0, 0, 0, 0};
+                float vv[4] = {0.f, 0.f, 0.f, 0.f};
+                for (int u = 0; u < 4; ++u)
+                    if (c + u < nnz_total) {
+                        gg[u] = indices[c + u];
+                        vv[u] = values[c + u];
+                    }
+                g = make_uint4(gg[0], gg[1], gg[2], gg[3]);
+                v = make_float4(vv[0], vv[1], vv[2], vv[3]);
+            }
+        };
+        auto apply4 = [&](unsigned long long c, unsigned long long lo, uint32_t n, float w, const uint4& g, const float4& v) {
+            const uint32_t e0 = (uint32_t)(c - lo);  // position of the group's first entry in the piece (wraps below 0: masked)
+            const uint32_t gi[4] = {g.x - g0, g.y - g0, g.z - g0, g.w - g0};
+            const float vi[4] = {v.x, v.y, v.z, v.w};
+            bool ok[4];
+            float a[4], term[4];
+            unsigned short sl[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                ok[u] = (e0 + (uint32_t)u) < n;
+                a[u] = ok[u] ? imp[gi[u]] : 0.0f;  // rows are distinct inside a column: the four updates never alias
+                sl[u] = ok[u] ? slot[gi[u]] : (unsigned short)0xFFFF;
+                term[u] = __fmul_rn(w, vi[u]);
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+                if (ok[u]) imp[gi[u]] = __fadd_rn(a[u], term[u]);
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+                if (sl[u] != 0xFFFF) my_yhat[sl[u]] = __fadd_rn(my_yhat[sl[u]], term[u]);
+        };
+        for (uint32_t p = 0; p < np_cells; ++p) {
+            const uint32_t buf = p & 1;
+            umma::mbar_wait(&bar_full[buf], (p >> 1) & 1);
+            const SubSeg* tb = tab + (size_t)buf * (T + 1) * MS_NW + warp;  // stride MS_NW between columns
+            auto issue = [&](uint32_t t, int s) {
+                if (t < T) {
+                    const SubSeg d = tb[(size_t)t * MS_NW];
+                    const unsigned long long c = (d.lo & ~3ull) + 4ull * lane;
+                    const bool on = (c < d.lo + d.n) && (c + 4 <= nnz_total);
+                    const unsigned long long cs = on ? c : 0ull;
+                    cp_async16(&myring[(s * 2 + 0) * 32 + lane], indices + cs, on);
+                    cp_async16(&myring[(s * 2 + 1) * 32 + lane], values + cs, on);
+                }
+                cp_async_commit();
+            };
+#pragma unroll
+            for (int s = 0; s < MS_PF; ++s) issue(s, s);
+            // this warp's share of the source cell's own column: pattern, values, slot map
+            const SubSeg own = tb[(size_t)T * MS_NW];
+            for (uint32_t i = lane; i < own.n; i += 32) {
+                const uint32_t g = indices[own.lo + i] - g0;
+                my_pg[i] = g;
+                my_pv[i] = values[own.lo + i];
+                my_yhat[i] = 0.0f;
+                slot[g] = (unsigned short)i;
+            }
+            __syncwarp();
+            for (uint32_t t0 = 0; t0 < T; t0 += MS_PF) {
+#pragma unroll
+                for (int s = 0; s < MS_PF; ++s) {
+                    const uint32_t t = t0 + s;
+                    cp_async_wait<MS_PF - 1>();  // this lane's copies for column t have landed
+                    if (t < T) {
+                        const SubSeg d = tb[(size_t)t * MS_NW];
+                        if (d.n) {  // warp-uniform
+                            const unsigned long long c0 = (d.lo & ~3ull) + 4ull * lane;
+                            if (c0 < d.lo + d.n) {
+                                uint4 g = myring[(s * 2 + 0) * 32 + lane];
+                                const uint4 vb = myring[(s * 2 + 1) * 32 + lane];
+                                float4 v = make_float4(__uint_as_float(vb.x), __uint_as_float(vb.y), __uint_as_float(vb.z), __uint_as_float(vb.w));
+                                if (c0 + 4 > nnz_total) fetch(c0, g, v);
+                                apply4(c0, d.lo, d.n, d.w, g, v);
+                            }
+                            for (unsigned long long c = c0 + MS_PASS; c < d.lo + d.n; c += MS_PASS) {  // pieces longer than one pass
+                                uint4 g;
+                                float4 v;
+                                fetch(c, g, v);
+                                apply4(c, d.lo, d.n, d.w, g, v);
+                            }
+                            __syncwarp();  // the next column may touch the same genes from other lanes
+                        }
+                    }
+                    issue(t + MS_PF, s);
+                }
+            }
+            cp_async_wait<0>();
+            __syncwarp();
+            const float sc = own.w;
+            for (uint32_t i = lane; i < own.n; i += 32) {
+                const float d = my_yhat[i];
+                float x = my_pv[i];
+                if (d > 0.0f) x = __fdiv_rn(x, __fmul_rn(d, sc));
+                const uint32_t g = my_pg[i];
+                res[g] = __fadd_rn(res[g], x);
+                slot[g] = 0xFFFF;
+            }
+            __syncwarp();
+            if (lane == 0) umma::mbar_arrive(&bar_empty[buf]);
         }
     }
     __syncthreads();
@@ -827,7 +879,7 @@ extern "C" int lg_collect_matched_stat(lg_ctx* ctx, const lg_csc* m, const uint3
     if (!ctx) return LG_ERR_INVALID;
     LG_REQUIRE(ctx, m && group_of_cell && matched_idx && matched_dist && out_imputed_ds && out_residual_ds,
                "lg_collect_matched_stat: null argument");
-    LG_REQUIRE(ctx, T >= 1 && T <= 4096 && S >= 1, "lg_collect_matched_stat: T must be in [1, 4096] and S >= 1");
+    LG_REQUIRE(ctx, T >= 1 && T <= 1024 && S >= 1, "lg_collect_matched_stat: T must be in [1, 1024] and S >= 1");
     cudaSetDevice(ctx->device);
     LgStage st(ctx);
     const uint64_t N = m->ncols, D = m->nrows;
@@ -847,34 +899,39 @@ extern "C" int lg_collect_matched_stat(lg_ctx* ctx, const lg_csc* m, const uint3
     LG_CUDA(ctx, cudaMemsetAsync(d_res, 0, sizeof(float) * (size_t)D * S, ctx->stream));
     if (N == 0 || D == 0) return st.finish();
 
-    // gene ranges: per range two f32 accumulators + a u16 slot map (10 B per gene) next to the per-cell pattern
-    // buffers (12 B per own nnz) and the T descriptors
-    const size_t budget = ctx->smem_optin - 2048 - (size_t)T * sizeof(MatchDesc) - MS_RING_BYTES;
+    // gene ranges: per range two f32 accumulators + a u16 slot map (10 B per gene) next to the cp.async rings, the
+    // double-buffered piece table and the per-warp pattern buffers (12 B per own nnz of a sub-range)
+    const size_t fixed = MS_RING_BYTES + (size_t)2 * (T + 1) * MS_NW * sizeof(SubSeg) + 2048;
+    LG_REQUIRE(ctx, fixed + 4096 < ctx->smem_optin, "lg_collect_matched_stat: T too large for shared memory");
+    const size_t budget = ctx->smem_optin - fixed;
     int R = 1;
-    uint32_t W = (uint32_t)D, pmax = 0;
+    uint32_t W = 0, wsub = 0, pmax = 0;
     float* d_colsum;
     uint32_t* d_split = nullptr;
     unsigned int* d_maxpart;
     LG_TRY(st.scratch(N, &d_colsum));
     LG_TRY(st.scratch(1, &d_maxpart));
+    LG_LAUNCH(ctx, k_cell_colsum, (unsigned)((N * 32 + 255) / 256), 256, 0, m->indptr, m->values, N, d_colsum);
     for (;; ++R) {
         LG_REQUIRE(ctx, R <= MS_MAXR, "lg_collect_matched_stat: too many genes for the shared-memory accumulators");
-        W = (uint32_t)((D + R - 1) / R);
-        W = (W + 7) & ~7u;
+        wsub = (uint32_t)((D + (uint64_t)R * MS_NW - 1) / ((uint64_t)R * MS_NW));
+        wsub = (wsub + 7) & ~7u;
+        W = wsub * MS_NW;
         if ((size_t)W * 10 + 64 > budget) continue;
-        LG_TRY(st.scratch((size_t)N * (R + 1), &d_split));
+        const uint32_t nb = (uint32_t)R * MS_NW;
+        LG_TRY(st.scratch((size_t)N * (nb + 1), &d_split));
         LG_CUDA(ctx, cudaMemsetAsync(d_maxpart, 0, sizeof(unsigned int), ctx->stream));
-        LG_LAUNCH(ctx, k_cell_ranges, (unsigned)((N * 32 + 255) / 256), 256, 0, m->indptr, m->indices, m->values, N, W, R, d_colsum,
-                  d_split, d_maxpart);
+        LG_LAUNCH(ctx, k_cell_splits, (unsigned)((N * (nb + 1) + 255) / 256), 256, 0, m->indptr, m->indices, N, wsub, nb, d_split);
+        LG_LAUNCH(ctx, k_max_part, (unsigned)((N * nb + 255) / 256), 256, 0, d_split, N, nb, d_maxpart);
         unsigned int* h = static_cast<unsigned int*>(ctx->pinned);
         LG_CUDA(ctx, cudaMemcpyAsync(h, d_maxpart, sizeof(unsigned int), cudaMemcpyDeviceToHost, ctx->stream));
         LG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
         pmax = (*h + 3) & ~3u;
         if (pmax < 4) pmax = 4;
-        if ((size_t)W * 10 + (size_t)pmax * 12 + 64 <= budget) break;
+        if ((size_t)W * 10 + (size_t)MS_NW * pmax * 12 + 64 <= budget) break;
     }
-    LG_REQUIRE(ctx, pmax < 65535, "lg_collect_matched_stat: a column holds more than 65534 entries in one gene range");
-    const size_t smem = MS_RING_BYTES + (size_t)W * 10 + (size_t)pmax * 12 + (size_t)T * sizeof(MatchDesc) + 64;
+    LG_REQUIRE(ctx, pmax < 65535, "lg_collect_matched_stat: a column holds more than 65534 entries in one gene sub-range");
+    const size_t smem = MS_RING_BYTES + (size_t)2 * (T + 1) * MS_NW * sizeof(SubSeg) + (size_t)W * 10 + (size_t)MS_NW * pmax * 12 + 64;
 
     // segments of at most MS_SEG group-sorted cells, never crossing a group boundary
     std::vector<uint32_t> counts;
@@ -906,19 +963,18 @@ extern "C" int lg_collect_matched_stat(lg_ctx* ctx, const lg_csc* m, const uint3
     LG_TRY(upload(ctx, st, seg_group, &d_seg_group));
     LG_TRY(upload(ctx, st, seg_single, &d_seg_single));
     LG_TRY(upload(ctx, st, group_seg0, &d_group_seg0));
-    MatchDesc* d_desc;
+    MatchW* d_mw;
     float *d_scale, *d_scratch;
-    LG_TRY(st.scratch((size_t)N * R * T, &d_desc));
+    LG_TRY(st.scratch((size_t)N * T, &d_mw));
     LG_TRY(st.scratch(N, &d_scale));
     const bool multi = std::any_of(seg_single.begin(), seg_single.end(), [](uint8_t x) { return x == 0; });
     LG_TRY(st.scratch(multi ? (size_t)nseg * 2 * D : 1, &d_scratch));
-    LG_LAUNCH(ctx, k_match_desc, (unsigned)((N * 32 + 255) / 256), 256, 0, m->indptr, d_split, d_colsum, N, d_midx, d_mdist, T, R,
-              d_desc, d_scale);
+    LG_LAUNCH(ctx, k_match_weights, (unsigned)((N * 32 + 255) / 256), 256, 0, d_colsum, N, d_midx, d_mdist, T, d_mw, d_scale);
     LG_CUDA(ctx, cudaFuncSetAttribute(k_matched_stat, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     {
         dim3 grid(nseg, (unsigned)R);
         k_matched_stat<<<grid, MS_THREADS, smem, ctx->stream>>>(m->indptr, m->indices, m->values, m->nnz, d_split, d_cell, d_seg_first, d_seg_len,
-                                                               d_seg_group, d_seg_single, d_desc, d_scale, T, R, D, W, pmax, d_scratch,
+                                                               d_seg_group, d_seg_single, d_mw, d_scale, N, T, R, D, W, wsub, pmax, d_scratch,
                                                                d_imp, d_res);
         ctx->launches++;
         LG_CUDA(ctx, cudaGetLastError());
