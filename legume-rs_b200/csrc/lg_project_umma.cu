@@ -19,6 +19,7 @@
 //     and leaves corr/norm and ln2/norm per cell.
 //   * K1a never materialises the dense A operand in memory: expander warps turn 64-bit bitmap words
 //     into 16 TMEM columns (u8 in {0, 128}) with two ALU ops per register and tcgen05.st them.
+#include <cstdio>
 #include <cstdlib>
 
 #include "lg_common.cuh"
@@ -32,16 +33,18 @@ constexpr int TILE_M = 128;          // cells per accumulator (UMMA M)
 constexpr int NT = 2;                // accumulators (cell tiles) per CTA
 constexpr int CELLS = TILE_M * NT;   // cells per CTA pass
 constexpr int GS = 128;              // genes per pipeline stage (4 MMAs of K = 32)
-constexpr int GC = 1024;             // genes per bitmap chunk (small chunks leave shared memory for a deep B ring)
-constexpr int BM_STRIDE = GC / 32 + 2;  // 34 words per cell row: 8-byte aligned, conflict-free LDS.64
-constexpr int NBST = 5;              // B-operand ring depth (stages)
+constexpr int GC = 2048;             // genes per bitmap chunk: K1b stores one 256-byte row piece per chunk (1024 costs it 1 ms)
+constexpr int BM_STRIDE = GC / 32 + 2;  // 66 words per cell row: 8-byte aligned, conflict-free LDS.64
+constexpr int NBST = 4;              // B-operand ring depth (stages)
+constexpr int NBM = 2;               // bitmap chunks in flight
 constexpr int NAST = 3;              // A-operand ring depth in TMEM (stages per tile)
 constexpr int A_COLS = GS / 4;       // 32 TMEM columns per A stage
 constexpr int N_EXP_WARPS = 4 * NT;  // 8 expander warps (also the epilogue)
-constexpr int WARP_MMA = N_EXP_WARPS;
-constexpr int WARP_LOAD_B = N_EXP_WARPS + 1;   // basis stages
-constexpr int WARP_LOAD_BM = N_EXP_WARPS + 2;  // bitmap chunks
-constexpr int THREADS = (N_EXP_WARPS + 3) * 32;  // 352
+constexpr int WARP_MMA = N_EXP_WARPS;           // NT issuing warps, one per cell tile: a single thread cannot issue
+                                                // 8 MMAs + their commits in the 640 clk the tensor pipe needs for them
+constexpr int WARP_LOAD_B = N_EXP_WARPS + NT;       // basis stages
+constexpr int WARP_LOAD_BM = N_EXP_WARPS + NT + 1;  // bitmap chunks
+constexpr int THREADS = (N_EXP_WARPS + NT + 2) * 32;  // 384
 constexpr uint32_t BM_CHUNK_BYTES = CELLS * BM_STRIDE * 4;  // 67584 bytes per (supertile, chunk)
 constexpr int PREP_WARPS = 8;
 constexpr float QSCALE = 1048576.0f;                       // 2^20
@@ -50,7 +53,7 @@ constexpr int QMAX = 127 * 65536 + 127 * 256 + 127;        // largest 3-digit si
 struct Barriers {
     uint64_t b_full[NBST], b_empty[NBST];
     uint64_t a_full[NT][NAST], a_empty[NT][NAST];
-    uint64_t bm_full[2], bm_empty[2];
+    uint64_t bm_full[NBM], bm_empty[NBM];
     uint64_t acc_full[NT], acc_empty[NT];
 };
 
@@ -290,11 +293,11 @@ __global__ void __launch_bounds__(THREADS, 1) k_project_umma(const uint32_t* __r
                                                              const int8_t* __restrict__ bq, int K, int NB, uint32_t nstages,
                                                              const float* __restrict__ scale, float* __restrict__ out) {
     extern __shared__ __align__(1024) uint8_t smem[];
-    // carve: [B ring][bitmap x2][barriers][tmem base]
+    // carve: [B ring][bitmap x NBM][barriers][tmem base]
     const uint32_t stage_bytes = (uint32_t)NB * 32u * (GS / 32);
     uint8_t* smem_b = smem;
     uint32_t* bitmap = reinterpret_cast<uint32_t*>(smem + (size_t)NBST * stage_bytes);
-    Barriers* bars = reinterpret_cast<Barriers*>(bitmap + 2 * CELLS * BM_STRIDE);
+    Barriers* bars = reinterpret_cast<Barriers*>(bitmap + NBM * CELLS * BM_STRIDE);
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 1);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -304,7 +307,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_project_umma(const uint32_t* __r
     if (threadIdx.x == 0) {
         for (int s = 0; s < NBST; ++s) {
             mbar_init(&bars->b_full[s], 1);
-            mbar_init(&bars->b_empty[s], 1);
+            mbar_init(&bars->b_empty[s], NT);
         }
         for (int t = 0; t < NT; ++t) {
             for (int s = 0; s < NAST; ++s) {
@@ -314,7 +317,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_project_umma(const uint32_t* __r
             mbar_init(&bars->acc_full[t], 1);
             mbar_init(&bars->acc_empty[t], 4);
         }
-        for (int b = 0; b < 2; ++b) {
+        for (int b = 0; b < NBM; ++b) {
             mbar_init(&bars->bm_full[b], 1);
             mbar_init(&bars->bm_empty[b], N_EXP_WARPS);
         }
@@ -340,8 +343,8 @@ __global__ void __launch_bounds__(THREADS, 1) k_project_umma(const uint32_t* __r
         for (uint64_t sup = blockIdx.x; sup < nsuper; sup += gridDim.x, ++super_it) {
             uint32_t stage = 0;
             for (uint32_t c = 0; c < nchunks; ++c, ++chunk_it) {
-                const uint32_t buf = chunk_it & 1;
-                mbar_wait(&bars->bm_full[buf], (chunk_it >> 1) & 1);
+                const uint32_t buf = chunk_it % NBM;
+                mbar_wait(&bars->bm_full[buf], (chunk_it / NBM) & 1);
                 const uint32_t* my = bitmap + (size_t)buf * CELLS * BM_STRIDE + (size_t)(t * TILE_M + row) * BM_STRIDE;
                 const uint32_t st_end = min(nstages, (c + 1) * (GC / GS));
                 for (uint32_t ls = 0; stage < st_end; ++stage, ++ls, ++a_it) {
@@ -408,32 +411,31 @@ __global__ void __launch_bounds__(THREADS, 1) k_project_umma(const uint32_t* __r
             __syncwarp();
             if (lane == 0) mbar_arrive(&bars->acc_empty[t]);
         }
-    } else if (warp == WARP_MMA) {
-        // ===== MMA issuer =====
+    } else if (warp >= WARP_MMA && warp < WARP_MMA + NT) {
+        // ===== MMA issuers: one elected thread per cell tile =====
+        const int t = warp - WARP_MMA;
         if (elect_one()) {
             const uint32_t idesc = make_idesc(CFMT_S32, FMT_U8, FMT_S8, TILE_M, (uint32_t)NB);
             uint32_t b_it = 0, a_it = 0, super_it = 0;
             for (uint64_t sup = blockIdx.x; sup < nsuper; sup += gridDim.x, ++super_it) {
-                for (int t = 0; t < NT; ++t) mbar_wait(&bars->acc_empty[t], (super_it & 1) ^ 1);
+                mbar_wait(&bars->acc_empty[t], (super_it & 1) ^ 1);
                 tc_fence_after();
                 for (uint32_t stage = 0; stage < nstages; ++stage, ++b_it, ++a_it) {
                     const uint32_t bs = b_it % NBST, as = a_it % NAST;
                     mbar_wait(&bars->b_full[bs], (b_it / NBST) & 1);
                     const uint32_t b_addr = smem_u32(smem_b + (size_t)bs * stage_bytes);
-                    for (int t = 0; t < NT; ++t) {
-                        mbar_wait(&bars->a_full[t][as], (a_it / NAST) & 1);
-                        tc_fence_after();
+                    mbar_wait(&bars->a_full[t][as], (a_it / NAST) & 1);
+                    tc_fence_after();
 #pragma unroll
-                        for (int j = 0; j < GS / 32; ++j) {
-                            const uint64_t db = make_smem_desc(b_addr + (uint32_t)j * NB * 32u, 128, 256);
-                            mma_i8_ts(tbase + (uint32_t)t * NB, tbase + a_col0 + (uint32_t)(t * NAST + as) * A_COLS + 8u * j, db, idesc,
-                                      stage > 0 || j > 0);
-                        }
-                        tc_commit(&bars->a_empty[t][as]);
+                    for (int j = 0; j < GS / 32; ++j) {
+                        const uint64_t db = make_smem_desc(b_addr + (uint32_t)j * NB * 32u, 128, 256);
+                        mma_i8_ts(tbase + (uint32_t)t * NB, tbase + a_col0 + (uint32_t)(t * NAST + as) * A_COLS + 8u * j, db, idesc,
+                                  stage > 0 || j > 0);
                     }
-                    tc_commit(&bars->b_empty[bs]);
+                    tc_commit(&bars->a_empty[t][as]);
+                    tc_commit(&bars->b_empty[bs]);  // NT arrivals free the B stage
                 }
-                for (int t = 0; t < NT; ++t) tc_commit(&bars->acc_full[t]);
+                tc_commit(&bars->acc_full[t]);
             }
         }
     } else if (warp == WARP_LOAD_B) {
@@ -455,8 +457,8 @@ __global__ void __launch_bounds__(THREADS, 1) k_project_umma(const uint32_t* __r
             uint32_t chunk_it = 0;
             for (uint64_t sup = blockIdx.x; sup < nsuper; sup += gridDim.x) {
                 for (uint32_t c = 0; c < nchunks; ++c, ++chunk_it) {
-                    const uint32_t buf = chunk_it & 1;
-                    mbar_wait(&bars->bm_empty[buf], ((chunk_it >> 1) & 1) ^ 1);
+                    const uint32_t buf = chunk_it % NBM;
+                    mbar_wait(&bars->bm_empty[buf], ((chunk_it / NBM) & 1) ^ 1);
                     mbar_arrive_expect_tx(&bars->bm_full[buf], BM_CHUNK_BYTES);
                     bulk_g2s(bitmap + (size_t)buf * CELLS * BM_STRIDE,
                              bm_global + (sup * nchunks + c) * (uint64_t)(CELLS * BM_STRIDE), BM_CHUNK_BYTES, &bars->bm_full[buf]);
@@ -496,6 +498,11 @@ int lg_project_raw_umma(lg_ctx* ctx, const lg_csc* m, const float* d_basis, int 
     LG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     if (*h_flag) return LG_OK;  // basis outside the fixed-point range (e.g. large row weights): fall back
 
+    const char* tr = getenv("LG_K1_TRACE");
+    const bool trace = tr && tr[0] == '1';
+    cudaEvent_t ev[3];
+    if (trace)
+        for (int i = 0; i < 3; ++i) cudaEventCreate(&ev[i]);
     // K1b first: bitmap + corr/norm in `out` + ln2/norm in `scale`; K1a then adds the tensor part
     const uint32_t nchunks = (uint32_t)((D + GC - 1) / GC);
     const uint64_t nsuper = (m->ncols + CELLS - 1) / CELLS;
@@ -520,17 +527,28 @@ int lg_project_raw_umma(lg_ctx* ctx, const lg_csc* m, const float* d_basis, int 
         LG_LAUNCH(ctx, (k_project_prep<NA, H2>), (unsigned)blocks, PREP_WARPS * 32, psmem, m->indptr, m->indices, m->values,      \
                   m->ncols, d_basis, K, nchunks, d_bm, d_out, d_scale);                                                             \
     } while (0)
+        if (trace) cudaEventRecord(ev[0], ctx->stream);
         if (half2) LG_PREP_LAUNCH(2, true);
         else if (nacc == 1) LG_PREP_LAUNCH(1, false);
         else LG_PREP_LAUNCH(2, false);
 #undef LG_PREP_LAUNCH
     }
     const size_t stage_bytes = (size_t)NB * 32 * (GS / 32);
-    const size_t smem = (size_t)NBST * stage_bytes + (size_t)2 * BM_CHUNK_BYTES + sizeof(Barriers) + 16;
+    const size_t smem = (size_t)NBST * stage_bytes + (size_t)NBM * BM_CHUNK_BYTES + sizeof(Barriers) + 16;
     if (smem > ctx->smem_optin) return lg_fail(ctx, LG_ERR_INTERNAL, "k_project_umma: shared memory budget exceeded");
     LG_CUDA(ctx, cudaFuncSetAttribute(k_project_umma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const unsigned grid = (unsigned)(nsuper < (uint64_t)ctx->num_sms ? nsuper : (uint64_t)ctx->num_sms);
+    if (trace) cudaEventRecord(ev[1], ctx->stream);
     LG_LAUNCH(ctx, k_project_umma, grid, THREADS, smem, d_bm, m->ncols, D, d_bq, K, NB, nstages, d_scale, d_out);
+    if (trace) {  // LG_K1_TRACE=1: per-kernel device times of this call (diagnostic; synchronises)
+        cudaEventRecord(ev[2], ctx->stream);
+        cudaEventSynchronize(ev[2]);
+        float a = 0.f, b = 0.f;
+        cudaEventElapsedTime(&a, ev[0], ev[1]);
+        cudaEventElapsedTime(&b, ev[1], ev[2]);
+        fprintf(stderr, "[lg_project] prep %.3f ms, umma %.3f ms\n", a, b);
+        for (int i = 0; i < 3; ++i) cudaEventDestroy(ev[i]);
+    }
     *used = 1;
     return LG_OK;
 }
