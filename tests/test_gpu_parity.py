@@ -439,3 +439,61 @@ def test_knn_tensor_path_is_exact(lg, ctx, nr, nq, d, k, kind):
     idx, dist = dct.search_indices(qry2, k)
     widx, wdist = orc.knn_topk(ref, qry2, k, nthreads=8)
     assert np.array_equal(idx, widx) and dist.tobytes() == wdist.tobytes()
+
+
+# ---- BASELINE-sized inputs: size-independent properties (the oracle does not finish at these sizes) ---------------
+def test_full_size_properties(lg, ctx):
+    """200k cells x 30k genes of the configs[1] generator (a fifth of it, same per-cell shape): conservation of
+    counts through the collapse, per-cell standardisation of the projection, code range, group ids dense and
+    ordered, posterior mean == (1 + sum) / (1 + n), kNN lists ascending with the query itself excluded"""
+    import torch
+    from legume_b200 import sim
+    from legume_b200.pipeline import HotPath
+    D, N, K, kk = 30000, 200_000, 50, 10
+    tabs = sim.make_tables(D, ntopic=8, nbatch=1, depth=1500, seed=42)
+    blk, _, _ = sim.sim_block(ctx, tabs, 0, N)
+    basis = torch.from_numpy(basis_for(D, K)).cuda()
+    batch = torch.zeros(N, dtype=torch.int32, device="cuda")
+    hp = HotPath(ctx)
+    out = hp.run(blk, basis, batch, 1, kk)
+    proj, codes, group = out["proj"], out["codes"], out["group"]
+    ip, ix, v = blk.download()
+    # projection: every cell standardised (population variance), nothing outside the clamp after re-scaling by much
+    assert float(proj.mean(1).abs().max()) < 1e-5 and float((proj.var(1, unbiased=False) - 1).abs().max()) < 1e-4
+    # codes and groups
+    assert int(codes.min()) >= 0 and int(codes.max()) < (1 << kk)
+    ng = out["num_groups"]
+    assert int(group.max()) == ng - 1 and len(torch.unique(group)) == ng
+    keys = sorted({str(int(c)) for c in torch.unique(codes).cpu().numpy()}, key=lambda s: s.encode())
+    lut = {int(k): i for i, k in enumerate(keys)}
+    sample = np.random.default_rng(0).integers(0, N, 2000)
+    assert all(lut[int(codes[j])] == int(group[j]) for j in sample)
+    # collapse: integer counts are conserved exactly, gene by gene and group by group
+    sum_ds, size_s = out["sum_ds"], out["size_s"]
+    assert float(size_s.sum()) == N
+    gene_tot = np.bincount(ix.astype(np.int64), weights=v.astype(np.float64), minlength=D)
+    assert np.array_equal(sum_ds.sum(0).double().cpu().numpy(), gene_tot)
+    cell_tot = np.add.reduceat(v.astype(np.float64), ip[:-1].astype(np.int64))
+    cell_tot[np.diff(ip.astype(np.int64)) == 0] = 0.0
+    grp_tot = np.bincount(group.cpu().numpy(), weights=cell_tot, minlength=ng)
+    assert np.array_equal(sum_ds.sum(1).double().cpu().numpy(), grp_tot)
+    # posterior (a0, b0) = (1, 1): mean = (1 + sum) / (1 + n)   (weighted_columns.rs:76-121)
+    want = (1.0 + sum_ds) / (1.0 + size_s[:, None])
+    assert close(out["posterior"]["mean"].cpu().numpy(), want.cpu().numpy(), TOL)
+    # kNN on the tensor path at a size the oracle cannot check: ascending, self excluded, exact distances
+    q = proj[:20000].contiguous()
+    excl = torch.arange(20000, dtype=torch.int32, device="cuda")
+    idx = torch.empty((20000, 10), dtype=torch.int32, device="cuda")
+    dist = torch.empty((20000, 10), dtype=torch.float32, device="cuda")
+    ctx.check(lg.lib.lg_knn_topk(ctx.h, proj.data_ptr(), N, q.data_ptr(), 20000, K, 10, excl.data_ptr(), idx.data_ptr(), dist.data_ptr()))
+    assert bool((dist[:, 1:] >= dist[:, :-1]).all()) and not bool((idx == excl[:, None]).any())
+    pick = np.random.default_rng(1).integers(0, 20000, 50)
+    P = proj.cpu().numpy()
+    for qi in pick:
+        d2 = np.array([orc.l2_sq(P[int(j)], P[qi]) for j in idx[qi].cpu().numpy()], np.float32)
+        assert np.sqrt(d2).tobytes() == dist[qi].cpu().numpy().tobytes()
+        # nothing closer was missed among a random sample of the other cells
+        others = np.random.default_rng(int(qi)).integers(0, N, 300)
+        far = np.array([orc.l2_sq(P[int(j)], P[qi]) for j in others if j != qi and j not in idx[qi].cpu().numpy()], np.float32)
+        assert far.min() >= d2.max()
+    blk.free()
