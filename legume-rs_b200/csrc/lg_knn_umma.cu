@@ -28,7 +28,7 @@ namespace {
 constexpr int QT = 128;        // queries per CTA tile (UMMA M)
 constexpr int RT = 256;        // reference points per tile (UMMA N)
 constexpr int CAND = 16;       // candidates kept per (query, list)
-constexpr int NRST = 2;        // reference-tile ring depth in shared memory
+constexpr int NRST = 3;        // reference-tile ring depth in shared memory: a 64 KB bulk copy outlasts the 1536 clk of MMAs it feeds
 constexpr int EPI_WARPS = 8;   // two warps per TMEM lane quadrant, each filtering half of the columns
 constexpr int W_MMA = EPI_WARPS, W_LOAD = EPI_WARPS + 1;
 constexpr int KTHREADS = (EPI_WARPS + 2) * 32;
@@ -118,9 +118,7 @@ __global__ void __launch_bounds__(KTHREADS, 1) k_knn_umma(const uint8_t* __restr
     uint8_t* sq = smem;
     uint8_t* sr = smem + ((qbytes + 127) / 128) * 128;
     const size_t rstride = ((rbytes + 127) / 128) * 128;
-    float* lk = reinterpret_cast<float*>(sr + NRST * rstride);                 // [CAND][EPI threads] sorted keys
-    uint32_t* li = reinterpret_cast<uint32_t*>(lk + CAND * EPI_WARPS * 32);   // [CAND][EPI threads] their indices
-    KBars* bars = reinterpret_cast<KBars*>(li + CAND * EPI_WARPS * 32);
+    KBars* bars = reinterpret_cast<KBars*>(sr + NRST * rstride);
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 1);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint64_t nrt = (nr + RT - 1) / RT;
@@ -379,7 +377,7 @@ int lg_knn_topk_umma(lg_ctx* ctx, const float* d_ref, uint64_t nr, const float* 
     if (k + 4 > CAND || d > 126 || nr < 4096 || nq == 0 || nr >= 0xFFFFFF00ull || (double)nq * (double)nr < 5e7) return LG_OK;
     const int ksteps = (d + 2 + 15) / 16;
     const size_t qbytes = tile_bytes(QT, ksteps), rbytes = tile_bytes(RT, ksteps);
-    const size_t smem = ((qbytes + 127) / 128) * 128 + NRST * (((rbytes + 127) / 128) * 128) + (size_t)CAND * EPI_WARPS * 32 * 8 + sizeof(KBars) + 16;
+    const size_t smem = ((qbytes + 127) / 128) * 128 + NRST * (((rbytes + 127) / 128) * 128) + sizeof(KBars) + 16;
     if (smem > ctx->smem_optin) return LG_OK;
     const uint64_t nqt = (nq + QT - 1) / QT, nrt = (nr + RT - 1) / RT;
     uint32_t nsplit = 1;
