@@ -1,0 +1,556 @@
+// legume_b200.hpp — C++ host-side mirror of the legume-rs operator interface for the hot path, over the C ABI
+// of liblegume_b200.so (include/legume_b200.h).
+//
+// The reference's host language is Rust; this image has no cargo/rustc, so — besides the Rust binding written out in
+// INTEGRATION.md — the host layer a compiled caller links against is this header: same names, argument meaning and
+// error behaviour as the reference's traits, one class per reference type:
+//
+//   legume::DMatrix          nalgebra::DMatrix<f32>               column-major, (nrows, ncols)
+//   legume::SparseIoVec      data_beans::sparse_io_vector::SparseIoVec with its derived caches
+//                            + RandProjOps      data-beans-alg/src/random_projection.rs:43-162
+//                            + CollapsingOps    data-beans-alg/src/collapse_data/mod.rs:315-361
+//                            + MultilevelCollapsingOps (un-refined path)   collapse_data/mod.rs:867-1050
+//   legume::GammaMatrix      matrix-param/src/dmatrix_gamma.rs (TwoStatParam + Inference)
+//   legume::CollapsedStat / CollapsedOut / optimize      collapse_data/stats.rs:378-582
+//   legume::ColumnDict       matrix-util/src/knn/mod.rs:62-299 (exact backend)
+//
+// Every failure is a legume::Error (the reference returns anyhow::Error); nothing here computes on the CPU — without
+// a CUDA device Context's constructor throws.  Header-only; link with -llegume_b200.
+#ifndef LEGUME_B200_HPP
+#define LEGUME_B200_HPP
+#include <algorithm>
+#include <cmath>
+#include <cstdint>
+#include <map>
+#include <memory>
+#include <optional>
+#include <stdexcept>
+#include <string>
+#include <utility>
+#include <vector>
+
+#include "legume_b200.h"
+
+namespace legume {
+
+constexpr uint64_t DEFAULT_PROJECTION_SEED = 0x50524F4A50524F4Aull;  // random_projection.rs:41
+constexpr size_t DEFAULT_KNN = 10;                                   // collapse_data/mod.rs:27
+constexpr size_t DEFAULT_OPT_ITER = 100;                             // collapse_data/mod.rs:28
+constexpr size_t DEFAULT_NUM_LEVELS = 2;                             // collapse_data/stats.rs:688
+
+enum class CalibrateTarget : int { All = LG_TARGET_ALL, MeanOnly = LG_TARGET_MEAN_ONLY, MeanAndLogMean = LG_TARGET_MEAN_AND_LOG_MEAN };
+
+struct Error : std::runtime_error {
+    int code;
+    Error(int c, const std::string& m) : std::runtime_error("legume_b200 error " + std::to_string(c) + ": " + m), code(c) {}
+};
+
+// nalgebra::DMatrix<f32>: column-major
+struct DMatrix {
+    size_t nrows = 0, ncols = 0;
+    std::vector<float> data;
+    DMatrix() = default;
+    DMatrix(size_t r, size_t c, float fill = 0.0f) : nrows(r), ncols(c), data(r * c, fill) {}
+    float& operator()(size_t i, size_t j) { return data[j * nrows + i]; }
+    float operator()(size_t i, size_t j) const { return data[j * nrows + i]; }
+    const float* column(size_t j) const { return data.data() + j * nrows; }
+};
+
+class Context {
+   public:
+    explicit Context(int device = 0) {
+        const int rc = lg_ctx_create(device, &h_);
+        if (rc != LG_OK) throw Error(rc, "lg_ctx_create failed: no usable CUDA device (there is no CPU fallback)");
+    }
+    ~Context() { lg_ctx_destroy(h_); }
+    Context(const Context&) = delete;
+    Context& operator=(const Context&) = delete;
+    lg_ctx* get() const { return h_; }
+    void check(int rc) const {
+        if (rc != LG_OK) throw Error(rc, lg_last_error(h_));
+    }
+    uint64_t launch_count() const { return lg_ctx_launch_count(h_); }
+
+   private:
+    lg_ctx* h_ = nullptr;
+};
+
+// rank of label.to_string() in byte-wise order (batch.rs:274-275, groups.rs:20-24)
+template <typename T>
+inline std::pair<std::vector<uint32_t>, std::vector<std::string>> rank_labels(const std::vector<T>& labels) {
+    std::vector<std::string> strs;
+    strs.reserve(labels.size());
+    for (const auto& x : labels) {
+        if constexpr (std::is_convertible_v<T, std::string>) strs.push_back(std::string(x));
+        else strs.push_back(std::to_string(x));
+    }
+    std::vector<std::string> keys = strs;
+    std::sort(keys.begin(), keys.end());
+    keys.erase(std::unique(keys.begin(), keys.end()), keys.end());
+    std::vector<uint32_t> idx(strs.size());
+    for (size_t i = 0; i < strs.size(); ++i) idx[i] = (uint32_t)(std::lower_bound(keys.begin(), keys.end(), strs[i]) - keys.begin());
+    return {idx, keys};
+}
+
+// collapse_data/refine.rs:718-734 (f32 arithmetic, round half away from zero)
+inline std::vector<size_t> compute_level_sort_dims(size_t finest, size_t num_levels) {
+    if (num_levels <= 1) return {finest};
+    const size_t coarsest = std::min<size_t>(7, finest);
+    std::vector<size_t> dims;
+    for (size_t level = 0; level < num_levels; ++level) {
+        const float t = (float)level / (float)(num_levels - 1);
+        const float dim = (float)finest - t * (float)(finest - coarsest);
+        const size_t d = (size_t)std::round(dim);
+        if (dims.empty() || dims.back() != d) dims.push_back(d);
+    }
+    return dims;
+}
+
+// random_projection.rs:535-564
+inline std::vector<uint64_t> binary_sort_columns(const Context& ctx, const DMatrix& proj_kn, size_t kk) {
+    std::vector<uint64_t> codes(proj_kn.ncols);
+    ctx.check(lg_binary_codes(ctx.get(), proj_kn.data.data(), (int)proj_kn.nrows, proj_kn.ncols, (int)kk, codes.data()));
+    return codes;
+}
+
+struct RandColProjOut {
+    DMatrix basis;  // D x K
+    DMatrix proj;   // K x N
+};
+
+// collapse_data/stats.rs:546-582
+struct CollapsedStat {
+    DMatrix observed_sum_ds, imputed_sum_ds, residual_sum_ds;  // D x S
+    std::vector<float> size_s;                                 // S
+    DMatrix observed_sum_db;                                   // D x B
+    DMatrix n_bs;                                              // B x S
+    CollapsedStat(size_t ngene, size_t nsample, size_t nbatch)
+        : observed_sum_ds(ngene, nsample), imputed_sum_ds(ngene, nsample), residual_sum_ds(ngene, nsample), size_s(nsample, 0.0f),
+          observed_sum_db(ngene, nbatch), n_bs(nbatch, nsample) {}
+    size_t num_genes() const { return observed_sum_ds.nrows; }
+    size_t num_samples() const { return observed_sum_ds.ncols; }
+    size_t num_batches() const { return observed_sum_db.ncols; }
+};
+
+// matrix-param/src/dmatrix_gamma.rs — the posterior planes a calibration fills
+struct GammaPosterior {
+    DMatrix mean, sd, log_mean, log_sd;
+    const DMatrix& posterior_mean() const { return mean; }
+    const DMatrix& posterior_sd() const { return sd; }
+    const DMatrix& posterior_log_mean() const { return log_mean; }
+    const DMatrix& posterior_log_sd() const { return log_sd; }
+};
+
+// matrix-param/src/dmatrix_gamma.rs:11-123 (TwoStatParam + Inference)
+class GammaMatrix {
+   public:
+    GammaMatrix(const Context& ctx, size_t nrows, size_t ncols, float a0, float b0)
+        : ctx_(ctx), a0_(a0), b0_(b0), a_stat_(nrows, ncols, a0), b_stat_(nrows, ncols, b0), post_{DMatrix(nrows, ncols), {}, {}, {}} {}
+    void update_stat(const DMatrix& a, const DMatrix& b) {
+        reset_stat();
+        add_stat(a, b);
+    }
+    void add_stat(const DMatrix& a, const DMatrix& b) {
+        if (a.data.size() != a_stat_.data.size() || b.data.size() != b_stat_.data.size()) throw Error(LG_ERR_INVALID, "shape mismatch");
+        for (size_t i = 0; i < a.data.size(); ++i) {
+            a_stat_.data[i] += a.data[i];
+            b_stat_.data[i] += b.data[i];
+        }
+    }
+    void reset_stat() {
+        std::fill(a_stat_.data.begin(), a_stat_.data.end(), a0_);
+        std::fill(b_stat_.data.begin(), b_stat_.data.end(), b0_);
+    }
+    void calibrate() { calibrate_with(CalibrateTarget::All); }
+    void calibrate_with(CalibrateTarget target) {
+        const size_t r = a_stat_.nrows, c = a_stat_.ncols;
+        post_.mean = DMatrix(r, c);
+        float *sd = nullptr, *lm = nullptr, *ls = nullptr;
+        if (target == CalibrateTarget::All) {
+            post_.sd = DMatrix(r, c);
+            post_.log_sd = DMatrix(r, c);
+            sd = post_.sd.data.data();
+            ls = post_.log_sd.data.data();
+        }
+        if (target != CalibrateTarget::MeanOnly) {
+            post_.log_mean = DMatrix(r, c);
+            lm = post_.log_mean.data.data();
+        }
+        // a_stat / b_stat already carry the hyper-parameters (fill + add, dmatrix_gamma.rs:64-75)
+        ctx_.check(lg_gamma_calibrate(ctx_.get(), a_stat_.data.data(), b_stat_.data.data(), a_stat_.data.size(), 0.0f, 0.0f, (int)target,
+                                      post_.mean.data.data(), sd, lm, ls));
+    }
+    const DMatrix& posterior_mean() const { return post_.mean; }
+    const DMatrix& posterior_sd() const { return post_.sd; }
+    const DMatrix& posterior_log_mean() const { return post_.log_mean; }
+    const DMatrix& posterior_log_sd() const { return post_.log_sd; }
+    size_t nrows() const { return a_stat_.nrows; }
+    size_t ncols() const { return a_stat_.ncols; }
+
+   private:
+    const Context& ctx_;
+    float a0_, b0_;
+    DMatrix a_stat_, b_stat_;
+    GammaPosterior post_;
+};
+
+// collapse_data/stats.rs:516-522
+struct CollapsedOut {
+    GammaPosterior mu_observed;
+    std::optional<GammaPosterior> mu_adjusted, mu_residual, gamma, delta;
+};
+
+// collapse_data/stats.rs:378-512; the gene-block loop is numerically inert (:370-377) and disappears
+inline CollapsedOut optimize(const Context& ctx, const CollapsedStat& stat, std::pair<float, float> hyper = {1.0f, 1.0f},
+                             size_t num_iter = DEFAULT_OPT_ITER, CalibrateTarget target = CalibrateTarget::All) {
+    const size_t D = stat.num_genes(), S = stat.num_samples(), B = stat.num_batches();
+    CollapsedOut out;
+    if (B <= 1) {
+        GammaPosterior& p = out.mu_observed;
+        p.mean = DMatrix(D, S);
+        float *sd = nullptr, *lm = nullptr, *ls = nullptr;
+        if (target == CalibrateTarget::All) {
+            p.sd = DMatrix(D, S);
+            p.log_sd = DMatrix(D, S);
+            sd = p.sd.data.data();
+            ls = p.log_sd.data.data();
+        }
+        if (target != CalibrateTarget::MeanOnly) {
+            p.log_mean = DMatrix(D, S);
+            lm = p.log_mean.data.data();
+        }
+        ctx.check(lg_optimize_single(ctx.get(), stat.observed_sum_ds.data.data(), stat.size_s.data(), D, (uint32_t)S, hyper.first,
+                                     hyper.second, (int)target, p.mean.data.data(), sd, lm, ls));
+        return out;
+    }
+    out.mu_observed.mean = DMatrix(D, S);
+    out.mu_adjusted.emplace();
+    out.mu_residual.emplace();
+    out.gamma.emplace();
+    out.delta.emplace();
+    out.mu_adjusted->mean = DMatrix(D, S);
+    out.mu_residual->mean = DMatrix(D, S);
+    out.gamma->mean = DMatrix(D, S);
+    out.delta->mean = DMatrix(D, B);
+    float* lm = nullptr;
+    if (target != CalibrateTarget::MeanOnly) {
+        out.mu_adjusted->log_mean = DMatrix(D, S);
+        lm = out.mu_adjusted->log_mean.data.data();
+    }
+    ctx.check(lg_optimize_batched(ctx.get(), stat.observed_sum_ds.data.data(), stat.imputed_sum_ds.data.data(),
+                                  stat.residual_sum_ds.data.data(), stat.size_s.data(), stat.observed_sum_db.data.data(),
+                                  stat.n_bs.data.data(), D, (uint32_t)S, (uint32_t)B, hyper.first, hyper.second, (int)num_iter, (int)target,
+                                  out.mu_observed.mean.data.data(), out.mu_adjusted->mean.data.data(), out.mu_residual->mean.data.data(),
+                                  out.gamma->mean.data.data(), out.delta->mean.data.data(), lm));
+    return out;
+}
+
+// collapse_data/mod.rs:64-130 (the fields the un-refined path reads)
+struct MultilevelParams {
+    size_t knn_pb_samples = DEFAULT_KNN, num_levels = DEFAULT_NUM_LEVELS, sort_dim = 10, num_opt_iter = DEFAULT_OPT_ITER;
+    bool refine = false;  // BBKNN + DC-SBM refinement is outside the hot path
+    explicit MultilevelParams(size_t proj_dim) : sort_dim(std::min<size_t>(proj_dim, 10)) {}
+};
+
+// data-beans/src/sparse_io_vector: one preloaded backend's columns on the device + the derived caches (mod.rs:70-85)
+class SparseIoVec {
+   public:
+    // SparseIo::csc_column_arrays() -> (&[u64] indptr, &[u64] indices, &[f32] data)   (sparse_io/traits.rs:98-100)
+    SparseIoVec(const Context& ctx, const std::vector<uint64_t>& indptr, const std::vector<uint64_t>& indices,
+                const std::vector<float>& data, size_t nrows)
+        : ctx_(ctx) {
+        if (indptr.empty()) throw Error(LG_ERR_INVALID, "empty indptr");
+        ctx_.check(lg_csc_upload(ctx_.get(), indptr.data(), indices.data(), data.data(), nrows, 0, indptr.size() - 1, nullptr, &csc_));
+        uint64_t r, c, z;
+        lg_csc_shape(csc_, &r, &c, &z);
+        nrows_ = r;
+        ncols_ = c;
+    }
+    ~SparseIoVec() { lg_csc_free(ctx_.get(), csc_); }
+    SparseIoVec(const SparseIoVec&) = delete;
+    SparseIoVec& operator=(const SparseIoVec&) = delete;
+    size_t num_rows() const { return nrows_; }
+    size_t num_columns() const { return ncols_; }
+    const lg_csc* block() const { return csc_; }
+
+    // ---- batch.rs:259-336 ----
+    template <typename T>
+    void register_batch_membership(const std::vector<T>& labels) {
+        if (labels.size() != ncols_) throw Error(LG_ERR_INVALID, "batch membership length mismatches the number of columns");
+        auto r = rank_labels(labels);
+        col_to_batch_ = std::move(r.first);
+        batch_names_ = std::move(r.second);
+    }
+    size_t num_batches() const { return batch_names_.size(); }
+    const std::vector<uint32_t>& col_to_batch() const { return col_to_batch_; }
+    void register_column_multiplicity(const std::vector<float>& w) {
+        if (w.size() != ncols_) throw Error(LG_ERR_INVALID, "column multiplicity length mismatches the number of columns");
+        for (float x : w)
+            if (!(x > 0.0f)) throw Error(LG_ERR_INVALID, "column multiplicity must be strictly positive");
+        multiplicity_ = w;
+    }
+
+    // ---- groups.rs:13-37 ----
+    template <typename T>
+    void assign_groups(const std::vector<T>& column_to_group) {
+        if (column_to_group.size() != ncols_) throw Error(LG_ERR_INVALID, "group membership length mismatches the number of columns");
+        auto r = rank_labels(column_to_group);
+        col_to_group_ = std::move(r.first);
+        num_groups_ = r.second.size();
+    }
+    size_t num_groups() const { return num_groups_; }
+    const std::vector<uint32_t>& get_group_membership() const {
+        if (col_to_group_.empty() && ncols_) throw Error(LG_ERR_INVALID, "groups were not assigned");
+        return col_to_group_;
+    }
+
+    // ---- RandProjOps (random_projection.rs:341-527).  The basis is an input (identical-projection-matrix contract):
+    //      basis_dk is D x K as the reference returns it; block_size is accepted and ignored. ----
+    template <typename T>
+    RandColProjOut project_columns_with_batch_correction(const DMatrix& basis_dk, std::optional<size_t> /*block_size*/,
+                                                         const std::vector<T>* batch_membership) const {
+        if (basis_dk.nrows != nrows_) throw Error(LG_ERR_INVALID, "basis must be D x K");
+        const size_t K = basis_dk.ncols;
+        DMatrix basis_kd(K, nrows_);  // basis_dk.transpose() (:360)
+        for (size_t g = 0; g < nrows_; ++g)
+            for (size_t k = 0; k < K; ++k) basis_kd(k, g) = basis_dk(g, k);
+        std::vector<uint32_t> batch;
+        uint32_t nb = 0;
+        if (batch_membership && batch_membership->size() == ncols_) {  // else: warn and skip the centring (:389-395)
+            auto r = rank_labels(*batch_membership);
+            batch = std::move(r.first);
+            nb = (uint32_t)r.second.size();
+        }
+        RandColProjOut out{basis_dk, DMatrix(K, ncols_)};
+        ctx_.check(lg_project(ctx_.get(), csc_, basis_kd.data.data(), (int)K, nb ? batch.data() : nullptr, nb, out.proj.data.data()));
+        return out;
+    }
+    RandColProjOut project_columns(const DMatrix& basis_dk, std::optional<size_t> block_size = std::nullopt) const {
+        return project_columns_with_batch_correction<uint32_t>(basis_dk, block_size, nullptr);
+    }
+    template <typename T>
+    RandColProjOut project_columns_weighted(DMatrix basis_dk, std::optional<size_t> block_size, const std::vector<T>* batch_membership,
+                                            const std::vector<float>& row_weights) const {
+        if (row_weights.size() != nrows_) throw Error(LG_ERR_INVALID, "row_weights length mismatch");
+        for (size_t g = 0; g < nrows_; ++g) {  // random_projection.rs:438-444
+            const float w = row_weights[g];
+            for (size_t k = 0; k < basis_dk.ncols; ++k) {
+                if (w <= 0.0f) basis_dk(g, k) = 0.0f;
+                else if (std::fabs(w - 1.0f) > 1e-6f) basis_dk(g, k) *= w;
+            }
+        }
+        return project_columns_with_batch_correction(basis_dk, block_size, batch_membership);
+    }
+    // random_projection.rs:506-527: returns max code + 1 and assigns the groups
+    size_t partition_columns_to_groups(const DMatrix& proj_kn, std::optional<size_t> num_features = std::nullopt) {
+        if (proj_kn.ncols != ncols_) throw Error(LG_ERR_INVALID, "number of columns mismatch");
+        const size_t kk = std::min({proj_kn.nrows, num_features.value_or(proj_kn.nrows), ncols_});
+        binary_codes_ = binary_sort_columns(ctx_, proj_kn, kk);
+        sort_dim_ = kk;
+        col_to_group_.assign(ncols_, 0);
+        uint32_t ng = 0;
+        ctx_.check(lg_assign_groups(ctx_.get(), binary_codes_.data(), ncols_, (int)kk, 0, col_to_group_.data(), &ng));
+        num_groups_ = ng;
+        return binary_codes_.empty() ? 0 : (size_t)*std::max_element(binary_codes_.begin(), binary_codes_.end()) + 1;
+    }
+    const std::vector<uint64_t>& binary_codes() const { return binary_codes_; }
+
+    // ---- CollapsingOps (collapse_data/mod.rs:315-500) ----
+    void collect_basic_stat(CollapsedStat& stat) const {
+        ctx_.check(lg_collapse_basic(ctx_.get(), csc_, get_group_membership().data(), mult(), (uint32_t)stat.num_samples(),
+                                     stat.observed_sum_ds.data.data(), stat.size_s.data()));
+    }
+    void collect_batch_stat(CollapsedStat& stat) const {
+        if (col_to_batch_.empty()) throw Error(LG_ERR_INVALID, "batches were not registered");
+        ctx_.check(lg_collapse_batch(ctx_.get(), csc_, get_group_membership().data(), col_to_batch_.data(), mult(),
+                                     (uint32_t)stat.num_samples(), (uint32_t)stat.num_batches(), stat.observed_sum_db.data.data(),
+                                     stat.n_bs.data.data()));
+    }
+    // collapse_data/mod.rs:364-383 -> register_batches_dmatrix (batch.rs:46-234): the exact backend needs no index
+    template <typename T>
+    void build_hnsw_per_batch(const DMatrix& proj_kn, const std::vector<T>& batch_membership) {
+        register_batch_membership(batch_membership);
+        batch_proj_ = proj_kn;
+        proximity_.clear();
+        const uint32_t B = (uint32_t)num_batches();
+        if (B > 2) {
+            proximity_.resize((size_t)B * B);
+            ctx_.check(lg_batch_proximity(ctx_.get(), proj_kn.data.data(), (int)proj_kn.nrows, ncols_, col_to_batch_.data(), B,
+                                          proximity_.data(), nullptr));
+        }
+    }
+    // collect_matched_stat_visitor over every group (stats.rs:26-108); knn_batches only sizes a Vec in the reference
+    void collect_matched_stat(size_t /*knn_batches*/, size_t knn_cells, const std::vector<uint32_t>* reference_indices,
+                              CollapsedStat& stat) const {
+        if (batch_proj_.data.empty()) throw Error(LG_ERR_INVALID, "no knn lookup");
+        const uint32_t B = (uint32_t)num_batches();
+        std::vector<uint32_t> order;
+        uint32_t nt = B;
+        if (reference_indices) {
+            nt = (uint32_t)reference_indices->size();
+            for (uint32_t s = 0; s < B; ++s) order.insert(order.end(), reference_indices->begin(), reference_indices->end());
+        } else if (!proximity_.empty()) {
+            order = proximity_;
+        }
+        const size_t T = (size_t)nt * knn_cells;
+        std::vector<uint32_t> midx(ncols_ * T);
+        std::vector<float> mdist(ncols_ * T);
+        ctx_.check(lg_knn_match_batches(ctx_.get(), batch_proj_.data.data(), (int)batch_proj_.nrows, ncols_, col_to_batch_.data(), B,
+                                        (int)knn_cells, order.empty() ? nullptr : order.data(), nt, midx.data(), mdist.data()));
+        ctx_.check(lg_collect_matched_stat(ctx_.get(), csc_, get_group_membership().data(), (uint32_t)stat.num_samples(), midx.data(),
+                                           mdist.data(), (uint32_t)T, stat.imputed_sum_ds.data.data(), stat.residual_sum_ds.data.data()));
+    }
+    // collapse_data/mod.rs:384-475
+    CollapsedOut collapse_columns(std::optional<size_t> knn_batches = std::nullopt, std::optional<size_t> knn_cells = std::nullopt,
+                                  const std::vector<std::string>* reference_batch_names = nullptr,
+                                  std::optional<size_t> num_opt_iter = std::nullopt, CollapsedStat* stat_out = nullptr) const {
+        if (col_to_group_.empty()) throw Error(LG_ERR_INVALID, "The columns were not assigned before. Call `assign_columns_to_groups`");
+        const size_t nb = num_batches();
+        CollapsedStat stat(nrows_, num_groups_, nb);
+        collect_basic_stat(stat);
+        if (nb > 1) {
+            std::vector<uint32_t> ref;
+            if (reference_batch_names) {
+                for (const auto& name : *reference_batch_names) {
+                    auto it = std::find(batch_names_.begin(), batch_names_.end(), name);
+                    if (it != batch_names_.end()) ref.push_back((uint32_t)(it - batch_names_.begin()));
+                }
+                if (ref.empty()) throw Error(LG_ERR_INVALID, "no reference batch names matched!");
+            }
+            collect_batch_stat(stat);
+            collect_matched_stat(knn_batches.value_or(2), knn_cells.value_or(DEFAULT_KNN), reference_batch_names ? &ref : nullptr, stat);
+        }
+        CollapsedOut out = optimize(ctx_, stat, {1.0f, 1.0f}, num_opt_iter.value_or(DEFAULT_OPT_ITER), CalibrateTarget::All);
+        if (stat_out) *stat_out = std::move(stat);
+        return out;
+    }
+
+    // ---- MultilevelCollapsingOps::collapse_columns_multilevel_vec, un-refined path (collapse_data/mod.rs:867-1050);
+    //      levels finest-first; per-level statistics are returned through stats_out when given ----
+    template <typename T>
+    std::vector<CollapsedOut> collapse_columns_multilevel_vec(const DMatrix& proj_kn, const std::vector<T>& batch_membership,
+                                                              const MultilevelParams& params,
+                                                              std::vector<CollapsedStat>* stats_out = nullptr) {
+        if (params.refine) throw Error(LG_ERR_INVALID, "BBKNN + DC-SBM refinement is outside the hot path (SURVEY.md §8f rank 3)");
+        register_batch_membership(batch_membership);
+        const uint32_t nb = (uint32_t)num_batches();
+        if (nb >= 2) build_hnsw_per_batch(proj_kn, batch_membership);
+        const std::vector<size_t> level_dims = compute_level_sort_dims(params.sort_dim, params.num_levels);
+        partition_columns_to_groups(proj_kn, level_dims[0]);
+        const uint32_t ng = (uint32_t)num_groups_;
+        CollapsedStat fine(nrows_, ng, nb);
+        collect_basic_stat(fine);
+        if (nb >= 2) {
+            collect_batch_stat(fine);
+            const size_t cap = (size_t)ng * nb, K = proj_kn.nrows;
+            std::vector<uint32_t> c2p(ncols_), pg(cap), pb(cap);
+            std::vector<float> cnt(cap), cen(cap * K);
+            uint32_t npb = 0;
+            ctx_.check(lg_pb_layout(ctx_.get(), proj_kn.data.data(), (int)K, ncols_, col_to_group_.data(), ng, col_to_batch_.data(), nb,
+                                    mult(), c2p.data(), pg.data(), pb.data(), cnt.data(), cen.data(), &npb));
+            std::vector<float> gene_sums((size_t)nrows_ * npb), gsize(npb);
+            ctx_.check(lg_collapse_basic(ctx_.get(), csc_, c2p.data(), mult(), npb, gene_sums.data(), gsize.data()));
+            const uint32_t nslot = nb * (uint32_t)params.knn_pb_samples;
+            std::vector<uint32_t> mp((size_t)npb * nslot);
+            std::vector<float> md((size_t)npb * nslot);
+            ctx_.check(lg_pb_match(ctx_.get(), proj_kn.data.data(), (int)K, ncols_, col_to_batch_.data(), nb, c2p.data(), cen.data(),
+                                   pb.data(), npb, (int)params.knn_pb_samples, mp.data(), md.data()));
+            ctx_.check(lg_collect_matched_stat_coarse(ctx_.get(), gene_sums.data(), nrows_, npb, cnt.data(), pg.data(), ng, mp.data(),
+                                                      md.data(), nslot, fine.imputed_sum_ds.data.data(), fine.residual_sum_ds.data.data()));
+        }
+        std::vector<CollapsedOut> results;
+        results.push_back(optimize(ctx_, fine, {1.0f, 1.0f}, params.num_opt_iter, CalibrateTarget::All));
+        std::vector<CollapsedStat> stats;
+        stats.push_back(std::move(fine));
+        std::vector<uint32_t> prev_group = col_to_group_;
+        uint32_t prev_n = ng;
+        for (size_t level = 1; level < level_dims.size(); ++level) {
+            std::vector<uint32_t> f2c(prev_n);
+            uint32_t nc = 0;
+            ctx_.check(lg_fine_to_coarse(ctx_.get(), binary_codes_.data(), prev_group.data(), ncols_, prev_n, (int)level_dims[level],
+                                         f2c.data(), &nc));
+            const CollapsedStat& prev = stats.back();
+            CollapsedStat coarse(nrows_, nc, nb);
+            ctx_.check(lg_merge_stat(ctx_.get(), prev.observed_sum_ds.data.data(), nrows_, prev_n, f2c.data(), nc, coarse.observed_sum_ds.data.data()));
+            ctx_.check(lg_merge_stat(ctx_.get(), prev.imputed_sum_ds.data.data(), nrows_, prev_n, f2c.data(), nc, coarse.imputed_sum_ds.data.data()));
+            ctx_.check(lg_merge_stat(ctx_.get(), prev.residual_sum_ds.data.data(), nrows_, prev_n, f2c.data(), nc, coarse.residual_sum_ds.data.data()));
+            for (uint32_t f = 0; f < prev_n; ++f) {  // stats.rs:813-816
+                coarse.size_s[f2c[f]] += prev.size_s[f];
+                for (uint32_t b = 0; b < nb; ++b) coarse.n_bs(b, f2c[f]) += prev.n_bs(b, f);
+            }
+            coarse.observed_sum_db = prev.observed_sum_db;
+            results.push_back(optimize(ctx_, coarse, {1.0f, 1.0f}, std::max<size_t>(params.num_opt_iter / 2, 10), CalibrateTarget::All));
+            for (auto& g : prev_group) g = f2c[g];
+            prev_n = nc;
+            stats.push_back(std::move(coarse));
+        }
+        if (stats_out) *stats_out = std::move(stats);
+        return results;
+    }
+
+   private:
+    const float* mult() const { return multiplicity_.empty() ? nullptr : multiplicity_.data(); }
+    const Context& ctx_;
+    lg_csc* csc_ = nullptr;
+    size_t nrows_ = 0, ncols_ = 0, num_groups_ = 0, sort_dim_ = 0;
+    std::vector<uint32_t> col_to_group_, col_to_batch_, proximity_;
+    std::vector<std::string> batch_names_;
+    std::vector<float> multiplicity_;
+    std::vector<uint64_t> binary_codes_;
+    DMatrix batch_proj_;
+};
+
+// matrix-util/src/knn/mod.rs:62-299 with the exact backend; names are the column indices 0..n-1 unless given
+class ColumnDict {
+   public:
+    ColumnDict(const Context& ctx, DMatrix data_dn, std::vector<size_t> names = {}) : ctx_(ctx), data_(std::move(data_dn)), names_(std::move(names)) {
+        if (names_.empty())
+            for (size_t i = 0; i < data_.ncols; ++i) names_.push_back(i);
+        if (names_.size() != data_.ncols) throw Error(LG_ERR_INVALID, "Data and names must have the same length");
+        for (size_t i = 0; i < names_.size(); ++i) name2index_[names_[i]] = i;
+    }
+    size_t num_points() const { return data_.ncols; }
+    size_t dim() const { return data_.nrows; }
+    // search_by_query_data: (names, Euclidean distances), nearest first
+    std::pair<std::vector<size_t>, std::vector<float>> search_by_query_data(const std::vector<float>& query, size_t knn) const {
+        if (query.size() != data_.nrows) throw Error(LG_ERR_INVALID, "query's dim does not match");
+        return search(query.data(), knn, nullptr, *this);
+    }
+    std::pair<std::vector<size_t>, std::vector<float>> search_others(size_t query_name, size_t knn) const {
+        const uint32_t q = (uint32_t)index_of(query_name);
+        return search(data_.column(q), knn, &q, *this);
+    }
+    std::pair<std::vector<size_t>, std::vector<float>> match_by_query_name_against(size_t query_name, size_t knn,
+                                                                                   const ColumnDict& against) const {
+        return search(data_.column(index_of(query_name)), knn, nullptr, against);
+    }
+
+   private:
+    size_t index_of(size_t name) const {
+        auto it = name2index_.find(name);
+        if (it == name2index_.end()) throw Error(LG_ERR_INVALID, "name not found");
+        return it->second;
+    }
+    std::pair<std::vector<size_t>, std::vector<float>> search(const float* q, size_t knn, const uint32_t* exclude,
+                                                              const ColumnDict& against) const {
+        std::pair<std::vector<size_t>, std::vector<float>> out;
+        if (knn == 0 || against.data_.ncols == 0) return out;
+        std::vector<uint32_t> idx(knn);
+        std::vector<float> dist(knn);
+        ctx_.check(lg_knn_topk(ctx_.get(), against.data_.data.data(), against.data_.ncols, q, 1, (int)data_.nrows, (int)knn, exclude,
+                               idx.data(), dist.data()));
+        for (size_t i = 0; i < knn; ++i)
+            if (idx[i] != 0xFFFFFFFFu) {
+                out.first.push_back(against.names_[idx[i]]);
+                out.second.push_back(dist[i]);
+            }
+        return out;
+    }
+    const Context& ctx_;
+    DMatrix data_;
+    std::vector<size_t> names_;
+    std::map<size_t, size_t> name2index_;
+};
+
+}  // namespace legume
+#endif  // LEGUME_B200_HPP

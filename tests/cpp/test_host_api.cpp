@@ -1,0 +1,237 @@
+// C++ host-API parity tests: the reference's own tests for the path, restated against include/legume_b200.hpp
+// (the CUDA library) with the CPU oracle (oracle/oracle.h, test infrastructure) as the checker.
+//
+//   random_projection.rs:578-645     tiny 8 x 12 fixture: seeded projection is reproducible
+//   weighted_columns.rs:76-121       mu = (1 + sum y) / (1 + n) under (a0, b0) = (1, 1)
+//   dmatrix_gamma_tests.rs:9-32      log_sd = sqrt(trigamma(a))
+//   knn/tests.rs:74-150              exact search == brute force, ascending, self excluded, cross-dict
+//   groups.rs:20-24                  groups ordered by the byte-wise order of code.to_string()
+//   collapse_data/mod.rs:867-1050    collapse_columns_multilevel_vec, un-refined, two batches-plus
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <random>
+#include <string>
+#include <vector>
+
+#include "legume_b200.hpp"
+#include "oracle.h"
+
+static int g_checks = 0, g_fail = 0;
+#define CHECK(cond)                                                          \
+    do {                                                                     \
+        ++g_checks;                                                          \
+        if (!(cond)) {                                                       \
+            ++g_fail;                                                        \
+            std::fprintf(stderr, "FAIL %s:%d: %s\n", __FILE__, __LINE__, #cond); \
+        }                                                                    \
+    } while (0)
+
+// stats_tests.rs:20-30 assert_mat_close
+static bool close_all(const float* x, const float* y, size_t n, double tol) {
+    for (size_t i = 0; i < n; ++i) {
+        const double a = x[i], b = y[i];
+        if (!(std::fabs(a - b) <= tol * (1.0 + std::max(std::fabs(a), std::fabs(b))))) return false;
+    }
+    return true;
+}
+
+struct Csc {
+    std::vector<uint64_t> indptr{0}, indices;
+    std::vector<float> data;
+    size_t nrows = 0;
+    size_t ncols() const { return indptr.size() - 1; }
+};
+
+static Csc tiny_fixture() {  // random_projection.rs:578-605
+    Csc m;
+    m.nrows = 8;
+    for (int j = 0; j < 12; ++j) {
+        for (int i = 0; i < 8; ++i)
+            if ((i * 7 + j * 3) % 5 < 3) {
+                m.indices.push_back(i);
+                m.data.push_back(1.0f + (float)((i + j) % 4));
+            }
+        m.indptr.push_back(m.indices.size());
+    }
+    return m;
+}
+
+static Csc random_counts(std::mt19937& rng, size_t D, size_t N, double density) {
+    Csc m;
+    m.nrows = D;
+    std::uniform_real_distribution<double> u(0.0, 1.0);
+    std::geometric_distribution<int> geo(0.7);
+    for (size_t j = 0; j < N; ++j) {
+        for (size_t i = 0; i < D; ++i)
+            if (u(rng) < density) {
+                m.indices.push_back(i);
+                m.data.push_back((float)std::min(1 + geo(rng), 6));
+            }
+        m.indptr.push_back(m.indices.size());
+    }
+    return m;
+}
+
+static legume::DMatrix gaussian(std::mt19937& rng, size_t r, size_t c) {
+    legume::DMatrix a(r, c);
+    std::normal_distribution<float> n(0.0f, 1.0f);
+    for (auto& x : a.data) x = n(rng);
+    return a;
+}
+
+int main() {
+    using namespace legume;
+    Context ctx(0);
+    std::mt19937 rng(20240517);
+
+    {  // ---- seeded projection is reproducible and matches the reference arithmetic ----
+        Csc m = tiny_fixture();
+        SparseIoVec data(ctx, m.indptr, m.indices, m.data, m.nrows);
+        DMatrix basis = gaussian(rng, 8, 3);
+        auto a = data.project_columns(basis), b = data.project_columns(basis);
+        CHECK(a.proj.nrows == 3 && a.proj.ncols == 12 && a.basis.nrows == 8);
+        CHECK(std::memcmp(a.proj.data.data(), b.proj.data.data(), a.proj.data.size() * 4) == 0);
+        DMatrix basis_kd(3, 8);
+        for (int g = 0; g < 8; ++g)
+            for (int k = 0; k < 3; ++k) basis_kd(k, g) = basis(g, k);
+        std::vector<float> want(3 * 12);
+        orc_project_raw(m.indptr.data(), m.indices.data(), m.data.data(), 12, basis_kd.data.data(), 3, want.data(), 1);
+        orc_project_finish(want.data(), 3, 12, nullptr, 0);
+        CHECK(close_all(a.proj.data.data(), want.data(), want.size(), 1e-5));
+    }
+
+    Csc m = random_counts(rng, 150, 600, 0.1);
+    const size_t D = m.nrows, N = m.ncols(), K = 12;
+    SparseIoVec data(ctx, m.indptr, m.indices, m.data, D);
+    DMatrix basis = gaussian(rng, D, K);
+    std::vector<std::string> batch(N);
+    for (size_t j = 0; j < N; ++j) batch[j] = "b" + std::to_string((j * 7 + j / 13) % 3);
+    auto rp = data.project_columns_with_batch_correction(basis, std::nullopt, &batch);
+    {  // ---- projection with batch centring vs the oracle ----
+        DMatrix basis_kd(K, D);
+        for (size_t g = 0; g < D; ++g)
+            for (size_t k = 0; k < K; ++k) basis_kd(k, g) = basis(g, k);
+        auto ranks = rank_labels(batch);
+        std::vector<float> want(K * N);
+        orc_project_raw(m.indptr.data(), m.indices.data(), m.data.data(), N, basis_kd.data.data(), (int)K, want.data(), 1);
+        orc_project_finish(want.data(), (int)K, N, ranks.first.data(), (uint32_t)ranks.second.size());
+        CHECK(close_all(rp.proj.data.data(), want.data(), want.size(), 1e-5));
+    }
+    {  // ---- groups: lexicographic order of the decimal code strings; sums conserved; mu = (1 + sum) / (1 + n) ----
+        const size_t ncode = data.partition_columns_to_groups(rp.proj, 5);
+        CHECK(ncode <= 32 && data.num_groups() >= 2);
+        std::vector<uint64_t> codes(N);
+        CHECK(orc_binary_codes(rp.proj.data.data(), (int)K, N, 5, codes.data(), nullptr, nullptr, nullptr, nullptr) == 0);
+        CHECK(codes == data.binary_codes());
+        std::vector<uint32_t> grp(N);
+        const uint32_t ng = orc_assign_groups(codes.data(), N, grp.data());
+        CHECK(ng == data.num_groups() && grp == data.get_group_membership());
+        SparseIoVec single(ctx, m.indptr, m.indices, m.data, D);
+        single.assign_groups(codes);
+        CHECK(single.get_group_membership() == grp);
+        CollapsedStat stat(D, ng, 0);
+        CollapsedOut out = single.collapse_columns(std::nullopt, std::nullopt, nullptr, std::nullopt, &stat);
+        std::vector<float> ws(D * ng), wn(ng);
+        orc_collapse_basic(m.indptr.data(), m.indices.data(), m.data.data(), D, N, grp.data(), nullptr, ng, ws.data(), wn.data());
+        CHECK(stat.observed_sum_ds.data == ws && stat.size_s == wn);
+        bool mu_ok = true;
+        for (uint32_t s = 0; s < ng; ++s)
+            for (size_t g = 0; g < D; ++g) {
+                const float want = (1.0f + ws[s * D + g]) / (1.0f + wn[s]);
+                mu_ok &= std::fabs(out.mu_observed.mean(g, s) - want) <= 1e-5f * (1.0f + std::fabs(want));
+            }
+        CHECK(mu_ok);
+    }
+    {  // ---- GammaMatrix: log_sd = sqrt(trigamma(a)) ----
+        GammaMatrix gm(ctx, 3, 1, 1.0f, 1.0f);
+        DMatrix a(3, 1), b(3, 1, 1.0f);
+        a(0, 0) = 0.0f;
+        a(1, 0) = 1.0f;
+        a(2, 0) = 4.0f;
+        gm.update_stat(a, b);
+        gm.calibrate();
+        const double pi2_6 = M_PI * M_PI / 6.0;
+        CHECK(std::fabs(gm.posterior_log_sd()(0, 0) - std::sqrt(pi2_6)) < 1e-4);
+        CHECK(std::fabs(gm.posterior_log_sd()(1, 0) - std::sqrt(pi2_6 - 1.0)) < 1e-4);
+        CHECK(std::fabs(gm.posterior_mean()(2, 0) - 2.5f) < 1e-6 && gm.posterior_log_sd()(2, 0) < gm.posterior_log_sd()(0, 0));
+    }
+    {  // ---- ColumnDict, exact backend ----
+        DMatrix pts = gaussian(rng, 16, 500);
+        ColumnDict dict(ctx, pts);
+        bool same = true, ascending = true, no_self = true;
+        for (size_t q = 0; q < 500; q += 37) {
+            auto res = dict.search_others(q, 8);
+            std::vector<uint32_t> widx(8), ex{(uint32_t)q};
+            std::vector<float> wd(8);
+            orc_knn_topk(pts.data.data(), 500, pts.column(q), 1, 16, 8, ex.data(), widx.data(), wd.data(), 1);
+            for (size_t i = 0; i < 8; ++i) {
+                same &= res.first[i] == widx[i] && res.second[i] == wd[i];
+                no_self &= res.first[i] != q;
+                if (i) ascending &= res.second[i] >= res.second[i - 1];
+            }
+        }
+        CHECK(same && ascending && no_self);
+        DMatrix other = gaussian(rng, 16, 40);
+        ColumnDict small(ctx, other);
+        auto cross = dict.match_by_query_name_against(3, 50, small);  // fewer points than knn: all of them, nearest first
+        CHECK(cross.first.size() == 40);
+        auto by_data = dict.search_by_query_data(std::vector<float>(pts.column(7), pts.column(7) + 16), 1);
+        CHECK(by_data.first.size() == 1 && by_data.first[0] == 7 && by_data.second[0] == 0.0f);
+    }
+    {  // ---- collapse_columns_multilevel_vec (pb-sample matched stats) vs the oracle's composition ----
+        MultilevelParams params(K);
+        params.sort_dim = 5;
+        params.num_levels = 2;
+        params.knn_pb_samples = 3;
+        params.num_opt_iter = 12;
+        std::vector<CollapsedStat> stats;
+        auto levels = data.collapse_columns_multilevel_vec(rp.proj, batch, params, &stats);
+        const uint32_t B = (uint32_t)data.num_batches(), S = (uint32_t)stats[0].num_samples();
+        CHECK(levels.size() == 1 && B == 3);  // dims(5, 2) = [5, 5] dedups to one level (refine.rs:718-734)
+        const std::vector<uint32_t>& grp = data.get_group_membership();
+        const std::vector<uint32_t>& bat = data.col_to_batch();
+        std::vector<uint32_t> c2p(N), pg(S * B), pb(S * B);
+        std::vector<float> cnt(S * B), cen((size_t)S * B * K);
+        const uint32_t npb = orc_pb_layout(rp.proj.data.data(), (int)K, N, grp.data(), S, bat.data(), B, nullptr, c2p.data(), pg.data(),
+                                           pb.data(), cnt.data(), cen.data());
+        std::vector<float> gs((size_t)D * npb), gsz(npb);
+        orc_collapse_basic(m.indptr.data(), m.indices.data(), m.data.data(), D, N, c2p.data(), nullptr, npb, gs.data(), gsz.data());
+        std::vector<uint32_t> mp((size_t)npb * B * 3);
+        std::vector<float> md((size_t)npb * B * 3);
+        orc_pb_match(rp.proj.data.data(), (int)K, N, bat.data(), B, c2p.data(), cen.data(), pb.data(), npb, 3, mp.data(), md.data(), 1);
+        std::vector<float> imp((size_t)D * S), res((size_t)D * S);
+        orc_collect_matched_stat_coarse(gs.data(), D, npb, cnt.data(), pg.data(), S, mp.data(), md.data(), B * 3, imp.data(), res.data());
+        CHECK(close_all(stats[0].imputed_sum_ds.data.data(), imp.data(), imp.size(), 1e-5));
+        CHECK(close_all(stats[0].residual_sum_ds.data.data(), res.data(), res.size(), 1e-5));
+        std::vector<float> mu_obs((size_t)D * S), mu_adj((size_t)D * S), mu_res((size_t)D * S), gam((size_t)D * S), delta((size_t)D * B),
+            lm((size_t)D * S);
+        orc_optimize_batched(stats[0].observed_sum_ds.data.data(), imp.data(), res.data(), stats[0].size_s.data(),
+                             stats[0].observed_sum_db.data.data(), stats[0].n_bs.data.data(), D, S, B, 1.0f, 1.0f, 12, 0, mu_obs.data(),
+                             mu_adj.data(), mu_res.data(), gam.data(), delta.data(), lm.data());
+        CHECK(close_all(levels[0].mu_adjusted->mean.data.data(), mu_adj.data(), mu_adj.size(), 1e-4));
+        CHECK(close_all(levels[0].delta->mean.data.data(), delta.data(), delta.size(), 1e-4));
+    }
+    {  // ---- error behaviour: anyhow::Error -> legume::Error, never a crash ----
+        bool threw = false;
+        try {
+            std::vector<std::string> bad(3, "x");
+            data.register_batch_membership(bad);
+        } catch (const Error&) {
+            threw = true;
+        }
+        CHECK(threw);
+        threw = false;
+        try {
+            Csc bad = tiny_fixture();
+            bad.indices[2] = 99;  // row out of range
+            SparseIoVec x(ctx, bad.indptr, bad.indices, bad.data, bad.nrows);
+        } catch (const Error& e) {
+            threw = std::string(e.what()).find("out of range") != std::string::npos;
+        }
+        CHECK(threw);
+    }
+    std::printf("%s: %d checks, %d failed, %llu kernel launches\n", g_fail ? "FAILED" : "ok", g_checks, g_fail,
+                (unsigned long long)ctx.launch_count());
+    return g_fail ? 1 : 0;
+}
