@@ -246,6 +246,29 @@ int lg_collect_matched_stat_coarse(lg_ctx* ctx, const float* gene_sums, uint64_t
                                    const uint32_t* pb_to_group, uint32_t S, const uint32_t* matched_pb,
                                    const float* matched_dist, uint32_t T, float* out_imputed_ds,
                                    float* out_residual_ds);
+/* staged form of the pb-sample arm for cell-sharded runs (device pointers unless noted; exchanges are the caller's):
+ *   pair_presence    flags[g*B + b] = 1 where a cell of group g and batch b exists      -> all-reduce(max)
+ *   pb_ids           HOST math: ids of the present (group, batch) blocks, group-major, batches ascending
+ *   cells_to_pb      cell -> pb-sample id
+ *   centroid_fold    continues the serial folds sum (K x npb) / count (npb) over this shard's cells; shards run it
+ *                    one after the other in rank order, handing sum / count on, so the centroids are those of one GPU
+ *   centroid_finish  centroid = sum * (1 / count)
+ *   min_keys         keys[(q - q0)*npb + p] = min over this shard's cells of pb-sample p of (l2_sq << 32 | global cell)
+ *                    for the query centroids q0 .. q0+nq                                 -> all-reduce(min) as int64
+ *   topk_keys        per query and batch the knn smallest keys -> (pb-sample, distance) lists               */
+int lg_pair_presence(lg_ctx* ctx, const uint32_t* d_group, const uint32_t* d_batch, uint64_t ncols, uint32_t S, uint32_t B,
+                     uint32_t* d_present);
+int lg_pb_ids(lg_ctx* ctx, const uint32_t* present, uint32_t S, uint32_t B, uint32_t* out_id, uint32_t* out_pb_group,
+              uint32_t* out_pb_batch, uint32_t* out_num_pb);
+int lg_cells_to_pb(lg_ctx* ctx, const uint32_t* d_group, const uint32_t* d_batch, uint64_t ncols, uint32_t S, uint32_t B,
+                   const uint32_t* d_id, uint32_t* d_cell_to_pb);
+int lg_pb_centroid_fold(lg_ctx* ctx, const float* d_proj, int K, uint64_t ncols, const uint32_t* d_cell_to_pb, uint32_t npb,
+                        const float* d_mult, float* d_sum, float* d_count);
+int lg_pb_centroid_finish(lg_ctx* ctx, const float* d_sum, const float* d_count, uint32_t npb, int K, float* d_centroids);
+int lg_pb_min_keys(lg_ctx* ctx, const float* d_proj, int K, uint64_t ncols, const uint32_t* d_cell_to_pb, uint64_t cell_offset,
+                   const float* d_centroids, const uint32_t* d_pb_batch, uint32_t npb, uint32_t q0, uint32_t nq, uint64_t* d_keys);
+int lg_pb_topk_keys(lg_ctx* ctx, const uint64_t* d_keys, uint32_t npb, uint32_t q0, uint32_t nq, uint32_t B,
+                    const uint32_t* pb_batch, int knn, uint32_t* d_out_pb, float* d_out_dist);
 /* compute_fine_to_coarse_mapping: coarse code = fine code & (2^coarse_dim - 1), ids by sorted unique code */
 int lg_fine_to_coarse(lg_ctx* ctx, const uint64_t* codes, const uint32_t* group_of_cell, uint64_t ncols, uint32_t nfine,
                       int coarse_dim, uint32_t* out_fine_to_coarse, uint32_t* out_num_coarse);

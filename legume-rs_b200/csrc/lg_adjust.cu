@@ -135,6 +135,8 @@ __device__ __forceinline__ float adj_l2_sq(const float* __restrict__ r, const fl
 // in ascending order with the loads unrolled ahead of the (serial) adds
 //   MODE 0: nalgebra column_mean     acc = (1/n) * x + acc                 (batch.rs:196-205)
 //   MODE 1: pb-sample centroid       acc += x * w ; then acc * (1/count)   (pb_samples.rs:141-160)
+//   MODE 2: the same fold CONTINUED from running sums / counts (cell shards hand the fold on in rank order,
+//           so the result is the single serial fold whatever the GPU count); no division
 // ------------------------------------------------------------------------------------------------
 template <int MODE>
 __global__ void k_segment_mean(const float* __restrict__ proj, int K, const uint32_t* __restrict__ cell_sorted,
@@ -143,14 +145,15 @@ __global__ void k_segment_mean(const float* __restrict__ proj, int K, const uint
     const uint32_t s = blockIdx.x;
     const int k = threadIdx.x;
     const uint64_t lo = seg_off[s], hi = seg_off[s + 1];
-    float cnt = 0.0f;
-    if (MODE == 1) {
+    float cnt = (MODE == 2) ? out_count[s] : 0.0f;
+    if (MODE >= 1) {
         // the count is a serial f32 sum of the multiplicities (every thread computes the same value)
         for (uint64_t i = lo; i < hi; ++i) cnt = __fadd_rn(cnt, mult ? mult[cell_sorted[i]] : 1.0f);
     }
+    if (MODE == 2) __syncthreads();  // every thread has read the running count before thread 0 replaces it
     if (k >= K) return;
     const float denom = (MODE == 0) ? __fdiv_rn(1.0f, (float)(double)(hi - lo)) : 0.0f;
-    float acc = 0.0f;
+    float acc = (MODE == 2) ? out_mean[(size_t)s * K + k] : 0.0f;
     uint64_t i = lo;
     for (; i + 8 <= hi; i += 8) {
         float x[8], w[8];
@@ -158,7 +161,7 @@ __global__ void k_segment_mean(const float* __restrict__ proj, int K, const uint
         for (int u = 0; u < 8; ++u) {
             const uint32_t c = cell_sorted[i + u];
             x[u] = proj[(size_t)c * K + k];
-            w[u] = (MODE == 1 && mult) ? mult[c] : 1.0f;
+            w[u] = (MODE >= 1 && mult) ? mult[c] : 1.0f;
         }
 #pragma unroll
         for (int u = 0; u < 8; ++u)
@@ -167,15 +170,22 @@ __global__ void k_segment_mean(const float* __restrict__ proj, int K, const uint
     for (; i < hi; ++i) {
         const uint32_t c = cell_sorted[i];
         const float x = proj[(size_t)c * K + k];
-        const float w = (MODE == 1 && mult) ? mult[c] : 1.0f;
+        const float w = (MODE >= 1 && mult) ? mult[c] : 1.0f;
         acc = (MODE == 0) ? __fadd_rn(__fmul_rn(denom, x), acc) : __fadd_rn(acc, __fmul_rn(x, w));
     }
     if (MODE == 1) {
         const float inv = __fdiv_rn(1.0f, cnt);
         acc = __fmul_rn(acc, inv);
-        if (k == 0 && out_count) out_count[s] = cnt;
     }
+    if (MODE >= 1 && k == 0 && out_count) out_count[s] = cnt;
     out_mean[(size_t)s * K + k] = acc;
+}
+
+__global__ void k_centroid_finish(const float* __restrict__ sum, const float* __restrict__ count, uint64_t n, int K,
+                                  float* __restrict__ cen) {
+    const uint64_t e = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n * (uint64_t)K) return;
+    cen[e] = __fmul_rn(sum[e], __fdiv_rn(1.0f, count[e / K]));  // pb_samples.rs:171-175
 }
 
 __global__ void k_gather_rows(const float* __restrict__ src, int K, const uint32_t* __restrict__ rows, uint64_t n,
@@ -568,7 +578,7 @@ constexpr int PM_U = 4;       // cells scored per pass over a query's coordinate
 __global__ void __launch_bounds__(PM_Q) k_pb_min_dist(const float* __restrict__ proj, int K, const uint32_t* __restrict__ cell_sorted,
                                                       const uint64_t* __restrict__ pb_off, const float* __restrict__ centroids,
                                                       const uint32_t* __restrict__ pb_batch, uint32_t npb, uint32_t q0, uint32_t nq,
-                                                      unsigned long long* __restrict__ keys) {
+                                                      uint32_t cell_offset, unsigned long long* __restrict__ keys) {
     extern __shared__ float pm_smem[];
     const int ds = K | 1;
     float* qs = pm_smem;                        // PM_Q x ds
@@ -622,13 +632,13 @@ __global__ void __launch_bounds__(PM_Q) k_pb_min_dist(const float* __restrict__ 
                     const float df = __fsub_rn(cs[(size_t)(t + u) * K + cc], myq[cc]);
                     sum = __fadd_rn(sum, __fmul_rn(df, df));
                 }
-                const unsigned long long key = ((unsigned long long)__float_as_uint(sum) << 32) | cell_id[t + u];
+                const unsigned long long key = ((unsigned long long)__float_as_uint(sum) << 32) | (cell_id[t + u] + cell_offset);
                 best = key < best ? key : best;
             }
         }
         for (; t < nt; ++t) {
             const float d2 = adj_l2_sq(cs + (size_t)t * K, myq, K);
-            const unsigned long long key = ((unsigned long long)__float_as_uint(d2) << 32) | cell_id[t];
+            const unsigned long long key = ((unsigned long long)__float_as_uint(d2) << 32) | (cell_id[t] + cell_offset);
             best = key < best ? key : best;
         }
     }
@@ -1103,7 +1113,7 @@ extern "C" int lg_pb_match(lg_ctx* ctx, const float* proj_kn, int K, uint64_t nc
     for (uint32_t q0 = 0; q0 < npb; q0 += QC) {
         const uint32_t nq = std::min(QC, npb - q0);
         dim3 grid(npb, (nq + PM_Q - 1) / PM_Q);
-        k_pb_min_dist<<<grid, PM_Q, smem, ctx->stream>>>(d_proj, K, d_cell, d_off, d_cen, d_pbb, npb, q0, nq, d_keys);
+        k_pb_min_dist<<<grid, PM_Q, smem, ctx->stream>>>(d_proj, K, d_cell, d_off, d_cen, d_pbb, npb, q0, nq, 0u, d_keys);
         ctx->launches++;
         LG_CUDA(ctx, cudaGetLastError());
         LG_LAUNCH(ctx, k_pb_topk, (unsigned)(((uint64_t)nq * B * 32 + 255) / 256), 256, 0, d_keys, npb, q0, nq, B, d_batch_pb, d_batch_off,
@@ -1192,5 +1202,131 @@ extern "C" int lg_fine_to_coarse(lg_ctx* ctx, const uint64_t* codes, const uint3
     *out_num_coarse = (uint32_t)uniq.size();
     LG_CUDA(ctx, cudaMemcpyAsync(out_fine_to_coarse, f2c.data(), sizeof(uint32_t) * nfine, cudaMemcpyDefault, ctx->stream));
     LG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return st.finish();
+}
+
+// ---- staged form of the pb-sample arm for cell-sharded runs (device pointers; the exchanges are the caller's) ----------
+extern "C" int lg_pair_presence(lg_ctx* ctx, const uint32_t* d_group, const uint32_t* d_batch, uint64_t ncols, uint32_t S, uint32_t B,
+                                uint32_t* d_present) {
+    if (!ctx) return LG_ERR_INVALID;
+    LG_REQUIRE(ctx, d_group && d_batch && d_present && S >= 1 && B >= 1, "lg_pair_presence: bad argument");
+    cudaSetDevice(ctx->device);
+    LG_CUDA(ctx, cudaMemsetAsync(d_present, 0, sizeof(uint32_t) * (size_t)S * B, ctx->stream));
+    if (ncols) LG_LAUNCH(ctx, k_pair_presence, (unsigned)((ncols + 255) / 256), 256, 0, d_group, d_batch, ncols, S, B, d_present);
+    return LG_OK;
+}
+
+// host math: pb-sample ids from the (all-reduced) presence flags, group-major with batches ascending
+extern "C" int lg_pb_ids(lg_ctx* ctx, const uint32_t* present, uint32_t S, uint32_t B, uint32_t* out_id, uint32_t* out_pb_group,
+                         uint32_t* out_pb_batch, uint32_t* out_num_pb) {
+    if (!ctx) return LG_ERR_INVALID;
+    LG_REQUIRE(ctx, present && out_id && out_pb_group && out_pb_batch && out_num_pb, "lg_pb_ids: null argument");
+    LG_REQUIRE(ctx, !lg_is_device_ptr(present) && !lg_is_device_ptr(out_id), "lg_pb_ids is host math: pass host arrays");
+    uint32_t n = 0;
+    for (size_t e = 0; e < (size_t)S * B; ++e) {
+        out_id[e] = NONE;
+        if (present[e]) {
+            out_id[e] = n;
+            out_pb_group[n] = (uint32_t)(e / B);
+            out_pb_batch[n] = (uint32_t)(e % B);
+            ++n;
+        }
+    }
+    *out_num_pb = n;
+    return LG_OK;
+}
+
+extern "C" int lg_cells_to_pb(lg_ctx* ctx, const uint32_t* d_group, const uint32_t* d_batch, uint64_t ncols, uint32_t S, uint32_t B,
+                              const uint32_t* d_id, uint32_t* d_cell_to_pb) {
+    if (!ctx) return LG_ERR_INVALID;
+    LG_REQUIRE(ctx, d_group && d_batch && d_id && d_cell_to_pb, "lg_cells_to_pb: null argument");
+    cudaSetDevice(ctx->device);
+    if (ncols) LG_LAUNCH(ctx, k_cell_to_pb, (unsigned)((ncols + 255) / 256), 256, 0, d_group, d_batch, ncols, S, B, d_id, d_cell_to_pb);
+    return LG_OK;
+}
+
+// continues the serial centroid folds (sum of K-vectors x multiplicity, sum of multiplicities) over this shard's cells
+extern "C" int lg_pb_centroid_fold(lg_ctx* ctx, const float* d_proj, int K, uint64_t ncols, const uint32_t* d_cell_to_pb, uint32_t npb,
+                                   const float* d_mult, float* d_sum, float* d_count) {
+    if (!ctx) return LG_ERR_INVALID;
+    LG_REQUIRE(ctx, d_proj && d_cell_to_pb && d_sum && d_count && K >= 1 && K <= 1024 && npb >= 1 && ncols < 0xFFFFFFFFull,
+               "lg_pb_centroid_fold: bad argument");
+    cudaSetDevice(ctx->device);
+    LgStage st(ctx);
+    std::vector<uint32_t> counts;
+    LG_TRY(label_counts_host(ctx, st, d_cell_to_pb, ncols, npb, counts));
+    std::vector<uint64_t> off(npb + 1, 0);
+    for (uint32_t p = 0; p < npb; ++p) off[p + 1] = off[p] + counts[p];
+    uint32_t *d_lab, *d_cell;
+    uint64_t* d_off;
+    LG_TRY(sort_cells_by_label(ctx, st, d_cell_to_pb, ncols, &d_lab, &d_cell));
+    LG_TRY(upload(ctx, st, off, &d_off));
+    LG_LAUNCH(ctx, k_segment_mean<2>, npb, ((K + 31) / 32) * 32, 0, d_proj, K, d_cell, d_off, d_mult, d_sum, d_count);
+    return st.finish();
+}
+
+extern "C" int lg_pb_centroid_finish(lg_ctx* ctx, const float* d_sum, const float* d_count, uint32_t npb, int K, float* d_centroids) {
+    if (!ctx) return LG_ERR_INVALID;
+    LG_REQUIRE(ctx, d_sum && d_count && d_centroids && K >= 1, "lg_pb_centroid_finish: bad argument");
+    cudaSetDevice(ctx->device);
+    if (npb) LG_LAUNCH(ctx, k_centroid_finish, (unsigned)(((uint64_t)npb * K + 255) / 256), 256, 0, d_sum, d_count, (uint64_t)npb, K, d_centroids);
+    return LG_OK;
+}
+
+// keys[q - q0][p] over THIS shard's cells, cell indices offset to the global numbering (min-reducible across shards)
+extern "C" int lg_pb_min_keys(lg_ctx* ctx, const float* d_proj, int K, uint64_t ncols, const uint32_t* d_cell_to_pb, uint64_t cell_offset,
+                              const float* d_centroids, const uint32_t* d_pb_batch, uint32_t npb, uint32_t q0, uint32_t nq,
+                              uint64_t* d_keys) {
+    if (!ctx) return LG_ERR_INVALID;
+    LG_REQUIRE(ctx, d_proj && d_cell_to_pb && d_centroids && d_pb_batch && d_keys, "lg_pb_min_keys: null argument");
+    LG_REQUIRE(ctx, K >= 1 && K <= 256 && npb >= 1 && q0 + (uint64_t)nq <= npb && cell_offset + ncols < 0xFFFFFFFFull,
+               "lg_pb_min_keys: bad shape");
+    cudaSetDevice(ctx->device);
+    LgStage st(ctx);
+    std::vector<uint32_t> counts;
+    LG_TRY(label_counts_host(ctx, st, d_cell_to_pb, ncols, npb, counts));
+    std::vector<uint64_t> off(npb + 1, 0);
+    for (uint32_t p = 0; p < npb; ++p) off[p + 1] = off[p] + counts[p];
+    uint32_t *d_lab, *d_cell;
+    uint64_t* d_off;
+    LG_TRY(sort_cells_by_label(ctx, st, d_cell_to_pb, ncols, &d_lab, &d_cell));
+    LG_TRY(upload(ctx, st, off, &d_off));
+    const size_t smem = ((size_t)PM_Q * (K | 1) + (size_t)PM_CELLS * K) * sizeof(float);
+    LG_REQUIRE(ctx, smem <= ctx->smem_optin, "lg_pb_min_keys: K too large for shared memory");
+    LG_CUDA(ctx, cudaFuncSetAttribute(k_pb_min_dist, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (nq) {
+        dim3 grid(npb, (nq + PM_Q - 1) / PM_Q);
+        k_pb_min_dist<<<grid, PM_Q, smem, ctx->stream>>>(d_proj, K, d_cell, d_off, d_centroids, d_pb_batch, npb, q0, nq, (uint32_t)cell_offset,
+                                                        reinterpret_cast<unsigned long long*>(d_keys));
+        ctx->launches++;
+        LG_CUDA(ctx, cudaGetLastError());
+    }
+    return st.finish();
+}
+
+extern "C" int lg_pb_topk_keys(lg_ctx* ctx, const uint64_t* d_keys, uint32_t npb, uint32_t q0, uint32_t nq, uint32_t B,
+                               const uint32_t* pb_batch, int knn, uint32_t* d_out_pb, float* d_out_dist) {
+    if (!ctx) return LG_ERR_INVALID;
+    LG_REQUIRE(ctx, d_keys && pb_batch && d_out_pb && d_out_dist && knn >= 1 && B >= 1, "lg_pb_topk_keys: bad argument");
+    cudaSetDevice(ctx->device);
+    LgStage st(ctx);
+    std::vector<uint32_t> pbb;
+    LG_TRY(to_host(ctx, pb_batch, npb, pbb));
+    std::vector<uint32_t> batch_off(B + 1, 0), batch_pb(npb);
+    for (uint32_t p = 0; p < npb; ++p) {
+        LG_REQUIRE(ctx, pbb[p] < B, "lg_pb_topk_keys: pb_batch out of range");
+        batch_off[pbb[p] + 1]++;
+    }
+    for (uint32_t b = 0; b < B; ++b) batch_off[b + 1] += batch_off[b];
+    {
+        std::vector<uint32_t> cur(batch_off.begin(), batch_off.end() - 1);
+        for (uint32_t p = 0; p < npb; ++p) batch_pb[cur[pbb[p]]++] = p;
+    }
+    uint32_t *d_batch_pb, *d_batch_off;
+    LG_TRY(upload(ctx, st, batch_pb, &d_batch_pb));
+    LG_TRY(upload(ctx, st, batch_off, &d_batch_off));
+    if (nq)
+        LG_LAUNCH(ctx, k_pb_topk, (unsigned)(((uint64_t)nq * B * 32 + 255) / 256), 256, 0, reinterpret_cast<const unsigned long long*>(d_keys),
+                  npb, q0, nq, B, d_batch_pb, d_batch_off, knn, d_out_pb, d_out_dist);
     return st.finish();
 }

@@ -75,6 +75,13 @@ _sig = {
     "lg_pb_layout": [_vp, _vp, _i, _u64, _vp, _u32, _vp, _u32, _vp, _vp, _vp, _vp, _vp, _vp, C.POINTER(_u32)],
     "lg_pb_match": [_vp, _vp, _i, _u64, _vp, _u32, _vp, _vp, _vp, _u32, _i, _vp, _vp],
     "lg_collect_matched_stat_coarse": [_vp, _vp, _u64, _u32, _vp, _vp, _u32, _vp, _vp, _u32, _vp, _vp],
+    "lg_pair_presence": [_vp, _vp, _vp, _u64, _u32, _u32, _vp],
+    "lg_pb_ids": [_vp, _vp, _u32, _u32, _vp, _vp, _vp, C.POINTER(_u32)],
+    "lg_cells_to_pb": [_vp, _vp, _vp, _u64, _u32, _u32, _vp, _vp],
+    "lg_pb_centroid_fold": [_vp, _vp, _i, _u64, _vp, _u32, _vp, _vp, _vp],
+    "lg_pb_centroid_finish": [_vp, _vp, _vp, _u32, _i, _vp],
+    "lg_pb_min_keys": [_vp, _vp, _i, _u64, _vp, _u64, _vp, _vp, _u32, _u32, _u32, _vp],
+    "lg_pb_topk_keys": [_vp, _vp, _u32, _u32, _u32, _u32, _vp, _i, _vp, _vp],
     "lg_fine_to_coarse": [_vp, _vp, _vp, _u64, _u32, _i, _vp, C.POINTER(_u32)],
     "lg_sim_poisson_csc": [_vp, _u64, _u64, _u64, _u64, _vp, _vp, _u32, _u32, _vp, _vp, _vp, C.POINTER(_vp)],
 }

@@ -204,6 +204,69 @@ class HotPath:
                                             _ptr(out_dist)))
         return out_idx, out_dist
 
+    # ---- stage 7, pb-sample arm ---------------------------------------------------------------------
+    def pb_matched_stat(self, block: CscBlock, proj: torch.Tensor, group: torch.Tensor, S: int, batch: torch.Tensor, B: int,
+                        knn: int, mult: torch.Tensor | None = None):
+        """collapse_columns_multilevel_vec's batch arm (collapse_data/mod.rs:940-990) over cell shards:
+        build_pb_samples + per_batch_sc_neighbors + collect_matched_stat_coarse.  Exchanges: all-reduce(max) of the
+        (group, batch) presence flags; the centroid folds handed on in rank order (they are serial f32 folds over
+        cells, so the result is the one a single GPU computes); all-reduce(sum) of the per-pb-sample gene sums;
+        all-reduce(min) of the (squared distance, global cell) keys.  Returns a dict with the layout, the matches and
+        the imputed / residual sums (S, D) — identical on every rank and for every GPU count."""
+        ctx, ex, dev = self.ctx, self.ex, self.dev
+        n, K = proj.shape
+        cap = S * B
+        present = torch.empty(cap, dtype=torch.int32, device=dev)
+        ctx.check(lib.lg_pair_presence(ctx.h, _ptr(group), _ptr(batch), n, S, B, _ptr(present)))
+        ex.max_(present)
+        present_h = present.cpu().numpy().astype(np.uint32)
+        id_h, pg_h, pb_h = np.empty(cap, np.uint32), np.empty(cap, np.uint32), np.empty(cap, np.uint32)
+        npb_c = C.c_uint32()
+        ctx.check(lib.lg_pb_ids(ctx.h, _ptr(present_h), S, B, _ptr(id_h), _ptr(pg_h), _ptr(pb_h), C.byref(npb_c)))
+        npb = int(npb_c.value)
+        if npb == 0:
+            raise LegumeError(1, "no pb-samples built")
+        as_i32 = lambda a: torch.from_numpy(a.view(np.int32).copy()).to(dev)
+        ids, pb_group, pb_batch = as_i32(id_h), as_i32(pg_h[:npb]), as_i32(pb_h[:npb])
+        c2p = torch.empty(n, dtype=torch.int32, device=dev)
+        ctx.check(lib.lg_cells_to_pb(ctx.h, _ptr(group), _ptr(batch), n, S, B, _ptr(ids), _ptr(c2p)))
+        # centroids: one serial fold per pb-sample, continued shard after shard
+        csum = torch.zeros((npb, K), dtype=torch.float32, device=dev)
+        ccnt = torch.zeros(npb, dtype=torch.float32, device=dev)
+        for r in range(self.world):
+            if r == self.rank:
+                ctx.check(lib.lg_pb_centroid_fold(ctx.h, _ptr(proj), K, n, _ptr(c2p), npb, _ptr(mult), _ptr(csum), _ptr(ccnt)))
+            ex.broadcast_(csum, r)
+            ex.broadcast_(ccnt, r)
+        cen = torch.empty((npb, K), dtype=torch.float32, device=dev)
+        ctx.check(lib.lg_pb_centroid_finish(ctx.h, _ptr(csum), _ptr(ccnt), npb, K, _ptr(cen)))
+        # per-pb-sample gene sums: the collapse with the pb-sample as the label (integer counts: exact in any order)
+        gene_sums, _ = self.collapse_basic(block, c2p, npb, mult)
+        # matches: min over every shard's cells, then the per-batch top-k
+        T = B * knn
+        mp = torch.empty((npb, T), dtype=torch.int32, device=dev)
+        md = torch.empty((npb, T), dtype=torch.float32, device=dev)
+        counts = ex.counts(n, dev)
+        offset = int(sum(counts[:self.rank]))
+        qc = max(256, min(npb, (1 << 27) // npb))
+        keys = torch.empty((qc, npb), dtype=torch.int64, device=dev)
+        for q0 in range(0, npb, qc):
+            nq = min(qc, npb - q0)
+            ctx.check(lib.lg_pb_min_keys(ctx.h, _ptr(proj), K, n, _ptr(c2p), offset, _ptr(cen), _ptr(pb_batch), npb, q0, nq, _ptr(keys)))
+            if self.world > 1:  # keys are < 2^63 (non-negative f32 bits << 32 | index): signed order == unsigned order;
+                # the all-ones "nothing here" key is -1 as int64, so shift it out of the way of the minimum
+                view = keys[:nq]
+                view[view < 0] = torch.iinfo(torch.int64).max
+                ex.dist.all_reduce(view, op=ex.dist.ReduceOp.MIN, group=ex.pg)
+                view[view == torch.iinfo(torch.int64).max] = -1
+            ctx.check(lib.lg_pb_topk_keys(ctx.h, _ptr(keys), npb, q0, nq, B, _ptr(pb_batch), knn, _ptr(mp), _ptr(md)))
+        imp = torch.empty((S, block.nrows), dtype=torch.float32, device=dev)
+        res = torch.empty((S, block.nrows), dtype=torch.float32, device=dev)
+        ctx.check(lib.lg_collect_matched_stat_coarse(ctx.h, _ptr(gene_sums), block.nrows, npb, _ptr(ccnt), _ptr(pb_group), S, _ptr(mp),
+                                                     _ptr(md), T, _ptr(imp), _ptr(res)))
+        return dict(num_pb=npb, cell_to_pb=c2p, pb_group=pb_group, pb_batch=pb_batch, pb_count=ccnt, centroids=cen,
+                    gene_sums=gene_sums, matched_pb=mp, matched_dist=md, imputed_sum_ds=imp, residual_sum_ds=res)
+
     # ---- whole path --------------------------------------------------------------------------------
     def run(self, block: CscBlock, basis_kd: torch.Tensor, batch, nbatch: int, kk: int, target=TARGET_ALL):
         """projection -> codes -> groups -> collapse -> posterior (single-batch arm of the path)"""

@@ -137,7 +137,68 @@ def _case_knn_shard_merge(ex, shard_range):
     assert np.array_equal(got_i, widx) and got_d.astype(np.float32).tobytes() == wdist.tobytes()
 
 
-@pytest.mark.parametrize("case", ["scalars", "block_partials", "collapse_allreduce", "knn_shard_merge"])
+def _case_centroid_fold_chain(ex, shard_range):
+    """K9: the pb-sample centroids are serial f32 folds over cells; shards continue the fold one after the other in
+    rank order (broadcast of the running sums), which reproduces the unsharded fold bit for bit — a plain all-reduce
+    of per-shard partial sums would not"""
+    import oracle as orc
+    N, K, S, B = 2600, 7, 5, 3
+    rng = np.random.default_rng(3)
+    proj = (rng.standard_normal((N, K)) * 10.0 ** rng.integers(-3, 4, (N, 1))).astype(np.float32)
+    grp = rng.integers(0, S, N).astype(np.uint32)
+    bat = rng.integers(0, B, N).astype(np.uint32)
+    want = orc.pb_layout(proj, grp, S, bat, B)
+    npb, c2p = want["num_pb"], want["cell_to_pb"]
+    lo, hi = shard_range(N, ex.rank, ex.world)
+    csum, ccnt = torch.zeros((npb, K), dtype=torch.float32), torch.zeros(npb, dtype=torch.float32)
+    for r in range(ex.world):
+        if r == ex.rank:  # lg_pb_centroid_fold: continue the folds over this shard's cells, ascending
+            a, c = csum.numpy(), ccnt.numpy()
+            for j in range(lo, hi):
+                a[c2p[j]] = a[c2p[j]] + proj[j] * np.float32(1.0)
+                c[c2p[j]] = c[c2p[j]] + np.float32(1.0)
+        ex.broadcast_(csum, r)
+        ex.broadcast_(ccnt, r)
+    cen = csum.numpy() * (np.float32(1.0) / ccnt.numpy())[:, None]  # lg_pb_centroid_finish
+    assert cen.astype(np.float32).tobytes() == want["centroids"].tobytes()
+    assert ccnt.numpy().tobytes() == want["pb_count"].tobytes()
+    # the contrast: summing per-shard partial folds is NOT the same arithmetic
+    part = np.zeros((npb, K), np.float32)
+    for j in range(lo, hi):
+        part[c2p[j]] = part[c2p[j]] + proj[j]
+    tot = torch.from_numpy(part.copy())
+    ex.sum_(tot)
+    assert tot.numpy().tobytes() != csum.numpy().tobytes()
+
+
+def _case_min_keys_allreduce(ex, shard_range):
+    """K9 matches: (squared distance << 32 | global cell) keys, min-reduced over shards as int64 with the all-ones
+    'nothing here' key moved out of the way, equal the unsharded minimum"""
+    rng = np.random.default_rng(4)
+    nq, npb, ncell = 6, 9, 500
+    d2 = rng.random((nq, ncell)).astype(np.float32)
+    owner = rng.integers(0, npb + 2, ncell)  # some pb-samples own no cell at all
+    keys_all = (d2.view(np.uint32).astype(np.uint64) << np.uint64(32)) | np.arange(ncell, dtype=np.uint64)[None, :]
+    full = np.full((nq, npb), np.uint64(0xFFFFFFFFFFFFFFFF))
+    for p in range(npb):
+        cols = np.flatnonzero(owner == p)
+        if len(cols):
+            full[:, p] = keys_all[:, cols].min(1)
+    lo, hi = (0, 260) if ex.rank == 0 else (260, ncell)
+    mine = np.full((nq, npb), np.uint64(0xFFFFFFFFFFFFFFFF))
+    for p in range(npb):
+        cols = np.flatnonzero(owner[lo:hi] == p) + lo
+        if len(cols):
+            mine[:, p] = keys_all[:, cols].min(1)
+    t = torch.from_numpy(mine.view(np.int64).copy())
+    t[t < 0] = torch.iinfo(torch.int64).max
+    ex.dist.all_reduce(t, op=ex.dist.ReduceOp.MIN, group=ex.pg)
+    t[t == torch.iinfo(torch.int64).max] = -1
+    assert np.array_equal(t.numpy().view(np.uint64), full)
+
+
+@pytest.mark.parametrize("case", ["scalars", "block_partials", "collapse_allreduce", "knn_shard_merge", "centroid_fold_chain",
+                                  "min_keys_allreduce"])
 def test_two_gloo_ranks(case):
     _run(case)
 

@@ -303,3 +303,28 @@ def test_merge_stat_many_groups(lg, ctx):
     fine = rng.integers(0, 50, (300, 64)).astype(np.float32)
     f2c = rng.integers(0, 37, 300).astype(np.uint32)
     assert np.array_equal(lg.merge_stat(ctx, fine, f2c, 37), orc.merge_stat(fine, f2c, 37))
+
+
+def test_sharded_driver_pb_arm_matches_oracle(lg, ctx):
+    """HotPath.pb_matched_stat (the staged, shard-able form of the pb-sample arm) on one rank against the oracle"""
+    import torch
+    from legume_b200.pipeline import HotPath
+    D, N, B, S, K, knn = 400, 3000, 3, 16, 20, 4
+    ip, ix, v, proj, batch, grp = make_case(21, D, N, B, S, K, clustered=True)
+    blk = lg.CscBlock.upload(ctx, ip, ix, v, D)
+    hp = HotPath(ctx)
+    t = lambda a, dt: torch.from_numpy(a.astype(dt)).cuda()
+    out = hp.pb_matched_stat(blk, t(proj, np.float32), t(grp, np.int32), S, t(batch, np.int32), B, knn)
+    torch.cuda.synchronize()
+    want = orc.pb_layout(proj, grp, S, batch, B)
+    assert out["num_pb"] == want["num_pb"]
+    assert np.array_equal(out["cell_to_pb"].cpu().numpy().astype(np.uint32), want["cell_to_pb"])
+    assert out["centroids"].cpu().numpy().tobytes() == want["centroids"].tobytes()
+    assert out["pb_count"].cpu().numpy().tobytes() == want["pb_count"].tobytes()
+    wmp, wmd = orc.pb_match(proj, batch, B, want, knn)
+    assert np.array_equal(out["matched_pb"].cpu().numpy().astype(np.uint32), wmp)
+    assert out["matched_dist"].cpu().numpy().tobytes() == wmd.tobytes()
+    gs, _ = orc.collapse_basic(ip, ix, v, D, want["cell_to_pb"], want["num_pb"])
+    assert np.array_equal(out["gene_sums"].cpu().numpy(), gs)
+    wimp, wres = orc.collect_matched_stat_coarse(gs, want["pb_count"], want["pb_group"], S, wmp, wmd)
+    assert close(out["imputed_sum_ds"].cpu().numpy(), wimp, TOL) and close(out["residual_sum_ds"].cpu().numpy(), wres, TOL)

@@ -41,13 +41,16 @@ sum_db, n_bs = hp.collapse_batch(blk, out["group"], batch, out["num_groups"], B)
 q_local = out["proj"][: min(4096, hi - lo)].contiguous()
 excl = torch.arange(lo, lo + q_local.shape[0], dtype=torch.int32, device=dev)
 kidx, kdist = hp.knn_topk_sharded(out["proj"], q_local, k, excl)
+# pb-sample arm of the cross-batch adjustment over the shards
+pbs = hp.pb_matched_stat(blk, out["proj"], out["group"], out["num_groups"], batch, B, 5)
 torch.cuda.synchronize()
 
 report = {"world": world, "cells": N, "genes": D}
 if world > 1:
     # rank 0 recomputes everything unsharded on its own GPU (no collectives) and compares with the gathered shards
     gathered = {}
-    for name, t in (("proj", out["proj"]), ("codes", out["codes"]), ("group", out["group"]), ("kidx", kidx), ("kdist", kdist)):
+    for name, t in (("proj", out["proj"]), ("codes", out["codes"]), ("group", out["group"]), ("kidx", kidx), ("kdist", kdist),
+                    ("c2p", pbs["cell_to_pb"])):
         rows, cnt = hp.ex.all_gather_rows(t.contiguous())
         gathered[name] = (rows, cnt)
     if rank == 0:
@@ -80,6 +83,13 @@ if world > 1:
         wdist = torch.empty((qall.shape[0], k), dtype=torch.float32, device=dev)
         ctx.check(lib.lg_knn_topk(ctx.h, lg._ptr(ref["proj"]), N, lg._ptr(qall), qall.shape[0], K, k, lg._ptr(exall), lg._ptr(widx),
                                   lg._ptr(wdist)))
+        rpb = solo.pb_matched_stat(fblk, ref["proj"], ref["group"], ref["num_groups"], fbatch, B, 5)
+        report["pb_layout_bit_exact"] = (pbs["num_pb"] == rpb["num_pb"] and same(gathered["c2p"][0], rpb["cell_to_pb"])
+                                         and same(pbs["centroids"], rpb["centroids"]) and same(pbs["pb_count"], rpb["pb_count"]))
+        report["pb_gene_sums_bit_exact"] = same(pbs["gene_sums"], rpb["gene_sums"])
+        report["pb_matches_bit_exact"] = same(pbs["matched_pb"], rpb["matched_pb"]) and same(pbs["matched_dist"], rpb["matched_dist"])
+        report["pb_matched_stat_bit_exact"] = (same(pbs["imputed_sum_ds"], rpb["imputed_sum_ds"])
+                                               and same(pbs["residual_sum_ds"], rpb["residual_sum_ds"]))
         report["knn_idx_bit_exact"] = same(gathered["kidx"][0], widx)
         report["knn_dist_bit_exact"] = same(gathered["kdist"][0], wdist)
         report["ok"] = all(v for key, v in report.items() if key.endswith("bit_exact"))
