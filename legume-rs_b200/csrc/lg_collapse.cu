@@ -14,7 +14,7 @@
 
 constexpr int COLLAPSE_THREADS = 1024;  // one CTA per SM (the accumulator fills most of shared memory)
 constexpr int COLLAPSE_CHUNK = 256;     // sorted cells per work item
-constexpr int COLLAPSE_UNROLL = 4;      // independent 32-nnz loads in flight per warp
+constexpr int COLLAPSE_UNROLL = 8;      // independent 32-nnz loads in flight per warp (the kernel is bound by bytes in flight)
 
 __global__ void k_iota_u32(uint32_t* p, uint64_t n) {
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -113,6 +113,24 @@ __global__ void __launch_bounds__(COLLAPSE_THREADS, 1) k_collapse_sorted(
 #pragma unroll
                         for (int u = 0; u < COLLAPSE_UNROLL; ++u)
                             if (gi[u] < W) A::add(&acc[gi[u]], vv[u], w);
+                    }
+                    for (; t + 96 < hi; t += 128) {  // lower tiers: keep several loads in flight for the ragged rest
+                        uint32_t gi[4];
+                        float vv[4];
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) {
+                            gi[u] = __ldg(indices + t + 32 * u) - g0;
+                            vv[u] = __ldg(values + t + 32 * u);
+                        }
+#pragma unroll
+                        for (int u = 0; u < 4; ++u)
+                            if (gi[u] < W) A::add(&acc[gi[u]], vv[u], w);
+                    }
+                    for (; t + 32 < hi; t += 64) {
+                        const uint32_t ga = __ldg(indices + t) - g0, gb = __ldg(indices + t + 32) - g0;
+                        const float va = __ldg(values + t), vb = __ldg(values + t + 32);
+                        if (ga < W) A::add(&acc[ga], va, w);
+                        if (gb < W) A::add(&acc[gb], vb, w);
                     }
                     for (; t < hi; t += 32) {
                         const uint32_t gi = __ldg(indices + t) - g0;
