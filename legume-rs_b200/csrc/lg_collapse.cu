@@ -50,9 +50,11 @@ struct Acc<false> {
 };
 
 // window [g0, g0 + W) of the gene axis lives in shared memory
-template <bool INT>
+// VEC: index / value arrays are 16-byte aligned, so a lane reads 4 consecutive nnz per 128-bit load (entries of the
+// neighbouring columns that share the first / last group are masked): four times the bytes in flight per load
+template <bool INT, bool VEC>
 __global__ void __launch_bounds__(COLLAPSE_THREADS, 1) k_collapse_sorted(
-    const uint64_t* __restrict__ indptr, const uint32_t* __restrict__ indices, const float* __restrict__ values,
+    const uint64_t* __restrict__ indptr, const uint32_t* __restrict__ indices, const float* __restrict__ values, uint64_t nnz_total,
     const uint32_t* __restrict__ sorted_label, const uint32_t* __restrict__ sorted_cell, uint64_t ncells,
     const float* __restrict__ mult, uint32_t S, uint64_t D, uint32_t g0, uint32_t W, float* __restrict__ sum_ds,
     float* __restrict__ size_s, unsigned long long* __restrict__ next_chunk) {
@@ -101,6 +103,45 @@ __global__ void __launch_bounds__(COLLAPSE_THREADS, 1) k_collapse_sorted(
                         hi_n = indptr[cell_n + 1];
                     }
                     const float w = (!INT && mult) ? mult[cell] : 1.0f;
+                    if constexpr (VEC) {
+                        constexpr int VU = 4;  // 128-bit groups in flight per lane and array
+                        const uint64_t hi4 = nnz_total & ~3ull;  // groups at or beyond this one would cross the array end
+                        for (uint64_t c = (lo & ~3ull) + 4ull * lane; c < hi; c += 128ull * VU) {
+                            uint4 gq[VU];
+                            float4 vq[VU];
+#pragma unroll
+                            for (int u = 0; u < VU; ++u) {
+                                const uint64_t cu = c + 128ull * u;
+                                gq[u] = make_uint4(0, 0, 0, 0);
+                                vq[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+                                if (cu < hi) {
+                                    if (cu < hi4) {
+                                        gq[u] = __ldg(reinterpret_cast<const uint4*>(indices + cu));
+                                        vq[u] = __ldg(reinterpret_cast<const float4*>(values + cu));
+                                    } else {  // the last, partial group of the whole array
+                                        uint32_t gg[4] = {0, 0, 0, 0};
+                                        float vv[4] = {0.f, 0.f, 0.f, 0.f};
+                                        for (int e = 0; e < 4; ++e)
+                                            if (cu + e < nnz_total) {
+                                                gg[e] = indices[cu + e];
+                                                vv[e] = values[cu + e];
+                                            }
+                                        gq[u] = make_uint4(gg[0], gg[1], gg[2], gg[3]);
+                                        vq[u] = make_float4(vv[0], vv[1], vv[2], vv[3]);
+                                    }
+                                }
+                            }
+#pragma unroll
+                            for (int u = 0; u < VU; ++u) {
+                                const uint64_t cu = c + 128ull * u;
+                                const uint32_t ge[4] = {gq[u].x - g0, gq[u].y - g0, gq[u].z - g0, gq[u].w - g0};
+                                const float ve[4] = {vq[u].x, vq[u].y, vq[u].z, vq[u].w};
+#pragma unroll
+                                for (int e = 0; e < 4; ++e)
+                                    if (cu + e >= lo && cu + e < hi && ge[e] < W) A::add(&acc[ge[e]], ve[e], w);
+                            }
+                        }
+                    } else {
                     uint64_t t = lo + lane;
                     for (; t + 32 * (COLLAPSE_UNROLL - 1) < hi; t += 32 * COLLAPSE_UNROLL) {
                         uint32_t gi[COLLAPSE_UNROLL];
@@ -135,6 +176,7 @@ __global__ void __launch_bounds__(COLLAPSE_THREADS, 1) k_collapse_sorted(
                     for (; t < hi; t += 32) {
                         const uint32_t gi = __ldg(indices + t) - g0;
                         if (gi < W) A::add(&acc[gi], __ldg(values + t), w);
+                    }
                     }
                     wsum += (mult ? mult[cell] : 1.0f);
                     p = pn;
@@ -212,15 +254,18 @@ static int collapse_by_label(lg_ctx* ctx, LgStage& st, const lg_csc* m, const ui
         const uint32_t W = (uint32_t)((D - g0) < Wmax ? (D - g0) : Wmax);
         const size_t smem = (size_t)W * sizeof(float);
         LG_CUDA(ctx, cudaMemsetAsync(d_next, 0, sizeof(unsigned long long), ctx->stream));
-        if (use_int) {
-            LG_CUDA(ctx, cudaFuncSetAttribute(k_collapse_sorted<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            LG_LAUNCH(ctx, k_collapse_sorted<true>, ctx->num_sms, COLLAPSE_THREADS, smem, m->indptr, m->indices, m->values,
-                      d_lab_out, d_cell_out, N, d_mult, S, D, (uint32_t)g0, W, d_sum, d_size, d_next);
-        } else {
-            LG_CUDA(ctx, cudaFuncSetAttribute(k_collapse_sorted<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            LG_LAUNCH(ctx, k_collapse_sorted<false>, ctx->num_sms, COLLAPSE_THREADS, smem, m->indptr, m->indices, m->values,
-                      d_lab_out, d_cell_out, N, d_mult, S, D, (uint32_t)g0, W, d_sum, d_size, d_next);
-        }
+        const bool vec = (((uintptr_t)m->indices | (uintptr_t)m->values) & 15) == 0;
+#define LG_COLLAPSE_LAUNCH(I, V)                                                                                                   \
+    do {                                                                                                                           \
+        LG_CUDA(ctx, cudaFuncSetAttribute(k_collapse_sorted<I, V>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));       \
+        LG_LAUNCH(ctx, (k_collapse_sorted<I, V>), ctx->num_sms, COLLAPSE_THREADS, smem, m->indptr, m->indices, m->values, m->nnz, \
+                  d_lab_out, d_cell_out, N, d_mult, S, D, (uint32_t)g0, W, d_sum, d_size, d_next);                                  \
+    } while (0)
+        if (use_int && vec) LG_COLLAPSE_LAUNCH(true, true);
+        else if (use_int) LG_COLLAPSE_LAUNCH(true, false);
+        else if (vec) LG_COLLAPSE_LAUNCH(false, true);
+        else LG_COLLAPSE_LAUNCH(false, false);
+#undef LG_COLLAPSE_LAUNCH
     }
     return LG_OK;
 }
