@@ -96,7 +96,10 @@ constexpr int PREP_LUT = 64;  // log1p look-up for integer counts below this
 // HALF2 (K even, basis 8-byte aligned): the basis rows of TWO exceptions are gathered at once, one per half-warp,
 // as float2 (lane l of a half holds dims 2l, 2l+1, 2l+32, 2l+33) — a third of the instructions per exception of the
 // lanes-as-dims form, which stays as the fallback for odd K.
-template <int NACC, bool HALF2>
+// VEC (index / value arrays 16-byte aligned): the aligned interior of a cell's nnz range is read with 128-bit loads (a lane
+// holds 4 consecutive nnz, twice the bytes in flight per warp and a quarter of the load instructions); the <= 3 entries
+// before and after it go through one masked round.
+template <int NACC, bool HALF2, bool VEC>
 __global__ void __launch_bounds__(PREP_WARPS * 32, 4) k_project_prep(const uint64_t* __restrict__ indptr,
                                                                      const uint32_t* __restrict__ indices,
                                                                      const float* __restrict__ values, uint64_t ncols,
@@ -198,6 +201,47 @@ __global__ void __launch_bounds__(PREP_WARPS * 32, 4) k_project_prep(const uint6
             }
         };
 
+        if constexpr (VEC) {
+            const uint64_t hi = lo + n;
+            const uint64_t a_up = (lo + 3) & ~3ull, z_dn = hi & ~3ull;
+            const uint64_t a = a_up < hi ? a_up : hi, z = z_dn > a ? z_dn : a;  // aligned interior [a, z)
+            {  // head [lo, a) on lanes 0..2, tail [z, hi) on lanes 3..5
+                const uint64_t e = lane < 3 ? lo + lane : z + (lane - 3);
+                const bool live = lane < 3 ? e < a : (lane < 6 && e < hi);
+                const uint32_t ixu = live ? __ldg(indices + e) : 0u;
+                const float vu = live ? __ldg(values + e) : 1.0f;
+                consume(ixu, vu, live);
+            }
+            const uint32_t nbat = (uint32_t)((z - a + 127) >> 7);
+            const uint4* ip4 = reinterpret_cast<const uint4*>(indices + a) + lane;
+            const float4* vp4 = reinterpret_cast<const float4*>(values + a) + lane;
+            const uint32_t ngrp = (uint32_t)((z - a) >> 2);  // 128-bit groups in the interior
+            uint4 g4 = make_uint4(0, 0, 0, 0);
+            float4 x4 = make_float4(1.f, 1.f, 1.f, 1.f);
+            if ((uint32_t)lane < ngrp) {
+                g4 = __ldg(ip4);
+                x4 = __ldg(vp4);
+            }
+            for (uint32_t b = 0; b < nbat; ++b) {
+                // software pipeline: the next 128 nnz are in flight while this batch is consumed
+                uint4 ng = make_uint4(0, 0, 0, 0);
+                float4 nx = make_float4(1.f, 1.f, 1.f, 1.f);
+                const bool nlive = 32u * (b + 1) + lane < ngrp;
+                if (nlive) {
+                    ng = __ldg(ip4 + 32 * (b + 1));
+                    nx = __ldg(vp4 + 32 * (b + 1));
+                }
+                const bool live = 32u * b + lane < ngrp;
+                consume(g4.x, x4.x, live);
+                consume(g4.y, x4.y, live);
+                consume(g4.z, x4.z, live);
+                consume(g4.w, x4.w, live);
+                __syncwarp();
+                while (qtail - qhead >= 32) drain(32);
+                g4 = ng;
+                x4 = nx;
+            }
+        } else {
         const uint32_t nfull = n >> 7;
         uint32_t ix[4];
         float v[4];
@@ -238,6 +282,7 @@ __global__ void __launch_bounds__(PREP_WARPS * 32, 4) k_project_prep(const uint6
                 consume(ixu, vu, live);
             }
             __syncwarp();
+        }
         }
         while (qtail != qhead) drain(min(32u, qtail - qhead));
         const uint32_t n_one = n - qtail;  // qtail counts every queued exception of this cell
@@ -521,16 +566,18 @@ int lg_project_raw_umma(lg_ctx* ctx, const lg_csc* m, const float* d_basis, int 
         if (blocks > cap) blocks = cap;
         const int nacc = (K + 31) / 32;
         const bool half2 = (K % 2 == 0) && (((uintptr_t)d_basis & 7) == 0);
-#define LG_PREP_LAUNCH(NA, H2)                                                                                                      \
+#define LG_PREP_LAUNCH(NA, H2, V)                                                                                                   \
     do {                                                                                                                            \
-        LG_CUDA(ctx, cudaFuncSetAttribute(k_project_prep<NA, H2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psmem));        \
-        LG_LAUNCH(ctx, (k_project_prep<NA, H2>), (unsigned)blocks, PREP_WARPS * 32, psmem, m->indptr, m->indices, m->values,      \
+        LG_CUDA(ctx, cudaFuncSetAttribute(k_project_prep<NA, H2, V>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psmem));     \
+        LG_LAUNCH(ctx, (k_project_prep<NA, H2, V>), (unsigned)blocks, PREP_WARPS * 32, psmem, m->indptr, m->indices, m->values,   \
                   m->ncols, d_basis, K, nchunks, d_bm, d_out, d_scale);                                                             \
     } while (0)
+        const bool vec = (((uintptr_t)m->indices | (uintptr_t)m->values) & 15) == 0;
         if (trace) cudaEventRecord(ev[0], ctx->stream);
-        if (half2) LG_PREP_LAUNCH(2, true);
-        else if (nacc == 1) LG_PREP_LAUNCH(1, false);
-        else LG_PREP_LAUNCH(2, false);
+        if (half2 && vec) LG_PREP_LAUNCH(2, true, true);
+        else if (half2) LG_PREP_LAUNCH(2, true, false);
+        else if (nacc == 1) LG_PREP_LAUNCH(1, false, false);
+        else LG_PREP_LAUNCH(2, false, false);
 #undef LG_PREP_LAUNCH
     }
     const size_t stage_bytes = (size_t)NB * 32 * (GS / 32);
