@@ -421,12 +421,24 @@ __global__ void __launch_bounds__(THREADS, 1) k_project_umma(const uint32_t* __r
             const uint64_t cell = sup * CELLS + (uint64_t)t * TILE_M + row;
             const bool live = cell < ncols;
             float* orow = out + (size_t)cell * K;
+            // rows are 8-byte aligned when K is even (and `out` is): 64-bit loads / stores halve the scattered transactions
+            const bool pair_io = (K % 2 == 0) && ((reinterpret_cast<uintptr_t>(out) & 7) == 0);
             float corr[64];
             float sc = 0.0f;
             if (live) {
                 sc = __ldg(scale + cell);
+                if (pair_io) {
 #pragma unroll
-                for (int k = 0; k < 64; ++k) corr[k] = (k < K) ? __ldcs(orow + k) : 0.0f;
+                    for (int k = 0; k < 64; k += 2) {
+                        float2 c2 = make_float2(0.f, 0.f);
+                        if (k < K) c2 = __ldcs(reinterpret_cast<const float2*>(orow + k));
+                        corr[k] = c2.x;
+                        corr[k + 1] = c2.y;
+                    }
+                } else {
+#pragma unroll
+                    for (int k = 0; k < 64; ++k) corr[k] = (k < K) ? __ldcs(orow + k) : 0.0f;
+                }
             }
             mbar_wait(&bars->acc_full[t], super_it & 1);
             tc_fence_after();
@@ -439,15 +451,22 @@ __global__ void __launch_bounds__(THREADS, 1) k_project_umma(const uint32_t* __r
                     tmem_ld_x16(acc_addr + 2 * K + kb, d2);
                     tmem_wait_ld();
                     if (live) {
+                        float res[16];
 #pragma unroll
                         for (int i = 0; i < 16; ++i) {
-                            const int k = kb + i;
-                            if (k < K) {
-                                // digits carry the A scale of 128: total = 128 * sum(q_i), q in 2^-20 units
-                                const long long tot = ((long long)(int)d2[i] << 16) + ((long long)(int)d1[i] << 8) + (long long)(int)d0[i];
-                                const float sv = (float)((double)tot * (1.0 / (128.0 * 1048576.0)));
-                                __stcs(orow + k, fmaf(sv, sc, corr[k]));
-                            }
+                            // digits carry the A scale of 128: total = 128 * sum(q_i), q in 2^-20 units
+                            const long long tot = ((long long)(int)d2[i] << 16) + ((long long)(int)d1[i] << 8) + (long long)(int)d0[i];
+                            const float sv = (float)((double)tot * (1.0 / (128.0 * 1048576.0)));
+                            res[i] = fmaf(sv, sc, corr[kb + i]);
+                        }
+                        if (pair_io) {
+#pragma unroll
+                            for (int i = 0; i < 16; i += 2)
+                                if (kb + i < K) __stcs(reinterpret_cast<float2*>(orow + kb + i), make_float2(res[i], res[i + 1]));
+                        } else {
+#pragma unroll
+                            for (int i = 0; i < 16; ++i)
+                                if (kb + i < K) __stcs(orow + kb + i, res[i]);
                         }
                     }
                 }
