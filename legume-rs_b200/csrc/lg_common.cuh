@@ -21,6 +21,10 @@ struct lg_ctx {
     // pinned staging for small host<->device scalars
     void* pinned = nullptr;
     size_t pinned_bytes = 0;
+    // pinned ring for host-side index narrowing in lg_csc_upload (allocated on first use)
+    void* ring = nullptr;
+    size_t ring_slots = 0;
+    std::vector<cudaEvent_t> ring_ev;
 };
 
 struct lg_csc {

@@ -1,4 +1,10 @@
 // lg_ctx.cu — context lifecycle and the device-resident CSC container (the data feed).
+#include <immintrin.h>
+
+#include <atomic>
+#include <cstdlib>
+#include <thread>
+
 #include "lg_common.cuh"
 
 extern "C" const char* lg_version(void) { return "legume-b200 0.1.0 (sm_100a)"; }
@@ -52,6 +58,8 @@ extern "C" int lg_ctx_destroy(lg_ctx* c) {
     cudaStreamSynchronize(c->stream);
     if (c->own_stream) cudaStreamDestroy(c->stream);
     if (c->pinned) cudaFreeHost(c->pinned);
+    if (c->ring) cudaFreeHost(c->ring);
+    for (auto e : c->ring_ev) cudaEventDestroy(e);
     delete c;
     return LG_OK;
 }
@@ -111,6 +119,197 @@ __global__ void k_widen_indices(const uint32_t* __restrict__ src, uint64_t* __re
     for (; i < n; i += stride) dst[i] = src[i];
 }
 
+// ---- host-side narrowing ------------------------------------------------------------------------
+// The reference hands out u64 row indices (csc_column_arrays, data-beans/src/sparse_io/traits.rs:98-100); on the wire
+// they are two thirds of the upload.  Worker threads narrow them to u32 into a pinned ring, chunk by chunk, and queue
+// the copies themselves, so the PCIe link carries 8 instead of 12 bytes per non-zero while the value chunks (which
+// need no CPU work) keep it busy.  LG_UPLOAD_THREADS=0 selects the device-side narrowing of wide copies instead.
+namespace {
+constexpr uint64_t UP_CHUNK = 2ull << 20;  // indices per ring slot (8 MiB of u32)
+
+__attribute__((target("avx2"))) void narrow_chunk_avx2(const uint64_t* s, uint32_t* d, uint64_t n, uint64_t* or_all,
+                                                       uint32_t* max_lo) {
+    const __m256i pick = _mm256_setr_epi32(0, 2, 4, 6, 0, 2, 4, 6);
+    __m256i acc = _mm256_setzero_si256(), mx = _mm256_setzero_si256();
+    uint64_t i = 0;
+    const bool aligned = (reinterpret_cast<uintptr_t>(d) & 31) == 0;
+    for (; i + 8 <= n; i += 8) {
+        const __m256i a = _mm256_loadu_si256(reinterpret_cast<const __m256i*>(s + i));
+        const __m256i b = _mm256_loadu_si256(reinterpret_cast<const __m256i*>(s + i + 4));
+        acc = _mm256_or_si256(acc, _mm256_or_si256(a, b));
+        const __m256i pa = _mm256_permutevar8x32_epi32(a, pick), pb = _mm256_permutevar8x32_epi32(b, pick);
+        const __m256i v = _mm256_blend_epi32(pa, pb, 0xF0);
+        mx = _mm256_max_epu32(mx, v);
+        if (aligned) _mm256_stream_si256(reinterpret_cast<__m256i*>(d + i), v);
+        else _mm256_storeu_si256(reinterpret_cast<__m256i*>(d + i), v);
+    }
+    alignas(32) uint64_t a4[4];
+    alignas(32) uint32_t m8[8];
+    _mm256_store_si256(reinterpret_cast<__m256i*>(a4), acc);
+    _mm256_store_si256(reinterpret_cast<__m256i*>(m8), mx);
+    uint64_t o = a4[0] | a4[1] | a4[2] | a4[3];
+    uint32_t m = 0;
+    for (int k = 0; k < 8; ++k) m = m8[k] > m ? m8[k] : m;
+    for (; i < n; ++i) {
+        o |= s[i];
+        const uint32_t v = (uint32_t)s[i];
+        m = v > m ? v : m;
+        d[i] = v;
+    }
+    _mm_sfence();
+    *or_all |= o;
+    *max_lo = m > *max_lo ? m : *max_lo;
+}
+void narrow_chunk_plain(const uint64_t* s, uint32_t* d, uint64_t n, uint64_t* or_all, uint32_t* max_lo) {
+    uint64_t o = 0;
+    uint32_t m = 0;
+    for (uint64_t i = 0; i < n; ++i) {
+        o |= s[i];
+        const uint32_t v = (uint32_t)s[i];
+        m = v > m ? v : m;
+        d[i] = v;
+    }
+    *or_all |= o;
+    *max_lo = m > *max_lo ? m : *max_lo;
+}
+
+int upload_threads() {
+    if (const char* e = getenv("LG_UPLOAD_THREADS")) return atoi(e);
+    unsigned hc = std::thread::hardware_concurrency();
+    if (hc < 4) return 0;  // too few cores to outrun the link: narrow on the device
+    return (int)(hc > 16 ? 16 : hc);
+}
+
+// returns a CUDA error (cudaSuccess when every chunk was queued); *bad = 1 when an index was out of range.
+// Chunks are claimed from both ends: the workers take them from the front and narrow on the host; the calling thread
+// takes them from the back and sends them wide (12 bytes per non-zero) through two device staging buffers, but only
+// while at most two of its chunks are in flight — the stream is a FIFO, so when the workers keep the link busy the
+// wide chunks complete slowly and few are sent, and when the host cores cannot keep up the wide share grows.
+cudaError_t upload_narrow_on_host(lg_ctx* ctx, const uint64_t* h_idx, const float* h_val, uint64_t nnz, uint64_t nrows,
+                                  uint32_t* d_idx, float* d_val, int nthreads, int* bad) {
+    const uint64_t nchunks = (nnz + UP_CHUNK - 1) / UP_CHUNK;
+    if ((uint64_t)nthreads > nchunks) nthreads = (int)nchunks;
+    const size_t want_slots = (size_t)2 * nthreads;
+    if (ctx->ring_slots < want_slots) {
+        if (ctx->ring) cudaFreeHost(ctx->ring);
+        ctx->ring = nullptr;
+        ctx->ring_slots = 0;
+        cudaError_t e = cudaHostAlloc(&ctx->ring, want_slots * UP_CHUNK * sizeof(uint32_t), cudaHostAllocDefault);
+        if (e != cudaSuccess) return e;
+        ctx->ring_slots = want_slots;
+        while (ctx->ring_ev.size() < want_slots + 2) {
+            cudaEvent_t ev;
+            e = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
+            if (e != cudaSuccess) return e;
+            ctx->ring_ev.push_back(ev);
+        }
+    }
+    const size_t nslots = ctx->ring_slots;
+    uint32_t* ring = static_cast<uint32_t*>(ctx->ring);
+    std::vector<std::atomic<int>> queued(nchunks);
+    for (auto& q : queued) q.store(0, std::memory_order_relaxed);
+    // claim word: low 32 bits = chunks taken from the front, high 32 bits = chunks taken from the back
+    std::atomic<uint64_t> claim{0};
+    auto take = [&](bool front, uint64_t* idx) {
+        uint64_t c = claim.load();
+        for (;;) {
+            const uint64_t f = c & 0xFFFFFFFFull, b = c >> 32;
+            if (f + b >= nchunks) return false;
+            if (claim.compare_exchange_weak(c, front ? c + 1 : c + (1ull << 32))) {
+                *idx = front ? f : nchunks - 1 - b;
+                return true;
+            }
+        }
+    };
+    std::atomic<int> first_err{(int)cudaSuccess};
+    auto note = [&](cudaError_t e) {
+        if (e != cudaSuccess) {
+            int exp = (int)cudaSuccess;
+            first_err.compare_exchange_strong(exp, (int)e);
+        }
+    };
+    std::atomic<uint64_t> or_all{0};
+    std::atomic<uint32_t> max_lo{0};
+    const bool avx2 = __builtin_cpu_supports("avx2");
+    auto worker = [&]() {
+        cudaSetDevice(ctx->device);
+        uint64_t my_or = 0;
+        uint32_t my_max = 0;
+        uint64_t i;
+        while (take(true, &i)) {
+            const uint64_t off = i * UP_CHUNK;
+            const uint64_t len = (nnz - off) < UP_CHUNK ? (nnz - off) : UP_CHUNK;
+            const size_t slot = (size_t)(i % nslots);
+            cudaError_t e = cudaSuccess;
+            if (i >= nslots) {  // the slot's previous copy (chunk i - nslots) must have left the host
+                while (!queued[i - nslots].load(std::memory_order_acquire)) std::this_thread::yield();
+                e = cudaEventSynchronize(ctx->ring_ev[slot]);
+            }
+            if (e == cudaSuccess)
+                e = cudaMemcpyAsync(d_val + off, h_val + off, len * sizeof(float), cudaMemcpyHostToDevice, ctx->stream);
+            uint32_t* dst = ring + slot * UP_CHUNK;
+            if (avx2) narrow_chunk_avx2(h_idx + off, dst, len, &my_or, &my_max);
+            else narrow_chunk_plain(h_idx + off, dst, len, &my_or, &my_max);
+            if (e == cudaSuccess)
+                e = cudaMemcpyAsync(d_idx + off, dst, len * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream);
+            if (e == cudaSuccess) e = cudaEventRecord(ctx->ring_ev[slot], ctx->stream);
+            note(e);
+            queued[i].store(1, std::memory_order_release);  // set even on error so nobody waits forever
+        }
+        or_all.fetch_or(my_or);
+        uint32_t cur = max_lo.load();
+        while (my_max > cur && !max_lo.compare_exchange_weak(cur, my_max)) {}
+    };
+    std::vector<std::thread> pool;
+    for (int t = 0; t < nthreads; ++t) pool.emplace_back(worker);
+    // the calling thread: wide chunks from the back
+    int h_flag = 0;
+    {
+        uint64_t* stage[2] = {nullptr, nullptr};
+        int* d_flag = nullptr;
+        cudaError_t e = cudaMallocAsync(&d_flag, sizeof(int), ctx->stream);
+        if (e == cudaSuccess) e = cudaMemsetAsync(d_flag, 0, sizeof(int), ctx->stream);
+        for (int k = 0; k < 2 && e == cudaSuccess; ++k) e = cudaMallocAsync(&stage[k], UP_CHUNK * sizeof(uint64_t), ctx->stream);
+        note(e);
+        uint64_t i, nwide = 0;
+        const bool wide_ok = getenv("LG_UPLOAD_NO_WIDE") == nullptr;
+        while (e == cudaSuccess && wide_ok) {
+            if (nwide >= 2) e = cudaEventSynchronize(ctx->ring_ev[nslots + (nwide & 1)]);
+            if (e != cudaSuccess || !take(false, &i)) break;
+            const uint64_t off = i * UP_CHUNK;
+            const uint64_t len = (nnz - off) < UP_CHUNK ? (nnz - off) : UP_CHUNK;
+            uint64_t* sbuf = stage[nwide & 1];
+            e = cudaMemcpyAsync(d_val + off, h_val + off, len * sizeof(float), cudaMemcpyHostToDevice, ctx->stream);
+            if (e == cudaSuccess)
+                e = cudaMemcpyAsync(sbuf, h_idx + off, len * sizeof(uint64_t), cudaMemcpyHostToDevice, ctx->stream);
+            if (e == cudaSuccess) {
+                k_narrow_indices<<<(unsigned)((len + 1023) / 1024), 256, 0, ctx->stream>>>(sbuf, d_idx + off, len, nrows, nrows,
+                                                                                            nullptr, d_flag);
+                ctx->launches++;
+                e = cudaGetLastError();
+            }
+            if (e == cudaSuccess) e = cudaEventRecord(ctx->ring_ev[nslots + (nwide & 1)], ctx->stream);
+            ++nwide;
+        }
+        note(e);
+        for (auto& t : pool) t.join();
+        if (d_flag) {
+            note(cudaMemcpyAsync(&h_flag, d_flag, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+            note(cudaStreamSynchronize(ctx->stream));
+            cudaFreeAsync(d_flag, ctx->stream);
+        }
+        for (int k = 0; k < 2; ++k)
+            if (stage[k]) cudaFreeAsync(stage[k], ctx->stream);
+        if (getenv("LG_UPLOAD_TRACE"))
+            fprintf(stderr, "[lg_csc_upload] %llu chunks: %llu narrowed on %d host threads, %llu sent wide\n",
+                    (unsigned long long)nchunks, (unsigned long long)(nchunks - nwide), nthreads,
+                    (unsigned long long)nwide);
+    }
+    *bad = (h_flag != 0 || (or_all.load() >> 32) != 0 || (uint64_t)max_lo.load() >= nrows) ? 1 : 0;
+    return (cudaError_t)first_err.load();
+}
+}  // namespace
+
 extern "C" int lg_csc_upload(lg_ctx* ctx, const uint64_t* indptr, const uint64_t* indices, const float* data,
                              uint64_t nrows, uint64_t col_lo, uint64_t col_hi, const uint32_t* row_remap,
                              lg_csc** out) {
@@ -160,7 +359,16 @@ extern "C" int lg_csc_upload(lg_ctx* ctx, const uint64_t* indptr, const uint64_t
         UP_CUDA(cudaGetLastError());
         UP_CUDA(cudaFreeAsync(tmp, st));
     }
-    if (nnz) {
+    const int up_threads = upload_threads();
+    if (nnz >= 4 * UP_CHUNK && !row_remap && up_threads > 0) {  // small blocks: not worth the threads
+        int bad = 0;
+        UP_CUDA(upload_narrow_on_host(ctx, indices + base, data + base, nnz, nrows, m->indices, m->values, up_threads, &bad));
+        UP_CUDA(cudaStreamSynchronize(st));
+        if (bad) {
+            ctx->err = "lg_csc_upload: row index out of range";
+            return fail(LG_ERR_INVALID);
+        }
+    } else if (nnz) {
         UP_CUDA(cudaMemcpyAsync(m->values, data + base, nnz * sizeof(float), cudaMemcpyHostToDevice, st));
         const uint32_t* d_remap = nullptr;
         uint32_t* remap_buf = nullptr;

@@ -49,6 +49,33 @@ def test_csc_upload_round_trip_and_range_check(lg, ctx):
         lg.CscBlock.upload(ctx, ip, bad, v, 300)
 
 
+@pytest.mark.parametrize("mode", ["default", "host_only", "device_only"])
+def test_csc_upload_large_block_host_narrowing(lg, ctx, mode, monkeypatch):
+    """blocks of >= 8 Mi non-zeros are narrowed u64 -> u32 by host threads into a pinned ring (with a wide share sent
+    through the device narrowing when the cores cannot keep up); every mix must give the same device arrays"""
+    if mode == "host_only":
+        monkeypatch.setenv("LG_UPLOAD_NO_WIDE", "1")
+        monkeypatch.setenv("LG_UPLOAD_THREADS", "3")
+    elif mode == "device_only":
+        monkeypatch.setenv("LG_UPLOAD_THREADS", "0")
+    rng = np.random.default_rng(5)
+    D, N, per = 30000, 9000, 1000
+    nnz = N * per + 5  # ragged last chunk
+    ip = np.minimum(np.arange(N + 1, dtype=np.uint64) * per, nnz).astype(np.uint64)
+    ip[-1] = nnz
+    ix = rng.integers(0, D, nnz, dtype=np.uint64)
+    v = rng.integers(1, 5, nnz).astype(np.float32)
+    blk = lg.CscBlock.upload(ctx, ip, ix, v, D)
+    ip2, ix2, v2 = blk.download()
+    blk.free()
+    assert np.array_equal(ip, ip2) and np.array_equal(ix, ix2) and np.array_equal(v, v2)
+    for pos, val in ((7, D), (nnz - 2, D + 5), (nnz // 2, 1 << 40)):
+        bad = ix.copy()
+        bad[pos] = val
+        with pytest.raises(lg.LegumeError):
+            lg.CscBlock.upload(ctx, ip, bad, v, D)
+
+
 def test_sim_matches_cpu_twin(lg, ctx):
     from legume_b200 import sim
     tabs = sim.make_tables(700, ntopic=4, nbatch=2, depth=400, seed=11)

@@ -19,17 +19,27 @@ basis = torch.from_numpy(np.random.default_rng(0).standard_normal((D, K)).astype
 batch = torch.zeros(N, dtype=torch.int32, device="cuda")
 def now():
     torch.cuda.synchronize(); return time.perf_counter()
-res = []
-for it in range(4):
-    t0 = now()
-    h = C.c_void_p()
-    ctx.check(lib.lg_csc_upload(ctx.h, h_ip.data_ptr(), h_ix.data_ptr(), h_v.data_ptr(), D, 0, N, None, C.byref(h)))
-    t1 = now()
-    b = lg.CscBlock(ctx, h)
-    o = hp.run(b, basis, batch, 1, kk)
-    t2 = now()
-    b.free()
-    t3 = now()
-    res.append({"upload_ms": 1e3 * (t1 - t0), "run_ms": 1e3 * (t2 - t1), "free_ms": 1e3 * (t3 - t2)})
+res = {}
+modes = [("device_narrow", {"LG_UPLOAD_THREADS": "0"}), ("default", {}), ("host4", {"LG_UPLOAD_THREADS": "4"}),
+         ("host8", {"LG_UPLOAD_THREADS": "8"}), ("host16", {"LG_UPLOAD_THREADS": "16"}), ("host32", {"LG_UPLOAD_THREADS": "32"}),
+         ("host16_nowide", {"LG_UPLOAD_THREADS": "16", "LG_UPLOAD_NO_WIDE": "1"})]
+os.environ["LG_UPLOAD_TRACE"] = "1"
+for name, env in modes:
+    for k in ("LG_UPLOAD_THREADS", "LG_UPLOAD_NO_WIDE"):
+        os.environ.pop(k, None)
+    os.environ.update(env)
+    rows = []
+    for it in range(3):
+        t0 = now()
+        h = C.c_void_p()
+        ctx.check(lib.lg_csc_upload(ctx.h, h_ip.data_ptr(), h_ix.data_ptr(), h_v.data_ptr(), D, 0, N, None, C.byref(h)))
+        t1 = now()
+        b = lg.CscBlock(ctx, h)
+        o = hp.run(b, basis, batch, 1, kk)
+        t2 = now()
+        b.free()
+        t3 = now()
+        rows.append({"upload_ms": 1e3 * (t1 - t0), "run_ms": 1e3 * (t2 - t1), "free_ms": 1e3 * (t3 - t2)})
+    res[name] = rows
 bytes_up = h_ip.numel() * 8 + h_ix.numel() * 8 + h_v.numel() * 4
-print(json.dumps({"cells": N, "h2d_bytes": bytes_up, "iters": res, "upload_GBps_last": bytes_up / res[-1]["upload_ms"] / 1e6}))
+print(json.dumps({"cells": N, "host_bytes": bytes_up, "host_cores": os.cpu_count(), "modes": res}))
