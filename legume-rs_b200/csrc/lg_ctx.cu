@@ -2,6 +2,7 @@
 #include <immintrin.h>
 
 #include <atomic>
+#include <cmath>
 #include <cstdlib>
 #include <thread>
 
@@ -108,6 +109,32 @@ __global__ void k_narrow_indices(const uint64_t* __restrict__ src, uint32_t* __r
         dst[i] = o;
     }
 }
+struct LgUpPatch {
+    uint32_t pos;
+    float val;
+};
+__global__ void k_expand_u8(const uint8_t* __restrict__ src, float* __restrict__ dst, uint64_t n,
+                            const LgUpPatch* __restrict__ patch, uint32_t npatch) {
+    // n4 full groups of four bytes, then the ragged tail; byte 255 marks a patched position (not written here)
+    const uint64_t n4 = n >> 2;
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t g = i; g < n4; g += stride) {
+        const uint32_t w = reinterpret_cast<const uint32_t*>(src)[g];
+        const uint32_t b0 = w & 255u, b1 = (w >> 8) & 255u, b2 = (w >> 16) & 255u, b3 = w >> 24;
+        if (b0 != 255u && b1 != 255u && b2 != 255u && b3 != 255u) {
+            reinterpret_cast<float4*>(dst)[g] = make_float4((float)b0, (float)b1, (float)b2, (float)b3);
+        } else {
+            if (b0 != 255u) dst[4 * g] = (float)b0;
+            if (b1 != 255u) dst[4 * g + 1] = (float)b1;
+            if (b2 != 255u) dst[4 * g + 2] = (float)b2;
+            if (b3 != 255u) dst[4 * g + 3] = (float)b3;
+        }
+    }
+    for (uint64_t t = (n4 << 2) + i; t < n; t += stride)
+        if (src[t] != 255) dst[t] = (float)src[t];
+    for (uint64_t t = i; t < npatch; t += stride) dst[patch[t].pos] = patch[t].val;
+}
 __global__ void k_rebase_indptr(const uint64_t* __restrict__ src, uint64_t* __restrict__ dst, uint64_t n,
                                 uint64_t base) {
     uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -125,7 +152,9 @@ __global__ void k_widen_indices(const uint32_t* __restrict__ src, uint64_t* __re
 // the copies themselves, so the PCIe link carries 8 instead of 12 bytes per non-zero while the value chunks (which
 // need no CPU work) keep it busy.  LG_UPLOAD_THREADS=0 selects the device-side narrowing of wide copies instead.
 namespace {
-constexpr uint64_t UP_CHUNK = 2ull << 20;  // indices per ring slot (8 MiB of u32)
+constexpr uint64_t UP_CHUNK = 2ull << 20;          // non-zeros per ring slot
+constexpr uint64_t UP_PATCH_BYTES = 8ull << 16;     // UP_PATCH_CAP (position, f32) pairs
+constexpr uint64_t UP_SLOT_BYTES = UP_CHUNK * 5 + UP_PATCH_BYTES;   // u32 indices, u8 values, patch list
 
 __attribute__((target("avx2"))) void narrow_chunk_avx2(const uint64_t* s, uint32_t* d, uint64_t n, uint64_t* or_all,
                                                        uint32_t* max_lo) {
@@ -173,6 +202,60 @@ void narrow_chunk_plain(const uint64_t* s, uint32_t* d, uint64_t n, uint64_t* or
     *max_lo = m > *max_lo ? m : *max_lo;
 }
 
+// count data: values that are whole numbers in 0..254 travel as one byte each (exactly); anything else is marked 255
+// and goes into the chunk's patch list as (position, f32).  Returns the number of patches, or -1 when the list is full
+// (the chunk then goes up as raw f32).
+struct UpPatch {
+    uint32_t pos;
+    float val;
+};
+constexpr int64_t UP_PATCH_CAP = 1 << 16;
+
+inline int64_t pack_scalar(const float* s, uint8_t* d, uint64_t lo, uint64_t hi, UpPatch* patch, int64_t np) {
+    for (uint64_t i = lo; i < hi; ++i) {
+        const float f = s[i];
+        const int q = (f >= 0.0f && f <= 254.0f) ? (int)f : -1;
+        if (q < 0 || (float)q != f || std::signbit(f)) {
+            if (np >= UP_PATCH_CAP) return -1;
+            patch[np++] = UpPatch{(uint32_t)i, f};
+            d[i] = 255;
+        } else {
+            d[i] = (uint8_t)q;
+        }
+    }
+    return np;
+}
+__attribute__((target("avx2"))) int64_t pack_values_avx2(const float* s, uint8_t* d, uint64_t n, UpPatch* patch) {
+    const __m256i hi = _mm256_set1_epi32(~255), esc = _mm256_set1_epi32(255);
+    const __m256i sign = _mm256_set1_epi32((int)0x80000000u);
+    const __m256i fix = _mm256_setr_epi32(0, 4, 1, 5, 2, 6, 3, 7);
+    int64_t np = 0;
+    uint64_t i = 0;
+    for (; i + 32 <= n; i += 32) {
+        __m256i q[4];
+        __m256i bad = _mm256_setzero_si256();
+        for (int k = 0; k < 4; ++k) {
+            const __m256 f = _mm256_loadu_ps(s + i + 8 * k);
+            q[k] = _mm256_cvttps_epi32(f);
+            const __m256 back = _mm256_cvtepi32_ps(q[k]);
+            bad = _mm256_or_si256(bad, _mm256_castps_si256(_mm256_cmp_ps(f, back, _CMP_NEQ_UQ)));
+            bad = _mm256_or_si256(bad, _mm256_and_si256(q[k], hi));
+            bad = _mm256_or_si256(bad, _mm256_cmpeq_epi32(q[k], esc));
+            bad = _mm256_or_si256(bad, _mm256_and_si256(_mm256_castps_si256(f), sign));  // -0.0 would lose its sign
+        }
+        if (!_mm256_testz_si256(bad, bad)) {  // rare: redo this group one value at a time
+            np = pack_scalar(s, d, i, i + 32, patch, np);
+            if (np < 0) return -1;
+            continue;
+        }
+        const __m256i w0 = _mm256_packus_epi32(q[0], q[1]), w1 = _mm256_packus_epi32(q[2], q[3]);
+        const __m256i b = _mm256_permutevar8x32_epi32(_mm256_packus_epi16(w0, w1), fix);
+        _mm256_storeu_si256(reinterpret_cast<__m256i*>(d + i), b);
+    }
+    return pack_scalar(s, d, i, n, patch, np);
+}
+int64_t pack_values_plain(const float* s, uint8_t* d, uint64_t n, UpPatch* patch) { return pack_scalar(s, d, 0, n, patch, 0); }
+
 int upload_threads() {
     if (const char* e = getenv("LG_UPLOAD_THREADS")) return atoi(e);
     unsigned hc = std::thread::hardware_concurrency();
@@ -194,7 +277,7 @@ cudaError_t upload_narrow_on_host(lg_ctx* ctx, const uint64_t* h_idx, const floa
         if (ctx->ring) cudaFreeHost(ctx->ring);
         ctx->ring = nullptr;
         ctx->ring_slots = 0;
-        cudaError_t e = cudaHostAlloc(&ctx->ring, want_slots * UP_CHUNK * sizeof(uint32_t), cudaHostAllocDefault);
+        cudaError_t e = cudaHostAlloc(&ctx->ring, want_slots * UP_SLOT_BYTES, cudaHostAllocDefault);
         if (e != cudaSuccess) return e;
         ctx->ring_slots = want_slots;
         while (ctx->ring_ev.size() < want_slots + 2) {
@@ -205,7 +288,15 @@ cudaError_t upload_narrow_on_host(lg_ctx* ctx, const uint64_t* h_idx, const floa
         }
     }
     const size_t nslots = ctx->ring_slots;
-    uint32_t* ring = static_cast<uint32_t*>(ctx->ring);
+    uint8_t* ring = static_cast<uint8_t*>(ctx->ring);
+    // device twin of the byte-value part of the ring (stream order makes a slot safe to reuse)
+    uint8_t* d_bytes = nullptr;
+    const bool pack_ok = getenv("LG_UPLOAD_NO_PACK") == nullptr;
+    if (pack_ok) {
+        cudaError_t e = cudaMallocAsync(&d_bytes, nslots * (UP_CHUNK + UP_PATCH_BYTES), ctx->stream);
+        if (e != cudaSuccess) return e;
+    }
+    std::atomic<uint64_t> extra_launches{0}, packed_chunks{0};
     std::vector<std::atomic<int>> queued(nchunks);
     for (auto& q : queued) q.store(0, std::memory_order_relaxed);
     // claim word: low 32 bits = chunks taken from the front, high 32 bits = chunks taken from the back
@@ -233,7 +324,7 @@ cudaError_t upload_narrow_on_host(lg_ctx* ctx, const uint64_t* h_idx, const floa
     const bool avx2 = __builtin_cpu_supports("avx2");
     auto worker = [&]() {
         cudaSetDevice(ctx->device);
-        uint64_t my_or = 0;
+        uint64_t my_or = 0, my_launches = 0, my_packed = 0;
         uint32_t my_max = 0;
         uint64_t i;
         while (take(true, &i)) {
@@ -245,9 +336,28 @@ cudaError_t upload_narrow_on_host(lg_ctx* ctx, const uint64_t* h_idx, const floa
                 while (!queued[i - nslots].load(std::memory_order_acquire)) std::this_thread::yield();
                 e = cudaEventSynchronize(ctx->ring_ev[slot]);
             }
-            if (e == cudaSuccess)
-                e = cudaMemcpyAsync(d_val + off, h_val + off, len * sizeof(float), cudaMemcpyHostToDevice, ctx->stream);
-            uint32_t* dst = ring + slot * UP_CHUNK;
+            uint32_t* dst = reinterpret_cast<uint32_t*>(ring + slot * UP_SLOT_BYTES);
+            uint8_t* vdst = ring + slot * UP_SLOT_BYTES + UP_CHUNK * sizeof(uint32_t);
+            UpPatch* pdst = reinterpret_cast<UpPatch*>(vdst + UP_CHUNK);
+            const int64_t npatch = !pack_ok ? -1 : avx2 ? pack_values_avx2(h_val + off, vdst, len, pdst)
+                                                        : pack_values_plain(h_val + off, vdst, len, pdst);
+            if (e == cudaSuccess) {
+                if (npatch >= 0) {
+                    uint8_t* dv = d_bytes + slot * (UP_CHUNK + UP_PATCH_BYTES);
+                    e = cudaMemcpyAsync(dv, vdst, len, cudaMemcpyHostToDevice, ctx->stream);
+                    if (e == cudaSuccess && npatch)
+                        e = cudaMemcpyAsync(dv + UP_CHUNK, pdst, (size_t)npatch * sizeof(UpPatch), cudaMemcpyHostToDevice, ctx->stream);
+                    if (e == cudaSuccess) {
+                        k_expand_u8<<<(unsigned)((len / 4 + 1023) / 1024 + 1), 256, 0, ctx->stream>>>(
+                            dv, d_val + off, len, reinterpret_cast<const LgUpPatch*>(dv + UP_CHUNK), (uint32_t)npatch);
+                        e = cudaGetLastError();
+                        ++my_launches;
+                        ++my_packed;
+                    }
+                } else {
+                    e = cudaMemcpyAsync(d_val + off, h_val + off, len * sizeof(float), cudaMemcpyHostToDevice, ctx->stream);
+                }
+            }
             if (avx2) narrow_chunk_avx2(h_idx + off, dst, len, &my_or, &my_max);
             else narrow_chunk_plain(h_idx + off, dst, len, &my_or, &my_max);
             if (e == cudaSuccess)
@@ -257,6 +367,8 @@ cudaError_t upload_narrow_on_host(lg_ctx* ctx, const uint64_t* h_idx, const floa
             queued[i].store(1, std::memory_order_release);  // set even on error so nobody waits forever
         }
         or_all.fetch_or(my_or);
+        extra_launches.fetch_add(my_launches);
+        packed_chunks.fetch_add(my_packed);
         uint32_t cur = max_lo.load();
         while (my_max > cur && !max_lo.compare_exchange_weak(cur, my_max)) {}
     };
@@ -293,6 +405,8 @@ cudaError_t upload_narrow_on_host(lg_ctx* ctx, const uint64_t* h_idx, const floa
         }
         note(e);
         for (auto& t : pool) t.join();
+        ctx->launches += extra_launches.load();
+        if (d_bytes) cudaFreeAsync(d_bytes, ctx->stream);
         if (d_flag) {
             note(cudaMemcpyAsync(&h_flag, d_flag, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
             note(cudaStreamSynchronize(ctx->stream));
@@ -301,9 +415,9 @@ cudaError_t upload_narrow_on_host(lg_ctx* ctx, const uint64_t* h_idx, const floa
         for (int k = 0; k < 2; ++k)
             if (stage[k]) cudaFreeAsync(stage[k], ctx->stream);
         if (getenv("LG_UPLOAD_TRACE"))
-            fprintf(stderr, "[lg_csc_upload] %llu chunks: %llu narrowed on %d host threads, %llu sent wide\n",
+            fprintf(stderr, "[lg_csc_upload] %llu chunks: %llu narrowed on %d host threads (%llu with byte values), %llu sent wide\n",
                     (unsigned long long)nchunks, (unsigned long long)(nchunks - nwide), nthreads,
-                    (unsigned long long)nwide);
+                    (unsigned long long)packed_chunks.load(), (unsigned long long)nwide);
     }
     *bad = (h_flag != 0 || (or_all.load() >> 32) != 0 || (uint64_t)max_lo.load() >= nrows) ? 1 : 0;
     return (cudaError_t)first_err.load();

@@ -49,13 +49,16 @@ def test_csc_upload_round_trip_and_range_check(lg, ctx):
         lg.CscBlock.upload(ctx, ip, bad, v, 300)
 
 
-@pytest.mark.parametrize("mode", ["default", "host_only", "device_only"])
+@pytest.mark.parametrize("mode", ["default", "host_only", "host_no_pack", "device_only"])
 def test_csc_upload_large_block_host_narrowing(lg, ctx, mode, monkeypatch):
-    """blocks of >= 8 Mi non-zeros are narrowed u64 -> u32 by host threads into a pinned ring (with a wide share sent
-    through the device narrowing when the cores cannot keep up); every mix must give the same device arrays"""
+    """blocks of >= 8 Mi non-zeros are narrowed u64 -> u32 by host threads into a pinned ring, count values packed to
+    bytes with a patch list (with a wide share sent through the device narrowing when the cores cannot keep up);
+    every mix must give the same device arrays, bit for bit"""
     if mode == "host_only":
         monkeypatch.setenv("LG_UPLOAD_NO_WIDE", "1")
         monkeypatch.setenv("LG_UPLOAD_THREADS", "3")
+    elif mode == "host_no_pack":
+        monkeypatch.setenv("LG_UPLOAD_NO_PACK", "1")
     elif mode == "device_only":
         monkeypatch.setenv("LG_UPLOAD_THREADS", "0")
     rng = np.random.default_rng(5)
@@ -64,11 +67,15 @@ def test_csc_upload_large_block_host_narrowing(lg, ctx, mode, monkeypatch):
     ip = np.minimum(np.arange(N + 1, dtype=np.uint64) * per, nnz).astype(np.uint64)
     ip[-1] = nnz
     ix = rng.integers(0, D, nnz, dtype=np.uint64)
-    v = rng.integers(1, 5, nnz).astype(np.float32)
+    v = rng.integers(0, 256, nnz).astype(np.float32)  # whole numbers 0..254 travel as bytes ...
+    v[3_000_000:3_000_010] = 0.5                      # ... anything else (255 too) through the chunk's patch list ...
+    v[5_000_001] = 70000.0
+    v[(2 << 20) * 3 - 1] = -0.0
+    v[6_500_000:6_600_000] = 1000.5                   # ... and a chunk with more than 65536 of those as raw f32
     blk = lg.CscBlock.upload(ctx, ip, ix, v, D)
     ip2, ix2, v2 = blk.download()
     blk.free()
-    assert np.array_equal(ip, ip2) and np.array_equal(ix, ix2) and np.array_equal(v, v2)
+    assert np.array_equal(ip, ip2) and np.array_equal(ix, ix2) and v.tobytes() == v2.tobytes()
     for pos, val in ((7, D), (nnz - 2, D + 5), (nnz // 2, 1 << 40)):
         bad = ix.copy()
         bad[pos] = val

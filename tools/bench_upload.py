@@ -22,10 +22,11 @@ def now():
 res = {}
 modes = [("device_narrow", {"LG_UPLOAD_THREADS": "0"}), ("default", {}), ("host4", {"LG_UPLOAD_THREADS": "4"}),
          ("host8", {"LG_UPLOAD_THREADS": "8"}), ("host16", {"LG_UPLOAD_THREADS": "16"}), ("host32", {"LG_UPLOAD_THREADS": "32"}),
-         ("host16_nowide", {"LG_UPLOAD_THREADS": "16", "LG_UPLOAD_NO_WIDE": "1"})]
+         ("host16_nowide", {"LG_UPLOAD_THREADS": "16", "LG_UPLOAD_NO_WIDE": "1"}),
+         ("host16_nopack", {"LG_UPLOAD_THREADS": "16", "LG_UPLOAD_NO_PACK": "1"})]
 os.environ["LG_UPLOAD_TRACE"] = "1"
 for name, env in modes:
-    for k in ("LG_UPLOAD_THREADS", "LG_UPLOAD_NO_WIDE"):
+    for k in ("LG_UPLOAD_THREADS", "LG_UPLOAD_NO_WIDE", "LG_UPLOAD_NO_PACK"):
         os.environ.pop(k, None)
     os.environ.update(env)
     rows = []
