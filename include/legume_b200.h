@@ -281,6 +281,23 @@ int lg_sim_poisson_csc(lg_ctx* ctx, uint64_t seed, uint64_t D, uint64_t col_lo, 
                        uint32_t nbatch, const float* lam, const float* p0, const uint8_t* npiece,
                        lg_csc** out);
 
+/* ---- the nnz streams either side of the path ---------------------------------
+ * lg_row_stats replaces SparseRunningStatistics::add_csc over a block (matrix-util/src/sparse_stat.rs:64-108) as
+ * driven by streaming_sparse_running_stats (data-beans-alg/src/sparse_streaming.rs:23-60; callers hvg.rs:389,
+ * gene_weighting.rs:113): per gene, over the FINITE stored values v: npos = #(v > 0), s1 = sum v, s2 = sum v*v.
+ * Outputs are f64 (D each, overwritten): for count data they are exact integers, so per-shard results add up to
+ * the same totals on any number of GPUs; the caller narrows to the reference's f32 after merging (merge = add,
+ * sparse_stat.rs:183-196).  ncols_processed is the block's column count. */
+int lg_row_stats(lg_ctx* ctx, const lg_csc* m, double* out_npos, double* out_s1, double* out_s2);
+/* lg_nystrom_project replaces nystrom_proj_visitor over a block (senna/src/svd/fit.rs:433-466):
+ *   x = y / max(||y||_2, 1e-8) * column_sum_norm;  x /= delta[row, pb(j)] * (sum x / sum delta) where delta > 0
+ *   (adjust_by_poisson_ratio, matrix-util/src/dmatrix_util.rs:226-244);  z = ln(1 + x), standardised over the cell's
+ *   stored entries (:791-824);  out[:, j] = sum_i z_i basis[i, :].
+ * basis_dk: D x K column-major (the reference's DMatrix); delta_dp: D x P column-major or NULL (then pb_of_cell is
+ * ignored); pb_of_cell: u32[N], values >= P leave the cell unadjusted; out: K x N column-major. */
+int lg_nystrom_project(lg_ctx* ctx, const lg_csc* m, const float* basis_dk, int K, const float* delta_dp,
+                       const uint32_t* pb_of_cell, uint32_t P, float column_sum_norm, float* out_proj_kn);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,418 @@
+// lg_next.cu — the nnz streams either side of the hot path:
+//   K10  per-gene running statistics   SparseRunningStatistics::add_csc  matrix-util/src/sparse_stat.rs:64-108,
+//                                       streaming_sparse_running_stats    data-beans-alg/src/sparse_streaming.rs:23-60
+//   K11  Nystrom re-projection          nystrom_proj_visitor              senna/src/svd/fit.rs:433-466
+#include <cub/cub.cuh>
+
+#include "lg_common.cuh"
+
+namespace {
+// 1 if every stored value is a non-negative whole number below 2^20 (same test as the collapse uses)
+__global__ void k_rs_all_integral(const float* __restrict__ v, uint64_t n, int* __restrict__ not_integral) {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    bool bad = false;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const float x = __ldg(v + i);
+        bad |= !(x >= 0.0f && x < 1048576.0f && x == truncf(x));
+    }
+    if (__any_sync(0xffffffffu, bad) && (threadIdx.x & 31) == 0) atomicOr(not_integral, 1);
+}
+}  // namespace
+
+// ---------------------------------------------------------------------------------------------
+// K10: one pass over the nnz stream for (npos, s1, s2) per gene.
+// Count data (every value a whole number in [0, 2^20), checked once per block and cached): a CTA owns a D-long
+// u32 accumulator in shared memory and packs the two statistics every non-zero touches into ONE native ATOMS.ADD:
+//   acc[g] += (1 << 23) | y          npos in the top 9 bits (<= 256 cells per chunk), s1 in the low 23
+// s2 = s1 + sum over y >= 2 of y (y - 1): only the few counts above one pay a second (global, replicated) atomic.
+// Every RS_CHUNK cells the CTA folds its accumulator into a private u64 slab with plain read-modify-writes; a
+// last kernel adds the slabs in a fixed order.  Integer arithmetic throughout: exact, order-free, identical for
+// any grid or GPU count.  Anything else (fractional / negative / non-finite values) takes the f64-atomic path.
+// ---------------------------------------------------------------------------------------------
+constexpr int RS_THREADS = 512;
+constexpr int RS_CHUNK = 256;          // cells per accumulator flush: npos <= 256 fits 9 bits
+constexpr uint32_t RS_S1_BITS = 23;    // per-chunk s1 < 2^23 is guaranteed for y < 2^15; larger counts bypass the packing
+constexpr uint32_t RS_Y_PACK_MAX = 1u << 15;
+constexpr int RS_REPL = 8;             // replicas of the global y(y-1) accumulator (spreads same-address atomics)
+
+template <bool VEC>
+__global__ void __launch_bounds__(RS_THREADS, 1) k_row_stats_int(const uint64_t* __restrict__ indptr,
+                                                                 const uint32_t* __restrict__ indices,
+                                                                 const float* __restrict__ values, uint64_t nnz_total,
+                                                                 uint64_t ncells, uint64_t D, uint32_t g0, uint32_t W,
+                                                                 unsigned long long* __restrict__ slab_npos,
+                                                                 unsigned long long* __restrict__ slab_s1,
+                                                                 unsigned long long* __restrict__ extra,
+                                                                 unsigned long long* __restrict__ next_chunk) {
+    extern __shared__ __align__(16) uint32_t acc[];  // W packed accumulators
+    __shared__ unsigned long long s_chunk;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = RS_THREADS / 32;
+    const uint64_t nchunks = (ncells + RS_CHUNK - 1) / RS_CHUNK;
+    unsigned long long* my_npos = slab_npos + (size_t)blockIdx.x * D + g0;
+    unsigned long long* my_s1 = slab_s1 + (size_t)blockIdx.x * D + g0;
+    unsigned long long* my_extra = extra + (size_t)(blockIdx.x % RS_REPL) * D + g0;
+    for (uint32_t g = threadIdx.x; g < W; g += RS_THREADS) acc[g] = 0;
+    auto one = [&](uint32_t g, float v) {
+        const uint32_t ge = g - g0;
+        if (ge >= W) return;
+        const uint32_t y = (uint32_t)v;
+        if (y == 0) return;  // a stored zero: finite, not positive, adds nothing
+        if (y < RS_Y_PACK_MAX) {
+            atomicAdd(&acc[ge], (1u << RS_S1_BITS) | y);
+        } else {  // a count too large for the packed field: straight to this CTA's slab
+            atomicAdd(&my_npos[ge], 1ull);
+            atomicAdd(&my_s1[ge], (unsigned long long)y);
+        }
+        if (y >= 2) atomicAdd(&my_extra[ge], (unsigned long long)y * (y - 1));
+    };
+    while (true) {
+        __syncthreads();
+        if (threadIdx.x == 0) s_chunk = atomicAdd(next_chunk, 1ull);
+        __syncthreads();
+        const uint64_t chunk = s_chunk;
+        if (chunk >= nchunks) break;
+        const uint64_t c0 = chunk * RS_CHUNK;
+        const uint64_t c1 = (c0 + RS_CHUNK) < ncells ? (c0 + RS_CHUNK) : ncells;
+        // the chunk's cells are consecutive columns: one contiguous nnz range, walked by all warps together
+        const uint64_t lo = indptr[c0], hi = indptr[c1];
+        if constexpr (VEC) {
+            constexpr int VU = 4;
+            const uint64_t hi4 = nnz_total & ~3ull;
+            for (uint64_t c = (lo & ~3ull) + 4ull * threadIdx.x; c < hi; c += 4ull * RS_THREADS * VU) {
+                uint4 gq[VU];
+                float4 vq[VU];
+#pragma unroll
+                for (int u = 0; u < VU; ++u) {
+                    const uint64_t cu = c + 4ull * RS_THREADS * u;
+                    gq[u] = make_uint4(0, 0, 0, 0);
+                    vq[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (cu < hi) {
+                        if (cu < hi4) {
+                            gq[u] = __ldg(reinterpret_cast<const uint4*>(indices + cu));
+                            vq[u] = __ldg(reinterpret_cast<const float4*>(values + cu));
+                        } else {  // the last, partial group of the whole array
+                            uint32_t gg[4] = {0, 0, 0, 0};
+                            float vv[4] = {0.f, 0.f, 0.f, 0.f};
+                            for (int e = 0; e < 4; ++e)
+                                if (cu + e < nnz_total) {
+                                    gg[e] = indices[cu + e];
+                                    vv[e] = values[cu + e];
+                                }
+                            gq[u] = make_uint4(gg[0], gg[1], gg[2], gg[3]);
+                            vq[u] = make_float4(vv[0], vv[1], vv[2], vv[3]);
+                        }
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < VU; ++u) {
+                    const uint64_t cu = c + 4ull * RS_THREADS * u;
+                    const uint32_t ge[4] = {gq[u].x, gq[u].y, gq[u].z, gq[u].w};
+                    const float ve[4] = {vq[u].x, vq[u].y, vq[u].z, vq[u].w};
+#pragma unroll
+                    for (int e = 0; e < 4; ++e)
+                        if (cu + e >= lo && cu + e < hi) one(ge[e], ve[e]);
+                }
+            }
+        } else {
+            for (uint64_t t = lo + threadIdx.x; t < hi; t += RS_THREADS) one(__ldg(indices + t), __ldg(values + t));
+        }
+        __syncthreads();
+        for (uint32_t g = threadIdx.x; g < W; g += RS_THREADS) {
+            const uint32_t v = acc[g];
+            if (v) {
+                my_npos[g] += v >> RS_S1_BITS;
+                my_s1[g] += v & ((1u << RS_S1_BITS) - 1u);
+                acc[g] = 0;
+            }
+        }
+    }
+    (void)lane;
+    (void)warp;
+    (void)nwarp;
+}
+
+__global__ void k_row_stats_finish(const unsigned long long* __restrict__ slab_npos,
+                                   const unsigned long long* __restrict__ slab_s1,
+                                   const unsigned long long* __restrict__ extra, uint64_t D, uint32_t nslab,
+                                   double* __restrict__ npos, double* __restrict__ s1, double* __restrict__ s2) {
+    const uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= D) return;
+    unsigned long long a = 0, b = 0, x = 0;
+    for (uint32_t s = 0; s < nslab; ++s) {
+        a += slab_npos[(size_t)s * D + g];
+        b += slab_s1[(size_t)s * D + g];
+    }
+    for (int r = 0; r < RS_REPL; ++r) x += extra[(size_t)r * D + g];
+    npos[g] = (double)a;
+    s1[g] = (double)b;
+    s2[g] = (double)(b + x);
+}
+
+// general values: f64 atomics on replicated accumulators (sums agree to ~1e-16 relative run to run; non-finite skipped)
+__global__ void __launch_bounds__(256) k_row_stats_f64(const uint32_t* __restrict__ indices, const float* __restrict__ values,
+                                                       uint64_t nnz, uint64_t D, double* __restrict__ rep) {
+    double* mine = rep + (size_t)(blockIdx.x % RS_REPL) * 3 * D;
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; t < nnz; t += stride) {
+        const float v = __ldg(values + t);
+        if (!isfinite(v)) continue;
+        const uint32_t g = __ldg(indices + t);
+        if (v > 0.0f) atomicAdd(&mine[g], 1.0);
+        atomicAdd(&mine[D + g], (double)v);
+        atomicAdd(&mine[2 * D + g], (double)v * (double)v);
+    }
+}
+__global__ void k_row_stats_f64_finish(const double* __restrict__ rep, uint64_t D, double* __restrict__ npos,
+                                       double* __restrict__ s1, double* __restrict__ s2) {
+    const uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= D) return;
+    double a = 0, b = 0, c = 0;
+    for (int r = 0; r < RS_REPL; ++r) {
+        a += rep[(size_t)r * 3 * D + g];
+        b += rep[(size_t)r * 3 * D + D + g];
+        c += rep[(size_t)r * 3 * D + 2 * D + g];
+    }
+    npos[g] = a;
+    s1[g] = b;
+    s2[g] = c;
+}
+
+extern "C" int lg_row_stats(lg_ctx* ctx, const lg_csc* m, double* out_npos, double* out_s1, double* out_s2) {
+    if (!ctx) return LG_ERR_INVALID;
+    LG_REQUIRE(ctx, m && out_npos && out_s1 && out_s2, "lg_row_stats: null argument");
+    cudaSetDevice(ctx->device);
+    const uint64_t D = m->nrows, N = m->ncols;
+    LgStage st(ctx);
+    double *d_npos, *d_s1, *d_s2;
+    LG_TRY(st.out(out_npos, D, &d_npos));
+    LG_TRY(st.out(out_s1, D, &d_s1));
+    LG_TRY(st.out(out_s2, D, &d_s2));
+    if (D == 0) return st.finish();
+    if (N == 0 || m->nnz == 0) {
+        LG_CUDA(ctx, cudaMemsetAsync(d_npos, 0, D * sizeof(double), ctx->stream));
+        LG_CUDA(ctx, cudaMemsetAsync(d_s1, 0, D * sizeof(double), ctx->stream));
+        LG_CUDA(ctx, cudaMemsetAsync(d_s2, 0, D * sizeof(double), ctx->stream));
+        return st.finish();
+    }
+    if (m->int_valued < 0) {
+        int* d_flag;
+        LG_TRY(st.scratch(1, &d_flag));
+        LG_CUDA(ctx, cudaMemsetAsync(d_flag, 0, sizeof(int), ctx->stream));
+        LG_LAUNCH(ctx, k_rs_all_integral, ctx->num_sms * 8, 256, 0, m->values, m->nnz, d_flag);
+        int* h_flag = static_cast<int*>(ctx->pinned);
+        LG_CUDA(ctx, cudaMemcpyAsync(h_flag, d_flag, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+        LG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        m->int_valued = (*h_flag == 0) ? 1 : 0;
+    }
+    if (m->int_valued == 1) {
+        const uint32_t nslab = (uint32_t)ctx->num_sms;
+        unsigned long long *d_slab_npos, *d_slab_s1, *d_extra, *d_next;
+        LG_TRY(st.scratch((size_t)nslab * D, &d_slab_npos));
+        LG_TRY(st.scratch((size_t)nslab * D, &d_slab_s1));
+        LG_TRY(st.scratch((size_t)RS_REPL * D, &d_extra));
+        LG_TRY(st.scratch(1, &d_next));
+        LG_CUDA(ctx, cudaMemsetAsync(d_slab_npos, 0, (size_t)nslab * D * 8, ctx->stream));
+        LG_CUDA(ctx, cudaMemsetAsync(d_slab_s1, 0, (size_t)nslab * D * 8, ctx->stream));
+        LG_CUDA(ctx, cudaMemsetAsync(d_extra, 0, (size_t)RS_REPL * D * 8, ctx->stream));
+        const uint32_t Wmax = (uint32_t)((ctx->smem_optin - 1024) / sizeof(uint32_t));
+        const bool vec = (((uintptr_t)m->indices | (uintptr_t)m->values) & 15) == 0;
+        for (uint64_t g0 = 0; g0 < D; g0 += Wmax) {  // one pass when the gene axis fits (D <= ~57k), else gene windows
+            const uint32_t W = (uint32_t)((D - g0) < Wmax ? (D - g0) : Wmax);
+            const size_t smem = (size_t)W * sizeof(uint32_t);
+            LG_CUDA(ctx, cudaMemsetAsync(d_next, 0, sizeof(unsigned long long), ctx->stream));
+            if (vec) {
+                LG_CUDA(ctx, cudaFuncSetAttribute(k_row_stats_int<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                LG_LAUNCH(ctx, k_row_stats_int<true>, nslab, RS_THREADS, smem, m->indptr, m->indices, m->values, m->nnz, N, D,
+                          (uint32_t)g0, W, d_slab_npos, d_slab_s1, d_extra, d_next);
+            } else {
+                LG_CUDA(ctx, cudaFuncSetAttribute(k_row_stats_int<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                LG_LAUNCH(ctx, k_row_stats_int<false>, nslab, RS_THREADS, smem, m->indptr, m->indices, m->values, m->nnz, N, D,
+                          (uint32_t)g0, W, d_slab_npos, d_slab_s1, d_extra, d_next);
+            }
+        }
+        LG_LAUNCH(ctx, k_row_stats_finish, (unsigned)((D + 255) / 256), 256, 0, d_slab_npos, d_slab_s1, d_extra, D, nslab, d_npos,
+                  d_s1, d_s2);
+    } else {
+        double* d_rep;
+        LG_TRY(st.scratch((size_t)RS_REPL * 3 * D, &d_rep));
+        LG_CUDA(ctx, cudaMemsetAsync(d_rep, 0, (size_t)RS_REPL * 3 * D * sizeof(double), ctx->stream));
+        LG_LAUNCH(ctx, k_row_stats_f64, ctx->num_sms * 8, 256, 0, m->indices, m->values, m->nnz, D, d_rep);
+        LG_LAUNCH(ctx, k_row_stats_f64_finish, (unsigned)((D + 255) / 256), 256, 0, d_rep, D, d_npos, d_s1, d_s2);
+    }
+    return st.finish();
+}
+
+// ---------------------------------------------------------------------------------------------
+// K11: Nystrom re-projection, one warp per cell (senna/src/svd/fit.rs:433-466).  Per cell j with stored counts y:
+//   x = y / max(||y||, 1e-8) * c                               normalize_columns_inplace, *= column_sum_norm
+//   d = delta[row, pb(j)];  x /= d * (sum x / sum d)  where d > 0    adjust_by_poisson_ratio (dmatrix_util.rs:226-244)
+//   z = ln(1 + x);  z = (z - mean z) / sd z  over the stored entries (CSC scale_columns_inplace :791-824; z - mean when sd = 0)
+//   out[:, j] = sum_i z_i basis[i, :]
+// Three sweeps over the cell's entries (the second and third re-read them from L1/L2): sums, moments of z, gather-FMA
+// of the basis rows (two entries at a time, one per half-warp, as float2 — the same gather as K1's exception path).
+// The fold order of the per-cell sums is a warp tree, not the reference's serial fold: inside the 1e-5 contract.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+    return v;
+}
+
+template <bool HAS_DELTA>
+__global__ void __launch_bounds__(256) k_nystrom(const uint64_t* __restrict__ indptr, const uint32_t* __restrict__ indices,
+                                                 const float* __restrict__ values, uint64_t ncols, uint64_t D,
+                                                 const float* __restrict__ basis_kd, int K, const float* __restrict__ delta_dp,
+                                                 const uint32_t* __restrict__ pb_of_cell, uint32_t P, float csn,
+                                                 float* __restrict__ out) {
+    const int lane = threadIdx.x & 31;
+    const uint64_t warp0 = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint64_t nwarps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+    const int half = lane >> 4, l = lane & 15;
+    for (uint64_t j = warp0; j < ncols; j += nwarps) {
+        const uint64_t lo = indptr[j], hi = indptr[j + 1];
+        const float* dcol = nullptr;
+        if (HAS_DELTA) {
+            const uint32_t pb = pb_of_cell[j];
+            dcol = pb < P ? delta_dp + (size_t)pb * D : nullptr;  // an unassigned cell is left unadjusted
+        }
+        // sweep 1: sum y^2, sum y, sum d
+        float sq = 0.f, sy = 0.f, sd = 0.f;
+        for (uint64_t t = lo + lane; t < hi; t += 32) {
+            const float y = __ldg(values + t);
+            sq = fmaf(y, y, sq);
+            sy += y;
+            if (HAS_DELTA && dcol) sd += __ldg(dcol + __ldg(indices + t));
+        }
+        sq = warp_sum(sq);
+        sy = warp_sum(sy);
+        sd = warp_sum(sd);
+        const float denom = fmaxf(sqrtf(sq), 1e-8f);
+        const float xsum = __fdiv_rn(sy, denom) * csn;
+        const float ratio = (HAS_DELTA && dcol && sd > 0.0f) ? __fdiv_rn(xsum, sd) : 1.0f;
+        auto zval = [&](uint64_t t, uint32_t g) {
+            float x = __fdiv_rn(__ldg(values + t), denom) * csn;
+            if (HAS_DELTA && dcol) {
+                const float d = __ldg(dcol + g);
+                if (d > 0.0f) x = __fdiv_rn(x, d * ratio);
+            }
+            return log1pf(x);
+        };
+        // sweep 2: moments of z over the stored entries
+        float s1 = 0.f, s2 = 0.f;
+        for (uint64_t t = lo + lane; t < hi; t += 32) {
+            const float z = zval(t, __ldg(indices + t));
+            s1 += z;
+            s2 = fmaf(z, z, s2);
+        }
+        s1 = warp_sum(s1);
+        s2 = warp_sum(s2);
+        const float n = fmaxf((float)(hi - lo), 1.0f);
+        const float mu = __fdiv_rn(s1, n);
+        const float sig = sqrtf(__fdiv_rn(s2, n) - mu * mu);  // NaN when rounding drives the variance below zero, as in the reference
+        const bool scale = sig > 0.0f;
+        // sweep 3: out = sum_i w_i basis[i, :]
+        float acc[4] = {0.f, 0.f, 0.f, 0.f};
+        for (uint64_t base = lo; base < hi; base += 32) {
+            const uint64_t t = base + lane;
+            uint32_t g = 0;
+            float w = 0.0f;
+            if (t < hi) {
+                g = __ldg(indices + t);
+                const float z = zval(t, g);
+                w = scale ? __fdiv_rn(z - mu, sig) : z - mu;
+            }
+            const int cnt = (hi - base) < 32 ? (int)(hi - base) : 32;
+            if ((K & 1) == 0 && K <= 64) {
+                for (int e0 = 0; e0 < cnt; e0 += 8) {
+                    float2 b0[4], b1[4];
+                    float ws[4];
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        const int src = e0 + 2 * e + half;  // lanes beyond cnt carry w = 0 and gene 0
+                        const uint32_t ge = __shfl_sync(0xffffffffu, g, src & 31);
+                        ws[e] = __shfl_sync(0xffffffffu, w, src & 31);
+                        if (src >= cnt) ws[e] = 0.0f;
+                        const float2* brow = reinterpret_cast<const float2*>(basis_kd + (size_t)ge * K);
+                        b0[e] = (2 * l < K) ? __ldg(brow + l) : make_float2(0.f, 0.f);
+                        b1[e] = (2 * (l + 16) < K) ? __ldg(brow + l + 16) : make_float2(0.f, 0.f);
+                    }
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        acc[0] = fmaf(ws[e], b0[e].x, acc[0]);
+                        acc[1] = fmaf(ws[e], b0[e].y, acc[1]);
+                        acc[2] = fmaf(ws[e], b1[e].x, acc[2]);
+                        acc[3] = fmaf(ws[e], b1[e].y, acc[3]);
+                    }
+                }
+            } else {  // lanes as dims, up to 128 dims
+                for (int e = 0; e < cnt; ++e) {
+                    const uint32_t ge = __shfl_sync(0xffffffffu, g, e);
+                    const float we = __shfl_sync(0xffffffffu, w, e);
+                    const float* brow = basis_kd + (size_t)ge * K;
+#pragma unroll
+                    for (int a = 0; a < 4; ++a)
+                        if (lane + 32 * a < K) acc[a] = fmaf(we, __ldg(brow + lane + 32 * a), acc[a]);
+                }
+            }
+        }
+        float* o = out + (size_t)j * K;
+        if ((K & 1) == 0 && K <= 64) {
+#pragma unroll
+            for (int a = 0; a < 4; ++a) acc[a] += __shfl_xor_sync(0xffffffffu, acc[a], 16);
+            if (lane < 16) {
+                if (2 * l < K) {
+                    o[2 * l] = acc[0];
+                    o[2 * l + 1] = acc[1];
+                }
+                if (2 * (l + 16) < K) {
+                    o[2 * l + 32] = acc[2];
+                    o[2 * l + 33] = acc[3];
+                }
+            }
+        } else {
+#pragma unroll
+            for (int a = 0; a < 4; ++a)
+                if (lane + 32 * a < K) o[lane + 32 * a] = acc[a];
+        }
+    }
+}
+
+// basis_dk (D x K column-major, the reference's DMatrix) -> rows of K contiguous dims
+__global__ void k_transpose_dk(const float* __restrict__ src_dk, uint64_t D, int K, float* __restrict__ dst_kd) {
+    const uint64_t e = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= D * (uint64_t)K) return;
+    const uint64_t g = e / K;
+    const int k = (int)(e % K);
+    dst_kd[e] = src_dk[(size_t)k * D + g];
+}
+
+extern "C" int lg_nystrom_project(lg_ctx* ctx, const lg_csc* m, const float* basis_dk, int K, const float* delta_dp,
+                                  const uint32_t* pb_of_cell, uint32_t P, float column_sum_norm, float* out_proj_kn) {
+    if (!ctx) return LG_ERR_INVALID;
+    LG_REQUIRE(ctx, m && basis_dk && out_proj_kn, "lg_nystrom_project: null argument");
+    LG_REQUIRE(ctx, K >= 1 && K <= 128, "lg_nystrom_project: K must be in [1, 128]");
+    LG_REQUIRE(ctx, !delta_dp || (pb_of_cell && P >= 1), "lg_nystrom_project: delta needs the pseudobulk of every cell");
+    cudaSetDevice(ctx->device);
+    const uint64_t D = m->nrows, N = m->ncols;
+    LgStage st(ctx);
+    const float *d_basis, *d_delta;
+    const uint32_t* d_pb;
+    float *d_out, *d_bt;
+    LG_TRY(st.in(basis_dk, (size_t)D * K, &d_basis));
+    LG_TRY(st.in(delta_dp, delta_dp ? (size_t)D * P : 0, &d_delta));
+    LG_TRY(st.in(pb_of_cell, delta_dp ? (size_t)N : 0, &d_pb));
+    LG_TRY(st.out(out_proj_kn, (size_t)K * N, &d_out));
+    if (N == 0 || D == 0) return st.finish();
+    LG_TRY(st.scratch((size_t)D * K, &d_bt));
+    LG_LAUNCH(ctx, k_transpose_dk, (unsigned)((D * K + 255) / 256), 256, 0, d_basis, D, K, d_bt);
+    uint64_t blocks = (N + 7) / 8;
+    const uint64_t cap = (uint64_t)ctx->num_sms * 32;
+    if (blocks > cap) blocks = cap;
+    if (d_delta)
+        LG_LAUNCH(ctx, k_nystrom<true>, (unsigned)blocks, 256, 0, m->indptr, m->indices, m->values, N, D, d_bt, K, d_delta, d_pb, P,
+                  column_sum_norm, d_out);
+    else
+        LG_LAUNCH(ctx, k_nystrom<false>, (unsigned)blocks, 256, 0, m->indptr, m->indices, m->values, N, D, d_bt, K,
+                  (const float*)nullptr, (const uint32_t*)nullptr, 0u, column_sum_norm, d_out);
+    return st.finish();
+}

@@ -22,7 +22,7 @@ _LIB_PATH = os.path.join(_HERE, "liblegume_oracle.so")
 
 def build(force: bool = False) -> str:
     """Compile the oracle with its committed Makefile (building the checker is not using it)."""
-    srcs = [os.path.join(_HERE, f) for f in ("oracle.cpp", "oracle_adjust.cpp", "oracle.h")]
+    srcs = [os.path.join(_HERE, f) for f in ("oracle.cpp", "oracle_adjust.cpp", "oracle_next.cpp", "oracle.h")]
     stale = (not os.path.exists(_LIB_PATH)) or os.path.getmtime(_LIB_PATH) < max(os.path.getmtime(f) for f in srcs)
     if force or stale:
         subprocess.run(["make", "-C", _HERE], check=True, capture_output=True)
@@ -387,3 +387,41 @@ def sim_poisson_csc(seed, D, col_lo, col_hi, topic_of_cell, batch_of_cell, ntopi
     data = np.zeros(nnz, np.float32)
     lib().orc_sim_poisson_csc(*args, _ptr(indices, C.c_uint64), _ptr(data, C.c_float))
     return indptr, indices, data
+
+
+# ---- the steps either side of the path -------------------------------------
+def row_stats(indptr, indices, data, nrows):
+    """SparseRunningStatistics::add_csc (matrix-util/src/sparse_stat.rs:64-108): (npos, s1, s2), f32, column order"""
+    indptr, indices, data = _csc(indptr, indices, data)
+    n = len(indptr) - 1
+    npos, s1, s2 = (np.zeros(nrows, np.float32) for _ in range(3))
+    lib().orc_row_stats(_ptr(indptr, C.c_uint64), _ptr(indices, C.c_uint64), _ptr(data, C.c_float), C.c_uint64(nrows),
+                        C.c_uint64(n), _ptr(npos, C.c_float), _ptr(s1, C.c_float), _ptr(s2, C.c_float))
+    return npos, s1, s2
+
+
+def row_stats_moments(s1, s2, ncols_processed):
+    """mean, variance, std (sparse_stat.rs:412-431)"""
+    s1 = np.ascontiguousarray(s1, np.float32)
+    s2 = np.ascontiguousarray(s2, np.float32)
+    mean, var, sd = (np.zeros(len(s1), np.float32) for _ in range(3))
+    lib().orc_row_stats_moments(_ptr(s1, C.c_float), _ptr(s2, C.c_float), C.c_uint64(len(s1)), C.c_uint64(ncols_processed),
+                                _ptr(mean, C.c_float), _ptr(var, C.c_float), _ptr(sd, C.c_float))
+    return mean, var, sd
+
+
+def nystrom_project(indptr, indices, data, nrows, basis_dk, delta_dp=None, pb_of_cell=None, column_sum_norm=1e4):
+    """nystrom_proj_visitor (senna/src/svd/fit.rs:433-466).  basis_dk: (K, D) array = D x K column-major;
+    delta_dp: (P, D) array = D x P column-major or None.  Returns (N, K) = K x N column-major."""
+    indptr, indices, data = _csc(indptr, indices, data)
+    basis = np.ascontiguousarray(basis_dk, np.float32)
+    K = basis.shape[0]
+    n = len(indptr) - 1
+    delta = None if delta_dp is None else np.ascontiguousarray(delta_dp, np.float32)
+    pb = None if delta is None else np.ascontiguousarray(pb_of_cell, np.uint32)
+    P = 0 if delta is None else delta.shape[0]
+    out = np.zeros((n, K), np.float32)
+    lib().orc_nystrom_project(_ptr(indptr, C.c_uint64), _ptr(indices, C.c_uint64), _ptr(data, C.c_float), C.c_uint64(nrows),
+                              C.c_uint64(n), _ptr(basis, C.c_float), C.c_int(K), _ptr(delta, C.c_float), _ptr(pb, C.c_uint32),
+                              C.c_uint32(P), C.c_float(column_sum_norm), _ptr(out, C.c_float))
+    return out

@@ -128,6 +128,18 @@ uint64_t orc_sim_poisson_csc(uint64_t seed, uint64_t D, uint64_t col_lo, uint64_
                              uint32_t nbatch, const float* lam, const float* p0, const uint8_t* npiece,
                              uint64_t* indptr, uint64_t* indices, float* data);
 
+/* ---- the steps either side of the path (oracle_next.cpp) ---------------------- */
+/* SparseRunningStatistics::add_csc (matrix-util/src/sparse_stat.rs:64-108), f32, column order */
+void orc_row_stats(const uint64_t* indptr, const uint64_t* indices, const float* data, uint64_t nrows, uint64_t ncols,
+                   float* npos, float* s1, float* s2);
+/* mean / variance / std (sparse_stat.rs:412-431) */
+void orc_row_stats_moments(const float* s1, const float* s2, uint64_t nrows, uint64_t ncols_processed, float* mean,
+                           float* variance, float* sd);
+/* nystrom_proj_visitor (senna/src/svd/fit.rs:433-466) */
+void orc_nystrom_project(const uint64_t* indptr, const uint64_t* indices, const float* data, uint64_t nrows,
+                         uint64_t ncols, const float* basis_dk, int K, const float* delta_dp, const uint32_t* pb_of_cell,
+                         uint32_t P, float column_sum_norm, float* out_kn);
+
 #ifdef __cplusplus
 }
 #endif
