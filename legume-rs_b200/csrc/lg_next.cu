@@ -248,25 +248,25 @@ extern "C" int lg_row_stats(lg_ctx* ctx, const lg_csc* m, double* out_npos, doub
 //   d = delta[row, pb(j)];  x /= d * (sum x / sum d)  where d > 0    adjust_by_poisson_ratio (dmatrix_util.rs:226-244)
 //   z = ln(1 + x);  z = (z - mean z) / sd z  over the stored entries (CSC scale_columns_inplace :791-824; z - mean when sd = 0)
 //   out[:, j] = sum_i z_i basis[i, :]
-// Three sweeps over the cell's entries (the second and third re-read them from L1/L2): sums, moments of z, gather-FMA
-// of the basis rows (two entries at a time, one per half-warp, as float2 — the same gather as K1's exception path).
-// The fold order of the per-cell sums is a warp tree, not the reference's serial fold: inside the 1e-5 contract.
+// The reference's per-cell scalars are ill-conditioned in f32: sd^2 = s2/n - mean^2 cancels about three digits (z ~ 5.5,
+// sd ~ 0.2), so ONE ulp of difference in a log1p (CUDA's vs glibc's) already moves every output of a cell by ~1e-4, and
+// the reference's own serial f32 folds sit up to ~5e-4 from exact arithmetic.  Bit-chasing that is meaningless, so the
+// per-cell sums are accumulated in f64 here (lane partials + a butterfly): the result is within 1e-5 of the float64
+// restatement of the reference's formulas, which is what the tests hold it to (and within the reference's own error of
+// the f32 oracle).  Sweeps re-read the cell's entries from L1/L2: A (sum y^2, sum y, sum d), C (sum z, sum z^2),
+// D gather-FMA of the basis rows (two entries at a time, one per half-warp, as float2).
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ float warp_sum(float v) {
-#pragma unroll
-    for (int off = 16; off >= 1; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
-    return v;
-}
+constexpr int NY_WARPS = 8;
 
 template <bool HAS_DELTA>
-__global__ void __launch_bounds__(256) k_nystrom(const uint64_t* __restrict__ indptr, const uint32_t* __restrict__ indices,
-                                                 const float* __restrict__ values, uint64_t ncols, uint64_t D,
-                                                 const float* __restrict__ basis_kd, int K, const float* __restrict__ delta_dp,
-                                                 const uint32_t* __restrict__ pb_of_cell, uint32_t P, float csn,
-                                                 float* __restrict__ out) {
-    const int lane = threadIdx.x & 31;
-    const uint64_t warp0 = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const uint64_t nwarps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+__global__ void __launch_bounds__(NY_WARPS * 32) k_nystrom(const uint64_t* __restrict__ indptr, const uint32_t* __restrict__ indices,
+                                                          const float* __restrict__ values, uint64_t ncols, uint64_t D,
+                                                          const float* __restrict__ basis_kd, int K,
+                                                          const float* __restrict__ delta_dp, const uint32_t* __restrict__ pb_of_cell,
+                                                          uint32_t P, float csn, float* __restrict__ out) {
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const uint64_t warp0 = (uint64_t)blockIdx.x * NY_WARPS + wib;
+    const uint64_t nwarps = (uint64_t)gridDim.x * NY_WARPS;
     const int half = lane >> 4, l = lane & 15;
     for (uint64_t j = warp0; j < ncols; j += nwarps) {
         const uint64_t lo = indptr[j], hi = indptr[j + 1];
@@ -275,43 +275,47 @@ __global__ void __launch_bounds__(256) k_nystrom(const uint64_t* __restrict__ in
             const uint32_t pb = pb_of_cell[j];
             dcol = pb < P ? delta_dp + (size_t)pb * D : nullptr;  // an unassigned cell is left unadjusted
         }
-        // sweep 1: sum y^2, sum y, sum d
-        float sq = 0.f, sy = 0.f, sd = 0.f;
+        // sweep A: sum y^2, sum y, sum d
+        double sq = 0.0, sy = 0.0, sd = 0.0;
         for (uint64_t t = lo + lane; t < hi; t += 32) {
-            const float y = __ldg(values + t);
-            sq = fmaf(y, y, sq);
+            const double y = (double)__ldg(values + t);
+            sq = fma(y, y, sq);
             sy += y;
-            if (HAS_DELTA && dcol) sd += __ldg(dcol + __ldg(indices + t));
+            if (HAS_DELTA && dcol) sd += (double)__ldg(dcol + __ldg(indices + t));
         }
-        sq = warp_sum(sq);
-        sy = warp_sum(sy);
-        sd = warp_sum(sd);
-        const float denom = fmaxf(sqrtf(sq), 1e-8f);
-        const float xsum = __fdiv_rn(sy, denom) * csn;
-        const float ratio = (HAS_DELTA && dcol && sd > 0.0f) ? __fdiv_rn(xsum, sd) : 1.0f;
+        sq = lg_butterfly32(sq);
+        sy = lg_butterfly32(sy);
+        if (HAS_DELTA) sd = lg_butterfly32(sd);
+        const float denom = fmaxf((float)sqrt(sq), 1e-8f);
+        // sum x = sum (y / denom) * c; the ratio xsum / dsum is well conditioned
+        const float ratio = (HAS_DELTA && dcol && sd > 0.0) ? (float)(sy / (double)denom * (double)csn / sd) : 1.0f;
         auto zval = [&](uint64_t t, uint32_t g) {
-            float x = __fdiv_rn(__ldg(values + t), denom) * csn;
+            float x = __fmul_rn(__fdiv_rn(__ldg(values + t), denom), csn);
             if (HAS_DELTA && dcol) {
                 const float d = __ldg(dcol + g);
-                if (d > 0.0f) x = __fdiv_rn(x, d * ratio);
+                if (d > 0.0f) x = __fdiv_rn(x, __fmul_rn(d, ratio));
             }
             return log1pf(x);
         };
-        // sweep 2: moments of z over the stored entries
-        float s1 = 0.f, s2 = 0.f;
+        // sweep C: moments of z over the stored entries
+        double s1 = 0.0, s2 = 0.0;
         for (uint64_t t = lo + lane; t < hi; t += 32) {
-            const float z = zval(t, __ldg(indices + t));
+            const double z = (double)zval(t, (HAS_DELTA && dcol) ? __ldg(indices + t) : 0u);
             s1 += z;
-            s2 = fmaf(z, z, s2);
+            s2 = fma(z, z, s2);
         }
-        s1 = warp_sum(s1);
-        s2 = warp_sum(s2);
-        const float n = fmaxf((float)(hi - lo), 1.0f);
-        const float mu = __fdiv_rn(s1, n);
-        const float sig = sqrtf(__fdiv_rn(s2, n) - mu * mu);  // NaN when rounding drives the variance below zero, as in the reference
-        const bool scale = sig > 0.0f;
-        // sweep 3: out = sum_i w_i basis[i, :]
-        float acc[4] = {0.f, 0.f, 0.f, 0.f};
+        s1 = lg_butterfly32(s1);
+        s2 = lg_butterfly32(s2);
+        const double nn = (double)(hi - lo) > 1.0 ? (double)(hi - lo) : 1.0;
+        const double mud = s1 / nn;
+        const double var = s2 / nn - mud * mud;
+        // a constant column (variance zero up to f64 rounding) is only centred (dmatrix_util.rs:815-819)
+        const double inv_sig = var > 1e-12 * (s2 / nn) ? 1.0 / sqrt(var) : 1.0;
+        // sweep D: out = sum_i w_i basis[i, :].  Each batch of 32 entries is summed in f32 and folded into an f64 total:
+        // a plain f32 chain over ~1500 terms of size O(1) drifts by ~4e-5 of the result (the reference's serial f32 sum
+        // does too), which would be the largest error left in the path
+        double tot[4] = {0.0, 0.0, 0.0, 0.0};
+        const bool pairs = (K & 1) == 0 && K <= 64;
         for (uint64_t base = lo; base < hi; base += 32) {
             const uint64_t t = base + lane;
             uint32_t g = 0;
@@ -319,19 +323,19 @@ __global__ void __launch_bounds__(256) k_nystrom(const uint64_t* __restrict__ in
             if (t < hi) {
                 g = __ldg(indices + t);
                 const float z = zval(t, g);
-                w = scale ? __fdiv_rn(z - mu, sig) : z - mu;
+                w = (float)(((double)z - mud) * inv_sig);  // z - mean cancels ~2 digits: centred in f64
             }
             const int cnt = (hi - base) < 32 ? (int)(hi - base) : 32;
-            if ((K & 1) == 0 && K <= 64) {
+            float acc[4] = {0.f, 0.f, 0.f, 0.f};
+            if (pairs) {
                 for (int e0 = 0; e0 < cnt; e0 += 8) {
                     float2 b0[4], b1[4];
                     float ws[4];
 #pragma unroll
                     for (int e = 0; e < 4; ++e) {
                         const int src = e0 + 2 * e + half;  // lanes beyond cnt carry w = 0 and gene 0
-                        const uint32_t ge = __shfl_sync(0xffffffffu, g, src & 31);
-                        ws[e] = __shfl_sync(0xffffffffu, w, src & 31);
-                        if (src >= cnt) ws[e] = 0.0f;
+                        const uint32_t ge = __shfl_sync(0xffffffffu, g, src);
+                        ws[e] = __shfl_sync(0xffffffffu, w, src);
                         const float2* brow = reinterpret_cast<const float2*>(basis_kd + (size_t)ge * K);
                         b0[e] = (2 * l < K) ? __ldg(brow + l) : make_float2(0.f, 0.f);
                         b1[e] = (2 * (l + 16) < K) ? __ldg(brow + l + 16) : make_float2(0.f, 0.f);
@@ -354,25 +358,27 @@ __global__ void __launch_bounds__(256) k_nystrom(const uint64_t* __restrict__ in
                         if (lane + 32 * a < K) acc[a] = fmaf(we, __ldg(brow + lane + 32 * a), acc[a]);
                 }
             }
+#pragma unroll
+            for (int a = 0; a < 4; ++a) tot[a] += (double)acc[a];
         }
         float* o = out + (size_t)j * K;
-        if ((K & 1) == 0 && K <= 64) {
+        if (pairs) {
 #pragma unroll
-            for (int a = 0; a < 4; ++a) acc[a] += __shfl_xor_sync(0xffffffffu, acc[a], 16);
+            for (int a = 0; a < 4; ++a) tot[a] += __shfl_xor_sync(0xffffffffu, tot[a], 16);
             if (lane < 16) {
                 if (2 * l < K) {
-                    o[2 * l] = acc[0];
-                    o[2 * l + 1] = acc[1];
+                    o[2 * l] = (float)tot[0];
+                    o[2 * l + 1] = (float)tot[1];
                 }
                 if (2 * (l + 16) < K) {
-                    o[2 * l + 32] = acc[2];
-                    o[2 * l + 33] = acc[3];
+                    o[2 * l + 32] = (float)tot[2];
+                    o[2 * l + 33] = (float)tot[3];
                 }
             }
         } else {
 #pragma unroll
             for (int a = 0; a < 4; ++a)
-                if (lane + 32 * a < K) o[lane + 32 * a] = acc[a];
+                if (lane + 32 * a < K) o[lane + 32 * a] = (float)tot[a];
         }
     }
 }
@@ -405,14 +411,14 @@ extern "C" int lg_nystrom_project(lg_ctx* ctx, const lg_csc* m, const float* bas
     if (N == 0 || D == 0) return st.finish();
     LG_TRY(st.scratch((size_t)D * K, &d_bt));
     LG_LAUNCH(ctx, k_transpose_dk, (unsigned)((D * K + 255) / 256), 256, 0, d_basis, D, K, d_bt);
-    uint64_t blocks = (N + 7) / 8;
+    uint64_t blocks = (N + NY_WARPS - 1) / NY_WARPS;
     const uint64_t cap = (uint64_t)ctx->num_sms * 32;
     if (blocks > cap) blocks = cap;
     if (d_delta)
-        LG_LAUNCH(ctx, k_nystrom<true>, (unsigned)blocks, 256, 0, m->indptr, m->indices, m->values, N, D, d_bt, K, d_delta, d_pb, P,
+        LG_LAUNCH(ctx, k_nystrom<true>, (unsigned)blocks, NY_WARPS * 32, 0, m->indptr, m->indices, m->values, N, D, d_bt, K, d_delta, d_pb, P,
                   column_sum_norm, d_out);
     else
-        LG_LAUNCH(ctx, k_nystrom<false>, (unsigned)blocks, 256, 0, m->indptr, m->indices, m->values, N, D, d_bt, K,
+        LG_LAUNCH(ctx, k_nystrom<false>, (unsigned)blocks, NY_WARPS * 32, 0, m->indptr, m->indices, m->values, N, D, d_bt, K,
                   (const float*)nullptr, (const uint32_t*)nullptr, 0u, column_sum_norm, d_out);
     return st.finish();
 }

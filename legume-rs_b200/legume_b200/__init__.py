@@ -34,7 +34,7 @@ __all__ = ["Context", "CscBlock", "SparseIoVec", "binary_sort_columns", "GammaMa
            "CollapsedOut", "optimize", "ColumnDict", "LegumeError", "CalibrateTarget", "compute_level_sort_dims",
            "pad_numeric_labels", "merge_stat", "MultilevelParams", "PbSampleLayout", "build_pb_sample_layout",
            "per_batch_sc_neighbors", "collect_matched_stat_coarse", "compute_fine_to_coarse_mapping",
-           "sort_batch_proximity", "knn_match_batches"]
+           "sort_batch_proximity", "knn_match_batches", "SparseRunningStatistics", "nystrom_project"]
 DEFAULT_NUM_LEVELS = 2                          # collapse_data/stats.rs:688
 
 
@@ -495,6 +495,85 @@ def optimize(ctx: Context, stat: CollapsedStat, hyper=(1.0, 1.0), num_iter=DEFAU
 # --------------------------------------------------------------------------------------------------
 # SparseIoVec: the data handle the reference's traits are implemented on
 # --------------------------------------------------------------------------------------------------
+class SparseRunningStatistics:
+    """matrix-util/src/sparse_stat.rs:33-198, 404-431 (T = f32): per-row (npos, s1, s2) over the columns seen so far.
+    The sufficient statistics are held as f64 — exact whole numbers for count data, so blocks and shards merge to
+    the same totals in any order — and narrowed to the reference's f32 by the accessors."""
+
+    def __init__(self, nrows):
+        self._nrows, self._ncols = int(nrows), 0
+        self._npos, self._s1, self._s2 = (np.zeros(self._nrows, np.float64) for _ in range(3))
+
+    def nrows(self):
+        return self._nrows
+
+    def ncols_processed(self):
+        return self._ncols
+
+    def add_block(self, ctx: "Context", block: "CscBlock"):
+        """add_csc over a device-resident block (sparse_stat.rs:97-108)"""
+        if block.nrows != self._nrows:
+            raise LegumeError(1, "SparseRunningStatistics: row count mismatch")
+        out = [np.empty(self._nrows, np.float64) for _ in range(3)]
+        ctx.check(lib.lg_row_stats(ctx.h, block.h, _ptr(out[0]), _ptr(out[1]), _ptr(out[2])))
+        self._npos += out[0]
+        self._s1 += out[1]
+        self._s2 += out[2]
+        self._ncols += block.ncols
+
+    def merge(self, other: "SparseRunningStatistics"):
+        """sparse_stat.rs:183-196"""
+        self._npos += other._npos
+        self._s1 += other._s1
+        self._s2 += other._s2
+        self._ncols += other._ncols
+
+    def _denom(self):
+        return np.float32(self._ncols) if self._ncols > 0 else np.float32(1e-8)  # safe_denom, :16-23
+
+    def count_positives(self):
+        return self._npos.astype(np.float32)
+
+    def sum(self):
+        return self._s1.astype(np.float32)
+
+    def mean(self):
+        return self.sum() / self._denom()
+
+    def variance(self):
+        mu = self.mean()
+        return self._s2.astype(np.float32) / self._denom() - mu * mu
+
+    def std(self):
+        with np.errstate(invalid="ignore"):
+            return np.sqrt(self.variance())
+
+    def to_vecs(self):
+        return self.count_positives(), self.sum(), self.mean(), self.std()
+
+
+def nystrom_project(ctx: "Context", block: "CscBlock", basis_dk, delta_dp=None, pb_of_cell=None, column_sum_norm=1e4):
+    """nystrom_proj_visitor over a block (senna/src/svd/fit.rs:433-466).  basis_dk: (K, D) array = the reference's
+    D x K column-major DMatrix; delta_dp: (P, D) = D x P or None; returns (N, K) = K x N column-major, next to the inputs."""
+    basis_dk = _as(basis_dk, np.float32)
+    K = int(basis_dk.shape[0])
+    if int(basis_dk.shape[1]) != block.nrows:
+        raise LegumeError(1, "nystrom_project: basis rows mismatch the number of genes")
+    P = 0
+    if delta_dp is not None:
+        delta_dp = _as(delta_dp, np.float32)
+        P = int(delta_dp.shape[0])
+        if int(delta_dp.shape[1]) != block.nrows:
+            raise LegumeError(1, "nystrom_project: delta rows mismatch the number of genes")
+        if pb_of_cell is None or len(pb_of_cell) != block.ncols:
+            raise LegumeError(1, "nystrom_project: delta needs the pseudobulk of every cell")
+        pb_of_cell = _as(pb_of_cell, np.uint32)
+    out = ctx.empty((block.ncols, K), np.float32, _is_torch(basis_dk))
+    ctx.check(lib.lg_nystrom_project(ctx.h, block.h, _ptr(basis_dk), K, _ptr(delta_dp),
+                                     _ptr(pb_of_cell) if delta_dp is not None else None, P, float(column_sum_norm), _ptr(out)))
+    return out
+
+
 class SparseIoVec:
     """One preloaded backend's columns on the device, with the derived caches of
     data-beans/src/sparse_io_vector/mod.rs:70-85 (groups, batches, multiplicity)."""
@@ -613,6 +692,18 @@ class SparseIoVec:
         self.col_to_group = group
         self.group_keys = sorted({str(int(c)) for c in np.unique(codes_h)}, key=lambda s: s.encode())
         return int(codes_h.max()) + 1
+
+    # ---- the nnz streams either side of the path ----
+    def streaming_sparse_running_stats(self, block_size=None, progress_label=""):
+        """data-beans-alg/src/sparse_streaming.rs:23-60: per-gene (npos, sum, sum_sq) over every column"""
+        stats = SparseRunningStatistics(self.num_rows())
+        stats.add_block(self.ctx, self.block)
+        return stats
+
+    def nystrom_project(self, basis_dk, delta_dp=None, column_sum_norm=1e4):
+        """do_nystrom_proj's visitor pass (senna/src/svd/fit.rs:421-466); the pseudobulk of a cell is its group"""
+        pb = self.get_group_membership() if delta_dp is not None else None
+        return nystrom_project(self.ctx, self.block, basis_dk, delta_dp, pb, column_sum_norm)
 
     # ---- CollapsingOps (collapse_data/mod.rs:315-483) ----
     def collect_basic_stat(self, stat: CollapsedStat):

@@ -83,6 +83,8 @@ _sig = {
     "lg_pb_min_keys": [_vp, _vp, _i, _u64, _vp, _u64, _vp, _vp, _u32, _u32, _u32, _vp],
     "lg_pb_topk_keys": [_vp, _vp, _u32, _u32, _u32, _u32, _vp, _i, _vp, _vp],
     "lg_fine_to_coarse": [_vp, _vp, _vp, _u64, _u32, _i, _vp, C.POINTER(_u32)],
+    "lg_row_stats": [_vp, _vp, _vp, _vp, _vp],
+    "lg_nystrom_project": [_vp, _vp, _vp, _i, _vp, _vp, _u32, _f, _vp],
     "lg_sim_poisson_csc": [_vp, _u64, _u64, _u64, _u64, _vp, _vp, _u32, _u32, _vp, _vp, _vp, C.POINTER(_vp)],
 }
 for _name, _args in _sig.items():

@@ -3,7 +3,7 @@ known-answer tests, and checks it against independent float64 numpy restatements
 import numpy as np
 
 import oracle as orc
-from util import close, random_csc
+from util import close, nystrom_f64, random_csc
 
 
 def csc_from_dense(a):
@@ -60,26 +60,6 @@ def test_row_stats_skips_non_finite_and_counts_only_positive():
     assert orc.row_stats_moments(np.zeros(2, np.float32), np.zeros(2, np.float32), 0)[0].tolist() == [0, 0]  # safe_denom
 
 
-def nystrom_f64(ip, ix, v, D, basis, delta, pb, csn):
-    ip = ip.astype(np.int64)
-    out = np.zeros((len(ip) - 1, basis.shape[0]))
-    for j in range(len(ip) - 1):
-        rows = ix[ip[j]:ip[j + 1]].astype(np.int64)
-        x = v[ip[j]:ip[j + 1]].astype(np.float64)
-        if len(x) == 0:
-            continue
-        x = x / max(np.sqrt((x * x).sum()), 1e-8) * csn
-        if delta is not None and pb[j] < delta.shape[0]:
-            d = delta[pb[j], rows].astype(np.float64)
-            scale = x.sum() / d.sum() if d.sum() > 0 else 1.0
-            x = np.where(d > 0, x / np.where(d > 0, d * scale, 1.0), x)
-        z = np.log1p(x)
-        mu, sig = z.mean(), z.std()
-        z = (z - mu) / sig if sig > 0 else z - mu
-        out[j] = basis[:, rows].astype(np.float64) @ z
-    return out
-
-
 def test_nystrom_matches_float64_restatement():
     rng = np.random.default_rng(2)
     D, N, K, P = 400, 300, 20, 7
@@ -91,7 +71,9 @@ def test_nystrom_matches_float64_restatement():
     for dl, pp in ((None, None), (delta, pb)):
         got = orc.nystrom_project(ip, ix, v, D, basis, dl, pp, 1e4)
         want = nystrom_f64(ip, ix, v, D, basis, dl, pp, 1e4)
-        assert got.shape == (N, K) and close(got, want, 1e-4)  # serial f32 folds over ~30 entries against float64
+        # the reference's f32 variance s2/n - mean^2 cancels about three digits (z ~ 5.5, sd ~ 0.2), so its own
+        # result sits ~5e-4 from exact arithmetic; the CUDA path mirrors the f32 folds and is held to 1e-5 in test_gpu_next
+        assert got.shape == (N, K) and close(got, want, 2e-3)
     # a one-entry column: sd = 0 -> z - mean = 0 -> a zero row; an empty column -> zeros
     assert not np.any(orc.nystrom_project(np.array([0, 1, 1], np.uint64), np.array([3], np.uint64), np.array([5.0], np.float32),
                                           D, basis))

@@ -82,3 +82,23 @@ def matched_stat_f64(ip, ix, v, D, grp, S, idx, dist):
             imp[grp[j]] += yhat
         res[grp[j]] += y1
     return imp, res
+
+
+def nystrom_f64(ip, ix, v, D, basis, delta, pb, csn):
+    ip = ip.astype(np.int64)
+    out = np.zeros((len(ip) - 1, basis.shape[0]))
+    for j in range(len(ip) - 1):
+        rows = ix[ip[j]:ip[j + 1]].astype(np.int64)
+        x = v[ip[j]:ip[j + 1]].astype(np.float64)
+        if len(x) == 0:
+            continue
+        x = x / max(np.sqrt((x * x).sum()), 1e-8) * csn
+        if delta is not None and pb[j] < delta.shape[0]:
+            d = delta[pb[j], rows].astype(np.float64)
+            scale = x.sum() / d.sum() if d.sum() > 0 else 1.0
+            x = np.where(d > 0, x / np.where(d > 0, d * scale, 1.0), x)
+        z = np.log1p(x)
+        mu, sig = z.mean(), z.std()
+        z = (z - mu) / sig if sig > 0 else z - mu
+        out[j] = basis[:, rows].astype(np.float64) @ z
+    return out
