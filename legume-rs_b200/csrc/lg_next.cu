@@ -2,7 +2,7 @@
 //   K10  per-gene running statistics   SparseRunningStatistics::add_csc  matrix-util/src/sparse_stat.rs:64-108,
 //                                       streaming_sparse_running_stats    data-beans-alg/src/sparse_streaming.rs:23-60
 //   K11  Nystrom re-projection          nystrom_proj_visitor              senna/src/svd/fit.rs:433-466
-#include <cub/cub.cuh>
+#include <cstdlib>
 
 #include "lg_common.cuh"
 
@@ -21,56 +21,91 @@ __global__ void k_rs_all_integral(const float* __restrict__ v, uint64_t n, int* 
 
 // ---------------------------------------------------------------------------------------------
 // K10: one pass over the nnz stream for (npos, s1, s2) per gene.
-// Count data (every value a whole number in [0, 2^20), checked once per block and cached): a CTA owns a D-long
-// u32 accumulator in shared memory and packs the two statistics every non-zero touches into ONE native ATOMS.ADD:
-//   acc[g] += (1 << 23) | y          npos in the top 9 bits (<= 256 cells per chunk), s1 in the low 23
-// s2 = s1 + sum over y >= 2 of y (y - 1): only the few counts above one pay a second (global, replicated) atomic.
-// Every RS_CHUNK cells the CTA folds its accumulator into a private u64 slab with plain read-modify-writes; a
-// last kernel adds the slabs in a fixed order.  Integer arithmetic throughout: exact, order-free, identical for
-// any grid or GPU count.  Anything else (fractional / negative / non-finite values) takes the f64-atomic path.
+// Count data (every value a whole number in [0, 2^20), checked once per block and cached): a CTA keeps two
+// shared-memory accumulators over the gene axis and every non-zero costs ONE native ATOMS.ADD on the first,
+//   acc[g] += (1 << 21) | y               npos in the top 11 bits (<= 1024 cells between folds), s1 in the low 21
+// and counts above one a second on a 16-bit field (two genes per word) holding y (y - 1), since
+//   s2 = s1 + sum over y >= 2 of y (y - 1).
+// Every RS_FOLD_CELLS cells the CTA folds both accumulators into its private slab in global memory with plain vector
+// read-modify-writes; a last kernel adds the slabs in a fixed order.  Counts too large for the fields (y >= 2048
+// resp. y >= 8, a ~1e-5 share) go to the slab directly with atomics.  Integer arithmetic throughout: exact,
+// order-free, identical for any grid or GPU count.  Anything else (fractional / negative / non-finite values) takes
+// the f64-atomic path below.
 // ---------------------------------------------------------------------------------------------
-constexpr int RS_THREADS = 512;
-constexpr int RS_CHUNK = 256;          // cells per accumulator flush: npos <= 256 fits 9 bits
-constexpr uint32_t RS_S1_BITS = 23;    // per-chunk s1 < 2^23 is guaranteed for y < 2^15; larger counts bypass the packing
-constexpr uint32_t RS_Y_PACK_MAX = 1u << 15;
-constexpr int RS_REPL = 8;             // replicas of the global y(y-1) accumulator (spreads same-address atomics)
+constexpr int RS_THREADS = 1024;
+constexpr int RS_CHUNK = 256;            // cells per work item (dynamic claim)
+constexpr int RS_FOLD_CELLS = 1024;      // cells between folds: npos <= 1024 needs 11 bits
+constexpr uint32_t RS_SHIFT = 21;        // s1 field: 1024 cells * (RS_YMAX - 1) < 2^21
+constexpr uint32_t RS_YMAX = 2048;
+constexpr uint32_t RS_XMAX = 8;          // y (y - 1) <= 42 for y < 8: 1024 cells * 42 < 2^16
 
 template <bool VEC>
 __global__ void __launch_bounds__(RS_THREADS, 1) k_row_stats_int(const uint64_t* __restrict__ indptr,
                                                                  const uint32_t* __restrict__ indices,
                                                                  const float* __restrict__ values, uint64_t nnz_total,
                                                                  uint64_t ncells, uint64_t D, uint32_t g0, uint32_t W,
-                                                                 unsigned long long* __restrict__ slab_npos,
+                                                                 uint32_t* __restrict__ slab_npos,
                                                                  unsigned long long* __restrict__ slab_s1,
-                                                                 unsigned long long* __restrict__ extra,
+                                                                 unsigned long long* __restrict__ slab_extra,
                                                                  unsigned long long* __restrict__ next_chunk) {
-    extern __shared__ __align__(16) uint32_t acc[];  // W packed accumulators
+    extern __shared__ __align__(16) uint32_t acc[];  // W packed (npos | s1), then ceil(W / 2) words of paired 16-bit extras
     __shared__ unsigned long long s_chunk;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = RS_THREADS / 32;
+    const uint32_t W2 = (W + 1) >> 1;
+    uint32_t* ext = acc + ((W + 1) & ~1u);
     const uint64_t nchunks = (ncells + RS_CHUNK - 1) / RS_CHUNK;
-    unsigned long long* my_npos = slab_npos + (size_t)blockIdx.x * D + g0;
+    uint32_t* my_npos = slab_npos + (size_t)blockIdx.x * D + g0;
     unsigned long long* my_s1 = slab_s1 + (size_t)blockIdx.x * D + g0;
-    unsigned long long* my_extra = extra + (size_t)(blockIdx.x % RS_REPL) * D + g0;
-    for (uint32_t g = threadIdx.x; g < W; g += RS_THREADS) acc[g] = 0;
+    unsigned long long* my_extra = slab_extra + (size_t)blockIdx.x * D + g0;
+    for (uint32_t g = threadIdx.x; g < ((W + 1) & ~1u) + W2; g += RS_THREADS) acc[g] = 0;
     auto one = [&](uint32_t g, float v) {
         const uint32_t ge = g - g0;
         if (ge >= W) return;
         const uint32_t y = (uint32_t)v;
-        if (y == 0) return;  // a stored zero: finite, not positive, adds nothing
-        if (y < RS_Y_PACK_MAX) {
-            atomicAdd(&acc[ge], (1u << RS_S1_BITS) | y);
-        } else {  // a count too large for the packed field: straight to this CTA's slab
-            atomicAdd(&my_npos[ge], 1ull);
+        if (y - 1u < RS_YMAX - 1u) {  // 1 <= y < RS_YMAX
+            atomicAdd(&acc[ge], (1u << RS_SHIFT) | y);
+        } else if (y) {  // too large for the packed field (a stored zero adds nothing)
+            atomicAdd(&my_npos[ge], 1u);
             atomicAdd(&my_s1[ge], (unsigned long long)y);
         }
-        if (y >= 2) atomicAdd(&my_extra[ge], (unsigned long long)y * (y - 1));
+        if (y >= 2) {
+            if (y < RS_XMAX) atomicAdd(&ext[ge >> 1], (y * (y - 1)) << ((ge & 1u) * 16));
+            else atomicAdd(&my_extra[ge], (unsigned long long)y * (y - 1));
+        }
     };
+    auto fold = [&]() {  // shared accumulators -> this CTA's slab (plain read-modify-writes: nobody else owns it)
+        __syncthreads();
+        for (uint32_t w = threadIdx.x; w < W2; w += RS_THREADS) {
+            const uint32_t a0 = acc[2 * w], a1 = (2 * w + 1 < W) ? acc[2 * w + 1] : 0u, e = ext[w];
+            if (a0) {
+                my_npos[2 * w] += a0 >> RS_SHIFT;
+                my_s1[2 * w] += a0 & ((1u << RS_SHIFT) - 1u);
+                acc[2 * w] = 0;
+            }
+            if (a1) {
+                my_npos[2 * w + 1] += a1 >> RS_SHIFT;
+                my_s1[2 * w + 1] += a1 & ((1u << RS_SHIFT) - 1u);
+                acc[2 * w + 1] = 0;
+            }
+            if (e) {
+                if (e & 0xffffu) my_extra[2 * w] += e & 0xffffu;
+                if (e >> 16) my_extra[2 * w + 1] += e >> 16;
+                ext[w] = 0;
+            }
+        }
+        __syncthreads();
+    };
+    uint32_t pending = 0;  // cells accumulated since the last fold
     while (true) {
         __syncthreads();
         if (threadIdx.x == 0) s_chunk = atomicAdd(next_chunk, 1ull);
         __syncthreads();
         const uint64_t chunk = s_chunk;
         if (chunk >= nchunks) break;
+        if (pending + RS_CHUNK > RS_FOLD_CELLS) {
+            fold();
+            pending = 0;
+        }
+        pending += RS_CHUNK;
         const uint64_t c0 = chunk * RS_CHUNK;
         const uint64_t c1 = (c0 + RS_CHUNK) < ncells ? (c0 + RS_CHUNK) : ncells;
         // the chunk's cells are consecutive columns: one contiguous nnz range, walked by all warps together
@@ -108,32 +143,25 @@ __global__ void __launch_bounds__(RS_THREADS, 1) k_row_stats_int(const uint64_t*
                     const uint64_t cu = c + 4ull * RS_THREADS * u;
                     const uint32_t ge[4] = {gq[u].x, gq[u].y, gq[u].z, gq[u].w};
                     const float ve[4] = {vq[u].x, vq[u].y, vq[u].z, vq[u].w};
+                    if (cu >= lo && cu + 3 < hi) {  // interior group: no per-entry range test
 #pragma unroll
-                    for (int e = 0; e < 4; ++e)
-                        if (cu + e >= lo && cu + e < hi) one(ge[e], ve[e]);
+                        for (int e = 0; e < 4; ++e) one(ge[e], ve[e]);
+                    } else {
+#pragma unroll
+                        for (int e = 0; e < 4; ++e)
+                            if (cu + e >= lo && cu + e < hi) one(ge[e], ve[e]);
+                    }
                 }
             }
         } else {
             for (uint64_t t = lo + threadIdx.x; t < hi; t += RS_THREADS) one(__ldg(indices + t), __ldg(values + t));
         }
-        __syncthreads();
-        for (uint32_t g = threadIdx.x; g < W; g += RS_THREADS) {
-            const uint32_t v = acc[g];
-            if (v) {
-                my_npos[g] += v >> RS_S1_BITS;
-                my_s1[g] += v & ((1u << RS_S1_BITS) - 1u);
-                acc[g] = 0;
-            }
-        }
     }
-    (void)lane;
-    (void)warp;
-    (void)nwarp;
+    fold();
 }
 
-__global__ void k_row_stats_finish(const unsigned long long* __restrict__ slab_npos,
-                                   const unsigned long long* __restrict__ slab_s1,
-                                   const unsigned long long* __restrict__ extra, uint64_t D, uint32_t nslab,
+__global__ void k_row_stats_finish(const uint32_t* __restrict__ slab_npos, const unsigned long long* __restrict__ slab_s1,
+                                   const unsigned long long* __restrict__ slab_extra, uint64_t D, uint32_t nslab,
                                    double* __restrict__ npos, double* __restrict__ s1, double* __restrict__ s2) {
     const uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (g >= D) return;
@@ -141,13 +169,14 @@ __global__ void k_row_stats_finish(const unsigned long long* __restrict__ slab_n
     for (uint32_t s = 0; s < nslab; ++s) {
         a += slab_npos[(size_t)s * D + g];
         b += slab_s1[(size_t)s * D + g];
+        x += slab_extra[(size_t)s * D + g];
     }
-    for (int r = 0; r < RS_REPL; ++r) x += extra[(size_t)r * D + g];
     npos[g] = (double)a;
     s1[g] = (double)b;
     s2[g] = (double)(b + x);
 }
 
+constexpr int RS_REPL = 8;  // replicas of the f64 accumulators (spreads same-address atomics)
 // general values: f64 atomics on replicated accumulators (sums agree to ~1e-16 relative run to run; non-finite skipped)
 __global__ void __launch_bounds__(256) k_row_stats_f64(const uint32_t* __restrict__ indices, const float* __restrict__ values,
                                                        uint64_t nnz, uint64_t D, double* __restrict__ rep) {
@@ -206,32 +235,34 @@ extern "C" int lg_row_stats(lg_ctx* ctx, const lg_csc* m, double* out_npos, doub
     }
     if (m->int_valued == 1) {
         const uint32_t nslab = (uint32_t)ctx->num_sms;
-        unsigned long long *d_slab_npos, *d_slab_s1, *d_extra, *d_next;
+        uint32_t* d_slab_npos;
+        unsigned long long *d_slab_s1, *d_slab_extra, *d_next;
         LG_TRY(st.scratch((size_t)nslab * D, &d_slab_npos));
         LG_TRY(st.scratch((size_t)nslab * D, &d_slab_s1));
-        LG_TRY(st.scratch((size_t)RS_REPL * D, &d_extra));
+        LG_TRY(st.scratch((size_t)nslab * D, &d_slab_extra));
         LG_TRY(st.scratch(1, &d_next));
-        LG_CUDA(ctx, cudaMemsetAsync(d_slab_npos, 0, (size_t)nslab * D * 8, ctx->stream));
+        LG_CUDA(ctx, cudaMemsetAsync(d_slab_npos, 0, (size_t)nslab * D * 4, ctx->stream));
         LG_CUDA(ctx, cudaMemsetAsync(d_slab_s1, 0, (size_t)nslab * D * 8, ctx->stream));
-        LG_CUDA(ctx, cudaMemsetAsync(d_extra, 0, (size_t)RS_REPL * D * 8, ctx->stream));
-        const uint32_t Wmax = (uint32_t)((ctx->smem_optin - 1024) / sizeof(uint32_t));
+        LG_CUDA(ctx, cudaMemsetAsync(d_slab_extra, 0, (size_t)nslab * D * 8, ctx->stream));
+        // 6 bytes of shared memory per gene: one pass when the gene axis fits (D <= ~38k), else gene windows
+        const uint32_t Wmax = (uint32_t)(((ctx->smem_optin - 1024) / 6) & ~1ull);
         const bool vec = (((uintptr_t)m->indices | (uintptr_t)m->values) & 15) == 0;
-        for (uint64_t g0 = 0; g0 < D; g0 += Wmax) {  // one pass when the gene axis fits (D <= ~57k), else gene windows
+        for (uint64_t g0 = 0; g0 < D; g0 += Wmax) {
             const uint32_t W = (uint32_t)((D - g0) < Wmax ? (D - g0) : Wmax);
-            const size_t smem = (size_t)W * sizeof(uint32_t);
+            const size_t smem = ((size_t)((W + 1) & ~1u) + ((W + 1) >> 1)) * sizeof(uint32_t);
             LG_CUDA(ctx, cudaMemsetAsync(d_next, 0, sizeof(unsigned long long), ctx->stream));
             if (vec) {
                 LG_CUDA(ctx, cudaFuncSetAttribute(k_row_stats_int<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
                 LG_LAUNCH(ctx, k_row_stats_int<true>, nslab, RS_THREADS, smem, m->indptr, m->indices, m->values, m->nnz, N, D,
-                          (uint32_t)g0, W, d_slab_npos, d_slab_s1, d_extra, d_next);
+                          (uint32_t)g0, W, d_slab_npos, d_slab_s1, d_slab_extra, d_next);
             } else {
                 LG_CUDA(ctx, cudaFuncSetAttribute(k_row_stats_int<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
                 LG_LAUNCH(ctx, k_row_stats_int<false>, nslab, RS_THREADS, smem, m->indptr, m->indices, m->values, m->nnz, N, D,
-                          (uint32_t)g0, W, d_slab_npos, d_slab_s1, d_extra, d_next);
+                          (uint32_t)g0, W, d_slab_npos, d_slab_s1, d_slab_extra, d_next);
             }
         }
-        LG_LAUNCH(ctx, k_row_stats_finish, (unsigned)((D + 255) / 256), 256, 0, d_slab_npos, d_slab_s1, d_extra, D, nslab, d_npos,
-                  d_s1, d_s2);
+        LG_LAUNCH(ctx, k_row_stats_finish, (unsigned)((D + 255) / 256), 256, 0, d_slab_npos, d_slab_s1, d_slab_extra, D, nslab,
+                  d_npos, d_s1, d_s2);
     } else {
         double* d_rep;
         LG_TRY(st.scratch((size_t)RS_REPL * 3 * D, &d_rep));

@@ -154,6 +154,28 @@ class HotPath:
         self.ex.sum_(n_bs)
         return sum_db, n_bs
 
+    # ---- either side of the path ------------------------------------------------
+    def row_stats(self, block: CscBlock):
+        """streaming_sparse_running_stats over every shard (sparse_streaming.rs:23-60): (npos, s1, s2) as f64 (D,)
+        tensors + the global column count.  Count data gives exact whole numbers, so the all-reduce(sum) returns the
+        same totals for any GPU count (merge = add, sparse_stat.rs:183-196)."""
+        ctx = self.ctx
+        out = torch.empty((3, block.nrows), dtype=torch.float64, device=self.dev)
+        ctx.check(lib.lg_row_stats(ctx.h, block.h, _ptr(out[0]), _ptr(out[1]), _ptr(out[2])))
+        self.ex.sum_(out)
+        return out[0], out[1], out[2], self._total(block.ncols)
+
+    def nystrom_project(self, block: CscBlock, basis_dk: torch.Tensor, delta_dp=None, pb_of_cell=None, column_sum_norm=1e4):
+        """nystrom_proj_visitor (senna/src/svd/fit.rs:433-466): cells are independent, every rank projects its own
+        shard against the replicated basis / delta; no exchange"""
+        ctx = self.ctx
+        K = int(basis_dk.shape[0])
+        P = 0 if delta_dp is None else int(delta_dp.shape[0])
+        out = torch.empty((block.ncols, K), dtype=torch.float32, device=self.dev)
+        ctx.check(lib.lg_nystrom_project(ctx.h, block.h, _ptr(basis_dk), K, _ptr(delta_dp),
+                                         _ptr(pb_of_cell) if delta_dp is not None else None, P, float(column_sum_norm), _ptr(out)))
+        return out
+
     # ---- stage 5 -----------------------------------------------------------------------------------
     def optimize_single(self, sum_ds: torch.Tensor, size_s: torch.Tensor, a0=1.0, b0=1.0, target=TARGET_ALL):
         """stats.rs:351-368 (replicated on every rank after the all-reduce)"""

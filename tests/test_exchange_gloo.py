@@ -103,6 +103,24 @@ def _case_collapse_allreduce(ex, shard_range):
     assert np.array_equal(t.numpy(), want) and np.array_equal(ts.numpy(), wsize)
 
 
+def _case_row_stats_allreduce(ex, shard_range):
+    """K10: per-shard (npos, s1, s2) held as f64 whole numbers, all-reduced, equal the unsharded statistics bit for bit
+    (merge = add, sparse_stat.rs:183-196)"""
+    import oracle as orc
+    from util import random_csc
+    D, N = 150, 2300
+    rng = np.random.default_rng(3)
+    ip, ix, v = random_csc(rng, D, N, 0.12)
+    want = orc.row_stats(ip, ix, v, D)
+    lo, hi = shard_range(N, ex.rank, ex.world)
+    sl = slice(int(ip[lo]), int(ip[hi]))
+    part = orc.row_stats(ip[lo:hi + 1] - ip[lo], ix[sl], v[sl], D)
+    t = torch.from_numpy(np.stack(part).astype(np.float64))
+    ex.sum_(t)
+    assert all(np.array_equal(t[k].numpy().astype(np.float32), want[k]) for k in range(3))
+    assert ex.total(hi - lo, "cpu") == N
+
+
 def _case_knn_shard_merge(ex, shard_range):
     """K7: reference cells sharded, queries all-gathered, k-lists sent home and merged by (squared distance,
     lower global index): identical to one exact search over all reference cells, ties included"""
@@ -198,7 +216,7 @@ def _case_min_keys_allreduce(ex, shard_range):
 
 
 @pytest.mark.parametrize("case", ["scalars", "block_partials", "collapse_allreduce", "knn_shard_merge", "centroid_fold_chain",
-                                  "min_keys_allreduce"])
+                                  "min_keys_allreduce", "row_stats_allreduce"])
 def test_two_gloo_ranks(case):
     _run(case)
 

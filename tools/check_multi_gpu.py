@@ -43,6 +43,11 @@ excl = torch.arange(lo, lo + q_local.shape[0], dtype=torch.int32, device=dev)
 kidx, kdist = hp.knn_topk_sharded(out["proj"], q_local, k, excl)
 # pb-sample arm of the cross-batch adjustment over the shards
 pbs = hp.pb_matched_stat(blk, out["proj"], out["group"], out["num_groups"], batch, B, 5)
+# the nnz streams either side of the path: per-gene statistics (all-reduced) and the Nystrom re-projection (no exchange)
+rs = hp.row_stats(blk)
+ny_basis = torch.from_numpy(np.random.default_rng(1).standard_normal((20, D)).astype(np.float32)).to(dev)
+ny_delta = (out["posterior"]["mean"] / out["posterior"]["mean"].mean(0, keepdim=True).clamp_min(1e-8)).contiguous()
+ny = hp.nystrom_project(blk, ny_basis, ny_delta, out["group"])
 torch.cuda.synchronize()
 
 report = {"world": world, "cells": N, "genes": D}
@@ -50,7 +55,7 @@ if world > 1:
     # rank 0 recomputes everything unsharded on its own GPU (no collectives) and compares with the gathered shards
     gathered = {}
     for name, t in (("proj", out["proj"]), ("codes", out["codes"]), ("group", out["group"]), ("kidx", kidx), ("kdist", kdist),
-                    ("c2p", pbs["cell_to_pb"])):
+                    ("c2p", pbs["cell_to_pb"]), ("ny", ny)):
         rows, cnt = hp.ex.all_gather_rows(t.contiguous())
         gathered[name] = (rows, cnt)
     if rank == 0:
@@ -90,6 +95,9 @@ if world > 1:
         report["pb_matches_bit_exact"] = same(pbs["matched_pb"], rpb["matched_pb"]) and same(pbs["matched_dist"], rpb["matched_dist"])
         report["pb_matched_stat_bit_exact"] = (same(pbs["imputed_sum_ds"], rpb["imputed_sum_ds"])
                                                and same(pbs["residual_sum_ds"], rpb["residual_sum_ds"]))
+        rrs = solo.row_stats(fblk)
+        report["row_stats_bit_exact"] = all(same(rs[i], rrs[i]) for i in range(3)) and rs[3] == rrs[3]
+        report["nystrom_bit_exact"] = same(gathered["ny"][0], solo.nystrom_project(fblk, ny_basis, ny_delta, ref["group"]))
         report["knn_idx_bit_exact"] = same(gathered["kidx"][0], widx)
         report["knn_dist_bit_exact"] = same(gathered["kdist"][0], wdist)
         report["ok"] = all(v for key, v in report.items() if key.endswith("bit_exact"))
