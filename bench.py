@@ -380,6 +380,7 @@ def main():
         e2e_step()
         sync_all()
         esteps = min(args.steps, 3)
+        wire0 = ctx.h2d_bytes
         t0 = time.perf_counter()
         a, b2 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record()
@@ -393,7 +394,11 @@ def main():
             dist.all_reduce(ems, op=dist.ReduceOp.MAX)
         e2e = {"value": e2e_cells * world / (float(ems.item()) * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(h2d),
                "d2h_bytes_per_step": int(d2h[0]), "cells_per_gpu": int(e2e_cells), "ms_per_step": float(ems.item()),
-               "steps": esteps}
+               "steps": esteps,
+               # h2d_bytes_per_step is the size of the pinned host arrays handed to the C ABI (u64 indptr / u64 indices /
+               # f32 values + basis); lg_csc_upload narrows the indices and packs count values on the host cores before
+               # they travel, so fewer bytes cross the link:
+               "h2d_wire_bytes_per_step": int((ctx.h2d_bytes - wire0) // esteps + h_basis.numel() * 4)}
         del h_ip, h_ix, h_v
 
     # ---- CPU baseline beside it (rank 0, N = 1 only) ----

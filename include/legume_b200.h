@@ -56,6 +56,9 @@ int lg_ctx_set_stream(lg_ctx* ctx, void* cuda_stream);
 int lg_ctx_sync(lg_ctx* ctx);
 /* number of kernels this library launched through ctx since creation */
 uint64_t lg_ctx_launch_count(const lg_ctx* ctx);
+/* bytes lg_csc_upload has put on the host->device link through ctx since creation (host arrays are narrowed /
+ * packed before they travel, so this is less than the size of the arrays handed in) */
+uint64_t lg_ctx_h2d_bytes(const lg_ctx* ctx);
 const char* lg_version(void);
 
 /* ---- data feed --------------------------------------------------------------------------

@@ -253,6 +253,60 @@ struct MultilevelParams {
 };
 
 // data-beans/src/sparse_io_vector: one preloaded backend's columns on the device + the derived caches (mod.rs:70-85)
+// matrix-util/src/sparse_stat.rs:33-198, 404-431 with T = f32.  The sufficient statistics are kept as f64 (exact whole
+// numbers for count data: blocks and shards merge to the same totals in any order) and narrowed by the accessors.
+class SparseRunningStatistics {
+   public:
+    explicit SparseRunningStatistics(size_t nrows) : npos_(nrows, 0.0), s1_(nrows, 0.0), s2_(nrows, 0.0) {}
+    size_t nrows() const { return npos_.size(); }
+    size_t ncols_processed() const { return ncols_; }
+    // add_csc over a device-resident block (:97-108)
+    void add_block(const Context& ctx, const lg_csc* block) {
+        uint64_t D = 0, N = 0, nnz = 0;
+        ctx.check(lg_csc_shape(block, &D, &N, &nnz));
+        if (D != npos_.size()) throw Error(LG_ERR_INVALID, "SparseRunningStatistics: row count mismatch");
+        std::vector<double> a(D), b(D), c(D);
+        ctx.check(lg_row_stats(ctx.get(), block, a.data(), b.data(), c.data()));
+        for (size_t g = 0; g < D; ++g) {
+            npos_[g] += a[g];
+            s1_[g] += b[g];
+            s2_[g] += c[g];
+        }
+        ncols_ += N;
+    }
+    void merge(const SparseRunningStatistics& o) {  // :183-196
+        for (size_t g = 0; g < npos_.size(); ++g) {
+            npos_[g] += o.npos_[g];
+            s1_[g] += o.s1_[g];
+            s2_[g] += o.s2_[g];
+        }
+        ncols_ += o.ncols_;
+    }
+    std::vector<float> count_positives() const { return narrow(npos_); }
+    std::vector<float> sum() const { return narrow(s1_); }
+    std::vector<float> mean() const {
+        std::vector<float> m = narrow(s1_);
+        for (auto& x : m) x /= denom();
+        return m;
+    }
+    std::vector<float> variance() const {  // s2 / n - mean^2 (:417-427)
+        std::vector<float> v = narrow(s2_), m = mean();
+        for (size_t g = 0; g < v.size(); ++g) v[g] = v[g] / denom() - m[g] * m[g];
+        return v;
+    }
+    std::vector<float> std() const {
+        std::vector<float> v = variance();
+        for (auto& x : v) x = std::sqrt(x);
+        return v;
+    }
+
+   private:
+    float denom() const { return ncols_ > 0 ? (float)ncols_ : 1e-8f; }  // safe_denom (:16-23)
+    static std::vector<float> narrow(const std::vector<double>& v) { return std::vector<float>(v.begin(), v.end()); }
+    std::vector<double> npos_, s1_, s2_;
+    size_t ncols_ = 0;
+};
+
 class SparseIoVec {
    public:
     // SparseIo::csc_column_arrays() -> (&[u64] indptr, &[u64] indices, &[f32] data)   (sparse_io/traits.rs:98-100)
@@ -365,6 +419,25 @@ class SparseIoVec {
         ctx_.check(lg_collapse_batch(ctx_.get(), csc_, get_group_membership().data(), col_to_batch_.data(), mult(),
                                      (uint32_t)stat.num_samples(), (uint32_t)stat.num_batches(), stat.observed_sum_db.data.data(),
                                      stat.n_bs.data.data()));
+    }
+    // ---- the nnz streams either side of the path ----
+    // data-beans-alg/src/sparse_streaming.rs:23-60
+    SparseRunningStatistics streaming_sparse_running_stats(std::optional<size_t> block_size = std::nullopt) const {
+        (void)block_size;
+        SparseRunningStatistics st(nrows_);
+        st.add_block(ctx_, csc_);
+        return st;
+    }
+    // nystrom_proj_visitor over every column (senna/src/svd/fit.rs:433-466); the pseudobulk of a cell is its group.
+    // basis_dk: D x K; delta_dp: D x P or nullptr; returns K x N
+    DMatrix nystrom_project(const DMatrix& basis_dk, const DMatrix* delta_dp = nullptr, float column_sum_norm = 1e4f) const {
+        if (basis_dk.nrows != nrows_) throw Error(LG_ERR_INVALID, "nystrom_project: basis rows mismatch the number of genes");
+        if (delta_dp && delta_dp->nrows != nrows_) throw Error(LG_ERR_INVALID, "nystrom_project: delta rows mismatch the number of genes");
+        DMatrix out(basis_dk.ncols, ncols_);
+        ctx_.check(lg_nystrom_project(ctx_.get(), csc_, basis_dk.data.data(), (int)basis_dk.ncols, delta_dp ? delta_dp->data.data() : nullptr,
+                                      delta_dp ? get_group_membership().data() : nullptr, delta_dp ? (uint32_t)delta_dp->ncols : 0u,
+                                      column_sum_norm, out.data.data()));
+        return out;
     }
     // collapse_data/mod.rs:364-383 -> register_batches_dmatrix (batch.rs:46-234): the exact backend needs no index
     template <typename T>

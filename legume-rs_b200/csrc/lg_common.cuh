@@ -17,6 +17,7 @@ struct lg_ctx {
     cudaStream_t stream = nullptr;
     bool own_stream = false;
     uint64_t launches = 0;
+    uint64_t h2d_bytes = 0;  // bytes lg_csc_upload put on the link
     std::string err;
     // pinned staging for small host<->device scalars
     void* pinned = nullptr;

@@ -87,6 +87,7 @@ extern "C" int lg_ctx_sync(lg_ctx* c) {
 }
 
 extern "C" uint64_t lg_ctx_launch_count(const lg_ctx* c) { return c ? c->launches : 0; }
+extern "C" uint64_t lg_ctx_h2d_bytes(const lg_ctx* c) { return c ? c->h2d_bytes : 0; }
 
 // ---- CSC container ----------------------------------------------------------------------------
 // narrow u64 row indices to u32 (optionally through a row remap), flagging out-of-range rows
@@ -296,7 +297,7 @@ cudaError_t upload_narrow_on_host(lg_ctx* ctx, const uint64_t* h_idx, const floa
         cudaError_t e = cudaMallocAsync(&d_bytes, nslots * (UP_CHUNK + UP_PATCH_BYTES), ctx->stream);
         if (e != cudaSuccess) return e;
     }
-    std::atomic<uint64_t> extra_launches{0}, packed_chunks{0};
+    std::atomic<uint64_t> extra_launches{0}, packed_chunks{0}, wire{0};
     std::vector<std::atomic<int>> queued(nchunks);
     for (auto& q : queued) q.store(0, std::memory_order_relaxed);
     // claim word: low 32 bits = chunks taken from the front, high 32 bits = chunks taken from the back
@@ -324,7 +325,7 @@ cudaError_t upload_narrow_on_host(lg_ctx* ctx, const uint64_t* h_idx, const floa
     const bool avx2 = __builtin_cpu_supports("avx2");
     auto worker = [&]() {
         cudaSetDevice(ctx->device);
-        uint64_t my_or = 0, my_launches = 0, my_packed = 0;
+        uint64_t my_or = 0, my_launches = 0, my_packed = 0, my_wire = 0;
         uint32_t my_max = 0;
         uint64_t i;
         while (take(true, &i)) {
@@ -345,6 +346,7 @@ cudaError_t upload_narrow_on_host(lg_ctx* ctx, const uint64_t* h_idx, const floa
                 if (npatch >= 0) {
                     uint8_t* dv = d_bytes + slot * (UP_CHUNK + UP_PATCH_BYTES);
                     e = cudaMemcpyAsync(dv, vdst, len, cudaMemcpyHostToDevice, ctx->stream);
+                    my_wire += len + (uint64_t)npatch * sizeof(UpPatch);
                     if (e == cudaSuccess && npatch)
                         e = cudaMemcpyAsync(dv + UP_CHUNK, pdst, (size_t)npatch * sizeof(UpPatch), cudaMemcpyHostToDevice, ctx->stream);
                     if (e == cudaSuccess) {
@@ -356,18 +358,21 @@ cudaError_t upload_narrow_on_host(lg_ctx* ctx, const uint64_t* h_idx, const floa
                     }
                 } else {
                     e = cudaMemcpyAsync(d_val + off, h_val + off, len * sizeof(float), cudaMemcpyHostToDevice, ctx->stream);
+                    my_wire += len * sizeof(float);
                 }
             }
             if (avx2) narrow_chunk_avx2(h_idx + off, dst, len, &my_or, &my_max);
             else narrow_chunk_plain(h_idx + off, dst, len, &my_or, &my_max);
             if (e == cudaSuccess)
                 e = cudaMemcpyAsync(d_idx + off, dst, len * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream);
+            my_wire += len * sizeof(uint32_t);
             if (e == cudaSuccess) e = cudaEventRecord(ctx->ring_ev[slot], ctx->stream);
             note(e);
             queued[i].store(1, std::memory_order_release);  // set even on error so nobody waits forever
         }
         or_all.fetch_or(my_or);
         extra_launches.fetch_add(my_launches);
+        wire.fetch_add(my_wire);
         packed_chunks.fetch_add(my_packed);
         uint32_t cur = max_lo.load();
         while (my_max > cur && !max_lo.compare_exchange_weak(cur, my_max)) {}
@@ -402,10 +407,12 @@ cudaError_t upload_narrow_on_host(lg_ctx* ctx, const uint64_t* h_idx, const floa
             }
             if (e == cudaSuccess) e = cudaEventRecord(ctx->ring_ev[nslots + (nwide & 1)], ctx->stream);
             ++nwide;
+            wire.fetch_add(len * (sizeof(float) + sizeof(uint64_t)));
         }
         note(e);
         for (auto& t : pool) t.join();
         ctx->launches += extra_launches.load();
+        ctx->h2d_bytes += wire.load();
         if (d_bytes) cudaFreeAsync(d_bytes, ctx->stream);
         if (d_flag) {
             note(cudaMemcpyAsync(&h_flag, d_flag, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
@@ -468,6 +475,7 @@ extern "C" int lg_csc_upload(lg_ctx* ctx, const uint64_t* indptr, const uint64_t
         uint64_t* tmp = nullptr;
         UP_CUDA(cudaMallocAsync(&tmp, (ncols + 1) * sizeof(uint64_t), st));
         UP_CUDA(cudaMemcpyAsync(tmp, indptr + col_lo, (ncols + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
+        ctx->h2d_bytes += (ncols + 1) * sizeof(uint64_t);
         k_rebase_indptr<<<(unsigned)((ncols + 1 + 255) / 256), 256, 0, st>>>(tmp, m->indptr, ncols + 1, base);
         ctx->launches++;
         UP_CUDA(cudaGetLastError());
@@ -484,6 +492,7 @@ extern "C" int lg_csc_upload(lg_ctx* ctx, const uint64_t* indptr, const uint64_t
         }
     } else if (nnz) {
         UP_CUDA(cudaMemcpyAsync(m->values, data + base, nnz * sizeof(float), cudaMemcpyHostToDevice, st));
+        ctx->h2d_bytes += nnz * (sizeof(float) + sizeof(uint64_t));
         const uint32_t* d_remap = nullptr;
         uint32_t* remap_buf = nullptr;
         uint64_t nrows_in = nrows;

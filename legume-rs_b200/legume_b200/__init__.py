@@ -103,6 +103,11 @@ class Context:
     def launch_count(self) -> int:
         return int(lib.lg_ctx_launch_count(self.h))
 
+    @property
+    def h2d_bytes(self) -> int:
+        """bytes lg_csc_upload has put on the host->device link"""
+        return int(lib.lg_ctx_h2d_bytes(self.h))
+
     def empty(self, shape, dtype, device: bool):
         """allocate an output next to the inputs (torch CUDA tensor or numpy array)"""
         if device:

@@ -212,6 +212,30 @@ int main() {
         CHECK(close_all(levels[0].mu_adjusted->mean.data.data(), mu_adj.data(), mu_adj.size(), 1e-4));
         CHECK(close_all(levels[0].delta->mean.data.data(), delta.data(), delta.size(), 1e-4));
     }
+    {  // ---- either side of the path: running statistics (sparse_stat.rs:671-728) and the Nystrom pass ----
+        std::mt19937 rng21(21);
+        Csc m = random_counts(rng21, 300, 500, 0.1);
+        SparseIoVec x(ctx, m.indptr, m.indices, m.data, 300);
+        SparseRunningStatistics st = x.streaming_sparse_running_stats();
+        std::vector<float> npos(300), s1(300), s2(300), mean(300), var(300), sd(300);
+        orc_row_stats(m.indptr.data(), m.indices.data(), m.data.data(), 300, 500, npos.data(), s1.data(), s2.data());
+        orc_row_stats_moments(s1.data(), s2.data(), 300, 500, mean.data(), var.data(), sd.data());
+        CHECK(st.ncols_processed() == 500 && st.count_positives() == npos && st.sum() == s1);
+        CHECK(st.mean() == mean && st.variance() == var);
+        // reference's own known answer: columns [1,0,2,0] and [0,3,0,4] -> npos 1,1,1,1, sum 1,3,2,4, mean .5,1.5,1,2
+        SparseIoVec tiny(ctx, std::vector<uint64_t>{0, 2, 4}, std::vector<uint64_t>{0, 2, 1, 3}, std::vector<float>{1, 2, 3, 4}, 4);
+        SparseRunningStatistics ts = tiny.streaming_sparse_running_stats();
+        CHECK((ts.count_positives() == std::vector<float>{1, 1, 1, 1}) && (ts.sum() == std::vector<float>{1, 3, 2, 4}) &&
+              (ts.mean() == std::vector<float>{0.5f, 1.5f, 1.0f, 2.0f}));
+        DMatrix basis(300, 12);
+        for (size_t i = 0; i < basis.data.size(); ++i) basis.data[i] = std::sin(0.37f * (float)i);
+        DMatrix ny = x.nystrom_project(basis);
+        std::vector<float> want(12 * 500);
+        orc_nystrom_project(m.indptr.data(), m.indices.data(), m.data.data(), 300, 500, basis.data.data(), 12, nullptr, nullptr, 0, 1e4f,
+                            want.data());
+        // the reference's f32 folds (the oracle) sit up to ~5e-4 from exact arithmetic here; see tests/test_gpu_next.py
+        CHECK(ny.nrows == 12 && ny.ncols == 500 && close_all(ny.data.data(), want.data(), want.size(), 2e-3));
+    }
     {  // ---- error behaviour: anyhow::Error -> legume::Error, never a crash ----
         bool threw = false;
         try {
