@@ -11,8 +11,8 @@
 //   proj_raw[:, j] = ( ln2 * sum_{i in nnz(j)} B[i, :]  +  sum_{i: y_ij != 1} (ln(1+y_ij) - ln2) B[i, :] ) / ||x_j||
 //                       `---- K1a: tcgen05 kind::i8 ----'   `---- K1b: CUDA cores, the few counts > 1 ----'
 //
-//   * the basis is quantised to 2^-20 fixed point and split into three signed 8-bit digits
-//     (N = 3K columns of the B operand); |B| < 7.97 is required, else the caller falls back.
+//   * the basis is quantised to 2^-20 fixed point (after a per-column power-of-two scale that brings the column's
+//     largest magnitude to [4, 7.96)) and split into three signed 8-bit digits (N = 3K columns of the B operand).
 //   * K1b (k_project_prep, one warp per cell, one coalesced pass over indices AND values) writes the
 //     sparsity pattern as a bitmap (1 bit per gene: smaller than the u32 index stream above 3% density),
 //     tiled per (256 cells x 2048 genes) so the tensor kernel fetches it with one bulk copy per chunk,
@@ -58,10 +58,33 @@ struct Barriers {
 };
 
 // ---- basis -> three signed base-256 digits, laid out as the UMMA B operand ---------------------
+// Every basis column (dim) gets its own power-of-two scale 2^e so that its largest magnitude lands in [4, 7.96) of the
+// 2^-20 fixed-point grid: a relative resolution of ~1e-7 of the column's range whatever its size (row-weighted bases,
+// U / sigma of a Nystrom basis), exact to undo in the epilogue.  A standard-normal basis keeps e = 0.
+__global__ void k_basis_colmax(const float* __restrict__ basis_kd, uint64_t D, int K, unsigned int* __restrict__ colmax_bits) {
+    const uint64_t e = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= D * (uint64_t)K) return;
+    const float a = fabsf(basis_kd[e]);
+    // non-negative floats order as uints; NaN (0x7fc00000) and +inf (0x7f800000) come out on top and are caught below
+    atomicMax(&colmax_bits[e % K], __float_as_uint(a));
+}
+// exponent e of the column's scale; sets *bad for a non-finite column
+__device__ __forceinline__ int basis_col_exp(unsigned int max_bits, int* bad) {
+    const float m = __uint_as_float(max_bits);
+    if (!(m <= 3.0e38f)) {
+        if (bad) *bad = 1;
+        return 0;
+    }
+    if (m == 0.0f) return 0;
+    int e = 2 - ilogbf(m);                       // m * 2^e in [4, 8)
+    if (ldexpf(m, e) >= 7.96f) --e;              // keep clear of the largest three-digit value
+    return e < -100 ? -100 : (e > 100 ? 100 : e);
+}
 // chunk = 32 genes x NB columns in the K-major no-swizzle canonical form:
 //   byte(n, k) = (n/8)*256 + (k/16)*128 + (n%8)*16 + (k%16),  n = digit*K + dim
 __global__ void k_quantize_basis(const float* __restrict__ basis_kd, uint64_t D, int K, int NB, uint64_t Dpad,
-                                 int8_t* __restrict__ bq, int* __restrict__ too_large) {
+                                 const unsigned int* __restrict__ colmax_bits, int8_t* __restrict__ bq,
+                                 int* __restrict__ too_large) {
     const uint64_t e = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= Dpad * (uint64_t)NB) return;
     const uint64_t gene = e / NB;
@@ -70,7 +93,7 @@ __global__ void k_quantize_basis(const float* __restrict__ basis_kd, uint64_t D,
     int8_t out = 0;
     if (gene < D && digit < 3) {
         const float b = basis_kd[gene * K + dim];
-        const float qf = rintf(b * QSCALE);
+        const float qf = rintf(ldexpf(b, 20 + basis_col_exp(colmax_bits[dim], too_large)));
         if (!(fabsf(qf) <= (float)QMAX)) atomicOr(too_large, 1);
         int q = (int)fminf(fmaxf(qf, -(float)QMAX), (float)QMAX);
         int d0 = ((q + 128) & 255) - 128;
@@ -336,7 +359,8 @@ __global__ void __launch_bounds__(PREP_WARPS * 32, 4) k_project_prep(const uint6
 // ---- K1a: the tcgen05 kernel -----------------------------------------------------------------
 __global__ void __launch_bounds__(THREADS, 1) k_project_umma(const uint32_t* __restrict__ bm_global, uint64_t ncols, uint64_t D,
                                                              const int8_t* __restrict__ bq, int K, int NB, uint32_t nstages,
-                                                             const float* __restrict__ scale, float* __restrict__ out) {
+                                                             const float* __restrict__ scale,
+                                                             const unsigned int* __restrict__ colmax_bits, float* __restrict__ out) {
     extern __shared__ __align__(1024) uint8_t smem[];
     // carve: [B ring][bitmap x NBM][barriers][tmem base]
     const uint32_t stage_bytes = (uint32_t)NB * 32u * (GS / 32);
@@ -344,6 +368,8 @@ __global__ void __launch_bounds__(THREADS, 1) k_project_umma(const uint32_t* __r
     uint32_t* bitmap = reinterpret_cast<uint32_t*>(smem + (size_t)NBST * stage_bytes);
     Barriers* bars = reinterpret_cast<Barriers*>(bitmap + NBM * CELLS * BM_STRIDE);
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 1);
+    __shared__ double col_inv[64];  // 1 / (A scale 128 * 2^20 * 2^e) per basis column: an exact power of two
+    if (threadIdx.x < 64) col_inv[threadIdx.x] = threadIdx.x < K ? ldexp(1.0, -(27 + basis_col_exp(colmax_bits[threadIdx.x], nullptr))) : 0.0;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t nchunks = (uint32_t)((D + GC - 1) / GC);
@@ -454,9 +480,9 @@ __global__ void __launch_bounds__(THREADS, 1) k_project_umma(const uint32_t* __r
                         float res[16];
 #pragma unroll
                         for (int i = 0; i < 16; ++i) {
-                            // digits carry the A scale of 128: total = 128 * sum(q_i), q in 2^-20 units
+                            // digits carry the A scale of 128: total = 128 * sum(q_i), q in 2^-(20 + e) units of column kb + i
                             const long long tot = ((long long)(int)d2[i] << 16) + ((long long)(int)d1[i] << 8) + (long long)(int)d0[i];
-                            const float sv = (float)((double)tot * (1.0 / (128.0 * 1048576.0)));
+                            const float sv = (float)((double)tot * col_inv[kb + i]);
                             res[i] = fmaf(sv, sc, corr[kb + i]);
                         }
                         if (pair_io) {
@@ -552,15 +578,20 @@ int lg_project_raw_umma(lg_ctx* ctx, const lg_csc* m, const float* d_basis, int 
     LG_TRY(st.scratch((size_t)Dpad * NB, &d_bq));
     LG_TRY(st.scratch(1, &d_flag));
     LG_TRY(st.scratch((size_t)m->ncols, &d_scale));
+    unsigned int* d_colmax;
+    LG_TRY(st.scratch(64, &d_colmax));
     LG_CUDA(ctx, cudaMemsetAsync(d_flag, 0, sizeof(int), ctx->stream));
+    LG_CUDA(ctx, cudaMemsetAsync(d_colmax, 0, 64 * sizeof(unsigned int), ctx->stream));
     {
+        const uint64_t nb = D * (uint64_t)K;
+        LG_LAUNCH(ctx, k_basis_colmax, (unsigned)((nb + 255) / 256), 256, 0, d_basis, D, K, d_colmax);
         const uint64_t tot = Dpad * (uint64_t)NB;
-        LG_LAUNCH(ctx, k_quantize_basis, (unsigned)((tot + 255) / 256), 256, 0, d_basis, D, K, NB, Dpad, d_bq, d_flag);
+        LG_LAUNCH(ctx, k_quantize_basis, (unsigned)((tot + 255) / 256), 256, 0, d_basis, D, K, NB, Dpad, d_colmax, d_bq, d_flag);
     }
     int* h_flag = static_cast<int*>(ctx->pinned);
     LG_CUDA(ctx, cudaMemcpyAsync(h_flag, d_flag, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
     LG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    if (*h_flag) return LG_OK;  // basis outside the fixed-point range (e.g. large row weights): fall back
+    if (*h_flag) return LG_OK;  // a non-finite basis column: fall back to the CUDA-core kernel (which propagates it)
 
     const char* tr = getenv("LG_K1_TRACE");
     const bool trace = tr && tr[0] == '1';
@@ -605,7 +636,7 @@ int lg_project_raw_umma(lg_ctx* ctx, const lg_csc* m, const float* d_basis, int 
     LG_CUDA(ctx, cudaFuncSetAttribute(k_project_umma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const unsigned grid = (unsigned)(nsuper < (uint64_t)ctx->num_sms ? nsuper : (uint64_t)ctx->num_sms);
     if (trace) cudaEventRecord(ev[1], ctx->stream);
-    LG_LAUNCH(ctx, k_project_umma, grid, THREADS, smem, d_bm, m->ncols, D, d_bq, K, NB, nstages, d_scale, d_out);
+    LG_LAUNCH(ctx, k_project_umma, grid, THREADS, smem, d_bm, m->ncols, D, d_bq, K, NB, nstages, d_scale, d_colmax, d_out);
     if (trace) {  // LG_K1_TRACE=1: per-kernel device times of this call (diagnostic; synchronises)
         cudaEventRecord(ev[2], ctx->stream);
         cudaEventSynchronize(ev[2]);

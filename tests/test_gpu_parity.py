@@ -148,6 +148,25 @@ def test_project_clamp_branch_and_weights(lg, ctx):
     assert close(gw, orc.project(ip, ix, v, bw), TOL)
 
 
+def test_project_raw_columns_of_very_different_scale(lg, ctx):
+    """the tensor path quantises every basis column on its own power-of-two grid, so a column 1e6 times smaller or 1e4
+    times larger than its neighbours keeps the same RELATIVE accuracy (row-weighted bases, U / sigma of a Nystrom basis)"""
+    rng = np.random.default_rng(12)
+    D, N, K = 3000, 2048, 50
+    ip, ix, v = random_csc(rng, D, N, 0.05)
+    col_scale = (10.0 ** rng.uniform(-6, 4, K)).astype(np.float32)
+    basis = basis_for(D, K) * col_scale[None, :]
+    data = lg.SparseIoVec.from_csc(ctx, ip, ix, v, D)
+    raw = np.empty((N, K), np.float32)
+    ctx.check(lg.lib.lg_project_raw(ctx.h, data.block.h, basis.ctypes.data, K, raw.ctypes.data))
+    want = orc.project_raw(ip, ix, v, basis, 4)
+    assert close(raw / col_scale[None, :], want / col_scale[None, :], TOL), max_err(raw / col_scale, want / col_scale)
+    # a non-finite column cannot be quantised: the call falls back to the CUDA-core kernel and propagates it
+    basis[7, 3] = np.inf
+    ctx.check(lg.lib.lg_project_raw(ctx.h, data.block.h, basis.ctypes.data, K, raw.ctypes.data))
+    assert not np.isfinite(raw[:, 3]).all() and np.isfinite(np.delete(raw, 3, axis=1)).all()
+
+
 def test_project_batch_label_mismatch_skips_centring(lg, ctx):
     rng = np.random.default_rng(4)
     ip, ix, v = random_csc(rng, 200, 300, 0.1)
