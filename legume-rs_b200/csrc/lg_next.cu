@@ -414,6 +414,8 @@ __global__ void __launch_bounds__(NY_WARPS * 32) k_nystrom(const uint64_t* __res
     }
 }
 
+int lg_project_raw_umma(lg_ctx* ctx, const lg_csc* m, const float* d_basis, int K, float* d_out, int* used, int mode, float csn);  // lg_project_umma.cu
+
 // basis_dk (D x K column-major, the reference's DMatrix) -> rows of K contiguous dims
 __global__ void k_transpose_dk(const float* __restrict__ src_dk, uint64_t D, int K, float* __restrict__ dst_kd) {
     const uint64_t e = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -442,6 +444,14 @@ extern "C" int lg_nystrom_project(lg_ctx* ctx, const lg_csc* m, const float* bas
     if (N == 0 || D == 0) return st.finish();
     LG_TRY(st.scratch((size_t)D * K, &d_bt));
     LG_LAUNCH(ctx, k_transpose_dk, (unsigned)((D * K + 255) / 256), 256, 0, d_basis, D, K, d_bt);
+    // without a batch divisor every count of one maps to the same value, so the tensor path of K1 applies: the 0/1
+    // pattern against the quantised basis on tcgen05, the counts above one on CUDA cores (LG_K11_CUDA_CORES=1: A/B runs)
+    const char* force = getenv("LG_K11_CUDA_CORES");
+    if (!d_delta && !(force && force[0] == '1')) {
+        int used = 0;
+        LG_TRY(lg_project_raw_umma(ctx, m, d_bt, K, d_out, &used, 1, column_sum_norm));
+        if (used) return st.finish();
+    }
     uint64_t blocks = (N + NY_WARPS - 1) / NY_WARPS;
     const uint64_t cap = (uint64_t)ctx->num_sms * 32;
     if (blocks > cap) blocks = cap;

@@ -58,7 +58,7 @@ __global__ void __launch_bounds__(256) k_project_raw_warp(const uint64_t* __rest
     }
 }
 
-int lg_project_raw_umma(lg_ctx* ctx, const lg_csc* m, const float* d_basis, int K, float* d_out, int* used);
+int lg_project_raw_umma(lg_ctx* ctx, const lg_csc* m, const float* d_basis, int K, float* d_out, int* used, int mode, float csn);
 
 static int launch_project_raw(lg_ctx* ctx, const lg_csc* m, const float* d_basis, int K, float* d_out) {
     if (m->ncols == 0) return LG_OK;
@@ -66,7 +66,7 @@ static int launch_project_raw(lg_ctx* ctx, const lg_csc* m, const float* d_basis
     const char* force = getenv("LG_K1_CUDA_CORES");
     if (!(force && force[0] == '1')) {
         int used = 0;
-        LG_TRY(lg_project_raw_umma(ctx, m, d_basis, K, d_out, &used));
+        LG_TRY(lg_project_raw_umma(ctx, m, d_basis, K, d_out, &used, 0, 0.0f));
         if (used) return LG_OK;
     }
     const int nacc = (K + 31) / 32;

@@ -122,13 +122,17 @@ constexpr int PREP_LUT = 64;  // log1p look-up for integer counts below this
 // VEC (index / value arrays 16-byte aligned): the aligned interior of a cell's nnz range is read with 128-bit loads (a lane
 // holds 4 consecutive nnz, twice the bytes in flight per warp and a quarter of the load instructions); the <= 3 entries
 // before and after it go through one masked round.
-template <int NACC, bool HALF2, bool VEC>
+// MODE 0: projection (x = ln(1 + y), L2-normalised).  MODE 1: Nystrom re-projection without a batch divisor
+// (senna/src/svd/fit.rs:433-466): x = ln(1 + y * csn / ||y||), standardised over the cell's stored entries; the common
+// value is then z1 = ln(1 + csn / ||y||) and the pattern sum gets the weight (z1 - mean) / sd, so the same two-part
+// split applies with exceptions weighted (x - z1) / sd.  ||y|| needs its own sweep over the cell's values first.
+template <int NACC, bool HALF2, bool VEC, int MODE>
 __global__ void __launch_bounds__(PREP_WARPS * 32, 4) k_project_prep(const uint64_t* __restrict__ indptr,
                                                                      const uint32_t* __restrict__ indices,
                                                                      const float* __restrict__ values, uint64_t ncols,
                                                                      const float* __restrict__ basis_kd, int K, uint32_t nchunks,
                                                                      uint32_t* __restrict__ bm_global, float* __restrict__ out,
-                                                                     float* __restrict__ scale) {
+                                                                     float* __restrict__ scale, float csn) {
     extern __shared__ __align__(16) uint32_t rows[];  // PREP_WARPS bitmap rows, then the exception queues
     __shared__ float lut_x[PREP_LUT];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -152,7 +156,20 @@ __global__ void __launch_bounds__(PREP_WARPS * 32, 4) k_project_prep(const uint6
         float acc[HALF2 ? 4 : NACC];
 #pragma unroll
         for (int a = 0; a < (HALF2 ? 4 : NACC); ++a) acc[a] = 0.0f;
-        float nsq = 0.0f;
+        float nsq = 0.0f;            // MODE 0: sum x^2 over the exceptions
+        double e1 = 0.0, e2 = 0.0;   // MODE 1: sum (x - z1), sum (x - z1)^2 over the exceptions (x - z1 is exact in f32)
+        float a_j = 0.0f, base_x = ln2;  // MODE 1: csn / ||y|| and the common value z1 = ln(1 + a_j)
+        if constexpr (MODE == 1) {
+            float q = 0.0f;
+            for (uint32_t t = lane; t < n; t += 32) {
+                const float y = __ldg(vp + t - lane);
+                q = fmaf(y, y, q);
+            }
+#pragma unroll
+            for (int off = 16; off >= 1; off >>= 1) q += __shfl_xor_sync(0xffffffffu, q, off);
+            a_j = __fdiv_rn(csn, fmaxf(sqrtf(q), 1e-8f));
+            base_x = log1pf(a_j);
+        }
         uint32_t qhead = 0, qtail = 0;  // warp-uniform ring cursors of the exception queue
 
         // entries != 1 are rare in count data: they are queued raw and handled 32 at a time, one queue entry per
@@ -163,10 +180,18 @@ __global__ void __launch_bounds__(PREP_WARPS * 32, 4) k_project_prep(const uint6
             float w = 0.0f;
             if (on) {
                 const float val = qv[(qhead + lane) & (PREP_Q - 1)];
-                const int vi = (int)val;
-                const float x = (val == (float)vi && vi >= 0 && vi < PREP_LUT) ? lut_x[vi] : log1pf(val);
-                nsq = fmaf(x, x, nsq);
-                w = x - ln2;
+                float x;
+                if constexpr (MODE == 1) {
+                    x = log1pf(val * a_j);
+                    w = x - base_x;
+                    e1 += (double)w;
+                    e2 = fma((double)w, (double)w, e2);
+                } else {
+                    const int vi = (int)val;
+                    x = (val == (float)vi && vi >= 0 && vi < PREP_LUT) ? lut_x[vi] : log1pf(val);
+                    nsq = fmaf(x, x, nsq);
+                    w = x - base_x;
+                }
             }
             if constexpr (HALF2) {
                 const int half = lane >> 4, l = lane & 15;
@@ -327,8 +352,22 @@ __global__ void __launch_bounds__(PREP_WARPS * 32, 4) k_project_prep(const uint6
         }
 #pragma unroll
         for (int off = 16; off >= 1; off >>= 1) nsq += __shfl_xor_sync(0xffffffffu, nsq, off);
-        nsq = fmaf((float)n_one, ln2 * ln2, nsq);
-        const float denom = fmaxf(sqrtf(nsq), 1e-8f);
+        float denom, pat_scale;  // out = corr / denom + pattern sum * pat_scale
+        if constexpr (MODE == 1) {
+            e1 = lg_butterfly32(e1);
+            e2 = lg_butterfly32(e2);
+            // moments of d = x - z1 over the stored entries (d = 0 for every count of one): mean = z1 + sum d / n and
+            // sd^2 = sum d^2 / n - (sum d / n)^2 has no cancellation, unlike the reference's s2/n - mean^2
+            const double nn = n > 0 ? (double)n : 1.0;
+            const double md = e1 / nn, var = e2 / nn - md * md;
+            const double inv_sig = var > 1e-12 * (e2 / nn) ? 1.0 / sqrt(var) : 1.0;  // a constant column is only centred
+            denom = (float)(1.0 / inv_sig);
+            pat_scale = (float)(-md * inv_sig);  // (z1 - mean) / sd
+        } else {
+            nsq = fmaf((float)n_one, ln2 * ln2, nsq);
+            denom = fmaxf(sqrtf(nsq), 1e-8f);
+            pat_scale = ln2 / denom;
+        }
         if constexpr (HALF2) {
 #pragma unroll
             for (int a = 0; a < 4; ++a) acc[a] += __shfl_xor_sync(0xffffffffu, acc[a], 16);  // the two half-warps' shares
@@ -351,7 +390,7 @@ __global__ void __launch_bounds__(PREP_WARPS * 32, 4) k_project_prep(const uint6
                 if (k < K) out[(size_t)j * K + k] = acc[a] / denom;
             }
         }
-        if (lane == 0) scale[j] = ln2 / denom;
+        if (lane == 0) scale[j] = pat_scale;
         __syncwarp();
     }
 }
@@ -564,7 +603,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_project_umma(const uint32_t* __r
 }  // namespace
 
 // returns LG_OK and sets *used = 1 when the tensor path ran, *used = 0 when the caller must fall back
-int lg_project_raw_umma(lg_ctx* ctx, const lg_csc* m, const float* d_basis, int K, float* d_out, int* used) {
+int lg_project_raw_umma(lg_ctx* ctx, const lg_csc* m, const float* d_basis, int K, float* d_out, int* used, int mode, float csn) {
     *used = 0;
     const int NB = ((3 * K + 15) / 16) * 16;
     if (K < 1 || NT * NB + NT * NAST * A_COLS > 512 || m->nrows > 131072 || m->ncols == 0 || m->nrows == 0) return LG_OK;
@@ -616,11 +655,16 @@ int lg_project_raw_umma(lg_ctx* ctx, const lg_csc* m, const float* d_basis, int 
         if (blocks > cap) blocks = cap;
         const int nacc = (K + 31) / 32;
         const bool half2 = (K % 2 == 0) && (((uintptr_t)d_basis & 7) == 0);
-#define LG_PREP_LAUNCH(NA, H2, V)                                                                                                   \
-    do {                                                                                                                            \
-        LG_CUDA(ctx, cudaFuncSetAttribute(k_project_prep<NA, H2, V>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psmem));     \
-        LG_LAUNCH(ctx, (k_project_prep<NA, H2, V>), (unsigned)blocks, PREP_WARPS * 32, psmem, m->indptr, m->indices, m->values,   \
-                  m->ncols, d_basis, K, nchunks, d_bm, d_out, d_scale);                                                             \
+#define LG_PREP_LAUNCH_M(NA, H2, V, M)                                                                                                \
+    do {                                                                                                                              \
+        LG_CUDA(ctx, cudaFuncSetAttribute(k_project_prep<NA, H2, V, M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psmem));    \
+        LG_LAUNCH(ctx, (k_project_prep<NA, H2, V, M>), (unsigned)blocks, PREP_WARPS * 32, psmem, m->indptr, m->indices, m->values,  \
+                  m->ncols, d_basis, K, nchunks, d_bm, d_out, d_scale, csn);                                                          \
+    } while (0)
+#define LG_PREP_LAUNCH(NA, H2, V)                 \
+    do {                                          \
+        if (mode == 1) LG_PREP_LAUNCH_M(NA, H2, V, 1); \
+        else LG_PREP_LAUNCH_M(NA, H2, V, 0);      \
     } while (0)
         const bool vec = (((uintptr_t)m->indices | (uintptr_t)m->values) & 15) == 0;
         if (trace) cudaEventRecord(ev[0], ctx->stream);
@@ -629,6 +673,7 @@ int lg_project_raw_umma(lg_ctx* ctx, const lg_csc* m, const float* d_basis, int 
         else if (nacc == 1) LG_PREP_LAUNCH(1, false, false);
         else LG_PREP_LAUNCH(2, false, false);
 #undef LG_PREP_LAUNCH
+#undef LG_PREP_LAUNCH_M
     }
     const size_t stage_bytes = (size_t)NB * 32 * (GS / 32);
     const size_t smem = (size_t)NBST * stage_bytes + (size_t)NBM * BM_CHUNK_BYTES + sizeof(Barriers) + 16;

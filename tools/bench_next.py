@@ -9,7 +9,8 @@ import legume_b200 as lg
 from legume_b200 import sim
 from legume_b200._lib import lib
 
-N = int(sys.argv[1]) if len(sys.argv) > 1 else 1_000_000
+_nums = [a for a in sys.argv[1:] if a.isdigit()]
+N = int(_nums[0]) if _nums else 1_000_000
 D, K, S = 30000, 50, 1024
 peak = 6545.6
 try:
