@@ -260,6 +260,11 @@ int64_t pack_values_plain(const float* s, uint8_t* d, uint64_t n, UpPatch* patch
 int upload_threads() {
     if (const char* e = getenv("LG_UPLOAD_THREADS")) return atoi(e);
     unsigned hc = std::thread::hardware_concurrency();
+    // one process per GPU shares the host cores with its siblings (torchrun exports LOCAL_WORLD_SIZE)
+    if (const char* lw = getenv("LOCAL_WORLD_SIZE")) {
+        const int n = atoi(lw);
+        if (n > 1) hc /= (unsigned)n;
+    }
     if (hc < 4) return 0;  // too few cores to outrun the link: narrow on the device
     return (int)(hc > 16 ? 16 : hc);
 }

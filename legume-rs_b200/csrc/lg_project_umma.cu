@@ -249,16 +249,53 @@ __global__ void __launch_bounds__(PREP_WARPS * 32, 4) k_project_prep(const uint6
             }
         };
 
+        // The queue must fill in ASCENDING POSITION inside the cell whatever the alignment of the cell's first entry:
+        // the drain adds the exceptions in queue order, so any other order would make a cell's projection depend (in
+        // the last bits) on where its column starts in the arrays, i.e. on how the cells were sharded.
+        auto consume4 = [&](const uint4 g, const float4 x, bool live) {
+            if (live) {
+                atomicOr(row + (g.x >> 5), 1u << (((g.x >> 2) & 7) | ((g.x & 3) << 3)));
+                atomicOr(row + (g.y >> 5), 1u << (((g.y >> 2) & 7) | ((g.y & 3) << 3)));
+                atomicOr(row + (g.z >> 5), 1u << (((g.z >> 2) & 7) | ((g.z & 3) << 3)));
+                atomicOr(row + (g.w >> 5), 1u << (((g.w >> 2) & 7) | ((g.w & 3) << 3)));
+            }
+            const bool e0 = x.x != 1.0f, e1 = x.y != 1.0f, e2 = x.z != 1.0f, e3 = x.w != 1.0f;  // dead lanes carry 1
+            const uint32_t cnt = (uint32_t)e0 + (uint32_t)e1 + (uint32_t)e2 + (uint32_t)e3;
+            const unsigned b0 = __ballot_sync(0xffffffffu, cnt & 1u), b1 = __ballot_sync(0xffffffffu, cnt & 2u),
+                           b2 = __ballot_sync(0xffffffffu, cnt & 4u);
+            if (b0 | b1 | b2) {
+                // a lane's four entries are consecutive positions: lanes in order, entries in order inside a lane
+                uint32_t slot = qtail + __popc(b0 & lt_mask) + 2 * __popc(b1 & lt_mask) + 4 * __popc(b2 & lt_mask);
+                if (e0) {
+                    qg[slot & (PREP_Q - 1)] = g.x;
+                    qv[slot & (PREP_Q - 1)] = x.x;
+                    ++slot;
+                }
+                if (e1) {
+                    qg[slot & (PREP_Q - 1)] = g.y;
+                    qv[slot & (PREP_Q - 1)] = x.y;
+                    ++slot;
+                }
+                if (e2) {
+                    qg[slot & (PREP_Q - 1)] = g.z;
+                    qv[slot & (PREP_Q - 1)] = x.z;
+                    ++slot;
+                }
+                if (e3) {
+                    qg[slot & (PREP_Q - 1)] = g.w;
+                    qv[slot & (PREP_Q - 1)] = x.w;
+                }
+                qtail += __popc(b0) + 2 * __popc(b1) + 4 * __popc(b2);
+            }
+        };
         if constexpr (VEC) {
             const uint64_t hi = lo + n;
             const uint64_t a_up = (lo + 3) & ~3ull, z_dn = hi & ~3ull;
             const uint64_t a = a_up < hi ? a_up : hi, z = z_dn > a ? z_dn : a;  // aligned interior [a, z)
-            {  // head [lo, a) on lanes 0..2, tail [z, hi) on lanes 3..5
-                const uint64_t e = lane < 3 ? lo + lane : z + (lane - 3);
-                const bool live = lane < 3 ? e < a : (lane < 6 && e < hi);
-                const uint32_t ixu = live ? __ldg(indices + e) : 0u;
-                const float vu = live ? __ldg(values + e) : 1.0f;
-                consume(ixu, vu, live);
+            if (a > lo) {  // head [lo, a): at most 3 entries, one per lane
+                const uint64_t e = lo + lane;
+                const bool live = e < a;
+                consume(live ? __ldg(indices + e) : 0u, live ? __ldg(values + e) : 1.0f, live);
             }
             const uint32_t nbat = (uint32_t)((z - a + 127) >> 7);
             const uint4* ip4 = reinterpret_cast<const uint4*>(indices + a) + lane;
@@ -279,15 +316,17 @@ __global__ void __launch_bounds__(PREP_WARPS * 32, 4) k_project_prep(const uint6
                     ng = __ldg(ip4 + 32 * (b + 1));
                     nx = __ldg(vp4 + 32 * (b + 1));
                 }
-                const bool live = 32u * b + lane < ngrp;
-                consume(g4.x, x4.x, live);
-                consume(g4.y, x4.y, live);
-                consume(g4.z, x4.z, live);
-                consume(g4.w, x4.w, live);
+                consume4(g4, x4, 32u * b + lane < ngrp);
                 __syncwarp();
                 while (qtail - qhead >= 32) drain(32);
                 g4 = ng;
                 x4 = nx;
+            }
+            if (hi > z) {  // tail [z, hi): at most 3 entries, after the interior
+                const uint64_t e = z + lane;
+                const bool live = e < hi;
+                consume(live ? __ldg(indices + e) : 0u, live ? __ldg(values + e) : 1.0f, live);
+                __syncwarp();
             }
         } else {
         const uint32_t nfull = n >> 7;

@@ -167,6 +167,26 @@ def test_project_raw_columns_of_very_different_scale(lg, ctx):
     assert not np.isfinite(raw[:, 3]).all() and np.isfinite(np.delete(raw, 3, axis=1)).all()
 
 
+def test_project_raw_bits_do_not_depend_on_where_a_column_starts(lg, ctx):
+    """a cell's raw projection must be bit-identical whether its block starts at column 0 or anywhere else (any alignment
+    of its first entry in the index / value arrays): that is what makes the cell-sharded run reproduce the single-GPU
+    bits.  The same for the Nystrom pass."""
+    rng = np.random.default_rng(77)
+    D, N, K = 4000, 1500, 50
+    ip, ix, v = random_csc(rng, D, N, 0.05, empty_every=89)
+    basis = basis_for(D, K)
+    whole = lg.CscBlock.upload(ctx, ip, ix, v, D)
+    raw = np.empty((N, K), np.float32)
+    ctx.check(lg.lib.lg_project_raw(ctx.h, whole.h, basis.ctypes.data, K, raw.ctypes.data))
+    ny = lg.nystrom_project(ctx, whole, np.ascontiguousarray(basis.T))
+    for lo, hi in ((1, 700), (2, 903), (3, 1500), (517, 1499), (1000, 1001)):
+        sub = lg.CscBlock.upload(ctx, ip, ix, v, D, lo, hi)
+        part = np.empty((hi - lo, K), np.float32)
+        ctx.check(lg.lib.lg_project_raw(ctx.h, sub.h, basis.ctypes.data, K, part.ctypes.data))
+        assert part.tobytes() == raw[lo:hi].tobytes(), (lo, hi)
+        assert lg.nystrom_project(ctx, sub, np.ascontiguousarray(basis.T)).tobytes() == ny[lo:hi].tobytes(), (lo, hi)
+
+
 def test_project_batch_label_mismatch_skips_centring(lg, ctx):
     rng = np.random.default_rng(4)
     ip, ix, v = random_csc(rng, 200, 300, 0.1)
