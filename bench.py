@@ -20,6 +20,18 @@ import sys
 import threading
 import time
 
+# stdout carries exactly ONE JSON line.  NCCL prints its version banner on fd 1, so the real stdout is kept aside and
+# fd 1 points at stderr while the run lasts; emit() writes the result line to the real stdout.
+os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+sys.stdout.flush()
+_REAL_STDOUT = os.dup(1)
+os.dup2(2, 1)
+
+
+def emit(obj):
+    os.write(_REAL_STDOUT, (json.dumps(obj) + "\n").encode())
+
+
 ROOT = os.path.dirname(os.path.abspath(__file__))
 for p in (ROOT, os.path.join(ROOT, "legume-rs_b200")):
     if p not in sys.path:
@@ -190,7 +202,7 @@ def run_reference(args):
     t = float(np.mean(ts))
     val = ncpu / t
     sample = f"first {ncpu} cells ({len(v)} nnz) of the workload per step, OpenMP projection + serial collapse/codes"
-    print(json.dumps({
+    emit(({
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": t * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
@@ -429,7 +441,7 @@ def main():
             "roofline": roofline, "roofline_knn": roofline_knn, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clk,
             "stages": stages,
         }
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 

@@ -8,6 +8,8 @@ import json
 import os
 import sys
 
+os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path[:0] = [ROOT, os.path.join(ROOT, "legume-rs_b200")]
 import numpy as np
