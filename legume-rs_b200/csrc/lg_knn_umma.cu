@@ -28,8 +28,11 @@ namespace {
 constexpr int QT = 128;        // queries per CTA tile (UMMA M)
 constexpr int RT = 256;        // reference points per tile (UMMA N)
 constexpr int CAND = 16;       // candidates kept per (query, list)
-constexpr int NRST = 3;        // reference-tile ring depth in shared memory: a 64 KB bulk copy outlasts the 1536 clk of MMAs it feeds
-constexpr int EPI_WARPS = 8;   // two warps per TMEM lane quadrant, each filtering half of the columns
+constexpr int NRST = 2;        // reference-tile ring depth in shared memory (64 KB per tile; a third stage measured no gain and the
+                               // space now holds the filter's append buffers)
+constexpr int NBUF = 16;       // append-buffer slots per filter thread
+constexpr int NPART = 2;        // filter warps per TMEM lane quadrant, each scanning RT / NPART columns of every tile
+constexpr int EPI_WARPS = 4 * NPART;
 constexpr int W_MMA = EPI_WARPS, W_LOAD = EPI_WARPS + 1;
 constexpr int KTHREADS = (EPI_WARPS + 2) * 32;
 
@@ -109,7 +112,7 @@ struct KBars {
     uint64_t d_full[2], d_empty[2];
 };
 
-// grid = (query tiles, reference splits).  Candidate lists: [query][split*2 + half][CAND]
+// grid = (query tiles, reference splits).  Candidate lists: [query][split*NPART + part][CAND]
 __global__ void __launch_bounds__(KTHREADS, 1) k_knn_umma(const uint8_t* __restrict__ qtiles, const uint8_t* __restrict__ rtiles,
                                                           uint64_t nq, uint64_t nr, int ksteps, uint32_t nlists,
                                                           float* __restrict__ cand_key, uint32_t* __restrict__ cand_idx) {
@@ -120,6 +123,9 @@ __global__ void __launch_bounds__(KTHREADS, 1) k_knn_umma(const uint8_t* __restr
     const size_t rstride = ((rbytes + 127) / 128) * 128;
     KBars* bars = reinterpret_cast<KBars*>(sr + NRST * rstride);
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 1);
+    // the filter threads' append buffers, slot-major (conflict-free): [NBUF][EPI_WARPS * 32] keys, then indices
+    float* buf_k = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 512);
+    uint32_t* buf_i = reinterpret_cast<uint32_t*>(buf_k + NBUF * EPI_WARPS * 32);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint64_t nrt = (nr + RT - 1) / RT;
     const uint32_t split = blockIdx.y, nsplit = gridDim.y;
@@ -146,8 +152,8 @@ __global__ void __launch_bounds__(KTHREADS, 1) k_knn_umma(const uint8_t* __restr
     const uint32_t tbase = *tmem_slot;
 
     if (warp < EPI_WARPS) {
-        // ===== fused filter: thread = (query row, column half) =====
-        const int quad = warp & 3, half = warp >> 2;
+        // ===== fused filter: thread = (query row, column part) =====
+        const int quad = warp & 3, half = warp >> 2;  // `half` = this warp's part of the columns, 0 .. NPART-1
         const int row = quad * 32 + lane;
         const uint32_t lane_base = (uint32_t)(quad * 32) << 16;
         // this thread's CAND best (key, index) pairs, ascending, in registers (static indexing only)
@@ -158,57 +164,93 @@ __global__ void __launch_bounds__(KTHREADS, 1) k_knn_umma(const uint8_t* __restr
             ck[c] = INFINITY;
             ci[c] = 0xffffffffu;
         }
+        // Deferred insertion.  A key below the list's worst entry used to be inserted on the spot by a 16-stage register
+        // network; one improving row out of a warp's 32 made all 32 lanes walk it, and with ~130 improvements per list
+        // almost every 8-column group had one: the network's ~70 instructions per element, not the MMAs or the TMEM
+        // reads, set the pace (4450 clk per tile against 1536 clk of MMAs).  Now a key below `tau` (the worst entry as
+        // of the last merge: stale, hence an upper bound, so nothing is lost) is only APPENDED to the thread's
+        // shared-memory buffer; when some lane's buffer could overflow on the next group the whole warp replays its
+        // buffers through the network.  Arrival order is kept, so the final lists are exactly those of immediate insertion.
+        float tau = INFINITY;
+        uint32_t cnt = 0;
+        float* bk = buf_k + threadIdx.x;
+        uint32_t* bi = buf_i + threadIdx.x;
+        auto merge = [&]() {
+            const uint32_t mx = __reduce_max_sync(0xffffffffu, cnt);
+            for (uint32_t sl = 0; sl < mx; ++sl) {
+                if (sl < cnt) {
+                    const float key = bk[sl * (EPI_WARPS * 32)];
+                    const uint32_t id = bi[sl * (EPI_WARPS * 32)];
+                    if (key < ck[CAND - 1]) {
+                        // branch-free sorted insertion (ascending); ties keep the earlier (lower) index first
+#pragma unroll
+                        for (int c = CAND - 1; c >= 1; --c) {
+                            const bool up = key < ck[c - 1];
+                            const bool in = key < ck[c];
+                            ck[c] = in ? (up ? ck[c - 1] : key) : ck[c];
+                            ci[c] = in ? (up ? ci[c - 1] : id) : ci[c];
+                        }
+                        const bool first = key < ck[0];
+                        ck[0] = first ? key : ck[0];
+                        ci[0] = first ? id : ci[0];
+                    }
+                }
+            }
+            cnt = 0;
+            tau = ck[CAND - 1];
+        };
         uint32_t it = 0;
         for (uint64_t rt = split; rt < nrt; rt += nsplit, ++it) {
             const uint32_t buf = it & 1;
             mbar_wait(&bars->d_full[buf], (it >> 1) & 1);
             tc_fence_after();
-            const uint32_t col0 = buf * RT + half * (RT / 2);
-            const uint32_t idx0 = (uint32_t)(rt * RT) + half * (RT / 2);
-#pragma unroll 1
-            for (int c0 = 0; c0 < RT / 2; c0 += 16) {
-                uint32_t dv[16];
-                tmem_ld_x16(tbase + lane_base + col0 + c0, dv);
-                tmem_wait_ld();
+            const uint32_t col0 = buf * RT + half * (RT / NPART);
+            const uint32_t idx0 = (uint32_t)(rt * RT) + half * (RT / NPART);
+            auto scan16 = [&](const uint32_t* dv, int c0) {
 #pragma unroll
                 for (int h8 = 0; h8 < 2; ++h8) {
-                    // tree minimum of 8 keys, then one warp-uniform branch: once the lists are warm almost no
-                    // 8-column group improves any of the 32 rows
+                    // tree minimum of 8 keys, then one warp-uniform branch
                     const float m01 = fminf(__uint_as_float(dv[8 * h8 + 0]), __uint_as_float(dv[8 * h8 + 1]));
                     const float m23 = fminf(__uint_as_float(dv[8 * h8 + 2]), __uint_as_float(dv[8 * h8 + 3]));
                     const float m45 = fminf(__uint_as_float(dv[8 * h8 + 4]), __uint_as_float(dv[8 * h8 + 5]));
                     const float m67 = fminf(__uint_as_float(dv[8 * h8 + 6]), __uint_as_float(dv[8 * h8 + 7]));
                     const float m = fminf(fminf(m01, m23), fminf(m45, m67));
-                    if (__any_sync(0xffffffffu, m < ck[CAND - 1])) {
+                    if (__any_sync(0xffffffffu, m < tau)) {
 #pragma unroll
                         for (int i = 0; i < 8; ++i) {
                             const float key = __uint_as_float(dv[8 * h8 + i]);
-                            if (key < ck[CAND - 1]) {
-                                // branch-free sorted insertion (ascending); ties keep the earlier (lower) index first
-                                const uint32_t id = idx0 + c0 + 8 * h8 + i;
-#pragma unroll
-                                for (int c = CAND - 1; c >= 1; --c) {
-                                    const bool up = key < ck[c - 1];
-                                    const bool in = key < ck[c];
-                                    ck[c] = in ? (up ? ck[c - 1] : key) : ck[c];
-                                    ci[c] = in ? (up ? ci[c - 1] : id) : ci[c];
-                                }
-                                const bool first = key < ck[0];
-                                ck[0] = first ? key : ck[0];
-                                ci[0] = first ? id : ci[0];
+                            if (key < tau) {  // cnt <= 8 on entry to a group: at most 16 after it
+                                bk[cnt * (EPI_WARPS * 32)] = key;
+                                bi[cnt * (EPI_WARPS * 32)] = idx0 + c0 + 8 * h8 + i;
+                                ++cnt;
                             }
                         }
+                        if (__any_sync(0xffffffffu, cnt > NBUF - 8)) merge();
                     }
                 }
+            };
+            // software-pipelined TMEM reads: the next 16 columns are in flight while these are scanned
+            uint32_t da[16], db[16];
+            const uint32_t t0 = tbase + lane_base + col0;
+            tmem_ld_x16(t0, da);
+#pragma unroll 1
+            for (int c0 = 0; c0 < RT / NPART; c0 += 32) {
+                tmem_wait_ld_x16(da);
+                tmem_ld_x16(t0 + c0 + 16, db);
+                scan16(da, c0);
+                tmem_wait_ld_x16(db);
+                if (c0 + 32 < RT / NPART) tmem_ld_x16(t0 + c0 + 32, da);
+                scan16(db, c0 + 16);
             }
             // this warp is done with accumulator `buf`
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&bars->d_empty[buf]);
         }
+        if (__any_sync(0xffffffffu, cnt > 0)) merge();
         const uint64_t q = (uint64_t)blockIdx.x * QT + row;
         if (q < nq) {
-            const size_t o = (q * nlists + (size_t)split * 2 + half) * CAND;
+            const size_t o = (q * nlists + (size_t)split * NPART + half) * CAND;
 #pragma unroll
             for (int c = 0; c < CAND; ++c) {
                 cand_key[o + c] = ck[c];
@@ -377,12 +419,13 @@ int lg_knn_topk_umma(lg_ctx* ctx, const float* d_ref, uint64_t nr, const float* 
     if (k + 4 > CAND || d > 126 || nr < 4096 || nq == 0 || nr >= 0xFFFFFF00ull || (double)nq * (double)nr < 5e7) return LG_OK;
     const int ksteps = (d + 2 + 15) / 16;
     const size_t qbytes = tile_bytes(QT, ksteps), rbytes = tile_bytes(RT, ksteps);
-    const size_t smem = ((qbytes + 127) / 128) * 128 + NRST * (((rbytes + 127) / 128) * 128) + sizeof(KBars) + 16;
+    static_assert(sizeof(KBars) + 16 <= 512, "barriers and the TMEM slot fit the 512 bytes ahead of the append buffers");
+    const size_t smem = ((qbytes + 127) / 128) * 128 + NRST * (((rbytes + 127) / 128) * 128) + 512 + (size_t)2 * NBUF * EPI_WARPS * 32 * 4;
     if (smem > ctx->smem_optin) return LG_OK;
     const uint64_t nqt = (nq + QT - 1) / QT, nrt = (nr + RT - 1) / RT;
     uint32_t nsplit = 1;
     while (nqt * nsplit < (uint64_t)2 * ctx->num_sms && nsplit * 2 <= nrt && nsplit < 16) nsplit *= 2;
-    const uint32_t nlists = nsplit * 2;
+    const uint32_t nlists = nsplit * NPART;
     LgStage st(ctx);
     unsigned int *d_absmax, *d_redo_count;
     uint8_t *d_qt, *d_rt;
