@@ -334,8 +334,11 @@ def main():
         roofline_knn = {"bound": "tensor", "kernel": "K7 exact kNN = k_knn_umma (split-f16 tcgen05 filter) + k_knn_refine", "achieved": ach,
                         "peak": tpeak, "unit": "TFLOP/s", "frac": ach / tpeak, "traffic": None, "peak_source": tsrc,
                         "algorithmic_flops_per_launch": flop, "launch_ms": t_knn, "queries_per_s": nq_k / (t_knn * 1e-3),
-                        "note": "algorithmic flops 2*d*Nq*Nr; the filter issues 3 f16 passes over a K axis padded 50 -> 64, i.e. "
-                                "3.84x these flops on the tensor pipe"}
+                        # tensor-pipe occupancy: what the kernel actually issues on tcgen05, against the same measured peak
+                        "issued": ach * 3.84, "issued_frac": ach * 3.84 / tpeak,
+                        "note": "achieved / frac count ALGORITHMIC flops 2*d*Nq*Nr; the filter issues 3 f16 passes over a K axis "
+                                "padded 50 -> 64, i.e. 3.84x these flops on the tensor pipe (issued / issued_frac; cf. "
+                                "sm__pipe_tensor_cycles_active in profiles/)"}
         del kref, kqry, kidx, kdist
 
     # ---- e2e: host buffers in the reference's form through the C ABI, results read back ----

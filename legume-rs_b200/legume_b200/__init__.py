@@ -34,7 +34,7 @@ __all__ = ["Context", "CscBlock", "SparseIoVec", "binary_sort_columns", "GammaMa
            "CollapsedOut", "optimize", "ColumnDict", "LegumeError", "CalibrateTarget", "compute_level_sort_dims",
            "pad_numeric_labels", "merge_stat", "MultilevelParams", "PbSampleLayout", "build_pb_sample_layout",
            "per_batch_sc_neighbors", "collect_matched_stat_coarse", "compute_fine_to_coarse_mapping",
-           "sort_batch_proximity", "knn_match_batches", "SparseRunningStatistics", "nystrom_project"]
+           "sort_batch_proximity", "knn_match_batches", "SparseRunningStatistics", "nystrom_project", "SparseIoStack", "mix_seed"]
 DEFAULT_NUM_LEVELS = 2                          # collapse_data/stats.rs:688
 
 
@@ -597,6 +597,32 @@ class SparseIoVec:
     def from_csc(cls, ctx, indptr, indices, data, nrows):
         return cls(ctx, CscBlock.upload(ctx, indptr, indices, data, nrows))
 
+    @classmethod
+    def from_backends(cls, ctx, backends, nrows):
+        """Several backends' columns side by side, as SparseIoVec::push + read_columns_csc see them
+        (data-beans/src/sparse_io_vector/read.rs:172-285): every backend is (indptr, indices, data, row_remap or None),
+        row_remap[local row] = row in the union (`g2c[l2g[row]]`, :202-219; rows a backend lacks simply never occur).
+        One backend goes straight through lg_csc_upload (the remap is applied on the device); several are remapped and
+        joined on the host first, then uploaded as one block."""
+        backends = list(backends)
+        if len(backends) == 1:
+            ip, ix, v, remap = backends[0]
+            return cls(ctx, CscBlock.upload(ctx, ip, ix, v, nrows, row_remap=remap))
+        ips, ixs, vs, base = [np.zeros(1, np.uint64)], [], [], 0
+        for ip, ix, v, remap in backends:
+            ip = np.asarray(ip, np.uint64)
+            ix = np.asarray(ix, np.uint64)
+            if remap is not None:
+                remap = np.asarray(remap, np.uint64)
+                if len(ix) and int(ix.max()) >= len(remap):
+                    raise LegumeError(1, "from_backends: row index outside the backend's remap")
+                ix = remap[ix]
+            ips.append(ip[1:] - ip[0] + np.uint64(base))
+            base += int(ip[-1] - ip[0])
+            ixs.append(ix[int(ip[0]):int(ip[-1])])
+            vs.append(np.asarray(v, np.float32)[int(ip[0]):int(ip[-1])])
+        return cls(ctx, CscBlock.upload(ctx, np.concatenate(ips), np.concatenate(ixs), np.concatenate(vs), nrows))
+
     def num_rows(self):
         return self.block.nrows
 
@@ -849,6 +875,74 @@ class SparseIoVec:
 # --------------------------------------------------------------------------------------------------
 # ColumnDict (matrix-util/src/knn/mod.rs) with the exact backend
 # --------------------------------------------------------------------------------------------------
+def mix_seed(base: int, salt: int) -> int:
+    """SplitMix64 avalanche of (base, salt): matrix-util/src/rand_util.rs:30-35"""
+    m = 0xFFFFFFFFFFFFFFFF
+    z = (base ^ (salt * 0x9E3779B97F4A7C15)) & m
+    z = ((z ^ (z >> 30)) * 0xBF58476D1CE4E5B9) & m
+    z = ((z ^ (z >> 27)) * 0x94D049BB133111EB) & m
+    return z ^ (z >> 31)
+
+
+class SparseIoStack:
+    """Several modalities over the same cells (data-beans/src/sparse_io_stack.rs): RandProjOps runs every modality with
+    its own sub-seed mix_seed(seed, m) and stacks the results vertically (random_projection.rs:200-330)."""
+
+    def __init__(self, stack):
+        self.stack = list(stack)
+        if not self.stack:
+            raise LegumeError(1, "SparseIoStack: empty stack")
+
+    def num_columns(self):
+        return max(x.num_columns() for x in self.stack)  # sparse_io_stack.rs:48-54
+
+    def num_rows(self):
+        return sum(x.num_rows() for x in self.stack)
+
+    def _stacked(self, one, target_dim, batch_membership, bases, seed):
+        n = self.num_columns()
+        if batch_membership is not None:
+            batch_membership = batch_membership[:n]  # `.get(0..ncols)` (:213)
+        if bases is not None and len(bases) != len(self.stack):
+            raise LegumeError(1, "SparseIoStack: one basis per modality")
+        outs = [one(m, x, batch_membership, None if bases is None else bases[m], mix_seed(seed, m))
+                for m, x in enumerate(self.stack)]
+        if any(p.shape[0] != outs[0][1].shape[0] for _, p in outs):
+            raise LegumeError(1, "SparseIoStack: modalities disagree on the number of columns")  # concatenate_vertical fails
+        basis = np.concatenate([np.asarray(b) for b, _ in outs], axis=0)              # (sum D_m, K): vertical concat of D x K
+        proj = np.concatenate([np.asarray(p) for _, p in outs], axis=1)               # (N, M * K): vertical concat of K x N
+        return basis, proj
+
+    def project_columns_with_batch_correction(self, target_dim, block_size=None, batch_membership=None, bases=None,
+                                              seed=DEFAULT_PROJECTION_SEED):
+        return self._stacked(lambda m, x, bm, b, sd: x.project_columns_with_batch_correction(target_dim, block_size, bm, basis=b, seed=sd),
+                             target_dim, batch_membership, bases, seed)
+
+    def project_columns(self, target_dim, block_size=None, bases=None):
+        return self.project_columns_with_batch_correction(target_dim, block_size, None, bases=bases)
+
+    def partition_columns_to_groups(self, proj_kn, num_features=None, ncols_per_group=None):
+        """random_projection.rs:311-340: one set of binary codes from the stacked projection, assigned to every modality"""
+        n, K = proj_kn.shape
+        if n != self.num_columns():
+            raise LegumeError(1, "number of columns mismatch")
+        first = self.stack[0]
+        out = first.partition_columns_to_groups(proj_kn, num_features, ncols_per_group)
+        for x in self.stack[1:]:
+            x.binary_codes, x.col_to_group, x.group_keys = first.binary_codes, first.col_to_group, first.group_keys
+        return out
+
+    def project_columns_weighted(self, target_dim, block_size, batch_membership, row_weights, bases=None,
+                                 seed=DEFAULT_PROJECTION_SEED):
+        """row_weights covers the stacked rows; every modality takes its own slice (random_projection.rs:253-330)"""
+        w = np.ascontiguousarray(row_weights, np.float32)
+        if len(w) != self.num_rows():
+            raise LegumeError(1, "SparseIoStack: row weights must cover the stacked rows")
+        offs = np.cumsum([0] + [x.num_rows() for x in self.stack])
+        return self._stacked(lambda m, x, bm, b, sd: x.project_columns_weighted(target_dim, block_size, bm, w[offs[m]:offs[m + 1]], basis=b, seed=sd),
+                             target_dim, batch_membership, bases, seed)
+
+
 class ColumnDict:
     def __init__(self, ctx: Context, data, names):
         """data: (n, d) array, one point per row here = one column of the reference's DMatrix"""

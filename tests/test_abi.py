@@ -57,6 +57,13 @@ def test_product_never_touches_the_oracle():
     assert not bad, bad
 
 
+def test_mix_seed_is_the_splitmix64_finaliser():
+    """matrix-util/src/rand_util.rs:30-35: mix_seed(0, 1) is the first output of SplitMix64 seeded with 0"""
+    import legume_b200 as lg
+    assert lg.mix_seed(0, 1) == 0xE220A8397B1DCDAF
+    assert lg.mix_seed(42, 0) != lg.mix_seed(42, 1)
+
+
 def test_host_label_rules():
     import legume_b200 as lg
     idx, keys = lg._rank_labels([10, 2, 2, 33, 10, 7, 100])

@@ -83,6 +83,32 @@ def test_csc_upload_large_block_host_narrowing(lg, ctx, mode, monkeypatch):
             lg.CscBlock.upload(ctx, ip, bad, v, D)
 
 
+def test_sparse_io_vec_from_several_backends_with_row_remaps(lg, ctx):
+    """SparseIoVec::read_columns_csc (read.rs:202-219): every backend's local rows are mapped into the union of rows;
+    the joined block equals the matrix assembled by hand"""
+    rng = np.random.default_rng(6)
+    D = 120
+    parts, dense = [], []
+    for nloc, ncol in ((80, 40), (120, 25), (55, 60)):
+        remap = rng.permutation(D)[:nloc].astype(np.uint32)  # local row -> union row
+        ip, ix, v = random_csc(rng, nloc, ncol, 0.15)
+        parts.append((ip, ix, v, remap))
+        a = np.zeros((D, ncol), np.float32)
+        for j in range(ncol):
+            a[remap[ix[ip[j]:ip[j + 1]].astype(np.int64)], j] = v[ip[j]:ip[j + 1]]
+        dense.append(a)
+    whole = np.concatenate(dense, axis=1)
+    data = lg.SparseIoVec.from_backends(ctx, parts, D)
+    assert (data.num_rows(), data.num_columns()) == (D, 125)
+    st = data.streaming_sparse_running_stats()
+    assert np.array_equal(st.sum(), whole.sum(1)) and np.array_equal(st.count_positives(), (whole > 0).sum(1))
+    one = lg.SparseIoVec.from_backends(ctx, parts[:1], D)  # a single backend: the remap is applied on the device
+    assert np.array_equal(one.streaming_sparse_running_stats().sum(), dense[0].sum(1))
+    bad = (parts[0][0], parts[0][1], parts[0][2], parts[0][3][:10])
+    with pytest.raises(lg.LegumeError):
+        lg.SparseIoVec.from_backends(ctx, [bad, parts[1]], D)
+
+
 def test_sim_matches_cpu_twin(lg, ctx):
     from legume_b200 import sim
     tabs = sim.make_tables(700, ntopic=4, nbatch=2, depth=400, seed=11)
@@ -185,6 +211,31 @@ def test_project_raw_bits_do_not_depend_on_where_a_column_starts(lg, ctx):
         ctx.check(lg.lib.lg_project_raw(ctx.h, sub.h, basis.ctypes.data, K, part.ctypes.data))
         assert part.tobytes() == raw[lo:hi].tobytes(), (lo, hi)
         assert lg.nystrom_project(ctx, sub, np.ascontiguousarray(basis.T)).tobytes() == ny[lo:hi].tobytes(), (lo, hi)
+
+
+def test_sparse_io_stack_projects_every_modality_and_stacks(lg, ctx):
+    """RandProjOps for SparseIoStack (random_projection.rs:200-340): per-modality projection with its own basis, vertical
+    concatenation of bases (rows) and projections (dims); batch labels cut to the shared column count; one set of codes"""
+    rng = np.random.default_rng(21)
+    N, K = 900, 12
+    mods = [random_csc(rng, D, N, 0.1) + (D,) for D in (300, 170)]
+    vecs = [lg.SparseIoVec.from_csc(ctx, ip, ix, v, D) for ip, ix, v, D in mods]
+    bases = [basis_for(D, K, 40 + m) for m, (_, _, _, D) in enumerate(mods)]
+    batch = rng.integers(0, 3, N + 5)  # longer than the columns: `.get(0..ncols)`
+    stack = lg.SparseIoStack(vecs)
+    assert (stack.num_columns(), stack.num_rows()) == (N, 470)
+    basis, proj = stack.project_columns_with_batch_correction(K, None, batch, bases=bases)
+    assert basis.shape == (470, K) and proj.shape == (N, 2 * K)
+    for m, (ip, ix, v, D) in enumerate(mods):
+        want = orc.project(ip, ix, v, bases[m], batch[:N].astype(np.uint32), 3, nthreads=4)
+        assert close(proj[:, m * K:(m + 1) * K], want, TOL)
+    w = rng.uniform(0.2, 1.0, 470).astype(np.float32)
+    _, pw = stack.project_columns_weighted(K, None, None, w, bases=bases)
+    assert close(pw[:, K:], orc.project(*mods[1][:3], bases[1] * w[300:, None]), TOL)
+    with pytest.raises(lg.LegumeError):
+        stack.project_columns_weighted(K, None, None, w[:-1], bases=bases)
+    ncode = stack.partition_columns_to_groups(proj, 6)
+    assert ncode <= 64 and np.array_equal(vecs[0].get_group_membership(), vecs[1].get_group_membership())
 
 
 def test_project_batch_label_mismatch_skips_centring(lg, ctx):
