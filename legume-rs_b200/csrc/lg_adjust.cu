@@ -20,6 +20,8 @@
 #include <cmath>
 #include <numeric>
 
+#include <cstdlib>
+
 #include "lg_common.cuh"
 #include "lg_umma.cuh"
 
@@ -645,6 +647,136 @@ __global__ void __launch_bounds__(PM_Q) k_pb_min_dist(const float* __restrict__ 
     if (live) keys[(size_t)ql * npb + p] = best;
 }
 
+// The same kernel with the query's first 16 * NCH coordinates in REGISTERS and the cell tile read with 128-bit broadcast
+// loads: the shared-memory form above issues one LDS per (dim, cell) next to three FP operations and is bound by the
+// one-wavefront-per-clock LSU pipe, not by FP issue.  Here an LDS.128 serves four dims of a cell (1 LDS per 12 FP
+// operations).  Accumulation order is unchanged: 16 lane accumulators per cell over the full 16-chunks, folded left to
+// right, then the tail dims one by one (knn/metric.rs:19-45) — bit-identical keys.
+template <int NCH>
+__global__ void __launch_bounds__(PM_Q, 2) k_pb_min_dist_reg(const float* __restrict__ proj, int K, const uint32_t* __restrict__ cell_sorted,
+                                                             const uint64_t* __restrict__ pb_off, const float* __restrict__ centroids,
+                                                             const uint32_t* __restrict__ pb_batch, uint32_t npb, uint32_t q0,
+                                                             uint32_t nq, uint32_t cell_offset, unsigned long long* __restrict__ keys) {
+    extern __shared__ __align__(16) float pm_smem[];
+    const int ds = K | 1, KP = (K + 3) & ~3;
+    float* cs = pm_smem;                              // PM_CELLS x KP (16-byte aligned rows)
+    float* qs = pm_smem + (size_t)PM_CELLS * KP;      // PM_Q x ds
+    __shared__ uint32_t cell_id[PM_CELLS];
+    const uint32_t p = blockIdx.x;
+    const uint32_t ql = blockIdx.y * PM_Q + threadIdx.x;
+    const bool live = ql < nq;
+    const uint32_t q = q0 + ql;
+    const uint32_t nq_here = min((uint32_t)PM_Q, nq - blockIdx.y * PM_Q);
+    for (uint32_t e = threadIdx.x; e < nq_here * (uint32_t)K; e += PM_Q)
+        qs[(e / K) * ds + (e % K)] = centroids[(size_t)(q0 + blockIdx.y * PM_Q) * K + e];
+    __syncthreads();
+    const float* myq = qs + (size_t)threadIdx.x * ds;
+    float qr[16 * NCH];
+#pragma unroll
+    for (int i = 0; i < 16 * NCH; ++i) qr[i] = (live || threadIdx.x < nq_here) ? myq[i] : 0.0f;
+    const uint32_t pbatch = pb_batch[p];
+    const bool want = live && pb_batch[q] != pbatch;
+    unsigned long long best = ~0ull;
+    const uint64_t lo = pb_off[p], hi = pb_off[p + 1];
+    for (uint64_t base = lo; base < hi; base += PM_CELLS) {
+        const int nt = (int)min((uint64_t)PM_CELLS, hi - base);
+        __syncthreads();
+        if ((int)threadIdx.x < nt) cell_id[threadIdx.x] = cell_sorted[base + threadIdx.x];
+        __syncthreads();
+        {   // tile fill without a division per element: (cell, dim) advanced incrementally
+            int cc = (int)threadIdx.x / K, dd = (int)threadIdx.x % K;
+            const int dc = PM_Q / K, dr = PM_Q % K;
+            while (cc < nt) {
+                cs[cc * KP + dd] = proj[(size_t)cell_id[cc] * K + dd];
+                cc += dc;
+                dd += dr;
+                if (dd >= K) {
+                    dd -= K;
+                    ++cc;
+                }
+            }
+        }
+        __syncthreads();
+        if (!want) continue;
+        int t = 0;
+        for (; t + PM_U <= nt; t += PM_U) {
+            float acc[PM_U][16];  // first chunk peeled: 0 + x == x exactly, so the accumulators start as the first squares
+#pragma unroll
+            for (int ch = 0; ch < NCH; ++ch) {
+#pragma unroll
+                for (int l4 = 0; l4 < 4; ++l4) {
+#pragma unroll
+                    for (int u = 0; u < PM_U; ++u) {
+                        const float4 cv = *reinterpret_cast<const float4*>(cs + (size_t)(t + u) * KP + 16 * ch + 4 * l4);
+                        const float d0 = __fsub_rn(cv.x, qr[16 * ch + 4 * l4 + 0]);
+                        const float d1 = __fsub_rn(cv.y, qr[16 * ch + 4 * l4 + 1]);
+                        const float d2 = __fsub_rn(cv.z, qr[16 * ch + 4 * l4 + 2]);
+                        const float d3 = __fsub_rn(cv.w, qr[16 * ch + 4 * l4 + 3]);
+                        if (ch == 0) {
+                            acc[u][4 * l4 + 0] = __fmul_rn(d0, d0);
+                            acc[u][4 * l4 + 1] = __fmul_rn(d1, d1);
+                            acc[u][4 * l4 + 2] = __fmul_rn(d2, d2);
+                            acc[u][4 * l4 + 3] = __fmul_rn(d3, d3);
+                        } else {
+                            acc[u][4 * l4 + 0] = __fadd_rn(acc[u][4 * l4 + 0], __fmul_rn(d0, d0));
+                            acc[u][4 * l4 + 1] = __fadd_rn(acc[u][4 * l4 + 1], __fmul_rn(d1, d1));
+                            acc[u][4 * l4 + 2] = __fadd_rn(acc[u][4 * l4 + 2], __fmul_rn(d2, d2));
+                            acc[u][4 * l4 + 3] = __fadd_rn(acc[u][4 * l4 + 3], __fmul_rn(d3, d3));
+                        }
+                    }
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < PM_U; ++u) {
+                float sum = 0.0f;
+#pragma unroll
+                for (int l = 0; l < 16; ++l) sum = __fadd_rn(sum, acc[u][l]);
+                for (int cc = 16 * NCH; cc < K; ++cc) {
+                    const float df = __fsub_rn(cs[(size_t)(t + u) * KP + cc], myq[cc]);
+                    sum = __fadd_rn(sum, __fmul_rn(df, df));
+                }
+                const unsigned long long key = ((unsigned long long)__float_as_uint(sum) << 32) | (cell_id[t + u] + cell_offset);
+                best = key < best ? key : best;
+            }
+        }
+        for (; t < nt; ++t) {
+            const float d2 = adj_l2_sq(cs + (size_t)t * KP, myq, K);
+            const unsigned long long key = ((unsigned long long)__float_as_uint(d2) << 32) | (cell_id[t] + cell_offset);
+            best = key < best ? key : best;
+        }
+    }
+    if (live) keys[(size_t)ql * npb + p] = best;
+}
+
+// launches the register form when the full 16-chunks of K fit it (K < 80), else the shared-memory form
+static int launch_pb_min_dist(lg_ctx* ctx, dim3 grid, const float* d_proj, int K, const uint32_t* d_cell, const uint64_t* d_off,
+                              const float* d_cen, const uint32_t* d_pbb, uint32_t npb, uint32_t q0, uint32_t nq, uint32_t cell_offset,
+                              unsigned long long* d_keys) {
+    const int nch = K / 16;
+    const size_t smem_reg = ((size_t)PM_CELLS * ((K + 3) & ~3) + (size_t)PM_Q * (K | 1)) * sizeof(float);
+    const char* force = getenv("LG_PB_SMEM_FORM");
+    if (nch >= 1 && nch <= 4 && smem_reg <= ctx->smem_optin && !(force && force[0] == '1')) {
+#define LG_PBMD(N)                                                                                                               \
+    do {                                                                                                                         \
+        LG_CUDA(ctx, cudaFuncSetAttribute(k_pb_min_dist_reg<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_reg));    \
+        k_pb_min_dist_reg<N><<<grid, PM_Q, smem_reg, ctx->stream>>>(d_proj, K, d_cell, d_off, d_cen, d_pbb, npb, q0, nq,        \
+                                                                    cell_offset, d_keys);                                       \
+    } while (0)
+        if (nch == 1) LG_PBMD(1);
+        else if (nch == 2) LG_PBMD(2);
+        else if (nch == 3) LG_PBMD(3);
+        else LG_PBMD(4);
+#undef LG_PBMD
+    } else {
+        const size_t smem = ((size_t)PM_Q * (K | 1) + (size_t)PM_CELLS * K) * sizeof(float);
+        LG_CUDA(ctx, cudaFuncSetAttribute(k_pb_min_dist, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_pb_min_dist<<<grid, PM_Q, smem, ctx->stream>>>(d_proj, K, d_cell, d_off, d_cen, d_pbb, npb, q0, nq, cell_offset, d_keys);
+    }
+    ctx->launches++;
+    LG_CUDA(ctx, cudaGetLastError());
+    return LG_OK;
+}
+
 // one warp per (query, target batch): the knn smallest keys among that batch's pb-samples, ascending
 __global__ void k_pb_topk(const unsigned long long* __restrict__ keys, uint32_t npb, uint32_t q0, uint32_t nq, uint32_t B,
                           const uint32_t* __restrict__ batch_pb, const uint32_t* __restrict__ batch_off, int knn,
@@ -1113,9 +1245,7 @@ extern "C" int lg_pb_match(lg_ctx* ctx, const float* proj_kn, int K, uint64_t nc
     for (uint32_t q0 = 0; q0 < npb; q0 += QC) {
         const uint32_t nq = std::min(QC, npb - q0);
         dim3 grid(npb, (nq + PM_Q - 1) / PM_Q);
-        k_pb_min_dist<<<grid, PM_Q, smem, ctx->stream>>>(d_proj, K, d_cell, d_off, d_cen, d_pbb, npb, q0, nq, 0u, d_keys);
-        ctx->launches++;
-        LG_CUDA(ctx, cudaGetLastError());
+        LG_TRY(launch_pb_min_dist(ctx, grid, d_proj, K, d_cell, d_off, d_cen, d_pbb, npb, q0, nq, 0u, d_keys));
         LG_LAUNCH(ctx, k_pb_topk, (unsigned)(((uint64_t)nq * B * 32 + 255) / 256), 256, 0, d_keys, npb, q0, nq, B, d_batch_pb, d_batch_off,
                   knn, d_mpb, d_md);
     }
@@ -1296,10 +1426,8 @@ extern "C" int lg_pb_min_keys(lg_ctx* ctx, const float* d_proj, int K, uint64_t 
     LG_CUDA(ctx, cudaFuncSetAttribute(k_pb_min_dist, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     if (nq) {
         dim3 grid(npb, (nq + PM_Q - 1) / PM_Q);
-        k_pb_min_dist<<<grid, PM_Q, smem, ctx->stream>>>(d_proj, K, d_cell, d_off, d_centroids, d_pb_batch, npb, q0, nq, (uint32_t)cell_offset,
-                                                        reinterpret_cast<unsigned long long*>(d_keys));
-        ctx->launches++;
-        LG_CUDA(ctx, cudaGetLastError());
+        LG_TRY(launch_pb_min_dist(ctx, grid, d_proj, K, d_cell, d_off, d_centroids, d_pb_batch, npb, q0, nq, (uint32_t)cell_offset,
+                                  reinterpret_cast<unsigned long long*>(d_keys)));
     }
     return st.finish();
 }
