@@ -25,6 +25,7 @@ struct lg_ctx {
     // pinned ring for host-side index narrowing in lg_csc_upload (allocated on first use)
     void* ring = nullptr;
     size_t ring_slots = 0;
+    size_t ring_slot_bytes = 0;
     std::vector<cudaEvent_t> ring_ev;
 };
 

@@ -155,7 +155,8 @@ __global__ void k_widen_indices(const uint32_t* __restrict__ src, uint64_t* __re
 namespace {
 constexpr uint64_t UP_CHUNK = 2ull << 20;          // non-zeros per ring slot
 constexpr uint64_t UP_PATCH_BYTES = 8ull << 16;     // UP_PATCH_CAP (position, f32) pairs
-constexpr uint64_t UP_SLOT_BYTES = UP_CHUNK * 5 + UP_PATCH_BYTES;   // u32 indices, u8 values, patch list
+constexpr uint64_t UP_SLOT_BYTES = UP_CHUNK * 5 + UP_PATCH_BYTES;       // u32 indices, u8 values, patch list
+constexpr uint64_t UP_SLOT_BYTES_RAW = UP_SLOT_BYTES + UP_CHUNK * 4;    // + raw f32 staging (pageable sources only)
 
 __attribute__((target("avx2"))) void narrow_chunk_avx2(const uint64_t* s, uint32_t* d, uint64_t n, uint64_t* or_all,
                                                        uint32_t* max_lo) {
@@ -279,13 +280,28 @@ cudaError_t upload_narrow_on_host(lg_ctx* ctx, const uint64_t* h_idx, const floa
     const uint64_t nchunks = (nnz + UP_CHUNK - 1) / UP_CHUNK;
     if ((uint64_t)nthreads > nchunks) nthreads = (int)nchunks;
     const size_t want_slots = (size_t)2 * nthreads;
-    if (ctx->ring_slots < want_slots) {
+    // Are the caller's arrays page-locked?  Copies from ordinary pageable memory (a Rust Vec) are staged by the driver
+    // and stall the stream, so then every byte goes through the pinned ring (measured on configs[1] from pageable
+    // arrays: 1510 ms with wide copies narrowed on the device, 500-790 ms with a wide share, 182 ms through the ring).
+    auto is_pinned = [](const void* p) {
+        cudaPointerAttributes a;
+        if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+            cudaGetLastError();
+            return false;
+        }
+        return a.type == cudaMemoryTypeHost;
+    };
+    const bool src_pinned = is_pinned(h_idx) && is_pinned(h_val);
+    const size_t want_bytes = src_pinned ? UP_SLOT_BYTES : UP_SLOT_BYTES_RAW;
+    if (ctx->ring_slots < want_slots || ctx->ring_slot_bytes < want_bytes) {
         if (ctx->ring) cudaFreeHost(ctx->ring);
         ctx->ring = nullptr;
         ctx->ring_slots = 0;
-        cudaError_t e = cudaHostAlloc(&ctx->ring, want_slots * UP_SLOT_BYTES, cudaHostAllocDefault);
+        const size_t sb = want_bytes > ctx->ring_slot_bytes ? want_bytes : ctx->ring_slot_bytes;
+        cudaError_t e = cudaHostAlloc(&ctx->ring, want_slots * sb, cudaHostAllocDefault);
         if (e != cudaSuccess) return e;
         ctx->ring_slots = want_slots;
+        ctx->ring_slot_bytes = sb;
         while (ctx->ring_ev.size() < want_slots + 2) {
             cudaEvent_t ev;
             e = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
@@ -293,6 +309,7 @@ cudaError_t upload_narrow_on_host(lg_ctx* ctx, const uint64_t* h_idx, const floa
             ctx->ring_ev.push_back(ev);
         }
     }
+    const size_t slot_bytes = ctx->ring_slot_bytes;
     const size_t nslots = ctx->ring_slots;
     uint8_t* ring = static_cast<uint8_t*>(ctx->ring);
     // device twin of the byte-value part of the ring (stream order makes a slot safe to reuse)
@@ -342,8 +359,8 @@ cudaError_t upload_narrow_on_host(lg_ctx* ctx, const uint64_t* h_idx, const floa
                 while (!queued[i - nslots].load(std::memory_order_acquire)) std::this_thread::yield();
                 e = cudaEventSynchronize(ctx->ring_ev[slot]);
             }
-            uint32_t* dst = reinterpret_cast<uint32_t*>(ring + slot * UP_SLOT_BYTES);
-            uint8_t* vdst = ring + slot * UP_SLOT_BYTES + UP_CHUNK * sizeof(uint32_t);
+            uint32_t* dst = reinterpret_cast<uint32_t*>(ring + slot * slot_bytes);
+            uint8_t* vdst = ring + slot * slot_bytes + UP_CHUNK * sizeof(uint32_t);
             UpPatch* pdst = reinterpret_cast<UpPatch*>(vdst + UP_CHUNK);
             const int64_t npatch = !pack_ok ? -1 : avx2 ? pack_values_avx2(h_val + off, vdst, len, pdst)
                                                         : pack_values_plain(h_val + off, vdst, len, pdst);
@@ -362,7 +379,13 @@ cudaError_t upload_narrow_on_host(lg_ctx* ctx, const uint64_t* h_idx, const floa
                         ++my_packed;
                     }
                 } else {
-                    e = cudaMemcpyAsync(d_val + off, h_val + off, len * sizeof(float), cudaMemcpyHostToDevice, ctx->stream);
+                    const float* vsrc = h_val + off;
+                    if (!src_pinned) {  // stage the raw values in the slot so that the copy is asynchronous
+                        float* rdst = reinterpret_cast<float*>(vdst + UP_CHUNK + UP_PATCH_BYTES);
+                        memcpy(rdst, vsrc, len * sizeof(float));
+                        vsrc = rdst;
+                    }
+                    e = cudaMemcpyAsync(d_val + off, vsrc, len * sizeof(float), cudaMemcpyHostToDevice, ctx->stream);
                     my_wire += len * sizeof(float);
                 }
             }
@@ -394,7 +417,8 @@ cudaError_t upload_narrow_on_host(lg_ctx* ctx, const uint64_t* h_idx, const floa
         for (int k = 0; k < 2 && e == cudaSuccess; ++k) e = cudaMallocAsync(&stage[k], UP_CHUNK * sizeof(uint64_t), ctx->stream);
         note(e);
         uint64_t i, nwide = 0;
-        const bool wide_ok = getenv("LG_UPLOAD_NO_WIDE") == nullptr;
+        // wide chunks are DMA'd straight from the caller's arrays: only when those are page-locked (see above)
+        const bool wide_ok = getenv("LG_UPLOAD_NO_WIDE") == nullptr && src_pinned;
         while (e == cudaSuccess && wide_ok) {
             if (nwide >= 2) e = cudaEventSynchronize(ctx->ring_ev[nslots + (nwide & 1)]);
             if (e != cudaSuccess || !take(false, &i)) break;

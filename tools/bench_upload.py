@@ -7,7 +7,8 @@ import legume_b200 as lg
 from legume_b200 import sim
 from legume_b200._lib import lib
 from legume_b200.pipeline import HotPath
-N = int(sys.argv[1]) if len(sys.argv) > 1 else 1_000_000
+_nums = [a for a in sys.argv[1:] if a.isdigit()]
+N = int(_nums[0]) if _nums else 1_000_000
 D, K, kk = 30000, 50, 10
 ctx = lg.Context(0); hp = HotPath(ctx)
 tabs = sim.make_tables(D, ntopic=8, nbatch=1, depth=1500, seed=42)
@@ -20,6 +21,9 @@ batch = torch.zeros(N, dtype=torch.int32, device="cuda")
 def now():
     torch.cuda.synchronize(); return time.perf_counter()
 res = {}
+PAGEABLE = "--pageable" in sys.argv  # the reference's Vec<u64> / Vec<f32> slices are ordinary (pageable) host memory
+if PAGEABLE:
+    h_ip, h_ix, h_v = (torch.from_numpy(t.numpy().copy()) for t in (h_ip, h_ix, h_v))
 modes = [("device_narrow", {"LG_UPLOAD_THREADS": "0"}), ("default", {}), ("host4", {"LG_UPLOAD_THREADS": "4"}),
          ("host8", {"LG_UPLOAD_THREADS": "8"}), ("host16", {"LG_UPLOAD_THREADS": "16"}), ("host32", {"LG_UPLOAD_THREADS": "32"}),
          ("host16_nowide", {"LG_UPLOAD_THREADS": "16", "LG_UPLOAD_NO_WIDE": "1"}),
@@ -43,4 +47,4 @@ for name, env in modes:
         rows.append({"upload_ms": 1e3 * (t1 - t0), "run_ms": 1e3 * (t2 - t1), "free_ms": 1e3 * (t3 - t2)})
     res[name] = rows
 bytes_up = h_ip.numel() * 8 + h_ix.numel() * 8 + h_v.numel() * 4
-print(json.dumps({"cells": N, "host_bytes": bytes_up, "host_cores": os.cpu_count(), "modes": res}))
+print(json.dumps({"cells": N, "pageable_host_arrays": PAGEABLE, "host_bytes": bytes_up, "host_cores": os.cpu_count(), "modes": res}))
