@@ -61,12 +61,21 @@ struct Barriers {
 // Every basis column (dim) gets its own power-of-two scale 2^e so that its largest magnitude lands in [4, 7.96) of the
 // 2^-20 fixed-point grid: a relative resolution of ~1e-7 of the column's range whatever its size (row-weighted bases,
 // U / sigma of a Nystrom basis), exact to undo in the epilogue.  A standard-normal basis keeps e = 0.
-__global__ void k_basis_colmax(const float* __restrict__ basis_kd, uint64_t D, int K, unsigned int* __restrict__ colmax_bits) {
-    const uint64_t e = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (e >= D * (uint64_t)K) return;
-    const float a = fabsf(basis_kd[e]);
-    // non-negative floats order as uints; NaN (0x7fc00000) and +inf (0x7f800000) come out on top and are caught below
-    atomicMax(&colmax_bits[e % K], __float_as_uint(a));
+__global__ void __launch_bounds__(256) k_basis_colmax(const float* __restrict__ basis_kd, uint64_t D, int K,
+                                                      unsigned int* __restrict__ colmax_bits) {
+    // per-block maxima in shared memory first: one global atomic per (block, column) instead of one per element
+    __shared__ unsigned int smax[128];
+    if (threadIdx.x < 128) smax[threadIdx.x] = 0u;
+    __syncthreads();
+    const uint64_t total = D * (uint64_t)K;
+    const uint64_t per_block = 256ull * 16ull;
+    const uint64_t e0 = (uint64_t)blockIdx.x * per_block;
+    for (uint64_t e = e0 + threadIdx.x; e < e0 + per_block && e < total; e += 256) {
+        // non-negative floats order as uints; NaN (0x7fc00000) and +inf (0x7f800000) come out on top and are caught below
+        atomicMax(&smax[e % K], __float_as_uint(fabsf(basis_kd[e])));
+    }
+    __syncthreads();
+    if ((int)threadIdx.x < K && smax[threadIdx.x]) atomicMax(&colmax_bits[threadIdx.x], smax[threadIdx.x]);
 }
 // exponent e of the column's scale; sets *bad for a non-finite column
 __device__ __forceinline__ int basis_col_exp(unsigned int max_bits, int* bad) {
@@ -662,14 +671,17 @@ int lg_project_raw_umma(lg_ctx* ctx, const lg_csc* m, const float* d_basis, int 
     LG_CUDA(ctx, cudaMemsetAsync(d_colmax, 0, 64 * sizeof(unsigned int), ctx->stream));
     {
         const uint64_t nb = D * (uint64_t)K;
-        LG_LAUNCH(ctx, k_basis_colmax, (unsigned)((nb + 255) / 256), 256, 0, d_basis, D, K, d_colmax);
+        LG_LAUNCH(ctx, k_basis_colmax, (unsigned)((nb + 4095) / 4096), 256, 0, d_basis, D, K, d_colmax);
         const uint64_t tot = Dpad * (uint64_t)NB;
         LG_LAUNCH(ctx, k_quantize_basis, (unsigned)((tot + 255) / 256), 256, 0, d_basis, D, K, NB, Dpad, d_colmax, d_bq, d_flag);
     }
+    // the flag travels home while K1b runs: the scan does not read the quantised basis, so the host round trip is hidden
+    // behind it and only the tensor kernel waits for the verdict (the scan's work is wasted in the rare fall-back case)
     int* h_flag = static_cast<int*>(ctx->pinned);
+    cudaEvent_t flag_ev;
+    LG_CUDA(ctx, cudaEventCreateWithFlags(&flag_ev, cudaEventDisableTiming));
     LG_CUDA(ctx, cudaMemcpyAsync(h_flag, d_flag, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
-    LG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    if (*h_flag) return LG_OK;  // a non-finite basis column: fall back to the CUDA-core kernel (which propagates it)
+    LG_CUDA(ctx, cudaEventRecord(flag_ev, ctx->stream));
 
     const char* tr = getenv("LG_K1_TRACE");
     const bool trace = tr && tr[0] == '1';
@@ -719,6 +731,16 @@ int lg_project_raw_umma(lg_ctx* ctx, const lg_csc* m, const float* d_basis, int 
     if (smem > ctx->smem_optin) return lg_fail(ctx, LG_ERR_INTERNAL, "k_project_umma: shared memory budget exceeded");
     LG_CUDA(ctx, cudaFuncSetAttribute(k_project_umma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const unsigned grid = (unsigned)(nsuper < (uint64_t)ctx->num_sms ? nsuper : (uint64_t)ctx->num_sms);
+    {
+        const cudaError_t fe = cudaEventSynchronize(flag_ev);
+        cudaEventDestroy(flag_ev);
+        LG_CUDA(ctx, fe);
+        if (*h_flag) {  // a non-finite basis column: fall back to the CUDA-core kernel (which propagates it)
+            if (trace)
+                for (int i = 0; i < 3; ++i) cudaEventDestroy(ev[i]);
+            return LG_OK;
+        }
+    }
     if (trace) cudaEventRecord(ev[1], ctx->stream);
     LG_LAUNCH(ctx, k_project_umma, grid, THREADS, smem, d_bm, m->ncols, D, d_bq, K, NB, nstages, d_scale, d_colmax, d_out);
     if (trace) {  // LG_K1_TRACE=1: per-kernel device times of this call (diagnostic; synchronises)
