@@ -180,7 +180,33 @@ __global__ void __launch_bounds__(SCALE_CELLS) k_scale_cells(float* __restrict__
     const int ncell = (ncols - cell0) < (uint64_t)SCALE_CELLS ? (int)(ncols - cell0) : SCALE_CELLS;
     const size_t total = (size_t)ncell * K;
     const float* src = proj + cell0 * K;
-    for (size_t e = threadIdx.x; e < total; e += SCALE_CELLS) tile[(e / K) * KS + (e % K)] = src[e];
+    // the tile is one contiguous run of ncell * K floats: 128-bit streams, (row, col) advanced without a division per element
+    const bool vec_io = ((reinterpret_cast<uintptr_t>(src) & 15) == 0);
+    const int total_i = (int)total, nvec = vec_io ? (total_i >> 2) : 0;
+    const int step_r = (4 * SCALE_CELLS) / K, step_c = (4 * SCALE_CELLS) % K;
+    {
+        int r = (4 * (int)threadIdx.x) / K, c = (4 * (int)threadIdx.x) % K;
+        for (int v = threadIdx.x; v < nvec; v += SCALE_CELLS) {
+            const float4 q = reinterpret_cast<const float4*>(src)[v];
+            const float qq[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                int cc = c + i, rr = r;
+                if (cc >= K) {
+                    cc -= K;
+                    ++rr;
+                }
+                tile[rr * KS + cc] = qq[i];
+            }
+            r += step_r;
+            c += step_c;
+            if (c >= K) {
+                c -= K;
+                ++r;
+            }
+        }
+        for (int e = 4 * nvec + threadIdx.x; e < total_i; e += SCALE_CELLS) tile[(e / K) * KS + (e % K)] = src[e];
+    }
     if (MODE == 0 && batch_sums) {
         for (uint32_t e = threadIdx.x; e < nbatch * (uint32_t)K; e += SCALE_CELLS) {
             const uint32_t b = e / K, k = e % K;
@@ -220,7 +246,29 @@ __global__ void __launch_bounds__(SCALE_CELLS) k_scale_cells(float* __restrict__
     }
     __syncthreads();
     float* dst = proj + cell0 * K;
-    for (size_t e = threadIdx.x; e < total; e += SCALE_CELLS) dst[e] = tile[(e / K) * KS + (e % K)];
+    {
+        int r = (4 * (int)threadIdx.x) / K, c = (4 * (int)threadIdx.x) % K;
+        for (int v = threadIdx.x; v < nvec; v += SCALE_CELLS) {
+            float qq[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                int cc = c + i, rr = r;
+                if (cc >= K) {
+                    cc -= K;
+                    ++rr;
+                }
+                qq[i] = tile[rr * KS + cc];
+            }
+            reinterpret_cast<float4*>(dst)[v] = make_float4(qq[0], qq[1], qq[2], qq[3]);
+            r += step_r;
+            c += step_c;
+            if (c >= K) {
+                c -= K;
+                ++r;
+            }
+        }
+        for (int e = 4 * nvec + threadIdx.x; e < total_i; e += SCALE_CELLS) dst[e] = tile[(e / K) * KS + (e % K)];
+    }
     if (MODE == 0 && minmax) {
 #pragma unroll
         for (int off = 16; off >= 1; off >>= 1) {
