@@ -18,7 +18,6 @@ __global__ void __launch_bounds__(1024) k_codes_gram(const float* __restrict__ p
                                                      const float* __restrict__ q, int kk, float* __restrict__ bout,
                                                      double* __restrict__ partials) {
     extern __shared__ float qs[];  // K * kk
-    __shared__ double red[32];
     for (int e = threadIdx.x; e < K * kk; e += blockDim.x) qs[e] = q[e];
     __syncthreads();
     const uint64_t cell = (uint64_t)blockIdx.x * LG_BLOCK_CELLS + threadIdx.x;
@@ -27,6 +26,8 @@ __global__ void __launch_bounds__(1024) k_codes_gram(const float* __restrict__ p
 #pragma unroll
     for (int i = 0; i < KK_MAX; ++i) b[i] = 0.0f;
     if (live) {
+        // every thread walks its own row (staging the block's rows through shared memory with coalesced loads was tried:
+        // 209 KB of tiles leave one block per SM with serialised phases, 0.70 -> 0.82 ms for the stage)
         const float* x = proj + (size_t)cell * K;
         for (int k = 0; k < K; ++k) {
             const float xv = x[k];
@@ -40,19 +41,21 @@ __global__ void __launch_bounds__(1024) k_codes_gram(const float* __restrict__ p
     }
     const int M = kk * (kk + 1) / 2;
     double* outp = partials + (size_t)blockIdx.x * M;
+    // the kk (kk + 1) / 2 Gram entries through the batched block sum (same tree as lg_block_sum_1024, one barrier in all)
+    __shared__ double stage[(KK_MAX * (KK_MAX + 1) / 2) * 32];
     int slot = 0;
 #pragma unroll
     for (int a = 0; a < KK_MAX; ++a) {
 #pragma unroll
         for (int c = 0; c < KK_MAX; ++c) {
             if (c >= a && a < kk && c < kk) {
-                const double v = live ? (double)b[a] * (double)b[c] : 0.0;
-                const double s = lg_block_sum_1024(v, red);
-                if (threadIdx.x == 0) outp[slot] = s;
+                lg_block_sums_stage1(live ? (double)b[a] * (double)b[c] : 0.0, slot, stage);
                 ++slot;
             }
         }
     }
+    __syncthreads();
+    lg_block_sums_stage2(stage, M, outp);
 }
 
 // K3b: V[k] = (sum_i U[i,k] * B[i]) / sigma_k per cell, plus block partials of the column sums.
@@ -61,7 +64,6 @@ __global__ void __launch_bounds__(1024) k_codes_vproj(const float* __restrict__ 
                                                       float* __restrict__ vout, double* __restrict__ partials) {
     __shared__ float us[KK_MAX * KK_MAX];
     __shared__ float sg[KK_MAX];
-    __shared__ double red[32];
     for (int e = threadIdx.x; e < kk * kk; e += blockDim.x) us[e] = u[e];
     if ((int)threadIdx.x < kk) sg[threadIdx.x] = sigma[threadIdx.x];
     __syncthreads();
@@ -90,13 +92,12 @@ __global__ void __launch_bounds__(1024) k_codes_vproj(const float* __restrict__ 
         }
     }
     double* outp = partials + (size_t)blockIdx.x * kk;
+    __shared__ double stage[KK_MAX * 32];
 #pragma unroll
-    for (int k = 0; k < KK_MAX; ++k) {
-        if (k < kk) {
-            const double s = lg_block_sum_1024(live ? (double)v[k] : 0.0, red);
-            if (threadIdx.x == 0) outp[k] = s;
-        }
-    }
+    for (int k = 0; k < KK_MAX; ++k)
+        if (k < kk) lg_block_sums_stage1(live ? (double)v[k] : 0.0, k, stage);
+    __syncthreads();
+    lg_block_sums_stage2(stage, kk, outp);
 }
 
 // K3c: warp-ballot sign packer.  V is cell-major (kk floats per cell); a warp takes 32 cells =

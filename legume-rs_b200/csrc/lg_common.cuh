@@ -184,6 +184,25 @@ __device__ __forceinline__ double lg_block_sum_1024(double v, double* smem32) {
     return w;
 }
 
+// Many sums at once with the SAME tree as lg_block_sum_1024 (so the results are bit-identical to it): stage 1 — every
+// warp butterflies value m and lane 0 parks it in stage[m * 32 + warp]; after ONE barrier, stage 2 — warp (m % 32)
+// butterflies the 32 warp sums of value m.  lg_block_sum_1024 pays two barriers and an idle second stage per value.
+constexpr int LG_SUMS_BATCH = 64;  // values per staging round: 64 * 32 doubles = 16 KB of shared memory
+__device__ __forceinline__ void lg_block_sums_stage1(double v, int m, double* stage) {
+    v = lg_butterfly32(v);
+    if ((threadIdx.x & 31) == 0) stage[m * 32 + (threadIdx.x >> 5)] = v;
+}
+// call after __syncthreads(); writes out[m] for m in [0, count); ends with a barrier so that `stage` can be reused
+__device__ __forceinline__ void lg_block_sums_stage2(const double* stage, int count, double* out) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int m = warp; m < count; m += 32) {
+        double w = stage[m * 32 + lane];
+        w = lg_butterfly32(w);
+        if (lane == 0) out[m] = w;
+    }
+    __syncthreads();
+}
+
 // host-side small dense math (lg_hostmath.cpp) — plain C++, no CUDA, no oracle
 void lgh_householder_q(const float* a_kr, int K, int r, float* q_kr);
 void lgh_jacobi_eig(const double* g, int n, double* evals, double* evecs);

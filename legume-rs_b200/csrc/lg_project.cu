@@ -105,20 +105,26 @@ extern "C" int lg_project_raw(lg_ctx* ctx, const lg_csc* m, const float* basis_k
 __global__ void __launch_bounds__(1024) k_batch_partials(const float* __restrict__ proj, int K, uint64_t ncols,
                                                          const uint32_t* __restrict__ batch, uint32_t nbatch,
                                                          double* __restrict__ partials) {
-    __shared__ double red[32];
+    __shared__ double stage[LG_SUMS_BATCH * 32];
     const uint64_t cell = (uint64_t)blockIdx.x * LG_BLOCK_CELLS + threadIdx.x;
     const bool live = cell < ncols;
     const uint32_t myb = live ? (batch ? batch[cell] : 0u) : 0xffffffffu;
     const float* row = proj + (size_t)cell * K;
     double* outp = partials + (size_t)blockIdx.x * nbatch * (K + 1);
-    for (uint32_t b = 0; b < nbatch; ++b) {
-        const bool mine = live && myb == b;
-        for (int k = 0; k <= K; ++k) {
+    // nbatch * (K + 1) sums (value k of batch b, then the cell count), LG_SUMS_BATCH at a time: same tree as
+    // lg_block_sum_1024, one barrier per batch instead of two per value
+    const uint32_t M = nbatch * (uint32_t)(K + 1);
+    for (uint32_t base = 0; base < M; base += LG_SUMS_BATCH) {
+        const uint32_t cnt = min((uint32_t)LG_SUMS_BATCH, M - base);
+        for (uint32_t i = 0; i < cnt; ++i) {
+            const uint32_t e = base + i, b = e / (uint32_t)(K + 1);
+            const int k = (int)(e % (uint32_t)(K + 1));
             double v = 0.0;
-            if (mine) v = (k < K) ? (double)row[k] : 1.0;
-            const double s = lg_block_sum_1024(v, red);
-            if (threadIdx.x == 0) outp[(size_t)b * (K + 1) + k] = s;
+            if (live && myb == b) v = (k < K) ? (double)row[k] : 1.0;
+            lg_block_sums_stage1(v, (int)i, stage);
         }
+        __syncthreads();
+        lg_block_sums_stage2(stage, (int)cnt, outp + base);
     }
 }
 
