@@ -144,8 +144,18 @@ __global__ void k_partials_finalize(const double* __restrict__ partials, uint64_
                                     double* __restrict__ out) {
     const uint32_t m = blockIdx.x * blockDim.x + threadIdx.x;
     if (m >= M) return;
+    // the adds are one dependent chain in block order (that order is the contract); the loads are not: 16 partials are
+    // fetched at a time so that the chain waits for one memory round trip per 16 blocks instead of one per block
     double s = 0.0;
-    for (uint64_t b = 0; b < nblocks; ++b) s = s + partials[b * M + m];
+    uint64_t b = 0;
+    for (; b + 16 <= nblocks; b += 16) {
+        double v[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] = partials[(b + i) * M + m];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) s = s + v[i];
+    }
+    for (; b < nblocks; ++b) s = s + partials[b * M + m];
     out[m] = s;
 }
 
