@@ -9,6 +9,10 @@ import os
 import sys
 
 os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+# only the report reaches stdout: NCCL prints its version banner on fd 1
+sys.stdout.flush()
+_REAL_STDOUT = os.dup(1)
+os.dup2(2, 1)
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path[:0] = [ROOT, os.path.join(ROOT, "legume-rs_b200")]
@@ -103,9 +107,9 @@ if world > 1:
         report["knn_idx_bit_exact"] = same(gathered["kidx"][0], widx)
         report["knn_dist_bit_exact"] = same(gathered["kdist"][0], wdist)
         report["ok"] = all(v for key, v in report.items() if key.endswith("bit_exact"))
-        print(json.dumps(report))
+        os.write(_REAL_STDOUT, (json.dumps(report) + "\n").encode())
     dist.barrier()
     dist.destroy_process_group()
 else:
     report["note"] = "single rank: nothing to compare"
-    print(json.dumps(report))
+    os.write(_REAL_STDOUT, (json.dumps(report) + "\n").encode())
