@@ -14,7 +14,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
 sys.path[:0] = [ROOT, os.path.join(ROOT, "tests")]
 import oracle as orc  # noqa: E402
-from util import random_csc  # noqa: E402
+from util import nystrom_f64, random_csc  # noqa: E402
 
 
 def build():
@@ -53,7 +53,32 @@ def build():
     return g
 
 
+def build_next():
+    """tests/golden/next_small.npz: the steps either side of the path on a small seeded input — per-gene
+    running statistics (oracle = reference f32 folds) and the Nystrom re-projection (the oracle's f32 result AND the float64
+    restatement the CUDA path is held to)"""
+    D, N, K, P = 150, 500, 10, 6
+    rng = np.random.default_rng(20241018)
+    ip, ix, v = random_csc(rng, D, N, density=0.15, empty_every=61)
+    basis_dk = (rng.standard_normal((K, D)) * (10.0 ** rng.uniform(-2, 1, K))[:, None]).astype(np.float32)
+    delta = np.exp(0.4 * rng.standard_normal((P, D))).astype(np.float32)
+    delta[:, ::11] = 0.0
+    pb = rng.integers(0, P, N).astype(np.uint32)
+    g = dict(D=D, N=N, K=K, P=P, indptr=ip, indices=ix, data=v, basis_dk=basis_dk, delta_dp=delta, pb=pb)
+    g["npos"], g["s1"], g["s2"] = orc.row_stats(ip, ix, v, D)
+    g["mean"], g["variance"], g["sd"] = orc.row_stats_moments(g["s1"], g["s2"], N)
+    g["nystrom_oracle"] = orc.nystrom_project(ip, ix, v, D, basis_dk, None, None, 1e4)
+    g["nystrom_oracle_delta"] = orc.nystrom_project(ip, ix, v, D, basis_dk, delta, pb, 1e4)
+    g["nystrom_exact"] = nystrom_f64(ip, ix, v, D, basis_dk, None, None, 1e4)
+    g["nystrom_exact_delta"] = nystrom_f64(ip, ix, v, D, basis_dk, delta, pb, 1e4)
+    return g
+
+
 if __name__ == "__main__":
+    gn = build_next()
+    outn = os.path.join(HERE, "next_small.npz")
+    np.savez_compressed(outn, **gn)
+    print(outn, os.path.getsize(outn), "bytes;", len(gn), "arrays")
     g = build()
     out = os.path.join(HERE, "hotpath_small.npz")
     np.savez_compressed(out, **g)

@@ -99,3 +99,43 @@ def test_cuda_path_hits_the_golden_vectors(lg, ctx):
     assert close(fit.mu_adjusted["mean"], G["mu_adjusted"], TOL) and close(fit.delta["mean"], G["delta"], TOL)
     f2c, nc = lg.compute_fine_to_coarse_mapping(ctx, G["codes"], G["group"], S, 4)
     assert nc == int(G["ncoarse_dim4"]) and np.array_equal(f2c, G["f2c_dim4"])
+
+
+# ---- the steps either side of the path: tests/golden/next_small.npz -------------------------------
+GN = np.load(os.path.join(HERE, "golden", "next_small.npz"))
+
+
+def test_generator_reproduces_the_committed_next_vectors():
+    sys.path.insert(0, os.path.join(HERE, "golden"))
+    import make_golden
+    fresh = make_golden.build_next()
+    assert sorted(fresh) == sorted(GN.files)
+    for key in GN.files:
+        a, b = np.asarray(fresh[key]), GN[key]
+        if key.startswith("nystrom_exact"):  # float64 numpy restatement: BLAS / pairwise sums may differ in the last bits
+            assert a.shape == b.shape and np.allclose(a, b, rtol=1e-11, atol=1e-11), key
+        else:
+            assert a.shape == b.shape and a.tobytes() == b.tobytes(), key
+    # the oracle's f32 folds against exact arithmetic: within the reference's own conditioning
+    assert close(GN["nystrom_oracle"], GN["nystrom_exact"], 2e-3) and close(GN["nystrom_oracle_delta"], GN["nystrom_exact_delta"], 2e-3)
+    assert GN["s1"].sum() == GN["data"].sum() and GN["npos"].sum() == (GN["data"] > 0).sum()
+
+
+@pytest.mark.gpu
+def test_cuda_path_hits_the_golden_next_vectors(lg, ctx):
+    D, N, P = (int(GN[k]) for k in ("D", "N", "P"))
+    data = lg.SparseIoVec.from_csc(ctx, GN["indptr"], GN["indices"], GN["data"], D)
+    st = data.streaming_sparse_running_stats()
+    assert st.ncols_processed() == N
+    assert np.array_equal(st.count_positives(), GN["npos"]) and np.array_equal(st.sum(), GN["s1"])
+    assert np.array_equal(st._s2.astype(np.float32), GN["s2"])
+    assert np.array_equal(st.mean(), GN["mean"]) and np.array_equal(st.variance(), GN["variance"])
+    assert np.array_equal(st.std(), GN["sd"], equal_nan=True)
+    cs = np.abs(GN["nystrom_exact"]).max(0) + 1e-30  # per-column scale: the basis columns span three decades
+    got = data.nystrom_project(GN["basis_dk"], None, 1e4)
+    assert close(got / cs, GN["nystrom_exact"] / cs, TOL), max_err(got / cs, GN["nystrom_exact"] / cs)
+    data.col_to_group = GN["pb"]  # the pseudobulk of a cell is its group id
+    got_d = data.nystrom_project(GN["basis_dk"], GN["delta_dp"], 1e4)
+    csd = np.abs(GN["nystrom_exact_delta"]).max(0) + 1e-30
+    assert close(got_d / csd, GN["nystrom_exact_delta"] / csd, TOL), max_err(got_d / csd, GN["nystrom_exact_delta"] / csd)
+    assert close(got_d, GN["nystrom_oracle_delta"], 2e-3)
