@@ -573,6 +573,66 @@ class SparseIoVec {
     DMatrix batch_proj_;
 };
 
+// SplitMix64 avalanche of (base, salt): matrix-util/src/rand_util.rs:30-35
+inline uint64_t mix_seed(uint64_t base, uint64_t salt) {
+    uint64_t z = base ^ (salt * 0x9E3779B97F4A7C15ull);
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+}
+
+// Several modalities over the same cells (data-beans/src/sparse_io_stack.rs): RandProjOps runs every modality with its
+// own basis (the reference derives it from mix_seed(seed, m); here the bases are inputs) and stacks the results
+// vertically (data-beans-alg/src/random_projection.rs:200-260)
+class SparseIoStack {
+   public:
+    explicit SparseIoStack(std::vector<const SparseIoVec*> stack) : stack_(std::move(stack)) {
+        if (stack_.empty()) throw Error(LG_ERR_INVALID, "SparseIoStack: empty stack");
+    }
+    size_t num_columns() const {
+        size_t n = 0;
+        for (auto* x : stack_) n = std::max(n, x->num_columns());
+        return n;
+    }
+    size_t num_rows() const {
+        size_t d = 0;
+        for (auto* x : stack_) d += x->num_rows();
+        return d;
+    }
+    template <typename T>
+    RandColProjOut project_columns_with_batch_correction(const std::vector<DMatrix>& bases_dk, std::optional<size_t> block_size,
+                                                         const std::vector<T>* batch_membership) const {
+        if (bases_dk.size() != stack_.size()) throw Error(LG_ERR_INVALID, "SparseIoStack: one basis per modality");
+        const size_t n = num_columns();
+        std::vector<T> cut;
+        if (batch_membership) cut.assign(batch_membership->begin(), batch_membership->begin() + std::min(n, batch_membership->size()));
+        std::vector<RandColProjOut> parts;
+        for (size_t m = 0; m < stack_.size(); ++m)
+            parts.push_back(stack_[m]->project_columns_with_batch_correction(bases_dk[m], block_size, batch_membership ? &cut : nullptr));
+        size_t Ktot = 0, Dtot = 0;
+        const size_t K = parts[0].proj.nrows;
+        for (auto& p : parts) {
+            if (p.proj.ncols != n || p.proj.nrows != K) throw Error(LG_ERR_INVALID, "SparseIoStack: modalities disagree on the shape");
+            Ktot += p.proj.nrows;
+            Dtot += p.basis.nrows;
+        }
+        RandColProjOut out{DMatrix(Dtot, K), DMatrix(Ktot, n)};
+        size_t r0 = 0, d0 = 0;
+        for (auto& p : parts) {  // concatenate_vertical of the bases (rows) and of the projections (dims)
+            for (size_t k = 0; k < K; ++k)
+                for (size_t g = 0; g < p.basis.nrows; ++g) out.basis(d0 + g, k) = p.basis(g, k);
+            for (size_t j = 0; j < n; ++j)
+                for (size_t k = 0; k < K; ++k) out.proj(r0 + k, j) = p.proj(k, j);
+            r0 += K;
+            d0 += p.basis.nrows;
+        }
+        return out;
+    }
+
+   private:
+    std::vector<const SparseIoVec*> stack_;
+};
+
 // matrix-util/src/knn/mod.rs:62-299 with the exact backend; names are the column indices 0..n-1 unless given
 class ColumnDict {
    public:

@@ -236,6 +236,21 @@ int main() {
         // the reference's f32 folds (the oracle) sit up to ~5e-4 from exact arithmetic here; see tests/test_gpu_next.py
         CHECK(ny.nrows == 12 && ny.ncols == 500 && close_all(ny.data.data(), want.data(), want.size(), 2e-3));
     }
+    {  // ---- SparseIoStack: per-modality projection stacked vertically (random_projection.rs:200-260) ----
+        std::mt19937 r1(31), r2(32);
+        Csc a = random_counts(r1, 200, 300, 0.1), b = random_counts(r2, 90, 300, 0.15);
+        SparseIoVec va(ctx, a.indptr, a.indices, a.data, 200), vb(ctx, b.indptr, b.indices, b.data, 90);
+        std::mt19937 rb(33);
+        std::vector<DMatrix> bases{gaussian(rb, 200, 8), gaussian(rb, 90, 8)};
+        SparseIoStack stack({&va, &vb});
+        RandColProjOut st = stack.project_columns_with_batch_correction<uint32_t>(bases, std::nullopt, nullptr);
+        RandColProjOut pa = va.project_columns(bases[0]), pb2 = vb.project_columns(bases[1]);
+        bool same = st.proj.nrows == 16 && st.proj.ncols == 300 && st.basis.nrows == 290 && stack.num_rows() == 290;
+        for (size_t j = 0; j < 300 && same; ++j)
+            for (size_t k = 0; k < 8; ++k) same = same && st.proj(k, j) == pa.proj(k, j) && st.proj(8 + k, j) == pb2.proj(k, j);
+        CHECK(same);
+        CHECK(mix_seed(0, 1) == 0xE220A8397B1DCDAFull);  // first output of SplitMix64 seeded with 0
+    }
     {  // ---- error behaviour: anyhow::Error -> legume::Error, never a crash ----
         bool threw = false;
         try {
