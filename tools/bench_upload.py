@@ -27,10 +27,14 @@ if PAGEABLE:
 modes = [("device_narrow", {"LG_UPLOAD_THREADS": "0"}), ("default", {}), ("host4", {"LG_UPLOAD_THREADS": "4"}),
          ("host8", {"LG_UPLOAD_THREADS": "8"}), ("host16", {"LG_UPLOAD_THREADS": "16"}), ("host32", {"LG_UPLOAD_THREADS": "32"}),
          ("host16_nowide", {"LG_UPLOAD_THREADS": "16", "LG_UPLOAD_NO_WIDE": "1"}),
-         ("host16_nopack", {"LG_UPLOAD_THREADS": "16", "LG_UPLOAD_NO_PACK": "1"})]
+         ("host16_nopack", {"LG_UPLOAD_THREADS": "16", "LG_UPLOAD_NO_PACK": "1"}),
+         ("wide2", {"LG_UPLOAD_WIDE_DEPTH": "2"}), ("wide3", {"LG_UPLOAD_WIDE_DEPTH": "3"}), ("wide4", {"LG_UPLOAD_WIDE_DEPTH": "4"}),
+         ("wide6", {"LG_UPLOAD_WIDE_DEPTH": "6"}), ("wide8", {"LG_UPLOAD_WIDE_DEPTH": "8"})]
+if "--wide-only" in sys.argv:
+    modes = [m for m in modes if m[0].startswith("wide")]
 os.environ["LG_UPLOAD_TRACE"] = "1"
 for name, env in modes:
-    for k in ("LG_UPLOAD_THREADS", "LG_UPLOAD_NO_WIDE", "LG_UPLOAD_NO_PACK"):
+    for k in ("LG_UPLOAD_THREADS", "LG_UPLOAD_NO_WIDE", "LG_UPLOAD_NO_PACK", "LG_UPLOAD_WIDE_DEPTH"):
         os.environ.pop(k, None)
     os.environ.update(env)
     rows = []
