@@ -20,7 +20,9 @@ def declared_symbols():
 def test_header_declares_the_path():
     syms = declared_symbols()
     for must in ["lg_csc_upload", "lg_project", "lg_binary_codes", "lg_assign_groups", "lg_collapse_basic",
-                 "lg_collapse_batch", "lg_gamma_calibrate", "lg_optimize_single", "lg_optimize_batched", "lg_knn_topk"]:
+                 "lg_collapse_batch", "lg_gamma_calibrate", "lg_optimize_single", "lg_optimize_batched", "lg_knn_topk",
+                 "lg_knn_match_batches", "lg_collect_matched_stat", "lg_pb_match", "lg_collect_matched_stat_coarse",
+                 "lg_row_stats", "lg_nystrom_project"]:
         assert must in syms
 
 
