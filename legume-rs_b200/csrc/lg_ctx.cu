@@ -478,6 +478,8 @@ extern "C" int lg_csc_upload(lg_ctx* ctx, const uint64_t* indptr, const uint64_t
     const uint64_t ncols = col_hi - col_lo;
     const uint64_t base = indptr[col_lo], end = indptr[col_hi];
     LG_REQUIRE(ctx, end >= base, "lg_csc_upload: indptr not monotone");
+    for (uint64_t j = col_lo; j < col_hi; ++j)  // a column pointer running backwards would send the kernels out of bounds
+        if (indptr[j + 1] < indptr[j]) return lg_fail(ctx, LG_ERR_INVALID, "lg_csc_upload: indptr not monotone");
     const uint64_t nnz = end - base;
     LG_REQUIRE(ctx, nnz == 0 || (indices && data), "lg_csc_upload: null indices/data");
     lg_csc* m = new lg_csc();

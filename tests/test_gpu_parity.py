@@ -47,6 +47,11 @@ def test_csc_upload_round_trip_and_range_check(lg, ctx):
     bad[3] = 300
     with pytest.raises(lg.LegumeError):
         lg.CscBlock.upload(ctx, ip, bad, v, 300)
+    back = ip.copy()
+    back[10], back[11] = back[11], back[10] - 1 if back[10] > 0 else 0  # a column pointer running backwards
+    if back[11] < back[10]:
+        with pytest.raises(lg.LegumeError):
+            lg.CscBlock.upload(ctx, back, ix, v, 300)
 
 
 @pytest.mark.parametrize("mode", ["default", "host_only", "host_no_pack", "device_only"])
