@@ -71,7 +71,21 @@ const char* lg_version(void);
 int lg_csc_upload(lg_ctx* ctx, const uint64_t* indptr, const uint64_t* indices, const float* data,
                   uint64_t nrows, uint64_t col_lo, uint64_t col_hi, const uint32_t* row_remap,
                   lg_csc** out);
-/* wrap arrays that already live on the device (no copy; the caller keeps them alive) */
+/* the same with the remap's length stated (nrows_backend): a backend row outside it is LG_ERR_INVALID instead of
+ * the caller's promise.  With a remap the block is made CANONICAL the way read_columns_csc does (read.rs:246-281):
+ * entries whose row maps to UINT32_MAX are dropped; a column that is no longer strictly ascending is stably sorted
+ * by row and equal rows are folded by summing in that order (so the block's nnz may be smaller than the input's).
+ * Without a remap the arrays must already be canonical CSC (rows strictly ascending inside a column) — checked
+ * on the device, LG_ERR_INVALID otherwise: the projection bitmap, the running statistics and the matched-column
+ * kernels rely on it. */
+int lg_csc_upload_remap(lg_ctx* ctx, const uint64_t* indptr, const uint64_t* indices, const float* data,
+                        uint64_t nrows, uint64_t col_lo, uint64_t col_hi, const uint32_t* row_remap,
+                        uint64_t nrows_backend, lg_csc** out);
+/* columns of several device blocks side by side over one feature axis (SparseIoVec::push of several backends,
+ * data-beans/src/sparse_io_vector/mod.rs); the parts stay valid and owned by the caller */
+int lg_csc_concat(lg_ctx* ctx, const lg_csc* const* parts, uint32_t nparts, lg_csc** out);
+/* wrap arrays that already live on the device (no copy; the caller keeps them alive).  Canonical form is checked
+ * lazily, by the first call that relies on it. */
 int lg_csc_wrap_device(lg_ctx* ctx, const uint64_t* d_indptr, const uint32_t* d_indices,
                        const float* d_values, uint64_t nrows, uint64_t ncols, uint64_t nnz,
                        lg_csc** out);
@@ -88,7 +102,8 @@ int lg_csc_download(lg_ctx* ctx, const lg_csc* m, uint64_t* indptr, uint64_t* in
  * project_columns_weighted_seeded (data-beans-alg/src/random_projection.rs:341-495).  The basis
  * is an INPUT (identical-projection-matrix contract): basis_kd is K x D column-major, i.e. the
  * reference's `basis_dk.transpose()` (:360); for the weighted variant the caller zeroes/scales
- * rows exactly as :438-444 do.  batch_of_cell: u32[ncols] in [0, nbatch) or NULL.
+ * rows exactly as :438-444 do.  batch_of_cell: u32[ncols] in [0, nbatch) or NULL; a label outside that
+ * range is LG_ERR_INVALID.
  * out_proj: K x ncols. */
 int lg_project(lg_ctx* ctx, const lg_csc* m, const float* basis_kd, int K,
                const uint32_t* batch_of_cell, uint32_t nbatch, float* out_proj);
@@ -108,6 +123,25 @@ int lg_block_partials_finalize(lg_ctx* ctx, const double* d_partials, uint64_t n
 int lg_proj_centre_scale(lg_ctx* ctx, float* d_proj, int K, uint64_t ncols, const uint32_t* d_batch,
                          uint32_t nbatch, const double* d_batch_sums, float* d_minmax);
 int lg_proj_clamp_rescale(lg_ctx* ctx, float* d_proj, int K, uint64_t ncols);
+/* EXACT-ORDER mode of the same stage: the reference's arithmetic operation by operation (ascending row, x divided by the
+ * norm first, product and sum rounded separately — random_projection.rs:181-194, dmatrix_util.rs:770-778; batch means
+ * as f32 left folds over the batch's cells in ascending order — random_projection.rs:380-387), so that for count data
+ * (whole numbers below 65536, whose ln_1p comes from a libm-built table) the projection is BIT-IDENTICAL to the CPU
+ * path and so are the codes, groups and sums derived from it.  Several times slower than lg_project (CUDA cores,
+ * one basis row gathered per non-zero); lg_project stays the throughput path with a 1e-5 contract.
+ *   lg_project_exact        composite, same arguments as lg_project
+ *   lg_project_raw_exact    project_columns_visitor only
+ *   lg_proj_batch_fold      continues the per-(batch, dim) f32 folds sum[nbatch*K] / cnt[nbatch] over this block's cells
+ *                           (device pointers, zero them first); cell shards call it one after the other in rank order,
+ *                           handing sum / cnt on, so the folds are those of one GPU
+ *   lg_proj_centre_scale_exact   subtract -(sum / (f32)cnt), per-cell standardise, track (min, max) */
+int lg_project_exact(lg_ctx* ctx, const lg_csc* m, const float* basis_kd, int K,
+                     const uint32_t* batch_of_cell, uint32_t nbatch, float* out_proj);
+int lg_project_raw_exact(lg_ctx* ctx, const lg_csc* m, const float* basis_kd, int K, float* out_proj);
+int lg_proj_batch_fold(lg_ctx* ctx, const float* d_proj, int K, uint64_t ncols, const uint32_t* d_batch,
+                       uint32_t nbatch, float* d_sum, uint64_t* d_cnt);
+int lg_proj_centre_scale_exact(lg_ctx* ctx, float* d_proj, int K, uint64_t ncols, const uint32_t* d_batch,
+                               uint32_t nbatch, const float* d_fold_sum, const uint64_t* d_fold_cnt, float* d_minmax);
 
 /* ---- stage 2: binary codes -----------------------------------------------------------------
  * replaces binary_sort_columns (random_projection.rs:535-564) = rsvd (matrix-util/src/

@@ -1023,6 +1023,7 @@ extern "C" int lg_collect_matched_stat(lg_ctx* ctx, const lg_csc* m, const uint3
                "lg_collect_matched_stat: null argument");
     LG_REQUIRE(ctx, T >= 1 && T <= 1024 && S >= 1, "lg_collect_matched_stat: T must be in [1, 1024] and S >= 1");
     cudaSetDevice(ctx->device);
+    LG_TRY(lg_csc_require_canonical(ctx, m, "lg_collect_matched_stat"));
     LgStage st(ctx);
     const uint64_t N = m->ncols, D = m->nrows;
     LG_REQUIRE(ctx, N < 0xFFFFFFFFull, "lg_collect_matched_stat: more than 2^32-1 cells in one block");

@@ -27,6 +27,7 @@ struct lg_ctx {
     size_t ring_slots = 0;
     size_t ring_slot_bytes = 0;
     std::vector<cudaEvent_t> ring_ev;
+    float* log1p_tab = nullptr;  // libm log1pf of 0 .. 65535 for the exact-order projection (built on first use)
 };
 
 struct lg_csc {
@@ -38,6 +39,8 @@ struct lg_csc {
     bool pooled = false;  // owned arrays came from the stream-ordered pool (cudaMallocAsync): freed with cudaFreeAsync
     // cached "all values are small non-negative integers" (-1 unknown); blocks are immutable
     mutable int int_valued = -1;
+    // cached "rows strictly ascending and in range inside every column" (-1 unknown): see lg_csc_require_canonical
+    mutable int canonical = -1;
 };
 
 inline int lg_fail(lg_ctx* ctx, int code, const std::string& msg) {
@@ -202,6 +205,11 @@ __device__ __forceinline__ void lg_block_sums_stage2(const double* stage, int co
     }
     __syncthreads();
 }
+
+// LG_OK when rows are strictly ascending and in range inside every column (checked once per block, cached)
+int lg_csc_require_canonical(lg_ctx* ctx, const lg_csc* m, const char* who);
+// rejects labels outside [0, bound) with LG_ERR_INVALID (one small kernel + a flag read-back)
+int lg_check_labels(lg_ctx* ctx, const uint32_t* d_label, uint64_t n, uint32_t bound, const char* what);
 
 // host-side small dense math (lg_hostmath.cpp) — plain C++, no CUDA, no oracle
 void lgh_householder_q(const float* a_kr, int K, int r, float* q_kr);

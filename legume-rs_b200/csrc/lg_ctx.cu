@@ -1,6 +1,7 @@
 // lg_ctx.cu — context lifecycle and the device-resident CSC container (the data feed).
 #include <immintrin.h>
 
+#include <algorithm>
 #include <atomic>
 #include <cmath>
 #include <cstdlib>
@@ -60,6 +61,7 @@ extern "C" int lg_ctx_destroy(lg_ctx* c) {
     if (c->own_stream) cudaStreamDestroy(c->stream);
     if (c->pinned) cudaFreeHost(c->pinned);
     if (c->ring) cudaFreeHost(c->ring);
+    if (c->log1p_tab) cudaFree(c->log1p_tab);
     for (auto e : c->ring_ev) cudaEventDestroy(e);
     delete c;
     return LG_OK;
@@ -465,9 +467,156 @@ cudaError_t upload_narrow_on_host(lg_ctx* ctx, const uint64_t* h_idx, const floa
 }
 }  // namespace
 
+
+// ---- canonical CSC (rows strictly ascending inside every column) -------------------------------------------------
+// The kernels rely on it: K1's pattern bitmap and K10's packed fields need unique rows, K8 binary-searches a column's
+// rows.  The reference guarantees it at the same place (read_columns_csc, data-beans/src/sparse_io_vector/read.rs:246-281).
+// Entry t+1 may be <= entry t only when t+1 starts a column (empty columns share a start).
+__global__ void k_check_canonical(const uint64_t* __restrict__ indptr, const uint32_t* __restrict__ indices, uint64_t ncols,
+                                  uint64_t nnz, uint64_t nrows, int* __restrict__ flag) {
+    uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (; t < nnz; t += stride) {
+        const uint32_t a = indices[t];
+        if ((uint64_t)a >= nrows) atomicOr(flag, 2);
+        if (t + 1 < nnz && indices[t + 1] <= a) {
+            // upper_bound(indptr, t + 1) - 1 = the column holding entry t + 1; canonical iff that column starts there
+            uint64_t lo = 0, hi = ncols + 1;
+            while (lo < hi) {
+                const uint64_t mid = (lo + hi) >> 1;
+                if (indptr[mid] <= t + 1) lo = mid + 1;
+                else hi = mid;
+            }
+            if (lo == 0 || indptr[lo - 1] != t + 1) atomicOr(flag, 1);
+        }
+    }
+}
+
+// LG_OK when the block is canonical (cached on the block: blocks are immutable); LG_ERR_INVALID otherwise
+int lg_csc_require_canonical(lg_ctx* ctx, const lg_csc* m, const char* who) {
+    if (m->canonical < 0) {
+        int h = 0;
+        if (m->nnz) {
+            int* d_flag = nullptr;
+            LG_CUDA(ctx, cudaMallocAsync(&d_flag, sizeof(int), ctx->stream));
+            LG_CUDA(ctx, cudaMemsetAsync(d_flag, 0, sizeof(int), ctx->stream));
+            uint64_t blocks = (m->nnz + 2047) / 2048;
+            if (blocks > (uint64_t)ctx->num_sms * 16) blocks = (uint64_t)ctx->num_sms * 16;
+            LG_LAUNCH(ctx, k_check_canonical, (unsigned)blocks, 256, 0, m->indptr, m->indices, m->ncols, m->nnz, m->nrows, d_flag);
+            int* h_flag = static_cast<int*>(ctx->pinned) + 8;
+            LG_CUDA(ctx, cudaMemcpyAsync(h_flag, d_flag, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+            LG_CUDA(ctx, cudaFreeAsync(d_flag, ctx->stream));
+            LG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+            h = *h_flag;
+        }
+        m->canonical = h ? 0 : 1;
+    }
+    if (!m->canonical)
+        return lg_fail(ctx, LG_ERR_INVALID, std::string(who) + ": the CSC block is not canonical (rows must be strictly ascending and "
+                                                               "in range inside every column; lg_csc_upload_remap sorts and merges)");
+    return LG_OK;
+}
+
+namespace {
+// the per-backend row remap of read_columns_csc (read.rs:202-281) on the host: map every row, drop the rows the shared
+// axis does not have (UINT32_MAX), and where a column is no longer strictly ascending sort it (stable) and fold equal
+// rows by summing in that order.  Column ranges are independent, so they are cut over threads; two passes (sizes, fill).
+struct RemapOut {
+    std::vector<uint64_t> indptr;
+    std::vector<uint32_t> idx;
+    std::vector<float> val;
+    int bad = 0;  // 1: backend row outside the remap, 2: mapped row outside the shared axis
+};
+void remap_columns(const uint64_t* indptr, const uint64_t* indices, const float* data, uint64_t col_lo, uint64_t col_hi,
+                   const uint32_t* remap, uint64_t nrows_backend, uint64_t nrows_out, RemapOut* out) {
+    const uint64_t ncols = col_hi - col_lo;
+    out->indptr.assign(ncols + 1, 0);
+    unsigned nt = std::thread::hardware_concurrency();
+    nt = nt < 1 ? 1 : (nt > 16 ? 16 : nt);
+    if (ncols < 4096) nt = 1;
+    std::vector<std::vector<std::pair<uint32_t, float>>> cols(ncols);
+    std::atomic<int> bad{0};
+    auto work = [&](unsigned w) {
+        const uint64_t a = ncols * w / nt, b = ncols * (w + 1) / nt;
+        for (uint64_t j = a; j < b; ++j) {
+            auto& c = cols[j];
+            const uint64_t s = indptr[col_lo + j], e = indptr[col_lo + j + 1];
+            c.reserve(e - s);
+            bool sorted = true;
+            for (uint64_t t = s; t < e; ++t) {
+                const uint64_t r = indices[t];
+                if (r >= nrows_backend) {
+                    bad.fetch_or(1);
+                    continue;
+                }
+                const uint32_t g = remap[r];
+                if (g == 0xFFFFFFFFu) continue;  // g2c == None: the row is not part of the shared axis (read.rs:217)
+                if ((uint64_t)g >= nrows_out) {
+                    bad.fetch_or(2);
+                    continue;
+                }
+                if (!c.empty() && c.back().first >= g) sorted = false;
+                c.emplace_back(g, data[t]);
+            }
+            if (!sorted) {  // read.rs:262-277
+                std::stable_sort(c.begin(), c.end(), [](const std::pair<uint32_t, float>& x, const std::pair<uint32_t, float>& y) {
+                    return x.first < y.first;
+                });
+                size_t wr = 0, rd = 0;
+                while (rd < c.size()) {
+                    const uint32_t r = c[rd].first;
+                    float v = c[rd].second;
+                    ++rd;
+                    while (rd < c.size() && c[rd].first == r) {
+                        v += c[rd].second;
+                        ++rd;
+                    }
+                    c[wr++] = {r, v};
+                }
+                c.resize(wr);
+            }
+            out->indptr[j + 1] = c.size();
+        }
+    };
+    {
+        std::vector<std::thread> pool;
+        for (unsigned w = 1; w < nt; ++w) pool.emplace_back(work, w);
+        work(0);
+        for (auto& t : pool) t.join();
+    }
+    for (uint64_t j = 0; j < ncols; ++j) out->indptr[j + 1] += out->indptr[j];
+    out->idx.resize(out->indptr[ncols]);
+    out->val.resize(out->indptr[ncols]);
+    auto fill = [&](unsigned w) {
+        const uint64_t a = ncols * w / nt, b = ncols * (w + 1) / nt;
+        for (uint64_t j = a; j < b; ++j) {
+            uint64_t o = out->indptr[j];
+            for (const auto& rv : cols[j]) {
+                out->idx[o] = rv.first;
+                out->val[o++] = rv.second;
+            }
+        }
+    };
+    {
+        std::vector<std::thread> pool;
+        for (unsigned w = 1; w < nt; ++w) pool.emplace_back(fill, w);
+        fill(0);
+        for (auto& t : pool) t.join();
+    }
+    out->bad = bad.load();
+}
+}  // namespace
+
 extern "C" int lg_csc_upload(lg_ctx* ctx, const uint64_t* indptr, const uint64_t* indices, const float* data,
                              uint64_t nrows, uint64_t col_lo, uint64_t col_hi, const uint32_t* row_remap,
                              lg_csc** out) {
+    // the remap's length is not part of this signature: the caller guarantees it covers every backend row that occurs
+    return lg_csc_upload_remap(ctx, indptr, indices, data, nrows, col_lo, col_hi, row_remap, ~0ull, out);
+}
+
+extern "C" int lg_csc_upload_remap(lg_ctx* ctx, const uint64_t* indptr, const uint64_t* indices, const float* data,
+                                   uint64_t nrows, uint64_t col_lo, uint64_t col_hi, const uint32_t* row_remap,
+                                   uint64_t nrows_backend, lg_csc** out) {
     if (!ctx || !out) return LG_ERR_INVALID;
     *out = nullptr;
     LG_REQUIRE(ctx, indptr && col_hi >= col_lo, "lg_csc_upload: null indptr or empty column range");
@@ -517,8 +666,30 @@ extern "C" int lg_csc_upload(lg_ctx* ctx, const uint64_t* indptr, const uint64_t
         UP_CUDA(cudaGetLastError());
         UP_CUDA(cudaFreeAsync(tmp, st));
     }
+    if (row_remap && nnz) {
+        // remapped rows: canonicalised on the host (sorted, duplicates summed, absent rows dropped), then sent narrow
+        RemapOut ro;
+        remap_columns(indptr, indices, data, col_lo, col_hi, row_remap, nrows_backend, nrows, &ro);
+        if (ro.bad) {
+            UP_CUDA(cudaStreamSynchronize(st));
+            ctx->err = ro.bad & 1 ? "lg_csc_upload: row index outside the backend's remap" : "lg_csc_upload: remapped row out of range";
+            return fail(LG_ERR_INVALID);
+        }
+        const uint64_t nnz2 = ro.indptr[ncols];
+        UP_CUDA(cudaMemcpyAsync(m->indptr, ro.indptr.data(), (ncols + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
+        if (nnz2) {
+            UP_CUDA(cudaMemcpyAsync(m->indices, ro.idx.data(), nnz2 * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+            UP_CUDA(cudaMemcpyAsync(m->values, ro.val.data(), nnz2 * sizeof(float), cudaMemcpyHostToDevice, st));
+        }
+        ctx->h2d_bytes += nnz2 * 8 + (ncols + 1) * sizeof(uint64_t);
+        UP_CUDA(cudaStreamSynchronize(st));  // the host vectors die with this scope
+        m->nnz = nnz2;
+        m->canonical = 1;
+        *out = m;
+        return LG_OK;
+    }
     const int up_threads = upload_threads();
-    if (nnz >= 4 * UP_CHUNK && !row_remap && up_threads > 0) {  // small blocks: not worth the threads
+    if (nnz >= 4 * UP_CHUNK && up_threads > 0) {  // small blocks: not worth the threads
         int bad = 0;
         UP_CUDA(upload_narrow_on_host(ctx, indices + base, data + base, nnz, nrows, m->indices, m->values, up_threads, &bad));
         UP_CUDA(cudaStreamSynchronize(st));
@@ -531,17 +702,7 @@ extern "C" int lg_csc_upload(lg_ctx* ctx, const uint64_t* indptr, const uint64_t
         ctx->h2d_bytes += nnz * (sizeof(float) + sizeof(uint64_t));
         const uint32_t* d_remap = nullptr;
         uint32_t* remap_buf = nullptr;
-        uint64_t nrows_in = nrows;
-        if (row_remap) {
-            // the remap is indexed by backend row; its length is not known here, so the caller
-            // guarantees it covers every index that occurs (read.rs:202-219 builds it that way)
-            uint64_t mx = 0;
-            for (uint64_t t = base; t < end; ++t) mx = indices[t] > mx ? indices[t] : mx;
-            nrows_in = mx + 1;
-            UP_CUDA(cudaMallocAsync(&remap_buf, nrows_in * sizeof(uint32_t), st));
-            UP_CUDA(cudaMemcpyAsync(remap_buf, row_remap, nrows_in * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
-            d_remap = remap_buf;
-        }
+        const uint64_t nrows_in = nrows;
         int* d_flag = nullptr;
         UP_CUDA(cudaMallocAsync(&d_flag, sizeof(int), st));
         UP_CUDA(cudaMemsetAsync(d_flag, 0, sizeof(int), st));
@@ -577,6 +738,63 @@ extern "C" int lg_csc_upload(lg_ctx* ctx, const uint64_t* indptr, const uint64_t
         UP_CUDA(cudaStreamSynchronize(st));
     }
 #undef UP_CUDA
+    // the arrays came from a backend: they must be canonical CSC (the reference's on-disk invariant); checked once here
+    {
+        const int rc = lg_csc_require_canonical(ctx, m, "lg_csc_upload");
+        if (rc != LG_OK) return fail(rc);
+    }
+    *out = m;
+    return LG_OK;
+}
+
+// columns of several blocks side by side (SparseIoVec::push of several backends over one feature axis)
+__global__ void k_offset_indptr(const uint64_t* __restrict__ src, uint64_t* __restrict__ dst, uint64_t n, uint64_t add) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) dst[i] = src[i] + add;
+}
+extern "C" int lg_csc_concat(lg_ctx* ctx, const lg_csc* const* parts, uint32_t nparts, lg_csc** out) {
+    if (!ctx || !out) return LG_ERR_INVALID;
+    *out = nullptr;
+    LG_REQUIRE(ctx, parts && nparts >= 1, "lg_csc_concat: no blocks");
+    cudaSetDevice(ctx->device);
+    uint64_t ncols = 0, nnz = 0;
+    int canonical = 1;
+    for (uint32_t p = 0; p < nparts; ++p) {
+        LG_REQUIRE(ctx, parts[p] && parts[p]->nrows == parts[0]->nrows, "lg_csc_concat: blocks disagree on the number of rows");
+        ncols += parts[p]->ncols;
+        nnz += parts[p]->nnz;
+        if (parts[p]->canonical != 1) canonical = -1;
+    }
+    lg_csc* m = new lg_csc();
+    m->nrows = parts[0]->nrows;
+    m->ncols = ncols;
+    m->nnz = nnz;
+    m->owned = m->pooled = true;
+    m->canonical = canonical;
+    cudaStream_t st = ctx->stream;
+    auto fail = [&](cudaError_t e) {
+        ctx->err = std::string("lg_csc_concat: ") + cudaGetErrorString(e);
+        lg_csc_free(ctx, m);
+        return e == cudaErrorMemoryAllocation ? LG_ERR_NOMEM : LG_ERR_CUDA;
+    };
+    cudaError_t e;
+    if ((e = cudaMallocAsync(&m->indptr, (ncols + 1) * sizeof(uint64_t), st)) != cudaSuccess) return fail(e);
+    if ((e = cudaMallocAsync(&m->indices, (nnz ? nnz : 1) * sizeof(uint32_t), st)) != cudaSuccess) return fail(e);
+    if ((e = cudaMallocAsync(&m->values, (nnz ? nnz : 1) * sizeof(float), st)) != cudaSuccess) return fail(e);
+    uint64_t c0 = 0, z0 = 0;
+    for (uint32_t p = 0; p < nparts; ++p) {
+        const lg_csc* q = parts[p];
+        // every block's indptr starts at 0; the last entry of the previous block is overwritten by the same value
+        k_offset_indptr<<<(unsigned)((q->ncols + 1 + 255) / 256), 256, 0, st>>>(q->indptr, m->indptr + c0, q->ncols + 1, z0);
+        ctx->launches++;
+        if ((e = cudaGetLastError()) != cudaSuccess) return fail(e);
+        if (q->nnz) {
+            if ((e = cudaMemcpyAsync(m->indices + z0, q->indices, q->nnz * sizeof(uint32_t), cudaMemcpyDeviceToDevice, st)) != cudaSuccess) return fail(e);
+            if ((e = cudaMemcpyAsync(m->values + z0, q->values, q->nnz * sizeof(float), cudaMemcpyDeviceToDevice, st)) != cudaSuccess) return fail(e);
+        }
+        c0 += q->ncols;
+        z0 += q->nnz;
+    }
     *out = m;
     return LG_OK;
 }

@@ -400,7 +400,13 @@ __global__ void __launch_bounds__(256) k_knn_refine(const float* __restrict__ re
         // accepted only if the exact k-th distance is below every pruned point's smallest possible distance
         const float kth_d2 = found == k ? __uint_as_float((uint32_t)(kth >> 32)) : INFINITY;
         const float lower = qn + prune / (s * s);
-        const float eps = 1.220703125e-4f * (fabsf(qn) + fabsf(lower) + 1e-30f);  // 2^-13 relative slack
+        // slack of the filter's keys: a RELATIVE part (2^-13 of the magnitudes: f16 hi/lo products, f32 key arithmetic)
+        // and an ABSOLUTE part — a scaled coordinate below 2^-14 makes the f16 "lo" half subnormal, i.e. up to 2^-25 of
+        // absolute error per coordinate, hence up to 2^-24 sqrt(d) (|q| + |r|) / s per dot product in distance units
+        // whatever the norms are (data with one large outlier and a tight cluster near the origin).  |r| <= |q| + dist.
+        const float rel = 1.220703125e-4f * (fabsf(qn) + fabsf(lower) + 1e-30f);
+        const float abs_part = 4.76837158e-7f * __fsqrt_rn((float)d) * (2.0f * __fsqrt_rn(qn) + __fsqrt_rn(fmaxf(lower, 0.0f))) / s;  // 2^-21
+        const float eps = rel + abs_part;
         if (!(kth_d2 < lower - eps)) redo_list[atomicAdd(redo_count, 1u)] = (uint32_t)q;
     }
 }

@@ -210,6 +210,7 @@ extern "C" int lg_row_stats(lg_ctx* ctx, const lg_csc* m, double* out_npos, doub
     if (!ctx) return LG_ERR_INVALID;
     LG_REQUIRE(ctx, m && out_npos && out_s1 && out_s2, "lg_row_stats: null argument");
     cudaSetDevice(ctx->device);
+    LG_TRY(lg_csc_require_canonical(ctx, m, "lg_row_stats"));
     const uint64_t D = m->nrows, N = m->ncols;
     LgStage st(ctx);
     double *d_npos, *d_s1, *d_s2;
@@ -432,6 +433,7 @@ extern "C" int lg_nystrom_project(lg_ctx* ctx, const lg_csc* m, const float* bas
     LG_REQUIRE(ctx, K >= 1 && K <= 128, "lg_nystrom_project: K must be in [1, 128]");
     LG_REQUIRE(ctx, !delta_dp || (pb_of_cell && P >= 1), "lg_nystrom_project: delta needs the pseudobulk of every cell");
     cudaSetDevice(ctx->device);
+    LG_TRY(lg_csc_require_canonical(ctx, m, "lg_nystrom_project"));
     const uint64_t D = m->nrows, N = m->ncols;
     LgStage st(ctx);
     const float *d_basis, *d_delta;

@@ -1,6 +1,7 @@
 // lg_project.cu — stage 1: random projection of the sparse gene x cell matrix.
 //   K1  project_columns_visitor       data-beans-alg/src/random_projection.rs:169-199
 //   K2  batch centring / standardise / clamp                         :378-407
+#include <cmath>
 #include <cstdlib>
 
 #include "lg_common.cuh"
@@ -58,10 +59,125 @@ __global__ void __launch_bounds__(256) k_project_raw_warp(const uint64_t* __rest
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// K1, EXACT-ORDER form (LG_PROJECT_EXACT): the reference's arithmetic operation by operation, so that the
+// projection of count data is bit-identical to the CPU path and the sign bits / groups derived from it are too:
+//   x = ln_1p(y)                               random_projection.rs:181-183   (libm log1pf: a host-built table for whole
+//                                                                              counts below 65536, so no second libm is involved)
+//   denom = max(sqrt(fold(x*x)), 1e-8); x /= denom   dmatrix_util.rs:770-778   (sequential fold, product rounded, then the sum)
+//   chunk[:, j] = x_i * B[:, i] + chunk[:, j]   random_projection.rs:188-194   (ascending row, product rounded, then the sum)
+// ---------------------------------------------------------------------------------------------
+constexpr int LG_LOG1P_TAB = 65536;
+
+__device__ __forceinline__ float exact_log1p(float y, const float* __restrict__ tab) {
+    const int yi = (int)y;
+    if (y == (float)yi && yi >= 0 && yi < LG_LOG1P_TAB) return __ldg(tab + yi);
+    return (float)log1p((double)y);  // correctly rounded from f64: what libm's log1pf returns in all but rare cases
+}
+
+// one thread per cell: the norm is ONE dependent chain per cell, so a warp runs 32 cells' chains side by side
+__global__ void __launch_bounds__(256) k_cell_norm_exact(const uint64_t* __restrict__ indptr, const float* __restrict__ values,
+                                                         uint64_t ncols, const float* __restrict__ tab, float* __restrict__ denom) {
+    const uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= ncols) return;
+    const uint64_t lo = indptr[j], hi = indptr[j + 1];
+    float s = 0.0f;
+    for (uint64_t t = lo; t < hi; ++t) {
+        const float x = exact_log1p(__ldg(values + t), tab);
+        s = __fadd_rn(s, __fmul_rn(x, x));
+    }
+    denom[j] = fmaxf(__fsqrt_rn(s), 1e-8f);
+}
+
+template <int NACC>
+__global__ void __launch_bounds__(256) k_project_raw_exact(const uint64_t* __restrict__ indptr, const uint32_t* __restrict__ indices,
+                                                           const float* __restrict__ values, uint64_t ncols,
+                                                           const float* __restrict__ basis_kd, int K, const float* __restrict__ tab,
+                                                           const float* __restrict__ denom, float* __restrict__ out) {
+    const int lane = threadIdx.x & 31;
+    const uint64_t warp0 = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint64_t nwarps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+    for (uint64_t j = warp0; j < ncols; j += nwarps) {
+        const uint64_t lo = indptr[j], hi = indptr[j + 1];
+        const float dn = denom[j];
+        float acc[NACC];
+#pragma unroll
+        for (int a = 0; a < NACC; ++a) acc[a] = 0.0f;
+        for (uint64_t base = lo; base < hi; base += 32) {
+            const uint64_t t = base + lane;
+            uint32_t idx = 0;
+            float x = 0.0f;
+            if (t < hi) {
+                idx = __ldg(indices + t);
+                x = __fdiv_rn(exact_log1p(__ldg(values + t), tab), dn);
+            }
+            const int n = (hi - base) < 32 ? (int)(hi - base) : 32;
+            for (int s = 0; s < n; ++s) {
+                const uint32_t i = __shfl_sync(0xffffffffu, idx, s);
+                const float xs = __shfl_sync(0xffffffffu, x, s);
+                const float* row = basis_kd + (size_t)i * K;
+#pragma unroll
+                for (int a = 0; a < NACC; ++a) {
+                    const int k = lane + 32 * a;
+                    if (k < K) acc[a] = __fadd_rn(__fmul_rn(xs, __ldg(row + k)), acc[a]);
+                }
+            }
+        }
+#pragma unroll
+        for (int a = 0; a < NACC; ++a) {
+            const int k = lane + 32 * a;
+            if (k < K) out[(size_t)j * K + k] = acc[a];
+        }
+    }
+}
+
+// the table is libm's: built on the host once per context
+static int exact_log1p_table(lg_ctx* ctx, const float** tab) {
+    if (!ctx->log1p_tab) {
+        std::vector<float> h(LG_LOG1P_TAB);
+        for (int i = 0; i < LG_LOG1P_TAB; ++i) h[i] = log1pf((float)i);
+        LG_CUDA(ctx, cudaMalloc(&ctx->log1p_tab, LG_LOG1P_TAB * sizeof(float)));
+        LG_CUDA(ctx, cudaMemcpy(ctx->log1p_tab, h.data(), LG_LOG1P_TAB * sizeof(float), cudaMemcpyHostToDevice));
+    }
+    *tab = ctx->log1p_tab;
+    return LG_OK;
+}
+
+static int launch_project_raw_exact(lg_ctx* ctx, const lg_csc* m, const float* d_basis, int K, float* d_out) {
+    if (m->ncols == 0) return LG_OK;
+    LG_TRY(lg_csc_require_canonical(ctx, m, "lg_project_exact"));  // "ascending row" is the order of the sum
+    const float* tab;
+    LG_TRY(exact_log1p_table(ctx, &tab));
+    LgStage st(ctx);
+    float* d_denom;
+    LG_TRY(st.scratch((size_t)m->ncols, &d_denom));
+    LG_LAUNCH(ctx, k_cell_norm_exact, (unsigned)((m->ncols + 255) / 256), 256, 0, m->indptr, m->values, m->ncols, tab, d_denom);
+    const int nacc = (K + 31) / 32;
+    uint64_t blocks = (m->ncols + 7) / 8;
+    const uint64_t cap = (uint64_t)ctx->num_sms * 32;
+    if (blocks > cap) blocks = cap;
+#define LG_EXACT_CASE(NA)                                                                                                  \
+    case NA:                                                                                                               \
+        LG_LAUNCH(ctx, k_project_raw_exact<NA>, (unsigned)blocks, 256, 0, m->indptr, m->indices, m->values, m->ncols, d_basis, \
+                  K, tab, d_denom, d_out);                                                                                 \
+        break
+    switch (nacc) {
+        LG_EXACT_CASE(1);
+        LG_EXACT_CASE(2);
+        LG_EXACT_CASE(3);
+        LG_EXACT_CASE(4);
+        default: return lg_fail(ctx, LG_ERR_INVALID, "lg_project: K must be in [1, 128]");
+    }
+#undef LG_EXACT_CASE
+    return LG_OK;
+}
+
 int lg_project_raw_umma(lg_ctx* ctx, const lg_csc* m, const float* d_basis, int K, float* d_out, int* used, int mode, float csn);
 
 static int launch_project_raw(lg_ctx* ctx, const lg_csc* m, const float* d_basis, int K, float* d_out) {
     if (m->ncols == 0) return LG_OK;
+    LG_TRY(lg_csc_require_canonical(ctx, m, "lg_project"));  // the pattern bitmap needs unique rows
     // tensor path first (lg_project_umma.cu); LG_K1_CUDA_CORES=1 forces the warp-per-cell kernel for A/B runs
     const char* force = getenv("LG_K1_CUDA_CORES");
     if (!(force && force[0] == '1')) {
@@ -188,6 +304,8 @@ template <int MODE>
 __global__ void __launch_bounds__(SCALE_CELLS) k_scale_cells(float* __restrict__ proj, int K, uint64_t ncols,
                                                              const uint32_t* __restrict__ batch, uint32_t nbatch,
                                                              const double* __restrict__ batch_sums,
+                                                             const float* __restrict__ fold_sum,
+                                                             const unsigned long long* __restrict__ fold_cnt,
                                                              float* __restrict__ minmax) {
     extern __shared__ float tile[];  // SCALE_CELLS rows of stride KS (odd -> conflict-free row walks)
     const int KS = K | 1;
@@ -223,20 +341,29 @@ __global__ void __launch_bounds__(SCALE_CELLS) k_scale_cells(float* __restrict__
         }
         for (int e = 4 * nvec + threadIdx.x; e < total_i; e += SCALE_CELLS) tile[(e / K) * KS + (e % K)] = src[e];
     }
+    const bool centre = MODE == 0 && (batch_sums || fold_sum);
     if (MODE == 0 && batch_sums) {
         for (uint32_t e = threadIdx.x; e < nbatch * (uint32_t)K; e += SCALE_CELLS) {
             const uint32_t b = e / K, k = e % K;
             const double cnt = batch_sums[(size_t)b * (K + 1) + K];
             neg_mean[e] = cnt > 0.0 ? -(float)(batch_sums[(size_t)b * (K + 1) + k] / cnt) : 0.0f;
         }
+    } else if (MODE == 0 && fold_sum) {
+        // exact-order form: the reference's own f32 fold divided by the f32 cell count (random_projection.rs:380-387)
+        for (uint32_t e = threadIdx.x; e < nbatch * (uint32_t)K; e += SCALE_CELLS) {
+            const unsigned long long cnt = fold_cnt[e / K];
+            neg_mean[e] = cnt ? -__fdiv_rn(fold_sum[e], (float)(double)cnt) : 0.0f;
+        }
     }
     __syncthreads();
     float lmin = INFINITY, lmax = -INFINITY;
     if ((int)threadIdx.x < ncell) {
         float* x = tile + threadIdx.x * KS;
-        if (MODE == 0 && batch_sums) {
-            const float* nm = neg_mean + (size_t)(batch ? batch[cell0 + threadIdx.x] : 0u) * K;
-            for (int k = 0; k < K; ++k) x[k] = x[k] + nm[k];
+        if (centre) {
+            // a label outside [0, nbatch) is rejected by the callers before any launch; the clamp keeps the read in bounds
+            const uint32_t bb = batch ? batch[cell0 + threadIdx.x] : 0u;
+            const float* nm = neg_mean + (size_t)(bb < nbatch ? bb : 0u) * K;
+            for (int k = 0; k < K; ++k) x[k] = __fadd_rn(x[k], nm[k]);
         }
         if (MODE == 1)
             for (int k = 0; k < K; ++k) x[k] = fminf(fmaxf(x[k], -4.0f), 4.0f);
@@ -320,7 +447,73 @@ extern "C" int lg_proj_centre_scale(lg_ctx* ctx, float* d_proj, int K, uint64_t 
     LG_CUDA(ctx, cudaFuncSetAttribute(k_scale_cells<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const uint64_t grid = (ncols + SCALE_CELLS - 1) / SCALE_CELLS;
     LG_LAUNCH(ctx, k_scale_cells<0>, (unsigned)grid, SCALE_CELLS, smem, d_proj, K, ncols, d_batch, nbatch,
-              d_batch_sums, d_minmax);
+              d_batch_sums, (const float*)nullptr, (const unsigned long long*)nullptr, d_minmax);
+    return LG_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// K2, EXACT-ORDER form: the batch means are the reference's left folds over the batch's cells in ascending cell
+// order (random_projection.rs:380-387; nalgebra column_mean).  One block per batch, one thread per dim: the adds of a
+// (batch, dim) pair are ONE dependent f32 chain (that order is the contract), cells staged through shared memory so
+// the global reads stay coalesced.  sum / cnt are carried IN and OUT: cell shards call it one after the other in rank
+// order, handing the running folds on, so the result is the single-GPU fold for any GPU count.
+// ---------------------------------------------------------------------------------------------
+constexpr int FOLD_CELLS = 64;
+__global__ void __launch_bounds__(128) k_batch_fold_exact(const float* __restrict__ proj, int K, uint64_t ncols,
+                                                          const uint32_t* __restrict__ batch, float* __restrict__ sum,
+                                                          unsigned long long* __restrict__ cnt) {
+    extern __shared__ float tile[];  // FOLD_CELLS * K values, then FOLD_CELLS batch ids
+    uint32_t* ids = reinterpret_cast<uint32_t*>(tile + FOLD_CELLS * K);
+    const uint32_t b = blockIdx.x;
+    const int k = threadIdx.x;
+    float s = k < K ? sum[(size_t)b * K + k] : 0.0f;
+    unsigned long long c = cnt[b];
+    for (uint64_t c0 = 0; c0 < ncols; c0 += FOLD_CELLS) {
+        const int nc = (ncols - c0) < (uint64_t)FOLD_CELLS ? (int)(ncols - c0) : FOLD_CELLS;
+        for (int e = threadIdx.x; e < nc * K; e += blockDim.x) tile[e] = proj[c0 * K + e];
+        for (int e = threadIdx.x; e < nc; e += blockDim.x) ids[e] = batch ? batch[c0 + e] : 0u;
+        __syncthreads();
+        if (k < K) {
+            for (int i = 0; i < nc; ++i)
+                if (ids[i] == b) {
+                    s = __fadd_rn(s, tile[i * K + k]);
+                    ++c;
+                }
+        }
+        __syncthreads();
+    }
+    if (k < K) sum[(size_t)b * K + k] = s;
+    if (k == 0) cnt[b] = c;
+}
+
+extern "C" int lg_proj_batch_fold(lg_ctx* ctx, const float* d_proj, int K, uint64_t ncols, const uint32_t* d_batch,
+                                  uint32_t nbatch, float* d_sum, uint64_t* d_cnt) {
+    if (!ctx) return LG_ERR_INVALID;
+    LG_REQUIRE(ctx, d_proj && d_sum && d_cnt && nbatch >= 1 && K >= 1 && K <= 128, "lg_proj_batch_fold: bad argument");
+    cudaSetDevice(ctx->device);
+    if (ncols == 0) return LG_OK;
+    const size_t smem = (size_t)FOLD_CELLS * (K + 1) * sizeof(float);
+    LG_LAUNCH(ctx, k_batch_fold_exact, nbatch, 128, smem, d_proj, K, ncols, d_batch, d_sum,
+              reinterpret_cast<unsigned long long*>(d_cnt));
+    return LG_OK;
+}
+
+extern "C" int lg_proj_centre_scale_exact(lg_ctx* ctx, float* d_proj, int K, uint64_t ncols, const uint32_t* d_batch,
+                                          uint32_t nbatch, const float* d_fold_sum, const uint64_t* d_fold_cnt,
+                                          float* d_minmax) {
+    if (!ctx) return LG_ERR_INVALID;
+    LG_REQUIRE(ctx, d_proj && K >= 1 && K <= 128, "lg_proj_centre_scale_exact: bad argument");
+    cudaSetDevice(ctx->device);
+    if (d_minmax) LG_LAUNCH(ctx, k_init_minmax, 1, 1, 0, d_minmax);
+    if (ncols == 0) return LG_OK;
+    if (!d_fold_sum || !d_fold_cnt) nbatch = 0;
+    const size_t smem = scale_smem(K, nbatch);
+    LG_REQUIRE(ctx, smem <= ctx->smem_optin, "lg_proj_centre_scale_exact: nbatch*K too large for shared memory");
+    LG_CUDA(ctx, cudaFuncSetAttribute(k_scale_cells<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const uint64_t grid = (ncols + SCALE_CELLS - 1) / SCALE_CELLS;
+    LG_LAUNCH(ctx, k_scale_cells<0>, (unsigned)grid, SCALE_CELLS, smem, d_proj, K, ncols, d_batch, nbatch,
+              (const double*)nullptr, nbatch ? d_fold_sum : nullptr,
+              reinterpret_cast<const unsigned long long*>(nbatch ? d_fold_cnt : nullptr), d_minmax);
     return LG_OK;
 }
 
@@ -333,15 +526,64 @@ extern "C" int lg_proj_clamp_rescale(lg_ctx* ctx, float* d_proj, int K, uint64_t
     LG_CUDA(ctx, cudaFuncSetAttribute(k_scale_cells<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const uint64_t grid = (ncols + SCALE_CELLS - 1) / SCALE_CELLS;
     LG_LAUNCH(ctx, k_scale_cells<1>, (unsigned)grid, SCALE_CELLS, smem, d_proj, K, ncols, (const uint32_t*)nullptr, 0u,
-              (const double*)nullptr, (float*)nullptr);
+              (const double*)nullptr, (const float*)nullptr, (const unsigned long long*)nullptr, (float*)nullptr);
     return LG_OK;
 }
 
 // ---------------------------------------------------------------------------------------------
 // composite: project_columns_with_batch_correction_seeded (random_projection.rs:341-415)
 // ---------------------------------------------------------------------------------------------
+// a batch label outside [0, nbatch) is an error (the reference indexes per-batch vectors with it and would panic)
+__global__ void k_check_labels(const uint32_t* __restrict__ label, uint64_t n, uint32_t bound, int* __restrict__ flag) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    bool bad = false;
+    for (; i < n; i += stride) bad |= label[i] >= bound;
+    if (bad) atomicOr(flag, 1);
+}
+int lg_check_labels(lg_ctx* ctx, const uint32_t* d_label, uint64_t n, uint32_t bound, const char* what) {
+    if (!d_label || n == 0) return LG_OK;
+    LgStage st(ctx);
+    int* d_flag;
+    LG_TRY(st.scratch(1, &d_flag));
+    LG_CUDA(ctx, cudaMemsetAsync(d_flag, 0, sizeof(int), ctx->stream));
+    uint64_t blocks = (n + 1023) / 1024;
+    if (blocks > 1184) blocks = 1184;
+    LG_LAUNCH(ctx, k_check_labels, (unsigned)blocks, 256, 0, d_label, n, bound, d_flag);
+    int* h_flag = static_cast<int*>(ctx->pinned);
+    LG_CUDA(ctx, cudaMemcpyAsync(h_flag, d_flag, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    LG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (*h_flag) return lg_fail(ctx, LG_ERR_INVALID, std::string(what) + ": label out of range");
+    return LG_OK;
+}
+
+static int project_impl(lg_ctx* ctx, const lg_csc* m, const float* basis_kd, int K, const uint32_t* batch_of_cell,
+                        uint32_t nbatch, float* out_proj, bool exact);
+
 extern "C" int lg_project(lg_ctx* ctx, const lg_csc* m, const float* basis_kd, int K, const uint32_t* batch_of_cell,
                           uint32_t nbatch, float* out_proj) {
+    return project_impl(ctx, m, basis_kd, K, batch_of_cell, nbatch, out_proj, false);
+}
+extern "C" int lg_project_exact(lg_ctx* ctx, const lg_csc* m, const float* basis_kd, int K, const uint32_t* batch_of_cell,
+                                uint32_t nbatch, float* out_proj) {
+    return project_impl(ctx, m, basis_kd, K, batch_of_cell, nbatch, out_proj, true);
+}
+extern "C" int lg_project_raw_exact(lg_ctx* ctx, const lg_csc* m, const float* basis_kd, int K, float* out_proj) {
+    if (!ctx) return LG_ERR_INVALID;
+    LG_REQUIRE(ctx, m && basis_kd && out_proj, "lg_project_raw_exact: null argument");
+    LG_REQUIRE(ctx, K >= 1 && K <= 128, "lg_project_raw_exact: K must be in [1, 128]");
+    cudaSetDevice(ctx->device);
+    LgStage st(ctx);
+    const float* d_basis;
+    float* d_out;
+    LG_TRY(st.in(basis_kd, (size_t)K * m->nrows, &d_basis));
+    LG_TRY(st.out(out_proj, (size_t)K * m->ncols, &d_out));
+    LG_TRY(launch_project_raw_exact(ctx, m, d_basis, K, d_out));
+    return st.finish();
+}
+
+static int project_impl(lg_ctx* ctx, const lg_csc* m, const float* basis_kd, int K, const uint32_t* batch_of_cell,
+                        uint32_t nbatch, float* out_proj, bool exact) {
     if (!ctx) return LG_ERR_INVALID;
     LG_REQUIRE(ctx, m && basis_kd && out_proj, "lg_project: null argument");
     LG_REQUIRE(ctx, K >= 1 && K <= 128, "lg_project: K must be in [1, 128]");
@@ -354,6 +596,27 @@ extern "C" int lg_project(lg_ctx* ctx, const lg_csc* m, const float* basis_kd, i
     LG_TRY(st.in(basis_kd, (size_t)K * m->nrows, &d_basis));
     LG_TRY(st.in(batch_of_cell, (size_t)m->ncols, &d_batch));
     LG_TRY(st.out(out_proj, (size_t)K * m->ncols, &d_out));
+    if (d_batch) LG_TRY(lg_check_labels(ctx, d_batch, m->ncols, nbatch, "lg_project: batch_of_cell"));
+    float* d_mm;
+    LG_TRY(st.scratch(2, &d_mm));
+    float* h_mm = static_cast<float*>(ctx->pinned);
+    if (exact) {
+        LG_TRY(launch_project_raw_exact(ctx, m, d_basis, K, d_out));
+        float* d_fsum = nullptr;
+        uint64_t* d_fcnt = nullptr;
+        if (d_batch && m->ncols) {
+            LG_TRY(st.scratch((size_t)nbatch * K, &d_fsum));
+            LG_TRY(st.scratch((size_t)nbatch, &d_fcnt));
+            LG_CUDA(ctx, cudaMemsetAsync(d_fsum, 0, (size_t)nbatch * K * sizeof(float), ctx->stream));
+            LG_CUDA(ctx, cudaMemsetAsync(d_fcnt, 0, (size_t)nbatch * sizeof(uint64_t), ctx->stream));
+            LG_TRY(lg_proj_batch_fold(ctx, d_out, K, m->ncols, d_batch, nbatch, d_fsum, d_fcnt));
+        }
+        LG_TRY(lg_proj_centre_scale_exact(ctx, d_out, K, m->ncols, d_batch, nbatch, d_fsum, d_fcnt, d_mm));
+        LG_CUDA(ctx, cudaMemcpyAsync(h_mm, d_mm, 2 * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+        LG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        if (m->ncols && (h_mm[1] > 4.0f || h_mm[0] < -4.0f)) LG_TRY(lg_proj_clamp_rescale(ctx, d_out, K, m->ncols));
+        return st.finish();
+    }
     LG_TRY(launch_project_raw(ctx, m, d_basis, K, d_out));
     const uint64_t nblk = (m->ncols + LG_BLOCK_CELLS - 1) / LG_BLOCK_CELLS;
     double* d_sums = nullptr;
@@ -365,11 +628,8 @@ extern "C" int lg_project(lg_ctx* ctx, const lg_csc* m, const float* basis_kd, i
         LG_TRY(lg_proj_batch_partials(ctx, d_out, K, m->ncols, d_batch, nbatch, d_part));
         LG_TRY(lg_block_partials_finalize(ctx, d_part, nblk, M, d_sums));
     }
-    float* d_mm;
-    LG_TRY(st.scratch(2, &d_mm));
     LG_TRY(lg_proj_centre_scale(ctx, d_out, K, m->ncols, d_batch, nbatch, d_sums, d_mm));
     // the clamp branch is a global decision (:401): read back (min, max)
-    float* h_mm = static_cast<float*>(ctx->pinned);
     LG_CUDA(ctx, cudaMemcpyAsync(h_mm, d_mm, 2 * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
     LG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     if (m->ncols && (h_mm[1] > 4.0f || h_mm[0] < -4.0f)) LG_TRY(lg_proj_clamp_rescale(ctx, d_out, K, m->ncols));

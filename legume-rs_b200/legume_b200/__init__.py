@@ -145,10 +145,22 @@ class CscBlock:
         data = np.ascontiguousarray(data, np.float32)
         if col_hi is None:
             col_hi = len(indptr) - 1
-        rr = None if row_remap is None else np.ascontiguousarray(row_remap, np.uint32)
         h = C.c_void_p()
-        ctx.check(lib.lg_csc_upload(ctx.h, _ptr(indptr), _ptr(indices), _ptr(data), nrows, col_lo, col_hi, _ptr(rr),
-                                    C.byref(h)))
+        if row_remap is None:
+            ctx.check(lib.lg_csc_upload(ctx.h, _ptr(indptr), _ptr(indices), _ptr(data), nrows, col_lo, col_hi, None, C.byref(h)))
+        else:
+            # remapped rows are made canonical on the way (sorted, duplicates summed, absent rows dropped: read.rs:246-281)
+            rr = np.ascontiguousarray(row_remap, np.uint32)
+            ctx.check(lib.lg_csc_upload_remap(ctx.h, _ptr(indptr), _ptr(indices), _ptr(data), nrows, col_lo, col_hi, _ptr(rr),
+                                              len(rr), C.byref(h)))
+        return cls(ctx, h)
+
+    @classmethod
+    def concat(cls, ctx, blocks):
+        """columns of several blocks side by side (lg_csc_concat)"""
+        arr = (C.c_void_p * len(blocks))(*[b.h for b in blocks])
+        h = C.c_void_p()
+        ctx.check(lib.lg_csc_concat(ctx.h, arr, len(blocks), C.byref(h)))
         return cls(ctx, h)
 
     @classmethod
@@ -602,26 +614,17 @@ class SparseIoVec:
         """Several backends' columns side by side, as SparseIoVec::push + read_columns_csc see them
         (data-beans/src/sparse_io_vector/read.rs:172-285): every backend is (indptr, indices, data, row_remap or None),
         row_remap[local row] = row in the union (`g2c[l2g[row]]`, :202-219; rows a backend lacks simply never occur).
-        One backend goes straight through lg_csc_upload (the remap is applied on the device); several are remapped and
-        joined on the host first, then uploaded as one block."""
-        backends = list(backends)
-        if len(backends) == 1:
-            ip, ix, v, remap = backends[0]
-            return cls(ctx, CscBlock.upload(ctx, ip, ix, v, nrows, row_remap=remap))
-        ips, ixs, vs, base = [np.zeros(1, np.uint64)], [], [], 0
-        for ip, ix, v, remap in backends:
-            ip = np.asarray(ip, np.uint64)
-            ix = np.asarray(ix, np.uint64)
-            if remap is not None:
-                remap = np.asarray(remap, np.uint64)
-                if len(ix) and int(ix.max()) >= len(remap):
-                    raise LegumeError(1, "from_backends: row index outside the backend's remap")
-                ix = remap[ix]
-            ips.append(ip[1:] - ip[0] + np.uint64(base))
-            base += int(ip[-1] - ip[0])
-            ixs.append(ix[int(ip[0]):int(ip[-1])])
-            vs.append(np.asarray(v, np.float32)[int(ip[0]):int(ip[-1])])
-        return cls(ctx, CscBlock.upload(ctx, np.concatenate(ips), np.concatenate(ixs), np.concatenate(vs), nrows))
+        Every backend goes through lg_csc_upload_remap, which makes its columns canonical the way the reference does
+        (a remap that is not monotone leaves a column unsorted, a many-to-one remap leaves duplicate rows: sorted and
+        summed, read.rs:246-281); the blocks are then joined on the device (lg_csc_concat)."""
+        blocks = [CscBlock.upload(ctx, ip, ix, v, nrows, row_remap=remap) for ip, ix, v, remap in backends]
+        if len(blocks) == 1:
+            return cls(ctx, blocks[0])
+        out = CscBlock.concat(ctx, blocks)
+        ctx.sync()
+        for b in blocks:
+            b.free()
+        return cls(ctx, out)
 
     def num_rows(self):
         return self.block.nrows
@@ -673,13 +676,14 @@ class SparseIoVec:
             raise LegumeError(1, f"basis must be K x D given as shape (D, K) = ({self.num_rows()}, {target_dim})")
         return basis
 
-    def project_columns(self, target_dim, block_size=None, basis=None):
-        return self.project_columns_with_batch_correction(target_dim, block_size, None, basis=basis)
+    def project_columns(self, target_dim, block_size=None, basis=None, exact=False):
+        return self.project_columns_with_batch_correction(target_dim, block_size, None, basis=basis, exact=exact)
 
     def project_columns_with_batch_correction(self, target_dim, block_size=None, batch_membership=None, basis=None,
-                                              seed=DEFAULT_PROJECTION_SEED):
+                                              seed=DEFAULT_PROJECTION_SEED, exact=False):
         """returns (basis_kd as (D, K), proj as (N, K)); block_size is accepted and ignored (the GPU streams
-        whole column ranges)."""
+        whole column ranges).  exact=True runs the exact-order kernels (lg_project_exact): bit-identical to the CPU
+        path on count data, several times slower; the default is the tensor-core path with a 1e-5 contract."""
         basis = self._basis(target_dim, seed, basis)
         n = self.num_columns()
         batch, nb = None, 0
@@ -693,11 +697,12 @@ class SparseIoVec:
         if dev and batch is not None:
             import torch
             batch = torch.from_numpy(batch.astype(np.int32)).to(basis.device)
-        self.ctx.check(lib.lg_project(self.ctx.h, self.block.h, _ptr(basis), target_dim, _ptr(batch), nb, _ptr(proj)))
+        fn = lib.lg_project_exact if exact else lib.lg_project
+        self.ctx.check(fn(self.ctx.h, self.block.h, _ptr(basis), target_dim, _ptr(batch), nb, _ptr(proj)))
         return basis, proj
 
     def project_columns_weighted(self, target_dim, block_size, batch_membership, row_weights, basis=None,
-                                 seed=DEFAULT_PROJECTION_SEED):
+                                 seed=DEFAULT_PROJECTION_SEED, exact=False):
         """random_projection.rs:417-495: rows with w <= 0 are zeroed, |w - 1| > 1e-6 scaled"""
         row_weights = np.asarray(row_weights, np.float32)
         if len(row_weights) != self.num_rows():
@@ -708,7 +713,7 @@ class SparseIoVec:
                 basis[r, :] = 0.0
             elif abs(w - 1.0) > 1e-6:
                 basis[r, :] *= w
-        return self.project_columns_with_batch_correction(target_dim, block_size, batch_membership, basis=basis)
+        return self.project_columns_with_batch_correction(target_dim, block_size, batch_membership, basis=basis, exact=exact)
 
     def partition_columns_to_groups(self, proj_kn, num_features=None, ncols_per_group=None):
         """random_projection.rs:506-527: returns max code + 1 and assigns groups"""

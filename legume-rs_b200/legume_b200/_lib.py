@@ -38,6 +38,8 @@ _sig = {
     "lg_ctx_set_stream": [_vp, _vp],
     "lg_ctx_sync": [_vp],
     "lg_csc_upload": [_vp, _vp, _vp, _vp, _u64, _u64, _u64, _vp, C.POINTER(_vp)],
+    "lg_csc_upload_remap": [_vp, _vp, _vp, _vp, _u64, _u64, _u64, _vp, _u64, C.POINTER(_vp)],
+    "lg_csc_concat": [_vp, _vp, _u32, C.POINTER(_vp)],
     "lg_csc_wrap_device": [_vp, _vp, _vp, _vp, _u64, _u64, _u64, C.POINTER(_vp)],
     "lg_csc_free": [_vp, _vp],
     "lg_csc_shape": [_vp, C.POINTER(_u64), C.POINTER(_u64), C.POINTER(_u64)],
@@ -49,6 +51,10 @@ _sig = {
     "lg_block_partials_finalize": [_vp, _vp, _u64, _u32, _vp],
     "lg_proj_centre_scale": [_vp, _vp, _i, _u64, _vp, _u32, _vp, _vp],
     "lg_proj_clamp_rescale": [_vp, _vp, _i, _u64],
+    "lg_project_exact": [_vp, _vp, _vp, _i, _vp, _u32, _vp],
+    "lg_project_raw_exact": [_vp, _vp, _vp, _i, _vp],
+    "lg_proj_batch_fold": [_vp, _vp, _i, _u64, _vp, _u32, _vp, _vp],
+    "lg_proj_centre_scale_exact": [_vp, _vp, _i, _u64, _vp, _u32, _vp, _vp, _vp],
     "lg_binary_codes": [_vp, _vp, _i, _u64, _i, _vp],
     "lg_codes_basis": [_vp, _vp, _i, _i, _i, _vp],
     "lg_codes_gram": [_vp, _vp, _i, _u64, _vp, _i, _vp, _vp],

@@ -58,8 +58,35 @@ class HotPath:
         return self.ex.total(n_local, self.dev)
 
     # ---- stage 1 -----------------------------------------------------------------------------------
-    def project(self, block: CscBlock, basis_kd: torch.Tensor, batch: torch.Tensor | None, nbatch: int):
+    def project_exact(self, block: CscBlock, basis_kd: torch.Tensor, batch: torch.Tensor | None, nbatch: int):
+        """the exact-order mode (lg_project_exact) over cell shards: the batch means are serial f32 folds over the cells
+        in ascending order, so the running folds are handed on shard after shard in rank order — the result is the
+        single-GPU (and the reference's) fold for any GPU count"""
+        ctx, ex, n = self.ctx, self.ex, block.ncols
+        K = basis_kd.shape[1]
+        proj = torch.empty((n, K), dtype=torch.float32, device=self.dev)
+        ctx.check(lib.lg_project_raw_exact(ctx.h, block.h, _ptr(basis_kd), K, _ptr(proj)))
+        fsum = fcnt = None
+        if batch is not None and nbatch >= 1:
+            fsum = torch.zeros((nbatch, K), dtype=torch.float32, device=self.dev)
+            fcnt = torch.zeros(nbatch, dtype=torch.int64, device=self.dev)
+            for r in range(self.world):
+                if r == self.rank:
+                    ctx.check(lib.lg_proj_batch_fold(ctx.h, _ptr(proj), K, n, _ptr(batch), nbatch, _ptr(fsum), _ptr(fcnt)))
+                ex.broadcast_(fsum, r)
+                ex.broadcast_(fcnt, r)
+        mm = torch.empty(2, dtype=torch.float32, device=self.dev)
+        ctx.check(lib.lg_proj_centre_scale_exact(ctx.h, _ptr(proj), K, n, _ptr(batch) if fsum is not None else None,
+                                                 nbatch if fsum is not None else 0, _ptr(fsum), _ptr(fcnt), _ptr(mm)))
+        mn, mx = ex.minmax(mm)
+        if mx > 4.0 or mn < -4.0:
+            ctx.check(lib.lg_proj_clamp_rescale(ctx.h, _ptr(proj), K, n))
+        return proj
+
+    def project(self, block: CscBlock, basis_kd: torch.Tensor, batch: torch.Tensor | None, nbatch: int, exact: bool = False):
         """random_projection.rs:341-415 on this rank's cells; basis_kd (D, K) f32, batch int32 (n_local,)"""
+        if exact:
+            return self.project_exact(block, basis_kd, batch, nbatch)
         ctx, n = self.ctx, block.ncols
         K = basis_kd.shape[1]
         proj = torch.empty((n, K), dtype=torch.float32, device=self.dev)
@@ -290,8 +317,9 @@ class HotPath:
                     gene_sums=gene_sums, matched_pb=mp, matched_dist=md, imputed_sum_ds=imp, residual_sum_ds=res)
 
     # ---- whole path --------------------------------------------------------------------------------
-    def run(self, block: CscBlock, basis_kd: torch.Tensor, batch, nbatch: int, kk: int, target=TARGET_ALL):
-        """projection -> codes -> groups -> collapse -> posterior (single-batch arm of the path)"""
+    def run(self, block: CscBlock, basis_kd: torch.Tensor, batch, nbatch: int, kk: int, target=TARGET_ALL, exact: bool = False):
+        """projection -> codes -> groups -> collapse -> posterior (single-batch arm of the path); exact=True takes the
+        exact-order projection (bit-identical groups and sums from counts, several times slower)"""
         trace = os.environ.get("LG_TRACE")
         t = [time.perf_counter()]
 
@@ -300,7 +328,7 @@ class HotPath:
                 torch.cuda.synchronize()
                 t.append(time.perf_counter())
 
-        proj = self.project(block, basis_kd, batch, nbatch)
+        proj = self.project(block, basis_kd, batch, nbatch, exact)
         mark()
         codes = self.binary_codes(proj, kk)
         mark()

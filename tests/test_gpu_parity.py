@@ -71,7 +71,9 @@ def test_csc_upload_large_block_host_narrowing(lg, ctx, mode, monkeypatch):
     nnz = N * per + 5  # ragged last chunk
     ip = np.minimum(np.arange(N + 1, dtype=np.uint64) * per, nnz).astype(np.uint64)
     ip[-1] = nnz
-    ix = rng.integers(0, D, nnz, dtype=np.uint64)
+    # canonical CSC (rows strictly ascending inside a column): position p of a column lands in [29 p, 29 p + 28]
+    ix = ((np.arange(nnz, dtype=np.uint64) - np.repeat(ip[:-1], np.diff(ip).astype(np.int64))) * np.uint64(29)
+          + rng.integers(0, 29, nnz, dtype=np.uint64))
     v = rng.integers(0, 256, nnz).astype(np.float32)  # whole numbers 0..254 travel as bytes ...
     v[3_000_000:3_000_010] = 0.5                      # ... anything else (255 too) through the chunk's patch list ...
     v[5_000_001] = 70000.0
@@ -85,6 +87,12 @@ def test_csc_upload_large_block_host_narrowing(lg, ctx, mode, monkeypatch):
         bad = ix.copy()
         bad[pos] = val
         with pytest.raises(lg.LegumeError):
+            lg.CscBlock.upload(ctx, ip, bad, v, D)
+    # rows running backwards / repeated inside a column are not canonical CSC: rejected, not silently mis-computed
+    for pos in (5, nnz // 3):
+        bad = ix.copy()
+        bad[pos] = bad[pos - 1] if pos % per else bad[pos + 1]
+        with pytest.raises(lg.LegumeError, match="canonical"):
             lg.CscBlock.upload(ctx, ip, bad, v, D)
 
 
@@ -107,11 +115,81 @@ def test_sparse_io_vec_from_several_backends_with_row_remaps(lg, ctx):
     assert (data.num_rows(), data.num_columns()) == (D, 125)
     st = data.streaming_sparse_running_stats()
     assert np.array_equal(st.sum(), whole.sum(1)) and np.array_equal(st.count_positives(), (whole > 0).sum(1))
-    one = lg.SparseIoVec.from_backends(ctx, parts[:1], D)  # a single backend: the remap is applied on the device
+    one = lg.SparseIoVec.from_backends(ctx, parts[:1], D)  # a single backend
     assert np.array_equal(one.streaming_sparse_running_stats().sum(), dense[0].sum(1))
     bad = (parts[0][0], parts[0][1], parts[0][2], parts[0][3][:10])
     with pytest.raises(lg.LegumeError):
         lg.SparseIoVec.from_backends(ctx, [bad, parts[1]], D)
+
+
+def _canonical_from_dense(a):
+    """dense (D, N) -> canonical CSC, the form read_columns_csc hands out"""
+    ip, ix, v = [0], [], []
+    for j in range(a.shape[1]):
+        r = np.nonzero(a[:, j])[0]
+        ix.extend(r.tolist())
+        v.extend(a[r, j].tolist())
+        ip.append(len(ix))
+    return np.array(ip, np.uint64), np.array(ix, np.uint64), np.array(v, np.float32)
+
+
+def test_remapped_backends_are_canonical_for_the_batch_arm(lg, ctx):
+    """read.rs:246-281: a permuted remap leaves a backend's columns unsorted, a many-to-one remap leaves duplicate rows
+    (summed), a row the shared axis lacks is dropped.  The block must come out canonical — the matched-column kernel
+    binary-searches a column's rows — and collapse_columns (batch arm) on it must equal the oracle on the matrix
+    assembled by hand."""
+    rng = np.random.default_rng(16)
+    D, K, knn = 150, 20, 5
+    parts, dense = [], []
+    for nloc, ncol, kind in ((100, 260, "perm"), (150, 240, "many_to_one"), (90, 200, "drop")):
+        ip, ix, v = random_csc(rng, nloc, ncol, 0.2)
+        if kind == "perm":
+            remap = rng.permutation(D)[:nloc].astype(np.uint32)
+        elif kind == "many_to_one":
+            remap = (rng.permutation(nloc) // 2).astype(np.uint32)          # two local rows per union row
+        else:
+            remap = rng.permutation(D)[:nloc].astype(np.uint32)
+            remap[rng.choice(nloc, 20, replace=False)] = 0xFFFFFFFF         # g2c == None
+        parts.append((ip, ix, v, remap))
+        a = np.zeros((D, ncol), np.float32)
+        for j in range(ncol):
+            for t in range(int(ip[j]), int(ip[j + 1])):
+                g = remap[int(ix[t])]
+                if g != 0xFFFFFFFF:
+                    a[g, j] += v[t]
+        dense.append(a)
+    whole = np.concatenate(dense, axis=1)
+    N = whole.shape[1]
+    data = lg.SparseIoVec.from_backends(ctx, parts, D)
+    ip2, ix2, v2 = data.block.download()
+    wip, wix, wv = _canonical_from_dense(whole)
+    assert np.array_equal(ip2, wip) and np.array_equal(ix2, wix) and np.array_equal(v2, wv)
+    # a backend row outside the remap is an error when the remap's length is known
+    with pytest.raises(lg.LegumeError):
+        lg.CscBlock.upload(ctx, parts[0][0], parts[0][1], parts[0][2], D, row_remap=parts[0][3][:10])
+    # the batch arm (per-cell matched statistics) on the joined block
+    proj = (rng.standard_normal((6, K))[rng.integers(0, 6, N)] * 3 + 0.3 * rng.standard_normal((N, K))).astype(np.float32)
+    batch = np.concatenate([np.full(a.shape[1], b, np.uint32) for b, a in enumerate(dense)])
+    data.build_hnsw_per_batch(proj, batch)
+    data.partition_columns_to_groups(proj, 4)
+    out, stat = data.collapse_columns(knn_batches=2, knn_cells=knn, num_opt_iter=10)
+    grp, S = np.asarray(data.col_to_group), data.num_groups()
+    order, _ = orc.batch_proximity(proj, batch, 3)
+    midx, mdist = orc.knn_match_batches(proj, batch, 3, knn, order)
+    obs, _ = orc.collapse_basic(wip, wix, wv, D, grp, S)
+    imp, res = orc.collect_matched_stat(wip, wix, wv, D, grp, S, midx, mdist)
+    assert np.array_equal(stat.observed_sum_ds, obs)
+    assert close(stat.imputed_sum_ds, imp, 1e-5) and close(stat.residual_sum_ds, res, 1e-4)
+    # wrapping device arrays that are not canonical is caught by the first kernel that relies on the order
+    import torch
+    bad_ix = ix2.astype(np.int32).copy()
+    lo, hi = int(ip2[3]), int(ip2[4])
+    if hi - lo >= 2:
+        bad_ix[lo], bad_ix[lo + 1] = bad_ix[lo + 1], bad_ix[lo]
+        blk = lg.CscBlock.wrap_device(ctx, torch.from_numpy(ip2.astype(np.int64)).cuda(), torch.from_numpy(bad_ix).cuda(),
+                                      torch.from_numpy(v2).cuda(), D)
+        with pytest.raises(lg.LegumeError, match="canonical"):
+            lg.SparseIoVec(ctx, blk).streaming_sparse_running_stats()
 
 
 def test_sim_matches_cpu_twin(lg, ctx):
@@ -568,6 +646,24 @@ def test_knn_tensor_path_is_exact(lg, ctx, nr, nq, d, k, kind):
     idx, dist = dct.search_indices(qry2, k)
     widx, wdist = orc.knn_topk(ref, qry2, k, nthreads=8)
     assert np.array_equal(idx, widx) and dist.tobytes() == wdist.tobytes()
+
+
+def test_knn_tensor_path_wide_dynamic_range(lg, ctx):
+    """one huge outlier sets the global f16 scale; a tight cluster near the origin then lives in the subnormal range of
+    the filter's "lo" halves, where its error is absolute, not relative: the acceptance test must still either prove
+    the answer or hand the query to the brute-force kernel.  Checked against the oracle (index sets and bytes)."""
+    rng = np.random.default_rng(99)
+    nr, nq, d, k = 20000, 4000, 50, 10
+    ref = (1e-4 * rng.normal(size=(nr, d))).astype(np.float32)       # tight cluster, norms ~ 7e-4
+    ref[nr - 1] = 50.0                                                 # the outlier: absmax 50 -> scale 2^-3
+    ref[nr // 2: nr // 2 + 500] *= 30.0                                # a shell further out, so that gaps differ in scale
+    qry = ref[:nq].copy()
+    ex = np.arange(nq, dtype=np.uint32)
+    dct = lg.ColumnDict.from_dmatrix(ctx, ref, list(range(nr)))
+    idx, dist = dct.search_indices(qry, k, ex)
+    widx, wdist = orc.knn_topk(ref, qry, k, ex, nthreads=8)
+    assert np.array_equal(idx, widx), int((idx != widx).sum())
+    assert dist.tobytes() == wdist.tobytes()
 
 
 # ---- BASELINE-sized inputs: size-independent properties (the oracle does not finish at these sizes) ---------------
