@@ -147,13 +147,16 @@ int lg_proj_centre_scale_exact(lg_ctx* ctx, float* d_proj, int K, uint64_t ncols
  * replaces binary_sort_columns (random_projection.rs:535-564) = rsvd (matrix-util/src/
  * dmatrix_rsvd.rs:85-180) + per-dimension standardise + sign bits.  codes: u64[ncols] < 2^kk. */
 int lg_binary_codes(lg_ctx* ctx, const float* proj_kn, int K, uint64_t ncols, int kk, uint64_t* out_codes);
-/* staged form (device pointers unless noted):
- *   basis      host math: Q (K x kk) = first kk columns of qr(X[:, 0..r]).q(), r = min(kk+5, N)
+/* staged form (device pointers; basis and factor also take host pointers):
+ *   basis      one-warp kernel: Q (K x kk) = first kk columns of qr(X[:, 0..r]).q(), r = min(kk+5, N) <= 21;
+ *              first_cols_kr = the K-vectors of the first r cells (the head of the projection itself)
  *   gram       B = Q^T X (kk x ncols) and block partials of the upper triangle of B B^T
  *              (M = kk(kk+1)/2, entry (a,b), a<=b, at a*kk - a(a-1)/2 + (b-a))
- *   factor     host math: Jacobi on the Gram sums -> U (kk x kk f32), sigma (kk), sign-fixed
+ *   factor     one-warp kernel: cyclic Jacobi (f64) on the Gram sums -> U (kk x kk f32), sigma (kk), sign-fixed
  *   vproj      V = B^T U / sigma (kk x ncols) and block partials of its column sums (M = kk)
- *   pack       warp-ballot sign packer: bit k of code_j = [V[k,j] > mean_k] */
+ *   means      mean[k] = (f32)(sums[k] / ncols_total)
+ *   pack       warp-ballot sign packer: bit k of code_j = [V[k,j] > mean_k]
+ * No stage reads anything back to the host: the whole of K3 is queued on the stream. */
 int lg_codes_basis(lg_ctx* ctx, const float* first_cols_kr, int K, int r, int kk, float* out_q);
 int lg_codes_gram(lg_ctx* ctx, const float* d_proj, int K, uint64_t ncols, const float* d_q, int kk,
                   float* d_b, double* d_partials);
@@ -161,6 +164,7 @@ int lg_codes_factor(lg_ctx* ctx, const double* gram_sums, const float* q, int K,
                     float* out_sigma);
 int lg_codes_vproj(lg_ctx* ctx, const float* d_b, int kk, uint64_t ncols, const float* d_u,
                    const float* d_sigma, float* d_v, double* d_partials);
+int lg_codes_means(lg_ctx* ctx, const double* d_sums, int kk, uint64_t ncols_total, float* d_mean);
 int lg_codes_pack(lg_ctx* ctx, const float* d_v, int kk, uint64_t ncols, const float* d_mean,
                   uint64_t* d_codes);
 

@@ -130,16 +130,189 @@ __global__ void __launch_bounds__(256) k_codes_pack(const float* __restrict__ v,
     if (cell < ncols) codes[cell] = (uint64_t)(window & ((1u << kk) - 1u));
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// K3 small factorisations ON THE DEVICE (one warp each): the K x r Householder QR whose first kk columns are the
+// range basis Q (dmatrix_rsvd.rs:129-131, `.qr().q()`), and the kk x kk symmetric eigen-decomposition that stands in
+// for SVD(B).  They used to run on the host between kernels (two stream synchronisations per call);
+// here every reduction keeps a fixed sequential order — a lane owns a column (QR) or a row (Jacobi) and walks it in
+// index order — and every operation is an explicit round-to-nearest intrinsic (no FMA contraction), so the result
+// does not depend on the launch shape.
+// ---------------------------------------------------------------------------------------------
+constexpr int QR_RMAX = KK_MAX + 5;  // r = kk + 5 columns at most
+
+__global__ void __launch_bounds__(32) k_codes_basis(const float* __restrict__ first_kr, int K, int r, int kk,
+                                                    float* __restrict__ q_out) {
+    extern __shared__ float qr_s[];  // A (K x r), then Q (K x dim), column-major
+    const int lane = threadIdx.x;
+    const int dim = K < r ? K : r;
+    float* A = qr_s;
+    float* Q = qr_s + (size_t)K * r;
+    __shared__ float diag[QR_RMAX];
+    for (int e = lane; e < K * r; e += 32) A[e] = first_kr[e];
+    __syncwarp();
+    for (int c = 0; c < dim; ++c) {
+        float* col = A + (size_t)c * K;
+        // reflection axis of A[c.., c]: every lane folds the same values in the same order (no broadcast needed)
+        float sq = 0.0f;
+        for (int i = c; i < K; ++i) sq = __fadd_rn(sq, __fmul_rn(col[i], col[i]));
+        const float norm = __fsqrt_rn(sq);
+        const float head = col[c];
+        const float signed_norm = head < 0.0f ? -norm : norm;
+        const float factor = __fmul_rn(__fadd_rn(sq, __fmul_rn(fabsf(head), norm)), 2.0f);
+        __syncwarp();
+        if (lane == 0) col[c] = __fadd_rn(head, signed_norm);
+        __syncwarp();
+        if (factor != 0.0f) {
+            const float fs = __fsqrt_rn(factor);
+            for (int i = c + lane; i < K; i += 32) col[i] = __fdiv_rn(col[i], fs);
+            __syncwarp();
+            float n2 = 0.0f;
+            for (int i = c; i < K; ++i) n2 = __fadd_rn(n2, __fmul_rn(col[i], col[i]));
+            const float nn = __fsqrt_rn(n2);
+            __syncwarp();
+            for (int i = c + lane; i < K; i += 32) col[i] = __fdiv_rn(col[i], nn);
+            __syncwarp();
+            const float dg = -signed_norm;
+            if (lane == 0) diag[c] = dg;
+            const float sign = dg > 0.0f ? 1.0f : (dg < 0.0f ? -1.0f : 0.0f);
+            const float m_two = __fmul_rn(sign, -2.0f);
+            const int j = c + 1 + lane;  // a lane reflects its own column
+            if (j < r) {
+                float* cj = A + (size_t)j * K;
+                float dot = 0.0f;
+                for (int i = c; i < K; ++i) dot = __fadd_rn(dot, __fmul_rn(col[i], cj[i]));
+                const float f = __fmul_rn(dot, m_two);
+                for (int i = c; i < K; ++i) cj[i] = __fadd_rn(__fmul_rn(f, col[i]), __fmul_rn(sign, cj[i]));
+            }
+        } else if (lane == 0) {
+            diag[c] = signed_norm;
+        }
+        __syncwarp();
+    }
+    // QR::q(): identity, reflected by the stored axes from the last to the first
+    for (int e = lane; e < K * dim; e += 32) Q[e] = (e % K) == (e / K) ? 1.0f : 0.0f;
+    __syncwarp();
+    for (int c = dim - 1; c >= 0; --c) {
+        const float* col = A + (size_t)c * K;
+        const float dg = diag[c];
+        const float sign = dg > 0.0f ? 1.0f : (dg < 0.0f ? -1.0f : 0.0f);
+        const float m_two = __fmul_rn(sign, -2.0f);
+        const int j = c + lane;
+        if (j < dim) {
+            float* qj = Q + (size_t)j * K;
+            float dot = 0.0f;
+            for (int i = c; i < K; ++i) dot = __fadd_rn(dot, __fmul_rn(col[i], qj[i]));
+            const float f = __fmul_rn(dot, m_two);
+            for (int i = c; i < K; ++i) qj[i] = __fadd_rn(__fmul_rn(f, col[i]), __fmul_rn(sign, qj[i]));
+        }
+        __syncwarp();
+    }
+    const int keep = kk < dim ? kk : dim;
+    for (int e = lane; e < K * kk; e += 32) q_out[e] = (e / K) < keep ? Q[e] : 0.0f;
+}
+
+// cyclic Jacobi on the kk x kk Gram matrix (f64), eigenvalues descending (stable), then the sign convention
+// (largest-magnitude component of Q u_k positive, first index wins ties) and sigma = sqrt(max(lambda, 0))
+__global__ void __launch_bounds__(32) k_codes_factor(const double* __restrict__ gram_sums, const float* __restrict__ q, int K,
+                                                     int n, float* __restrict__ out_u, float* __restrict__ out_sigma) {
+    __shared__ double a[KK_MAX * KK_MAX], v[KK_MAX * KK_MAX];
+    __shared__ int order[KK_MAX];
+    const int lane = threadIdx.x;
+#define JA(i, j) a[(j) * n + (i)]
+#define JV(i, j) v[(j) * n + (i)]
+    if (lane == 0) {
+        int slot = 0;
+        for (int x = 0; x < n; ++x)
+            for (int y = x; y < n; ++y) {
+                JA(x, y) = gram_sums[slot];
+                JA(y, x) = gram_sums[slot];
+                ++slot;
+            }
+    }
+    for (int e = lane; e < n * n; e += 32) v[e] = (e % n) == (e / n) ? 1.0 : 0.0;
+    __syncwarp();
+    for (int sweep = 0; sweep < 64; ++sweep) {
+        double off = 0.0, dg = 0.0;
+        for (int p = 0; p < n; ++p) {
+            dg = __dadd_rn(dg, __dmul_rn(JA(p, p), JA(p, p)));
+            for (int qq = p + 1; qq < n; ++qq) off = __dadd_rn(off, __dmul_rn(JA(p, qq), JA(p, qq)));
+        }
+        if (off <= 1e-60 || off <= __dmul_rn(1e-32, dg)) break;
+        for (int p = 0; p < n - 1; ++p)
+            for (int qq = p + 1; qq < n; ++qq) {
+                const double apq = JA(p, qq);
+                if (apq == 0.0) continue;  // warp-uniform: every lane reads the same element
+                const double theta = __ddiv_rn(__dsub_rn(JA(qq, qq), JA(p, p)), __dmul_rn(2.0, apq));
+                const double t = __ddiv_rn(theta >= 0.0 ? 1.0 : -1.0,
+                                           __dadd_rn(fabs(theta), __dsqrt_rn(__dadd_rn(__dmul_rn(theta, theta), 1.0))));
+                const double c = __ddiv_rn(1.0, __dsqrt_rn(__dadd_rn(__dmul_rn(t, t), 1.0)));
+                const double s = __dmul_rn(t, c);
+                __syncwarp();
+                if (lane < n) {  // columns p, q: lane = row
+                    const double akp = JA(lane, p), akq = JA(lane, qq);
+                    JA(lane, p) = __dsub_rn(__dmul_rn(c, akp), __dmul_rn(s, akq));
+                    JA(lane, qq) = __dadd_rn(__dmul_rn(s, akp), __dmul_rn(c, akq));
+                }
+                __syncwarp();
+                if (lane < n) {  // rows p, q: lane = column
+                    const double apk = JA(p, lane), aqk = JA(qq, lane);
+                    JA(p, lane) = __dsub_rn(__dmul_rn(c, apk), __dmul_rn(s, aqk));
+                    JA(qq, lane) = __dadd_rn(__dmul_rn(s, apk), __dmul_rn(c, aqk));
+                    const double vkp = JV(lane, p), vkq = JV(lane, qq);
+                    JV(lane, p) = __dsub_rn(__dmul_rn(c, vkp), __dmul_rn(s, vkq));
+                    JV(lane, qq) = __dadd_rn(__dmul_rn(s, vkp), __dmul_rn(c, vkq));
+                }
+                __syncwarp();
+            }
+    }
+    __syncwarp();
+    if (lane == 0) {  // stable insertion sort, descending eigenvalue
+        for (int i = 0; i < n; ++i) order[i] = i;
+        for (int i = 1; i < n; ++i) {
+            const int o = order[i];
+            int j = i - 1;
+            while (j >= 0 && JA(order[j], order[j]) < JA(o, o)) {
+                order[j + 1] = order[j];
+                --j;
+            }
+            order[j + 1] = o;
+        }
+    }
+    __syncwarp();
+    if (lane < n) {  // lane = singular vector k
+        const int src = order[lane];
+        double best = 0.0, bestv = 0.0;
+        for (int d = 0; d < K; ++d) {
+            double s = 0.0;
+            for (int i = 0; i < n; ++i) s = __dadd_rn(s, __dmul_rn((double)q[(size_t)i * K + d], JV(i, src)));
+            if (fabs(s) > best) {
+                best = fabs(s);
+                bestv = s;
+            }
+        }
+        const double flip = bestv < 0.0 ? -1.0 : 1.0;
+        for (int i = 0; i < n; ++i) out_u[(size_t)lane * n + i] = (float)__dmul_rn(flip, JV(i, src));
+        const double ev = JA(src, src);
+        out_sigma[lane] = (float)__dsqrt_rn(ev > 0.0 ? ev : 0.0);
+    }
+#undef JA
+#undef JV
+}
+
 // ---- staged entry points --------------------------------------------------------------------
 extern "C" int lg_codes_basis(lg_ctx* ctx, const float* first_cols_kr, int K, int r, int kk, float* out_q) {
     if (!ctx) return LG_ERR_INVALID;
-    LG_REQUIRE(ctx, first_cols_kr && out_q && K >= 1 && r >= 1 && kk >= 1 && kk <= r && kk <= K,
+    LG_REQUIRE(ctx, first_cols_kr && out_q && K >= 1 && K <= 128 && r >= 1 && r <= QR_RMAX && kk >= 1 && kk <= r && kk <= K,
                "lg_codes_basis: bad argument");
-    LG_REQUIRE(ctx, !lg_is_device_ptr(first_cols_kr) && !lg_is_device_ptr(out_q), "lg_codes_basis takes host arrays");
-    std::vector<float> qf((size_t)K * r);
-    lgh_householder_q(first_cols_kr, K, r, qf.data());
-    std::copy(qf.begin(), qf.begin() + (size_t)K * kk, out_q);
-    return LG_OK;
+    cudaSetDevice(ctx->device);
+    LgStage st(ctx);
+    const float* d_first;
+    float* d_q;
+    LG_TRY(st.in(first_cols_kr, (size_t)K * r, &d_first));
+    LG_TRY(st.out(out_q, (size_t)K * kk, &d_q));
+    LG_LAUNCH(ctx, k_codes_basis, 1, 32, (size_t)2 * K * r * sizeof(float), d_first, K, r, kk, d_q);
+    return st.finish();
 }
 
 extern "C" int lg_codes_gram(lg_ctx* ctx, const float* d_proj, int K, uint64_t ncols, const float* d_q, int kk,
@@ -158,34 +331,18 @@ extern "C" int lg_codes_gram(lg_ctx* ctx, const float* d_proj, int K, uint64_t n
 extern "C" int lg_codes_factor(lg_ctx* ctx, const double* gram_sums, const float* q, int K, int kk, float* out_u,
                                float* out_sigma) {
     if (!ctx) return LG_ERR_INVALID;
-    LG_REQUIRE(ctx, gram_sums && q && out_u && out_sigma && kk >= 1 && kk <= KK_MAX, "lg_codes_factor: bad argument");
-    LG_REQUIRE(ctx, !lg_is_device_ptr(gram_sums) && !lg_is_device_ptr(q) && !lg_is_device_ptr(out_u),
-               "lg_codes_factor takes host arrays");
-    std::vector<double> G((size_t)kk * kk), ev(kk), U((size_t)kk * kk);
-    int slot = 0;
-    for (int a = 0; a < kk; ++a)
-        for (int b = a; b < kk; ++b) {
-            G[(size_t)b * kk + a] = gram_sums[slot];
-            G[(size_t)a * kk + b] = gram_sums[slot];
-            ++slot;
-        }
-    lgh_jacobi_eig(G.data(), kk, ev.data(), U.data());
-    for (int k = 0; k < kk; ++k) {
-        // sign convention: largest-magnitude component of Q u_k (in R^K) positive, first index wins ties
-        double best = 0.0, bestv = 0.0;
-        for (int d = 0; d < K; ++d) {
-            double s = 0.0;
-            for (int i = 0; i < kk; ++i) s += (double)q[(size_t)i * K + d] * U[(size_t)k * kk + i];
-            if (std::fabs(s) > best) {
-                best = std::fabs(s);
-                bestv = s;
-            }
-        }
-        const double flip = bestv < 0.0 ? -1.0 : 1.0;
-        for (int i = 0; i < kk; ++i) out_u[(size_t)k * kk + i] = (float)(flip * U[(size_t)k * kk + i]);
-        out_sigma[k] = (float)std::sqrt(std::max(ev[k], 0.0));
-    }
-    return LG_OK;
+    LG_REQUIRE(ctx, gram_sums && q && out_u && out_sigma && kk >= 1 && kk <= KK_MAX && K >= 1, "lg_codes_factor: bad argument");
+    cudaSetDevice(ctx->device);
+    LgStage st(ctx);
+    const double* d_g;
+    const float* d_q;
+    float *d_u, *d_s;
+    LG_TRY(st.in(gram_sums, (size_t)kk * (kk + 1) / 2, &d_g));
+    LG_TRY(st.in(q, (size_t)K * kk, &d_q));
+    LG_TRY(st.out(out_u, (size_t)kk * kk, &d_u));
+    LG_TRY(st.out(out_sigma, (size_t)kk, &d_s));
+    LG_LAUNCH(ctx, k_codes_factor, 1, 32, 0, d_g, d_q, K, kk, d_u, d_s);
+    return st.finish();
 }
 
 extern "C" int lg_codes_vproj(lg_ctx* ctx, const float* d_b, int kk, uint64_t ncols, const float* d_u,
@@ -217,6 +374,14 @@ __global__ void k_means_from_sums(const double* __restrict__ sums, int kk, uint6
     if (k < kk) mean[k] = (float)(sums[k] / (double)ncols);
 }
 
+extern "C" int lg_codes_means(lg_ctx* ctx, const double* d_sums, int kk, uint64_t ncols_total, float* d_mean) {
+    if (!ctx) return LG_ERR_INVALID;
+    LG_REQUIRE(ctx, d_sums && d_mean && kk >= 1 && kk <= KK_MAX && ncols_total >= 1, "lg_codes_means: bad argument");
+    cudaSetDevice(ctx->device);
+    LG_LAUNCH(ctx, k_means_from_sums, 1, 32, 0, d_sums, kk, ncols_total, d_mean);
+    return LG_OK;
+}
+
 // ---- composite: binary_sort_columns -------------------------------------------------------------
 extern "C" int lg_binary_codes(lg_ctx* ctx, const float* proj_kn, int K, uint64_t ncols, int kk, uint64_t* out_codes) {
     if (!ctx) return LG_ERR_INVALID;
@@ -233,11 +398,6 @@ extern "C" int lg_binary_codes(lg_ctx* ctx, const float* proj_kn, int K, uint64_
     int rank = (int)std::min<uint64_t>((uint64_t)K, ncols);
     int r = rank > kk ? kk + 5 : rank;
     if ((uint64_t)r > ncols) r = (int)ncols;
-    std::vector<float> first((size_t)K * r), q((size_t)K * kk);
-    LG_CUDA(ctx, cudaMemcpyAsync(first.data(), d_proj, first.size() * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
-    LG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    LG_TRY(lg_codes_basis(ctx, first.data(), K, r, kk, q.data()));
-
     const uint64_t nblk = (ncols + LG_BLOCK_CELLS - 1) / LG_BLOCK_CELLS;
     const int M = kk * (kk + 1) / 2;
     float *d_q, *d_b, *d_v, *d_u, *d_sig, *d_mean;
@@ -250,22 +410,15 @@ extern "C" int lg_binary_codes(lg_ctx* ctx, const float* proj_kn, int K, uint64_
     LG_TRY(st.scratch((size_t)kk, &d_mean));
     LG_TRY(st.scratch((size_t)nblk * M, &d_part));
     LG_TRY(st.scratch((size_t)M, &d_sums));
-    LG_CUDA(ctx, cudaMemcpyAsync(d_q, q.data(), q.size() * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+    // everything stays on the stream: the first r cells' K-vectors are the head of the projection itself
+    LG_TRY(lg_codes_basis(ctx, d_proj, K, r, kk, d_q));
     LG_TRY(lg_codes_gram(ctx, d_proj, K, ncols, d_q, kk, d_b, d_part));
     LG_TRY(lg_block_partials_finalize(ctx, d_part, nblk, M, d_sums));
-    std::vector<double> gram(M);
-    LG_CUDA(ctx, cudaMemcpyAsync(gram.data(), d_sums, M * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
-    LG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    std::vector<float> u((size_t)kk * kk), sig(kk);
-    LG_TRY(lg_codes_factor(ctx, gram.data(), q.data(), K, kk, u.data(), sig.data()));
-    LG_CUDA(ctx, cudaMemcpyAsync(d_u, u.data(), u.size() * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
-    LG_CUDA(ctx, cudaMemcpyAsync(d_sig, sig.data(), sig.size() * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+    LG_TRY(lg_codes_factor(ctx, d_sums, d_q, K, kk, d_u, d_sig));
     LG_TRY(lg_codes_vproj(ctx, d_b, kk, ncols, d_u, d_sig, d_v, d_part));
     LG_TRY(lg_block_partials_finalize(ctx, d_part, nblk, kk, d_sums));
     LG_LAUNCH(ctx, k_means_from_sums, 1, 32, 0, d_sums, kk, ncols, d_mean);
     LG_TRY(lg_codes_pack(ctx, d_v, kk, ncols, d_mean, d_codes));
-    // u/sig/q host vectors must outlive the async copies
-    LG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return st.finish();
 }
 

@@ -212,6 +212,4 @@ int lg_csc_require_canonical(lg_ctx* ctx, const lg_csc* m, const char* who);
 int lg_check_labels(lg_ctx* ctx, const uint32_t* d_label, uint64_t n, uint32_t bound, const char* what);
 
 // host-side small dense math (lg_hostmath.cpp) — plain C++, no CUDA, no oracle
-void lgh_householder_q(const float* a_kr, int K, int r, float* q_kr);
-void lgh_jacobi_eig(const double* g, int n, double* evals, double* evecs);
 float lgh_l2_sq(const float* a, const float* b, int d);

@@ -60,6 +60,7 @@ _sig = {
     "lg_codes_gram": [_vp, _vp, _i, _u64, _vp, _i, _vp, _vp],
     "lg_codes_factor": [_vp, _vp, _vp, _i, _i, _vp, _vp],
     "lg_codes_vproj": [_vp, _vp, _i, _u64, _vp, _vp, _vp, _vp],
+    "lg_codes_means": [_vp, _vp, _i, _u64, _vp],
     "lg_codes_pack": [_vp, _vp, _i, _u64, _vp, _vp],
     "lg_assign_groups": [_vp, _vp, _u64, _i, _i, _vp, C.POINTER(_u32)],
     "lg_code_presence": [_vp, _vp, _u64, _i, _vp],

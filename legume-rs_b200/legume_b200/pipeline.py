@@ -121,24 +121,24 @@ class HotPath:
                 raise LegumeError(1, "rank 0 must hold at least kk+5 cells")
             first.copy_(proj[:r])
         self.ex.broadcast_(first, src=0)
-        first_h = first.cpu().numpy()
-        q_h = np.empty((kk, K), np.float32)
-        ctx.check(lib.lg_codes_basis(ctx.h, _ptr(first_h), K, r, kk, _ptr(q_h)))
-        q = torch.from_numpy(q_h).to(self.dev)
+        # K3 stays on the stream: the K x r QR and the kk x kk eigen-decomposition are one-warp kernels
+        q = torch.empty((kk, K), dtype=torch.float32, device=self.dev)
+        ctx.check(lib.lg_codes_basis(ctx.h, _ptr(first), K, r, kk, _ptr(q)))
         nblk = self._nblk(n)
         M = kk * (kk + 1) // 2
         b = torch.empty((n, kk), dtype=torch.float32, device=self.dev)
         part = torch.empty((max(nblk, 1), M), dtype=torch.float64, device=self.dev)
         ctx.check(lib.lg_codes_gram(ctx.h, _ptr(proj), K, n, _ptr(q), kk, _ptr(b), _ptr(part)))
-        gram_h = self._sum_partials(part, nblk, M).cpu().numpy()
-        u_h, sig_h = np.empty((kk, kk), np.float32), np.empty(kk, np.float32)
-        ctx.check(lib.lg_codes_factor(ctx.h, _ptr(gram_h), _ptr(q_h), K, kk, _ptr(u_h), _ptr(sig_h)))
-        u, sig = torch.from_numpy(u_h).to(self.dev), torch.from_numpy(sig_h).to(self.dev)
+        gram = self._sum_partials(part, nblk, M)
+        u = torch.empty((kk, kk), dtype=torch.float32, device=self.dev)
+        sig = torch.empty(kk, dtype=torch.float32, device=self.dev)
+        ctx.check(lib.lg_codes_factor(ctx.h, _ptr(gram), _ptr(q), K, kk, _ptr(u), _ptr(sig)))
         v = torch.empty((n, kk), dtype=torch.float32, device=self.dev)
         part2 = torch.empty((max(nblk, 1), kk), dtype=torch.float64, device=self.dev)
         ctx.check(lib.lg_codes_vproj(ctx.h, _ptr(b), kk, n, _ptr(u), _ptr(sig), _ptr(v), _ptr(part2)))
-        sums_h = self._sum_partials(part2, nblk, kk).cpu().numpy()
-        mean = torch.from_numpy((sums_h / float(ntot)).astype(np.float32)).to(self.dev)
+        sums = self._sum_partials(part2, nblk, kk)
+        mean = torch.empty(kk, dtype=torch.float32, device=self.dev)
+        ctx.check(lib.lg_codes_means(ctx.h, _ptr(sums), kk, ntot, _ptr(mean)))
         codes = torch.empty(n, dtype=torch.int64, device=self.dev)
         ctx.check(lib.lg_codes_pack(ctx.h, _ptr(v), kk, n, _ptr(mean), _ptr(codes)))
         return codes

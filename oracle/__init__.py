@@ -22,7 +22,7 @@ _LIB_PATH = os.path.join(_HERE, "liblegume_oracle.so")
 
 def build(force: bool = False) -> str:
     """Compile the oracle with its committed Makefile (building the checker is not using it)."""
-    srcs = [os.path.join(_HERE, f) for f in ("oracle.cpp", "oracle_adjust.cpp", "oracle_next.cpp", "oracle.h")]
+    srcs = [os.path.join(_HERE, f) for f in ("oracle.cpp", "oracle_adjust.cpp", "oracle_next.cpp", "oracle_svd.cpp", "oracle.h")]
     stale = (not os.path.exists(_LIB_PATH)) or os.path.getmtime(_LIB_PATH) < max(os.path.getmtime(f) for f in srcs)
     if force or stale:
         subprocess.run(["make", "-C", _HERE], check=True, capture_output=True)
@@ -58,6 +58,7 @@ def lib():
         L.orc_assign_groups_padded.restype = C.c_uint32
         L.orc_level_sort_dims.restype = C.c_int
         L.orc_binary_codes.restype = C.c_int
+        L.orc_binary_codes_svd.restype = C.c_int
         L.orc_sim_poisson_csc.restype = C.c_uint64
         L.orc_pb_layout.restype = C.c_uint32
         L.orc_fine_to_coarse.restype = C.c_uint32
@@ -113,6 +114,31 @@ def binary_codes(proj, kk, details=False):
     if rc != 0:
         raise ValueError("orc_binary_codes: bad arguments")
     return (codes, q, u, sig, mean) if details else codes
+
+
+def binary_codes_svd(proj, kk, details=False):
+    """the independent restatement (oracle_svd.cpp): f32 bidiagonalisation + implicit QR SVD, the reference's route.
+    Bits are defined up to per-bit complement."""
+    proj = np.ascontiguousarray(proj, np.float32)
+    n, K = proj.shape
+    codes = np.zeros(n, np.uint64)
+    v = np.zeros((kk, n), np.float32)
+    sig = np.zeros(kk, np.float32)
+    rc = lib().orc_binary_codes_svd(_ptr(proj, C.c_float), C.c_int(K), C.c_uint64(n), C.c_int(kk), _ptr(codes, C.c_uint64),
+                                    _ptr(v, C.c_float), _ptr(sig, C.c_float))
+    if rc != 0:
+        raise ValueError(f"orc_binary_codes_svd failed ({rc})")
+    return (codes, v, sig) if details else codes
+
+
+def partition_agreement(codes_a, codes_b, kk):
+    """per bit: the fraction of cells two code sets put on the same side, up to complement of the bit"""
+    a, b = np.asarray(codes_a, np.uint64), np.asarray(codes_b, np.uint64)
+    out = []
+    for k in range(kk):
+        same = float(np.mean(((a >> np.uint64(k)) & np.uint64(1)) == ((b >> np.uint64(k)) & np.uint64(1))))
+        out.append(max(same, 1.0 - same))
+    return out
 
 
 def householder_q(a):

@@ -41,6 +41,11 @@ void orc_project_finish(float* proj_kn, int K, uint64_t ncols, const uint32_t* b
  * out_q (K×kk), out_b (kk×N), out_u (kk×kk, f32), out_sigma (kk), out_mean (kk). */
 int orc_binary_codes(const float* proj_kn, int K, uint64_t ncols, int kk, uint64_t* codes,
                      float* out_q, float* out_u, float* out_sigma, float* out_mean);
+/* the INDEPENDENT restatement (oracle_svd.cpp): the reference's own route — f32 Householder bidiagonalisation +
+ * implicit-shift QR SVD of B, then scale_columns_inplace with f32 left folds and [V > 0].  Defines each bit's
+ * partition of the cells up to complement (singular-vector signs are free).  out_v: N x kk column-major or NULL. */
+int orc_binary_codes_svd(const float* proj_kn, int K, uint64_t ncols, int kk, uint64_t* codes, float* out_v,
+                         float* out_sigma);
 /* Householder QR of a K×r block, thin Q (K×r) — nalgebra qr().q() restated */
 void orc_householder_q(const float* a_kr, int K, int r, float* q_kr);
 /* cyclic Jacobi on a symmetric n×n f64 matrix: eigenvalues descending */

@@ -314,6 +314,41 @@ def test_binary_codes_match_f64_svd_up_to_bit_complement():
         assert max(agree, 1 - agree) > 0.999, (k, agree)
 
 
+def test_independent_svd_oracle_against_numpy_and_the_mirror():
+    """oracle_svd.cpp (f32 Householder bidiagonalisation + implicit-shift QR, the reference's route) is a second,
+    independent statement of binary_sort_columns: its singular values match numpy's f64 SVD, its factor is
+    orthonormal (rsvd_tests.rs:75-93), and the partitions it defines agree with numpy's and with the mirror oracle's
+    (the one the GPU is held to bit for bit) up to per-bit complement on all but the cells whose standardised
+    coordinate is rounding noise away from zero."""
+    rng = np.random.default_rng(31)
+    for n, K, kk in ((5000, 50, 10), (20000, 50, 10), (777, 24, 7)):
+        z = rng.normal(size=(n, 6)) @ rng.normal(size=(6, K)) + 0.3 * rng.normal(size=(n, K))
+        proj = orc.project_finish(z.astype(np.float32))
+        codes, v, sig = orc.binary_codes_svd(proj, kk, details=True)
+        assert np.array_equal(codes, orc.binary_codes_svd(proj, kk))  # reproducible, rsvd_tests.rs:22-32
+        mirror, q, _, msig, _ = orc.binary_codes(proj, kk, details=True)
+        X = proj.astype(np.float64)
+        B = X @ q.astype(np.float64).T
+        U, S, _ = np.linalg.svd(B, full_matrices=False)
+        assert np.allclose(sig, S, rtol=1e-4) and np.allclose(msig, S, rtol=1e-4)
+        # v holds the standardised columns: unit variance, zero mean, mutually orthogonal
+        g = (v.astype(np.float64) @ v.astype(np.float64).T) / n
+        assert np.allclose(g, np.eye(kk), atol=2e-2)  # centring costs a little orthogonality
+        ref = np.zeros(n, np.uint64)
+        for k in range(kk):
+            ref |= ((U[:, k] - U[:, k].mean()) > 0).astype(np.uint64) << np.uint64(k)
+        for other in (ref, mirror):
+            agree = orc.partition_agreement(codes, other, kk)
+            assert min(agree) > 0.998, agree
+        # the cells that differ are exactly the ones sitting on the boundary
+        diff = codes ^ mirror
+        for k in range(kk):
+            a = float(np.mean(((diff >> np.uint64(k)) & np.uint64(1)) == 0))
+            flipped = (((diff >> np.uint64(k)) & np.uint64(1)) == (1 if a > 0.5 else 0))
+            if flipped.any():
+                assert np.abs(v[k][flipped]).max() < 1e-2, (k, np.abs(v[k][flipped]).max())
+
+
 def test_collapse_basic_and_batch_against_dense():
     rng = np.random.default_rng(4)
     D, N, S, B = 40, 300, 7, 3
