@@ -22,7 +22,7 @@ _LIB_PATH = os.path.join(_HERE, "liblegume_oracle.so")
 
 def build(force: bool = False) -> str:
     """Compile the oracle with its committed Makefile (building the checker is not using it)."""
-    srcs = [os.path.join(_HERE, f) for f in ("oracle.cpp", "oracle_adjust.cpp", "oracle_next.cpp", "oracle_svd.cpp", "oracle.h")]
+    srcs = [os.path.join(_HERE, f) for f in ("oracle.cpp", "oracle_adjust.cpp", "oracle_next.cpp", "oracle_svd.cpp", "oracle_bench.cpp", "oracle.h")]
     stale = (not os.path.exists(_LIB_PATH)) or os.path.getmtime(_LIB_PATH) < max(os.path.getmtime(f) for f in srcs)
     if force or stale:
         subprocess.run(["make", "-C", _HERE], check=True, capture_output=True)
@@ -451,3 +451,39 @@ def nystrom_project(indptr, indices, data, nrows, basis_dk, delta_dp=None, pb_of
                               C.c_uint64(n), _ptr(basis, C.c_float), C.c_int(K), _ptr(delta, C.c_float), _ptr(pb, C.c_uint32),
                               C.c_uint32(P), C.c_float(column_sum_norm), _ptr(out, C.c_float))
     return out
+
+
+# ---- the CPU baseline leg (oracle_bench.cpp) -------------------------------------------------
+def bench_project_blocks(indptr, indices, data, basis_kd, block=0, nthreads=0):
+    """visit_columns_by_block + project_columns_visitor, 100-cell blocks, per-block repack, Mutex copy-out"""
+    ip, ix, v = _csc(indptr, indices, data)
+    basis_kd = np.ascontiguousarray(basis_kd, np.float32)
+    D, K = basis_kd.shape
+    n = len(ip) - 1
+    out = np.zeros((n, K), np.float32)
+    lib().orc_bench_project_blocks(_ptr(ip, C.c_uint64), _ptr(ix, C.c_uint64), _ptr(v, C.c_float), C.c_uint64(D), C.c_uint64(n),
+                                   _ptr(basis_kd, C.c_float), C.c_int(K), C.c_uint64(block), C.c_int(nthreads), _ptr(out, C.c_float))
+    return out
+
+
+def bench_collapse_groups(indptr, indices, data, nrows, group_of_cell, S, locked=True, nthreads=0):
+    ip, ix, v = _csc(indptr, indices, data)
+    grp = np.ascontiguousarray(group_of_cell, np.uint32)
+    s = np.zeros((S, nrows), np.float32)
+    size = np.zeros(S, np.float32)
+    lib().orc_bench_collapse_groups(_ptr(ip, C.c_uint64), _ptr(ix, C.c_uint64), _ptr(v, C.c_float), C.c_uint64(nrows),
+                                    C.c_uint64(len(ip) - 1), _ptr(grp, C.c_uint32), C.c_uint32(S), C.c_int(int(locked)),
+                                    C.c_int(nthreads), _ptr(s, C.c_float), _ptr(size, C.c_float))
+    return s, size
+
+
+def bench_optimize_single_mt(sum_ds, size_s, a0=1.0, b0=1.0, target=TARGET_ALL, nthreads=0):
+    sum_ds = np.ascontiguousarray(sum_ds, np.float32)
+    size_s = np.ascontiguousarray(size_s, np.float32)
+    S, D = sum_ds.shape
+    outs = {k: np.empty_like(sum_ds) for k in ("mean", "sd", "log_mean", "log_sd")}
+    lib().orc_bench_optimize_single_mt(_ptr(sum_ds, C.c_float), _ptr(size_s, C.c_float), C.c_uint64(D), C.c_uint32(S),
+                                       C.c_float(a0), C.c_float(b0), C.c_int(target), C.c_int(nthreads),
+                                       _ptr(outs["mean"], C.c_float), _ptr(outs["sd"], C.c_float),
+                                       _ptr(outs["log_mean"], C.c_float), _ptr(outs["log_sd"], C.c_float))
+    return outs

@@ -145,6 +145,20 @@ void orc_nystrom_project(const uint64_t* indptr, const uint64_t* indices, const 
                          uint64_t ncols, const float* basis_dk, int K, const float* delta_dp, const uint32_t* pb_of_cell,
                          uint32_t P, float column_sum_norm, float* out_kn);
 
+/* ---- the CPU BASELINE leg (oracle_bench.cpp): the same arithmetic in the reference's execution structure ---------- */
+uint64_t orc_default_block_size(uint64_t num_features);   /* matrix-util/src/utils.rs:86-94 */
+/* visit_columns_by_block + project_columns_visitor: block = 0 selects default_block_size(D) */
+void orc_bench_project_blocks(const uint64_t* indptr, const uint64_t* indices, const float* data, uint64_t D,
+                              uint64_t ncols, const float* basis_kd, int K, uint64_t block, int nthreads, float* proj_kn);
+/* visit_columns_by_group + collect_basic_stat_visitor; locked = 1 holds the global Mutex across the accumulate loop
+ * (stats.rs:119), locked = 0 is the lock-free variant */
+void orc_bench_collapse_groups(const uint64_t* indptr, const uint64_t* indices, const float* data, uint64_t D,
+                               uint64_t ncols, const uint32_t* group_of_cell, uint32_t S, int locked, int nthreads,
+                               float* sum_ds, float* size_s);
+/* optimize: par_iter over gene blocks (stats.rs:462-478), B <= 1 arm */
+void orc_bench_optimize_single_mt(const float* sum_ds, const float* size_s, uint64_t D, uint32_t S, float a0, float b0,
+                                  int target, int nthreads, float* mean, float* sd, float* log_mean, float* log_sd);
+
 #ifdef __cplusplus
 }
 #endif

@@ -77,9 +77,20 @@ def compare(got, want, kk):
     return out
 
 
-def run_e2e_parity(ctx, D=20000, N=50000, K=50, kk=10, depth=1000, seed=42, modes=("exact", "fast"), nthreads=0):
+def sim_counts_gpu(ctx, D, N, ntopic=8, depth=1000, seed=42):
+    """the same counts from the GPU generator (bit-identical twin, tests/test_gpu_parity.py::test_sim_matches_cpu_twin);
+    used by bench.py, where the single-threaded CPU generator would cost 15 s"""
+    from legume_b200 import sim
+    tabs = sim.make_tables(D, ntopic=ntopic, nbatch=1, depth=depth, seed=seed)
+    blk, _, batch = sim.sim_block(ctx, tabs, 0, N)
+    ip, ix, v = blk.download()
+    blk.free()
+    return ip, ix, v, batch.astype(np.uint32)
+
+
+def run_e2e_parity(ctx, D=20000, N=50000, K=50, kk=10, depth=1000, seed=42, modes=("exact", "fast"), nthreads=0, counts="cpu"):
     """configs[0] by default.  Returns {"config": ..., "oracle_seconds": ..., "exact": {...}, "fast": {...}}"""
-    ip, ix, v, batch = sim_counts_cpu(D, N, depth=depth, seed=seed)
+    ip, ix, v, batch = sim_counts_cpu(D, N, depth=depth, seed=seed) if counts == "cpu" else sim_counts_gpu(ctx, D, N, depth=depth, seed=seed)
     basis = np.random.default_rng(seed).standard_normal((D, K)).astype(np.float32)
     want = oracle_path(ip, ix, v, D, basis, batch, 1, kk, nthreads)
     rep = dict(config=dict(D=D, N=N, nnz=int(len(v)), K=K, kk=kk, depth=depth, seed=seed, nbatch=1),
