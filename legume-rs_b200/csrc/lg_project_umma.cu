@@ -113,15 +113,19 @@ __global__ void k_quantize_basis(const float* __restrict__ basis_kd, uint64_t D,
         out = (int8_t)d[digit];
     }
     const uint64_t chunk = gene >> 5;
-    const int k = (int)(gene & 31);
+    // K position of a gene inside its group of 32: the expander's (w << (7 - b)) & 0x80808080 puts bit b + 8j of a bitmap
+    // word at K position 4b + j, and the scan keeps the NATURAL bit order (gene offset o at bit o: one shift per entry),
+    // so the operand rows are permuted here instead, once per call
+    const int o = (int)(gene & 31);
+    const int k = 4 * (o & 7) + (o >> 3);
     bq[chunk * (uint64_t)(NB * 32) + (uint64_t)(n >> 3) * 256 + (k >> 4) * 128 + (n & 7) * 16 + (k & 15)] = out;
 }
 
 // ---- K1b: one pass over the CSC block (CUDA cores, HBM-bound) -----------------------------------
 // per cell: (1) pattern bitmap row -> tiled global scratch, (2) norm, (3) correction for counts != 1.
 // writes out[j*K + k] = corr_k / norm_j and scale[j] = ln2 / norm_j.
-// bitmap word w of a cell covers genes 32w..32w+31; gene offset o sits at bit (o>>2) + 8*(o&3) so that
-// the expander's (w << (7-b)) & 0x80808080 yields the four K-positions 4b..4b+3 of an MMA operand column.
+// bitmap word w of a cell covers genes 32w..32w+31, gene offset o at bit o; the expander's (w << (7-b)) & 0x80808080
+// yields the four K-positions 4b..4b+3 of an MMA operand column, which k_quantize_basis fills with genes b, b+8, b+16, b+24.
 constexpr int PREP_Q = 256;   // exception queue entries per warp (>= 31 + 128)
 constexpr int PREP_LUT = 64;  // log1p look-up for integer counts below this
 
@@ -245,7 +249,7 @@ __global__ void __launch_bounds__(PREP_WARPS * 32, 4) k_project_prep(const uint6
             qhead += cnt;
         };
         auto consume = [&](uint32_t ixu, float vu, bool live) {
-            if (live) atomicOr(row + (ixu >> 5), 1u << (((ixu >> 2) & 7) | ((ixu & 3) << 3)));
+            if (live) atomicOr(row + (ixu >> 5), 1u << (ixu & 31));
             const bool exc = vu != 1.0f;  // dead lanes carry 1
             const unsigned m = __ballot_sync(0xffffffffu, exc);
             if (m) {
@@ -263,10 +267,10 @@ __global__ void __launch_bounds__(PREP_WARPS * 32, 4) k_project_prep(const uint6
         // the last bits) on where its column starts in the arrays, i.e. on how the cells were sharded.
         auto consume4 = [&](const uint4 g, const float4 x, bool live) {
             if (live) {
-                atomicOr(row + (g.x >> 5), 1u << (((g.x >> 2) & 7) | ((g.x & 3) << 3)));
-                atomicOr(row + (g.y >> 5), 1u << (((g.y >> 2) & 7) | ((g.y & 3) << 3)));
-                atomicOr(row + (g.z >> 5), 1u << (((g.z >> 2) & 7) | ((g.z & 3) << 3)));
-                atomicOr(row + (g.w >> 5), 1u << (((g.w >> 2) & 7) | ((g.w & 3) << 3)));
+                atomicOr(row + (g.x >> 5), 1u << (g.x & 31));
+                atomicOr(row + (g.y >> 5), 1u << (g.y & 31));
+                atomicOr(row + (g.z >> 5), 1u << (g.z & 31));
+                atomicOr(row + (g.w >> 5), 1u << (g.w & 31));
             }
             const bool e0 = x.x != 1.0f, e1 = x.y != 1.0f, e2 = x.z != 1.0f, e3 = x.w != 1.0f;  // dead lanes carry 1
             const uint32_t cnt = (uint32_t)e0 + (uint32_t)e1 + (uint32_t)e2 + (uint32_t)e3;
@@ -648,6 +652,505 @@ __global__ void __launch_bounds__(THREADS, 1) k_project_umma(const uint32_t* __r
     if (warp == WARP_MMA) tmem_dealloc(tbase, 512);
 }
 
+
+// ---- K1 fused: CSC stream -> bitmap chunks in shared memory -> tcgen05, ONE kernel ---------------------------------
+// The two-kernel form above writes the pattern bitmap to a 4.4 GB scratch and reads it back (1.83x the algorithmic
+// traffic) and cannot overlap the issue-bound scan with the tensor pipeline.  Here sixteen PRODUCER warps take the place
+// of the bitmap loader: rows are ascending inside a column, so a cell's share of the 2048-gene chunk the tensor pipe needs
+// next is ONE contiguous piece of its stream, found by a per-cell cursor that simply carries over from the previous chunk
+// (no split table).  A producer warp owns 16 cells of the 256-cell supertile; per chunk and cell it fetches the next
+// 4 x 32 entries at the cursor before the piece's length is known (what lies beyond the chunk is read again, from L2,
+// one chunk later), sets the bits with shared-memory atomics and appends the counts != 1 to the cell's exception list in
+// an L2-resident scratch.  The list is consumed by the SAME warp one supertile later (one cell per chunk, in the shadow of
+// the bm_empty wait): full batches of 32 exceptions into register accumulators exactly as k_project_prep drains its
+// queue, the norm, and the final combine with the tensor sum that the epilogue left in `out` — so nobody waits for the
+// exceptions and the projection is bit-identical to the two-kernel form.
+constexpr int F_PW = 16;                               // producer warps
+constexpr int F_CPW = CELLS / F_PW;                    // cells of a supertile per producer warp
+constexpr int F_WARP_PROD = 12;                        // warps 0-7 expanders / epilogue, 8-9 MMA, 10 basis loader, 11 idle
+constexpr int F_THREADS = (F_WARP_PROD + F_PW) * 32;   // 896
+constexpr int F_CAPX = 256;                            // exception list entries per cell; a longer list: the cell is re-scanned
+
+struct FBarriers {
+    uint64_t b_full[NBST], b_empty[NBST];
+    uint64_t a_full[NT][NAST], a_empty[NT][NAST];
+    uint64_t bm_full[NBM], bm_empty[NBM];
+    uint64_t acc_full[NT], acc_empty[NT];
+    uint64_t epi_done;
+};
+
+// one batch of <= 32 exceptions (lane e holds entry e; lanes >= cnt carry gene 0, weight 0) into the HALF2 accumulators:
+// the arithmetic of k_project_prep's drain, operation for operation
+__device__ __forceinline__ void f_drain(uint32_t g, float val, bool on, uint32_t cnt, const float* __restrict__ basis_kd, int K,
+                                        const float* lut_x, float ln2, int lane, float (&acc)[4], float& nsq) {
+    float w = 0.0f;
+    if (on) {
+        const int vi = (int)val;
+        const float x = (val == (float)vi && vi >= 0 && vi < PREP_LUT) ? lut_x[vi] : log1pf(val);
+        nsq = fmaf(x, x, nsq);
+        w = x - ln2;
+    }
+    const int half = lane >> 4, l = lane & 15;
+    const bool hi_on = 2 * (l + 16) < K;
+    for (uint32_t e0 = 0; e0 < cnt; e0 += 8) {
+        float2 b0[4], b1[4];
+        float ws[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const int src = (int)e0 + 2 * e + half;
+            const uint32_t ge = __shfl_sync(0xffffffffu, g, src);
+            ws[e] = __shfl_sync(0xffffffffu, w, src);
+            const float2* brow = reinterpret_cast<const float2*>(basis_kd + (size_t)ge * K);
+            b0[e] = (2 * l < K) ? __ldg(brow + l) : make_float2(0.f, 0.f);
+            b1[e] = hi_on ? __ldg(brow + l + 16) : make_float2(0.f, 0.f);
+        }
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            acc[0] = fmaf(ws[e], b0[e].x, acc[0]);
+            acc[1] = fmaf(ws[e], b0[e].y, acc[1]);
+            acc[2] = fmaf(ws[e], b1[e].x, acc[2]);
+            acc[3] = fmaf(ws[e], b1[e].y, acc[3]);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(F_THREADS, 1)
+    k_project_fused(const uint64_t* __restrict__ indptr, const uint32_t* __restrict__ indices, const float* __restrict__ values,
+                    uint64_t ncols, uint64_t nnz, uint64_t D, const float* __restrict__ basis_kd, const int8_t* __restrict__ bq, int K,
+                    int NB, uint32_t nstages, const unsigned int* __restrict__ colmax_bits, const int* __restrict__ bad_flag,
+                    uint2* __restrict__ xl, float* out, int dbg) {
+    if (*bad_flag) return;  // a non-finite basis column: the host falls back to the CUDA-core kernel
+    extern __shared__ __align__(1024) uint8_t smem[];
+    // carve: [B ring][bitmap x NBM][barriers][tmem base]
+    const uint32_t stage_bytes = (uint32_t)NB * 32u * (GS / 32);
+    uint8_t* smem_b = smem;
+    uint32_t* bitmap = reinterpret_cast<uint32_t*>(smem + (size_t)NBST * stage_bytes);
+    FBarriers* bars = reinterpret_cast<FBarriers*>(bitmap + NBM * CELLS * BM_STRIDE);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 1);
+    __shared__ double col_inv[64];
+    __shared__ float lut_x[PREP_LUT];
+    if (threadIdx.x < 64) col_inv[threadIdx.x] = (int)threadIdx.x < K ? ldexp(1.0, -(27 + basis_col_exp(colmax_bits[threadIdx.x], nullptr))) : 0.0;
+    if (threadIdx.x >= 64 && threadIdx.x < 64 + PREP_LUT) lut_x[threadIdx.x - 64] = log1pf((float)(threadIdx.x - 64));
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t nchunks = (uint32_t)((D + GC - 1) / GC);
+    const uint64_t nsuper = (ncols + CELLS - 1) / CELLS;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < NBST; ++s) {
+            mbar_init(&bars->b_full[s], 1);
+            mbar_init(&bars->b_empty[s], NT);
+        }
+        for (int t = 0; t < NT; ++t) {
+            for (int s = 0; s < NAST; ++s) {
+                mbar_init(&bars->a_full[t][s], 4);
+                mbar_init(&bars->a_empty[t][s], 1);
+            }
+            mbar_init(&bars->acc_full[t], 1);
+            mbar_init(&bars->acc_empty[t], 4);
+        }
+        for (int b = 0; b < NBM; ++b) {
+            mbar_init(&bars->bm_full[b], F_PW);
+            mbar_init(&bars->bm_empty[b], N_EXP_WARPS);
+        }
+        mbar_init(&bars->epi_done, N_EXP_WARPS);
+        fence_barrier_init();
+    }
+    if (warp == WARP_MMA) {
+        tmem_alloc(tmem_slot, 512);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tbase = *tmem_slot;
+    const uint32_t a_col0 = (uint32_t)NT * (uint32_t)NB;
+
+    // register file: the kernel starts at 72 per thread (896 threads); the tensor-side warpgroups hand registers to the
+    // producers, whose windows in flight are what hides the HBM latency of the stream.  Each setmaxnreg sits at the top
+    // of its role's branch (ptxas takes the limit of a join to be the smaller one).
+    if (warp < N_EXP_WARPS) {
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 64;");
+        // ===== expanders / epilogue: one thread per cell row =====
+        const int t = warp >> 2;
+        const int row = (warp & 3) * 32 + lane;
+        const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
+        const uint32_t acc_addr = tbase + lane_base + (uint32_t)t * NB;
+        uint32_t a_it = 0, chunk_it = 0, super_it = 0;
+        long long tw_bm = 0, tw_epi = 0, t_all0 = clock64();
+        for (uint64_t sup = blockIdx.x; sup < nsuper; sup += gridDim.x, ++super_it) {
+            uint32_t stage = 0;
+            for (uint32_t c = 0; c < nchunks; ++c, ++chunk_it) {
+                const uint32_t buf = chunk_it % NBM;
+                const long long tq0 = clock64();
+                mbar_wait(&bars->bm_full[buf], (chunk_it / NBM) & 1);
+                tw_bm += clock64() - tq0;
+                const uint32_t* my = bitmap + (size_t)buf * CELLS * BM_STRIDE + (size_t)(t * TILE_M + row) * BM_STRIDE;
+                const uint32_t st_end = min(nstages, (c + 1) * (GC / GS));
+                for (uint32_t ls = 0; stage < st_end; ++stage, ++ls, ++a_it) {
+                    const uint32_t slot = a_it % NAST;
+                    mbar_wait(&bars->a_empty[t][slot], ((a_it / NAST) & 1) ^ 1);
+                    tc_fence_after();
+                    const uint32_t a_addr = tbase + lane_base + a_col0 + (uint32_t)(t * NAST + slot) * A_COLS;
+#pragma unroll
+                    for (int hh = 0; hh < GS / 64; ++hh) {
+                        const uint2 w = *reinterpret_cast<const uint2*>(my + (GS / 32) * ls + 2 * hh);
+                        uint32_t r[16];
+#pragma unroll
+                        for (int b = 0; b < 8; ++b) {
+                            r[b] = (w.x << (7 - b)) & 0x80808080u;
+                            r[8 + b] = (w.y << (7 - b)) & 0x80808080u;
+                        }
+                        tmem_st_x16(a_addr + 16u * hh, r);
+                    }
+                    tmem_wait_st();
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&bars->a_full[t][slot]);
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&bars->bm_empty[buf]);
+            }
+            // ---- epilogue: the tensor sum of the pattern, unscaled; the cell's producer warp combines it later ----
+            const uint64_t cell = sup * CELLS + (uint64_t)t * TILE_M + row;
+            const bool live = cell < ncols;
+            float* orow = out + (size_t)cell * K;
+            const long long te0 = clock64();
+            mbar_wait(&bars->acc_full[t], super_it & 1);
+            tc_fence_after();
+#pragma unroll
+            for (int kb = 0; kb < 64; kb += 8) {
+                if (kb < K) {
+                    uint32_t d0[8], d1[8], d2[8];
+                    tmem_ld_x8(acc_addr + kb, d0);
+                    tmem_ld_x8(acc_addr + K + kb, d1);
+                    tmem_ld_x8(acc_addr + 2 * K + kb, d2);
+                    tmem_wait_ld();
+                    if (live) {
+                        float res[8];
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            const long long tot = ((long long)(int)d2[i] << 16) + ((long long)(int)d1[i] << 8) + (long long)(int)d0[i];
+                            res[i] = (float)((double)tot * col_inv[kb + i]);
+                        }
+#pragma unroll
+                        for (int i = 0; i < 8; i += 2)
+                            if (kb + i < K) __stcg(reinterpret_cast<float2*>(orow + kb + i), make_float2(res[i], res[i + 1]));
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) {
+                mbar_arrive(&bars->acc_empty[t]);
+                mbar_arrive(&bars->epi_done);
+            }
+            tw_epi += clock64() - te0;
+        }
+        if ((dbg & 8) && blockIdx.x == 0 && threadIdx.x == 0)
+            printf("[fused exp] total %lld clk, wait bm_full %lld, epilogue(incl. acc wait) %lld\n", clock64() - t_all0, tw_bm, tw_epi);
+    } else if (warp < F_WARP_PROD) {
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 24;");
+      if (warp < WARP_MMA + NT) {
+        // ===== MMA issuers: one elected thread per cell tile =====
+        const int t = warp - WARP_MMA;
+        if (elect_one()) {
+            const uint32_t idesc = make_idesc(CFMT_S32, FMT_U8, FMT_S8, TILE_M, (uint32_t)NB);
+            uint32_t b_it = 0, a_it = 0, super_it = 0;
+            for (uint64_t sup = blockIdx.x; sup < nsuper; sup += gridDim.x, ++super_it) {
+                mbar_wait(&bars->acc_empty[t], (super_it & 1) ^ 1);
+                tc_fence_after();
+                for (uint32_t stage = 0; stage < nstages; ++stage, ++b_it, ++a_it) {
+                    const uint32_t bs = b_it % NBST, as = a_it % NAST;
+                    mbar_wait(&bars->b_full[bs], (b_it / NBST) & 1);
+                    const uint32_t b_addr = smem_u32(smem_b + (size_t)bs * stage_bytes);
+                    mbar_wait(&bars->a_full[t][as], (a_it / NAST) & 1);
+                    tc_fence_after();
+#pragma unroll
+                    for (int j = 0; j < GS / 32; ++j) {
+                        const uint64_t db = make_smem_desc(b_addr + (uint32_t)j * NB * 32u, 128, 256);
+                        mma_i8_ts(tbase + (uint32_t)t * NB, tbase + a_col0 + (uint32_t)(t * NAST + as) * A_COLS + 8u * j, db, idesc,
+                                  stage > 0 || j > 0);
+                    }
+                    tc_commit(&bars->a_empty[t][as]);
+                    tc_commit(&bars->b_empty[bs]);
+                }
+                tc_commit(&bars->acc_full[t]);
+            }
+        }
+      } else if (warp == WARP_LOAD_B) {
+        // ===== B-operand loader: one bulk copy per stage =====
+        if (elect_one()) {
+            uint32_t b_it = 0;
+            for (uint64_t sup = blockIdx.x; sup < nsuper; sup += gridDim.x) {
+                for (uint32_t stage = 0; stage < nstages; ++stage, ++b_it) {
+                    const uint32_t bs = b_it % NBST;
+                    mbar_wait(&bars->b_empty[bs], ((b_it / NBST) & 1) ^ 1);
+                    mbar_arrive_expect_tx(&bars->b_full[bs], stage_bytes);
+                    bulk_g2s(smem_b + (size_t)bs * stage_bytes, bq + (size_t)stage * stage_bytes, stage_bytes, &bars->b_full[bs]);
+                }
+            }
+        }
+      }
+    } else {
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 88;");
+        // ===== producers: CSC stream -> bitmap chunk, exception lists; finalisation of the previous supertile =====
+        const int pw = warp - F_WARP_PROD;
+        const int row0 = pw * F_CPW;
+        const unsigned lt_mask = (1u << lane) - 1u;
+        const float ln2 = lut_x[1];
+        // lanes 0..15 hold the state of the warp's 16 cells (lanes 16..31 mirror them, unused)
+        uint32_t cur = 0, end = 0, nexc = 0;      // cursor / end of the stream (relative to `base`), exceptions so far
+        uint64_t base = 0;                        // first entry of the supertile (warp-uniform)
+        uint32_t p_lo = 0, p_n = 0, p_nexc = 0;   // the previous supertile's cells: start, length, exceptions
+        uint64_t p_base = 0, p_sup = 0;
+        bool have_prev = false;
+        uint32_t chunk_it = 0, it = 0;
+        const uint32_t c0 = nchunks > 2 ? 2u : nchunks - 1;  // first chunk with a finalisation slot: epilogue(it - 1) is over by then
+
+        // the cell `i` of the previous supertile: exceptions -> correction and norm, combine with the tensor sum in `out`
+        auto finalize = [&](int i) {
+            const uint64_t cell = p_sup * CELLS + (uint64_t)(row0 + i);
+            if (cell >= ncols) return;
+            const uint32_t cnt = __shfl_sync(0xffffffffu, p_nexc, i), n = __shfl_sync(0xffffffffu, p_n, i);
+            float acc[4] = {0.f, 0.f, 0.f, 0.f};
+            float nsq = 0.0f;
+            if (cnt <= (uint32_t)F_CAPX) {
+                const uint2* xlist = xl + ((size_t)(blockIdx.x * 2 + ((it + 1) & 1)) * CELLS + (size_t)(row0 + i)) * F_CAPX;
+                for (uint32_t q0 = 0; q0 < cnt; q0 += 32) {
+                    const uint32_t c = min(32u, cnt - q0);
+                    const bool on = (uint32_t)lane < c;
+                    uint2 e = make_uint2(0u, 0u);
+                    if (on) e = __ldcg(xlist + q0 + lane);
+                    f_drain(e.x, __uint_as_float(e.y), on, c, basis_kd, K, lut_x, ln2, lane, acc, nsq);
+                }
+            } else {
+                // too many exceptions for the list (non-count data): stream the cell again and batch them 32 at a time
+                const uint64_t lo = p_base + __shfl_sync(0xffffffffu, p_lo, i);
+                uint32_t pg = 0, pc = 0;
+                float pv = 1.0f;
+                for (uint32_t t0 = 0; t0 < n; t0 += 32) {
+                    const bool live = t0 + lane < n;
+                    const uint32_t gi = live ? __ldg(indices + lo + t0 + lane) : 0u;
+                    const float vv = live ? __ldg(values + lo + t0 + lane) : 1.0f;
+                    unsigned m = __ballot_sync(0xffffffffu, vv != 1.0f);
+                    while (m) {
+                        const int want = lane - (int)pc;  // this lane takes the want-th pending set bit of m
+                        const unsigned src = want >= 0 ? __fns(m, 0, want + 1) : 0xffffffffu;
+                        const uint32_t g_in = __shfl_sync(0xffffffffu, gi, src & 31u);
+                        const float v_in = __shfl_sync(0xffffffffu, vv, src & 31u);
+                        if (src != 0xffffffffu) {
+                            pg = g_in;
+                            pv = v_in;
+                        }
+                        const uint32_t ntake = min((uint32_t)__popc(m), 32u - pc);
+                        const unsigned last = __fns(m, 0, (int)ntake);  // position of the last bit taken
+                        m &= ~((2u << last) - 1u);
+                        pc += ntake;
+                        if (pc == 32) {
+                            f_drain(pg, pv, true, 32, basis_kd, K, lut_x, ln2, lane, acc, nsq);
+                            pc = 0;
+                        }
+                    }
+                }
+                if (pc) {
+                    const bool on = (uint32_t)lane < pc;
+                    f_drain(on ? pg : 0u, pv, on, pc, basis_kd, K, lut_x, ln2, lane, acc, nsq);
+                }
+            }
+#pragma unroll
+            for (int off = 16; off >= 1; off >>= 1) nsq += __shfl_xor_sync(0xffffffffu, nsq, off);
+            nsq = fmaf((float)(n - cnt), ln2 * ln2, nsq);
+            const float denom = fmaxf(sqrtf(nsq), 1e-8f);
+            const float pat_scale = ln2 / denom;
+#pragma unroll
+            for (int a = 0; a < 4; ++a) acc[a] += __shfl_xor_sync(0xffffffffu, acc[a], 16);
+            if (lane < 16) {
+                float* o = out + (size_t)cell * K;
+                if (2 * lane < K) {
+                    const float2 sv = __ldcg(reinterpret_cast<const float2*>(o + 2 * lane));
+                    __stcs(reinterpret_cast<float2*>(o + 2 * lane), make_float2(fmaf(sv.x, pat_scale, acc[0] / denom), fmaf(sv.y, pat_scale, acc[1] / denom)));
+                }
+                if (2 * (lane + 16) < K) {
+                    const float2 sv = __ldcg(reinterpret_cast<const float2*>(o + 2 * lane + 32));
+                    __stcs(reinterpret_cast<float2*>(o + 2 * lane + 32), make_float2(fmaf(sv.x, pat_scale, acc[2] / denom), fmaf(sv.y, pat_scale, acc[3] / denom)));
+                }
+            }
+        };
+
+        long long tp_fin = 0, tp_wait = 0, tp_scan = 0, tp_all0 = clock64();
+        for (uint64_t sup = blockIdx.x; sup < nsuper; sup += gridDim.x, ++it) {
+            {
+                const uint64_t first = sup * CELLS;
+                base = indptr[first];
+                const uint64_t cell = first + (uint64_t)(row0 + (lane & 15));
+                uint64_t lo = base, hi = base;
+                if (cell < ncols) {
+                    lo = indptr[cell];
+                    hi = indptr[cell + 1];
+                }
+                cur = (uint32_t)(lo - base);
+                end = (uint32_t)(hi - base);
+                nexc = 0;
+            }
+            const uint32_t my_lo = cur;
+            uint2* xl_cur = xl + ((size_t)(blockIdx.x * 2 + (it & 1)) * CELLS + (size_t)row0) * F_CAPX;
+            uint32_t fin_done = 0;
+            bool waited = false;
+            for (uint32_t c = 0; c < nchunks; ++c, ++chunk_it) {
+                // ---- finalisation slot (previous supertile), ahead of the wait for a free bitmap buffer ----
+                const long long tf0 = clock64();
+                if (have_prev && c >= c0) {
+                    const uint32_t target = (c + 1 == nchunks) ? (uint32_t)F_CPW : ((c - c0 + 1) * (uint32_t)F_CPW) / (nchunks - c0);
+                    if (fin_done < target) {
+                        if (!waited) {
+                            mbar_wait(&bars->epi_done, (it - 1) & 1);
+                            waited = true;
+                        }
+                        for (; fin_done < target; ++fin_done)
+                            if (!(dbg & 1)) finalize((int)fin_done);
+                    }
+                }
+                const uint32_t buf = chunk_it % NBM;
+                const long long tf1 = clock64();
+                mbar_wait(&bars->bm_empty[buf], ((chunk_it / NBM) & 1) ^ 1);
+                const long long tf2 = clock64();
+                tp_fin += tf1 - tf0;
+                tp_wait += tf2 - tf1;
+                uint32_t* rows = bitmap + (size_t)buf * CELLS * BM_STRIDE + (size_t)row0 * BM_STRIDE;
+                for (int q = lane; q < F_CPW * BM_STRIDE / 4; q += 32) reinterpret_cast<uint4*>(rows)[q] = make_uint4(0, 0, 0, 0);
+                __syncwarp();
+                const uint32_t g1 = (c + 1 == nchunks) ? 0xffffffffu : (c + 1) * (uint32_t)GC;
+                // A piece is fetched as ONE window of 32 x 128-bit groups (128 entries) from the 16-byte boundary at or below
+                // the cursor, before its length is known; entries outside [cursor, end of the cell) or at genes beyond the
+                // chunk are masked, the part of the window beyond the chunk is read again (from L2) one chunk later.
+                struct Win {
+                    uint4 ix;
+                    float4 v;
+                    int a0;  // window start relative to `base` (may be -3 .. -1 for the first cell)
+                };
+                auto fetch = [&](int a0, uint32_t en, Win& w) {
+                    w.a0 = a0;
+                    w.ix = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu);
+                    w.v = make_float4(1.f, 1.f, 1.f, 1.f);
+                    const int p0 = a0 + 4 * lane;
+                    if (p0 < (int)en) {
+                        const uint64_t e0 = base + (int64_t)p0;  // absolute entry index, a multiple of 4
+                        if (e0 + 4 <= nnz) {
+                            w.ix = __ldg(reinterpret_cast<const uint4*>(indices + e0));
+                            w.v = __ldg(reinterpret_cast<const float4*>(values + e0));
+                        } else {  // the last, partial group of the arrays
+                            uint32_t gi[4] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu};
+                            float gv[4] = {1.f, 1.f, 1.f, 1.f};
+                            for (int j = 0; j < 4; ++j)
+                                if (e0 + j < nnz) {
+                                    gi[j] = __ldg(indices + e0 + j);
+                                    gv[j] = __ldg(values + e0 + j);
+                                }
+                            w.ix = make_uint4(gi[0], gi[1], gi[2], gi[3]);
+                            w.v = make_float4(gv[0], gv[1], gv[2], gv[3]);
+                        }
+                    }
+                };
+                auto issue = [&](int i, Win& w) {
+                    const uint32_t cu = __shfl_sync(0xffffffffu, cur, i), en = __shfl_sync(0xffffffffu, end, i);
+                    const int mis = (int)((base + cu) & 3ull);
+                    fetch((int)cu - mis, en, w);
+                };
+                auto consume = [&](int i, Win w) {
+                    uint32_t* browc = rows + (size_t)i * BM_STRIDE - (size_t)c * (GC / 32);
+                    uint2* xlist = xl_cur + (size_t)i * F_CAPX;
+                    const uint32_t cu = __shfl_sync(0xffffffffu, cur, i), en = __shfl_sync(0xffffffffu, end, i);
+                    uint32_t xc = __shfl_sync(0xffffffffu, nexc, i);
+                    uint32_t taken = 0;
+                    for (;;) {
+                        const int p0 = w.a0 + 4 * lane;
+                        const uint32_t gx[4] = {w.ix.x, w.ix.y, w.ix.z, w.ix.w};
+                        const float vx[4] = {w.v.x, w.v.y, w.v.z, w.v.w};
+                        bool in[4], ex[4];
+                        uint32_t cnt = 0, xcnt = 0;
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            in[j] = p0 + j >= (int)cu && p0 + j < (int)en && gx[j] < g1;
+                            if (in[j] && !(dbg & 4)) atomicOr(browc + (gx[j] >> 5), 1u << (gx[j] & 31));
+                            ex[j] = in[j] && vx[j] != 1.0f && !(dbg & 2);
+                            cnt += in[j];
+                            xcnt += ex[j];
+                        }
+                        // exceptions join the list in ascending position: lanes in order, entries in order inside a lane
+                        const unsigned b0 = __ballot_sync(0xffffffffu, xcnt & 1u), b1 = __ballot_sync(0xffffffffu, xcnt & 2u),
+                                       b2 = __ballot_sync(0xffffffffu, xcnt & 4u);
+                        if (b0 | b1 | b2) {
+                            uint32_t slot = xc + __popc(b0 & lt_mask) + 2 * __popc(b1 & lt_mask) + 4 * __popc(b2 & lt_mask);
+#pragma unroll
+                            for (int j = 0; j < 4; ++j)
+                                if (ex[j]) {
+                                    if (slot < (uint32_t)F_CAPX) __stcg(xlist + slot, make_uint2(gx[j], __float_as_uint(vx[j])));
+                                    ++slot;
+                                }
+                            xc += __popc(b0) + 2 * __popc(b1) + 4 * __popc(b2);
+                        }
+                        taken += __reduce_add_sync(0xffffffffu, cnt);
+                        // the piece goes on beyond this window iff its last entry is still inside the chunk
+                        const bool more = (__ballot_sync(0xffffffffu, in[3]) >> 31) != 0;
+                        if (!more) break;
+                        fetch(w.a0 + 128, en, w);
+                    }
+                    if ((lane & 15) == i) {
+                        cur += taken;
+                        nexc = xc;
+                    }
+                };
+
+                Win wA, wB, wC, wD;
+                issue(0, wA);
+                issue(1, wB);
+                issue(2, wC);
+#pragma unroll 1
+                for (int i = 0; i < F_CPW; i += 4) {
+                    issue(i + 3, wD);
+                    consume(i, wA);
+                    if (i + 4 < F_CPW) issue(i + 4, wA);
+                    consume(i + 1, wB);
+                    if (i + 5 < F_CPW) issue(i + 5, wB);
+                    consume(i + 2, wC);
+                    if (i + 6 < F_CPW) issue(i + 6, wC);
+                    consume(i + 3, wD);
+                }
+                // pull the lines that the chunk after the next one will start in into L2 (what the next chunk's windows
+                // fetch lies behind this chunk's windows already): lanes 0-15 the index lines, 16-31 the value lines
+                if (c + 2 < nchunks) {
+                    const char* pf = (lane < 16 ? reinterpret_cast<const char*>(indices) : reinterpret_cast<const char*>(values)) +
+                                     (base + cur + 128) * 4;
+                    if (cur + 128 < end) {
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) asm volatile("prefetch.global.L2 [%0];" ::"l"(pf + 128 * k));
+                    }
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&bars->bm_full[buf]);
+                tp_scan += clock64() - tf2;
+            }
+            p_lo = my_lo;
+            p_n = end - my_lo;
+            p_nexc = nexc;
+            p_base = base;
+            p_sup = sup;
+            have_prev = true;
+        }
+        if ((dbg & 8) && blockIdx.x == 0 && lane == 0 && (pw == 0 || pw == 15))
+            printf("[fused prod %d] total %lld clk, finalize %lld, wait bm_empty %lld, scan %lld\n", pw, clock64() - tp_all0, tp_fin, tp_wait, tp_scan);
+        if (have_prev) {  // the last supertile of this CTA
+            mbar_wait(&bars->epi_done, (it - 1) & 1);
+            for (int i = 0; i < F_CPW; ++i)
+                if (!(dbg & 1)) finalize(i);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == WARP_MMA) tmem_dealloc(tbase, 512);
+}
+
 }  // namespace
 
 // returns LG_OK and sets *used = 1 when the tensor path ran, *used = 0 when the caller must fall back
@@ -688,6 +1191,39 @@ int lg_project_raw_umma(lg_ctx* ctx, const lg_csc* m, const float* d_basis, int 
     cudaEvent_t ev[3];
     if (trace)
         for (int i = 0; i < 3; ++i) cudaEventCreate(&ev[i]);
+    // the fused kernel (projection mode, even K, 8-byte aligned basis and output); LG_K1_FUSED=0 keeps the two-kernel form
+    {
+        const char* fz = getenv("LG_K1_FUSED");
+        const bool fused = mode == 0 && !(fz && fz[0] == '0') && K % 2 == 0 && (((uintptr_t)d_basis | (uintptr_t)d_out) & 7) == 0 &&
+                           (((uintptr_t)m->indices | (uintptr_t)m->values) & 15) == 0;
+        if (fused) {
+            const size_t stage_bytes = (size_t)NB * 32 * (GS / 32);
+            const size_t smem = (size_t)NBST * stage_bytes + (size_t)NBM * BM_CHUNK_BYTES + sizeof(FBarriers) + 16;
+            if (smem + 1024 > ctx->smem_optin) return lg_fail(ctx, LG_ERR_INTERNAL, "k_project_fused: shared memory budget exceeded");
+            const uint64_t nsuper = (m->ncols + CELLS - 1) / CELLS;
+            const unsigned grid = (unsigned)(nsuper < (uint64_t)ctx->num_sms ? nsuper : (uint64_t)ctx->num_sms);
+            uint2* d_xl;
+            LG_TRY(st.scratch((size_t)grid * 2 * CELLS * F_CAPX, &d_xl));
+            LG_CUDA(ctx, cudaFuncSetAttribute(k_project_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            if (trace) cudaEventRecord(ev[0], ctx->stream);
+            LG_LAUNCH(ctx, k_project_fused, grid, F_THREADS, smem, m->indptr, m->indices, m->values, m->ncols, m->nnz, D, d_basis, d_bq, K,
+                      NB, nstages, d_colmax, d_flag, d_xl, d_out, getenv("LG_K1_DBG") ? atoi(getenv("LG_K1_DBG")) : 0);
+            if (trace) cudaEventRecord(ev[1], ctx->stream);
+            const cudaError_t fe = cudaEventSynchronize(flag_ev);  // the quantiser's verdict: long home by now
+            cudaEventDestroy(flag_ev);
+            if (trace) {
+                cudaEventSynchronize(ev[1]);
+                float a = 0.f;
+                cudaEventElapsedTime(&a, ev[0], ev[1]);
+                fprintf(stderr, "[lg_project] fused %.3f ms\n", a);
+                for (int i = 0; i < 3; ++i) cudaEventDestroy(ev[i]);
+            }
+            LG_CUDA(ctx, fe);
+            if (*h_flag) return LG_OK;  // the kernel returned at once; the caller falls back (and propagates the non-finite column)
+            *used = 1;
+            return LG_OK;
+        }
+    }
     // K1b first: bitmap + corr/norm in `out` + ln2/norm in `scale`; K1a then adds the tensor part
     const uint32_t nchunks = (uint32_t)((D + GC - 1) / GC);
     const uint64_t nsuper = (m->ncols + CELLS - 1) / CELLS;
