@@ -653,30 +653,34 @@ __global__ void __launch_bounds__(THREADS, 1) k_project_umma(const uint32_t* __r
 }
 
 
-// ---- K1 fused: CSC stream -> bitmap chunks in shared memory -> tcgen05, ONE kernel ---------------------------------
+// ---- K1 fused (LG_K1_FUSED=1, NOT the default): CSC stream -> bitmap chunks in shared memory -> tcgen05 -----------------
 // The two-kernel form above writes the pattern bitmap to a 4.4 GB scratch and reads it back (1.83x the algorithmic
-// traffic) and cannot overlap the issue-bound scan with the tensor pipeline.  Here sixteen PRODUCER warps take the place
-// of the bitmap loader: rows are ascending inside a column, so a cell's share of the 2048-gene chunk the tensor pipe needs
-// next is ONE contiguous piece of its stream, found by a per-cell cursor that simply carries over from the previous chunk
-// (no split table).  A producer warp owns 16 cells of the 256-cell supertile; per chunk and cell it fetches the next
-// 4 x 32 entries at the cursor before the piece's length is known (what lies beyond the chunk is read again, from L2,
-// one chunk later), sets the bits with shared-memory atomics and appends the counts != 1 to the cell's exception list in
-// an L2-resident scratch.  The list is consumed by the SAME warp one supertile later (one cell per chunk, in the shadow of
-// the bm_empty wait): full batches of 32 exceptions into register accumulators exactly as k_project_prep drains its
-// queue, the norm, and the final combine with the tensor sum that the epilogue left in `out` — so nobody waits for the
-// exceptions and the projection is bit-identical to the two-kernel form.
+// traffic).  Here sixteen PRODUCER warps take the place of the bitmap loader: rows are ascending inside a column, so a
+// cell's share of the 2048-gene chunk the tensor pipe needs next is ONE contiguous piece of its stream, found by a per-cell
+// cursor that simply carries over from the previous chunk (no split table).  A producer warp owns 16 cells of the 256-cell
+// supertile; per chunk and cell it fetches one 128-entry window at the cursor before the piece's length is known (four
+// windows in flight per warp; what lies beyond the chunk is read again, from L2, one chunk later), sets the bits with
+// shared-memory reductions and appends the counts != 1 to the cell's exception list.  k_project_finalize then turns
+// the lists into the correction and the norm (the arithmetic of k_project_prep's drain, batch for batch) and combines them
+// with the tensor sum the epilogue left in `out`: the result is BIT-IDENTICAL to the two-kernel form, which is what
+// tests/test_gpu_parity.py::test_project_fused_form_is_bit_identical holds it to — an independent second scan of the
+// same stream.
+// Measured (262 144 cells x 30 000 genes, 369 M nnz): 2.65 + 0.47 ms against 1.09 + 0.69 ms.  The
+// fused kernel issues 7 700 warp instructions per cell at IPC 2.9 — it is ISSUE-bound, the tensor pipe 12 % active, the
+// expanders 75 % of their time waiting for bitmap chunks: the scan is instruction work (3 900 per cell here, 3 300 in
+// k_project_prep) that the same four schedulers must issue either way, and inside this kernel only 16 of the SM's warps
+// (the others feed the tensor pipe) share it.  Kept as the cross-check and as the record of the experiment.
 constexpr int F_PW = 16;                               // producer warps
 constexpr int F_CPW = CELLS / F_PW;                    // cells of a supertile per producer warp
 constexpr int F_WARP_PROD = 12;                        // warps 0-7 expanders / epilogue, 8-9 MMA, 10 basis loader, 11 idle
 constexpr int F_THREADS = (F_WARP_PROD + F_PW) * 32;   // 896
-constexpr int F_CAPX = 256;                            // exception list entries per cell; a longer list: the cell is re-scanned
+constexpr int F_CAPX = 128;                            // exception list entries per cell; a longer list: the cell is re-scanned
 
 struct FBarriers {
     uint64_t b_full[NBST], b_empty[NBST];
     uint64_t a_full[NT][NAST], a_empty[NT][NAST];
     uint64_t bm_full[NBM], bm_empty[NBM];
     uint64_t acc_full[NT], acc_empty[NT];
-    uint64_t epi_done;
 };
 
 // one batch of <= 32 exceptions (lane e holds entry e; lanes >= cnt carry gene 0, weight 0) into the HALF2 accumulators:
@@ -714,11 +718,98 @@ __device__ __forceinline__ void f_drain(uint32_t g, float val, bool on, uint32_t
     }
 }
 
+// second half of the fused form: per cell (one warp), the exception list -> correction and norm in full batches of 32,
+// exactly as k_project_prep drains its queue, then the combine with the tensor sum the fused kernel's epilogue left in
+// `out`.  A kernel of its own because the gathers need an occupancy that the 16 producer warps of the fused kernel cannot
+// give (~110 basis rows in flight per SM at L2 latency).
+__global__ void __launch_bounds__(256) k_project_finalize(const uint64_t* __restrict__ indptr, const uint32_t* __restrict__ indices,
+                                                          const float* __restrict__ values, uint64_t ncols,
+                                                          const float* __restrict__ basis_kd, int K, const uint2* __restrict__ xl,
+                                                          const uint32_t* __restrict__ xn, const int* __restrict__ bad_flag,
+                                                          float* out) {
+    if (*bad_flag) return;
+    __shared__ float lut_x[PREP_LUT];
+    if (threadIdx.x < PREP_LUT) lut_x[threadIdx.x] = log1pf((float)threadIdx.x);
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const float ln2 = lut_x[1];
+    const uint64_t nwarps = (uint64_t)gridDim.x * 8;
+    for (uint64_t cell = (uint64_t)blockIdx.x * 8 + (threadIdx.x >> 5); cell < ncols; cell += nwarps) {
+        const uint32_t cnt = xn[cell];
+        const uint64_t lo = indptr[cell];
+        const uint32_t n = (uint32_t)(indptr[cell + 1] - lo);
+        float acc[4] = {0.f, 0.f, 0.f, 0.f};
+        float nsq = 0.0f;
+        if (cnt <= (uint32_t)F_CAPX) {
+            const uint2* xlist = xl + cell * F_CAPX;
+            uint2 e = make_uint2(0u, 0u);
+            if ((uint32_t)lane < cnt) e = __ldcs(xlist + lane);
+            for (uint32_t q0 = 0; q0 < cnt; q0 += 32) {
+                const uint32_t c = min(32u, cnt - q0);
+                uint2 ne = make_uint2(0u, 0u);
+                if (q0 + 32 + lane < cnt) ne = __ldcs(xlist + q0 + 32 + lane);  // the next batch travels while this one is folded
+                f_drain(e.x, __uint_as_float(e.y), (uint32_t)lane < c, c, basis_kd, K, lut_x, ln2, lane, acc, nsq);
+                e = ne;
+            }
+        } else {
+            // too many exceptions for the list (non-count data): stream the cell again and batch them 32 at a time
+            uint32_t pg = 0, pc = 0;
+            float pv = 1.0f;
+            for (uint32_t t0 = 0; t0 < n; t0 += 32) {
+                const bool live = t0 + lane < n;
+                const uint32_t gi = live ? __ldg(indices + lo + t0 + lane) : 0u;
+                const float vv = live ? __ldg(values + lo + t0 + lane) : 1.0f;
+                unsigned m = __ballot_sync(0xffffffffu, vv != 1.0f);
+                while (m) {
+                    const int want = lane - (int)pc;  // this lane takes the want-th pending set bit of m
+                    const unsigned src = want >= 0 ? __fns(m, 0, want + 1) : 0xffffffffu;
+                    const uint32_t g_in = __shfl_sync(0xffffffffu, gi, src & 31u);
+                    const float v_in = __shfl_sync(0xffffffffu, vv, src & 31u);
+                    if (src != 0xffffffffu) {
+                        pg = g_in;
+                        pv = v_in;
+                    }
+                    const uint32_t ntake = min((uint32_t)__popc(m), 32u - pc);
+                    const unsigned last = __fns(m, 0, (int)ntake);  // position of the last bit taken
+                    m &= ~((2u << last) - 1u);
+                    pc += ntake;
+                    if (pc == 32) {
+                        f_drain(pg, pv, true, 32, basis_kd, K, lut_x, ln2, lane, acc, nsq);
+                        pc = 0;
+                    }
+                }
+            }
+            if (pc) {
+                const bool on = (uint32_t)lane < pc;
+                f_drain(on ? pg : 0u, pv, on, pc, basis_kd, K, lut_x, ln2, lane, acc, nsq);
+            }
+        }
+#pragma unroll
+        for (int off = 16; off >= 1; off >>= 1) nsq += __shfl_xor_sync(0xffffffffu, nsq, off);
+        nsq = fmaf((float)(n - cnt), ln2 * ln2, nsq);
+        const float denom = fmaxf(sqrtf(nsq), 1e-8f);
+        const float pat_scale = ln2 / denom;
+#pragma unroll
+        for (int a = 0; a < 4; ++a) acc[a] += __shfl_xor_sync(0xffffffffu, acc[a], 16);
+        if (lane < 16) {
+            float* o = out + (size_t)cell * K;
+            if (2 * lane < K) {
+                const float2 sv = __ldcs(reinterpret_cast<const float2*>(o + 2 * lane));
+                __stcs(reinterpret_cast<float2*>(o + 2 * lane), make_float2(fmaf(sv.x, pat_scale, acc[0] / denom), fmaf(sv.y, pat_scale, acc[1] / denom)));
+            }
+            if (2 * (lane + 16) < K) {
+                const float2 sv = __ldcs(reinterpret_cast<const float2*>(o + 2 * lane + 32));
+                __stcs(reinterpret_cast<float2*>(o + 2 * lane + 32), make_float2(fmaf(sv.x, pat_scale, acc[2] / denom), fmaf(sv.y, pat_scale, acc[3] / denom)));
+            }
+        }
+    }
+}
+
 __global__ void __launch_bounds__(F_THREADS, 1)
     k_project_fused(const uint64_t* __restrict__ indptr, const uint32_t* __restrict__ indices, const float* __restrict__ values,
                     uint64_t ncols, uint64_t nnz, uint64_t D, const float* __restrict__ basis_kd, const int8_t* __restrict__ bq, int K,
                     int NB, uint32_t nstages, const unsigned int* __restrict__ colmax_bits, const int* __restrict__ bad_flag,
-                    uint2* __restrict__ xl, float* out, int dbg) {
+                    uint2* __restrict__ xl, uint32_t* __restrict__ xn, float* out) {
     if (*bad_flag) return;  // a non-finite basis column: the host falls back to the CUDA-core kernel
     extern __shared__ __align__(1024) uint8_t smem[];
     // carve: [B ring][bitmap x NBM][barriers][tmem base]
@@ -753,7 +844,6 @@ __global__ void __launch_bounds__(F_THREADS, 1)
             mbar_init(&bars->bm_full[b], F_PW);
             mbar_init(&bars->bm_empty[b], N_EXP_WARPS);
         }
-        mbar_init(&bars->epi_done, N_EXP_WARPS);
         fence_barrier_init();
     }
     if (warp == WARP_MMA) {
@@ -777,14 +867,11 @@ __global__ void __launch_bounds__(F_THREADS, 1)
         const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
         const uint32_t acc_addr = tbase + lane_base + (uint32_t)t * NB;
         uint32_t a_it = 0, chunk_it = 0, super_it = 0;
-        long long tw_bm = 0, tw_epi = 0, t_all0 = clock64();
         for (uint64_t sup = blockIdx.x; sup < nsuper; sup += gridDim.x, ++super_it) {
             uint32_t stage = 0;
             for (uint32_t c = 0; c < nchunks; ++c, ++chunk_it) {
                 const uint32_t buf = chunk_it % NBM;
-                const long long tq0 = clock64();
-                mbar_wait(&bars->bm_full[buf], (chunk_it / NBM) & 1);
-                tw_bm += clock64() - tq0;
+                mbar_wait_sleep(&bars->bm_full[buf], (chunk_it / NBM) & 1);
                 const uint32_t* my = bitmap + (size_t)buf * CELLS * BM_STRIDE + (size_t)(t * TILE_M + row) * BM_STRIDE;
                 const uint32_t st_end = min(nstages, (c + 1) * (GC / GS));
                 for (uint32_t ls = 0; stage < st_end; ++stage, ++ls, ++a_it) {
@@ -815,7 +902,6 @@ __global__ void __launch_bounds__(F_THREADS, 1)
             const uint64_t cell = sup * CELLS + (uint64_t)t * TILE_M + row;
             const bool live = cell < ncols;
             float* orow = out + (size_t)cell * K;
-            const long long te0 = clock64();
             mbar_wait(&bars->acc_full[t], super_it & 1);
             tc_fence_after();
 #pragma unroll
@@ -841,14 +927,8 @@ __global__ void __launch_bounds__(F_THREADS, 1)
             }
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) {
-                mbar_arrive(&bars->acc_empty[t]);
-                mbar_arrive(&bars->epi_done);
-            }
-            tw_epi += clock64() - te0;
+            if (lane == 0) mbar_arrive(&bars->acc_empty[t]);
         }
-        if ((dbg & 8) && blockIdx.x == 0 && threadIdx.x == 0)
-            printf("[fused exp] total %lld clk, wait bm_full %lld, epilogue(incl. acc wait) %lld\n", clock64() - t_all0, tw_bm, tw_epi);
     } else if (warp < F_WARP_PROD) {
         asm volatile("setmaxnreg.dec.sync.aligned.u32 24;");
       if (warp < WARP_MMA + NT) {
@@ -864,7 +944,7 @@ __global__ void __launch_bounds__(F_THREADS, 1)
                     const uint32_t bs = b_it % NBST, as = a_it % NAST;
                     mbar_wait(&bars->b_full[bs], (b_it / NBST) & 1);
                     const uint32_t b_addr = smem_u32(smem_b + (size_t)bs * stage_bytes);
-                    mbar_wait(&bars->a_full[t][as], (a_it / NAST) & 1);
+                    mbar_wait_sleep(&bars->a_full[t][as], (a_it / NAST) & 1);
                     tc_fence_after();
 #pragma unroll
                     for (int j = 0; j < GS / 32; ++j) {
@@ -885,7 +965,7 @@ __global__ void __launch_bounds__(F_THREADS, 1)
             for (uint64_t sup = blockIdx.x; sup < nsuper; sup += gridDim.x) {
                 for (uint32_t stage = 0; stage < nstages; ++stage, ++b_it) {
                     const uint32_t bs = b_it % NBST;
-                    mbar_wait(&bars->b_empty[bs], ((b_it / NBST) & 1) ^ 1);
+                    mbar_wait_sleep(&bars->b_empty[bs], ((b_it / NBST) & 1) ^ 1);
                     mbar_arrive_expect_tx(&bars->b_full[bs], stage_bytes);
                     bulk_g2s(smem_b + (size_t)bs * stage_bytes, bq + (size_t)stage * stage_bytes, stage_bytes, &bars->b_full[bs]);
                 }
@@ -894,140 +974,52 @@ __global__ void __launch_bounds__(F_THREADS, 1)
       }
     } else {
         asm volatile("setmaxnreg.inc.sync.aligned.u32 88;");
-        // ===== producers: CSC stream -> bitmap chunk, exception lists; finalisation of the previous supertile =====
+        // ===== producers: CSC stream -> bitmap chunk + per-cell exception lists =====
         const int pw = warp - F_WARP_PROD;
         const int row0 = pw * F_CPW;
         const unsigned lt_mask = (1u << lane) - 1u;
-        const float ln2 = lut_x[1];
-        // lanes 0..15 hold the state of the warp's 16 cells (lanes 16..31 mirror them, unused)
-        uint32_t cur = 0, end = 0, nexc = 0;      // cursor / end of the stream (relative to `base`), exceptions so far
-        uint64_t base = 0;                        // first entry of the supertile (warp-uniform)
-        uint32_t p_lo = 0, p_n = 0, p_nexc = 0;   // the previous supertile's cells: start, length, exceptions
-        uint64_t p_base = 0, p_sup = 0;
-        bool have_prev = false;
-        uint32_t chunk_it = 0, it = 0;
-        const uint32_t c0 = nchunks > 2 ? 2u : nchunks - 1;  // first chunk with a finalisation slot: epilogue(it - 1) is over by then
-
-        // the cell `i` of the previous supertile: exceptions -> correction and norm, combine with the tensor sum in `out`
-        auto finalize = [&](int i) {
-            const uint64_t cell = p_sup * CELLS + (uint64_t)(row0 + i);
-            if (cell >= ncols) return;
-            const uint32_t cnt = __shfl_sync(0xffffffffu, p_nexc, i), n = __shfl_sync(0xffffffffu, p_n, i);
-            float acc[4] = {0.f, 0.f, 0.f, 0.f};
-            float nsq = 0.0f;
-            if (cnt <= (uint32_t)F_CAPX) {
-                const uint2* xlist = xl + ((size_t)(blockIdx.x * 2 + ((it + 1) & 1)) * CELLS + (size_t)(row0 + i)) * F_CAPX;
-                for (uint32_t q0 = 0; q0 < cnt; q0 += 32) {
-                    const uint32_t c = min(32u, cnt - q0);
-                    const bool on = (uint32_t)lane < c;
-                    uint2 e = make_uint2(0u, 0u);
-                    if (on) e = __ldcg(xlist + q0 + lane);
-                    f_drain(e.x, __uint_as_float(e.y), on, c, basis_kd, K, lut_x, ln2, lane, acc, nsq);
-                }
-            } else {
-                // too many exceptions for the list (non-count data): stream the cell again and batch them 32 at a time
-                const uint64_t lo = p_base + __shfl_sync(0xffffffffu, p_lo, i);
-                uint32_t pg = 0, pc = 0;
-                float pv = 1.0f;
-                for (uint32_t t0 = 0; t0 < n; t0 += 32) {
-                    const bool live = t0 + lane < n;
-                    const uint32_t gi = live ? __ldg(indices + lo + t0 + lane) : 0u;
-                    const float vv = live ? __ldg(values + lo + t0 + lane) : 1.0f;
-                    unsigned m = __ballot_sync(0xffffffffu, vv != 1.0f);
-                    while (m) {
-                        const int want = lane - (int)pc;  // this lane takes the want-th pending set bit of m
-                        const unsigned src = want >= 0 ? __fns(m, 0, want + 1) : 0xffffffffu;
-                        const uint32_t g_in = __shfl_sync(0xffffffffu, gi, src & 31u);
-                        const float v_in = __shfl_sync(0xffffffffu, vv, src & 31u);
-                        if (src != 0xffffffffu) {
-                            pg = g_in;
-                            pv = v_in;
-                        }
-                        const uint32_t ntake = min((uint32_t)__popc(m), 32u - pc);
-                        const unsigned last = __fns(m, 0, (int)ntake);  // position of the last bit taken
-                        m &= ~((2u << last) - 1u);
-                        pc += ntake;
-                        if (pc == 32) {
-                            f_drain(pg, pv, true, 32, basis_kd, K, lut_x, ln2, lane, acc, nsq);
-                            pc = 0;
-                        }
-                    }
-                }
-                if (pc) {
-                    const bool on = (uint32_t)lane < pc;
-                    f_drain(on ? pg : 0u, pv, on, pc, basis_kd, K, lut_x, ln2, lane, acc, nsq);
-                }
-            }
-#pragma unroll
-            for (int off = 16; off >= 1; off >>= 1) nsq += __shfl_xor_sync(0xffffffffu, nsq, off);
-            nsq = fmaf((float)(n - cnt), ln2 * ln2, nsq);
-            const float denom = fmaxf(sqrtf(nsq), 1e-8f);
-            const float pat_scale = ln2 / denom;
-#pragma unroll
-            for (int a = 0; a < 4; ++a) acc[a] += __shfl_xor_sync(0xffffffffu, acc[a], 16);
-            if (lane < 16) {
-                float* o = out + (size_t)cell * K;
-                if (2 * lane < K) {
-                    const float2 sv = __ldcg(reinterpret_cast<const float2*>(o + 2 * lane));
-                    __stcs(reinterpret_cast<float2*>(o + 2 * lane), make_float2(fmaf(sv.x, pat_scale, acc[0] / denom), fmaf(sv.y, pat_scale, acc[1] / denom)));
-                }
-                if (2 * (lane + 16) < K) {
-                    const float2 sv = __ldcg(reinterpret_cast<const float2*>(o + 2 * lane + 32));
-                    __stcs(reinterpret_cast<float2*>(o + 2 * lane + 32), make_float2(fmaf(sv.x, pat_scale, acc[2] / denom), fmaf(sv.y, pat_scale, acc[3] / denom)));
-                }
-            }
-        };
-
-        long long tp_fin = 0, tp_wait = 0, tp_scan = 0, tp_all0 = clock64();
-        for (uint64_t sup = blockIdx.x; sup < nsuper; sup += gridDim.x, ++it) {
+        // lanes 0..15 hold the state of the warp's 16 cells (lanes 16..31 mirror them)
+        uint32_t cur = 0, end = 0, nexc = 0;  // cursor / end of the stream (relative to the supertile's first entry), exceptions so far
+        uint32_t chunk_it = 0;
+        const uint32_t bm_s = smem_u32(bitmap);
+        for (uint64_t sup = blockIdx.x; sup < nsuper; sup += gridDim.x) {
+            const uint64_t first = sup * CELLS;
+            const uint64_t base = indptr[first];  // first entry of the supertile (warp-uniform)
+            const uint64_t mycell = first + (uint64_t)(row0 + (lane & 15));
             {
-                const uint64_t first = sup * CELLS;
-                base = indptr[first];
-                const uint64_t cell = first + (uint64_t)(row0 + (lane & 15));
                 uint64_t lo = base, hi = base;
-                if (cell < ncols) {
-                    lo = indptr[cell];
-                    hi = indptr[cell + 1];
+                if (mycell < ncols) {
+                    lo = indptr[mycell];
+                    hi = indptr[mycell + 1];
                 }
                 cur = (uint32_t)(lo - base);
                 end = (uint32_t)(hi - base);
                 nexc = 0;
             }
-            const uint32_t my_lo = cur;
-            uint2* xl_cur = xl + ((size_t)(blockIdx.x * 2 + (it & 1)) * CELLS + (size_t)row0) * F_CAPX;
-            uint32_t fin_done = 0;
-            bool waited = false;
+            const uint32_t* ibase = indices + base;
+            const float* vbase = values + base;
+            const int lim = (int)(nnz - base < 0x7fffffffull ? nnz - base : 0x7fffffffull);  // entries left in the arrays
+            const int mis0 = (int)(base & 3ull);
+            uint2* xl_sup = xl + (first + (uint64_t)row0) * F_CAPX;
             for (uint32_t c = 0; c < nchunks; ++c, ++chunk_it) {
-                // ---- finalisation slot (previous supertile), ahead of the wait for a free bitmap buffer ----
-                const long long tf0 = clock64();
-                if (have_prev && c >= c0) {
-                    const uint32_t target = (c + 1 == nchunks) ? (uint32_t)F_CPW : ((c - c0 + 1) * (uint32_t)F_CPW) / (nchunks - c0);
-                    if (fin_done < target) {
-                        if (!waited) {
-                            mbar_wait(&bars->epi_done, (it - 1) & 1);
-                            waited = true;
-                        }
-                        for (; fin_done < target; ++fin_done)
-                            if (!(dbg & 1)) finalize((int)fin_done);
-                    }
-                }
                 const uint32_t buf = chunk_it % NBM;
-                const long long tf1 = clock64();
-                mbar_wait(&bars->bm_empty[buf], ((chunk_it / NBM) & 1) ^ 1);
-                const long long tf2 = clock64();
-                tp_fin += tf1 - tf0;
-                tp_wait += tf2 - tf1;
-                uint32_t* rows = bitmap + (size_t)buf * CELLS * BM_STRIDE + (size_t)row0 * BM_STRIDE;
-                for (int q = lane; q < F_CPW * BM_STRIDE / 4; q += 32) reinterpret_cast<uint4*>(rows)[q] = make_uint4(0, 0, 0, 0);
+                mbar_wait_sleep(&bars->bm_empty[buf], ((chunk_it / NBM) & 1) ^ 1);
+                {
+                    uint32_t* rows = bitmap + (size_t)buf * CELLS * BM_STRIDE + (size_t)row0 * BM_STRIDE;
+                    for (int q = lane; q < F_CPW * BM_STRIDE / 4; q += 32) reinterpret_cast<uint4*>(rows)[q] = make_uint4(0, 0, 0, 0);
+                }
                 __syncwarp();
+                // shared-window byte address of the warp's first row, moved back by the chunk's first word
+                const uint32_t rows_s = bm_s + ((uint32_t)buf * CELLS * BM_STRIDE + (uint32_t)row0 * BM_STRIDE - c * (GC / 32)) * 4u;
                 const uint32_t g1 = (c + 1 == nchunks) ? 0xffffffffu : (c + 1) * (uint32_t)GC;
+
                 // A piece is fetched as ONE window of 32 x 128-bit groups (128 entries) from the 16-byte boundary at or below
-                // the cursor, before its length is known; entries outside [cursor, end of the cell) or at genes beyond the
-                // chunk are masked, the part of the window beyond the chunk is read again (from L2) one chunk later.
+                // the cursor, before its length is known; entries outside [cursor, end of the cell) are blanked, genes beyond
+                // the chunk stay for the next chunk (that part of the window is read again, from L2).
                 struct Win {
                     uint4 ix;
                     float4 v;
-                    int a0;  // window start relative to `base` (may be -3 .. -1 for the first cell)
+                    int a0;  // window start relative to the supertile's first entry (-3 .. -1 possible for its first cell)
                 };
                 auto fetch = [&](int a0, uint32_t en, Win& w) {
                     w.a0 = a0;
@@ -1035,17 +1027,16 @@ __global__ void __launch_bounds__(F_THREADS, 1)
                     w.v = make_float4(1.f, 1.f, 1.f, 1.f);
                     const int p0 = a0 + 4 * lane;
                     if (p0 < (int)en) {
-                        const uint64_t e0 = base + (int64_t)p0;  // absolute entry index, a multiple of 4
-                        if (e0 + 4 <= nnz) {
-                            w.ix = __ldg(reinterpret_cast<const uint4*>(indices + e0));
-                            w.v = __ldg(reinterpret_cast<const float4*>(values + e0));
+                        if (p0 + 4 <= lim) {
+                            w.ix = __ldg(reinterpret_cast<const uint4*>(ibase + p0));
+                            w.v = __ldg(reinterpret_cast<const float4*>(vbase + p0));
                         } else {  // the last, partial group of the arrays
                             uint32_t gi[4] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu};
                             float gv[4] = {1.f, 1.f, 1.f, 1.f};
                             for (int j = 0; j < 4; ++j)
-                                if (e0 + j < nnz) {
-                                    gi[j] = __ldg(indices + e0 + j);
-                                    gv[j] = __ldg(values + e0 + j);
+                                if (p0 + j < lim) {
+                                    gi[j] = __ldg(ibase + p0 + j);
+                                    gv[j] = __ldg(vbase + p0 + j);
                                 }
                             w.ix = make_uint4(gi[0], gi[1], gi[2], gi[3]);
                             w.v = make_float4(gv[0], gv[1], gv[2], gv[3]);
@@ -1054,47 +1045,69 @@ __global__ void __launch_bounds__(F_THREADS, 1)
                 };
                 auto issue = [&](int i, Win& w) {
                     const uint32_t cu = __shfl_sync(0xffffffffu, cur, i), en = __shfl_sync(0xffffffffu, end, i);
-                    const int mis = (int)((base + cu) & 3ull);
-                    fetch((int)cu - mis, en, w);
+                    fetch((int)cu - (int)((cu + mis0) & 3u), en, w);
                 };
                 auto consume = [&](int i, Win w) {
-                    uint32_t* browc = rows + (size_t)i * BM_STRIDE - (size_t)c * (GC / 32);
-                    uint2* xlist = xl_cur + (size_t)i * F_CAPX;
-                    const uint32_t cu = __shfl_sync(0xffffffffu, cur, i), en = __shfl_sync(0xffffffffu, end, i);
+                    const uint32_t rowa = rows_s + (uint32_t)i * (BM_STRIDE * 4);
+                    uint2* xlist = xl_sup + (size_t)i * F_CAPX;
+                    const int cu = (int)__shfl_sync(0xffffffffu, cur, i), en = (int)__shfl_sync(0xffffffffu, end, i);
                     uint32_t xc = __shfl_sync(0xffffffffu, nexc, i);
                     uint32_t taken = 0;
                     for (;;) {
                         const int p0 = w.a0 + 4 * lane;
-                        const uint32_t gx[4] = {w.ix.x, w.ix.y, w.ix.z, w.ix.w};
+                        uint32_t gx[4] = {w.ix.x, w.ix.y, w.ix.z, w.ix.w};
                         const float vx[4] = {w.v.x, w.v.y, w.v.z, w.v.w};
-                        bool in[4], ex[4];
-                        uint32_t cnt = 0, xcnt = 0;
+                        if (p0 < cu) {  // the group the cursor sits in: its leading entries belong to the previous piece
+#pragma unroll
+                            for (int j = 0; j < 3; ++j)
+                                if (p0 + j < cu) gx[j] = 0xffffffffu;
+                        }
+                        if (p0 + 4 > en) {  // the group the cell ends in
+#pragma unroll
+                            for (int j = 1; j < 4; ++j)
+                                if (p0 + j >= en) gx[j] = 0xffffffffu;
+                        }
+                        bool in[4];
+                        uint32_t cnt = 0, nx = 0, xg = 0;
+                        float xv = 1.0f;
 #pragma unroll
                         for (int j = 0; j < 4; ++j) {
-                            in[j] = p0 + j >= (int)cu && p0 + j < (int)en && gx[j] < g1;
-                            if (in[j] && !(dbg & 4)) atomicOr(browc + (gx[j] >> 5), 1u << (gx[j] & 31));
-                            ex[j] = in[j] && vx[j] != 1.0f && !(dbg & 2);
-                            cnt += in[j];
-                            xcnt += ex[j];
-                        }
-                        // exceptions join the list in ascending position: lanes in order, entries in order inside a lane
-                        const unsigned b0 = __ballot_sync(0xffffffffu, xcnt & 1u), b1 = __ballot_sync(0xffffffffu, xcnt & 2u),
-                                       b2 = __ballot_sync(0xffffffffu, xcnt & 4u);
-                        if (b0 | b1 | b2) {
-                            uint32_t slot = xc + __popc(b0 & lt_mask) + 2 * __popc(b1 & lt_mask) + 4 * __popc(b2 & lt_mask);
-#pragma unroll
-                            for (int j = 0; j < 4; ++j)
-                                if (ex[j]) {
-                                    if (slot < (uint32_t)F_CAPX) __stcg(xlist + slot, make_uint2(gx[j], __float_as_uint(vx[j])));
-                                    ++slot;
+                            in[j] = gx[j] < g1;
+                            if (in[j]) {
+                                asm volatile("red.shared.or.b32 [%0], %1;" ::"r"(rowa + ((gx[j] >> 5) << 2)), "r"(1u << (gx[j] & 31)) : "memory");
+                                ++cnt;
+                                if (vx[j] != 1.0f) {
+                                    ++nx;
+                                    xg = gx[j];
+                                    xv = vx[j];
                                 }
-                            xc += __popc(b0) + 2 * __popc(b1) + 4 * __popc(b2);
+                            }
+                        }
+                        // exceptions join the cell's list in ascending position: lanes in order, entries in order inside a lane
+                        const unsigned b_any = __ballot_sync(0xffffffffu, nx != 0);
+                        if (b_any) {
+                            const unsigned b_multi = __ballot_sync(0xffffffffu, nx > 1);
+                            if (!b_multi) {  // at most one per lane (the usual case): xg / xv hold it
+                                const uint32_t slot = xc + __popc(b_any & lt_mask);
+                                if (nx && slot < (uint32_t)F_CAPX) __stcg(xlist + slot, make_uint2(xg, __float_as_uint(xv)));
+                                xc += __popc(b_any);
+                            } else {
+                                const unsigned b0 = __ballot_sync(0xffffffffu, nx & 1u), b1 = __ballot_sync(0xffffffffu, nx & 2u),
+                                               b2 = __ballot_sync(0xffffffffu, nx & 4u);
+                                uint32_t slot = xc + __popc(b0 & lt_mask) + 2 * __popc(b1 & lt_mask) + 4 * __popc(b2 & lt_mask);
+#pragma unroll
+                                for (int j = 0; j < 4; ++j)
+                                    if (in[j] && vx[j] != 1.0f) {
+                                        if (slot < (uint32_t)F_CAPX) __stcg(xlist + slot, make_uint2(gx[j], __float_as_uint(vx[j])));
+                                        ++slot;
+                                    }
+                                xc += __popc(b0) + 2 * __popc(b1) + 4 * __popc(b2);
+                            }
                         }
                         taken += __reduce_add_sync(0xffffffffu, cnt);
                         // the piece goes on beyond this window iff its last entry is still inside the chunk
-                        const bool more = (__ballot_sync(0xffffffffu, in[3]) >> 31) != 0;
-                        if (!more) break;
-                        fetch(w.a0 + 128, en, w);
+                        if (!(__ballot_sync(0xffffffffu, in[3]) >> 31)) break;
+                        fetch(w.a0 + 128, (uint32_t)en, w);
                     }
                     if ((lane & 15) == i) {
                         cur += taken;
@@ -1119,31 +1132,15 @@ __global__ void __launch_bounds__(F_THREADS, 1)
                 }
                 // pull the lines that the chunk after the next one will start in into L2 (what the next chunk's windows
                 // fetch lies behind this chunk's windows already): lanes 0-15 the index lines, 16-31 the value lines
-                if (c + 2 < nchunks) {
-                    const char* pf = (lane < 16 ? reinterpret_cast<const char*>(indices) : reinterpret_cast<const char*>(values)) +
-                                     (base + cur + 128) * 4;
-                    if (cur + 128 < end) {
+                if (c + 2 < nchunks && cur + 128 < end) {
+                    const char* pf = (lane < 16 ? reinterpret_cast<const char*>(ibase) : reinterpret_cast<const char*>(vbase)) + ((size_t)cur + 128) * 4;
 #pragma unroll
-                        for (int k = 0; k < 4; ++k) asm volatile("prefetch.global.L2 [%0];" ::"l"(pf + 128 * k));
-                    }
+                    for (int k = 0; k < 4; ++k) asm volatile("prefetch.global.L2 [%0];" ::"l"(pf + 128 * k));
                 }
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&bars->bm_full[buf]);
-                tp_scan += clock64() - tf2;
             }
-            p_lo = my_lo;
-            p_n = end - my_lo;
-            p_nexc = nexc;
-            p_base = base;
-            p_sup = sup;
-            have_prev = true;
-        }
-        if ((dbg & 8) && blockIdx.x == 0 && lane == 0 && (pw == 0 || pw == 15))
-            printf("[fused prod %d] total %lld clk, finalize %lld, wait bm_empty %lld, scan %lld\n", pw, clock64() - tp_all0, tp_fin, tp_wait, tp_scan);
-        if (have_prev) {  // the last supertile of this CTA
-            mbar_wait(&bars->epi_done, (it - 1) & 1);
-            for (int i = 0; i < F_CPW; ++i)
-                if (!(dbg & 1)) finalize(i);
+            if (lane < F_CPW && mycell < ncols) xn[mycell] = nexc;  // the list's length (may exceed F_CAPX: that cell is re-scanned)
         }
     }
     tc_fence_before();
@@ -1194,7 +1191,7 @@ int lg_project_raw_umma(lg_ctx* ctx, const lg_csc* m, const float* d_basis, int 
     // the fused kernel (projection mode, even K, 8-byte aligned basis and output); LG_K1_FUSED=0 keeps the two-kernel form
     {
         const char* fz = getenv("LG_K1_FUSED");
-        const bool fused = mode == 0 && !(fz && fz[0] == '0') && K % 2 == 0 && (((uintptr_t)d_basis | (uintptr_t)d_out) & 7) == 0 &&
+        const bool fused = mode == 0 && fz && fz[0] == '1' && K % 2 == 0 && (((uintptr_t)d_basis | (uintptr_t)d_out) & 7) == 0 &&
                            (((uintptr_t)m->indices | (uintptr_t)m->values) & 15) == 0;
         if (fused) {
             const size_t stage_bytes = (size_t)NB * 32 * (GS / 32);
@@ -1203,19 +1200,30 @@ int lg_project_raw_umma(lg_ctx* ctx, const lg_csc* m, const float* d_basis, int 
             const uint64_t nsuper = (m->ncols + CELLS - 1) / CELLS;
             const unsigned grid = (unsigned)(nsuper < (uint64_t)ctx->num_sms ? nsuper : (uint64_t)ctx->num_sms);
             uint2* d_xl;
-            LG_TRY(st.scratch((size_t)grid * 2 * CELLS * F_CAPX, &d_xl));
+            uint32_t* d_xn;
+            LG_TRY(st.scratch((size_t)m->ncols * F_CAPX, &d_xl));
+            LG_TRY(st.scratch((size_t)m->ncols, &d_xn));
             LG_CUDA(ctx, cudaFuncSetAttribute(k_project_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             if (trace) cudaEventRecord(ev[0], ctx->stream);
             LG_LAUNCH(ctx, k_project_fused, grid, F_THREADS, smem, m->indptr, m->indices, m->values, m->ncols, m->nnz, D, d_basis, d_bq, K,
-                      NB, nstages, d_colmax, d_flag, d_xl, d_out, getenv("LG_K1_DBG") ? atoi(getenv("LG_K1_DBG")) : 0);
+                      NB, nstages, d_colmax, d_flag, d_xl, d_xn, d_out);
             if (trace) cudaEventRecord(ev[1], ctx->stream);
+            {
+                uint64_t fb = (m->ncols + 7) / 8;
+                const uint64_t cap = (uint64_t)ctx->num_sms * 8;
+                if (fb > cap) fb = cap;
+                LG_LAUNCH(ctx, k_project_finalize, (unsigned)fb, 256, 0, m->indptr, m->indices, m->values, m->ncols, d_basis, K, d_xl, d_xn,
+                          d_flag, d_out);
+            }
+            if (trace) cudaEventRecord(ev[2], ctx->stream);
             const cudaError_t fe = cudaEventSynchronize(flag_ev);  // the quantiser's verdict: long home by now
             cudaEventDestroy(flag_ev);
             if (trace) {
-                cudaEventSynchronize(ev[1]);
-                float a = 0.f;
+                cudaEventSynchronize(ev[2]);
+                float a = 0.f, b = 0.f;
                 cudaEventElapsedTime(&a, ev[0], ev[1]);
-                fprintf(stderr, "[lg_project] fused %.3f ms\n", a);
+                cudaEventElapsedTime(&b, ev[1], ev[2]);
+                fprintf(stderr, "[lg_project] fused %.3f ms, finalize %.3f ms\n", a, b);
                 for (int i = 0; i < 3; ++i) cudaEventDestroy(ev[i]);
             }
             LG_CUDA(ctx, fe);

@@ -37,6 +37,20 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     }
 }
 
+// for waits that are long by design (a starved consumer, a producer ahead of its ring): the plain try_wait loop comes back
+// after a few cycles and its iterations take issue slots from the warps that do the work, so this one lets the thread
+// sleep in the barrier unit for up to ~1 us per attempt (it wakes at once when the phase completes)
+__device__ __forceinline__ void mbar_wait_sleep(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok)
+            : "r"(smem_u32(bar)), "r"(parity), "r"(1000u)
+            : "memory");
+    } while (!ok);
+}
+
 // ---- 1-D bulk async copy global -> shared, completion on an mbarrier (TMA engine, no tensor map) ----
 __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(

@@ -296,6 +296,34 @@ def test_project_raw_bits_do_not_depend_on_where_a_column_starts(lg, ctx):
         assert lg.nystrom_project(ctx, sub, np.ascontiguousarray(basis.T)).tobytes() == ny[lo:hi].tobytes(), (lo, hi)
 
 
+def test_project_fused_form_is_bit_identical(lg, ctx, monkeypatch):
+    """LG_K1_FUSED=1 runs K1 as the one-kernel form (producer warps build the pattern bitmap in shared memory from per-cell
+    cursors, k_project_finalize folds the exception lists): an independent second scan of the same stream whose raw
+    projection must equal the default two-kernel form bit for bit — counts, empty columns, a ragged last supertile, blocks
+    that start at any alignment, and non-count values (every entry an exception: the list overflows and the cell is
+    re-scanned)."""
+    rng = np.random.default_rng(5)
+    K = 50
+    cases = []
+    for D, N, dens, ee in ((4000, 1500, 0.05, 89), (9000, 700, 0.2, 0), (300, 257, 0.5, 7), (20000, 513, 0.02, 0)):
+        cases.append((D, N) + random_csc(rng, D, N, dens, empty_every=ee))
+    D, N = 5000, 600
+    ip, ix, v = random_csc(rng, D, N, 0.08)
+    cases.append((D, N, ip, ix, (v + rng.uniform(0.1, 0.9, v.size)).astype(np.float32)))  # no entry equals one
+    for D, N, ip, ix, v in cases:
+        basis = basis_for(D, K, 9)
+        for lo, hi in ((0, N), (3, N - 1)):
+            blk = lg.CscBlock.upload(ctx, ip, ix, v, D, lo, hi)
+            got = {}
+            for mode in ("0", "1"):
+                monkeypatch.setenv("LG_K1_FUSED", mode)
+                raw = np.full((hi - lo, K), np.nan, np.float32)
+                ctx.check(lg.lib.lg_project_raw(ctx.h, blk.h, basis.ctypes.data, K, raw.ctypes.data))
+                got[mode] = raw
+            assert np.isfinite(got["1"]).all()
+            assert got["0"].tobytes() == got["1"].tobytes(), (D, N, lo, hi)
+
+
 def test_sparse_io_stack_projects_every_modality_and_stacks(lg, ctx):
     """RandProjOps for SparseIoStack (random_projection.rs:200-340): per-modality projection with its own basis, vertical
     concatenation of bases (rows) and projections (dims); batch labels cut to the shared column count; one set of codes"""
