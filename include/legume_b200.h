@@ -216,6 +216,26 @@ int lg_optimize_batched(lg_ctx* ctx, const float* obs_ds, const float* imp_ds, c
                         float* mu_obs, float* mu_adj, float* mu_res, float* gamma, float* delta,
                         float* mu_adj_log_mean);
 
+/* optimize_block with panel observability attached (stats.rs:176-204, 299-322): size_ds (D x S, optional) replaces the
+ * per-sample size in every denominator (add_effective_size / scale_by_effective_size), obs_mask_db (D x B of 0 / 1,
+ * optional) multiplies both sides of the delta ratio.  With both NULL these are lg_optimize_single / _batched. */
+int lg_optimize_single_obs(lg_ctx* ctx, const float* sum_ds, const float* size_s, const float* size_ds, uint64_t D,
+                           uint32_t S, float a0, float b0, int target, float* mean, float* sd, float* log_mean,
+                           float* log_sd);
+int lg_optimize_batched_obs(lg_ctx* ctx, const float* obs_ds, const float* imp_ds, const float* res_ds,
+                            const float* size_s, const float* size_ds, const float* obs_db, const float* n_bs,
+                            const float* obs_mask_db, uint64_t D, uint32_t S, uint32_t B, float a0, float b0,
+                            int num_iter, int target, float* mu_obs, float* mu_adj, float* mu_res, float* gamma,
+                            float* delta, float* mu_adj_log_mean);
+/* attach_observability (collapse_data/mod.rs:221-301): coverage is nsrc x D (1 = the backend measures the gene),
+ * source_of_cell the backend every column came from.  size_ds[g, s] = multiplicity-weighted mass of sample s from the
+ * backends that cover g; mask_db[g, b] = 1 iff some backend used by batch b covers g (optional; *out_mask_has_zero
+ * tells whether any entry is 0 — the reference keeps the mask only then). */
+int lg_attach_observability(lg_ctx* ctx, const uint8_t* coverage, uint32_t nsrc, const uint32_t* source_of_cell,
+                            const uint32_t* group_of_cell, const uint32_t* batch_of_cell, const float* mult,
+                            uint64_t ncols, uint64_t D, uint32_t S, uint32_t B, float* out_size_ds,
+                            float* out_mask_db, int* out_mask_has_zero);
+
 /* ---- stage 6: exact kNN ----------------------------------------------------------------------
  * replaces ColumnDict::search_by_query_data / match_by_query_name_against / search_others with the
  * exact backend (matrix-util/src/knn/mod.rs:152-299, exact.rs:36-55, metric.rs:19-45).

@@ -95,7 +95,7 @@ __device__ __forceinline__ void gamma_element(const GammaLut& t, float x, float 
 
 // den[e] is a full plane (GammaMatrix::update_stat with arbitrary B)
 __global__ void __launch_bounds__(256) k_gamma_calibrate(const float* __restrict__ num, const float* __restrict__ den,
-                                                         uint64_t n, float a0, float b0, int target,
+                                                         uint64_t n, float a0, float b0, int target, int sparsify,
                                                          float* __restrict__ mean, float* __restrict__ sd,
                                                          float* __restrict__ log_mean, float* __restrict__ log_sd) {
     __shared__ GammaLut t;
@@ -104,11 +104,11 @@ __global__ void __launch_bounds__(256) k_gamma_calibrate(const float* __restrict
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
     for (uint64_t e = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += stride) {
         const float x = num[e];
-        const float b = b0 + den[e];
+        const float b = b0 + (0.0f + den[e]);
         float m, s = 0.f, lm = 0.f, ls = 0.f;
-        if (target == LG_TARGET_ALL) gamma_element<true, true>(t, x, a0, b, logf(b), 0, m, s, lm, ls);
-        else if (target == LG_TARGET_MEAN_ONLY) gamma_element<false, false>(t, x, a0, b, 0.0f, 0, m, s, lm, ls);
-        else gamma_element<true, false>(t, x, a0, b, logf(b), 0, m, s, lm, ls);
+        if (target == LG_TARGET_ALL) gamma_element<true, true>(t, x, a0, b, logf(b), sparsify, m, s, lm, ls);
+        else if (target == LG_TARGET_MEAN_ONLY) gamma_element<false, false>(t, x, a0, b, 0.0f, sparsify, m, s, lm, ls);
+        else gamma_element<true, false>(t, x, a0, b, logf(b), sparsify, m, s, lm, ls);
         if (mean) mean[e] = m;
         if (target != LG_TARGET_MEAN_ONLY && log_mean) log_mean[e] = lm;
         if (target == LG_TARGET_ALL) {
@@ -182,29 +182,41 @@ extern "C" int lg_gamma_calibrate(lg_ctx* ctx, const float* num, const float* de
     LG_TRY(st.out(sd, n, &d_sd));
     LG_TRY(st.out(log_mean, n, &d_lm));
     LG_TRY(st.out(log_sd, n, &d_ls));
-    if (n) LG_LAUNCH(ctx, k_gamma_calibrate, ew_grid(ctx, n), 256, 0, d_num, d_den, n, a0, b0, target, d_mean, d_sd, d_lm, d_ls);
+    if (n) LG_LAUNCH(ctx, k_gamma_calibrate, ew_grid(ctx, n), 256, 0, d_num, d_den, n, a0, b0, target, 0, d_mean, d_sd, d_lm, d_ls);
     return st.finish();
 }
 
 extern "C" int lg_optimize_single(lg_ctx* ctx, const float* sum_ds, const float* size_s, uint64_t D, uint32_t S, float a0,
                                   float b0, int target, float* mean, float* sd, float* log_mean, float* log_sd) {
+    return lg_optimize_single_obs(ctx, sum_ds, size_s, nullptr, D, S, a0, b0, target, mean, sd, log_mean, log_sd);
+}
+
+extern "C" int lg_optimize_single_obs(lg_ctx* ctx, const float* sum_ds, const float* size_s, const float* size_ds, uint64_t D,
+                                      uint32_t S, float a0, float b0, int target, float* mean, float* sd, float* log_mean,
+                                      float* log_sd) {
     if (!ctx) return LG_ERR_INVALID;
-    LG_REQUIRE(ctx, sum_ds && size_s, "lg_optimize_single: null argument");
+    LG_REQUIRE(ctx, sum_ds && (size_s || size_ds), "lg_optimize_single: null argument");
     LG_REQUIRE(ctx, target >= 0 && target <= 2, "lg_optimize_single: bad target");
     cudaSetDevice(ctx->device);
     const uint64_t n = D * (uint64_t)S;
     LgStage st(ctx);
     const float *d_num, *d_size;
     float *d_mean, *d_sd, *d_lm, *d_ls;
+    const float* d_size_ds;
     LG_TRY(st.in(sum_ds, n, &d_num));
     LG_TRY(st.in(size_s, (size_t)S, &d_size));
+    LG_TRY(st.in(size_ds, n, &d_size_ds));
     LG_TRY(st.out(mean, n, &d_mean));
     LG_TRY(st.out(sd, n, &d_sd));
     LG_TRY(st.out(log_mean, n, &d_lm));
     LG_TRY(st.out(log_sd, n, &d_ls));
     // MeanOnly drops the prior baseline where nothing was observed (stats.rs:357-359)
     const int sparsify = target == LG_TARGET_MEAN_ONLY;
-    if (n) {
+    if (n && d_size_ds) {
+        // per-(gene, sample) denominators (add_effective_size with size_ds attached, stats.rs:176-186)
+        LG_LAUNCH(ctx, k_gamma_calibrate, ew_grid(ctx, n), 256, 0, d_num, d_size_ds, n, a0, b0, target, sparsify, d_mean, d_sd,
+                  d_lm, d_ls);
+    } else if (n) {
         const uintptr_t align = (uintptr_t)d_num | (uintptr_t)d_mean | (uintptr_t)d_sd | (uintptr_t)d_lm | (uintptr_t)d_ls;
         const bool vec = (D % 4 == 0) && (align & 15) == 0;
         const uint64_t per_col = vec ? D / 4 : D;
@@ -233,14 +245,15 @@ extern "C" int lg_optimize_single(lg_ctx* ctx, const float* sum_ds, const float*
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_optimize_sweeps(const float* __restrict__ obs, const float* __restrict__ imp,
                                                          const float* __restrict__ res, const float* __restrict__ size_s,
-                                                         uint64_t n, uint64_t D, float a0, float b0, int num_iter, int target,
+                                                         const float* __restrict__ size_ds, uint64_t n, uint64_t D, float a0,
+                                                         float b0, int num_iter, int target,
                                                          float* __restrict__ mu_obs, float* __restrict__ mu_adj,
                                                          float* __restrict__ mu_res, float* __restrict__ gamma,
                                                          float* __restrict__ mu_adj_lm) {
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
     for (uint64_t e = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += stride) {
         const float o = obs[e], im = imp[e], r = res[e];
-        const float sz = size_s[e / D];
+        const float sz = size_ds ? size_ds[e] : size_s[e / D];
         const float m_res = __fdiv_rn(a0 + r, b0 + (0.0f + sz));
         float m_gam = 0.0f, m_adj = 0.0f, a_adj = a0, b_adj = b0;
         for (int it = 0; it < num_iter; ++it) {
@@ -263,31 +276,50 @@ __global__ void __launch_bounds__(256) k_optimize_sweeps(const float* __restrict
 // delta[g,b] = (a0 + obs_db[g,b]) / (b0 + sum_s mu_adj[g,s] * n_bs[b,s])   (stats.rs:296-324)
 // one thread per (gene, batch); the sum runs over s in order with fma, genes are the fast axis.
 // mu_adj here must be the un-sparsified mean, so it is recomputed by the caller into scratch.
+// obs_mask_db (optional, D x B of 0 / 1) multiplies BOTH sides of the ratio so that a masked entry lands on the prior
+// exactly (stats.rs:299-322)
 __global__ void __launch_bounds__(256) k_optimize_delta(const float* __restrict__ mu_adj, const float* __restrict__ n_bs,
-                                                        const float* __restrict__ obs_db, uint64_t D, uint32_t S, uint32_t B,
-                                                        float a0, float b0, float* __restrict__ delta) {
+                                                        const float* __restrict__ obs_db, const float* __restrict__ mask_db,
+                                                        uint64_t D, uint32_t S, uint32_t B, float a0, float b0,
+                                                        float* __restrict__ delta) {
     const uint64_t e = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= D * B) return;
     const uint64_t g = e % D;
     const uint32_t b = (uint32_t)(e / D);
     float acc = 0.0f;
     for (uint32_t s = 0; s < S; ++s) acc = fmaf(mu_adj[(size_t)s * D + g], n_bs[(size_t)s * B + b], acc);
-    delta[e] = __fdiv_rn(a0 + obs_db[e], b0 + acc);
+    float num = obs_db[e];
+    if (mask_db) {
+        acc = __fmul_rn(acc, mask_db[e]);
+        num = __fmul_rn(num, mask_db[e]);
+    }
+    delta[e] = __fdiv_rn(a0 + num, b0 + acc);
 }
 
 extern "C" int lg_optimize_batched(lg_ctx* ctx, const float* obs_ds, const float* imp_ds, const float* res_ds,
                                    const float* size_s, const float* obs_db, const float* n_bs, uint64_t D, uint32_t S,
                                    uint32_t B, float a0, float b0, int num_iter, int target, float* mu_obs, float* mu_adj,
                                    float* mu_res, float* gamma, float* delta, float* mu_adj_log_mean) {
+    return lg_optimize_batched_obs(ctx, obs_ds, imp_ds, res_ds, size_s, nullptr, obs_db, n_bs, nullptr, D, S, B, a0, b0, num_iter,
+                                   target, mu_obs, mu_adj, mu_res, gamma, delta, mu_adj_log_mean);
+}
+
+extern "C" int lg_optimize_batched_obs(lg_ctx* ctx, const float* obs_ds, const float* imp_ds, const float* res_ds,
+                                       const float* size_s, const float* size_ds, const float* obs_db, const float* n_bs,
+                                       const float* obs_mask_db, uint64_t D, uint32_t S, uint32_t B, float a0, float b0,
+                                       int num_iter, int target, float* mu_obs, float* mu_adj, float* mu_res, float* gamma,
+                                       float* delta, float* mu_adj_log_mean) {
     if (!ctx) return LG_ERR_INVALID;
-    LG_REQUIRE(ctx, obs_ds && imp_ds && res_ds && size_s, "lg_optimize_batched: null statistic");
+    LG_REQUIRE(ctx, obs_ds && imp_ds && res_ds && (size_s || size_ds), "lg_optimize_batched: null statistic");
     LG_REQUIRE(ctx, !delta || (obs_db && n_bs), "lg_optimize_batched: delta needs obs_db and n_bs");
     LG_REQUIRE(ctx, target >= 0 && target <= 2 && num_iter >= 0, "lg_optimize_batched: bad target / num_iter");
     cudaSetDevice(ctx->device);
     const uint64_t n = D * (uint64_t)S;
     LgStage st(ctx);
-    const float *d_obs, *d_imp, *d_res, *d_size, *d_obs_db, *d_nbs;
+    const float *d_obs, *d_imp, *d_res, *d_size, *d_obs_db, *d_nbs, *d_size_ds, *d_mask;
     float *d_mo, *d_ma, *d_mr, *d_g, *d_delta, *d_lm;
+    LG_TRY(st.in(size_ds, n, &d_size_ds));
+    LG_TRY(st.in(obs_mask_db, (size_t)D * B, &d_mask));
     LG_TRY(st.in(obs_ds, n, &d_obs));
     LG_TRY(st.in(imp_ds, n, &d_imp));
     LG_TRY(st.in(res_ds, n, &d_res));
@@ -305,14 +337,100 @@ extern "C" int lg_optimize_batched(lg_ctx* ctx, const float* obs_ds, const float
     float* d_ma_dense = d_ma;
     if (d_delta && (target == LG_TARGET_MEAN_ONLY || !d_ma)) {
         LG_TRY(st.scratch(n, &d_ma_dense));
-        LG_LAUNCH(ctx, k_optimize_sweeps, ew_grid(ctx, n), 256, 0, d_obs, d_imp, d_res, d_size, n, D, a0, b0, num_iter,
+        LG_LAUNCH(ctx, k_optimize_sweeps, ew_grid(ctx, n), 256, 0, d_obs, d_imp, d_res, d_size, d_size_ds, n, D, a0, b0, num_iter,
                   LG_TARGET_ALL, (float*)nullptr, d_ma_dense, (float*)nullptr, (float*)nullptr, (float*)nullptr);
     }
-    LG_LAUNCH(ctx, k_optimize_sweeps, ew_grid(ctx, n), 256, 0, d_obs, d_imp, d_res, d_size, n, D, a0, b0, num_iter, target,
-              d_mo, d_ma, d_mr, d_g, d_lm);
+    LG_LAUNCH(ctx, k_optimize_sweeps, ew_grid(ctx, n), 256, 0, d_obs, d_imp, d_res, d_size, d_size_ds, n, D, a0, b0, num_iter,
+              target, d_mo, d_ma, d_mr, d_g, d_lm);
     if (d_delta) {
         const uint64_t tot = D * (uint64_t)B;
-        LG_LAUNCH(ctx, k_optimize_delta, (unsigned)((tot + 255) / 256), 256, 0, d_ma_dense, d_nbs, d_obs_db, D, S, B, a0, b0, d_delta);
+        LG_LAUNCH(ctx, k_optimize_delta, (unsigned)((tot + 255) / 256), 256, 0, d_ma_dense, d_nbs, d_obs_db, d_mask, D, S, B, a0, b0,
+                  d_delta);
+    }
+    return st.finish();
+}
+
+// ---------------------------------------------------------------------------------------------
+// attach_observability (collapse_data/mod.rs:221-301): per-(gene, sample) effective sizes and the (gene, batch) mask
+// of delta when the backends of a SparseIoVec cover different rows.
+// ---------------------------------------------------------------------------------------------
+__global__ void k_obs_counts(const uint32_t* __restrict__ source, const uint32_t* __restrict__ group,
+                             const uint32_t* __restrict__ batch, const float* __restrict__ mult, uint64_t ncols, uint32_t nsrc,
+                             uint32_t S, uint32_t B, float* __restrict__ count_ss, unsigned int* __restrict__ used_sb) {
+    const uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= ncols) return;
+    const uint32_t src = source[j];
+    if (src >= nsrc) return;
+    const uint32_t s = group[j];
+    if (s < S) atomicAdd(&count_ss[(size_t)s * nsrc + src], mult ? mult[j] : 1.0f);
+    if (batch && batch[j] < B) used_sb[(size_t)src * B + batch[j]] = 1u;
+}
+// size_ds[g, s] = sum over the sources that cover g, in source order, of the mass of sample s that came from the source
+__global__ void __launch_bounds__(256) k_obs_size(const uint8_t* __restrict__ cover, const float* __restrict__ count_ss,
+                                                  uint64_t D, uint32_t S, uint32_t nsrc, float* __restrict__ size_ds) {
+    const uint64_t e = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= D * S) return;
+    const uint64_t g = e % D;
+    const uint32_t s = (uint32_t)(e / D);
+    float acc = 0.0f;
+    for (uint32_t src = 0; src < nsrc; ++src)
+        if (cover[(size_t)src * D + g]) acc = __fadd_rn(acc, count_ss[(size_t)s * nsrc + src]);
+    size_ds[e] = acc;
+}
+__global__ void __launch_bounds__(256) k_obs_mask(const uint8_t* __restrict__ cover, const unsigned int* __restrict__ used_sb,
+                                                  uint64_t D, uint32_t B, uint32_t nsrc, float* __restrict__ mask_db,
+                                                  int* __restrict__ any_zero) {
+    const uint64_t e = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= D * B) return;
+    const uint64_t g = e % D;
+    const uint32_t b = (uint32_t)(e / D);
+    float m = 0.0f;
+    for (uint32_t src = 0; src < nsrc; ++src)
+        if (used_sb[(size_t)src * B + b] && cover[(size_t)src * D + g]) m = 1.0f;
+    mask_db[e] = m;
+    if (m == 0.0f) *any_zero = 1;
+}
+
+extern "C" int lg_attach_observability(lg_ctx* ctx, const uint8_t* coverage, uint32_t nsrc, const uint32_t* source_of_cell,
+                                       const uint32_t* group_of_cell, const uint32_t* batch_of_cell, const float* mult,
+                                       uint64_t ncols, uint64_t D, uint32_t S, uint32_t B, float* out_size_ds,
+                                       float* out_mask_db, int* out_mask_has_zero) {
+    if (!ctx) return LG_ERR_INVALID;
+    LG_REQUIRE(ctx, coverage && source_of_cell && group_of_cell && out_size_ds && nsrc >= 1, "lg_attach_observability: null argument");
+    LG_REQUIRE(ctx, !out_mask_db || (batch_of_cell && B >= 1 && out_mask_has_zero), "lg_attach_observability: the mask needs batches");
+    cudaSetDevice(ctx->device);
+    LgStage st(ctx);
+    const uint8_t* d_cov;
+    const uint32_t *d_src, *d_grp, *d_bat;
+    const float* d_mult;
+    float *d_size, *d_mask, *d_count;
+    unsigned int* d_used;
+    int* d_zero;
+    LG_TRY(st.in(coverage, (size_t)nsrc * D, &d_cov));
+    LG_TRY(st.in(source_of_cell, (size_t)ncols, &d_src));
+    LG_TRY(st.in(group_of_cell, (size_t)ncols, &d_grp));
+    LG_TRY(st.in(batch_of_cell, (size_t)ncols, &d_bat));
+    LG_TRY(st.in(mult, (size_t)ncols, &d_mult));
+    LG_TRY(st.out(out_size_ds, (size_t)D * S, &d_size));
+    LG_TRY(st.out(out_mask_db, (size_t)D * B, &d_mask));
+    LG_TRY(st.scratch((size_t)S * nsrc, &d_count));
+    LG_TRY(st.scratch((size_t)nsrc * (B ? B : 1), &d_used));
+    LG_TRY(st.scratch(1, &d_zero));
+    LG_CUDA(ctx, cudaMemsetAsync(d_count, 0, sizeof(float) * (size_t)S * nsrc, ctx->stream));
+    LG_CUDA(ctx, cudaMemsetAsync(d_used, 0, sizeof(unsigned int) * (size_t)nsrc * (B ? B : 1), ctx->stream));
+    LG_CUDA(ctx, cudaMemsetAsync(d_zero, 0, sizeof(int), ctx->stream));
+    if (ncols)
+        LG_LAUNCH(ctx, k_obs_counts, (unsigned)((ncols + 255) / 256), 256, 0, d_src, d_grp, d_mask ? d_bat : nullptr, d_mult, ncols, nsrc,
+                  S, B, d_count, d_used);
+    const uint64_t tot = D * (uint64_t)S;
+    if (tot) LG_LAUNCH(ctx, k_obs_size, (unsigned)((tot + 255) / 256), 256, 0, d_cov, d_count, D, S, nsrc, d_size);
+    if (d_mask) {
+        const uint64_t tb = D * (uint64_t)B;
+        if (tb) LG_LAUNCH(ctx, k_obs_mask, (unsigned)((tb + 255) / 256), 256, 0, d_cov, d_used, D, B, nsrc, d_mask, d_zero);
+        int* h = static_cast<int*>(ctx->pinned);
+        LG_CUDA(ctx, cudaMemcpyAsync(h, d_zero, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+        LG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        *out_mask_has_zero = *h;
     }
     return st.finish();
 }

@@ -28,6 +28,7 @@ from ._lib import (BLOCK_CELLS, EXPORTED, LIB_PATH, TARGET_ALL, TARGET_MEAN_AND_
 
 DEFAULT_PROJECTION_SEED = 0x50524F4A_50524F4A  # random_projection.rs:41
 DEFAULT_KNN = 10                                # collapse_data/mod.rs:27
+NONE_U32 = 0xFFFFFFFF
 DEFAULT_OPT_ITER = 100                          # collapse_data/mod.rs:28
 
 __all__ = ["Context", "CscBlock", "SparseIoVec", "binary_sort_columns", "GammaMatrix", "CollapsedStat",
@@ -357,17 +358,77 @@ def compute_fine_to_coarse_mapping(ctx: Context, fine_codes, col_to_group, num_f
     return f2c, k.value
 
 
+class RefineParams:
+    """refine_multilevel.rs RefineParams::default(): the BBKNN + Poisson DC-SBM refinement of the pb-sample partition.  With
+    one batch the refinement is the identity (refine.rs:126-147) and this arm is built; with two or more it is SURVEY.md
+    section 8f rank 3 and refused."""
+
+
 class MultilevelParams:
-    """collapse_data/mod.rs:64-130 (the fields the un-refined path reads)"""
+    """collapse_data/mod.rs:64-130.  `MultilevelParams::new` sets refine = Some(default) and observe_panels = true; pass
+    refine=None for the legacy un-refined descent (mod.rs:943-1046)."""
 
     def __init__(self, proj_dim, knn_pb_samples=DEFAULT_KNN, num_levels=DEFAULT_NUM_LEVELS, sort_dim=None,
-                 num_opt_iter=DEFAULT_OPT_ITER, refine=None, output_calibration=TARGET_ALL):
+                 num_opt_iter=DEFAULT_OPT_ITER, refine="default", output_calibration=TARGET_ALL, observe_panels=True,
+                 anchor_batches=None, bulk_batches=None):
         self.knn_pb_samples = knn_pb_samples
         self.num_levels = num_levels
-        self.sort_dim = min(proj_dim, 10) if sort_dim is None else sort_dim
+        self.sort_dim = min(proj_dim, 12) if sort_dim is None else sort_dim  # mod.rs:119
         self.num_opt_iter = num_opt_iter
-        self.refine = refine
+        self.refine = RefineParams() if isinstance(refine, str) and refine == "default" else refine
         self.output_calibration = output_calibration
+        self.observe_panels = observe_panels
+        self.anchor_batches, self.bulk_batches = anchor_batches, bulk_batches
+
+
+# ---- the refinement arm's bookkeeping (dc_poisson.rs:493-509, refine.rs:43-88, collapse_data/mod.rs:823-841) ----
+def compact_labels(labels):
+    """labels -> 0..k in order of first appearance: (compact uint32, k)"""
+    labels = np.asarray(labels)
+    if labels.size == 0:
+        return np.zeros(0, np.uint32), 0
+    uniq, first, inv = np.unique(labels, return_index=True, return_inverse=True)
+    rank = np.empty(len(uniq), np.uint32)
+    rank[np.argsort(first, kind="stable")] = np.arange(len(uniq), dtype=np.uint32)
+    return rank[inv.reshape(-1)], len(uniq)
+
+
+def initial_per_level_from_hash(fine_codes, first_cell_of_pb, level_dims):
+    """refine.rs:68-88"""
+    codes = np.asarray(fine_codes, np.uint64)[first_cell_of_pb]
+    out = []
+    for d in level_dims:
+        mask = np.uint64(0xFFFFFFFFFFFFFFFF) if d >= 64 else np.uint64((1 << d) - 1)
+        out.append(compact_labels(codes & mask)[0])
+    return out
+
+
+def fine_to_coarse_from_refined(pbsamp_to_fine, pbsamp_to_coarse, num_fine):
+    """refine.rs:43-62: the coarse label of the first pb-sample of every fine group"""
+    p2f = np.asarray(pbsamp_to_fine)
+    _, first = np.unique(p2f, return_index=True)
+    m = np.full(num_fine, NONE_U32, np.uint32)
+    m[p2f[first]] = np.asarray(pbsamp_to_coarse, np.uint32)[first]
+    return m
+
+
+def modal_groups(cell_to_pbsamp, num_pb, lvl):
+    """collapse_data/mod.rs:823-841 for every pb-sample at once: the most frequent inherited label among its cells (the
+    reference leaves the choice among equally frequent labels to its hash map; here the smallest label wins), 0 for an
+    empty pb-sample"""
+    c2p = np.asarray(cell_to_pbsamp).astype(np.int64)
+    lvl = np.asarray(lvl).astype(np.int64)
+    live = c2p != NONE_U32
+    L = int(lvl.max()) + 1 if lvl.size else 1
+    key, cnt = np.unique(c2p[live] * L + lvl[live], return_counts=True)
+    pb, lab = key // L, key % L
+    order = np.lexsort((lab, -cnt, pb))  # per pb-sample: highest count first, then the smallest label
+    pb, lab = pb[order], lab[order]
+    head = np.ones(len(pb), bool)
+    head[1:] = pb[1:] != pb[:-1]
+    out = np.zeros(num_pb, np.uint32)
+    out[pb[head]] = lab[head]
+    return out
 
 
 # --------------------------------------------------------------------------------------------------
@@ -452,6 +513,9 @@ class CollapsedStat:
         self.size_s = z(nsample)
         self.observed_sum_db = z(nbatch, ngene)
         self.n_bs = z(nsample, nbatch)
+        # panel observability (stats.rs:556-567): (S, D) effective sizes and the (B, D) mask of delta, None = fully observed
+        self.size_ds = None
+        self.obs_mask_db = None
 
     def num_genes(self):
         return self.observed_sum_ds.shape[1]
@@ -470,6 +534,10 @@ class CollapsedStat:
         out.residual_sum_ds = np.ascontiguousarray(self.residual_sum_ds[:, sl])
         out.observed_sum_db = np.ascontiguousarray(self.observed_sum_db[:, sl])
         out.size_s, out.n_bs = self.size_s.copy(), self.n_bs.copy()
+        if self.size_ds is not None:
+            out.size_ds = np.ascontiguousarray(np.asarray(self.size_ds)[:, sl])
+        if self.obs_mask_db is not None:
+            out.obs_mask_db = np.ascontiguousarray(np.asarray(self.obs_mask_db)[:, sl])
         return out
 
 
@@ -495,16 +563,20 @@ def optimize(ctx: Context, stat: CollapsedStat, hyper=(1.0, 1.0), num_iter=DEFAU
             sd, ls = new(), new()
         if out_target != TARGET_MEAN_ONLY:
             lm = new()
-        ctx.check(lib.lg_optimize_single(ctx.h, _ptr(stat.observed_sum_ds), _ptr(stat.size_s), D, S, a0, b0, out_target,
-                                         _ptr(mean), _ptr(sd), _ptr(lm), _ptr(ls)))
+        size_ds = None if stat.size_ds is None else _as(stat.size_ds, np.float32)
+        ctx.check(lib.lg_optimize_single_obs(ctx.h, _ptr(stat.observed_sum_ds), _ptr(stat.size_s), _ptr(size_ds), D, S, a0, b0,
+                                             out_target, _ptr(mean), _ptr(sd), _ptr(lm), _ptr(ls)))
         return CollapsedOut(mu_observed=dict(mean=mean, sd=sd, log_mean=lm, log_sd=ls), mu_adjusted=None,
                             mu_residual=None, gamma=None, delta=None)
     mu_obs, mu_adj, mu_res, gam, delta = new(), new(), new(), new(), new((B, D))
     lm = new() if out_target != TARGET_MEAN_ONLY else None
-    ctx.check(lib.lg_optimize_batched(ctx.h, _ptr(stat.observed_sum_ds), _ptr(stat.imputed_sum_ds),
-                                      _ptr(stat.residual_sum_ds), _ptr(stat.size_s), _ptr(stat.observed_sum_db),
-                                      _ptr(stat.n_bs), D, S, B, a0, b0, num_iter, out_target, _ptr(mu_obs), _ptr(mu_adj),
-                                      _ptr(mu_res), _ptr(gam), _ptr(delta), _ptr(lm)))
+    size_ds = None if stat.size_ds is None else _as(stat.size_ds, np.float32)
+    mask = None if stat.obs_mask_db is None else _as(stat.obs_mask_db, np.float32)
+    ctx.check(lib.lg_optimize_batched_obs(ctx.h, _ptr(stat.observed_sum_ds), _ptr(stat.imputed_sum_ds),
+                                          _ptr(stat.residual_sum_ds), _ptr(stat.size_s), _ptr(size_ds),
+                                          _ptr(stat.observed_sum_db), _ptr(stat.n_bs), _ptr(mask), D, S, B, a0, b0, num_iter,
+                                          out_target, _ptr(mu_obs), _ptr(mu_adj), _ptr(mu_res), _ptr(gam), _ptr(delta),
+                                          _ptr(lm)))
     return CollapsedOut(mu_observed=dict(mean=mu_obs), mu_adjusted=dict(mean=mu_adj, log_mean=lm),
                         mu_residual=dict(mean=mu_res), gamma=dict(mean=gam), delta=dict(mean=delta))
 
@@ -604,6 +676,8 @@ class SparseIoVec:
         self.multiplicity = None      # float32[N] or None
         self.batch_proj = None        # (N, K) features the per-batch kNN dictionaries were built on
         self.between_batch_proximity = None  # uint32 (B, B) or None (batch.rs:176-178: only when B > 2)
+        self.row_coverage = None      # bool (nbackends, D): which rows every backend measures; None = all of them
+        self.col_source = None        # uint32[N]: the backend every column came from
 
     @classmethod
     def from_csc(cls, ctx, indptr, indices, data, nrows):
@@ -618,13 +692,46 @@ class SparseIoVec:
         (a remap that is not monotone leaves a column unsorted, a many-to-one remap leaves duplicate rows: sorted and
         summed, read.rs:246-281); the blocks are then joined on the device (lg_csc_concat)."""
         blocks = [CscBlock.upload(ctx, ip, ix, v, nrows, row_remap=remap) for ip, ix, v, remap in backends]
+        # row_coverage_by_backend / column_source (sparse_io_vector/mod.rs:378-403): a backend without a remap measures
+        # every row, one with a remap the rows its map reaches
+        cov = np.ones((len(backends), nrows), bool)
+        for d, (_, _, _, remap) in enumerate(backends):
+            if remap is not None:
+                r = np.asarray(remap).astype(np.int64)
+                cov[d] = False
+                cov[d, r[(r >= 0) & (r < nrows)]] = True
+        src = np.concatenate([np.full(b.ncols, d, np.uint32) for d, b in enumerate(blocks)]) if blocks else np.zeros(0, np.uint32)
         if len(blocks) == 1:
-            return cls(ctx, blocks[0])
-        out = CscBlock.concat(ctx, blocks)
-        ctx.sync()
-        for b in blocks:
-            b.free()
-        return cls(ctx, out)
+            out = cls(ctx, blocks[0])
+        else:
+            blk = CscBlock.concat(ctx, blocks)
+            ctx.sync()
+            for b in blocks:
+                b.free()
+            out = cls(ctx, blk)
+        out.row_coverage, out.col_source = (cov if not cov.all() else None), src
+        return out
+
+    def row_coverage_by_backend(self):
+        return self.row_coverage
+
+    def attach_observability(self, stat: "CollapsedStat"):
+        """collapse_data/mod.rs:221-301: no-op when every backend measures every row"""
+        cov = self.row_coverage_by_backend()
+        if cov is None:
+            return
+        S, B, D = stat.num_samples(), stat.num_batches(), self.num_rows()
+        grp = _as(self.get_group_membership(), np.uint32)
+        bat = None if self.col_to_batch is None or B == 0 else _as(self.col_to_batch, np.uint32)
+        size_ds = np.empty((S, D), np.float32)
+        mask = np.empty((B, D), np.float32) if bat is not None else None
+        has_zero = C.c_int(0)
+        self.ctx.check(lib.lg_attach_observability(self.ctx.h, _ptr(np.ascontiguousarray(cov, np.uint8)), cov.shape[0],
+                                                   _ptr(self.col_source), _ptr(grp), _ptr(bat), _ptr(self.multiplicity),
+                                                   self.num_columns(), D, S, B, _ptr(size_ds), _ptr(mask),
+                                                   C.byref(has_zero) if mask is not None else None))
+        stat.size_ds = size_ds
+        stat.obs_mask_db = mask if (mask is not None and has_zero.value) else None
 
     def num_rows(self):
         return self.block.nrows
@@ -827,11 +934,12 @@ class SparseIoVec:
                                       DEFAULT_KNN if knn_cells is None else knn_cells, ref, stat)
         return optimize(self.ctx, stat, (1.0, 1.0), num_opt_iter or DEFAULT_OPT_ITER, out_target), stat
 
-    # ---- MultilevelCollapsingOps (collapse_data/mod.rs:867-1050, un-refined path) ----
-    def collapse_columns_multilevel_vec(self, proj_kn, batch_membership, params: MultilevelParams):
-        """returns (levels finest-first: list of CollapsedOut, list of CollapsedStat)"""
-        if params.refine is not None:
-            raise LegumeError(1, "BBKNN + DC-SBM refinement is outside the hot path (SURVEY.md §8f rank 3)")
+    # ---- MultilevelCollapsingOps (collapse_data/mod.rs:503-1050) ----
+    def _multilevel_prologue(self, proj_kn, batch_membership, params):
+        """what all three entries share (mod.rs:542-560, 640-662, 876-910): batches, per-batch dictionaries, level dims,
+        finest codes, finest hash groups"""
+        if params.anchor_batches or params.bulk_batches:
+            raise LegumeError(1, "anchor / bulk batches are outside the hot path (pb_samples.rs:75-88)")
         ctx = self.ctx
         proj_kn = _as(proj_kn, np.float32)
         n, K = proj_kn.shape
@@ -846,31 +954,130 @@ class SparseIoVec:
         group, ng = assign_groups_from_codes(ctx, codes_h, kk)
         self.col_to_group, self.binary_codes = group, codes_h
         self.group_keys = sorted({str(int(c)) for c in np.unique(codes_h)}, key=lambda s: s.encode())
+        return proj_kn, nb, level_dims, codes_h, np.asarray(group), ng
+
+    def _build_pb_samples(self, proj_kn, group, ng, nb):
+        """pb_samples.rs:274-307: layout + per-pb-sample gene sums"""
+        ctx = self.ctx
+        bat = self.col_to_batch if self.col_to_batch is not None else np.zeros(self.num_columns(), np.uint32)
+        layout = build_pb_sample_layout(ctx, group, ng, bat, max(nb, 1), proj_kn, self.multiplicity)
+        gs = CollapsedStat(self.num_rows(), layout.num_pb, 1)
+        ctx.check(lib.lg_collapse_basic(ctx.h, self.block.h, _ptr(layout.cell_to_pbsamp), _ptr(self.multiplicity),
+                                        layout.num_pb, _ptr(gs.observed_sum_ds), _ptr(gs.size_s)))
+        return layout, gs.observed_sum_ds
+
+    def _merge_level(self, prev: CollapsedStat, f2c, nc, nb):
+        """merge_stat (stats.rs:790-833): sums, sizes and effective sizes add per coarse group in ascending fine index"""
+        ctx = self.ctx
+        coarse = CollapsedStat(self.num_rows(), nc, nb)
+        for name in ("observed_sum_ds", "imputed_sum_ds", "residual_sum_ds"):
+            setattr(coarse, name, merge_stat(ctx, getattr(prev, name), f2c, nc))
+        prev_n = len(f2c)
+        size, nbs = np.zeros(nc, np.float32), np.zeros((nc, max(nb, 1)), np.float32)
+        psize, pnbs = np.asarray(prev.size_s, np.float32), np.asarray(prev.n_bs, np.float32).reshape(prev_n, -1)
+        for f, c in enumerate(f2c):  # ascending fine index, f32 adds (stats.rs:813-816)
+            size[c] += psize[f]
+            nbs[c] += pnbs[f]
+        coarse.size_s, coarse.n_bs = size, nbs
+        coarse.observed_sum_db = prev.observed_sum_db
+        if prev.size_ds is not None:
+            coarse.size_ds = merge_stat(ctx, prev.size_ds, f2c, nc)
+        coarse.obs_mask_db = prev.obs_mask_db
+        return coarse
+
+    def _collect_refined_levels(self, proj_kn, nb, layout, gene_sums, p2g_levels, k_levels, params, target):
+        """the post-refinement tail shared by refine_and_collect_single_layer (refine.rs:380-500) and
+        collapse_columns_multilevel_with_partition (mod.rs:715-815): finest groups from the pb-sample partition, one data
+        pass for the finest statistics, merge_stat descent, the per-level cell -> pb map"""
+        ctx = self.ctx
+        c2p = np.asarray(layout.cell_to_pbsamp).astype(np.int64)
+        k0 = k_levels[0]
+        fine = np.asarray(p2g_levels[0], np.uint32)[c2p]
+        # pad_numeric_labels + assign_groups (refine.rs:21-35, groups.rs:13-37): the rank of a zero-padded number is the number
+        self.col_to_group, self.group_keys = fine, pad_numeric_labels(range(k0), k0)
+        fine_stat = CollapsedStat(self.num_rows(), k0, nb)
+        self.collect_basic_stat(fine_stat)
+        if nb >= 2:
+            self.collect_batch_stat(fine_stat)
+            matched = per_batch_sc_neighbors(ctx, layout, proj_kn, self.col_to_batch, nb, params.knn_pb_samples)
+            collect_matched_stat_coarse(ctx, layout, gene_sums, p2g_levels[0], matched, fine_stat)
+        if params.observe_panels:
+            self.attach_observability(fine_stat)
+        outs = [optimize(ctx, fine_stat, (1.0, 1.0), params.num_opt_iter, target)]
+        stats = [fine_stat]
+        prev = fine_stat
+        for level in range(1, len(k_levels)):
+            f2c = fine_to_coarse_from_refined(p2g_levels[level - 1], p2g_levels[level], k_levels[level - 1])
+            coarse = self._merge_level(prev, f2c, k_levels[level], nb)
+            outs.append(optimize(ctx, coarse, (1.0, 1.0), max(params.num_opt_iter // 2, 10), target))
+            stats.append(coarse)
+            prev = coarse
+        cell_to_pb = [np.asarray(p2g, np.uint32)[c2p] for p2g in p2g_levels]
+        return dict(levels=outs, cell_to_pb_per_level=cell_to_pb, stats=stats)
+
+    def _refine_and_collect(self, proj_kn, nb, level_dims, codes_h, group, ng, params):
+        """refine_and_collect_single_layer (refine.rs:264-500).  refine_or_identity(num_batches >= 2, ..): with one batch
+        the refined assignment is the compacted hash partition of every level"""
+        if nb >= 2:
+            raise LegumeError(1, "BBKNN + DC-SBM refinement over two or more batches is outside the hot path (SURVEY.md "
+                                 "section 8f rank 3); pass MultilevelParams(refine=None) or inherit a partition")
+        layout, gene_sums = self._build_pb_samples(proj_kn, group, ng, nb)
+        c2p = np.asarray(layout.cell_to_pbsamp).astype(np.int64)
+        first = np.full(layout.num_pb, len(c2p), np.int64)
+        np.minimum.at(first, c2p, np.arange(len(c2p)))  # a pb-sample's first cell (pb_samples.rs:472-481)
+        p2g = initial_per_level_from_hash(codes_h, first, level_dims)
+        p2g, k = zip(*(compact_labels(l) for l in p2g))
+        return self._collect_refined_levels(proj_kn, nb, layout, gene_sums, list(p2g), list(k), params,
+                                            params.output_calibration)
+
+    def collapse_columns_multilevel_with_hierarchy(self, proj_kn, batch_membership, params: MultilevelParams):
+        """collapse_data/mod.rs:534-607: the levels plus the per-level cell -> pb map; needs params.refine"""
+        if params.refine is None:
+            raise LegumeError(1, "collapse_columns_multilevel_with_hierarchy requires MultilevelParams.refine = Some(..); "
+                                 "the legacy non-refinement path doesn't surface per-level cell->pb mappings")
+        proj_kn, nb, level_dims, codes_h, group, ng = self._multilevel_prologue(proj_kn, batch_membership, params)
+        return self._refine_and_collect(proj_kn, nb, level_dims, codes_h, group, ng, params)
+
+    def collapse_columns_multilevel_with_partition(self, proj_kn, batch_membership, params: MultilevelParams,
+                                                   cell_to_pb_per_level):
+        """collapse_data/mod.rs:617-821: skip the refinement and take every level's pb-sample -> group from an inherited
+        cell -> pb map (finest first) by majority vote inside each pb-sample"""
+        proj_kn, nb, level_dims, codes_h, group, ng = self._multilevel_prologue(proj_kn, batch_membership, params)
+        if len(cell_to_pb_per_level) != len(level_dims):
+            raise LegumeError(1, f"inherited cell_to_pb has {len(cell_to_pb_per_level)} levels but --num-levels is "
+                                 f"{len(level_dims)}; pass --num-levels to match the source run")
+        layout, gene_sums = self._build_pb_samples(proj_kn, group, ng, nb)
+        p2g, k = [], []
+        for i, lvl in enumerate(cell_to_pb_per_level):
+            if len(lvl) != self.num_columns():
+                raise LegumeError(1, f"inherited cell_to_pb level {i} has {len(lvl)} cells, data has {self.num_columns()}")
+            compact, kl = compact_labels(modal_groups(layout.cell_to_pbsamp, layout.num_pb, lvl))
+            p2g.append(compact)
+            k.append(kl)
+        return self._collect_refined_levels(proj_kn, nb, layout, gene_sums, p2g, k, params, TARGET_ALL)
+
+    def collapse_columns_multilevel_vec(self, proj_kn, batch_membership, params: MultilevelParams):
+        """collapse_data/mod.rs:867-1046; returns (levels finest-first: list of CollapsedOut, list of CollapsedStat)"""
+        proj_kn, nb, level_dims, codes_h, group, ng = self._multilevel_prologue(proj_kn, batch_membership, params)
+        ctx = self.ctx
+        if params.refine is not None:  # mod.rs:914-941
+            out = self._refine_and_collect(proj_kn, nb, level_dims, codes_h, group, ng, params)
+            return out["levels"], out["stats"]
         fine_stat = CollapsedStat(self.num_rows(), ng, nb)
         self.collect_basic_stat(fine_stat)
         if nb >= 2:
             self.collect_batch_stat(fine_stat)
-            layout = build_pb_sample_layout(ctx, group, ng, self.col_to_batch, nb, proj_kn, self.multiplicity)
-            gs = CollapsedStat(self.num_rows(), layout.num_pb, 1)
-            ctx.check(lib.lg_collapse_basic(ctx.h, self.block.h, _ptr(layout.cell_to_pbsamp), _ptr(self.multiplicity),
-                                            layout.num_pb, _ptr(gs.observed_sum_ds), _ptr(gs.size_s)))
+            layout, gene_sums = self._build_pb_samples(proj_kn, group, ng, nb)
             matched = per_batch_sc_neighbors(ctx, layout, proj_kn, self.col_to_batch, nb, params.knn_pb_samples)
-            collect_matched_stat_coarse(ctx, layout, gs.observed_sum_ds, layout.pb_sample_to_group, matched, fine_stat)
+            collect_matched_stat_coarse(ctx, layout, gene_sums, layout.pb_sample_to_group, matched, fine_stat)
+        if params.observe_panels:
+            self.attach_observability(fine_stat)
         outs = [optimize(ctx, fine_stat, (1.0, 1.0), params.num_opt_iter, TARGET_ALL)]
         stats = [fine_stat]
-        prev, prev_group, prev_n = fine_stat, np.asarray(group), ng
+        prev, prev_group, prev_n = fine_stat, group, ng
         for dim in level_dims[1:]:
             f2c, nc = compute_fine_to_coarse_mapping(ctx, codes_h, prev_group, prev_n, dim)
-            coarse = CollapsedStat(self.num_rows(), nc, nb)
-            for name in ("observed_sum_ds", "imputed_sum_ds", "residual_sum_ds"):
-                setattr(coarse, name, merge_stat(ctx, getattr(prev, name), f2c, nc))
-            size, nbs = np.zeros(nc, np.float32), np.zeros((nc, max(nb, 1)), np.float32)
-            psize, pnbs = np.asarray(prev.size_s, np.float32), np.asarray(prev.n_bs, np.float32).reshape(prev_n, -1)
-            for f, c in enumerate(f2c):  # ascending fine index, f32 adds (stats.rs:813-816)
-                size[c] += psize[f]
-                nbs[c] += pnbs[f]
-            coarse.size_s, coarse.n_bs = size, nbs
-            coarse.observed_sum_db = prev.observed_sum_db
+            coarse = self._merge_level(prev, f2c, nc, nb)
             outs.append(optimize(ctx, coarse, (1.0, 1.0), max(params.num_opt_iter // 2, 10), TARGET_ALL))
             stats.append(coarse)
             prev, prev_group, prev_n = coarse, f2c[prev_group], nc

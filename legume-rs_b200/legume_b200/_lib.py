@@ -71,6 +71,10 @@ _sig = {
     "lg_merge_stat": [_vp, _vp, _u64, _u32, _vp, _u32, _vp],
     "lg_gamma_calibrate": [_vp, _vp, _vp, _u64, _f, _f, _i, _vp, _vp, _vp, _vp],
     "lg_optimize_single": [_vp, _vp, _vp, _u64, _u32, _f, _f, _i, _vp, _vp, _vp, _vp],
+    "lg_optimize_single_obs": [_vp, _vp, _vp, _vp, _u64, _u32, _f, _f, _i, _vp, _vp, _vp, _vp],
+    "lg_optimize_batched_obs": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _u64, _u32, _u32, _f, _f, _i, _i, _vp, _vp, _vp,
+                                _vp, _vp, _vp],
+    "lg_attach_observability": [_vp, _vp, _u32, _vp, _vp, _vp, _vp, _u64, _u64, _u32, _u32, _vp, _vp, _vp],
     "lg_optimize_batched": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _u64, _u32, _u32, _f, _f, _i, _i, _vp, _vp, _vp, _vp,
                             _vp, _vp],
     "lg_knn_topk": [_vp, _vp, _u64, _vp, _u64, _i, _i, _vp, _vp, _vp],

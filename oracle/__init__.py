@@ -272,6 +272,110 @@ def optimize_batched(obs, imp, res, size_s, obs_db, n_bs, a0=1.0, b0=1.0, num_it
                 mu_adjusted_log_mean=lm)
 
 
+def optimize_single_obs(sum_ds, size_s, size_ds, a0=1.0, b0=1.0, target=TARGET_ALL):
+    """optimize_block, B <= 1 arm, with per-(gene, sample) effective sizes (stats.rs:176-186, 351-368)"""
+    sum_ds = np.ascontiguousarray(sum_ds, np.float32)
+    size_s = np.ascontiguousarray(size_s, np.float32)
+    size_ds = None if size_ds is None else np.ascontiguousarray(size_ds, np.float32)
+    S, D = sum_ds.shape
+    outs = [np.zeros_like(sum_ds) for _ in range(4)]
+    lib().orc_optimize_single_obs(_ptr(sum_ds, C.c_float), _ptr(size_s, C.c_float),
+                                  None if size_ds is None else _ptr(size_ds, C.c_float), C.c_uint64(D), C.c_uint32(S),
+                                  C.c_float(a0), C.c_float(b0), C.c_int(target), *[_ptr(o, C.c_float) for o in outs])
+    return dict(mean=outs[0], sd=outs[1], log_mean=outs[2], log_sd=outs[3])
+
+
+def optimize_batched_obs(obs, imp, res, size_s, size_ds, obs_db, n_bs, mask_db, a0=1.0, b0=1.0, num_iter=30, target=TARGET_ALL):
+    """optimize_block, B > 1 arm, with size_ds (S, D) and obs_mask_db (B, D), either may be None (stats.rs:176-204, 299-322)"""
+    obs, imp, res = (np.ascontiguousarray(x, np.float32) for x in (obs, imp, res))
+    size_s, obs_db, n_bs = (np.ascontiguousarray(x, np.float32) for x in (size_s, obs_db, n_bs))
+    size_ds = None if size_ds is None else np.ascontiguousarray(size_ds, np.float32)
+    mask_db = None if mask_db is None else np.ascontiguousarray(mask_db, np.float32)
+    S, D = obs.shape
+    B = obs_db.shape[0]
+    mu_obs, mu_adj, mu_res, gam, lm = [np.zeros_like(obs) for _ in range(5)]
+    delta = np.zeros_like(obs_db)
+    fp = lambda x: None if x is None else _ptr(x, C.c_float)
+    lib().orc_optimize_batched_obs(fp(obs), fp(imp), fp(res), fp(size_s), fp(size_ds), fp(obs_db), fp(n_bs), fp(mask_db),
+                                   C.c_uint64(D), C.c_uint32(S), C.c_uint32(B), C.c_float(a0), C.c_float(b0),
+                                   C.c_int(num_iter), C.c_int(target), fp(mu_obs), fp(mu_adj), fp(mu_res), fp(gam),
+                                   fp(delta), fp(lm))
+    return dict(mu_observed=mu_obs, mu_adjusted=mu_adj, mu_residual=mu_res, gamma=gam, delta=delta,
+                mu_adjusted_log_mean=lm)
+
+
+def attach_observability(coverage, source, group, batch, mult, S, B):
+    """collapse_data/mod.rs:221-301 restated loop for loop.  coverage: (nsrc, D) bool; source / group / batch: per column.
+    Returns (size_ds (S, D) f32, mask_db (B, D) f32 or None when no entry is zero)."""
+    coverage = np.asarray(coverage, bool)
+    nsrc, D = coverage.shape
+    count_bs = np.zeros((nsrc, S), np.float32)
+    used = np.zeros((nsrc, B), bool)
+    for c in range(len(source)):
+        s = int(group[c])
+        if s < S:
+            count_bs[source[c], s] = np.float32(count_bs[source[c], s] + np.float32(1.0 if mult is None else mult[c]))
+        if batch is not None and int(batch[c]) < B:
+            used[source[c], int(batch[c])] = True
+    size_ds = np.zeros((S, D), np.float32)
+    for src in range(nsrc):
+        for g in np.nonzero(coverage[src])[0]:
+            size_ds[:, g] = size_ds[:, g] + count_bs[src]
+    mask = np.zeros((B, D), np.float32)
+    for src in range(nsrc):
+        for b in np.nonzero(used[src])[0]:
+            mask[b, coverage[src]] = 1.0
+    return size_ds, (mask if (mask == 0.0).any() else None)
+
+
+# ---- refine.rs / dc_poisson.rs helpers of the refinement arm without refinement (B = 1, inherited partitions) ----------
+def compact_labels(labels):
+    """dc_poisson.rs:493-509: labels -> 0..k in order of first appearance"""
+    lut, out = {}, []
+    for g in labels:
+        out.append(lut.setdefault(int(g), len(lut)))
+    return np.array(out, np.uint32), len(lut)
+
+
+def pb_sample_to_cells(cell_to_pb, num_pb):
+    """pb_samples.rs:472-481"""
+    out = [[] for _ in range(num_pb)]
+    for c, p in enumerate(cell_to_pb):
+        if int(p) != 0xFFFFFFFF:
+            out[int(p)].append(c)
+    return out
+
+
+def initial_per_level_from_hash(fine_codes, pb_cells, level_dims):
+    """refine.rs:68-88: every level's pb-sample -> group from the finest code of the pb-sample's first cell, masked"""
+    out = []
+    for d in level_dims:
+        mask = 0xFFFFFFFFFFFFFFFF if d >= 64 else (1 << d) - 1
+        out.append(compact_labels([int(fine_codes[cells[0]]) & mask for cells in pb_cells])[0])
+    return out
+
+
+def fine_to_coarse_from_refined(p2f, p2c, num_fine):
+    """refine.rs:43-62: the coarse label of the first pb-sample of every fine group"""
+    m = np.full(num_fine, 0xFFFFFFFF, np.uint32)
+    for p in range(len(p2f)):
+        if m[p2f[p]] == 0xFFFFFFFF:
+            m[p2f[p]] = p2c[p]
+    return m
+
+
+def modal_group(cells, lvl):
+    """collapse_data/mod.rs:823-841; among equally frequent labels the reference takes whichever its hash map yields last
+    (unspecified) - the oracle fixes the smallest label"""
+    if not cells:
+        return 0
+    cnt = {}
+    for c in cells:
+        cnt[int(lvl[c])] = cnt.get(int(lvl[c]), 0) + 1
+    best = max(cnt.values())
+    return min(g for g, n in cnt.items() if n == best)
+
+
 # ---- stage 6 -------------------------------------------------------------------------------
 def l2_sq(a, b):
     a = np.ascontiguousarray(a, np.float32)

@@ -538,14 +538,20 @@ extern "C" void orc_gamma_calibrate(const float* num, const float* den, uint64_t
     }
 }
 
-/* stats.rs:351-368 (B <= 1 arm) */
+/* stats.rs:351-368 (B <= 1 arm); size_ds (optional, D x S): add_effective_size with observability attached (:176-186) */
+extern "C" void orc_optimize_single_obs(const float* sum_ds, const float* size_s, const float* size_ds, uint64_t D, uint32_t S,
+                                        float a0, float b0, int target, float* mean, float* sd, float* log_mean, float* log_sd);
 extern "C" void orc_optimize_single(const float* sum_ds, const float* size_s, uint64_t D, uint32_t S, float a0,
                                     float b0, int target, float* mean, float* sd, float* log_mean, float* log_sd) {
+    orc_optimize_single_obs(sum_ds, size_s, nullptr, D, S, a0, b0, target, mean, sd, log_mean, log_sd);
+}
+extern "C" void orc_optimize_single_obs(const float* sum_ds, const float* size_s, const float* size_ds, uint64_t D, uint32_t S,
+                                        float a0, float b0, int target, float* mean, float* sd, float* log_mean, float* log_sd) {
     std::vector<float> den(D);
     for (uint32_t s = 0; s < S; ++s) {
-        // add_effective_size: denom (zeros) + size_s[s]
-        for (uint64_t g = 0; g < D; ++g) den[g] = 0.0f + size_s[s];
+        // add_effective_size: denom (zeros) + size_s[s], or + size_ds[:, s]
         const size_t off = (size_t)s * D;
+        for (uint64_t g = 0; g < D; ++g) den[g] = 0.0f + (size_ds ? size_ds[off + g] : size_s[s]);
         orc_gamma_calibrate(sum_ds + off, den.data(), D, a0, b0, target, mean ? mean + off : nullptr,
                             sd ? sd + off : nullptr, log_mean ? log_mean + off : nullptr,
                             log_sd ? log_sd + off : nullptr);
@@ -555,15 +561,29 @@ extern "C" void orc_optimize_single(const float* sum_ds, const float* size_s, ui
     }
 }
 
-/* stats.rs:219-350 (B > 1 arm) */
+/* stats.rs:219-350 (B > 1 arm); size_ds (optional): per-(gene, sample) effective sizes (:176-204); mask_db (optional,
+ * D x B): both sides of the delta ratio are multiplied by it (:299-322) */
+extern "C" void orc_optimize_batched_obs(const float* obs, const float* imp, const float* res, const float* size_s,
+                                         const float* size_ds, const float* obs_db, const float* n_bs, const float* mask_db,
+                                         uint64_t D, uint32_t S, uint32_t B, float a0, float b0, int num_iter, int target,
+                                         float* mu_obs, float* mu_adj, float* mu_res, float* gamma, float* delta,
+                                         float* mu_adj_log_mean);
 extern "C" void orc_optimize_batched(const float* obs, const float* imp, const float* res, const float* size_s,
                                      const float* obs_db, const float* n_bs, uint64_t D, uint32_t S, uint32_t B,
                                      float a0, float b0, int num_iter, int target, float* mu_obs, float* mu_adj,
                                      float* mu_res, float* gamma, float* delta, float* mu_adj_log_mean) {
+    orc_optimize_batched_obs(obs, imp, res, size_s, nullptr, obs_db, n_bs, nullptr, D, S, B, a0, b0, num_iter, target, mu_obs,
+                             mu_adj, mu_res, gamma, delta, mu_adj_log_mean);
+}
+extern "C" void orc_optimize_batched_obs(const float* obs, const float* imp, const float* res, const float* size_s,
+                                         const float* size_ds, const float* obs_db, const float* n_bs, const float* mask_db,
+                                         uint64_t D, uint32_t S, uint32_t B, float a0, float b0, int num_iter, int target,
+                                         float* mu_obs, float* mu_adj, float* mu_res, float* gamma, float* delta,
+                                         float* mu_adj_log_mean) {
     const size_t n = (size_t)D * S;
     // GammaMatrix::new starts estimated_mean at zero (dmatrix_gamma.rs:49-52) and a_stat/b_stat at (a0, b0)
     std::vector<float> m_res(n), m_gam(n, 0.0f), m_adj(n, 0.0f), a_adj(n, a0), b_adj(n, b0);
-    auto sz = [&](size_t e) { return size_s[e / D]; };
+    auto sz = [&](size_t e) { return size_ds ? size_ds[e] : size_s[e / D]; };
     // :240-247 mu_resid = Gamma(a0 + residual, b0 + (0 + size))
     for (size_t e = 0; e < n; ++e) m_res[e] = (a0 + res[e]) / (b0 + (0.0f + sz(e)));
     for (int it = 0; it < num_iter; ++it) {
@@ -584,7 +604,12 @@ extern "C" void orc_optimize_batched(const float* obs, const float* imp, const f
             for (uint64_t g = 0; g < D; ++g) {
                 float acc = 0.0f;
                 for (uint32_t s = 0; s < S; ++s) acc = fmaf(m_adj[(size_t)s * D + g], n_bs[(size_t)s * B + b], acc);
-                delta[(size_t)b * D + g] = (a0 + obs_db[(size_t)b * D + g]) / (b0 + acc);
+                float num = obs_db[(size_t)b * D + g];
+                if (mask_db) {  // denom_db.component_mul_assign(mask); num_db = observed_sum_db .* mask
+                    acc = acc * mask_db[(size_t)b * D + g];
+                    num = num * mask_db[(size_t)b * D + g];
+                }
+                delta[(size_t)b * D + g] = (a0 + num) / (b0 + acc);
             }
     }
     for (size_t e = 0; e < n; ++e) {

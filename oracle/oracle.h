@@ -80,6 +80,13 @@ void orc_gamma_calibrate(const float* num, const float* den, uint64_t n, float a
 /* single-batch optimize_block (B<=1 arm): denom = size_s broadcast, optional sparsify */
 void orc_optimize_single(const float* sum_ds, const float* size_s, uint64_t D, uint32_t S, float a0, float b0,
                          int target, float* mean, float* sd, float* log_mean, float* log_sd);
+/* the two arms with panel observability attached (stats.rs:176-204, 299-322): size_ds / mask_db may be NULL */
+void orc_optimize_single_obs(const float* sum_ds, const float* size_s, const float* size_ds, uint64_t D, uint32_t S, float a0,
+                             float b0, int target, float* mean, float* sd, float* log_mean, float* log_sd);
+void orc_optimize_batched_obs(const float* obs_ds, const float* imp_ds, const float* res_ds, const float* size_s,
+                              const float* size_ds, const float* obs_db, const float* n_bs, const float* mask_db, uint64_t D,
+                              uint32_t S, uint32_t B, float a0, float b0, int num_iter, int target, float* mu_obs, float* mu_adj,
+                              float* mu_res, float* gamma, float* delta, float* mu_adj_log_mean);
 /* batched optimize_block (B>1 arm), means only + optional log planes of mu_adj.
  * outs: each D×S (delta D×B); any may be NULL. */
 void orc_optimize_batched(const float* obs_ds, const float* imp_ds, const float* res_ds, const float* size_s,

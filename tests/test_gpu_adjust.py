@@ -221,7 +221,7 @@ def test_collapse_columns_multilevel_matches_oracle(lg, ctx):
     D, N, B, K = 500, 4000, 3, 20
     ip, ix, v, proj, batch, _ = make_case(11, D, N, B, 4, K, clustered=True)
     data = lg.SparseIoVec.from_csc(ctx, ip, ix, v, D)
-    params = lg.MultilevelParams(K, knn_pb_samples=4, num_levels=2, sort_dim=8, num_opt_iter=12)
+    params = lg.MultilevelParams(K, knn_pb_samples=4, num_levels=2, sort_dim=8, num_opt_iter=12, refine=None)
     outs, stats = data.collapse_columns_multilevel_vec(proj, batch, params)
     dims = orc.level_sort_dims(8, 2)
     assert len(outs) == len(dims) == 2
@@ -253,6 +253,187 @@ def test_collapse_columns_multilevel_matches_oracle(lg, ctx):
     assert np.array_equal(stats[1].size_s, csize) and np.array_equal(stats[1].n_bs, cnbs)
     want1 = orc.optimize_batched(cobs, cimp, cres, csize, obs_db, cnbs, 1.0, 1.0, 10, 0)
     assert close(outs[1].mu_adjusted["mean"], want1["mu_adjusted"], 1e-4)
+
+
+def _oracle_refined_levels(ip, ix, v, D, proj, batch, B, codes, dims, p2g_levels, k_levels, lay, knn, iters, size_ds=None,
+                           mask=None):
+    """the tail of refine_and_collect_single_layer / ..._with_partition on the oracle (refine.rs:380-500, mod.rs:715-815)"""
+    c2p = lay["cell_to_pb"].astype(np.int64)
+    fine = p2g_levels[0][c2p].astype(np.uint32)
+    S = k_levels[0]
+    obs, size = orc.collapse_basic(ip, ix, v, D, fine, S)
+    imp, res = np.zeros_like(obs), np.zeros_like(obs)
+    obs_db = n_bs = None
+    if B >= 2:
+        obs_db, n_bs = orc.collapse_batch(ip, ix, v, D, fine, batch, S, B)
+        gs, _ = orc.collapse_basic(ip, ix, v, D, lay["cell_to_pb"], lay["num_pb"])
+        mp, md = orc.pb_match(proj, batch, B, lay, knn)
+        imp, res = orc.collect_matched_stat_coarse(gs, lay["pb_count"], p2g_levels[0], S, mp, md)
+    levels = []
+    for level in range(len(k_levels)):
+        it = iters if level == 0 else max(iters // 2, 10)
+        if level > 0:
+            f2c = orc.fine_to_coarse_from_refined(p2g_levels[level - 1], p2g_levels[level], k_levels[level - 1])
+            nc = k_levels[level]
+            obs, imp, res = (orc.merge_stat(x, f2c, nc) for x in (obs, imp, res))
+            csize = np.zeros(nc, np.float32)
+            cnbs = None if n_bs is None else np.zeros((nc, B), np.float32)
+            for f, c in enumerate(f2c):
+                csize[c] += size[f]
+                if cnbs is not None:
+                    cnbs[c] += n_bs[f]
+            size, n_bs = csize, cnbs
+            if size_ds is not None:
+                size_ds = orc.merge_stat(size_ds, f2c, nc)
+        if B >= 2:
+            fit = orc.optimize_batched_obs(obs, imp, res, size, size_ds, obs_db, n_bs, mask, 1.0, 1.0, it, 0)
+        else:
+            fit = orc.optimize_single_obs(obs, size, size_ds, 1.0, 1.0, 0)
+        levels.append(dict(obs=obs, imp=imp, res=res, size=size, n_bs=n_bs, fit=fit))
+    return levels, fine
+
+
+def test_multilevel_refine_arm_single_batch(lg, ctx):
+    """MultilevelParams::new has refine = Some(..) (collapse_data/mod.rs:115-130): with one batch refine_or_identity keeps the
+    compacted hash partition of every level (refine.rs:126-147, 68-88) and the statistics descend by merge_stat along
+    fine_to_coarse_from_refined; collapse_columns_multilevel_with_hierarchy adds the per-level cell -> pb map"""
+    D, N, K = 400, 3000, 20
+    ip, ix, v, proj, _, _ = make_case(21, D, N, 1, 4, K, clustered=True)
+    batch = np.zeros(N, np.uint32)
+    data = lg.SparseIoVec.from_csc(ctx, ip, ix, v, D)
+    params = lg.MultilevelParams(K, knn_pb_samples=4, num_levels=3, sort_dim=9, num_opt_iter=12)
+    assert params.refine is not None and params.observe_panels
+    out = data.collapse_columns_multilevel_with_hierarchy(proj, batch, params)
+    dims = orc.level_sort_dims(9, 3)
+    assert len(out["levels"]) == len(dims) == 3
+    codes = orc.binary_codes(proj, dims[0])
+    grp, S = orc.assign_groups(codes)
+    lay = orc.pb_layout(proj, grp, S, batch, 1)
+    cells = orc.pb_sample_to_cells(lay["cell_to_pb"], lay["num_pb"])
+    init = orc.initial_per_level_from_hash(codes, cells, dims)
+    p2g, k = zip(*(orc.compact_labels(l) for l in init))
+    want, fine = _oracle_refined_levels(ip, ix, v, D, proj, batch, 1, codes, dims, list(p2g), list(k), lay, 4, 12)
+    assert np.array_equal(np.asarray(data.col_to_group), fine)
+    for level in range(3):
+        st, w = out["stats"][level], want[level]
+        assert np.array_equal(st.observed_sum_ds, w["obs"]) and np.array_equal(st.size_s, w["size"])
+        assert close(out["levels"][level].mu_observed["mean"], w["fit"]["mean"], TOL)
+        assert close(out["levels"][level].mu_observed["log_mean"], w["fit"]["log_mean"], TOL)
+        assert np.array_equal(out["cell_to_pb_per_level"][level], p2g[level][lay["cell_to_pb"].astype(np.int64)])
+    # the trait entry takes the same arm and returns the levels only
+    outs, stats = lg.SparseIoVec.from_csc(ctx, ip, ix, v, D).collapse_columns_multilevel_vec(proj, batch, params)
+    assert np.array_equal(stats[2].observed_sum_ds, want[2]["obs"])
+    # two or more batches would need the refinement itself
+    with pytest.raises(lg.LegumeError):
+        data.collapse_columns_multilevel_vec(proj, np.arange(N) % 2, params)
+    with pytest.raises(lg.LegumeError):
+        data.collapse_columns_multilevel_with_hierarchy(proj, batch, lg.MultilevelParams(K, refine=None))
+
+
+@pytest.mark.parametrize("B", [1, 3])
+def test_multilevel_with_inherited_partition(lg, ctx, B):
+    """collapse_columns_multilevel_with_partition (collapse_data/mod.rs:617-821): every level's pb-sample -> group is the
+    majority of an inherited cell -> pb map over the pb-sample's cells, compacted; no refinement even with several batches"""
+    D, N, K = 300, 2500, 16
+    ip, ix, v, proj, batch, _ = make_case(22 + B, D, N, B, 4, K, clustered=True)
+    rng = np.random.default_rng(3)
+    lvl0 = rng.integers(0, 40, N)
+    inherited = [lvl0, lvl0 // 4]  # a hierarchy: the coarse label is a function of the fine one
+    data = lg.SparseIoVec.from_csc(ctx, ip, ix, v, D)
+    params = lg.MultilevelParams(K, knn_pb_samples=3, num_levels=2, sort_dim=8, num_opt_iter=14)
+    out = data.collapse_columns_multilevel_with_partition(proj, batch, params, inherited)
+    dims = orc.level_sort_dims(8, 2)
+    codes = orc.binary_codes(proj, dims[0])
+    grp, S = orc.assign_groups(codes)
+    lay = orc.pb_layout(proj, grp, S, batch, B)
+    cells = orc.pb_sample_to_cells(lay["cell_to_pb"], lay["num_pb"])
+    p2g, k = [], []
+    for lvl in inherited:
+        votes = [orc.modal_group(c, lvl) for c in cells]
+        compact, kl = orc.compact_labels(votes)
+        p2g.append(compact)
+        k.append(kl)
+    want, fine = _oracle_refined_levels(ip, ix, v, D, proj, batch, B, codes, dims, p2g, k, lay, 3, 14)
+    assert np.array_equal(np.asarray(data.col_to_group), fine)
+    for level in range(2):
+        st, w = out["stats"][level], want[level]
+        assert np.array_equal(st.observed_sum_ds, w["obs"]) and np.array_equal(st.size_s, w["size"])
+        if B >= 2:
+            assert close(st.imputed_sum_ds, w["imp"], TOL) and close(st.residual_sum_ds, w["res"], TOL)
+            assert np.array_equal(st.n_bs, w["n_bs"])
+            assert close(out["levels"][level].mu_adjusted["mean"], w["fit"]["mu_adjusted"], 1e-4)
+            assert close(out["levels"][level].delta["mean"], w["fit"]["delta"], 1e-4)
+        else:
+            assert close(out["levels"][level].mu_observed["mean"], w["fit"]["mean"], TOL)
+        assert np.array_equal(out["cell_to_pb_per_level"][level], p2g[level][lay["cell_to_pb"].astype(np.int64)])
+    with pytest.raises(lg.LegumeError):
+        data.collapse_columns_multilevel_with_partition(proj, batch, params, inherited[:1])
+
+
+@pytest.mark.parametrize("B", [1, 2])
+def test_panel_observability(lg, ctx, B):
+    """attach_observability (collapse_data/mod.rs:221-301) + the size_ds / obs_mask_db arms of optimize_block
+    (stats.rs:176-204, 299-322): two backends with different gene panels side by side"""
+    rng = np.random.default_rng(31 + B)
+    D, K = 260, 12
+    panels = [np.sort(rng.choice(D, 200, replace=False)), np.sort(rng.choice(D, 170, replace=False))]
+    backends, cols = [], []
+    for pan, n in zip(panels, (900, 700)):
+        ip, ix, v = random_csc(rng, len(pan), n, density=0.1)
+        backends.append((ip, ix, v, pan.astype(np.uint32)))
+        cols.append((ip, pan[ix.astype(np.int64)].astype(np.uint64), v))
+    N = 1600
+    ip = np.concatenate([cols[0][0], cols[1][0][1:] + cols[0][0][-1]]).astype(np.uint64)
+    ix, v = np.concatenate([c[1] for c in cols]), np.concatenate([c[2] for c in cols])
+    data = lg.SparseIoVec.from_backends(ctx, backends, D)
+    cov = np.zeros((2, D), bool)
+    cov[0, panels[0]], cov[1, panels[1]] = True, True
+    assert np.array_equal(data.row_coverage_by_backend(), cov)
+    source = np.repeat([0, 1], [900, 700]).astype(np.uint32)
+    # batch 0 draws from backend 0 only when B == 2, so its delta mask has zeros
+    batch = source.copy() if B == 2 else np.zeros(N, np.uint32)
+    mult = rng.uniform(0.5, 2.0, N).astype(np.float32)
+    S = 9
+    grp = rng.integers(0, S, N).astype(np.uint32)
+    data.register_batch_membership(batch)
+    data.register_column_multiplicity(mult)
+    data.assign_groups([f"{g:02d}" for g in grp])
+    stat = lg.CollapsedStat(D, S, B)
+    data.collect_basic_stat(stat)
+    if B >= 2:
+        data.collect_batch_stat(stat)
+        stat.imputed_sum_ds = rng.uniform(0, 3, (S, D)).astype(np.float32)
+        stat.residual_sum_ds = rng.uniform(0, 3, (S, D)).astype(np.float32)
+    data.attach_observability(stat)
+    wsize, wmask = orc.attach_observability(cov, source, grp, batch, mult, S, B)
+    assert close(stat.size_ds, wsize, 1e-6)
+    # genes that no backend of a batch measures (with one batch: the genes outside both panels) put zeros in the mask
+    assert wmask is not None and np.array_equal(stat.obs_mask_db, wmask)
+    if B == 2:
+        assert np.array_equal(wmask == 0, ~cov)
+    out = lg.optimize(ctx, stat, (1.0, 1.0), 15, 0)
+    if B == 1:
+        want = orc.optimize_single_obs(stat.observed_sum_ds, stat.size_s, stat.size_ds, 1.0, 1.0, 0)
+        for plane in ("mean", "sd", "log_mean", "log_sd"):
+            assert close(out.mu_observed[plane], want[plane], TOL), plane
+        # an unmeasured gene keeps the prior: a denominator of b0 alone
+        g = int(np.nonzero(~cov[0] & ~cov[1])[0][0]) if (~cov[0] & ~cov[1]).any() else None
+        if g is not None:
+            assert np.allclose(out.mu_observed["mean"][:, g], 1.0)
+    else:
+        want = orc.optimize_batched_obs(stat.observed_sum_ds, stat.imputed_sum_ds, stat.residual_sum_ds, stat.size_s,
+                                        stat.size_ds, stat.observed_sum_db, stat.n_bs, stat.obs_mask_db, 1.0, 1.0, 15, 0)
+        for name, key in (("mu_observed", "mu_observed"), ("mu_adjusted", "mu_adjusted"), ("gamma", "gamma"), ("delta", "delta")):
+            assert close(out[name]["mean"], want[key], 1e-4), name
+        masked = wmask == 0
+        assert np.allclose(np.asarray(out.delta["mean"])[masked], 1.0)  # a0 / b0: no evidence, the prior
+    # the coarse level inherits the effective sizes by merge_stat and the mask unchanged (stats.rs:820-829)
+    f2c = (np.arange(S) // 3).astype(np.uint32)
+    coarse = data._merge_level(stat, f2c, 3, B)
+    assert close(coarse.size_ds, orc.merge_stat(wsize, f2c, 3), 1e-6)
+    assert (coarse.obs_mask_db is None) == (wmask is None)
+    sub = stat.select_rows(10, 50)
+    assert np.array_equal(sub.size_ds, np.asarray(stat.size_ds)[:, 10:60])
 
 
 # ---- edge cases: empty batches / groups / columns, one batch only ---------------------------------------------------

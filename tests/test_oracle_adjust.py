@@ -192,3 +192,48 @@ def test_fine_to_coarse_mapping():
     assert k == 3 and f2c.tolist() == [0, 0, 0, 0, 1, 2]
     f2c, k = orc.fine_to_coarse(codes, 4)
     assert k == 6 and f2c.tolist() == [0, 1, 3, 4, 2, 5]
+
+
+# ---- the refinement arm's bookkeeping and panel observability (oracle side; the GPU checks are in test_gpu_adjust.py) ----
+def test_refine_bookkeeping_restatements():
+    """dc_poisson.rs:493-509 (first-appearance compaction), refine.rs:43-62, 68-88, collapse_data/mod.rs:823-841"""
+    c, k = orc.compact_labels([7, 7, 2, 9, 2, 7])
+    assert c.tolist() == [0, 0, 1, 2, 1, 0] and k == 3
+    cells = orc.pb_sample_to_cells(np.array([1, 0, 1, 0xFFFFFFFF, 2], np.uint32), 3)
+    assert cells == [[1], [0, 2], [4]]
+    codes = np.array([0b1011, 0b0011, 0b1011, 0, 0b0111], np.uint64)
+    init = orc.initial_per_level_from_hash(codes, cells, [4, 2])
+    assert init[0].tolist() == [0, 1, 2] and init[1].tolist() == [0, 0, 0]  # masked to 2 bits every pb-sample reads 0b11
+    f2c = orc.fine_to_coarse_from_refined(np.array([0, 1, 1, 2]), np.array([0, 1, 1, 0]), 3)
+    assert f2c.tolist() == [0, 1, 0]
+    assert orc.modal_group([], [1, 2]) == 0 and orc.modal_group([1], [4, 6]) == 6
+    assert orc.modal_group([0, 1, 2], [3, 5, 5]) == 5
+
+
+def test_full_observability_is_bitwise_the_plain_fit():
+    """stats.rs:172-175: 'full observability is bitwise-identical by construction' - size_ds = 1_d * size_s' and a mask of
+    ones must reproduce optimize_block without them; a zero of the mask sends delta to a0 / b0"""
+    rng = np.random.default_rng(8)
+    S, D, B = 5, 40, 3
+    obs, imp, res = (rng.integers(0, 9, (S, D)).astype(np.float32) for _ in range(3))
+    size = rng.integers(1, 30, S).astype(np.float32)
+    obs_db = rng.integers(0, 50, (B, D)).astype(np.float32)
+    n_bs = rng.integers(0, 9, (S, B)).astype(np.float32)
+    size_ds = np.repeat(size[:, None], D, axis=1)
+    a = orc.optimize_batched(obs, imp, res, size, obs_db, n_bs, 1.0, 1.0, 7, 0)
+    b = orc.optimize_batched_obs(obs, imp, res, size, size_ds, obs_db, n_bs, np.ones((B, D), np.float32), 1.0, 1.0, 7, 0)
+    for key in a:
+        assert a[key].tobytes() == b[key].tobytes(), key
+    s0 = orc.optimize_single(obs, size, 1.0, 1.0, 0)
+    s1 = orc.optimize_single_obs(obs, size, size_ds, 1.0, 1.0, 0)
+    for key in s0:
+        assert s0[key].tobytes() == s1[key].tobytes(), key
+    mask = np.ones((B, D), np.float32)
+    mask[1, :7] = 0.0
+    c = orc.optimize_batched_obs(obs, imp, res, size, None, obs_db, n_bs, mask, 1.0, 1.0, 7, 0)
+    assert np.all(c["delta"][1, :7] == 1.0) and np.array_equal(c["delta"][0], a["delta"][0])
+    # attach_observability: the mass of a sample counts for a gene only where the column's backend measures it
+    cov = np.array([[1, 1, 0], [0, 1, 1]], bool)
+    size_ds, m = orc.attach_observability(cov, [0, 0, 1], [0, 1, 1], [0, 0, 1], None, 2, 2)
+    assert size_ds.tolist() == [[1.0, 1.0, 0.0], [1.0, 2.0, 1.0]]
+    assert m.tolist() == [[1.0, 1.0, 0.0], [0.0, 1.0, 1.0]]
