@@ -123,6 +123,8 @@ int lg_block_partials_finalize(lg_ctx* ctx, const double* d_partials, uint64_t n
 int lg_proj_centre_scale(lg_ctx* ctx, float* d_proj, int K, uint64_t ncols, const uint32_t* d_batch,
                          uint32_t nbatch, const double* d_batch_sums, float* d_minmax);
 int lg_proj_clamp_rescale(lg_ctx* ctx, float* d_proj, int K, uint64_t ncols);
+/* the same, decided ON THE DEVICE: d_minmax holds the global (min, max); a no-op when both lie inside [-4, 4] */
+int lg_proj_clamp_rescale_if(lg_ctx* ctx, float* d_proj, int K, uint64_t ncols, const float* d_minmax);
 /* EXACT-ORDER mode of the same stage: the reference's arithmetic operation by operation (ascending row, x divided by the
  * norm first, product and sum rounded separately — random_projection.rs:181-194, dmatrix_util.rs:770-778; batch means
  * as f32 left folds over the batch's cells in ascending order — random_projection.rs:380-387), so that for count data
@@ -358,6 +360,32 @@ int lg_row_stats(lg_ctx* ctx, const lg_csc* m, double* out_npos, double* out_s1,
  * ignored); pb_of_cell: u32[N], values >= P leave the cell unadjusted; out: K x N column-major. */
 int lg_nystrom_project(lg_ctx* ctx, const lg_csc* m, const float* basis_dk, int K, const float* delta_dp,
                        const uint32_t* pb_of_cell, uint32_t P, float column_sum_norm, float* out_proj_kn);
+
+/* ---- multi-GPU: cells sharded over the GPUs of one box, one process (or thread) per GPU ------------------------
+ * (section 8b row 4 `lg_allreduce_stats`).  The reference is a single process; what these entry
+ * points replace is the rayon reduction over column blocks inside project_columns / collect_basic_stat
+ * (random_projection.rs:341-415, collapse_data/stats.rs:110-164) once the blocks live on different GPUs.
+ * NCCL is bound at run time (dlopen libnccl.so.2).  Bootstrap: rank 0 calls lg_comm_unique_id, the host ships the
+ * 128 bytes to every rank by its own means, every rank calls lg_comm_init on its context.  world == 1 needs no id and
+ * makes every exchange a no-op. */
+#define LG_COMM_ID_BYTES 128
+int lg_comm_unique_id(lg_ctx* ctx, void* out_id_128_bytes);
+int lg_comm_init(lg_ctx* ctx, const void* id_128_bytes, int rank, int world);
+int lg_comm_info(lg_ctx* ctx, int* rank, int* world);
+int lg_comm_destroy(lg_ctx* ctx);
+/* in-place all-reduce(sum) over the ranks of the collapse statistics (device pointers, any may be NULL):
+ * sum_ds D x S, size_s S, sum_db D x B, n_bs B x S.  Exact for count data in any order (sums below 2^24). */
+int lg_allreduce_stats(lg_ctx* ctx, float* d_sum_ds, float* d_size_s, float* d_sum_db, float* d_n_bs, uint64_t D,
+                       uint32_t S, uint32_t B);
+/* The single-batch arm of the whole path on this rank's shard `m` (every shard but the last a multiple of 1024 cells,
+ * rank 0 holding at least kk + 5): projection + batch centring -> binary codes -> groups -> collapse + all-reduce ->
+ * posterior.  All pointers are device memory: d_proj K x ncols, d_codes / d_group per cell, d_sum_ds (and the optional
+ * posterior planes) with room for D x 2^kk, d_size_s for 2^kk; *out_num_groups the number of groups found.  Results
+ * are bit-identical for any number of ranks (order-sensitive sums travel as per-block partials in global order). */
+int lg_hotpath_run_sharded(lg_ctx* ctx, const lg_csc* m, const float* d_basis_kd, int K, const uint32_t* d_batch,
+                           uint32_t nbatch, int kk, int target, float* d_proj, uint64_t* d_codes, uint32_t* d_group,
+                           uint32_t* out_num_groups, float* d_sum_ds, float* d_size_s, float* d_mean, float* d_sd,
+                           float* d_log_mean, float* d_log_sd);
 
 #ifdef __cplusplus
 }

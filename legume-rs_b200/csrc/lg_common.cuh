@@ -28,6 +28,9 @@ struct lg_ctx {
     size_t ring_slot_bytes = 0;
     std::vector<cudaEvent_t> ring_ev;
     float* log1p_tab = nullptr;  // libm log1pf of 0 .. 65535 for the exact-order projection (built on first use)
+    // NCCL communicator of the cell-sharded path (lg_comm.cu); world 1 = no communicator, every exchange is a no-op
+    void* comm = nullptr;
+    int comm_rank = 0, comm_world = 1;
 };
 
 struct lg_csc {

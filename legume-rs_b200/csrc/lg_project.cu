@@ -308,6 +308,10 @@ __global__ void __launch_bounds__(SCALE_CELLS) k_scale_cells(float* __restrict__
                                                              const unsigned long long* __restrict__ fold_cnt,
                                                              float* __restrict__ minmax) {
     extern __shared__ float tile[];  // SCALE_CELLS rows of stride KS (odd -> conflict-free row walks)
+    if constexpr (MODE == 1) {
+        // gated form (lg_proj_clamp_rescale_if): `minmax` holds the GLOBAL (min, max); nothing to do inside [-4, 4]
+        if (minmax && !(minmax[1] > 4.0f || minmax[0] < -4.0f)) return;
+    }
     const int KS = K | 1;
     float* neg_mean = tile + SCALE_CELLS * KS;  // nbatch * K
     const uint64_t cell0 = (uint64_t)blockIdx.x * SCALE_CELLS;
@@ -518,6 +522,10 @@ extern "C" int lg_proj_centre_scale_exact(lg_ctx* ctx, float* d_proj, int K, uin
 }
 
 extern "C" int lg_proj_clamp_rescale(lg_ctx* ctx, float* d_proj, int K, uint64_t ncols) {
+    return lg_proj_clamp_rescale_if(ctx, d_proj, K, ncols, nullptr);
+}
+
+extern "C" int lg_proj_clamp_rescale_if(lg_ctx* ctx, float* d_proj, int K, uint64_t ncols, const float* d_minmax) {
     if (!ctx) return LG_ERR_INVALID;
     LG_REQUIRE(ctx, d_proj && K >= 1 && K <= 128, "lg_proj_clamp_rescale: bad argument");
     cudaSetDevice(ctx->device);
@@ -526,7 +534,7 @@ extern "C" int lg_proj_clamp_rescale(lg_ctx* ctx, float* d_proj, int K, uint64_t
     LG_CUDA(ctx, cudaFuncSetAttribute(k_scale_cells<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const uint64_t grid = (ncols + SCALE_CELLS - 1) / SCALE_CELLS;
     LG_LAUNCH(ctx, k_scale_cells<1>, (unsigned)grid, SCALE_CELLS, smem, d_proj, K, ncols, (const uint32_t*)nullptr, 0u,
-              (const double*)nullptr, (const float*)nullptr, (const unsigned long long*)nullptr, (float*)nullptr);
+              (const double*)nullptr, (const float*)nullptr, (const unsigned long long*)nullptr, const_cast<float*>(d_minmax));
     return LG_OK;
 }
 

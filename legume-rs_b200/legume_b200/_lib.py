@@ -75,6 +75,13 @@ _sig = {
     "lg_optimize_batched_obs": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _u64, _u32, _u32, _f, _f, _i, _i, _vp, _vp, _vp,
                                 _vp, _vp, _vp],
     "lg_attach_observability": [_vp, _vp, _u32, _vp, _vp, _vp, _vp, _u64, _u64, _u32, _u32, _vp, _vp, _vp],
+    "lg_proj_clamp_rescale_if": [_vp, _vp, _i, _u64, _vp],
+    "lg_comm_unique_id": [_vp, _vp],
+    "lg_comm_init": [_vp, _vp, _i, _i],
+    "lg_comm_info": [_vp, _vp, _vp],
+    "lg_comm_destroy": [_vp],
+    "lg_allreduce_stats": [_vp, _vp, _vp, _vp, _vp, _u64, _u32, _u32],
+    "lg_hotpath_run_sharded": [_vp, _vp, _vp, _i, _vp, _u32, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
     "lg_optimize_batched": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _u64, _u32, _u32, _f, _f, _i, _i, _vp, _vp, _vp, _vp,
                             _vp, _vp],
     "lg_knn_topk": [_vp, _vp, _u64, _vp, _u64, _i, _i, _vp, _vp, _vp],

@@ -316,6 +316,47 @@ class HotPath:
         return dict(num_pb=npb, cell_to_pb=c2p, pb_group=pb_group, pb_batch=pb_batch, pb_count=ccnt, centroids=cen,
                     gene_sums=gene_sums, matched_pb=mp, matched_dist=md, imputed_sum_ds=imp, residual_sum_ds=res)
 
+    # ---- the same path inside the library (lg_comm.cu): what a Rust host calls ----------------------------------------
+    def init_native_comm(self):
+        """give the library's context its own NCCL communicator over the ranks of this process group: rank 0 draws the
+        id (lg_comm_unique_id), torch.distributed carries the 128 bytes, every rank calls lg_comm_init"""
+        if getattr(self, "_native_comm", False):
+            return
+        ident = torch.zeros(128, dtype=torch.uint8, device=self.dev)
+        if self.world > 1:
+            if self.rank == 0:
+                buf = (C.c_ubyte * 128)()
+                self.ctx.check(lib.lg_comm_unique_id(self.ctx.h, buf))
+                ident.copy_(torch.frombuffer(bytearray(buf), dtype=torch.uint8))
+            self.ex.broadcast_(ident, 0)
+        raw = bytes(ident.cpu().numpy().tobytes())
+        self.ctx.check(lib.lg_comm_init(self.ctx.h, raw, self.rank, self.world))
+        self._native_comm = True
+
+    def run_native(self, block: CscBlock, basis_kd: torch.Tensor, batch, nbatch: int, kk: int, target=TARGET_ALL):
+        """lg_hotpath_run_sharded: projection -> codes -> groups -> collapse (+ all-reduce) -> posterior in ONE library
+        call, the exchanges on the library's own NCCL communicator; same results, bit for bit, as run()"""
+        self.init_native_comm()
+        ctx, n, D = self.ctx, block.ncols, block.nrows
+        K = basis_kd.shape[1]
+        cap = 1 << kk
+        f32 = lambda *shape: torch.empty(shape, dtype=torch.float32, device=self.dev)
+        proj = f32(n, K)
+        codes = torch.empty(n, dtype=torch.int64, device=self.dev)
+        group = torch.empty(n, dtype=torch.int32, device=self.dev)
+        sum_ds, size_s, mean = f32(cap, D), f32(cap), f32(cap, D)
+        sd = f32(cap, D) if target == TARGET_ALL else None
+        ls = f32(cap, D) if target == TARGET_ALL else None
+        lm = f32(cap, D) if target != TARGET_MEAN_ONLY else None
+        ng = C.c_uint32()
+        ctx.check(lib.lg_hotpath_run_sharded(ctx.h, block.h, _ptr(basis_kd), K, _ptr(batch) if batch is not None and nbatch >= 1 else None,
+                                             nbatch if batch is not None else 0, kk, target, _ptr(proj), _ptr(codes), _ptr(group),
+                                             C.byref(ng), _ptr(sum_ds), _ptr(size_s), _ptr(mean), _ptr(sd), _ptr(lm), _ptr(ls)))
+        S = int(ng.value)
+        cut = lambda t: None if t is None else t[:S]
+        return dict(proj=proj, codes=codes, group=group, num_groups=S, sum_ds=sum_ds[:S], size_s=size_s[:S],
+                    posterior=dict(mean=cut(mean), sd=cut(sd), log_mean=cut(lm), log_sd=cut(ls)))
+
     # ---- whole path --------------------------------------------------------------------------------
     def run(self, block: CscBlock, basis_kd: torch.Tensor, batch, nbatch: int, kk: int, target=TARGET_ALL, exact: bool = False):
         """projection -> codes -> groups -> collapse -> posterior (single-batch arm of the path); exact=True takes the

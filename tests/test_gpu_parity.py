@@ -324,6 +324,35 @@ def test_project_fused_form_is_bit_identical(lg, ctx, monkeypatch):
             assert got["0"].tobytes() == got["1"].tobytes(), (D, N, lo, hi)
 
 
+def test_hotpath_run_sharded_one_rank_equals_staged_path(lg, ctx):
+    """lg_hotpath_run_sharded (lg_comm.cu) with a world of one: the whole single-batch arm as ONE C-ABI call must equal the
+    staged calls of legume_b200.pipeline bit for bit (the multi-rank comparison is tools/check_multi_gpu.py), with and
+    without batch labels; lg_comm_init / lg_comm_info / lg_allreduce_stats are no-ops on one rank"""
+    import torch
+    from legume_b200 import sim
+    from legume_b200.pipeline import HotPath
+    D, N, K, kk = 3000, 5000, 50, 8
+    tabs = sim.make_tables(D, ntopic=5, nbatch=3, depth=300, seed=9)
+    blk, _, batch_h = sim.sim_block(ctx, tabs, 0, N)
+    basis = torch.from_numpy(basis_for(D, K, 4)).cuda()
+    batch = torch.from_numpy(batch_h.astype(np.int32)).cuda()
+    hp = HotPath(ctx)
+    for b, nb in ((batch, 3), (None, 0)):
+        a = hp.run(blk, basis, b, nb, kk)
+        c = hp.run_native(blk, basis, b, nb, kk)
+        assert a["num_groups"] == c["num_groups"]
+        for key in ("proj", "codes", "group", "sum_ds", "size_s"):
+            assert torch.equal(a[key], c[key]), key
+        for key in ("mean", "sd", "log_mean", "log_sd"):
+            assert torch.equal(a["posterior"][key], c["posterior"][key]), key
+    r, w = C.c_int(-1), C.c_int(-1)
+    ctx.check(lg.lib.lg_comm_info(ctx.h, C.byref(r), C.byref(w)))
+    assert (r.value, w.value) == (0, 1)
+    s = a["sum_ds"].clone()
+    ctx.check(lg.lib.lg_allreduce_stats(ctx.h, lg._ptr(s), None, None, None, D, a["num_groups"], 0))
+    assert torch.equal(s, a["sum_ds"])
+
+
 def test_sparse_io_stack_projects_every_modality_and_stacks(lg, ctx):
     """RandProjOps for SparseIoStack (random_projection.rs:200-340): per-modality projection with its own basis, vertical
     concatenation of bases (rows) and projections (dims); batch labels cut to the shared column count; one set of codes"""

@@ -42,6 +42,11 @@ lo, hi = shard_range(N, rank, world)
 blk, _, batch_h = sim.sim_block(ctx, tabs, lo, hi)
 batch = torch.from_numpy(batch_h.astype(np.int32)).to(dev)
 out = hp.run(blk, basis, batch, B, kk)
+# the same path as ONE library call on the library's own NCCL communicator (lg_hotpath_run_sharded)
+nat = hp.run_native(blk, basis, batch, B, kk)
+native_same = all(bool(torch.equal(out[key], nat[key])) for key in ("proj", "codes", "group", "sum_ds", "size_s")) and \
+    out["num_groups"] == nat["num_groups"] and \
+    all(bool(torch.equal(out["posterior"][key], nat["posterior"][key])) for key in ("mean", "sd", "log_mean", "log_sd"))
 sum_db, n_bs = hp.collapse_batch(blk, out["group"], batch, out["num_groups"], B)
 # sharded kNN: this rank's cells are both its query shard and its reference shard; self excluded by global index
 q_local = out["proj"][: min(4096, hi - lo)].contiguous()
@@ -58,6 +63,9 @@ torch.cuda.synchronize()
 
 report = {"world": world, "cells": N, "genes": D}
 if world > 1:
+    flag = torch.tensor([1 if native_same else 0], dtype=torch.int32, device=dev)
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    report["native_c_abi_path_bit_exact"] = bool(flag.item())
     # rank 0 recomputes everything unsharded on its own GPU (no collectives) and compares with the gathered shards
     gathered = {}
     for name, t in (("proj", out["proj"]), ("codes", out["codes"]), ("group", out["group"]), ("kidx", kidx), ("kdist", kdist),
@@ -111,5 +119,6 @@ if world > 1:
     dist.barrier()
     dist.destroy_process_group()
 else:
-    report["note"] = "single rank: nothing to compare"
+    report["native_c_abi_path_bit_exact"] = native_same
+    report["note"] = "single rank: only the one-call C-ABI path is compared with the staged one"
     os.write(_REAL_STDOUT, (json.dumps(report) + "\n").encode())
