@@ -318,8 +318,13 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    # the timed path is ONE C-ABI call per step (lg_hotpath_run_sharded: what a Rust host calls, exchanges on the
+    # library's own NCCL communicator); LG_BENCH_STAGED=1 times the staged calls of legume_b200.pipeline instead
+    staged = os.environ.get("LG_BENCH_STAGED") == "1"
+    run_path = hp.run if staged else hp.run_native
+
     def step():
-        return hp.run(blk, basis, batch, 1, kk, lg.TARGET_ALL)
+        return run_path(blk, basis, batch, 1, kk, lg.TARGET_ALL)
 
     for _ in range(args.warmup):
         out = step()
@@ -452,7 +457,7 @@ def main():
             ctx.check(lib.lg_csc_upload(ctx.h, h_ip.data_ptr(), h_ix.data_ptr(), h_v.data_ptr(), D, 0, e2e_cells, None,
                                         lg.C.byref(h)))
             b = lg.CscBlock(ctx, h)
-            o = hp.run(b, basis.copy_(h_basis, non_blocking=True), batch[:e2e_cells], 1, kk, lg.TARGET_ALL)
+            o = run_path(b, basis.copy_(h_basis, non_blocking=True), batch[:e2e_cells], 1, kk, lg.TARGET_ALL)
             h_proj.copy_(o["proj"], non_blocking=True)
             h_group.copy_(o["group"], non_blocking=True)
             nb = h_proj.numel() * 4 + h_group.numel() * 4
@@ -527,7 +532,8 @@ def main():
             "config": {"workload": workload_name(args, world, cells_per_gpu), "cells_per_gpu": cells_per_gpu,
                        "genes": D, "nnz_per_gpu": int(nnz_local), "proj_dim": K, "sort_dim": kk, "groups": int(ngroups),
                        "l2": "inputs larger than L2 (nnz stream %.1f GB per GPU)" % (8e-9 * nnz_local),
-                       "parallelism": f"cells sharded x{world}"},
+                       "parallelism": f"cells sharded x{world}",
+                       "api": "staged C-ABI calls (legume_b200.pipeline)" if staged else "lg_hotpath_run_sharded (one C-ABI call per step)"},
             "roofline": roofline, "roofline_knn": roofline_knn, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clk,
             "stages": stages, "parity": parity, "extras": extras,
         }

@@ -179,6 +179,18 @@ extern "C" int lg_hotpath_run_sharded(lg_ctx* ctx, const lg_csc* m, const float*
     const int W = ctx->comm_world;
     const uint64_t n = m->ncols, D = m->nrows;
     LgStage st(ctx);
+    // LG_TRACE=1: device time of every stage of this call on stderr (diagnostic; synchronises at the end)
+    const char* tr = getenv("LG_TRACE");
+    const bool trace = tr && tr[0] == '1';
+    std::vector<cudaEvent_t> evs;
+    auto mark = [&]() {
+        if (!trace) return;
+        cudaEvent_t e;
+        cudaEventCreate(&e);
+        cudaEventRecord(e, ctx->stream);
+        evs.push_back(e);
+    };
+    mark();
     // ---- every rank's cell count (one small exchange; the only host read before the group table) ----
     std::vector<unsigned long long> counts(W, n);
     if (W > 1) {
@@ -220,6 +232,7 @@ extern "C" int lg_hotpath_run_sharded(lg_ctx* ctx, const lg_csc* m, const float*
         LG_NCCL(ctx, a->GroupEnd());
     }
     LG_TRY(lg_proj_clamp_rescale_if(ctx, d_proj, K, n, d_mm));  // decided on the device: no read-back
+    mark();
     // ---- K3 ----
     const uint64_t rank_all = std::min<uint64_t>((uint64_t)K, ntot);
     uint64_t r = rank_all > (uint64_t)kk ? (uint64_t)kk + 5 : rank_all;
@@ -250,6 +263,7 @@ extern "C" int lg_hotpath_run_sharded(lg_ctx* ctx, const lg_csc* m, const float*
     LG_TRY(st.scratch((size_t)kk, &d_cmean));
     LG_TRY(lg_codes_means(ctx, d_vsum, kk, ntot, d_cmean));
     LG_TRY(lg_codes_pack(ctx, d_v, kk, n, d_cmean, d_codes));
+    mark();
     // ---- K4: presence flags -> (host) lexicographic group table -> group of every cell ----
     const size_t ncode = (size_t)1 << kk;
     uint32_t *d_present, *d_lut;
@@ -257,7 +271,9 @@ extern "C" int lg_hotpath_run_sharded(lg_ctx* ctx, const lg_csc* m, const float*
     LG_TRY(st.scratch(ncode, &d_lut));
     LG_TRY(lg_code_presence(ctx, d_codes, n, kk, d_present));
     if (W > 1) LG_NCCL(ctx, a->AllReduce(d_present, d_present, ncode, ncclUint32, ncclMax, comm_of(ctx), ctx->stream));
-    std::vector<uint32_t> h_present(ncode), h_lut(ncode);
+    std::vector<uint32_t> h_present(ncode);
+    std::vector<uint32_t>& h_lut = ctx->lut_keep;
+    h_lut.assign(ncode, 0u);
     LG_CUDA(ctx, cudaMemcpyAsync(h_present.data(), d_present, sizeof(uint32_t) * ncode, cudaMemcpyDeviceToHost, ctx->stream));
     LG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     uint32_t S = 0;
@@ -265,12 +281,37 @@ extern "C" int lg_hotpath_run_sharded(lg_ctx* ctx, const lg_csc* m, const float*
     LG_CUDA(ctx, cudaMemcpyAsync(d_lut, h_lut.data(), sizeof(uint32_t) * ncode, cudaMemcpyHostToDevice, ctx->stream));
     LG_TRY(lg_codes_to_groups(ctx, d_codes, n, kk, d_lut, d_group));
     *out_num_groups = S;
+    mark();
     // ---- K5 + the all-reduce of the sums ----
     LG_TRY(lg_collapse_basic(ctx, m, d_group, nullptr, S, d_sum_ds, d_size_s));
+    mark();
     LG_TRY(lg_allreduce_stats(ctx, d_sum_ds, d_size_s, nullptr, nullptr, D, S, 0));
+    mark();
     // ---- K6 (replicated) ----
     if (d_mean || d_sd || d_log_mean || d_log_sd)
         LG_TRY(lg_optimize_single(ctx, d_sum_ds, d_size_s, D, S, 1.0f, 1.0f, target, d_mean, d_sd, d_log_mean, d_log_sd));
-    LG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // h_lut must outlive its copy
+    mark();
+    if (trace && evs.size() == 7) {
+        static cudaEvent_t prev_end = nullptr;  // diagnostic only: the stream time between two consecutive calls
+        cudaEventSynchronize(evs.back());
+        if (prev_end) {
+            float gap = 0.f;
+            if (cudaEventElapsedTime(&gap, prev_end, evs[0]) == cudaSuccess) fprintf(stderr, "[lg_hotpath] since the previous call ended: %.3f ms; ", gap);
+            cudaEventDestroy(prev_end);
+        }
+        prev_end = evs.back();
+        evs.pop_back();
+        evs.push_back(nullptr);
+        const char* names[6] = {"project", "codes", "groups", "collapse", "allreduce", "posterior"};
+        fprintf(stderr, "[lg_hotpath rank %d]", ctx->comm_rank);
+        for (int i = 0; i < 6; ++i) {
+            float ms = 0.f;
+            cudaEventElapsedTime(&ms, evs[i], i + 1 == 6 ? prev_end : evs[i + 1]);
+            fprintf(stderr, " %s %.3f ms", names[i], ms);
+        }
+        fprintf(stderr, "\n");
+    }
+    for (auto e : evs)
+        if (e) cudaEventDestroy(e);
     return LG_OK;
 }

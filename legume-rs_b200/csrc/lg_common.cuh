@@ -31,6 +31,18 @@ struct lg_ctx {
     // NCCL communicator of the cell-sharded path (lg_comm.cu); world 1 = no communicator, every exchange is a no-op
     void* comm = nullptr;
     int comm_rank = 0, comm_world = 1;
+    std::vector<uint32_t> lut_keep;  // host copy of the last group table (outlives its asynchronous upload)
+    // Large scratch (>= LG_CACHE_MIN bytes) is kept by the context and handed out again, smallest fitting block first:
+    // every use is ordered on ctx->stream, so a block may be reused by the next call while the previous one's kernels
+    // are still queued.  The driver's stream-ordered pool does this too, but with the path's mix of one 4 GB block and
+    // many 40 MB ones it fragments (small blocks land inside the big freed one, the next big request maps new memory)
+    // until calls stall for hundreds of milliseconds; small scratch still comes from that pool.
+    struct CacheBlk {
+        void* p;
+        size_t bytes;
+        bool used;
+    };
+    std::vector<CacheBlk> cache;
 };
 
 struct lg_csc {
@@ -45,6 +57,8 @@ struct lg_csc {
     // cached "rows strictly ascending and in range inside every column" (-1 unknown): see lg_csc_require_canonical
     mutable int canonical = -1;
 };
+
+constexpr size_t LG_CACHE_MIN = 1u << 20;
 
 inline int lg_fail(lg_ctx* ctx, int code, const std::string& msg) {
     if (ctx) ctx->err = msg;
@@ -99,6 +113,7 @@ class LgStage {
     explicit LgStage(lg_ctx* c) : ctx_(c) {}
     ~LgStage() {
         for (auto& t : tmp_) cudaFreeAsync(t, ctx_->stream);
+        for (auto i : cached_) ctx_->cache[i].used = false;
     }
     // read-only input; bytes may be 0 / p may be NULL -> nullptr
     template <typename T>
@@ -138,8 +153,28 @@ class LgStage {
     // device scratch owned by the stage
     template <typename T>
     int scratch(size_t count, T** dev) {
+        const size_t bytes = (count ? count : 1) * sizeof(T);
+        if (bytes >= LG_CACHE_MIN) {
+            int best = -1;
+            for (size_t i = 0; i < ctx_->cache.size(); ++i) {
+                const auto& b = ctx_->cache[i];
+                if (!b.used && b.bytes >= bytes && (best < 0 || b.bytes < ctx_->cache[best].bytes)) best = (int)i;
+            }
+            // a much larger block is not worth tying up for a small request
+            if (best >= 0 && ctx_->cache[best].bytes > 4 * bytes + (64u << 20)) best = -1;
+            if (best < 0) {
+                void* d = nullptr;
+                LG_CUDA(ctx_, cudaMalloc(&d, bytes));
+                ctx_->cache.push_back({d, bytes, false});
+                best = (int)ctx_->cache.size() - 1;
+            }
+            ctx_->cache[best].used = true;
+            cached_.push_back((size_t)best);
+            *dev = static_cast<T*>(ctx_->cache[best].p);
+            return LG_OK;
+        }
         void* d = nullptr;
-        LG_CUDA(ctx_, cudaMallocAsync(&d, (count ? count : 1) * sizeof(T), ctx_->stream));
+        LG_CUDA(ctx_, cudaMallocAsync(&d, bytes, ctx_->stream));
         tmp_.push_back(d);
         *dev = static_cast<T*>(d);
         return LG_OK;
@@ -162,6 +197,7 @@ class LgStage {
     };
     lg_ctx* ctx_;
     std::vector<void*> tmp_;
+    std::vector<size_t> cached_;
     std::vector<Out> outs_;
     bool any_host_ = false;
 };

@@ -62,6 +62,7 @@ extern "C" int lg_ctx_destroy(lg_ctx* c) {
     if (c->pinned) cudaFreeHost(c->pinned);
     if (c->ring) cudaFreeHost(c->ring);
     if (c->log1p_tab) cudaFree(c->log1p_tab);
+    for (auto& b : c->cache) cudaFree(b.p);
     for (auto e : c->ring_ev) cudaEventDestroy(e);
     delete c;
     return LG_OK;
@@ -76,6 +77,8 @@ extern "C" int lg_ctx_set_stream(lg_ctx* c, void* s) {
         cudaStreamSynchronize(c->stream);
         cudaStreamDestroy(c->stream);
         c->own_stream = false;
+    } else if (c->stream != static_cast<cudaStream_t>(s)) {
+        cudaStreamSynchronize(c->stream);  // cached scratch is handed out again in the order of ONE stream
     }
     // NULL is the legacy default stream (what torch reports for its default stream)
     c->stream = static_cast<cudaStream_t>(s);
