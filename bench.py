@@ -437,7 +437,7 @@ def main():
         if world > 1:  # same sample size on every rank
             t_cells = torch.tensor([e2e_cells], dtype=torch.int64, device=dev)
             dist.all_reduce(t_cells, op=dist.ReduceOp.MIN)
-            e2e_cells = int(t_cells.item())
+            e2e_cells = int(t_cells.item()) // 1024 * 1024  # shards are cut at multiples of the 1024-cell reduction block
         sub, _, _ = (blk, None, None) if e2e_cells == n_local else sim.sim_block(ctx, tabs, lo, lo + e2e_cells)
         ip, ix, v = sub.download()
         if sub is not blk:
