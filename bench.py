@@ -415,6 +415,13 @@ def main():
                         "algorithmic_flops_per_launch": flop, "launch_ms": t_knn, "queries_per_s": nq_k / (t_knn * 1e-3),
                         # tensor-pipe occupancy: what the kernel actually issues on tcgen05, against the same measured peak
                         "issued": ach * 3.84, "issued_frac": ach * 3.84 / tpeak,
+                        # every one of the Nq x Nr f32 accumulators has to leave TMEM to be ranked: 64 B / clk / SM (tcgen05.ld),
+                        # 148 SMs at the sampled SM clock — the bound of an exact brute-force search at this d
+                        "tmem_read_bytes": 4.0 * nq_k * nr_k,
+                        "tmem_read_peak_TBps": 148 * 64 * 1.965e9 / 1e12,
+                        "tmem_read_achieved_TBps": 4.0 * nq_k * nr_k / (t_knn * 1e-3) / 1e12,
+                        "tmem_read_frac": (4.0 * nq_k * nr_k / (t_knn * 1e-3)) / (148 * 64 * 1.965e9),
+                        "tensor_frac_ceiling": (flop / (4.0 * nq_k * nr_k / (148 * 64 * 1.965e9))) / 1e12 / tpeak,
                         "note": "achieved / frac count ALGORITHMIC flops 2*d*Nq*Nr; the filter issues 3 f16 passes over a K axis "
                                 "padded 50 -> 64, i.e. 3.84x these flops on the tensor pipe (issued / issued_frac; cf. "
                                 "sm__pipe_tensor_cycles_active in profiles/)"}

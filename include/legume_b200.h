@@ -59,6 +59,12 @@ uint64_t lg_ctx_launch_count(const lg_ctx* ctx);
 /* bytes lg_csc_upload has put on the host->device link through ctx since creation (host arrays are narrowed /
  * packed before they travel, so this is less than the size of the arrays handed in) */
 uint64_t lg_ctx_h2d_bytes(const lg_ctx* ctx);
+/* how many calls a tensor-core path (K1 projection, K7 kNN) declined for a reason of capability — K above 53 or more
+ * than 131 072 genes or a non-finite basis for the projection; k above 12, d above 126 for the kNN filter — and handed to
+ * the (several times slower) CUDA-core kernel, and the last reason.  Each distinct reason is also printed once on
+ * stderr unless LG_QUIET=1.  Results are the same either way. */
+uint64_t lg_ctx_fallback_count(const lg_ctx* ctx);
+const char* lg_ctx_last_fallback(const lg_ctx* ctx);
 const char* lg_version(void);
 
 /* ---- data feed --------------------------------------------------------------------------

@@ -4,6 +4,7 @@
 #include <stdint.h>
 
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -43,6 +44,10 @@ struct lg_ctx {
         bool used;
     };
     std::vector<CacheBlk> cache;
+    // tensor-core paths that could not take a call and handed it to the CUDA-core kernel (lg_note_fallback)
+    uint64_t fallbacks = 0;
+    std::string last_fallback;
+    std::vector<std::string> fallback_seen;
 };
 
 struct lg_csc {
@@ -63,6 +68,19 @@ constexpr size_t LG_CACHE_MIN = 1u << 20;
 inline int lg_fail(lg_ctx* ctx, int code, const std::string& msg) {
     if (ctx) ctx->err = msg;
     return code;
+}
+
+// A tensor-core path declined a call for a reason of capability (not of size): counted on the context, remembered, and said
+// once per distinct reason on stderr (LG_QUIET=1 silences it) — a 5x slower kernel must not be taken silently.
+inline void lg_note_fallback(lg_ctx* ctx, const std::string& what) {
+    if (!ctx) return;
+    ctx->fallbacks++;
+    ctx->last_fallback = what;
+    for (const auto& s : ctx->fallback_seen)
+        if (s == what) return;
+    ctx->fallback_seen.push_back(what);
+    const char* q = getenv("LG_QUIET");
+    if (!(q && q[0] == '1')) fprintf(stderr, "[legume_b200] %s\n", what.c_str());
 }
 
 #define LG_CUDA(ctx, call)                                                                         \

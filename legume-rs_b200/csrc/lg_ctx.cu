@@ -93,6 +93,8 @@ extern "C" int lg_ctx_sync(lg_ctx* c) {
 
 extern "C" uint64_t lg_ctx_launch_count(const lg_ctx* c) { return c ? c->launches : 0; }
 extern "C" uint64_t lg_ctx_h2d_bytes(const lg_ctx* c) { return c ? c->h2d_bytes : 0; }
+extern "C" uint64_t lg_ctx_fallback_count(const lg_ctx* c) { return c ? c->fallbacks : 0; }
+extern "C" const char* lg_ctx_last_fallback(const lg_ctx* c) { return c ? c->last_fallback.c_str() : ""; }
 
 // ---- CSC container ----------------------------------------------------------------------------
 // narrow u64 row indices to u32 (optionally through a row remap), flagging out-of-range rows

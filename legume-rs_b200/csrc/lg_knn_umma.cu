@@ -422,7 +422,13 @@ int lg_knn_exact_list(lg_ctx* ctx, const float* d_ref, uint64_t nr, const float*
 int lg_knn_topk_umma(lg_ctx* ctx, const float* d_ref, uint64_t nr, const float* d_qry, uint64_t nq, int d, int k,
                      const uint32_t* d_ex, uint32_t* d_idx, float* d_dist, int squared, int* used) {
     *used = 0;
-    if (k + 4 > CAND || d > 126 || nr < 4096 || nq == 0 || nr >= 0xFFFFFF00ull || (double)nq * (double)nr < 5e7) return LG_OK;
+    if (nr < 4096 || nq == 0 || (double)nq * (double)nr < 5e7) return LG_OK;  // small searches: the brute-force kernel is the faster one
+    if (k + 4 > CAND || d > 126 || nr >= 0xFFFFFF00ull) {
+        char b[200];
+        snprintf(b, sizeof(b), "kNN: k = %d, d = %d is outside the tensor-core filter (k <= %d, d <= 126): CUDA-core kernel", k, d, CAND - 4);
+        lg_note_fallback(ctx, b);
+        return LG_OK;
+    }
     const int ksteps = (d + 2 + 15) / 16;
     const size_t qbytes = tile_bytes(QT, ksteps), rbytes = tile_bytes(RT, ksteps);
     static_assert(sizeof(KBars) + 16 <= 512, "barriers and the TMEM slot fit the 512 bytes ahead of the append buffers");

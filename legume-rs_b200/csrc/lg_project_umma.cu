@@ -1154,7 +1154,14 @@ __global__ void __launch_bounds__(F_THREADS, 1)
 int lg_project_raw_umma(lg_ctx* ctx, const lg_csc* m, const float* d_basis, int K, float* d_out, int* used, int mode, float csn) {
     *used = 0;
     const int NB = ((3 * K + 15) / 16) * 16;
-    if (K < 1 || NT * NB + NT * NAST * A_COLS > 512 || m->nrows > 131072 || m->ncols == 0 || m->nrows == 0) return LG_OK;
+    if (K < 1 || m->ncols == 0 || m->nrows == 0) return LG_OK;
+    if (NT * NB + NT * NAST * A_COLS > 512 || m->nrows > 131072) {
+        char b[200];
+        snprintf(b, sizeof(b), "projection: K = %d, %llu genes is outside the tensor-core path (K <= 53, genes <= 131072): CUDA-core kernel", K,
+                 (unsigned long long)m->nrows);
+        lg_note_fallback(ctx, b);
+        return LG_OK;
+    }
     const uint64_t D = m->nrows;
     const uint64_t Dpad = ((D + GS - 1) / GS) * GS;
     const uint32_t nstages = (uint32_t)(Dpad / GS);
@@ -1227,7 +1234,10 @@ int lg_project_raw_umma(lg_ctx* ctx, const lg_csc* m, const float* d_basis, int 
                 for (int i = 0; i < 3; ++i) cudaEventDestroy(ev[i]);
             }
             LG_CUDA(ctx, fe);
-            if (*h_flag) return LG_OK;  // the kernel returned at once; the caller falls back (and propagates the non-finite column)
+            if (*h_flag) {  // the kernel returned at once; the caller falls back (and propagates the non-finite column)
+                lg_note_fallback(ctx, "projection: a basis column is not finite or too large for the fixed-point grid: CUDA-core kernel");
+                return LG_OK;
+            }
             *used = 1;
             return LG_OK;
         }
@@ -1280,6 +1290,7 @@ int lg_project_raw_umma(lg_ctx* ctx, const lg_csc* m, const float* d_basis, int 
         cudaEventDestroy(flag_ev);
         LG_CUDA(ctx, fe);
         if (*h_flag) {  // a non-finite basis column: fall back to the CUDA-core kernel (which propagates it)
+            lg_note_fallback(ctx, "projection: a basis column is not finite or too large for the fixed-point grid: CUDA-core kernel");
             if (trace)
                 for (int i = 0; i < 3; ++i) cudaEventDestroy(ev[i]);
             return LG_OK;

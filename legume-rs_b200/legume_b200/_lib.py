@@ -115,7 +115,12 @@ lib.lg_ctx_launch_count.argtypes = [_vp]
 lib.lg_ctx_launch_count.restype = C.c_uint64
 lib.lg_ctx_h2d_bytes.argtypes = [_vp]
 lib.lg_ctx_h2d_bytes.restype = C.c_uint64
+lib.lg_ctx_fallback_count.argtypes = [_vp]
+lib.lg_ctx_fallback_count.restype = C.c_uint64
+lib.lg_ctx_last_fallback.argtypes = [_vp]
+lib.lg_ctx_last_fallback.restype = C.c_char_p
 lib.lg_version.argtypes = []
 lib.lg_version.restype = C.c_char_p
 
-EXPORTED = sorted(list(_sig) + ["lg_last_error", "lg_ctx_launch_count", "lg_ctx_h2d_bytes", "lg_version"])
+EXPORTED = sorted(list(_sig) + ["lg_last_error", "lg_ctx_launch_count", "lg_ctx_h2d_bytes", "lg_ctx_fallback_count", "lg_ctx_last_fallback",
+                          "lg_version"])

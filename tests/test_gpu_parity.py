@@ -324,6 +324,29 @@ def test_project_fused_form_is_bit_identical(lg, ctx, monkeypatch):
             assert got["0"].tobytes() == got["1"].tobytes(), (D, N, lo, hi)
 
 
+def test_tensor_path_fallbacks_are_counted_not_silent(lg, ctx, capfd):
+    """a call the tcgen05 paths cannot take (K > 53 for the projection) runs on the CUDA-core kernel with the same contract,
+    and says so: once on stderr per distinct reason, and in lg_ctx_fallback_count / lg_ctx_last_fallback"""
+    rng = np.random.default_rng(3)
+    D, N, K = 600, 300, 60
+    ip, ix, v = random_csc(rng, D, N, 0.1)
+    basis = basis_for(D, K, 2)
+    blk = lg.CscBlock.upload(ctx, ip, ix, v, D)
+    before = lg.lib.lg_ctx_fallback_count(ctx.h)
+    raw = np.empty((N, K), np.float32)
+    for _ in range(2):
+        ctx.check(lg.lib.lg_project_raw(ctx.h, blk.h, basis.ctypes.data, K, raw.ctypes.data))
+    assert lg.lib.lg_ctx_fallback_count(ctx.h) == before + 2
+    assert b"K = 60" in lg.lib.lg_ctx_last_fallback(ctx.h)
+    assert capfd.readouterr().err.count("outside the tensor-core path") == 1  # said once, counted every time
+    want = orc.project_raw(ip, ix, v, basis) if hasattr(orc, "project_raw") else None
+    if want is not None:
+        assert close(raw, want, TOL)
+    # a call the tensor path takes does not count
+    ctx.check(lg.lib.lg_project_raw(ctx.h, blk.h, np.ascontiguousarray(basis[:, :50]).ctypes.data, 50, np.empty((N, 50), np.float32).ctypes.data))
+    assert lg.lib.lg_ctx_fallback_count(ctx.h) == before + 2
+
+
 def test_hotpath_run_sharded_one_rank_equals_staged_path(lg, ctx):
     """lg_hotpath_run_sharded (lg_comm.cu) with a world of one: the whole single-batch arm as ONE C-ABI call must equal the
     staged calls of legume_b200.pipeline bit for bit (the multi-rank comparison is tools/check_multi_gpu.py), with and
