@@ -212,6 +212,67 @@ def pad_numeric_labels(cell_to_group, k):
     return [f"{int(g):0{width}d}" for g in cell_to_group]
 
 
+PARTITION_SHUFFLE_SEED = 0x5041525453485546  # "PARTSHUF", matrix-util/src/utils.rs:12
+
+
+class _Xoshiro256pp:
+    """xoshiro256++ seeded through SplitMix64 (the construction behind rand's SmallRng::seed_from_u64 on 64-bit targets)"""
+    M = 0xFFFFFFFFFFFFFFFF
+
+    def __init__(self, seed):
+        s, st = seed & self.M, []
+        for _ in range(4):
+            s = (s + 0x9E3779B97F4A7C15) & self.M
+            z = s
+            z = ((z ^ (z >> 30)) * 0xBF58476D1CE4E5B9) & self.M
+            z = ((z ^ (z >> 27)) * 0x94D049BB133111EB) & self.M
+            st.append(z ^ (z >> 31))
+        self.s = st
+
+    def next(self):
+        s, M = self.s, self.M
+        rot = lambda x, k: ((x << k) | (x >> (64 - k))) & M
+        out = (rot((s[0] + s[3]) & M, 23) + s[0]) & M
+        t = (s[1] << 17) & M
+        s[2] ^= s[0]
+        s[3] ^= s[1]
+        s[1] ^= s[2]
+        s[0] ^= s[3]
+        s[2] ^= t
+        s[3] = rot(s[3], 45)
+        return out
+
+    def below(self, n):
+        """uniform integer in [0, n): widening multiply with rejection (unbiased)"""
+        lim = (1 << 64) - ((1 << 64) % n)
+        while True:
+            x = self.next()
+            if x < lim:
+                return x % n
+
+
+def downsample_groups(col_to_group, num_groups, ntarget):
+    """partition_by_membership with nelem_per_group (matrix-util/src/utils.rs:36-66): every group with more than `ntarget`
+    columns keeps `ntarget` of them — a Fisher-Yates shuffle of its members (ascending) by a generator seeded with
+    mix_seed(PARTITION_SHUFFLE_SEED, smallest member), truncated; the others get the label 0xFFFFFFFF"""
+    g = np.asarray(col_to_group, np.uint32).copy()
+    if ntarget < 0:
+        raise LegumeError(1, "ncolumns_per_group must not be negative")
+    order = np.argsort(g, kind="stable")
+    bounds = np.searchsorted(g[order], np.arange(num_groups + 1))
+    for k in range(num_groups):
+        cells = order[bounds[k]:bounds[k + 1]]
+        if len(cells) <= ntarget:
+            continue
+        rng = _Xoshiro256pp(mix_seed(PARTITION_SHUFFLE_SEED, int(cells[0])))
+        perm = cells.copy()
+        for i in range(len(perm) - 1, 0, -1):
+            j = rng.below(i + 1)
+            perm[i], perm[j] = perm[j], perm[i]
+        g[perm[ntarget:]] = NONE_U32
+    return g
+
+
 def compute_level_sort_dims(finest_sort_dim, num_levels):
     """collapse_data/refine.rs:718-734 (f32 arithmetic, round half away from zero)"""
     if num_levels <= 1:
@@ -481,6 +542,24 @@ class GammaMatrix:
             self.estimated_log_mean = lm
         if ls is not None:
             self.estimated_log_sd = ls
+
+    @classmethod
+    def vconcat(cls, blocks, stack_stats: bool):
+        """dmatrix_gamma.rs:301-326: row blocks (same columns, same hyper-parameters) stacked into one parameter; the
+        planes the first block has calibrated are stacked, the sufficient statistics only when asked for.  Planes are
+        stored (columns, rows) here, so the rows are the trailing axis."""
+        if not blocks:
+            raise LegumeError(1, "vconcat of empty block list")
+        first = blocks[0]
+        if any(b.num_columns != first.num_columns for b in blocks):
+            raise LegumeError(1, "vconcat: blocks differ in their column count")
+        out = cls(first.ctx, (sum(b.num_rows for b in blocks), first.num_columns), first.a0, first.b0)
+        stack = lambda name: np.concatenate([np.asarray(getattr(b, name)) for b in blocks], axis=1)
+        out.a_stat = stack("a_stat") if stack_stats else None
+        out.b_stat = stack("b_stat") if stack_stats else None
+        for name in ("estimated_mean", "estimated_sd", "estimated_log_mean", "estimated_log_sd"):
+            setattr(out, name, stack(name) if getattr(first, name) is not None else None)
+        return out
 
     def posterior_mean(self):
         return self.estimated_mean
@@ -758,11 +837,17 @@ class SparseIoVec:
 
     # ---- groups.rs:13-37 ----
     def assign_groups(self, column_to_group, ncolumns_per_group=None):
-        if ncolumns_per_group is not None:
-            raise LegumeError(1, "ncolumns_per_group down-sampling is outside the hot path (utils.rs:48-62)")
+        """groups.rs:13-37.  ncolumns_per_group: groups with more columns are down-sampled to that many
+        (partition_by_membership, matrix-util/src/utils.rs:36-66): one generator per group, seeded with
+        mix_seed(PARTITION_SHUFFLE_SEED, smallest member) so the subset does not depend on thread order; the columns
+        left out belong to no group (label 0xFFFFFFFF: every statistic skips them).  The subset itself is NOT the
+        reference's: that is rand 0.9's SmallRng + SliceRandom::shuffle, a third-party stream that is not restated
+        (parity unpinned) — the sizes, the seeding rule and the run-to-run stability are."""
         if len(column_to_group) != self.num_columns():
             raise LegumeError(1, "group membership length mismatches the number of columns")
         self.col_to_group, self.group_keys = _rank_labels(column_to_group)
+        if ncolumns_per_group is not None:
+            self.col_to_group = downsample_groups(self.col_to_group, len(self.group_keys), int(ncolumns_per_group))
 
     def num_groups(self):
         return 0 if self.group_keys is None else len(self.group_keys)
@@ -832,7 +917,7 @@ class SparseIoVec:
         codes_h = codes.cpu().numpy().astype(np.uint64) if _is_torch(codes) else codes
         self.binary_codes = codes_h
         group, ng = assign_groups_from_codes(self.ctx, codes_h, kk)
-        self.col_to_group = group
+        self.col_to_group = group if ncols_per_group is None else downsample_groups(np.asarray(group), ng, int(ncols_per_group))
         self.group_keys = sorted({str(int(c)) for c in np.unique(codes_h)}, key=lambda s: s.encode())
         return int(codes_h.max()) + 1
 

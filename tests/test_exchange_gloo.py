@@ -233,3 +233,25 @@ def test_single_process_is_the_identity():
     rows, cnt = ex.all_gather_rows(x)
     assert cnt == [4] and rows is x
     assert ex.exchange_query_lists(x, [4]).shape == (1, 4, 3)
+
+
+# ---- host logic of the mirror that needs no GPU -----------------------------------------------------------------------
+def test_downsample_groups_host_logic():
+    """partition_by_membership with nelem_per_group (matrix-util/src/utils.rs:36-66): sizes, per-group seeding by the smallest
+    member (the subset of one group does not depend on the other groups), stability from run to run"""
+    import legume_b200 as lg
+    rng = np.random.default_rng(0)
+    g = rng.integers(0, 5, 400).astype(np.uint32)
+    out = lg.downsample_groups(g, 5, 30)
+    assert np.array_equal(out, lg.downsample_groups(g, 5, 30))
+    for k in range(5):
+        assert (out == k).sum() == min(30, (g == k).sum())
+        assert np.all(g[out == k] == k)
+    assert np.all((out == g) | (out == 0xFFFFFFFF))
+    # the members of group 2 keep their draw when another group changes
+    g2 = g.copy()
+    g2[g2 == 4] = 3
+    assert np.array_equal(lg.downsample_groups(g2, 5, 30) == 2, out == 2)
+    # nothing to do below the target
+    assert np.array_equal(lg.downsample_groups(g, 5, 1000), g)
+    assert lg.mix_seed(lg.PARTITION_SHUFFLE_SEED, 7) == lg.mix_seed(0x5041525453485546, 7)

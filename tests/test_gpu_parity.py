@@ -324,6 +324,40 @@ def test_project_fused_form_is_bit_identical(lg, ctx, monkeypatch):
             assert got["0"].tobytes() == got["1"].tobytes(), (D, N, lo, hi)
 
 
+def test_assign_groups_downsampled_and_gamma_vconcat(lg, ctx):
+    """assign_groups(.., ncolumns_per_group) (groups.rs:13-37 + utils.rs:36-66): the columns left out of a down-sampled group
+    belong to no group and every statistic skips them; GammaMatrix::vconcat (dmatrix_gamma.rs:301-326) stacks gene blocks
+    of calibrated planes into the planes of the whole fit"""
+    rng = np.random.default_rng(12)
+    D, N, S = 300, 2000, 6
+    ip, ix, v = random_csc(rng, D, N, 0.08)
+    labels = rng.integers(0, S, N)
+    data = lg.SparseIoVec.from_csc(ctx, ip, ix, v, D)
+    data.assign_groups(labels, ncolumns_per_group=150)
+    grp = np.asarray(data.get_group_membership())
+    assert all((grp == k).sum() == min(150, (labels == k).sum()) for k in range(S)) and (grp == 0xFFFFFFFF).sum() == N - 6 * 150
+    stat = lg.CollapsedStat(D, S, 1)
+    data.collect_basic_stat(stat)
+    wsum, wsize = orc.collapse_basic(ip, ix, v, D, grp, S)
+    assert np.array_equal(stat.observed_sum_ds, wsum) and np.array_equal(stat.size_s, wsize) and np.all(wsize == 150)
+    # vconcat: fit gene blocks separately, stack, compare with the whole fit
+    whole = lg.GammaMatrix(ctx, (D, S), 1.0, 1.0)
+    whole.update_stat(stat.observed_sum_ds, np.repeat(stat.size_s[:, None], D, axis=1))
+    whole.calibrate()
+    blocks = []
+    for r0 in range(0, D, 110):
+        sub = stat.select_rows(r0, min(110, D - r0))
+        b = lg.GammaMatrix(ctx, (sub.num_genes(), S), 1.0, 1.0)
+        b.update_stat(sub.observed_sum_ds, np.repeat(sub.size_s[:, None], sub.num_genes(), axis=1))
+        b.calibrate()
+        blocks.append(b)
+    cat = lg.GammaMatrix.vconcat(blocks, stack_stats=False)
+    assert (cat.nrows(), cat.ncols()) == (D, S) and cat.a_stat is None
+    for plane in ("estimated_mean", "estimated_sd", "estimated_log_mean", "estimated_log_sd"):
+        assert np.array_equal(getattr(cat, plane), getattr(whole, plane)), plane
+    assert np.array_equal(lg.GammaMatrix.vconcat(blocks, True).a_stat, whole.a_stat)
+
+
 def test_tensor_path_fallbacks_are_counted_not_silent(lg, ctx, capfd):
     """a call the tcgen05 paths cannot take (K > 53 for the projection) runs on the CUDA-core kernel with the same contract,
     and says so: once on stderr per distinct reason, and in lg_ctx_fallback_count / lg_ctx_last_fallback"""
@@ -343,7 +377,8 @@ def test_tensor_path_fallbacks_are_counted_not_silent(lg, ctx, capfd):
     if want is not None:
         assert close(raw, want, TOL)
     # a call the tensor path takes does not count
-    ctx.check(lg.lib.lg_project_raw(ctx.h, blk.h, np.ascontiguousarray(basis[:, :50]).ctypes.data, 50, np.empty((N, 50), np.float32).ctypes.data))
+    b50, r50 = np.ascontiguousarray(basis[:, :50]), np.empty((N, 50), np.float32)  # kept alive across the call
+    ctx.check(lg.lib.lg_project_raw(ctx.h, blk.h, b50.ctypes.data, 50, r50.ctypes.data))
     assert lg.lib.lg_ctx_fallback_count(ctx.h) == before + 2
 
 
