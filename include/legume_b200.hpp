@@ -124,6 +124,9 @@ struct CollapsedStat {
     std::vector<float> size_s;                                 // S
     DMatrix observed_sum_db;                                   // D x B
     DMatrix n_bs;                                              // B x S
+    // panel observability (stats.rs:556-567): per-(gene, sample) effective sizes and the (gene, batch) mask of delta;
+    // nullopt = fully observed, the historical code path
+    std::optional<DMatrix> size_ds, obs_mask_db;
     CollapsedStat(size_t ngene, size_t nsample, size_t nbatch)
         : observed_sum_ds(ngene, nsample), imputed_sum_ds(ngene, nsample), residual_sum_ds(ngene, nsample), size_s(nsample, 0.0f),
           observed_sum_db(ngene, nbatch), n_bs(nbatch, nsample) {}
@@ -219,8 +222,9 @@ inline CollapsedOut optimize(const Context& ctx, const CollapsedStat& stat, std:
             p.log_mean = DMatrix(D, S);
             lm = p.log_mean.data.data();
         }
-        ctx.check(lg_optimize_single(ctx.get(), stat.observed_sum_ds.data.data(), stat.size_s.data(), D, (uint32_t)S, hyper.first,
-                                     hyper.second, (int)target, p.mean.data.data(), sd, lm, ls));
+        ctx.check(lg_optimize_single_obs(ctx.get(), stat.observed_sum_ds.data.data(), stat.size_s.data(),
+                                         stat.size_ds ? stat.size_ds->data.data() : nullptr, D, (uint32_t)S, hyper.first, hyper.second,
+                                         (int)target, p.mean.data.data(), sd, lm, ls));
         return out;
     }
     out.mu_observed.mean = DMatrix(D, S);
@@ -237,20 +241,49 @@ inline CollapsedOut optimize(const Context& ctx, const CollapsedStat& stat, std:
         out.mu_adjusted->log_mean = DMatrix(D, S);
         lm = out.mu_adjusted->log_mean.data.data();
     }
-    ctx.check(lg_optimize_batched(ctx.get(), stat.observed_sum_ds.data.data(), stat.imputed_sum_ds.data.data(),
-                                  stat.residual_sum_ds.data.data(), stat.size_s.data(), stat.observed_sum_db.data.data(),
-                                  stat.n_bs.data.data(), D, (uint32_t)S, (uint32_t)B, hyper.first, hyper.second, (int)num_iter, (int)target,
-                                  out.mu_observed.mean.data.data(), out.mu_adjusted->mean.data.data(), out.mu_residual->mean.data.data(),
-                                  out.gamma->mean.data.data(), out.delta->mean.data.data(), lm));
+    ctx.check(lg_optimize_batched_obs(ctx.get(), stat.observed_sum_ds.data.data(), stat.imputed_sum_ds.data.data(),
+                                      stat.residual_sum_ds.data.data(), stat.size_s.data(), stat.size_ds ? stat.size_ds->data.data() : nullptr,
+                                      stat.observed_sum_db.data.data(), stat.n_bs.data.data(),
+                                      stat.obs_mask_db ? stat.obs_mask_db->data.data() : nullptr, D, (uint32_t)S, (uint32_t)B, hyper.first,
+                                      hyper.second, (int)num_iter, (int)target, out.mu_observed.mean.data.data(),
+                                      out.mu_adjusted->mean.data.data(), out.mu_residual->mean.data.data(), out.gamma->mean.data.data(),
+                                      out.delta->mean.data.data(), lm));
     return out;
 }
 
-// collapse_data/mod.rs:64-130 (the fields the un-refined path reads)
+// collapse_data/mod.rs:64-130.  MultilevelParams::new sets refine = Some(default): served for one batch, where
+// refine_or_identity keeps the compacted hash partition (refine.rs:126-147); the BBKNN + DC-SBM refinement over several
+// batches is SURVEY.md section 8f rank 3 and refused.  refine = false is the legacy un-refined descent.
 struct MultilevelParams {
-    size_t knn_pb_samples = DEFAULT_KNN, num_levels = DEFAULT_NUM_LEVELS, sort_dim = 10, num_opt_iter = DEFAULT_OPT_ITER;
-    bool refine = false;  // BBKNN + DC-SBM refinement is outside the hot path
-    explicit MultilevelParams(size_t proj_dim) : sort_dim(std::min<size_t>(proj_dim, 10)) {}
+    size_t knn_pb_samples = DEFAULT_KNN, num_levels = DEFAULT_NUM_LEVELS, sort_dim = 12, num_opt_iter = DEFAULT_OPT_ITER;
+    bool refine = true;
+    CalibrateTarget output_calibration = CalibrateTarget::All;
+    explicit MultilevelParams(size_t proj_dim) : sort_dim(std::min<size_t>(proj_dim, 12)) {}
 };
+
+// MultilevelCollapseOut (collapse_data/mod.rs): the levels finest-first and every level's cell -> pb map
+struct MultilevelCollapseOut {
+    std::vector<CollapsedOut> levels;
+    std::vector<std::vector<uint32_t>> cell_to_pb_per_level;
+    std::vector<CollapsedStat> stats;
+};
+
+// dc_poisson.rs:493-509: labels -> 0..k in order of first appearance
+inline std::pair<std::vector<uint32_t>, uint32_t> compact_labels(const std::vector<uint64_t>& labels) {
+    std::map<uint64_t, uint32_t> lut;
+    std::vector<uint32_t> out;
+    out.reserve(labels.size());
+    for (uint64_t g : labels) out.push_back(lut.emplace(g, (uint32_t)lut.size()).first->second);
+    return {out, (uint32_t)lut.size()};
+}
+// refine.rs:43-62: the coarse label of the first pb-sample of every fine group
+inline std::vector<uint32_t> fine_to_coarse_from_refined(const std::vector<uint32_t>& p2f, const std::vector<uint32_t>& p2c,
+                                                         uint32_t num_fine) {
+    std::vector<uint32_t> m(num_fine, 0xFFFFFFFFu);
+    for (size_t p = 0; p < p2f.size(); ++p)
+        if (m[p2f[p]] == 0xFFFFFFFFu) m[p2f[p]] = p2c[p];
+    return m;
+}
 
 // data-beans/src/sparse_io_vector: one preloaded backend's columns on the device + the derived caches (mod.rs:70-85)
 // matrix-util/src/sparse_stat.rs:33-198, 404-431 with T = f32.  The sufficient statistics are kept as f64 (exact whole
@@ -504,13 +537,17 @@ class SparseIoVec {
     std::vector<CollapsedOut> collapse_columns_multilevel_vec(const DMatrix& proj_kn, const std::vector<T>& batch_membership,
                                                               const MultilevelParams& params,
                                                               std::vector<CollapsedStat>* stats_out = nullptr) {
-        if (params.refine) throw Error(LG_ERR_INVALID, "BBKNN + DC-SBM refinement is outside the hot path (SURVEY.md §8f rank 3)");
         register_batch_membership(batch_membership);
         const uint32_t nb = (uint32_t)num_batches();
         if (nb >= 2) build_hnsw_per_batch(proj_kn, batch_membership);
         const std::vector<size_t> level_dims = compute_level_sort_dims(params.sort_dim, params.num_levels);
         partition_columns_to_groups(proj_kn, level_dims[0]);
         const uint32_t ng = (uint32_t)num_groups_;
+        if (params.refine) {  // mod.rs:914-941
+            MultilevelCollapseOut out = refine_and_collect(proj_kn, level_dims, params, nullptr);
+            if (stats_out) *stats_out = std::move(out.stats);
+            return std::move(out.levels);
+        }
         CollapsedStat fine(nrows_, ng, nb);
         collect_basic_stat(fine);
         if (nb >= 2) {
@@ -561,7 +598,143 @@ class SparseIoVec {
         return results;
     }
 
+    // ---- collapse_columns_multilevel_with_hierarchy (collapse_data/mod.rs:534-607) ----
+    template <typename T>
+    MultilevelCollapseOut collapse_columns_multilevel_with_hierarchy(const DMatrix& proj_kn, const std::vector<T>& batch_membership,
+                                                                     const MultilevelParams& params) {
+        if (!params.refine)
+            throw Error(LG_ERR_INVALID, "collapse_columns_multilevel_with_hierarchy requires MultilevelParams.refine = Some(..); the "
+                                        "legacy non-refinement path doesn't surface per-level cell->pb mappings");
+        register_batch_membership(batch_membership);
+        if (num_batches() >= 2) build_hnsw_per_batch(proj_kn, batch_membership);
+        const std::vector<size_t> level_dims = compute_level_sort_dims(params.sort_dim, params.num_levels);
+        partition_columns_to_groups(proj_kn, level_dims[0]);
+        return refine_and_collect(proj_kn, level_dims, params, nullptr);
+    }
+    // ---- collapse_columns_multilevel_with_partition (collapse_data/mod.rs:617-821): every level's pb-sample -> group by
+    //      majority vote of an inherited cell -> pb map (ties: the smallest label; the reference leaves them to its hash map) ----
+    template <typename T>
+    MultilevelCollapseOut collapse_columns_multilevel_with_partition(const DMatrix& proj_kn, const std::vector<T>& batch_membership,
+                                                                     const MultilevelParams& params,
+                                                                     const std::vector<std::vector<uint32_t>>& cell_to_pb_per_level) {
+        register_batch_membership(batch_membership);
+        if (num_batches() >= 2) build_hnsw_per_batch(proj_kn, batch_membership);
+        const std::vector<size_t> level_dims = compute_level_sort_dims(params.sort_dim, params.num_levels);
+        if (cell_to_pb_per_level.size() != level_dims.size())
+            throw Error(LG_ERR_INVALID, "inherited cell_to_pb has " + std::to_string(cell_to_pb_per_level.size()) +
+                                            " levels but --num-levels is " + std::to_string(level_dims.size()));
+        for (const auto& lvl : cell_to_pb_per_level)
+            if (lvl.size() != ncols_) throw Error(LG_ERR_INVALID, "inherited cell_to_pb level has the wrong number of cells");
+        partition_columns_to_groups(proj_kn, level_dims[0]);
+        MultilevelParams p = params;
+        p.output_calibration = CalibrateTarget::All;
+        return refine_and_collect(proj_kn, level_dims, p, &cell_to_pb_per_level);
+    }
+
    private:
+    // refine_and_collect_single_layer (refine.rs:264-500) and the tail of ..._with_partition (mod.rs:715-815): pb-samples
+    // from the finest hash partition, every level's pb-sample -> group (hash-initialised and compacted, or inherited by
+    // majority vote), finest statistics from one data pass, merge_stat descent along fine_to_coarse_from_refined
+    MultilevelCollapseOut refine_and_collect(const DMatrix& proj_kn, const std::vector<size_t>& level_dims, const MultilevelParams& params,
+                                             const std::vector<std::vector<uint32_t>>* inherited) {
+        const uint32_t nb = (uint32_t)num_batches(), nbl = std::max<uint32_t>(nb, 1), ng = (uint32_t)num_groups_;
+        if (!inherited && nb >= 2)
+            throw Error(LG_ERR_INVALID, "BBKNN + DC-SBM refinement over two or more batches is outside the hot path (SURVEY.md section "
+                                        "8f rank 3); set refine = false or inherit a partition");
+        const size_t cap = (size_t)ng * nbl, K = proj_kn.nrows;
+        std::vector<uint32_t> c2p(ncols_), pg(cap), pb(cap), zero_batch;
+        std::vector<float> cnt(cap), cen(cap * K);
+        const uint32_t* bat = col_to_batch_.data();
+        if (col_to_batch_.empty()) {
+            zero_batch.assign(ncols_, 0u);
+            bat = zero_batch.data();
+        }
+        uint32_t npb = 0;
+        ctx_.check(lg_pb_layout(ctx_.get(), proj_kn.data.data(), (int)K, ncols_, col_to_group_.data(), ng, bat, nbl, mult(), c2p.data(),
+                                pg.data(), pb.data(), cnt.data(), cen.data(), &npb));
+        std::vector<float> gene_sums((size_t)nrows_ * npb), gsize(npb);
+        ctx_.check(lg_collapse_basic(ctx_.get(), csc_, c2p.data(), mult(), npb, gene_sums.data(), gsize.data()));
+        // every level's pb-sample -> group
+        std::vector<std::vector<uint32_t>> p2g;
+        std::vector<uint32_t> k_level;
+        if (inherited) {
+            for (const auto& lvl : *inherited) {
+                std::vector<std::map<uint32_t, uint32_t>> votes(npb);
+                for (size_t c = 0; c < ncols_; ++c)
+                    if (c2p[c] != 0xFFFFFFFFu) votes[c2p[c]][lvl[c]]++;
+                std::vector<uint64_t> modal(npb, 0);
+                for (uint32_t p = 0; p < npb; ++p) {
+                    uint32_t best = 0;
+                    for (const auto& kv : votes[p])  // ascending labels: the first maximum is the smallest label
+                        if (kv.second > best) {
+                            best = kv.second;
+                            modal[p] = kv.first;
+                        }
+                }
+                auto cl = compact_labels(modal);
+                p2g.push_back(std::move(cl.first));
+                k_level.push_back(cl.second);
+            }
+        } else {
+            std::vector<size_t> first(npb, ncols_);  // a pb-sample's first cell carries its finest code (refine.rs:68-88)
+            for (size_t c = ncols_; c-- > 0;)
+                if (c2p[c] != 0xFFFFFFFFu) first[c2p[c]] = c;
+            for (size_t d : level_dims) {
+                const uint64_t mask = d >= 64 ? ~0ull : ((1ull << d) - 1);
+                std::vector<uint64_t> codes(npb);
+                for (uint32_t p = 0; p < npb; ++p) codes[p] = binary_codes_[first[p]] & mask;
+                auto cl = compact_labels(codes);
+                p2g.push_back(std::move(cl.first));
+                k_level.push_back(cl.second);
+            }
+        }
+        // finest groups: pad_numeric_labels + assign_groups = the numeric id itself (refine.rs:21-35, 393-399)
+        const uint32_t k0 = k_level[0];
+        for (size_t c = 0; c < ncols_; ++c) col_to_group_[c] = p2g[0][c2p[c]];
+        num_groups_ = k0;
+        MultilevelCollapseOut out;
+        CollapsedStat fine(nrows_, k0, nb);
+        collect_basic_stat(fine);
+        if (nb >= 2) {
+            collect_batch_stat(fine);
+            const uint32_t nslot = nb * (uint32_t)params.knn_pb_samples;
+            std::vector<uint32_t> mp((size_t)npb * nslot);
+            std::vector<float> md((size_t)npb * nslot);
+            ctx_.check(lg_pb_match(ctx_.get(), proj_kn.data.data(), (int)K, ncols_, col_to_batch_.data(), nb, c2p.data(), cen.data(), pb.data(),
+                                   npb, (int)params.knn_pb_samples, mp.data(), md.data()));
+            ctx_.check(lg_collect_matched_stat_coarse(ctx_.get(), gene_sums.data(), nrows_, npb, cnt.data(), p2g[0].data(), k0, mp.data(),
+                                                      md.data(), nslot, fine.imputed_sum_ds.data.data(), fine.residual_sum_ds.data.data()));
+        }
+        out.levels.push_back(optimize(ctx_, fine, {1.0f, 1.0f}, params.num_opt_iter, params.output_calibration));
+        out.stats.push_back(std::move(fine));
+        for (size_t level = 1; level < k_level.size(); ++level) {
+            const uint32_t prev_n = k_level[level - 1], nc = k_level[level];
+            const std::vector<uint32_t> f2c = fine_to_coarse_from_refined(p2g[level - 1], p2g[level], prev_n);
+            const CollapsedStat& prev = out.stats.back();
+            CollapsedStat coarse(nrows_, nc, nb);
+            ctx_.check(lg_merge_stat(ctx_.get(), prev.observed_sum_ds.data.data(), nrows_, prev_n, f2c.data(), nc, coarse.observed_sum_ds.data.data()));
+            ctx_.check(lg_merge_stat(ctx_.get(), prev.imputed_sum_ds.data.data(), nrows_, prev_n, f2c.data(), nc, coarse.imputed_sum_ds.data.data()));
+            ctx_.check(lg_merge_stat(ctx_.get(), prev.residual_sum_ds.data.data(), nrows_, prev_n, f2c.data(), nc, coarse.residual_sum_ds.data.data()));
+            for (uint32_t f = 0; f < prev_n; ++f) {
+                coarse.size_s[f2c[f]] += prev.size_s[f];
+                for (uint32_t b = 0; b < nb; ++b) coarse.n_bs(b, f2c[f]) += prev.n_bs(b, f);
+            }
+            coarse.observed_sum_db = prev.observed_sum_db;
+            if (prev.size_ds) {
+                coarse.size_ds.emplace(nrows_, nc);
+                ctx_.check(lg_merge_stat(ctx_.get(), prev.size_ds->data.data(), nrows_, prev_n, f2c.data(), nc, coarse.size_ds->data.data()));
+            }
+            coarse.obs_mask_db = prev.obs_mask_db;
+            out.levels.push_back(optimize(ctx_, coarse, {1.0f, 1.0f}, std::max<size_t>(params.num_opt_iter / 2, 10), params.output_calibration));
+            out.stats.push_back(std::move(coarse));
+        }
+        for (const auto& lvl : p2g) {
+            std::vector<uint32_t> c2g(ncols_);
+            for (size_t c = 0; c < ncols_; ++c) c2g[c] = lvl[c2p[c]];
+            out.cell_to_pb_per_level.push_back(std::move(c2g));
+        }
+        return out;
+    }
     const float* mult() const { return multiplicity_.empty() ? nullptr : multiplicity_.data(); }
     const Context& ctx_;
     lg_csc* csc_ = nullptr;

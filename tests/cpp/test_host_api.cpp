@@ -181,6 +181,7 @@ int main() {
     }
     {  // ---- collapse_columns_multilevel_vec (pb-sample matched stats) vs the oracle's composition ----
         MultilevelParams params(K);
+        params.refine = false;  // the legacy un-refined descent (MultilevelParams::new has refine = Some)
         params.sort_dim = 5;
         params.num_levels = 2;
         params.knn_pb_samples = 3;
@@ -211,6 +212,68 @@ int main() {
                              mu_adj.data(), mu_res.data(), gam.data(), delta.data(), lm.data());
         CHECK(close_all(levels[0].mu_adjusted->mean.data.data(), mu_adj.data(), mu_adj.size(), 1e-4));
         CHECK(close_all(levels[0].delta->mean.data.data(), delta.data(), delta.size(), 1e-4));
+    }
+    {  // ---- the refinement arm with ONE batch (refine.rs:126-147, 264-500): hash partition compacted per level, merge descent ----
+        SparseIoVec one(ctx, m.indptr, m.indices, m.data, m.nrows);
+        MultilevelParams params(K);
+        params.sort_dim = 6;
+        params.num_levels = 3;
+        params.num_opt_iter = 12;
+        std::vector<uint32_t> b1(N, 0u);
+        MultilevelCollapseOut out = one.collapse_columns_multilevel_with_hierarchy(rp.proj, b1, params);
+        const std::vector<size_t> dims = compute_level_sort_dims(6, 3);
+        CHECK(params.refine && out.levels.size() == dims.size() && out.cell_to_pb_per_level.size() == dims.size());
+        std::vector<uint64_t> codes(N);
+        CHECK(orc_binary_codes(rp.proj.data.data(), (int)K, N, (int)dims[0], codes.data(), nullptr, nullptr, nullptr, nullptr) == 0);
+        // one batch: a pb-sample is a hash group, so level l is the compacted masked code of the group's first cell
+        std::vector<uint32_t> hash_grp(N);
+        const uint32_t ng = orc_assign_groups(codes.data(), N, hash_grp.data());
+        std::vector<uint32_t> c2p(N), pg(ng), pb(ng);
+        std::vector<float> cnt(ng), cen((size_t)ng * K);
+        const uint32_t npb = orc_pb_layout(rp.proj.data.data(), (int)K, N, hash_grp.data(), ng, b1.data(), 1, nullptr, c2p.data(), pg.data(),
+                                           pb.data(), cnt.data(), cen.data());
+        bool maps_ok = npb == ng;
+        for (size_t level = 0; level < dims.size() && maps_ok; ++level) {
+            std::vector<uint64_t> first_code(npb, ~0ull);
+            for (size_t c = N; c-- > 0;) first_code[c2p[c]] = codes[c] & ((1ull << dims[level]) - 1);
+            auto cl = compact_labels(first_code);
+            for (size_t c = 0; c < N; ++c) maps_ok = maps_ok && out.cell_to_pb_per_level[level][c] == cl.first[c2p[c]];
+            CHECK(out.stats[level].num_samples() == cl.second);
+        }
+        CHECK(maps_ok);
+        const std::vector<uint32_t>& fine = out.cell_to_pb_per_level[0];
+        const uint32_t S0 = (uint32_t)out.stats[0].num_samples();
+        std::vector<float> ws((size_t)D * S0), wn(S0);
+        orc_collapse_basic(m.indptr.data(), m.indices.data(), m.data.data(), D, N, fine.data(), nullptr, S0, ws.data(), wn.data());
+        CHECK(out.stats[0].observed_sum_ds.data == ws && out.stats[0].size_s == wn);
+        std::vector<float> mean((size_t)D * S0), sd((size_t)D * S0), lm((size_t)D * S0), ls((size_t)D * S0);
+        orc_optimize_single(ws.data(), wn.data(), D, S0, 1.0f, 1.0f, 0, mean.data(), sd.data(), lm.data(), ls.data());
+        CHECK(close_all(out.levels[0].mu_observed.mean.data.data(), mean.data(), mean.size(), 1e-5));
+        CHECK(close_all(out.levels[0].mu_observed.log_mean.data.data(), lm.data(), lm.size(), 1e-5));
+        // the coarsest level's sums are the finest ones merged: totals per gene agree exactly (whole numbers)
+        const CollapsedStat& last = out.stats.back();
+        bool totals = true;
+        for (size_t g = 0; g < D && totals; ++g) {
+            double a = 0, b = 0;
+            for (size_t sidx = 0; sidx < S0; ++sidx) a += out.stats[0].observed_sum_ds(g, sidx);
+            for (size_t sidx = 0; sidx < last.num_samples(); ++sidx) b += last.observed_sum_ds(g, sidx);
+            totals = a == b;
+        }
+        CHECK(totals);
+        // inheriting the finest map as a one-level partition reproduces the finest statistics
+        MultilevelParams p1(K);
+        p1.sort_dim = 6;
+        p1.num_levels = 1;
+        SparseIoVec again(ctx, m.indptr, m.indices, m.data, m.nrows);
+        MultilevelCollapseOut inh = again.collapse_columns_multilevel_with_partition(rp.proj, b1, p1, {fine});
+        CHECK(inh.levels.size() == 1 && inh.stats[0].observed_sum_ds.data == out.stats[0].observed_sum_ds.data);
+        bool threw = false;
+        try {
+            again.collapse_columns_multilevel_with_partition(rp.proj, b1, params, {fine});  // 1 level given, 3 asked for
+        } catch (const Error&) {
+            threw = true;
+        }
+        CHECK(threw);
     }
     {  // ---- either side of the path: running statistics (sparse_stat.rs:671-728) and the Nystrom pass ----
         std::mt19937 rng21(21);
