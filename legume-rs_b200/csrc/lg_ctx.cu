@@ -143,6 +143,66 @@ __global__ void k_expand_u8(const uint8_t* __restrict__ src, float* __restrict__
         if (src[t] != 255) dst[t] = (float)src[t];
     for (uint64_t t = i; t < npatch; t += stride) dst[patch[t].pos] = patch[t].val;
 }
+// Row indices that travelled as one-byte gaps (upload_narrow_on_host): entry i is the entry before it plus byte i; byte 0
+// marks an entry whose gap does not fit (a column start, a gap above 255) and is found in the patch list as
+// (position, gap modulo 2^32).  Every tile of LG_UP_TILE entries carries the absolute value of the entry before it
+// (its anchor), so tiles decode independently: one inclusive sum per tile, 8 consecutive entries per thread.
+constexpr uint32_t LG_UP_TILE = 2048;
+struct LgUpIPatch {
+    uint32_t pos;
+    uint32_t gap;
+};
+__global__ void __launch_bounds__(256) k_expand_idx_gaps(const uint8_t* __restrict__ bytes, const uint32_t* __restrict__ anchors,
+                                                         const LgUpIPatch* __restrict__ patch, uint32_t npatch,
+                                                         uint32_t* __restrict__ dst, uint32_t n) {
+    __shared__ uint32_t wsum[8];
+    const uint32_t base = blockIdx.x * LG_UP_TILE + threadIdx.x * 8;
+    uint32_t d[8];
+    if (base + 8 <= n) {
+        const uint2 w = *reinterpret_cast<const uint2*>(bytes + base);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            d[k] = (w.x >> (8 * k)) & 255u;
+            d[4 + k] = (w.y >> (8 * k)) & 255u;
+        }
+    } else {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) d[k] = base + k < n ? bytes[base + k] : 1u;
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        if (d[k] == 0u && base + k < n) {  // rare: look the gap up (positions ascend in the list)
+            uint32_t lo = 0, hi = npatch;
+            while (lo < hi) {
+                const uint32_t mid = (lo + hi) >> 1;
+                if (patch[mid].pos < base + k) lo = mid + 1;
+                else hi = mid;
+            }
+            d[k] = patch[lo].gap;
+        }
+    }
+#pragma unroll
+    for (int k = 1; k < 8; ++k) d[k] += d[k - 1];
+    uint32_t run = d[7];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xffffffffu, run, off);
+        if (lane >= off) run += t;
+    }
+    if (lane == 31) wsum[warp] = run;
+    __syncthreads();
+    uint32_t before = anchors[blockIdx.x] + run - d[7];
+    for (int w = 0; w < warp; ++w) before += wsum[w];
+    if (base + 8 <= n) {
+        reinterpret_cast<uint4*>(dst + base)[0] = make_uint4(before + d[0], before + d[1], before + d[2], before + d[3]);
+        reinterpret_cast<uint4*>(dst + base)[1] = make_uint4(before + d[4], before + d[5], before + d[6], before + d[7]);
+    } else {
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+            if (base + k < n) dst[base + k] = before + d[k];
+    }
+}
 __global__ void k_rebase_indptr(const uint64_t* __restrict__ src, uint64_t* __restrict__ dst, uint64_t n,
                                 uint64_t base) {
     uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -163,6 +223,9 @@ namespace {
 constexpr uint64_t UP_CHUNK = 2ull << 20;          // non-zeros per ring slot
 constexpr uint64_t UP_PATCH_BYTES = 8ull << 16;     // UP_PATCH_CAP (position, f32) pairs
 constexpr uint64_t UP_SLOT_BYTES = UP_CHUNK * 5 + UP_PATCH_BYTES;       // u32 indices, u8 values, patch list
+constexpr uint64_t UP_ANCHOR_BYTES = (UP_CHUNK / 2048) * 4;             // one u32 per LG_UP_TILE entries
+constexpr uint64_t UP_GAP_SLOT = UP_ANCHOR_BYTES + UP_CHUNK + 8 + UP_PATCH_BYTES;  // device twin of a slot's index part as gaps
+static_assert(UP_ANCHOR_BYTES + UP_CHUNK + 2 * UP_PATCH_BYTES + 8 <= UP_CHUNK * 4, "the gap form fits the slot's u32 index region");
 constexpr uint64_t UP_SLOT_BYTES_RAW = UP_SLOT_BYTES + UP_CHUNK * 4;    // + raw f32 staging (pageable sources only)
 
 __attribute__((target("avx2"))) void narrow_chunk_avx2(const uint64_t* s, uint32_t* d, uint64_t n, uint64_t* or_all,
@@ -265,6 +328,95 @@ __attribute__((target("avx2"))) int64_t pack_values_avx2(const float* s, uint8_t
 }
 int64_t pack_values_plain(const float* s, uint8_t* d, uint64_t n, UpPatch* patch) { return pack_scalar(s, d, 0, n, patch, 0); }
 
+// Row indices as one-byte gaps: inside a column the rows ascend, and at the densities of count matrices (a few per cent)
+// the gap to the previous entry is below 256 for all but one entry in ~10^5, so an index travels as ONE byte instead of
+// four; the others (and every column's first entry, whose gap is negative) go into the chunk's patch list as (position,
+// gap modulo 2^32).  anchors[t] = the entry before tile t (LG_UP_TILE entries), `prev0` = the entry before s[0].
+// Returns the number of patches, or -1 when the list is full (the chunk then goes up as u32).
+struct UpIPatch {
+    uint32_t pos;
+    uint32_t gap;
+};
+inline int64_t gaps_scalar(const uint64_t* s, uint8_t* d, uint64_t lo, uint64_t hi, uint32_t prev, UpIPatch* patch, int64_t np,
+                           uint64_t* or_all, uint32_t* max_lo) {
+    uint64_t o = *or_all;
+    uint32_t m = *max_lo;
+    for (uint64_t i = lo; i < hi; ++i) {
+        o |= s[i];
+        const uint32_t v = (uint32_t)s[i];
+        m = v > m ? v : m;
+        const uint32_t g = v - prev;
+        prev = v;
+        if (g - 1u < 255u) {
+            d[i] = (uint8_t)g;
+        } else {
+            if (np >= UP_PATCH_CAP) return -1;
+            patch[np++] = UpIPatch{(uint32_t)i, g};
+            d[i] = 0;
+        }
+    }
+    *or_all = o;
+    *max_lo = m;
+    return np;
+}
+__attribute__((target("avx2"))) int64_t gaps_chunk_avx2(const uint64_t* s, uint64_t prev0, uint8_t* d, uint32_t* anchors, uint64_t n,
+                                                        UpIPatch* patch, uint64_t* or_all, uint32_t* max_lo) {
+    for (uint64_t t = 0; t * LG_UP_TILE < n; ++t) anchors[t] = (uint32_t)(t ? s[t * LG_UP_TILE - 1] : prev0);
+    const __m256i pick = _mm256_setr_epi32(0, 2, 4, 6, 0, 2, 4, 6);
+    const __m256i fix = _mm256_setr_epi32(0, 4, 1, 5, 2, 6, 3, 7);
+    const __m256i one = _mm256_set1_epi32(1), hi = _mm256_set1_epi32(~255);
+    __m256i acc = _mm256_setzero_si256(), mx = _mm256_setzero_si256();
+    int64_t np = 0;
+    // the first group reads s[-1]: done one entry at a time
+    const uint64_t head = n < 32 ? n : 32;
+    np = gaps_scalar(s, d, 0, head, (uint32_t)prev0, patch, np, or_all, max_lo);
+    if (np < 0) return -1;
+    uint64_t i = head;
+    for (; i + 32 <= n; i += 32) {
+        __m256i g[4];
+        __m256i bad = _mm256_setzero_si256();
+        for (int k = 0; k < 4; ++k) {
+            const uint64_t* p = s + i + 8 * k;
+            const __m256i a = _mm256_loadu_si256(reinterpret_cast<const __m256i*>(p));
+            const __m256i b = _mm256_loadu_si256(reinterpret_cast<const __m256i*>(p + 4));
+            const __m256i a1 = _mm256_loadu_si256(reinterpret_cast<const __m256i*>(p - 1));
+            const __m256i b1 = _mm256_loadu_si256(reinterpret_cast<const __m256i*>(p + 3));
+            acc = _mm256_or_si256(acc, _mm256_or_si256(a, b));
+            const __m256i v = _mm256_blend_epi32(_mm256_permutevar8x32_epi32(a, pick), _mm256_permutevar8x32_epi32(b, pick), 0xF0);
+            const __m256i v1 = _mm256_blend_epi32(_mm256_permutevar8x32_epi32(a1, pick), _mm256_permutevar8x32_epi32(b1, pick), 0xF0);
+            mx = _mm256_max_epu32(mx, v);
+            g[k] = _mm256_sub_epi32(v, v1);
+            bad = _mm256_or_si256(bad, _mm256_and_si256(_mm256_or_si256(_mm256_sub_epi32(g[k], one), g[k]), hi));  // gap outside 1..255
+        }
+        if (!_mm256_testz_si256(bad, bad)) {  // a column start or a wide gap in this group: one entry at a time
+            uint64_t o2 = 0;
+            uint32_t m2 = 0;
+            np = gaps_scalar(s, d, i, i + 32, (uint32_t)s[i - 1], patch, np, &o2, &m2);  // (range checks already taken above)
+            if (np < 0) return -1;
+            continue;
+        }
+        const __m256i w0 = _mm256_packus_epi32(g[0], g[1]), w1 = _mm256_packus_epi32(g[2], g[3]);
+        const __m256i b = _mm256_permutevar8x32_epi32(_mm256_packus_epi16(w0, w1), fix);
+        _mm256_storeu_si256(reinterpret_cast<__m256i*>(d + i), b);
+    }
+    alignas(32) uint64_t a4[4];
+    alignas(32) uint32_t m8[8];
+    _mm256_store_si256(reinterpret_cast<__m256i*>(a4), acc);
+    _mm256_store_si256(reinterpret_cast<__m256i*>(m8), mx);
+    uint64_t o = a4[0] | a4[1] | a4[2] | a4[3];
+    uint32_t m = 0;
+    for (int k = 0; k < 8; ++k) m = m8[k] > m ? m8[k] : m;
+    *or_all |= o;
+    *max_lo = m > *max_lo ? m : *max_lo;
+    if (i < n) np = gaps_scalar(s, d, i, n, (uint32_t)s[i - 1], patch, np, or_all, max_lo);
+    return np;
+}
+int64_t gaps_chunk_plain(const uint64_t* s, uint64_t prev0, uint8_t* d, uint32_t* anchors, uint64_t n, UpIPatch* patch,
+                         uint64_t* or_all, uint32_t* max_lo) {
+    for (uint64_t t = 0; t * LG_UP_TILE < n; ++t) anchors[t] = (uint32_t)(t ? s[t * LG_UP_TILE - 1] : prev0);
+    return gaps_scalar(s, d, 0, n, (uint32_t)prev0, patch, 0, or_all, max_lo);
+}
+
 int upload_threads() {
     if (const char* e = getenv("LG_UPLOAD_THREADS")) return atoi(e);
     unsigned hc = std::thread::hardware_concurrency();
@@ -326,6 +478,14 @@ cudaError_t upload_narrow_on_host(lg_ctx* ctx, const uint64_t* h_idx, const floa
         cudaError_t e = cudaMallocAsync(&d_bytes, nslots * (UP_CHUNK + UP_PATCH_BYTES), ctx->stream);
         if (e != cudaSuccess) return e;
     }
+    // ... and of the one-byte index gaps: [anchors][gap bytes][patches] per slot (LG_UPLOAD_NO_GAPS=1: indices travel as u32)
+    uint8_t* d_gaps = nullptr;
+    const bool gaps_ok = getenv("LG_UPLOAD_NO_GAPS") == nullptr;
+    if (gaps_ok) {
+        cudaError_t e = cudaMallocAsync(&d_gaps, nslots * UP_GAP_SLOT, ctx->stream);
+        if (e != cudaSuccess) return e;
+    }
+    std::atomic<uint64_t> gap_chunks{0};
     std::atomic<uint64_t> extra_launches{0}, packed_chunks{0}, wire{0};
     std::vector<std::atomic<int>> queued(nchunks);
     for (auto& q : queued) q.store(0, std::memory_order_relaxed);
@@ -354,7 +514,7 @@ cudaError_t upload_narrow_on_host(lg_ctx* ctx, const uint64_t* h_idx, const floa
     const bool avx2 = __builtin_cpu_supports("avx2");
     auto worker = [&]() {
         cudaSetDevice(ctx->device);
-        uint64_t my_or = 0, my_launches = 0, my_packed = 0, my_wire = 0;
+        uint64_t my_or = 0, my_launches = 0, my_packed = 0, my_wire = 0, my_gaps = 0;
         uint32_t my_max = 0;
         uint64_t i;
         while (take(true, &i)) {
@@ -396,11 +556,40 @@ cudaError_t upload_narrow_on_host(lg_ctx* ctx, const uint64_t* h_idx, const floa
                     my_wire += len * sizeof(float);
                 }
             }
-            if (avx2) narrow_chunk_avx2(h_idx + off, dst, len, &my_or, &my_max);
-            else narrow_chunk_plain(h_idx + off, dst, len, &my_or, &my_max);
-            if (e == cudaSuccess)
-                e = cudaMemcpyAsync(d_idx + off, dst, len * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream);
-            my_wire += len * sizeof(uint32_t);
+            // indices: one-byte gaps when they fit (the u32 region of the slot holds [anchors][gap bytes][patches]: ONE copy)
+            int64_t nip = -1;
+            if (gaps_ok) {
+                uint8_t* gbase = reinterpret_cast<uint8_t*>(dst);
+                uint32_t* anchors = reinterpret_cast<uint32_t*>(gbase);
+                uint8_t* gbytes = gbase + UP_ANCHOR_BYTES;
+                UpIPatch* ipatch = reinterpret_cast<UpIPatch*>(gbase + UP_ANCHOR_BYTES + UP_CHUNK + UP_PATCH_BYTES);  // scratch
+                const uint64_t prev0 = off ? h_idx[off - 1] : 0;
+                nip = avx2 ? gaps_chunk_avx2(h_idx + off, prev0, gbytes, anchors, len, ipatch, &my_or, &my_max)
+                           : gaps_chunk_plain(h_idx + off, prev0, gbytes, anchors, len, ipatch, &my_or, &my_max);
+                if (nip >= 0) {
+                    const uint64_t pofs = UP_ANCHOR_BYTES + ((len + 7) & ~7ull);  // patches travel right behind the bytes
+                    memcpy(gbase + pofs, ipatch, (size_t)nip * sizeof(UpIPatch));
+                    const uint64_t total = pofs + (uint64_t)nip * sizeof(UpIPatch);
+                    uint8_t* dg = d_gaps + slot * UP_GAP_SLOT;
+                    if (e == cudaSuccess) e = cudaMemcpyAsync(dg, gbase, total, cudaMemcpyHostToDevice, ctx->stream);
+                    if (e == cudaSuccess) {
+                        k_expand_idx_gaps<<<(unsigned)((len + LG_UP_TILE - 1) / LG_UP_TILE), 256, 0, ctx->stream>>>(
+                            dg + UP_ANCHOR_BYTES, reinterpret_cast<const uint32_t*>(dg), reinterpret_cast<const LgUpIPatch*>(dg + pofs),
+                            (uint32_t)nip, d_idx + off, (uint32_t)len);
+                        e = cudaGetLastError();
+                        ++my_launches;
+                        ++my_gaps;
+                    }
+                    my_wire += total;
+                }
+            }
+            if (nip < 0) {
+                if (avx2) narrow_chunk_avx2(h_idx + off, dst, len, &my_or, &my_max);
+                else narrow_chunk_plain(h_idx + off, dst, len, &my_or, &my_max);
+                if (e == cudaSuccess)
+                    e = cudaMemcpyAsync(d_idx + off, dst, len * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream);
+                my_wire += len * sizeof(uint32_t);
+            }
             if (e == cudaSuccess) e = cudaEventRecord(ctx->ring_ev[slot], ctx->stream);
             note(e);
             queued[i].store(1, std::memory_order_release);  // set even on error so nobody waits forever
@@ -409,6 +598,7 @@ cudaError_t upload_narrow_on_host(lg_ctx* ctx, const uint64_t* h_idx, const floa
         extra_launches.fetch_add(my_launches);
         wire.fetch_add(my_wire);
         packed_chunks.fetch_add(my_packed);
+        gap_chunks.fetch_add(my_gaps);
         uint32_t cur = max_lo.load();
         while (my_max > cur && !max_lo.compare_exchange_weak(cur, my_max)) {}
     };
@@ -455,6 +645,7 @@ cudaError_t upload_narrow_on_host(lg_ctx* ctx, const uint64_t* h_idx, const floa
         ctx->launches += extra_launches.load();
         ctx->h2d_bytes += wire.load();
         if (d_bytes) cudaFreeAsync(d_bytes, ctx->stream);
+        if (d_gaps) cudaFreeAsync(d_gaps, ctx->stream);
         if (d_flag) {
             note(cudaMemcpyAsync(&h_flag, d_flag, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
             note(cudaStreamSynchronize(ctx->stream));
@@ -463,9 +654,9 @@ cudaError_t upload_narrow_on_host(lg_ctx* ctx, const uint64_t* h_idx, const floa
         for (int k = 0; k < WD_MAX; ++k)
             if (stage[k]) cudaFreeAsync(stage[k], ctx->stream);
         if (getenv("LG_UPLOAD_TRACE"))
-            fprintf(stderr, "[lg_csc_upload] %llu chunks: %llu narrowed on %d host threads (%llu with byte values), %llu sent wide\n",
+            fprintf(stderr, "[lg_csc_upload] %llu chunks: %llu narrowed on %d host threads (%llu with byte values, %llu with one-byte index gaps), %llu sent wide\n",
                     (unsigned long long)nchunks, (unsigned long long)(nchunks - nwide), nthreads,
-                    (unsigned long long)packed_chunks.load(), (unsigned long long)nwide);
+                    (unsigned long long)packed_chunks.load(), (unsigned long long)gap_chunks.load(), (unsigned long long)nwide);
     }
     *bad = (h_flag != 0 || (or_all.load() >> 32) != 0 || (uint64_t)max_lo.load() >= nrows) ? 1 : 0;
     return (cudaError_t)first_err.load();

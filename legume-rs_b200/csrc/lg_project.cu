@@ -218,14 +218,51 @@ extern "C" int lg_project_raw(lg_ctx* ctx, const lg_csc* m, const float* basis_k
 // K2a: per-1024-cell-block f64 partial sums of proj per (batch, dim) + cell counts.
 // One block = LG_BLOCK_CELLS threads = one cell each.  partials[blk][b*(K+1) + k].
 // ---------------------------------------------------------------------------------------------
+// STAGED: the block's 1024 x K tile (one contiguous run of the projection) is first brought into shared memory with
+// 128-bit streams and a row stride of K | 1 words; the per-value reads of a thread's own row are then conflict-free
+// shared-memory loads instead of 32-sector global ones (one per lane and value: 0.33 -> 0.1 ms at 1M cells).  Same sums,
+// same tree.
+template <bool STAGED>
 __global__ void __launch_bounds__(1024) k_batch_partials(const float* __restrict__ proj, int K, uint64_t ncols,
                                                          const uint32_t* __restrict__ batch, uint32_t nbatch,
                                                          double* __restrict__ partials) {
     __shared__ double stage[LG_SUMS_BATCH * 32];
-    const uint64_t cell = (uint64_t)blockIdx.x * LG_BLOCK_CELLS + threadIdx.x;
+    extern __shared__ float ptile[];
+    const uint64_t cell0 = (uint64_t)blockIdx.x * LG_BLOCK_CELLS;
+    const uint64_t cell = cell0 + threadIdx.x;
     const bool live = cell < ncols;
     const uint32_t myb = live ? (batch ? batch[cell] : 0u) : 0xffffffffu;
     const float* row = proj + (size_t)cell * K;
+    if constexpr (STAGED) {
+        const int KS = K | 1;
+        const int ncell = (ncols - cell0) < (uint64_t)LG_BLOCK_CELLS ? (int)(ncols - cell0) : LG_BLOCK_CELLS;
+        const int total = ncell * K, nvec = total >> 2;
+        const float* src = proj + cell0 * K;  // 16-byte aligned: the host checks the base, a block is 4096 K bytes
+        const int step_r = (4 * LG_BLOCK_CELLS) / K, step_c = (4 * LG_BLOCK_CELLS) % K;
+        int r = (4 * (int)threadIdx.x) / K, c = (4 * (int)threadIdx.x) % K;
+        for (int v = threadIdx.x; v < nvec; v += LG_BLOCK_CELLS) {
+            const float4 q = __ldcs(reinterpret_cast<const float4*>(src) + v);
+            const float qq[4] = {q.x, q.y, q.z, q.w};
+            int rr = r, cc = c;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                ptile[rr * KS + cc] = qq[i];
+                if (++cc == K) {
+                    cc = 0;
+                    ++rr;
+                }
+            }
+            r += step_r;
+            c += step_c;
+            if (c >= K) {
+                c -= K;
+                ++r;
+            }
+        }
+        for (int e = (nvec << 2) + threadIdx.x; e < total; e += LG_BLOCK_CELLS) ptile[(e / K) * KS + (e % K)] = src[e];
+        __syncthreads();
+        row = ptile + (size_t)threadIdx.x * KS;
+    }
     double* outp = partials + (size_t)blockIdx.x * nbatch * (K + 1);
     // nbatch * (K + 1) sums (value k of batch b, then the cell count), LG_SUMS_BATCH at a time: same tree as
     // lg_block_sum_1024, one barrier per batch instead of two per value
@@ -251,7 +288,13 @@ extern "C" int lg_proj_batch_partials(lg_ctx* ctx, const float* d_proj, int K, u
     cudaSetDevice(ctx->device);
     const uint64_t nblk = (ncols + LG_BLOCK_CELLS - 1) / LG_BLOCK_CELLS;
     if (nblk == 0) return LG_OK;
-    LG_LAUNCH(ctx, k_batch_partials, (unsigned)nblk, LG_BLOCK_CELLS, 0, d_proj, K, ncols, d_batch, nbatch, d_partials);
+    const size_t tile = (size_t)LG_BLOCK_CELLS * (K | 1) * sizeof(float);
+    if (tile + sizeof(double) * LG_SUMS_BATCH * 32 + 1024 <= ctx->smem_optin && ((uintptr_t)d_proj & 15) == 0) {
+        LG_CUDA(ctx, cudaFuncSetAttribute(k_batch_partials<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tile));
+        LG_LAUNCH(ctx, k_batch_partials<true>, (unsigned)nblk, LG_BLOCK_CELLS, tile, d_proj, K, ncols, d_batch, nbatch, d_partials);
+    } else {
+        LG_LAUNCH(ctx, k_batch_partials<false>, (unsigned)nblk, LG_BLOCK_CELLS, 0, d_proj, K, ncols, d_batch, nbatch, d_partials);
+    }
     return LG_OK;
 }
 
@@ -314,7 +357,12 @@ __global__ void __launch_bounds__(SCALE_CELLS) k_scale_cells(float* __restrict__
     }
     const int KS = K | 1;
     float* neg_mean = tile + SCALE_CELLS * KS;  // nbatch * K
-    const uint64_t cell0 = (uint64_t)blockIdx.x * SCALE_CELLS;
+    float lmin = INFINITY, lmax = -INFINITY;
+    // a grid-stride walk over the 128-cell tiles: one tile per CTA in the usual launch; the gated clamp is launched with a
+    // few CTAs per SM only, so that the common "nothing to clamp" case costs a handful of CTAs instead of one per tile
+    const uint64_t ntiles = (ncols + SCALE_CELLS - 1) / SCALE_CELLS;
+    for (uint64_t tile_i = blockIdx.x; tile_i < ntiles; tile_i += gridDim.x) {
+    const uint64_t cell0 = tile_i * SCALE_CELLS;
     const int ncell = (ncols - cell0) < (uint64_t)SCALE_CELLS ? (int)(ncols - cell0) : SCALE_CELLS;
     const size_t total = (size_t)ncell * K;
     const float* src = proj + cell0 * K;
@@ -360,7 +408,6 @@ __global__ void __launch_bounds__(SCALE_CELLS) k_scale_cells(float* __restrict__
         }
     }
     __syncthreads();
-    float lmin = INFINITY, lmax = -INFINITY;
     if ((int)threadIdx.x < ncell) {
         float* x = tile + threadIdx.x * KS;
         if (centre) {
@@ -415,6 +462,8 @@ __global__ void __launch_bounds__(SCALE_CELLS) k_scale_cells(float* __restrict__
             }
         }
         for (int e = 4 * nvec + threadIdx.x; e < total_i; e += SCALE_CELLS) dst[e] = tile[(e / K) * KS + (e % K)];
+    }
+    __syncthreads();  // the tile is overwritten by the next round
     }
     if (MODE == 0 && minmax) {
 #pragma unroll
@@ -532,7 +581,8 @@ extern "C" int lg_proj_clamp_rescale_if(lg_ctx* ctx, float* d_proj, int K, uint6
     if (ncols == 0) return LG_OK;
     const size_t smem = scale_smem(K, 0);
     LG_CUDA(ctx, cudaFuncSetAttribute(k_scale_cells<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const uint64_t grid = (ncols + SCALE_CELLS - 1) / SCALE_CELLS;
+    uint64_t grid = (ncols + SCALE_CELLS - 1) / SCALE_CELLS;
+    if (d_minmax && grid > (uint64_t)ctx->num_sms * 8) grid = (uint64_t)ctx->num_sms * 8;  // gated: usually nothing to do
     LG_LAUNCH(ctx, k_scale_cells<1>, (unsigned)grid, SCALE_CELLS, smem, d_proj, K, ncols, (const uint32_t*)nullptr, 0u,
               (const double*)nullptr, (const float*)nullptr, (const unsigned long long*)nullptr, const_cast<float*>(d_minmax));
     return LG_OK;

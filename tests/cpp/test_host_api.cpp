@@ -216,12 +216,13 @@ int main() {
     {  // ---- the refinement arm with ONE batch (refine.rs:126-147, 264-500): hash partition compacted per level, merge descent ----
         SparseIoVec one(ctx, m.indptr, m.indices, m.data, m.nrows);
         MultilevelParams params(K);
-        params.sort_dim = 6;
+        params.sort_dim = 9;  // levels 9, 8, 7: below 8 compute_level_sort_dims gives one level only
         params.num_levels = 3;
         params.num_opt_iter = 12;
         std::vector<uint32_t> b1(N, 0u);
         MultilevelCollapseOut out = one.collapse_columns_multilevel_with_hierarchy(rp.proj, b1, params);
-        const std::vector<size_t> dims = compute_level_sort_dims(6, 3);
+        const std::vector<size_t> dims = compute_level_sort_dims(9, 3);
+        CHECK(dims.size() == 3);
         CHECK(params.refine && out.levels.size() == dims.size() && out.cell_to_pb_per_level.size() == dims.size());
         std::vector<uint64_t> codes(N);
         CHECK(orc_binary_codes(rp.proj.data.data(), (int)K, N, (int)dims[0], codes.data(), nullptr, nullptr, nullptr, nullptr) == 0);
@@ -262,7 +263,7 @@ int main() {
         CHECK(totals);
         // inheriting the finest map as a one-level partition reproduces the finest statistics
         MultilevelParams p1(K);
-        p1.sort_dim = 6;
+        p1.sort_dim = 9;
         p1.num_levels = 1;
         SparseIoVec again(ctx, m.indptr, m.indices, m.data, m.nrows);
         MultilevelCollapseOut inh = again.collapse_columns_multilevel_with_partition(rp.proj, b1, p1, {fine});

@@ -54,16 +54,20 @@ def test_csc_upload_round_trip_and_range_check(lg, ctx):
             lg.CscBlock.upload(ctx, back, ix, v, 300)
 
 
-@pytest.mark.parametrize("mode", ["default", "host_only", "host_no_pack", "device_only"])
+@pytest.mark.parametrize("mode", ["default", "host_only", "host_no_pack", "host_no_gaps", "device_only"])
 def test_csc_upload_large_block_host_narrowing(lg, ctx, mode, monkeypatch):
-    """blocks of >= 8 Mi non-zeros are narrowed u64 -> u32 by host threads into a pinned ring, count values packed to
-    bytes with a patch list (with a wide share sent through the device narrowing when the cores cannot keep up);
+    """blocks of >= 8 Mi non-zeros are narrowed by host threads into a pinned ring — row indices as one-byte gaps to the
+    previous entry (patch list for column starts and wide gaps, u32 when the list overflows), count values packed to
+    bytes with a patch list — with a wide share sent through the device narrowing when the cores cannot keep up;
     every mix must give the same device arrays, bit for bit"""
     if mode == "host_only":
         monkeypatch.setenv("LG_UPLOAD_NO_WIDE", "1")
         monkeypatch.setenv("LG_UPLOAD_THREADS", "3")
     elif mode == "host_no_pack":
         monkeypatch.setenv("LG_UPLOAD_NO_PACK", "1")
+    elif mode == "host_no_gaps":
+        monkeypatch.setenv("LG_UPLOAD_NO_GAPS", "1")
+        monkeypatch.setenv("LG_UPLOAD_NO_WIDE", "1")
     elif mode == "device_only":
         monkeypatch.setenv("LG_UPLOAD_THREADS", "0")
     rng = np.random.default_rng(5)
@@ -74,6 +78,13 @@ def test_csc_upload_large_block_host_narrowing(lg, ctx, mode, monkeypatch):
     # canonical CSC (rows strictly ascending inside a column): position p of a column lands in [29 p, 29 p + 28]
     ix = ((np.arange(nnz, dtype=np.uint64) - np.repeat(ip[:-1], np.diff(ip).astype(np.int64))) * np.uint64(29)
           + rng.integers(0, 29, nnz, dtype=np.uint64))
+    # ... gaps of 1..57 travel as one byte; every 37th column gets a gap of 256..800 somewhere (patch list), one column a gap
+    # of exactly 255 and one of exactly 256 (the largest byte / the smallest patch)
+    for c in range(3, N, 37):
+        ix[int(ip[c]) + 100 + (c % 800):int(ip[c + 1])] += np.uint64(256 + c % 545)
+    ix[int(ip[11]) + 500:int(ip[12])] += np.uint64(255) - (ix[int(ip[11]) + 500] - ix[int(ip[11]) + 499])
+    ix[int(ip[13]) + 500:int(ip[14])] += np.uint64(256) - (ix[int(ip[13]) + 500] - ix[int(ip[13]) + 499])
+    assert ix.max() < D
     v = rng.integers(0, 256, nnz).astype(np.float32)  # whole numbers 0..254 travel as bytes ...
     v[3_000_000:3_000_010] = 0.5                      # ... anything else (255 too) through the chunk's patch list ...
     v[5_000_001] = 70000.0
@@ -94,6 +105,23 @@ def test_csc_upload_large_block_host_narrowing(lg, ctx, mode, monkeypatch):
         bad[pos] = bad[pos - 1] if pos % per else bad[pos + 1]
         with pytest.raises(lg.LegumeError, match="canonical"):
             lg.CscBlock.upload(ctx, ip, bad, v, D)
+
+
+def test_csc_upload_many_short_columns_overflow_the_gap_patches(lg, ctx, monkeypatch):
+    """400k columns of 21 entries about 1400 rows apart: every gap is a patch, every chunk's list overflows and the chunk
+    travels as u32 — same arrays"""
+    monkeypatch.setenv("LG_UPLOAD_NO_WIDE", "1")
+    rng = np.random.default_rng(15)
+    D, N, per = 30000, 400_000, 21
+    nnz = N * per
+    ip = (np.arange(N + 1, dtype=np.uint64) * np.uint64(per))
+    ix = (np.tile(np.arange(per, dtype=np.uint64) * np.uint64(1400), N) + rng.integers(0, 1400, nnz, dtype=np.uint64))
+    ix[::per][: N // 2] = 0  # half of the columns start at row 0
+    v = rng.integers(1, 5, nnz).astype(np.float32)
+    blk = lg.CscBlock.upload(ctx, ip, ix, v, D)
+    ip2, ix2, v2 = blk.download()
+    blk.free()
+    assert np.array_equal(ip, ip2) and np.array_equal(ix, ix2) and v.tobytes() == v2.tobytes()
 
 
 def test_sparse_io_vec_from_several_backends_with_row_remaps(lg, ctx):

@@ -24,7 +24,8 @@ res = {}
 PAGEABLE = "--pageable" in sys.argv  # the reference's Vec<u64> / Vec<f32> slices are ordinary (pageable) host memory
 if PAGEABLE:
     h_ip, h_ix, h_v = (torch.from_numpy(t.numpy().copy()) for t in (h_ip, h_ix, h_v))
-modes = [("device_narrow", {"LG_UPLOAD_THREADS": "0"}), ("default", {}), ("host4", {"LG_UPLOAD_THREADS": "4"}),
+modes = [("device_narrow", {"LG_UPLOAD_THREADS": "0"}), ("default", {}), ("no_gaps", {"LG_UPLOAD_NO_GAPS": "1"}),
+         ("nowide", {"LG_UPLOAD_NO_WIDE": "1"}), ("host4", {"LG_UPLOAD_THREADS": "4"}),
          ("host8", {"LG_UPLOAD_THREADS": "8"}), ("host16", {"LG_UPLOAD_THREADS": "16"}), ("host32", {"LG_UPLOAD_THREADS": "32"}),
          ("host16_nowide", {"LG_UPLOAD_THREADS": "16", "LG_UPLOAD_NO_WIDE": "1"}),
          ("host16_nopack", {"LG_UPLOAD_THREADS": "16", "LG_UPLOAD_NO_PACK": "1"}),
@@ -32,9 +33,11 @@ modes = [("device_narrow", {"LG_UPLOAD_THREADS": "0"}), ("default", {}), ("host4
          ("wide6", {"LG_UPLOAD_WIDE_DEPTH": "6"}), ("wide8", {"LG_UPLOAD_WIDE_DEPTH": "8"})]
 if "--wide-only" in sys.argv:
     modes = [m for m in modes if m[0].startswith("wide")]
+if "--quick" in sys.argv:
+    modes = [m for m in modes if m[0] in ("default", "no_gaps", "nowide", "wide3", "wide4")]
 os.environ["LG_UPLOAD_TRACE"] = "1"
 for name, env in modes:
-    for k in ("LG_UPLOAD_THREADS", "LG_UPLOAD_NO_WIDE", "LG_UPLOAD_NO_PACK", "LG_UPLOAD_WIDE_DEPTH"):
+    for k in ("LG_UPLOAD_THREADS", "LG_UPLOAD_NO_WIDE", "LG_UPLOAD_NO_PACK", "LG_UPLOAD_NO_GAPS", "LG_UPLOAD_WIDE_DEPTH"):
         os.environ.pop(k, None)
     os.environ.update(env)
     rows = []
@@ -50,5 +53,6 @@ for name, env in modes:
         t3 = now()
         rows.append({"upload_ms": 1e3 * (t1 - t0), "run_ms": 1e3 * (t2 - t1), "free_ms": 1e3 * (t3 - t2)})
     res[name] = rows
+    print(name, [round(r["upload_ms"], 1) for r in rows], file=sys.stderr, flush=True)
 bytes_up = h_ip.numel() * 8 + h_ix.numel() * 8 + h_v.numel() * 4
 print(json.dumps({"cells": N, "pageable_host_arrays": PAGEABLE, "host_bytes": bytes_up, "host_cores": os.cpu_count(), "modes": res}))
