@@ -367,6 +367,29 @@ int lg_row_stats(lg_ctx* ctx, const lg_csc* m, double* out_npos, double* out_s1,
 int lg_nystrom_project(lg_ctx* ctx, const lg_csc* m, const float* basis_dk, int K, const float* delta_dp,
                        const uint32_t* pb_of_cell, uint32_t P, float column_sum_norm, float* out_proj_kn);
 
+/* ---- column-block ingest: the reference's zarr backend as the feed of the path ---------
+ * lg_zarr_* replaces, for a matrix written by the reference's zarr backend (data-beans/src/sparse_backend/zarr.rs: a Zarr V3
+ * FilesystemStore directory holding /by_column/{indptr u64, indices u64, data f32} as 1-D arrays in ~1 MiB chunks,
+ * bytes(little) + zstd level 5, root attributes nrow / ncol / nnz; zarr.rs:31-64, 285-310, 515-523;
+ * utilities/io_helpers.rs:105-115):
+ *   SparseMtxData::open + num_rows / num_columns / num_non_zeros    zarr.rs:640-690, 515-523   -> lg_zarr_open, lg_zarr_shape
+ *   preload_columns + csc_column_arrays over a column range            zarr.rs:573-587, 982-994   -> lg_zarr_read_columns_host
+ *   read_columns_csc (the block handed to the visitors)                sparse_io_vector/read.rs:172-285 -> lg_zarr_read_columns
+ * Chunks are inflated on the host cores (libzstd bound at run time with dlopen; LG_INGEST_THREADS, default all cores up to
+ * 32) and the block goes through lg_csc_upload.  The hdf5 twin, the /by_row copy and `.zarr.zip` stores are not read.
+ * lg_zarr_open reports through `err` (it has no context yet); the other calls through lg_zarr_last_error. */
+typedef struct lg_zarr lg_zarr;
+int lg_zarr_open(const char* path, lg_zarr** out, char* err, size_t err_len);
+void lg_zarr_close(lg_zarr* z);
+const char* lg_zarr_last_error(const lg_zarr* z);
+int lg_zarr_shape(const lg_zarr* z, uint64_t* nrows, uint64_t* ncols, uint64_t* nnz);
+/* entries of columns [col_lo, col_hi) are [*first, *last) of the indices / data arrays */
+int lg_zarr_column_extent(lg_zarr* z, uint64_t col_lo, uint64_t col_hi, uint64_t* first, uint64_t* last);
+/* host arrays of the range: indptr (col_hi - col_lo + 1 entries, rebased to 0), indices and data (*last - *first each) */
+int lg_zarr_read_columns_host(lg_zarr* z, uint64_t col_lo, uint64_t col_hi, uint64_t* indptr, uint64_t* indices, float* data);
+/* the range as a device-resident block (rows = the store's nrow) */
+int lg_zarr_read_columns(lg_ctx* ctx, lg_zarr* z, uint64_t col_lo, uint64_t col_hi, lg_csc** out);
+
 /* ---- multi-GPU: cells sharded over the GPUs of one box, one process (or thread) per GPU ------------------------
  * (section 8b row 4 `lg_allreduce_stats`).  The reference is a single process; what these entry
  * points replace is the rayon reduction over column blocks inside project_columns / collect_basic_stat

@@ -353,6 +353,23 @@ class SparseIoVec {
         nrows_ = r;
         ncols_ = c;
     }
+    // open_sparse_matrix(zarr) + SparseIoVec::push: the columns [col_lo, col_hi) of a store written by the reference's
+    // zarr backend (data-beans/src/sparse_backend/zarr.rs), inflated on the host cores and fed through lg_csc_upload
+    SparseIoVec(const Context& ctx, const std::string& zarr_file, uint64_t col_lo = 0, uint64_t col_hi = UINT64_MAX) : ctx_(ctx) {
+        lg_zarr* z = nullptr;
+        char err[512] = {0};
+        int rc = lg_zarr_open(zarr_file.c_str(), &z, err, sizeof err);
+        if (rc != LG_OK) throw Error(rc, err);
+        uint64_t r = 0, c = 0, nz = 0;
+        lg_zarr_shape(z, &r, &c, &nz);
+        if (col_hi == UINT64_MAX) col_hi = c;
+        rc = lg_zarr_read_columns(ctx_.get(), z, col_lo, col_hi, &csc_);
+        lg_zarr_close(z);
+        ctx_.check(rc);
+        lg_csc_shape(csc_, &r, &c, &nz);
+        nrows_ = r;
+        ncols_ = c;
+    }
     ~SparseIoVec() { lg_csc_free(ctx_.get(), csc_); }
     SparseIoVec(const SparseIoVec&) = delete;
     SparseIoVec& operator=(const SparseIoVec&) = delete;

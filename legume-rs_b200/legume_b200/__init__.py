@@ -20,11 +20,12 @@ Arrays may be numpy (host) or torch CUDA tensors (device, used in place, no copi
 from __future__ import annotations
 
 import ctypes as C
+import os
 
 import numpy as np
 
 from ._lib import (BLOCK_CELLS, EXPORTED, LIB_PATH, TARGET_ALL, TARGET_MEAN_AND_LOG_MEAN, TARGET_MEAN_ONLY,
-                   LegumeError, lib)
+                   LG_OK, LegumeError, lib)
 
 DEFAULT_PROJECTION_SEED = 0x50524F4A_50524F4A  # random_projection.rs:41
 DEFAULT_KNN = 10                                # collapse_data/mod.rs:27
@@ -35,7 +36,8 @@ __all__ = ["Context", "CscBlock", "SparseIoVec", "binary_sort_columns", "GammaMa
            "CollapsedOut", "optimize", "ColumnDict", "LegumeError", "CalibrateTarget", "compute_level_sort_dims",
            "pad_numeric_labels", "merge_stat", "MultilevelParams", "PbSampleLayout", "build_pb_sample_layout",
            "per_batch_sc_neighbors", "collect_matched_stat_coarse", "compute_fine_to_coarse_mapping",
-           "sort_batch_proximity", "knn_match_batches", "SparseRunningStatistics", "nystrom_project", "SparseIoStack", "mix_seed"]
+           "sort_batch_proximity", "knn_match_batches", "SparseRunningStatistics", "nystrom_project", "SparseIoStack", "mix_seed",
+           "SparseMtxData"]
 DEFAULT_NUM_LEVELS = 2                          # collapse_data/stats.rs:688
 
 
@@ -195,6 +197,82 @@ class CscBlock:
 # --------------------------------------------------------------------------------------------------
 # label helpers (host side, exactly the reference's string-rank rules)
 # --------------------------------------------------------------------------------------------------
+class SparseMtxData:
+    """The reference's zarr backend as a reader (data-beans/src/sparse_backend/zarr.rs: `SparseMtxData::open`, the
+    `SparseIo` trait methods the path uses).  The store is the Zarr V3 directory the reference writes; chunks are inflated
+    on the host cores inside the library (lg_zarr_*, csrc/lg_ingest.cu) and blocks reach the device through
+    lg_csc_upload.  Read-only: writing stores is the reference's `data-beans` CLI, outside the path."""
+
+    def __init__(self, handle, file_name):
+        self.h, self.file_name = handle, file_name
+        a, b, c = C.c_uint64(), C.c_uint64(), C.c_uint64()
+        lib.lg_zarr_shape(self.h, C.byref(a), C.byref(b), C.byref(c))
+        self._shape = (a.value, b.value, c.value)
+        self._preloaded = None
+
+    @classmethod
+    def open(cls, zarr_file):
+        """zarr.rs:640-690 (`open`): shape from the root attributes nrow / ncol / nnz (:515-523)"""
+        h = C.c_void_p()
+        err = C.create_string_buffer(512)
+        rc = lib.lg_zarr_open(os.fsencode(zarr_file), C.byref(h), err, len(err))
+        if rc != LG_OK:
+            raise LegumeError(rc, err.value.decode(errors="replace"))
+        return cls(h, str(zarr_file))
+
+    def _check(self, rc):
+        if rc != LG_OK:
+            raise LegumeError(rc, lib.lg_zarr_last_error(self.h).decode(errors="replace"))
+
+    def num_rows(self):
+        return self._shape[0]
+
+    def num_columns(self):
+        return self._shape[1]
+
+    def num_non_zeros(self):
+        return self._shape[2]
+
+    def read_columns_host(self, col_lo=0, col_hi=None):
+        """(indptr rebased to 0, indices, data) of columns [col_lo, col_hi) as the reference's u64 / u64 / f32 arrays"""
+        col_hi = self.num_columns() if col_hi is None else col_hi
+        first, last = C.c_uint64(), C.c_uint64()
+        self._check(lib.lg_zarr_column_extent(self.h, col_lo, col_hi, C.byref(first), C.byref(last)))
+        n = last.value - first.value
+        ip, ix, v = np.empty(col_hi - col_lo + 1, np.uint64), np.empty(n, np.uint64), np.empty(n, np.float32)
+        self._check(lib.lg_zarr_read_columns_host(self.h, col_lo, col_hi, _ptr(ip), _ptr(ix), _ptr(v)))
+        return ip, ix, v
+
+    def preload_columns(self):
+        """zarr.rs:573-587"""
+        self._preloaded = self.read_columns_host()
+
+    def clean_preloaded_columns(self):
+        self._preloaded = None
+
+    def csc_column_arrays(self):
+        """zarr.rs:982-994: None until preload_columns"""
+        return self._preloaded
+
+    def read_columns_csc(self, ctx: Context, col_lo=0, col_hi=None):
+        """the column range as a device-resident block (SparseIoVec::read_columns_csc, read.rs:172-285)"""
+        col_hi = self.num_columns() if col_hi is None else col_hi
+        h = C.c_void_p()
+        ctx.check(lib.lg_zarr_read_columns(ctx.h, self.h, col_lo, col_hi, C.byref(h)))
+        return CscBlock(ctx, h)
+
+    def close(self):
+        if self.h:
+            lib.lg_zarr_close(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 def _rank_labels(labels):
     """index = rank of label.to_string() in byte-wise order (batch.rs:274-275, groups.rs:20-24)"""
     strs = [str(int(x)) if isinstance(x, (np.integer, int)) else str(x) for x in labels]
@@ -761,6 +839,15 @@ class SparseIoVec:
     @classmethod
     def from_csc(cls, ctx, indptr, indices, data, nrows):
         return cls(ctx, CscBlock.upload(ctx, indptr, indices, data, nrows))
+
+    @classmethod
+    def from_zarr(cls, ctx, zarr_file, col_lo=0, col_hi=None):
+        """open_sparse_matrix + SparseIoVec::push of one zarr backend (sparse_io_vector/mod.rs `push`)"""
+        be = SparseMtxData.open(zarr_file)
+        try:
+            return cls(ctx, be.read_columns_csc(ctx, col_lo, col_hi))
+        finally:
+            be.close()
 
     @classmethod
     def from_backends(cls, ctx, backends, nrows):

@@ -103,6 +103,11 @@ _sig = {
     "lg_fine_to_coarse": [_vp, _vp, _vp, _u64, _u32, _i, _vp, C.POINTER(_u32)],
     "lg_row_stats": [_vp, _vp, _vp, _vp, _vp],
     "lg_nystrom_project": [_vp, _vp, _vp, _i, _vp, _vp, _u32, _f, _vp],
+    "lg_zarr_open": [C.c_char_p, C.POINTER(_vp), C.c_char_p, C.c_size_t],
+    "lg_zarr_shape": [_vp, C.POINTER(_u64), C.POINTER(_u64), C.POINTER(_u64)],
+    "lg_zarr_column_extent": [_vp, _u64, _u64, C.POINTER(_u64), C.POINTER(_u64)],
+    "lg_zarr_read_columns_host": [_vp, _u64, _u64, _vp, _vp, _vp],
+    "lg_zarr_read_columns": [_vp, _vp, _u64, _u64, C.POINTER(_vp)],
     "lg_sim_poisson_csc": [_vp, _u64, _u64, _u64, _u64, _vp, _vp, _u32, _u32, _vp, _vp, _vp, C.POINTER(_vp)],
 }
 for _name, _args in _sig.items():
@@ -119,8 +124,12 @@ lib.lg_ctx_fallback_count.argtypes = [_vp]
 lib.lg_ctx_fallback_count.restype = C.c_uint64
 lib.lg_ctx_last_fallback.argtypes = [_vp]
 lib.lg_ctx_last_fallback.restype = C.c_char_p
+lib.lg_zarr_close.argtypes = [_vp]
+lib.lg_zarr_close.restype = None
+lib.lg_zarr_last_error.argtypes = [_vp]
+lib.lg_zarr_last_error.restype = C.c_char_p
 lib.lg_version.argtypes = []
 lib.lg_version.restype = C.c_char_p
 
 EXPORTED = sorted(list(_sig) + ["lg_last_error", "lg_ctx_launch_count", "lg_ctx_h2d_bytes", "lg_ctx_fallback_count", "lg_ctx_last_fallback",
-                          "lg_version"])
+                          "lg_version", "lg_zarr_close", "lg_zarr_last_error"])

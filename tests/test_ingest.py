@@ -1,0 +1,135 @@
+"""Column-block ingest: lg_zarr_* reads the store layout of the reference's zarr backend
+(data-beans/src/sparse_backend/zarr.rs).  The host half (metadata, chunk arithmetic, zstd) runs without a GPU; the device
+half checks that the block lg_zarr_read_columns hands to the path is the block a direct lg_csc_upload gives.
+Parity unpinned for this row: no store written by the reference's own zarrs exists in this environment (tests/zarr_store.py
+writes the layout from the Zarr V3 specification)."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+import legume_b200 as lg
+from zarr_store import chunk_elems, write_array, write_store
+
+
+def random_csc(D, N, density, seed):
+    rng = np.random.default_rng(seed)
+    cnt = rng.binomial(D, density, N)
+    cnt[rng.integers(0, N, max(N // 10, 1))] = 0  # empty columns too
+    indptr = np.zeros(N + 1, np.uint64)
+    indptr[1:] = np.cumsum(cnt)
+    idx = np.concatenate([np.sort(rng.choice(D, c, replace=False)) for c in cnt] + [np.zeros(0, np.int64)]).astype(np.uint64)
+    val = rng.poisson(0.3, len(idx)).astype(np.float32) + 1
+    return indptr, idx, val
+
+
+def test_chunk_elems_follows_the_reference():
+    # utilities/io_helpers.rs:105-115 and its tests: 1 MiB target, never below 8192 elements, never above the array
+    assert chunk_elems(10_000_000, 4) == 262_144
+    assert chunk_elems(10_000_000, 8) == 131_072
+    assert chunk_elems(100, 8) == 100
+    assert chunk_elems(0, 4) == 1
+    assert chunk_elems(10_000_000, 1024) == 8192
+
+
+@pytest.mark.parametrize("compress", [True, False])
+def test_zarr_host_read_round_trip(tmp_path, compress):
+    D, N = 700, 900
+    ip, ix, v = random_csc(D, N, 0.05, 1)
+    root = str(tmp_path / "m.zarr")
+    write_store(root, ip, ix, v, D, chunk=1000, compress=compress)  # many chunks, ragged last one
+    be = lg.SparseMtxData.open(root)
+    assert (be.num_rows(), be.num_columns(), be.num_non_zeros()) == (D, N, len(v))
+    assert be.csc_column_arrays() is None
+    be.preload_columns()
+    gip, gix, gv = be.csc_column_arrays()
+    assert np.array_equal(gip, ip) and np.array_equal(gix, ix) and gv.tobytes() == v.tobytes()
+    # column ranges that start / end inside chunks, the empty range, single columns
+    for lo, hi in [(0, 1), (17, 403), (402, 403), (N - 5, N), (250, 250), (0, N)]:
+        rip, rix, rv = be.read_columns_host(lo, hi)
+        a, b = int(ip[lo]), int(ip[hi])
+        assert np.array_equal(rip, ip[lo:hi + 1] - ip[lo])
+        assert np.array_equal(rix, ix[a:b]) and rv.tobytes() == v[a:b].tobytes()
+    be.close()
+
+
+def test_zarr_default_chunking_and_missing_chunk(tmp_path):
+    # the reference's own chunk size (the whole array when it is below 1 MiB); an absent chunk reads as the fill value
+    D, N = 300, 400
+    ip, ix, v = random_csc(D, N, 0.1, 2)
+    root = str(tmp_path / "d.zarr")
+    write_store(root, ip, ix, v, D)
+    be = lg.SparseMtxData.open(root)
+    gip, gix, gv = be.read_columns_host()
+    assert np.array_equal(gip, ip) and np.array_equal(gix, ix) and np.array_equal(gv, v)
+    be.close()
+    write_array(os.path.join(root, "by_column", "data"), v, chunk=4096, skip_chunks=(1,))
+    for f in os.listdir(os.path.join(root, "by_column", "data", "c")):
+        assert f != "1"
+    be = lg.SparseMtxData.open(root)
+    _, _, gv = be.read_columns_host()
+    assert np.array_equal(gv[:4096], v[:4096]) and np.isnan(gv[4096:8192]).all() and np.array_equal(gv[8192:], v[8192:])
+    be.close()
+
+
+def test_zarr_open_errors(tmp_path):
+    with pytest.raises(lg.LegumeError, match="zarr.json"):
+        lg.SparseMtxData.open(str(tmp_path / "absent.zarr"))
+    D, N = 50, 60
+    ip, ix, v = random_csc(D, N, 0.2, 3)
+    root = str(tmp_path / "e.zarr")
+    write_store(root, ip, ix, v, D, chunk=64)
+    meta_path = os.path.join(root, "by_column", "indices", "zarr.json")
+    meta = json.load(open(meta_path))
+    bad = dict(meta, data_type="int32")
+    json.dump(bad, open(meta_path, "w"))
+    with pytest.raises(lg.LegumeError, match="data_type"):
+        lg.SparseMtxData.open(root)
+    bad = dict(meta, codecs=meta["codecs"] + [{"name": "blosc"}])
+    json.dump(bad, open(meta_path, "w"))
+    with pytest.raises(lg.LegumeError, match="blosc"):
+        lg.SparseMtxData.open(root)
+    json.dump(meta, open(meta_path, "w"))
+    # a chunk that does not inflate to the chunk shape
+    with open(os.path.join(root, "by_column", "indices", "c", "0"), "wb") as f:
+        f.write(b"not zstd")
+    be = lg.SparseMtxData.open(root)
+    with pytest.raises(lg.LegumeError, match="c/0"):
+        be.read_columns_host()
+    with pytest.raises(lg.LegumeError, match="range"):
+        be.read_columns_host(0, N + 1)
+    be.close()
+    # lengths that contradict the attributes
+    json.dump({"zarr_format": 3, "node_type": "group", "attributes": {"nrow": D, "ncol": N + 1, "nnz": len(v)}},
+              open(os.path.join(root, "zarr.json"), "w"))
+    with pytest.raises(lg.LegumeError, match="lengths"):
+        lg.SparseMtxData.open(root)
+
+
+@pytest.mark.gpu
+def test_zarr_block_equals_direct_upload(tmp_path):
+    import oracle as orc
+    D, N, K = 3000, 5000, 50
+    ip, ix, v = random_csc(D, N, 0.04, 4)
+    root = str(tmp_path / "g.zarr")
+    write_store(root, ip, ix, v, D, chunk=20000)
+    ctx = lg.Context(0)
+    be = lg.SparseMtxData.open(root)
+    whole = be.read_columns_csc(ctx)
+    gip, gix, gv = whole.download()
+    assert np.array_equal(gip, ip) and np.array_equal(gix, ix) and gv.tobytes() == v.tobytes()
+    lo, hi = 1024, 4096
+    part = be.read_columns_csc(ctx, lo, hi)
+    pip, pix, pv = part.download()
+    a, b = int(ip[lo]), int(ip[hi])
+    assert np.array_equal(pip, ip[lo:hi + 1] - ip[lo]) and np.array_equal(pix, ix[a:b]) and pv.tobytes() == v[a:b].tobytes()
+    # and the path runs on it: projection of the ingested block against the oracle on the arrays that were written
+    basis = np.random.default_rng(0).standard_normal((D, K)).astype(np.float32)
+    data = lg.SparseIoVec.from_zarr(ctx, root)
+    _, got = data.project_columns_with_batch_correction(K, basis=basis)
+    want = orc.project(ip, ix, v, basis, np.zeros(N, np.uint32), 1, nthreads=4)
+    got = np.asarray(got.cpu() if hasattr(got, "cpu") else got)
+    assert got.shape == want.shape
+    assert np.max(np.abs(got - want) / (1 + np.maximum(np.abs(got), np.abs(want)))) <= 1e-5
+    be.close()
