@@ -128,7 +128,7 @@ def test_zarr_block_equals_direct_upload(tmp_path):
     basis = np.random.default_rng(0).standard_normal((D, K)).astype(np.float32)
     data = lg.SparseIoVec.from_zarr(ctx, root)
     _, got = data.project_columns_with_batch_correction(K, basis=basis)
-    want = orc.project(ip, ix, v, basis, np.zeros(N, np.uint32), 1, nthreads=4)
+    want = orc.project(ip, ix, v, basis, None, 0, nthreads=4)  # no batch labels on either side: no centring
     got = np.asarray(got.cpu() if hasattr(got, "cpu") else got)
     assert got.shape == want.shape
     assert np.max(np.abs(got - want) / (1 + np.maximum(np.abs(got), np.abs(want)))) <= 1e-5
