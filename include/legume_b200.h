@@ -367,6 +367,28 @@ int lg_row_stats(lg_ctx* ctx, const lg_csc* m, double* out_npos, double* out_s1,
 int lg_nystrom_project(lg_ctx* ctx, const lg_csc* m, const float* basis_dk, int K, const float* delta_dp,
                        const uint32_t* pb_of_cell, uint32_t P, float column_sum_norm, float* out_proj_kn);
 
+/* ---- BBKNN + DC-Poisson refinement of the pb-sample partition --------------------------
+ * What `MultilevelParams::refine = Some(..)` runs between the hash partition and the collapse when there are two or more
+ * batches (collapse_data/refine.rs:264-345 -> refine_multilevel.rs:170-298 -> dc_poisson.rs:778-915).  The entities are the
+ * pb-samples, their profiles the dense pb-sample x gene sums the path already holds (npb x D, an entity's row contiguous;
+ * a stored entry is a value > 0, the filter of Profiles::from_gene_sums, dc_poisson.rs:136-160).  The label bookkeeping
+ * around the levels (compact_labels, project_to_refinement, sibling / candidate sets; dc_poisson.rs:493-633,
+ * refine_multilevel.rs:85-112, 315-345) is host code in the mirrors; these entry points are the numeric part.
+ *   lg_dcp_fisher_weights  Profiles::nb_fisher_weights (dc_poisson.rs:230-295; nb_dispersion.rs:58-151): per-gene serial f32
+ *                          folds over the entities on the device, the D-long trend fit on the host.
+ *   lg_dcp_profiles        weight_by_vec (:197-213) in place + every entity's size factor (serial f32 fold).
+ *   lg_dcp_refine_level    refine_with_candidates_guarded (:778-915) for one level with RefineParams::parallel = true (Jacobi
+ *                          sweeps) and no move guard: num_gibbs Gumbel-max sweeps (per-entity SmallRng streams from
+ *                          jacobi_base_seed, early exit after three sweeps below `stagnation` * npb moves), then num_greedy
+ *                          arg-max sweeps (exit on a sweep without moves).  Scores are accumulated in the reference's order
+ *                          (one f64 accumulator per (entity, group) over ascending genes).  Candidates: CSR, groups ascending
+ *                          inside an entity.  labels: in / out, values < k.  Pointers may be host or device memory. */
+int lg_dcp_fisher_weights(lg_ctx* ctx, const float* profiles, uint64_t D, uint32_t npb, float* out_w);
+int lg_dcp_profiles(lg_ctx* ctx, float* profiles, uint64_t D, uint32_t npb, const float* weights, float* out_size_factor);
+int lg_dcp_refine_level(lg_ctx* ctx, const float* profiles, const float* size_factor, uint64_t D, uint32_t npb,
+                        const uint32_t* cand_ptr, const uint32_t* cand, uint32_t k, int num_gibbs, int num_greedy,
+                        uint64_t jacobi_base_seed, double stagnation, uint32_t* labels, uint64_t* out_moves);
+
 /* ---- column-block ingest: the reference's zarr backend as the feed of the path ---------
  * lg_zarr_* replaces, for a matrix written by the reference's zarr backend (data-beans/src/sparse_backend/zarr.rs: a Zarr V3
  * FilesystemStore directory holding /by_column/{indptr u64, indices u64, data f32} as 1-D arrays in ~1 MiB chunks,

@@ -37,7 +37,9 @@ __all__ = ["Context", "CscBlock", "SparseIoVec", "binary_sort_columns", "GammaMa
            "pad_numeric_labels", "merge_stat", "MultilevelParams", "PbSampleLayout", "build_pb_sample_layout",
            "per_batch_sc_neighbors", "collect_matched_stat_coarse", "compute_fine_to_coarse_mapping",
            "sort_batch_proximity", "knn_match_batches", "SparseRunningStatistics", "nystrom_project", "SparseIoStack", "mix_seed",
-           "SparseMtxData"]
+           "SparseMtxData", "RefineParams", "refine_assignments", "build_reproject_offsets", "project_to_refinement",
+           "child_offset_within_parent", "compute_sibling_sets", "intersect_with_siblings_fallback", "build_candidate_sets",
+           "compact_labels"]
 DEFAULT_NUM_LEVELS = 2                          # collapse_data/stats.rs:688
 
 
@@ -498,9 +500,22 @@ def compute_fine_to_coarse_mapping(ctx: Context, fine_codes, col_to_group, num_f
 
 
 class RefineParams:
-    """refine_multilevel.rs RefineParams::default(): the BBKNN + Poisson DC-SBM refinement of the pb-sample partition.  With
-    one batch the refinement is the identity (refine.rs:126-147) and this arm is built; with two or more it is SURVEY.md
-    section 8f rank 3 and refused."""
+    """dc_poisson.rs:71-117 `RefineParams::default()`: the BBKNN + Poisson refinement of the pb-sample partition.  With one batch
+    the refinement is the identity (refine.rs:126-147); with two or more it runs the Jacobi sweeps of dc_poisson.rs:778-915
+    through lg_dcp_refine_level.  The sequential Gauss-Seidel sweeps (parallel = false) and the projected profile source
+    are outside the hot path and refused."""
+
+    def __init__(self, num_gibbs=20, num_greedy=10, feature_weighting="FisherInfoNb", seed=42, gibbs_stagnation=0.005,
+                 profile_source="Raw", parallel=True):
+        if feature_weighting not in ("None", "FisherInfoNb"):
+            raise LegumeError(1, "RefineParams.feature_weighting is None or FisherInfoNb (dc_poisson.rs:54-66)")
+        if profile_source != "Raw":
+            raise LegumeError(1, "RefineParams.profile_source = Projected is outside the hot path (dc_poisson.rs:39-49)")
+        if not parallel:
+            raise LegumeError(1, "RefineParams.parallel = false (Gauss-Seidel sweeps, dc_poisson.rs:688-731) is outside the hot path")
+        self.num_gibbs, self.num_greedy = int(num_gibbs), int(num_greedy)
+        self.feature_weighting, self.seed, self.gibbs_stagnation = feature_weighting, int(seed), float(gibbs_stagnation)
+        self.profile_source, self.parallel = profile_source, parallel
 
 
 class MultilevelParams:
@@ -549,6 +564,119 @@ def fine_to_coarse_from_refined(pbsamp_to_fine, pbsamp_to_coarse, num_fine):
     m = np.full(num_fine, NONE_U32, np.uint32)
     m[p2f[first]] = np.asarray(pbsamp_to_coarse, np.uint32)[first]
     return m
+
+
+def build_reproject_offsets(fine_codes, first_cell_of_pb, level_dims):
+    """refine.rs:95-125: per level the finest hash bits above the parent level's sort dim; empty for the coarsest level"""
+    raw = np.asarray(fine_codes, np.uint64)[first_cell_of_pb]
+    out = []
+    for level in range(len(level_dims)):
+        if level + 1 < len(level_dims):
+            parent_dim = level_dims[level + 1]
+            nbits = max(level_dims[level] - parent_dim, 0)
+            mask = np.uint64(0xFFFFFFFFFFFFFFFF) if nbits >= 64 else np.uint64((1 << nbits) - 1)
+            out.append(((raw >> np.uint64(parent_dim)) & mask).astype(np.uint32))
+        else:
+            out.append(np.zeros(0, np.uint32))
+    return out
+
+
+def project_to_refinement(child, parent):
+    """refine_multilevel.rs:315-320: dense labels of the (child, parent) pairs in order of first appearance"""
+    c, p = np.asarray(child, np.uint64), np.asarray(parent, np.uint64)
+    return compact_labels(c * (np.uint64(int(p.max()) + 1) if p.size else np.uint64(1)) + p)
+
+
+def child_offset_within_parent(child, parent):
+    """refine_multilevel.rs:333-345: the index of an entity's child label inside its parent, in first-seen order"""
+    per, out = {}, np.zeros(len(child), np.uint32)
+    for i, (c, q) in enumerate(zip(np.asarray(child).tolist(), np.asarray(parent).tolist())):
+        local = per.setdefault(q, {})
+        out[i] = local.setdefault(c, len(local))
+    return out
+
+
+def compute_sibling_sets(refined, level, num_groups_at_level):
+    """dc_poisson.rs:518-550: per entity the sorted groups of `level` that share its parent at `level + 1` (all groups at the
+    coarsest level); entities with the same parent share one list object"""
+    n = len(refined[level])
+    if level + 1 >= len(refined):
+        allg = list(range(num_groups_at_level))
+        return [allg] * n
+    kids = {}
+    for c, q in zip(np.asarray(refined[level]).tolist(), np.asarray(refined[level + 1]).tolist()):
+        kids.setdefault(q, set()).add(c)
+    kids = {q: sorted(v) for q, v in kids.items()}
+    return [kids[q] for q in np.asarray(refined[level + 1]).tolist()]
+
+
+def intersect_with_siblings_fallback(siblings, neighbor_groups, current):
+    """dc_poisson.rs:599-633"""
+    if len(siblings) <= 1:
+        return list(siblings)
+    inter = [g for g in siblings if g in neighbor_groups]
+    if not inter:
+        return list(siblings)
+    if current not in inter:
+        inter = sorted(inter + [current])
+    return inter
+
+
+def build_candidate_sets(siblings, bbknn, pbsamp_to_group):
+    """refine_multilevel.rs:85-112: siblings ∩ (groups of the BBKNN neighbours), sibling fall-back, own group always in"""
+    lab = np.asarray(pbsamp_to_group).tolist()
+    return [intersect_with_siblings_fallback(sib, {lab[j] for j in bbknn[e]}, lab[e]) for e, sib in enumerate(siblings)]
+
+
+def refine_assignments(ctx: Context, gene_sums, bbknn, initial_per_level, reproject_offsets, params: "RefineParams"):
+    """refine_multilevel.rs:170-298: top-down BBKNN + DC-Poisson refinement of the pb-sample -> group maps (finest first).
+    gene_sums: (npb, D) dense pb-sample gene sums; bbknn: per pb-sample the matched foreign pb-samples.  Returns
+    (pbsamp_to_group per level, num_groups per level, accepted moves)."""
+    L = len(initial_per_level)
+    if L == 0:
+        raise LegumeError(1, "no levels")
+    gs = _as(gene_sums, np.float32)
+    npb, D = gs.shape
+    for i, lvl in enumerate(initial_per_level):
+        if len(lvl) != npb:
+            raise LegumeError(1, f"level {i} has {len(lvl)} entries, expected {npb}")
+    refined, ks = [], []
+    for lvl in initial_per_level:
+        c, k = compact_labels(lvl)
+        refined.append(c)
+        ks.append(k)
+    if params.num_gibbs == 0 and params.num_greedy == 0:  # :215-222
+        return refined, ks, 0
+    # profiles once: stored entries of the gene sums, NB Fisher-information weights, size factors (:224-243)
+    dev = _is_torch(gs)
+    prof = gs.clone() if dev else np.array(gs, np.float32, copy=True)
+    w = None
+    if params.feature_weighting == "FisherInfoNb":
+        w = ctx.empty((D,), np.float32, dev)
+        ctx.check(lib.lg_dcp_fisher_weights(ctx.h, _ptr(prof), D, npb, _ptr(w)))
+    sf = ctx.empty((npb,), np.float32, dev)
+    ctx.check(lib.lg_dcp_profiles(ctx.h, _ptr(prof), D, npb, _ptr(w), _ptr(sf)))
+    rng = _Xoshiro256pp(params.seed)
+    total = 0
+    for level in range(L - 1, -1, -1):
+        if level + 1 < L:  # re-anchor this level in its REFINED parent by the child hash relative to the parent (:255-280)
+            off = reproject_offsets[level] if reproject_offsets is not None and level < len(reproject_offsets) else ()
+            if len(off) == 0:
+                off = child_offset_within_parent(initial_per_level[level], initial_per_level[level + 1])
+            refined[level], ks[level] = project_to_refinement(off, refined[level + 1])
+        k = ks[level]
+        cand = build_candidate_sets(compute_sibling_sets(refined, level, k), bbknn, refined[level])
+        cptr = np.zeros(npb + 1, np.uint32)
+        cptr[1:] = np.cumsum([len(c) for c in cand])
+        cflat = np.fromiter((g for c in cand for g in c), np.uint32, int(cptr[-1]))
+        base_seed = rng.next() | 1  # dc_poisson.rs:824
+        labels = np.ascontiguousarray(refined[level], np.uint32)
+        moves = C.c_uint64(0)
+        ctx.check(lib.lg_dcp_refine_level(ctx.h, _ptr(prof), _ptr(sf), D, npb, _ptr(cptr), _ptr(cflat), k, params.num_gibbs,
+                                          params.num_greedy, base_seed, params.gibbs_stagnation, _ptr(labels), C.byref(moves)))
+        total += moves.value
+        refined[level], ks[level] = compact_labels(labels)  # greedy sweeps can empty a group (:292-295)
+    return refined, ks, total
 
 
 def modal_groups(cell_to_pbsamp, num_pb, lvl):
@@ -1190,15 +1318,20 @@ class SparseIoVec:
     def _refine_and_collect(self, proj_kn, nb, level_dims, codes_h, group, ng, params):
         """refine_and_collect_single_layer (refine.rs:264-500).  refine_or_identity(num_batches >= 2, ..): with one batch
         the refined assignment is the compacted hash partition of every level"""
-        if nb >= 2:
-            raise LegumeError(1, "BBKNN + DC-SBM refinement over two or more batches is outside the hot path (SURVEY.md "
-                                 "section 8f rank 3); pass MultilevelParams(refine=None) or inherit a partition")
         layout, gene_sums = self._build_pb_samples(proj_kn, group, ng, nb)
         c2p = np.asarray(layout.cell_to_pbsamp).astype(np.int64)
         first = np.full(layout.num_pb, len(c2p), np.int64)
         np.minimum.at(first, c2p, np.arange(len(c2p)))  # a pb-sample's first cell (pb_samples.rs:472-481)
         p2g = initial_per_level_from_hash(codes_h, first, level_dims)
-        p2g, k = zip(*(compact_labels(l) for l in p2g))
+        if nb >= 2:  # refine_or_identity(num_batches >= 2, ..): BBKNN candidates + DC-Poisson sweeps (refine.rs:329-345)
+            matched, _ = per_batch_sc_neighbors(self.ctx, layout, proj_kn, self.col_to_batch, nb, params.knn_pb_samples)
+            mp = np.asarray(matched.cpu() if _is_torch(matched) else matched)
+            bbknn = [row[row != NONE_U32].tolist() for row in mp]  # build_bbknn_neighbors (refine_multilevel.rs:60-83)
+            offsets = build_reproject_offsets(codes_h, first, level_dims)
+            p2g, k, moves = refine_assignments(self.ctx, gene_sums, bbknn, p2g, offsets, params.refine)
+            self.refine_moves = moves
+        else:
+            p2g, k = zip(*(compact_labels(l) for l in p2g))
         return self._collect_refined_levels(proj_kn, nb, layout, gene_sums, list(p2g), list(k), params,
                                             params.output_calibration)
 

@@ -103,6 +103,9 @@ _sig = {
     "lg_fine_to_coarse": [_vp, _vp, _vp, _u64, _u32, _i, _vp, C.POINTER(_u32)],
     "lg_row_stats": [_vp, _vp, _vp, _vp, _vp],
     "lg_nystrom_project": [_vp, _vp, _vp, _i, _vp, _vp, _u32, _f, _vp],
+    "lg_dcp_fisher_weights": [_vp, _vp, _u64, _u32, _vp],
+    "lg_dcp_profiles": [_vp, _vp, _u64, _u32, _vp, _vp],
+    "lg_dcp_refine_level": [_vp, _vp, _vp, _u64, _u32, _vp, _vp, _u32, _i, _i, _u64, C.c_double, _vp, C.POINTER(_u64)],
     "lg_zarr_open": [C.c_char_p, C.POINTER(_vp), C.c_char_p, C.c_size_t],
     "lg_zarr_shape": [_vp, C.POINTER(_u64), C.POINTER(_u64), C.POINTER(_u64)],
     "lg_zarr_column_extent": [_vp, _u64, _u64, C.POINTER(_u64), C.POINTER(_u64)],

@@ -22,7 +22,7 @@ _LIB_PATH = os.path.join(_HERE, "liblegume_oracle.so")
 
 def build(force: bool = False) -> str:
     """Compile the oracle with its committed Makefile (building the checker is not using it)."""
-    srcs = [os.path.join(_HERE, f) for f in ("oracle.cpp", "oracle_adjust.cpp", "oracle_next.cpp", "oracle_svd.cpp", "oracle_bench.cpp", "oracle.h")]
+    srcs = [os.path.join(_HERE, f) for f in ("oracle.cpp", "oracle_adjust.cpp", "oracle_next.cpp", "oracle_svd.cpp", "oracle_bench.cpp", "oracle_refine.cpp", "oracle.h")]
     stale = (not os.path.exists(_LIB_PATH)) or os.path.getmtime(_LIB_PATH) < max(os.path.getmtime(f) for f in srcs)
     if force or stale:
         subprocess.run(["make", "-C", _HERE], check=True, capture_output=True)
@@ -62,6 +62,11 @@ def lib():
         L.orc_sim_poisson_csc.restype = C.c_uint64
         L.orc_pb_layout.restype = C.c_uint32
         L.orc_fine_to_coarse.restype = C.c_uint32
+        for f in ("orc_smallrng_u64", "orc_sibling_sets", "orc_candidate_sets", "orc_dcp_refine_level", "orc_refine_assignments"):
+            getattr(L, f).restype = C.c_uint64
+        L.orc_smallrng_range_f64.restype = C.c_double
+        L.orc_compact_labels.restype = C.c_uint32
+        L.orc_project_to_refinement.restype = C.c_uint32
     return _lib
 
 
@@ -591,3 +596,141 @@ def bench_optimize_single_mt(sum_ds, size_s, a0=1.0, b0=1.0, target=TARGET_ALL, 
                                        _ptr(outs["mean"], C.c_float), _ptr(outs["sd"], C.c_float),
                                        _ptr(outs["log_mean"], C.c_float), _ptr(outs["log_sd"], C.c_float))
     return outs
+
+
+# ---- BBKNN + DC-Poisson refinement (oracle_refine.cpp) -----------------------
+def _csr(sets):
+    ptr = np.zeros(len(sets) + 1, np.uint32)
+    ptr[1:] = np.cumsum([len(s) for s in sets])
+    flat = np.fromiter((x for s in sets for x in s), np.uint32, int(ptr[-1]))
+    return ptr, np.ascontiguousarray(flat)
+
+
+def _sets(ptr, flat):
+    return [flat[ptr[i]:ptr[i + 1]].tolist() for i in range(len(ptr) - 1)]
+
+
+def smallrng_u64(seed, skip=0):
+    return int(lib().orc_smallrng_u64(C.c_uint64(seed), C.c_int(skip)))
+
+
+def smallrng_range_f64(seed, lo, hi, skip=0):
+    return float(lib().orc_smallrng_range_f64(C.c_uint64(seed), C.c_int(skip), C.c_double(lo), C.c_double(hi)))
+
+
+def project_to_refinement(child, parent):
+    """refine_multilevel.rs:315-320"""
+    c, p = np.ascontiguousarray(child, np.uint32), np.ascontiguousarray(parent, np.uint32)
+    out = np.empty(len(c), np.uint32)
+    k = lib().orc_project_to_refinement(_ptr(c, C.c_uint32), _ptr(p, C.c_uint32), C.c_uint64(len(c)), _ptr(out, C.c_uint32))
+    return out, int(k)
+
+
+def child_offset_within_parent(child, parent):
+    """refine_multilevel.rs:333-345"""
+    c, p = np.ascontiguousarray(child, np.uint32), np.ascontiguousarray(parent, np.uint32)
+    out = np.empty(len(c), np.uint32)
+    lib().orc_child_offset_within_parent(_ptr(c, C.c_uint32), _ptr(p, C.c_uint32), C.c_uint64(len(c)), _ptr(out, C.c_uint32))
+    return out
+
+
+def sibling_sets(level, parent, k):
+    """dc_poisson.rs:518-550; parent=None at the coarsest level"""
+    lv = np.ascontiguousarray(level, np.uint32)
+    pa = None if parent is None else np.ascontiguousarray(parent, np.uint32)
+    E = len(lv)
+    ptr = np.empty(E + 1, np.uint32)
+    n = lib().orc_sibling_sets(_ptr(lv, C.c_uint32), _ptr(pa, C.c_uint32), C.c_uint64(E), C.c_uint32(k), _ptr(ptr, C.c_uint32), None, C.c_uint64(0))
+    flat = np.empty(max(int(n), 1), np.uint32)
+    lib().orc_sibling_sets(_ptr(lv, C.c_uint32), _ptr(pa, C.c_uint32), C.c_uint64(E), C.c_uint32(k), _ptr(ptr, C.c_uint32), _ptr(flat, C.c_uint32),
+                           C.c_uint64(len(flat)))
+    return _sets(ptr, flat)
+
+
+def candidate_sets(siblings, bbknn, labels):
+    """refine_multilevel.rs:85-112"""
+    sp, sf = _csr(siblings)
+    bp, bf = _csr(bbknn)
+    lb = np.ascontiguousarray(labels, np.uint32)
+    E = len(lb)
+    ptr = np.empty(E + 1, np.uint32)
+    args = (_ptr(sp, C.c_uint32), _ptr(sf, C.c_uint32), _ptr(bp, C.c_uint32), _ptr(bf, C.c_uint32), _ptr(lb, C.c_uint32), C.c_uint64(E),
+            _ptr(ptr, C.c_uint32))
+    n = lib().orc_candidate_sets(*args, None, C.c_uint64(0))
+    flat = np.empty(max(int(n), 1), np.uint32)
+    lib().orc_candidate_sets(*args, _ptr(flat, C.c_uint32), C.c_uint64(len(flat)))
+    return _sets(ptr, flat)
+
+
+def dcp_fisher_weights(profiles):
+    """Profiles::nb_fisher_weights (dc_poisson.rs:230-295) of a dense entity x feature matrix"""
+    P = np.ascontiguousarray(profiles, np.float32)
+    w = np.empty(P.shape[1], np.float32)
+    lib().orc_dcp_fisher_weights(_ptr(P, C.c_float), C.c_uint32(P.shape[0]), C.c_uint64(P.shape[1]), _ptr(w, C.c_float))
+    return w
+
+
+def dcp_profiles(gene_sums, weights=None):
+    """(weighted profile values as a dense matrix, size factors): from_gene_sums + weight_by_vec"""
+    P = np.ascontiguousarray(gene_sums, np.float32).copy()
+    w = None if weights is None else np.ascontiguousarray(weights, np.float32)
+    sf = np.empty(P.shape[0], np.float32)
+    lib().orc_dcp_profiles(_ptr(P, C.c_float), C.c_uint32(P.shape[0]), C.c_uint64(P.shape[1]), _ptr(w, C.c_float), _ptr(sf, C.c_float))
+    return P, sf
+
+
+def dcp_stats(profiles, k, labels, moves=()):
+    """DcPoissonStats::from_profiles followed by delta_move for every (entity, to) of `moves`"""
+    P = np.ascontiguousarray(profiles, np.float32)
+    E, M = P.shape
+    lb = np.ascontiguousarray(labels, np.uint32)
+    me = np.ascontiguousarray([m[0] for m in moves], np.uint32)
+    mt = np.ascontiguousarray([m[1] for m in moves], np.uint32)
+    gs, lg = np.empty((k, M), np.float64), np.empty((k, M), np.float32)
+    ss, lso, mem = np.empty(k, np.float64), np.empty(k, np.float32), np.empty(E, np.uint32)
+    lib().orc_dcp_stats(_ptr(P, C.c_float), C.c_uint32(E), C.c_uint64(M), C.c_uint32(k), _ptr(lb, C.c_uint32), _ptr(me, C.c_uint32),
+                        _ptr(mt, C.c_uint32), C.c_uint64(len(me)), _ptr(gs, C.c_double), _ptr(lg, C.c_float), _ptr(ss, C.c_double),
+                        _ptr(lso, C.c_float), _ptr(mem, C.c_uint32))
+    return dict(gene_sum=gs, log_gene=lg, size_sum=ss, log_size_offset=lso, membership=mem)
+
+
+def dcp_scores(profiles, k, labels, e):
+    P = np.ascontiguousarray(profiles, np.float32)
+    lb = np.ascontiguousarray(labels, np.uint32)
+    out = np.empty(k, np.float64)
+    lib().orc_dcp_scores(_ptr(P, C.c_float), C.c_uint32(P.shape[0]), C.c_uint64(P.shape[1]), C.c_uint32(k), _ptr(lb, C.c_uint32), C.c_uint32(e),
+                         _ptr(out, C.c_double))
+    return out
+
+
+def dcp_refine_level(profiles, candidates, k, labels, num_gibbs, num_greedy, jacobi_base_seed, stagnation=0.005):
+    """refine_with_candidates_guarded (dc_poisson.rs:778-915), Jacobi sweeps: (labels, moves)"""
+    P = np.ascontiguousarray(profiles, np.float32)
+    cp, cf = _csr(candidates)
+    lb = np.ascontiguousarray(labels, np.uint32).copy()
+    moves = lib().orc_dcp_refine_level(_ptr(P, C.c_float), C.c_uint32(P.shape[0]), C.c_uint64(P.shape[1]), _ptr(cp, C.c_uint32),
+                                       _ptr(cf, C.c_uint32), C.c_uint32(k), C.c_int(num_gibbs), C.c_int(num_greedy),
+                                       C.c_uint64(jacobi_base_seed), C.c_double(stagnation), _ptr(lb, C.c_uint32))
+    return lb, int(moves)
+
+
+def refine_assignments(gene_sums, bbknn, initial_per_level, reproject_offsets=None, num_gibbs=20, num_greedy=10, fisher=True, seed=42,
+                       stagnation=0.005):
+    """refine_multilevel.rs:170-298: (pbsamp_to_group per level finest first, num_groups per level, moves)"""
+    P = np.ascontiguousarray(gene_sums, np.float32)
+    E, M = P.shape
+    bp, bf = _csr(bbknn)
+    init = np.ascontiguousarray(np.stack([np.asarray(l, np.uint32) for l in initial_per_level]), np.uint32)
+    L = init.shape[0]
+    off = None
+    if reproject_offsets is not None:
+        off = np.zeros((L, E), np.uint32)
+        for l, o in enumerate(reproject_offsets):
+            if len(o):
+                off[l] = np.asarray(o, np.uint32)
+    out, ks = np.empty((L, E), np.uint32), np.empty(L, np.uint32)
+    moves = lib().orc_refine_assignments(_ptr(P, C.c_float), C.c_uint32(E), C.c_uint64(M), _ptr(bp, C.c_uint32), _ptr(bf, C.c_uint32), C.c_int(L),
+                                         _ptr(init, C.c_uint32), _ptr(off, C.c_uint32), C.c_int(num_gibbs), C.c_int(num_greedy),
+                                         C.c_int(1 if fisher else 0), C.c_uint64(seed), C.c_double(stagnation), _ptr(out, C.c_uint32),
+                                         _ptr(ks, C.c_uint32))
+    return [out[l].copy() for l in range(L)], [int(x) for x in ks], int(moves)

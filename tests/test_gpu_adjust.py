@@ -323,9 +323,6 @@ def test_multilevel_refine_arm_single_batch(lg, ctx):
     # the trait entry takes the same arm and returns the levels only
     outs, stats = lg.SparseIoVec.from_csc(ctx, ip, ix, v, D).collapse_columns_multilevel_vec(proj, batch, params)
     assert np.array_equal(stats[2].observed_sum_ds, want[2]["obs"])
-    # two or more batches would need the refinement itself
-    with pytest.raises(lg.LegumeError):
-        data.collapse_columns_multilevel_vec(proj, np.arange(N) % 2, params)
     with pytest.raises(lg.LegumeError):
         data.collapse_columns_multilevel_with_hierarchy(proj, batch, lg.MultilevelParams(K, refine=None))
 
