@@ -24,6 +24,7 @@
 #include <map>
 #include <memory>
 #include <optional>
+#include <set>
 #include <stdexcept>
 #include <string>
 #include <utility>
@@ -251,12 +252,21 @@ inline CollapsedOut optimize(const Context& ctx, const CollapsedStat& stat, std:
     return out;
 }
 
-// collapse_data/mod.rs:64-130.  MultilevelParams::new sets refine = Some(default): served for one batch, where
-// refine_or_identity keeps the compacted hash partition (refine.rs:126-147); the BBKNN + DC-SBM refinement over several
-// batches is SURVEY.md section 8f rank 3 and refused.  refine = false is the legacy un-refined descent.
+// dc_poisson.rs:71-117 RefineParams::default().  Served: Jacobi sweeps (parallel = true), raw profiles, the two feature weightings.
+struct RefineParams {
+    size_t num_gibbs = 20, num_greedy = 10;
+    bool fisher_info_nb = true;  // FeatureWeighting::FisherInfoNb (false: FeatureWeighting::None)
+    uint64_t seed = 42;
+    double gibbs_stagnation = 0.005;
+};
+
+// collapse_data/mod.rs:64-130.  MultilevelParams::new sets refine = Some(default): with one batch refine_or_identity keeps the
+// compacted hash partition (refine.rs:126-147), with two or more the BBKNN + DC-Poisson refinement runs (refine_assignments
+// below).  refine = false is the legacy un-refined descent.
 struct MultilevelParams {
     size_t knn_pb_samples = DEFAULT_KNN, num_levels = DEFAULT_NUM_LEVELS, sort_dim = 12, num_opt_iter = DEFAULT_OPT_ITER;
     bool refine = true;
+    RefineParams refine_params;
     CalibrateTarget output_calibration = CalibrateTarget::All;
     explicit MultilevelParams(size_t proj_dim) : sort_dim(std::min<size_t>(proj_dim, 12)) {}
 };
@@ -283,6 +293,151 @@ inline std::vector<uint32_t> fine_to_coarse_from_refined(const std::vector<uint3
     for (size_t p = 0; p < p2f.size(); ++p)
         if (m[p2f[p]] == 0xFFFFFFFFu) m[p2f[p]] = p2c[p];
     return m;
+}
+
+// ---- BBKNN + DC-Poisson refinement of the pb-sample partition (refine_multilevel.rs, dc_poisson.rs) ----------------------
+// rand 0.10 SmallRng on 64-bit targets (xoshiro256++ seeded through SplitMix64): the refinement draws one u64 per level
+struct SmallRng {
+    uint64_t s[4];
+    explicit SmallRng(uint64_t seed) {
+        for (int i = 0; i < 4; ++i) {
+            seed += 0x9E3779B97F4A7C15ull;
+            uint64_t z = seed;
+            z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+            z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+            s[i] = z ^ (z >> 31);
+        }
+    }
+    uint64_t next_u64() {
+        auto rotl = [](uint64_t x, int k) { return (x << k) | (x >> (64 - k)); };
+        const uint64_t out = rotl(s[0] + s[3], 23) + s[0], t = s[1] << 17;
+        s[2] ^= s[0];
+        s[3] ^= s[1];
+        s[1] ^= s[2];
+        s[0] ^= s[3];
+        s[2] ^= t;
+        s[3] = rotl(s[3], 45);
+        return out;
+    }
+};
+// refine_multilevel.rs:315-320: dense labels of the (child, parent) pairs in order of first appearance
+inline std::pair<std::vector<uint32_t>, uint32_t> project_to_refinement(const std::vector<uint32_t>& child, const std::vector<uint32_t>& parent) {
+    std::map<std::pair<uint32_t, uint32_t>, uint32_t> lut;
+    std::vector<uint32_t> out;
+    out.reserve(child.size());
+    for (size_t i = 0; i < child.size(); ++i) out.push_back(lut.emplace(std::make_pair(child[i], parent[i]), (uint32_t)lut.size()).first->second);
+    return {out, (uint32_t)lut.size()};
+}
+// refine_multilevel.rs:333-345
+inline std::vector<uint32_t> child_offset_within_parent(const std::vector<uint32_t>& child, const std::vector<uint32_t>& parent) {
+    std::map<uint32_t, std::map<uint32_t, uint32_t>> per;
+    std::vector<uint32_t> out(child.size());
+    for (size_t i = 0; i < child.size(); ++i) {
+        auto& local = per[parent[i]];
+        out[i] = local.emplace(child[i], (uint32_t)local.size()).first->second;
+    }
+    return out;
+}
+// dc_poisson.rs:518-550
+inline std::vector<std::vector<uint32_t>> compute_sibling_sets(const std::vector<std::vector<uint32_t>>& refined, size_t level, uint32_t k) {
+    const size_t n = refined[level].size();
+    std::vector<std::vector<uint32_t>> out(n);
+    if (level + 1 >= refined.size()) {
+        std::vector<uint32_t> all(k);
+        for (uint32_t i = 0; i < k; ++i) all[i] = i;
+        for (auto& v : out) v = all;
+        return out;
+    }
+    std::map<uint32_t, std::set<uint32_t>> kids;
+    for (size_t e = 0; e < n; ++e) kids[refined[level + 1][e]].insert(refined[level][e]);
+    for (size_t e = 0; e < n; ++e) {
+        const auto& c = kids[refined[level + 1][e]];
+        out[e].assign(c.begin(), c.end());
+    }
+    return out;
+}
+// dc_poisson.rs:599-633
+inline std::vector<uint32_t> intersect_with_siblings_fallback(const std::vector<uint32_t>& siblings, const std::vector<uint32_t>& neighbor_groups,
+                                                              uint32_t current) {
+    if (siblings.size() <= 1) return siblings;
+    std::vector<uint32_t> inter;
+    for (uint32_t g : siblings)
+        if (std::binary_search(neighbor_groups.begin(), neighbor_groups.end(), g)) inter.push_back(g);
+    if (inter.empty()) return siblings;
+    if (std::find(inter.begin(), inter.end(), current) == inter.end()) {
+        inter.push_back(current);
+        std::sort(inter.begin(), inter.end());
+    }
+    return inter;
+}
+// refine_multilevel.rs:85-112
+inline std::vector<std::vector<uint32_t>> build_candidate_sets(const std::vector<std::vector<uint32_t>>& siblings,
+                                                               const std::vector<std::vector<uint32_t>>& bbknn, const std::vector<uint32_t>& labels) {
+    std::vector<std::vector<uint32_t>> out(siblings.size());
+    for (size_t e = 0; e < siblings.size(); ++e) {
+        std::vector<uint32_t> ng;
+        for (uint32_t j : bbknn[e]) ng.push_back(labels[j]);
+        std::sort(ng.begin(), ng.end());
+        ng.erase(std::unique(ng.begin(), ng.end()), ng.end());
+        out[e] = intersect_with_siblings_fallback(siblings[e], ng, labels[e]);
+    }
+    return out;
+}
+struct RefinedAssignment {  // refine_multilevel.rs:44-47
+    std::vector<std::vector<uint32_t>> pbsamp_to_group;
+    std::vector<uint32_t> num_groups_per_level;
+    uint64_t moves = 0;
+};
+// refine_assignments (refine_multilevel.rs:170-298).  gene_sums: D x npb column-major (a pb-sample's genes contiguous);
+// bbknn: the matched foreign pb-samples of every pb-sample; initial / offsets: per level (finest first) one entry per pb-sample,
+// an empty offsets level falls back to child_offset_within_parent.
+inline RefinedAssignment refine_assignments(const Context& ctx, const std::vector<float>& gene_sums, size_t D, uint32_t npb,
+                                            const std::vector<std::vector<uint32_t>>& bbknn, const std::vector<std::vector<uint32_t>>& initial,
+                                            const std::vector<std::vector<uint32_t>>& offsets, const RefineParams& params) {
+    if (initial.empty()) throw Error(LG_ERR_INVALID, "no levels");
+    const size_t L = initial.size();
+    RefinedAssignment out;
+    for (size_t l = 0; l < L; ++l) {
+        if (initial[l].size() != npb)
+            throw Error(LG_ERR_INVALID, "level " + std::to_string(l) + " has " + std::to_string(initial[l].size()) + " entries, expected " + std::to_string(npb));
+        auto cl = compact_labels(std::vector<uint64_t>(initial[l].begin(), initial[l].end()));
+        out.pbsamp_to_group.push_back(std::move(cl.first));
+        out.num_groups_per_level.push_back(cl.second);
+    }
+    if (params.num_gibbs == 0 && params.num_greedy == 0) return out;  // :215-222
+    std::vector<float> prof(gene_sums), w, sf(npb);
+    if (params.fisher_info_nb) {
+        w.resize(D);
+        ctx.check(lg_dcp_fisher_weights(ctx.get(), prof.data(), D, npb, w.data()));
+    }
+    ctx.check(lg_dcp_profiles(ctx.get(), prof.data(), D, npb, w.empty() ? nullptr : w.data(), sf.data()));
+    SmallRng rng(params.seed);
+    auto& refined = out.pbsamp_to_group;
+    for (size_t level = L; level-- > 0;) {
+        if (level + 1 < L) {  // re-anchor in the REFINED parent by the child hash relative to its parent (:255-280)
+            const std::vector<uint32_t> off = (level < offsets.size() && !offsets[level].empty()) ? offsets[level]
+                                                                                                   : child_offset_within_parent(initial[level], initial[level + 1]);
+            auto pr = project_to_refinement(off, refined[level + 1]);
+            refined[level] = std::move(pr.first);
+            out.num_groups_per_level[level] = pr.second;
+        }
+        const uint32_t k = out.num_groups_per_level[level];
+        const auto cand = build_candidate_sets(compute_sibling_sets(refined, level, k), bbknn, refined[level]);
+        std::vector<uint32_t> cptr(npb + 1, 0), cflat;
+        for (uint32_t e = 0; e < npb; ++e) {
+            cflat.insert(cflat.end(), cand[e].begin(), cand[e].end());
+            cptr[e + 1] = (uint32_t)cflat.size();
+        }
+        const uint64_t base_seed = rng.next_u64() | 1ull;  // dc_poisson.rs:824
+        uint64_t moves = 0;
+        ctx.check(lg_dcp_refine_level(ctx.get(), prof.data(), sf.data(), D, npb, cptr.data(), cflat.data(), k, (int)params.num_gibbs,
+                                      (int)params.num_greedy, base_seed, params.gibbs_stagnation, refined[level].data(), &moves));
+        out.moves += moves;
+        auto cl = compact_labels(std::vector<uint64_t>(refined[level].begin(), refined[level].end()));  // a sweep can empty a group (:292-295)
+        refined[level] = std::move(cl.first);
+        out.num_groups_per_level[level] = cl.second;
+    }
+    return out;
 }
 
 // data-beans/src/sparse_io_vector: one preloaded backend's columns on the device + the derived caches (mod.rs:70-85)
@@ -374,6 +529,7 @@ class SparseIoVec {
     SparseIoVec(const SparseIoVec&) = delete;
     SparseIoVec& operator=(const SparseIoVec&) = delete;
     size_t num_rows() const { return nrows_; }
+    uint64_t refine_moves() const { return refine_moves_; }  // accepted DC-Poisson moves of the last multilevel collapse
     size_t num_columns() const { return ncols_; }
     const lg_csc* block() const { return csc_; }
 
@@ -655,9 +811,6 @@ class SparseIoVec {
     MultilevelCollapseOut refine_and_collect(const DMatrix& proj_kn, const std::vector<size_t>& level_dims, const MultilevelParams& params,
                                              const std::vector<std::vector<uint32_t>>* inherited) {
         const uint32_t nb = (uint32_t)num_batches(), nbl = std::max<uint32_t>(nb, 1), ng = (uint32_t)num_groups_;
-        if (!inherited && nb >= 2)
-            throw Error(LG_ERR_INVALID, "BBKNN + DC-SBM refinement over two or more batches is outside the hot path (SURVEY.md section "
-                                        "8f rank 3); set refine = false or inherit a partition");
         const size_t cap = (size_t)ng * nbl, K = proj_kn.nrows;
         std::vector<uint32_t> c2p(ncols_), pg(cap), pb(cap), zero_batch;
         std::vector<float> cnt(cap), cen(cap * K);
@@ -703,6 +856,27 @@ class SparseIoVec {
                 auto cl = compact_labels(codes);
                 p2g.push_back(std::move(cl.first));
                 k_level.push_back(cl.second);
+            }
+            if (nb >= 2) {  // refine_or_identity(num_batches >= 2, ..) (refine.rs:329-345)
+                const uint32_t nslot = nb * (uint32_t)params.knn_pb_samples;
+                std::vector<uint32_t> mp((size_t)npb * nslot);
+                std::vector<float> md((size_t)npb * nslot);
+                ctx_.check(lg_pb_match(ctx_.get(), proj_kn.data.data(), (int)K, ncols_, col_to_batch_.data(), nb, c2p.data(), cen.data(), pb.data(),
+                                       npb, (int)params.knn_pb_samples, mp.data(), md.data()));
+                std::vector<std::vector<uint32_t>> bbknn(npb), offsets(level_dims.size());  // build_bbknn_neighbors (refine_multilevel.rs:60-83)
+                for (uint32_t p = 0; p < npb; ++p)
+                    for (uint32_t i = 0; i < nslot; ++i)
+                        if (mp[(size_t)p * nslot + i] != 0xFFFFFFFFu) bbknn[p].push_back(mp[(size_t)p * nslot + i]);
+                for (size_t level = 0; level + 1 < level_dims.size(); ++level) {  // build_reproject_offsets (refine.rs:95-125)
+                    const size_t parent_dim = level_dims[level + 1], nbits = level_dims[level] > parent_dim ? level_dims[level] - parent_dim : 0;
+                    const uint64_t mask = nbits >= 64 ? ~0ull : ((1ull << nbits) - 1);
+                    offsets[level].resize(npb);
+                    for (uint32_t p = 0; p < npb; ++p) offsets[level][p] = (uint32_t)((binary_codes_[first[p]] >> parent_dim) & mask);
+                }
+                RefinedAssignment ra = refine_assignments(ctx_, gene_sums, nrows_, npb, bbknn, p2g, offsets, params.refine_params);
+                p2g = std::move(ra.pbsamp_to_group);
+                k_level = std::move(ra.num_groups_per_level);
+                refine_moves_ = ra.moves;
             }
         }
         // finest groups: pad_numeric_labels + assign_groups = the numeric id itself (refine.rs:21-35, 393-399)
@@ -753,6 +927,7 @@ class SparseIoVec {
         return out;
     }
     const float* mult() const { return multiplicity_.empty() ? nullptr : multiplicity_.data(); }
+    uint64_t refine_moves_ = 0;
     const Context& ctx_;
     lg_csc* csc_ = nullptr;
     size_t nrows_ = 0, ncols_ = 0, num_groups_ = 0, sort_dim_ = 0;

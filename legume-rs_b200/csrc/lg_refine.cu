@@ -19,6 +19,7 @@
 // The picks (a few thousand Gumbel draws per sweep from per-entity xoshiro256++ streams), the k-long size sums and the sweep
 // control (stagnation / no-move exits) stay on the host between the kernels.  The label bookkeeping around the levels
 // (compact_labels, project_to_refinement, sibling and candidate sets) is host code in the mirrors.
+#include <chrono>
 #include <cmath>
 #include <cstring>
 #include <limits>
@@ -346,11 +347,22 @@ extern "C" int lg_dcp_refine_level(lg_ctx* ctx, const float* profiles, const flo
     std::vector<double> scores(npairs);
     std::vector<uint32_t> prop(npb), mv;
     uint64_t total_moves = 0;
+    // LG_TRACE=1: where a level's time goes (scores kernel + read-back, the host picks, applying the moves), on stderr
+    const char* tr = getenv("LG_TRACE");
+    const bool trace = tr && tr[0] == '1';
+    double t_score = 0.0, t_pick = 0.0, t_apply = 0.0;
+    int nsweeps = 0;
+    auto now = [] { return std::chrono::steady_clock::now(); };
+    auto ms = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) {
+        return std::chrono::duration<double, std::milli>(b - a).count();
+    };
     auto sweep = [&](bool gibbs, uint64_t sweep_seed, uint64_t* moved) -> int {
+        const auto t0 = now();
         if (vec) LG_LAUNCH(ctx, k_dcp_scores<true>, (unsigned)((npairs + 127) / 128), 128, 0, d_p, D, d_sf_in, d_lg, d_lso, d_pe, d_pk, npairs, d_scores);
         else LG_LAUNCH(ctx, k_dcp_scores<false>, (unsigned)((npairs + 127) / 128), 128, 0, d_p, D, d_sf_in, d_lg, d_lso, d_pe, d_pk, npairs, d_scores);
         LG_CUDA(ctx, cudaMemcpyAsync(scores.data(), d_scores, sizeof(double) * npairs, cudaMemcpyDeviceToHost, ctx->stream));
         LG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        const auto t1 = now();
         for (uint32_t e = 0; e < npb; ++e) {
             prop[e] = mem[e];
             const uint32_t a = first[e], b = first[e + 1];
@@ -391,6 +403,7 @@ extern "C" int lg_dcp_refine_level(lg_ctx* ctx, const float* profiles, const flo
             mem[e] = prop[e];
         }
         *moved = mv.size() / 3;
+        const auto t2 = now();
         if (*moved) {
             LG_CUDA(ctx, cudaMemcpyAsync(d_mv, mv.data(), sizeof(uint32_t) * mv.size(), cudaMemcpyHostToDevice, ctx->stream));
             LG_CUDA(ctx, cudaMemcpyAsync(d_lso, lso.data(), sizeof(float) * k, cudaMemcpyHostToDevice, ctx->stream));
@@ -398,6 +411,10 @@ extern "C" int lg_dcp_refine_level(lg_ctx* ctx, const float* profiles, const flo
             LG_LAUNCH(ctx, k_dcp_logs, (unsigned)((KM + 255) / 256), 256, 0, d_gs, KM, d_lg);
             LG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // mv / lso are reused by the next sweep
         }
+        t_score += ms(t0, t1);
+        t_pick += ms(t1, t2);
+        t_apply += ms(t2, now());
+        ++nsweeps;
         return LG_OK;
     };
     int low = 0;
@@ -422,5 +439,8 @@ extern "C" int lg_dcp_refine_level(lg_ctx* ctx, const float* profiles, const flo
     LG_CUDA(ctx, cudaMemcpyAsync(labels, mem.data(), sizeof(uint32_t) * npb, cudaMemcpyDefault, ctx->stream));
     LG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     if (out_moves) *out_moves = total_moves;
+    if (trace)
+        fprintf(stderr, "[lg_dcp_refine_level] %u entities x %llu features, k = %u, %llu scored pairs, %d sweeps, %llu moves: scores %.1f ms, picks %.1f ms, apply %.1f ms\n",
+                npb, (unsigned long long)D, k, (unsigned long long)npairs, nsweeps, (unsigned long long)total_moves, t_score, t_pick, t_apply);
     return LG_OK;
 }

@@ -131,6 +131,13 @@ void orc_collect_matched_stat_coarse(const float* gene_sums_dp, uint64_t nrows, 
 /* refine.rs:741-769; returns the number of coarse groups */
 uint32_t orc_fine_to_coarse(const uint64_t* group_code, uint32_t nfine, int coarse_dim, uint32_t* fine_to_coarse);
 
+/* ---- BBKNN + DC-Poisson refinement of the pb-sample partition (oracle_refine.cpp; refine_multilevel.rs:170-298) ----
+ * gene_sums: E x M dense (an entity's row contiguous); bbknn: CSR of matched entities; initial / offsets: num_levels x E
+ * (finest first; offsets may be NULL); out_levels: num_levels x E; out_k: num_levels.  Returns the accepted moves. */
+uint64_t orc_refine_assignments(const float* gene_sums, uint32_t E, uint64_t M, const uint32_t* bb_ptr, const uint32_t* bb,
+                                int num_levels, const uint32_t* initial, const uint32_t* offsets, int num_gibbs, int num_greedy,
+                                int fisher, uint64_t seed, double stagnation, uint32_t* out_levels, uint32_t* out_k);
+
 /* ---- synthetic counts (data-beans-sim/src/core.rs:155-203 restated with a
  *      counter-based RNG so CPU and GPU produce identical matrices) ---------- */
 /* table entry e = ((k*B + b)*D + g): lam[e], p0[e]=exp(-lam[e]) precomputed by the caller,

@@ -276,6 +276,64 @@ int main() {
         }
         CHECK(threw);
     }
+    {  // ---- the refinement arm with THREE batches: BBKNN candidates + DC-Poisson sweeps (refine_multilevel.rs:170-298) ----
+        SparseIoVec three(ctx, m.indptr, m.indices, m.data, m.nrows);
+        MultilevelParams params(K);
+        params.sort_dim = 9;
+        params.num_levels = 2;
+        params.knn_pb_samples = 3;
+        params.num_opt_iter = 12;
+        MultilevelCollapseOut out = three.collapse_columns_multilevel_with_hierarchy(rp.proj, batch, params);
+        const std::vector<size_t> dims = compute_level_sort_dims(9, 2);
+        const uint32_t B = (uint32_t)three.num_batches();
+        CHECK(B == 3 && out.levels.size() == dims.size());
+        std::vector<uint64_t> codes(N);
+        CHECK(orc_binary_codes(rp.proj.data.data(), (int)K, N, (int)dims[0], codes.data(), nullptr, nullptr, nullptr, nullptr) == 0);
+        std::vector<uint32_t> hash_grp(N);
+        const uint32_t ng = orc_assign_groups(codes.data(), N, hash_grp.data());
+        const std::vector<uint32_t>& bat = three.col_to_batch();
+        std::vector<uint32_t> c2p(N), pg((size_t)ng * B), pb((size_t)ng * B);
+        std::vector<float> cnt((size_t)ng * B), cen((size_t)ng * B * K);
+        const uint32_t npb = orc_pb_layout(rp.proj.data.data(), (int)K, N, hash_grp.data(), ng, bat.data(), B, nullptr, c2p.data(), pg.data(),
+                                           pb.data(), cnt.data(), cen.data());
+        std::vector<float> gs((size_t)D * npb), gsz(npb);
+        orc_collapse_basic(m.indptr.data(), m.indices.data(), m.data.data(), D, N, c2p.data(), nullptr, npb, gs.data(), gsz.data());
+        std::vector<uint32_t> mp((size_t)npb * B * 3), bb_ptr(npb + 1, 0), bb;
+        std::vector<float> md((size_t)npb * B * 3);
+        orc_pb_match(rp.proj.data.data(), (int)K, N, bat.data(), B, c2p.data(), cen.data(), pb.data(), npb, 3, mp.data(), md.data(), 1);
+        for (uint32_t p = 0; p < npb; ++p) {
+            for (uint32_t i = 0; i < B * 3; ++i)
+                if (mp[(size_t)p * B * 3 + i] != 0xFFFFFFFFu) bb.push_back(mp[(size_t)p * B * 3 + i]);
+            bb_ptr[p + 1] = (uint32_t)bb.size();
+        }
+        const size_t L = dims.size();
+        std::vector<uint64_t> first_code(npb, 0);
+        for (size_t c = N; c-- > 0;) first_code[c2p[c]] = codes[c];
+        std::vector<uint32_t> init(L * npb), offs(L * npb, 0u), want(L * npb), want_k(L);
+        for (size_t level = 0; level < L; ++level) {
+            std::vector<uint64_t> masked(npb);
+            for (uint32_t p = 0; p < npb; ++p) masked[p] = first_code[p] & ((1ull << dims[level]) - 1);
+            auto cl = compact_labels(masked);
+            std::copy(cl.first.begin(), cl.first.end(), init.begin() + level * npb);
+            if (level + 1 < L)
+                for (uint32_t p = 0; p < npb; ++p)
+                    offs[level * npb + p] = (uint32_t)((first_code[p] >> dims[level + 1]) & ((1ull << (dims[level] - dims[level + 1])) - 1));
+        }
+        const uint64_t wmoves = orc_refine_assignments(gs.data(), npb, D, bb_ptr.data(), bb.data(), (int)L, init.data(), offs.data(), 20, 10, 1, 42,
+                                                       0.005, want.data(), want_k.data());
+        CHECK(three.refine_moves() == wmoves);
+        bool maps_ok = true;
+        for (size_t level = 0; level < L; ++level) {
+            CHECK(out.stats[level].num_samples() == want_k[level]);
+            for (size_t c = 0; c < N; ++c) maps_ok = maps_ok && out.cell_to_pb_per_level[level][c] == want[level * npb + c2p[c]];
+        }
+        CHECK(maps_ok);
+        const std::vector<uint32_t>& fine = out.cell_to_pb_per_level[0];
+        const uint32_t S0 = (uint32_t)out.stats[0].num_samples();
+        std::vector<float> ws((size_t)D * S0), wn(S0);
+        orc_collapse_basic(m.indptr.data(), m.indices.data(), m.data.data(), D, N, fine.data(), nullptr, S0, ws.data(), wn.data());
+        CHECK(out.stats[0].observed_sum_ds.data == ws && out.stats[0].size_s == wn);
+    }
     {  // ---- either side of the path: running statistics (sparse_stat.rs:671-728) and the Nystrom pass ----
         std::mt19937 rng21(21);
         Csc m = random_counts(rng21, 300, 500, 0.1);

@@ -31,7 +31,7 @@ def _timed(fn, reps=2, warm=2):
     return out, a.elapsed_time(b) / reps
 
 
-def c3_adjust(ctx, hp, N=1_000_000, B=8, D=30000, K=50, kk=10, knn=10, reps=2, per_cell=True):
+def c3_adjust(ctx, hp, N=1_000_000, B=8, D=30000, K=50, kk=10, knn=10, reps=2, per_cell=True, do_refine=True):
     """stage times (ms) of configs[2] on one GPU; returns a dict ready for the bench line"""
     import legume_b200 as lg
     from legume_b200 import sim
@@ -84,9 +84,33 @@ def c3_adjust(ctx, hp, N=1_000_000, B=8, D=30000, K=50, kk=10, knn=10, reps=2, p
                                                                             p(outs[3]), p(delta), p(outs[4]))))
     pb_arm = ["project", "binary_codes", "assign_groups", "collapse_basic", "collapse_batch", "pb_layout", "pb_gene_sums", "pb_match",
               "pb_matched_stat_coarse", "optimize_batched_30it"]
+    # the refinement of the pb-sample partition that MultilevelParams::new switches on (refine.rs:329-345): 20 Gibbs + 10 greedy
+    # Jacobi sweeps per level, two levels, NB Fisher weights; wall clock (the picks and the candidate sets are host work)
+    refine = None
+    if do_refine:
+        import time
+        codes_h = codes.cpu().numpy().astype(np.uint64)
+        c2p_h = c2p.cpu().numpy().astype(np.int64)
+        first = np.full(npb, N, np.int64)
+        np.minimum.at(first, c2p_h, np.arange(N))
+        dims = lg.compute_level_sort_dims(kk, 2)
+        init = lg.initial_per_level_from_hash(codes_h, first, dims)
+        offs = lg.build_reproject_offsets(codes_h, first, dims)
+        mp_h = mp.cpu().numpy().astype(np.uint32)
+        bbknn = [row[row != 0xFFFFFFFF].tolist() for row in mp_h]
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        lv, ks, moves = lg.refine_assignments(ctx, gs, bbknn, init, offs, lg.RefineParams())
+        torch.cuda.synchronize()
+        t["pb_refine"] = (time.perf_counter() - t0) * 1e3
+        refine = {"levels": [int(d) for d in dims], "groups_before": [int(x.max()) + 1 for x in init], "groups_after": ks, "moves": moves,
+                  "sweeps": "20 Gibbs (stagnation 0.005) + 10 greedy per level, Fisher weights"}
     del gs
     out = {"workload": f"{D} genes x {N} cells, {B} batches, k={knn}, 2^{kk} bins -> {S} groups, {npb} pb-samples, nnz={blk.nnz}",
            "pb_arm_ms": sum(t[k] for k in pb_arm), "pb_arm_cells_per_s": N / sum(t[k] for k in pb_arm) * 1e3}
+    if refine is not None:
+        out["pb_refine"] = refine
+        out["pb_arm_with_refine_ms"] = out["pb_arm_ms"] + t["pb_refine"]
     if per_cell:
         order = np.empty((B, B), np.uint32)
         run("batch_proximity", lambda: ctx.check(lib.lg_batch_proximity(ctx.h, p(proj), K, N, p(batch), B, p(order), None)))
