@@ -23,6 +23,8 @@
 #include <cmath>
 #include <cstring>
 #include <limits>
+#include <thread>
+#include <type_traits>
 
 #include "lg_common.cuh"
 
@@ -150,6 +152,72 @@ __global__ void __launch_bounds__(128) k_dcp_scores(const float* __restrict__ P,
         }
     }
     out[i] = acc;
+}
+
+// The same scores with the operands staged through shared memory.  In the one-thread-per-pair form every pair streams its own
+// copy of a log_gene row (4 * M bytes per pair and sweep out of L2: 14 GB per sweep at 120 000 pairs x 30 000 genes, which is
+// what bounded it).  Here a CTA owns up to DCP_PAIRS consecutive pairs — consecutive entities, whose candidate groups overlap —
+// and walks the feature axis in tiles of DCP_GT: all threads copy the tile of the CTA's DISTINCT log_gene rows and of its
+// entities' profile rows into shared memory (coalesced 512-byte row pieces), then thread p continues ITS pair's single f64
+// accumulator over the tile, ascending.  The order of every pair's additions is unchanged, so the scores are bit-identical to
+// k_dcp_scores; the traffic drops to (rows + entities) * 4 * M bytes per CTA.  Row stride DCP_GT + 1: lanes that read different
+// rows at the same column hit different banks, lanes on the same row broadcast.
+constexpr int DCP_PAIRS = 512, DCP_ROWS = 128, DCP_ENTS = 64, DCP_GT = 128, DCP_LD = DCP_GT + 1;
+constexpr size_t DCP_SMEM = (size_t)(DCP_ROWS + DCP_ENTS) * DCP_LD * sizeof(float);
+__global__ void __launch_bounds__(DCP_PAIRS, 2) k_dcp_scores_tiled(const float* __restrict__ P, uint64_t M, const float* __restrict__ sf,
+                                                                  const float* __restrict__ lg, const float* __restrict__ lso,
+                                                                  const uint32_t* __restrict__ pair_e, const uint32_t* __restrict__ pair_k,
+                                                                  const uint32_t* __restrict__ cta_pair, const uint32_t* __restrict__ cta_row,
+                                                                  const uint32_t* __restrict__ rows, const uint32_t* __restrict__ cta_ent,
+                                                                  const uint32_t* __restrict__ ents, const uint16_t* __restrict__ pair_slot,
+                                                                  const uint16_t* __restrict__ pair_el, double* __restrict__ out) {
+    extern __shared__ float dcp_sm[];  // (nr + ne) rows of DCP_LD floats: the log_gene rows first, then the profile rows
+    __shared__ const float* base[DCP_ROWS + DCP_ENTS];
+    const uint32_t p0 = cta_pair[blockIdx.x], np = cta_pair[blockIdx.x + 1] - p0;
+    const uint32_t r0 = cta_row[blockIdx.x], nr = cta_row[blockIdx.x + 1] - r0;
+    const uint32_t e0 = cta_ent[blockIdx.x], ne = cta_ent[blockIdx.x + 1] - e0;
+    if (threadIdx.x < nr + ne)
+        base[threadIdx.x] = threadIdx.x < nr ? lg + (size_t)rows[r0 + threadIdx.x] * M : P + (size_t)ents[e0 + threadIdx.x - nr] * M;
+    const bool live = threadIdx.x < np;
+    double acc = 0.0;
+    const float *my_l = dcp_sm, *my_p = dcp_sm;
+    if (live) {
+        const uint32_t i = p0 + threadIdx.x;
+        acc = (double)sf[pair_e[i]] * (double)lso[pair_k[i]];
+        my_l = dcp_sm + (size_t)pair_slot[i] * DCP_LD;
+        my_p = dcp_sm + (size_t)(nr + pair_el[i]) * DCP_LD;
+    }
+    const uint32_t total = (nr + ne) * DCP_GT;
+    constexpr int U = 8;  // row pieces in flight per thread: the copy is latency-bound otherwise (one L2 round trip per element)
+    for (uint64_t g0 = 0; g0 < M; g0 += DCP_GT) {
+        __syncthreads();  // the previous tile has been consumed (and `base` is visible on the first round)
+        for (uint32_t idx = threadIdx.x; idx < total; idx += DCP_PAIRS * U) {
+            float v[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const uint32_t i = idx + u * DCP_PAIRS;
+                v[u] = 0.0f;
+                if (i < total) {
+                    const uint64_t g = g0 + (i % DCP_GT);
+                    if (g < M) v[u] = base[i / DCP_GT][g];
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const uint32_t i = idx + u * DCP_PAIRS;
+                if (i < total) dcp_sm[(i / DCP_GT) * DCP_LD + (i % DCP_GT)] = v[u];
+            }
+        }
+        __syncthreads();
+        if (live) {
+#pragma unroll 8
+            for (int j = 0; j < DCP_GT; ++j) {
+                const float v = my_p[j];
+                if (v > 0.0f) acc = fma((double)v, (double)my_l[j], acc);  // columns past M hold 0
+            }
+        }
+    }
+    if (live) out[p0 + threadIdx.x] = acc;
 }
 
 // delta_move (:352-377) for a list of accepted moves in entity order; one thread per feature
@@ -344,6 +412,68 @@ extern "C" int lg_dcp_refine_level(lg_ctx* ctx, const float* profiles, const flo
     LG_CUDA(ctx, cudaMemcpyAsync(d_lso, lso.data(), sizeof(float) * k, cudaMemcpyHostToDevice, ctx->stream));
 
     const bool vec = (D % 4 == 0) && ((reinterpret_cast<uintptr_t>(d_p) & 15) == 0) && ((reinterpret_cast<uintptr_t>(d_lg) & 15) == 0);
+    // plan of the tiled score kernel: consecutive entities go to one CTA while its pairs, its distinct candidate groups and its
+    // entities fit (DCP_PAIRS / DCP_ROWS / DCP_ENTS); the candidate sets are fixed for the level, so the plan is built once.
+    // An entity with more than DCP_ROWS candidates (a coarsest level beyond 2^7 groups) keeps the one-thread-per-pair kernel.
+    bool tiled = !getenv("LG_DCP_UNTILED") && DCP_SMEM <= ctx->smem_optin;
+    std::vector<uint32_t> cta_pair{0}, cta_row{0}, cta_ent{0}, rows_flat, ents_flat;
+    std::vector<uint16_t> pslot(npairs), pel(npairs);
+    if (tiled) {
+        std::vector<uint32_t> slot_of(k, 0xFFFFFFFFu), cur_rows;
+        uint32_t cur_pairs = 0, cur_ents = 0;
+        auto close = [&]() {
+            for (uint32_t r : cur_rows) slot_of[r] = 0xFFFFFFFFu;
+            rows_flat.insert(rows_flat.end(), cur_rows.begin(), cur_rows.end());
+            cta_pair.push_back(cta_pair.back() + cur_pairs);
+            cta_row.push_back((uint32_t)rows_flat.size());
+            cta_ent.push_back((uint32_t)ents_flat.size());
+            cur_rows.clear();
+            cur_pairs = cur_ents = 0;
+        };
+        for (uint32_t e = 0; e < npb && tiled; ++e) {
+            const uint32_t a = first[e], b = first[e + 1];
+            if (a == b) continue;
+            if (b - a > (uint32_t)DCP_ROWS || b - a > (uint32_t)DCP_PAIRS) {
+                tiled = false;
+                break;
+            }
+            uint32_t fresh = 0;
+            for (uint32_t i = a; i < b; ++i) fresh += slot_of[pk[i]] == 0xFFFFFFFFu;
+            if (cur_pairs + (b - a) > (uint32_t)DCP_PAIRS || cur_rows.size() + fresh > (size_t)DCP_ROWS || cur_ents + 1 > (uint32_t)DCP_ENTS) close();
+            for (uint32_t i = a; i < b; ++i) {
+                if (slot_of[pk[i]] == 0xFFFFFFFFu) {
+                    slot_of[pk[i]] = (uint32_t)cur_rows.size();
+                    cur_rows.push_back(pk[i]);
+                }
+                pslot[i] = (uint16_t)slot_of[pk[i]];
+                pel[i] = (uint16_t)cur_ents;
+            }
+            ents_flat.push_back(e);
+            cur_pairs += b - a;
+            ++cur_ents;
+        }
+        if (tiled && cur_pairs) close();
+    }
+    uint32_t *d_cta_pair = nullptr, *d_cta_row = nullptr, *d_cta_ent = nullptr, *d_rows = nullptr, *d_ents = nullptr;
+    uint16_t *d_pslot = nullptr, *d_pel = nullptr;
+    const uint32_t ncta = tiled ? (uint32_t)cta_pair.size() - 1 : 0;
+    if (tiled) {
+        auto up = [&](const auto& v, auto** d) -> int {
+            using T = typename std::remove_reference<decltype(v)>::type::value_type;
+            LG_TRY(st.scratch(v.size(), d));
+            if (!v.empty()) LG_CUDA(ctx, cudaMemcpyAsync(*d, v.data(), sizeof(T) * v.size(), cudaMemcpyHostToDevice, ctx->stream));
+            return LG_OK;
+        };
+        LG_TRY(up(cta_pair, &d_cta_pair));
+        LG_TRY(up(cta_row, &d_cta_row));
+        LG_TRY(up(cta_ent, &d_cta_ent));
+        LG_TRY(up(rows_flat, &d_rows));
+        LG_TRY(up(ents_flat, &d_ents));
+        LG_TRY(up(pslot, &d_pslot));
+        LG_TRY(up(pel, &d_pel));
+        LG_CUDA(ctx, cudaFuncSetAttribute(k_dcp_scores_tiled, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DCP_SMEM));
+        LG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // the plan vectors are host temporaries
+    }
     std::vector<double> scores(npairs);
     std::vector<uint32_t> prop(npb), mv;
     uint64_t total_moves = 0;
@@ -358,12 +488,17 @@ extern "C" int lg_dcp_refine_level(lg_ctx* ctx, const float* profiles, const flo
     };
     auto sweep = [&](bool gibbs, uint64_t sweep_seed, uint64_t* moved) -> int {
         const auto t0 = now();
-        if (vec) LG_LAUNCH(ctx, k_dcp_scores<true>, (unsigned)((npairs + 127) / 128), 128, 0, d_p, D, d_sf_in, d_lg, d_lso, d_pe, d_pk, npairs, d_scores);
+        if (tiled)
+            LG_LAUNCH(ctx, k_dcp_scores_tiled, ncta, DCP_PAIRS, DCP_SMEM, d_p, D, d_sf_in, d_lg, d_lso, d_pe, d_pk, d_cta_pair, d_cta_row, d_rows,
+                      d_cta_ent, d_ents, d_pslot, d_pel, d_scores);
+        else if (vec) LG_LAUNCH(ctx, k_dcp_scores<true>, (unsigned)((npairs + 127) / 128), 128, 0, d_p, D, d_sf_in, d_lg, d_lso, d_pe, d_pk, npairs, d_scores);
         else LG_LAUNCH(ctx, k_dcp_scores<false>, (unsigned)((npairs + 127) / 128), 128, 0, d_p, D, d_sf_in, d_lg, d_lso, d_pe, d_pk, npairs, d_scores);
         LG_CUDA(ctx, cudaMemcpyAsync(scores.data(), d_scores, sizeof(double) * npairs, cudaMemcpyDeviceToHost, ctx->stream));
         LG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
         const auto t1 = now();
-        for (uint32_t e = 0; e < npb; ++e) {
+        // the picks are independent per entity (per-entity RNG streams): a few host threads share them
+        auto pick_range = [&](uint32_t e_lo, uint32_t e_hi) {
+        for (uint32_t e = e_lo; e < e_hi; ++e) {
             prop[e] = mem[e];
             const uint32_t a = first[e], b = first[e + 1];
             if (a == b) continue;
@@ -387,6 +522,16 @@ extern "C" int lg_dcp_refine_level(lg_ctx* ctx, const float* profiles, const flo
                     if (scores[i] > scores[bi]) bi = i;
                 prop[e] = pk[bi];
             }
+        }
+        };
+        {
+            const unsigned hc = std::thread::hardware_concurrency();
+            const uint32_t nt = gibbs && npairs >= 16384 ? std::min<uint32_t>(hc ? hc : 4u, 8u) : 1u;
+            std::vector<std::thread> pool;
+            const uint32_t per = (npb + nt - 1) / nt;
+            for (uint32_t t = 1; t < nt; ++t) pool.emplace_back(pick_range, std::min(npb, t * per), std::min(npb, (t + 1) * per));
+            pick_range(0, std::min(npb, per));
+            for (auto& th : pool) th.join();
         }
         // apply_proposals (:661-686) in entity order
         mv.clear();

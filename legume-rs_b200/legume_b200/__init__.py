@@ -628,6 +628,35 @@ def build_candidate_sets(siblings, bbknn, pbsamp_to_group):
     return [intersect_with_siblings_fallback(sib, {lab[j] for j in bbknn[e]}, lab[e]) for e, sib in enumerate(siblings)]
 
 
+def _candidate_csr(refined, level, k, bbknn_matrix):
+    """compute_sibling_sets + build_candidate_sets for every entity at once, as (cand_ptr, cand) of the CSR the ABI takes.
+    bbknn_matrix: (npb, T) matched entities, NONE_U32 where there is none.  Same sets as the list forms above (tested); used
+    when the npb x k membership matrices are small enough, which they are for every partition the path produces."""
+    lab = np.asarray(refined[level], np.int64)
+    n = len(lab)
+    if level + 1 < len(refined):
+        par = np.asarray(refined[level + 1], np.int64)
+        parent_of_group = np.zeros(k, np.int64)
+        parent_of_group[lab] = par  # a strict hierarchy: every entity of a group names the same parent
+        sib = parent_of_group[None, :] == par[:, None]
+    else:
+        sib = np.ones((n, k), bool)
+    bb = np.asarray(bbknn_matrix)
+    ok = bb != NONE_U32
+    nb_groups = np.zeros((n, k), bool)
+    rows = np.broadcast_to(np.arange(n)[:, None], bb.shape)[ok]
+    nb_groups[rows, lab[bb[ok].astype(np.int64)]] = True
+    inter = sib & nb_groups
+    some = inter.any(axis=1)
+    inter[np.arange(n)[some], lab[some]] = True          # staying put is always legal (dc_poisson.rs:624-632)
+    single = sib.sum(axis=1) <= 1
+    use_sib = single | ~some                               # a lone sibling, or an empty intersection: the siblings (:604-617)
+    cand = np.where(use_sib[:, None], sib, inter)
+    ptr = np.zeros(n + 1, np.uint32)
+    ptr[1:] = np.cumsum(cand.sum(axis=1))
+    return ptr, np.nonzero(cand)[1].astype(np.uint32)
+
+
 def refine_assignments(ctx: Context, gene_sums, bbknn, initial_per_level, reproject_offsets, params: "RefineParams"):
     """refine_multilevel.rs:170-298: top-down BBKNN + DC-Poisson refinement of the pb-sample -> group maps (finest first).
     gene_sums: (npb, D) dense pb-sample gene sums; bbknn: per pb-sample the matched foreign pb-samples.  Returns
@@ -658,6 +687,10 @@ def refine_assignments(ctx: Context, gene_sums, bbknn, initial_per_level, reproj
     ctx.check(lib.lg_dcp_profiles(ctx.h, _ptr(prof), D, npb, _ptr(w), _ptr(sf)))
     rng = _Xoshiro256pp(params.seed)
     total = 0
+    # bbknn: per entity a list of matched entities, or the (npb, T) matrix of per_batch_sc_neighbors with NONE_U32 padding
+    bb_matrix = bbknn if isinstance(bbknn, np.ndarray) and bbknn.ndim == 2 else None
+    if bb_matrix is not None:
+        bbknn = None
     for level in range(L - 1, -1, -1):
         if level + 1 < L:  # re-anchor this level in its REFINED parent by the child hash relative to the parent (:255-280)
             off = reproject_offsets[level] if reproject_offsets is not None and level < len(reproject_offsets) else ()
@@ -665,10 +698,15 @@ def refine_assignments(ctx: Context, gene_sums, bbknn, initial_per_level, reproj
                 off = child_offset_within_parent(initial_per_level[level], initial_per_level[level + 1])
             refined[level], ks[level] = project_to_refinement(off, refined[level + 1])
         k = ks[level]
-        cand = build_candidate_sets(compute_sibling_sets(refined, level, k), bbknn, refined[level])
-        cptr = np.zeros(npb + 1, np.uint32)
-        cptr[1:] = np.cumsum([len(c) for c in cand])
-        cflat = np.fromiter((g for c in cand for g in c), np.uint32, int(cptr[-1]))
+        if bb_matrix is not None and npb * k <= (1 << 28):
+            cptr, cflat = _candidate_csr(refined, level, k, bb_matrix)
+        else:
+            if bbknn is None:
+                bbknn = [row[row != NONE_U32].tolist() for row in bb_matrix]
+            cand = build_candidate_sets(compute_sibling_sets(refined, level, k), bbknn, refined[level])
+            cptr = np.zeros(npb + 1, np.uint32)
+            cptr[1:] = np.cumsum([len(c) for c in cand])
+            cflat = np.fromiter((g for c in cand for g in c), np.uint32, int(cptr[-1]))
         base_seed = rng.next() | 1  # dc_poisson.rs:824
         labels = np.ascontiguousarray(refined[level], np.uint32)
         moves = C.c_uint64(0)
@@ -1325,8 +1363,7 @@ class SparseIoVec:
         p2g = initial_per_level_from_hash(codes_h, first, level_dims)
         if nb >= 2:  # refine_or_identity(num_batches >= 2, ..): BBKNN candidates + DC-Poisson sweeps (refine.rs:329-345)
             matched, _ = per_batch_sc_neighbors(self.ctx, layout, proj_kn, self.col_to_batch, nb, params.knn_pb_samples)
-            mp = np.asarray(matched.cpu() if _is_torch(matched) else matched)
-            bbknn = [row[row != NONE_U32].tolist() for row in mp]  # build_bbknn_neighbors (refine_multilevel.rs:60-83)
+            bbknn = np.asarray(matched.cpu() if _is_torch(matched) else matched)  # build_bbknn_neighbors (refine_multilevel.rs:60-83)
             offsets = build_reproject_offsets(codes_h, first, level_dims)
             p2g, k, moves = refine_assignments(self.ctx, gene_sums, bbknn, p2g, offsets, params.refine)
             self.refine_moves = moves

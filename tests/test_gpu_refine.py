@@ -194,3 +194,51 @@ def test_multilevel_collapse_with_refinement_over_batches(lg, ctx):
         assert close(st.imputed_sum_ds, w["imp"], TOL) and close(st.residual_sum_ds, w["res"], TOL)
         assert close(out["levels"][level].mu_adjusted["mean"], w["fit"]["mu_adjusted"], 1e-4)
         assert np.array_equal(out["cell_to_pb_per_level"][level], p2g[level][lay["cell_to_pb"].astype(np.int64)])
+
+
+@pytest.mark.gpu
+def test_refine_level_tiled_and_untiled_forms_agree(lg, ctx, monkeypatch):
+    """the shared-memory form of the score kernel keeps every pair's order of additions: same labels as the one-thread-per-pair
+    form (LG_DCP_UNTILED=1) and as the oracle; a level whose candidate sets exceed 128 groups takes the untiled form by itself"""
+    from legume_b200._lib import lib
+    n, m = 700, 517  # a feature count that is neither a multiple of 4 nor of the 128-feature tile
+    for k, full in ((24, False), (160, True)):
+        P, truth = planted(n, m, min(k, 8), 11)
+        P, sf = orc.dcp_profiles(P, None)
+        rng = np.random.default_rng(12)
+        start = rng.integers(0, k, n).astype(np.uint32)
+        cand = [list(range(k)) if full or e % 2 else sorted({int(start[e]), int((start[e] + 3) % k), int((start[e] + 7) % k)}) for e in range(n)]
+        cp, cf = csr(cand)
+        got = {}
+        for form in ("tiled", "untiled"):
+            if form == "untiled":
+                monkeypatch.setenv("LG_DCP_UNTILED", "1")
+            else:
+                monkeypatch.delenv("LG_DCP_UNTILED", raising=False)
+            labels, moves = start.copy(), C.c_uint64(0)
+            ctx.check(lib.lg_dcp_refine_level(ctx.h, P.ctypes.data, sf.ctypes.data, m, n, cp.ctypes.data, cf.ctypes.data, k, 4, 6, 77, 0.0,
+                                              labels.ctypes.data, C.byref(moves)))
+            got[form] = (labels, moves.value)
+        want, wmoves = orc.dcp_refine_level(P, cand, k, start, 4, 6, 77, 0.0)
+        for form in got:
+            assert np.array_equal(got[form][0], want) and got[form][1] == wmoves
+
+
+def test_vectorised_candidate_sets_equal_the_list_form(lg):
+    from legume_b200 import _candidate_csr
+    rng = np.random.default_rng(21)
+    for n, kf, kc, T in ((1, 1, 1, 3), (50, 12, 3, 6), (400, 64, 8, 14)):
+        coarse = rng.integers(0, kc, n)
+        fine, k = lg.compact_labels(rng.integers(0, max(kf // kc, 1), n) * kc + coarse)  # a strict refinement of `coarse`
+        coarse, kcc = lg.compact_labels(coarse)
+        bb = rng.integers(0, n, (n, T)).astype(np.uint32)
+        bb[rng.random((n, T)) < 0.3] = 0xFFFFFFFF
+        bb[0] = 0xFFFFFFFF  # an entity without any neighbour falls back to its siblings
+        lists = [row[row != 0xFFFFFFFF].tolist() for row in bb]
+        for level, kk_ in ((0, k), (1, kcc)):
+            refined = [fine, coarse]
+            want = lg.build_candidate_sets(lg.compute_sibling_sets(refined, level, kk_), lists, refined[level])
+            ptr, flat = _candidate_csr(refined, level, kk_, bb)
+            got = [flat[ptr[e]:ptr[e + 1]].tolist() for e in range(n)]
+            assert got == want
+            assert got == orc.candidate_sets(orc.sibling_sets(refined[level], refined[1] if level == 0 else None, kk_), lists, refined[level])

@@ -97,7 +97,7 @@ def c3_adjust(ctx, hp, N=1_000_000, B=8, D=30000, K=50, kk=10, knn=10, reps=2, p
         init = lg.initial_per_level_from_hash(codes_h, first, dims)
         offs = lg.build_reproject_offsets(codes_h, first, dims)
         mp_h = mp.cpu().numpy().astype(np.uint32)
-        bbknn = [row[row != 0xFFFFFFFF].tolist() for row in mp_h]
+        bbknn = mp_h  # the (npb, B * knn) matrix of per_batch_sc_neighbors, as SparseIoVec._refine_and_collect passes it
         torch.cuda.synchronize()
         t0 = time.perf_counter()
         lv, ks, moves = lg.refine_assignments(ctx, gs, bbknn, init, offs, lg.RefineParams())
