@@ -57,14 +57,21 @@ __global__ void __launch_bounds__(COLLAPSE_THREADS, 1) k_collapse_sorted(
     const uint64_t* __restrict__ indptr, const uint32_t* __restrict__ indices, const float* __restrict__ values, uint64_t nnz_total,
     const uint32_t* __restrict__ sorted_label, const uint32_t* __restrict__ sorted_cell, uint64_t ncells,
     const float* __restrict__ mult, uint32_t S, uint64_t D, uint32_t g0, uint32_t W, float* __restrict__ sum_ds,
-    float* __restrict__ size_s, unsigned long long* __restrict__ next_chunk) {
+    float* __restrict__ size_s, unsigned long long* __restrict__ next_chunk, const uint32_t* __restrict__ cell_range) {
     using A = Acc<INT>;
+    // cell_range (or NULL): this launch takes the sorted positions [cell_range[0], cell_range[1]) only — the sharded path
+    // collapses the groups in two halves so that the first half's sums can be all-reduced while the second is summed
+    uint64_t pos0 = 0;
+    if (cell_range) {
+        pos0 = cell_range[0];
+        ncells = cell_range[1];
+    }
     extern __shared__ __align__(16) unsigned char smem_raw[];
     typename A::T* acc = reinterpret_cast<typename A::T*>(smem_raw);  // W accumulators
     __shared__ unsigned long long s_chunk;
     __shared__ uint32_t s_label[COLLAPSE_CHUNK];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = COLLAPSE_THREADS / 32;
-    const uint64_t nchunks = (ncells + COLLAPSE_CHUNK - 1) / COLLAPSE_CHUNK;
+    const uint64_t nchunks = (ncells - pos0 + COLLAPSE_CHUNK - 1) / COLLAPSE_CHUNK;
     for (uint32_t g = threadIdx.x; g < W; g += COLLAPSE_THREADS) acc[g] = 0;
     while (true) {
         __syncthreads();
@@ -72,7 +79,7 @@ __global__ void __launch_bounds__(COLLAPSE_THREADS, 1) k_collapse_sorted(
         __syncthreads();
         const uint64_t chunk = s_chunk;
         if (chunk >= nchunks) break;
-        const uint64_t p0 = chunk * COLLAPSE_CHUNK;
+        const uint64_t p0 = pos0 + chunk * COLLAPSE_CHUNK;
         const int np = (int)((p0 + COLLAPSE_CHUNK) < ncells ? COLLAPSE_CHUNK : (ncells - p0));
         if ((int)threadIdx.x < np) s_label[threadIdx.x] = sorted_label[p0 + threadIdx.x];
         __syncthreads();
@@ -210,13 +217,31 @@ __global__ void k_count_bs(const uint32_t* __restrict__ group, const uint32_t* _
     if (s < S && b < B) atomicAdd(&n_bs[(size_t)s * B + b], mult ? mult[j] : 1.0f);
 }
 
+// first sorted position whose label is >= split: out = {0, c, c, n} (the two position ranges of the split collapse)
+__global__ void k_split_point(const uint32_t* __restrict__ sorted_label, uint32_t n, uint32_t split, uint32_t* __restrict__ out) {
+    uint32_t lo = 0, hi = n;
+    while (lo < hi) {
+        const uint32_t mid = lo + (hi - lo) / 2;
+        if (sorted_label[mid] < split) lo = mid + 1;
+        else hi = mid;
+    }
+    out[0] = 0;
+    out[1] = lo;
+    out[2] = lo;
+    out[3] = n;
+}
+
 // generic "sum columns by label" driver shared by the basic (label = group) and batch (label = batch) stats
 static int collapse_by_label(lg_ctx* ctx, LgStage& st, const lg_csc* m, const uint32_t* d_label, const float* d_mult,
-                             uint32_t S, float* d_sum, float* d_size) {
+                             uint32_t S, float* d_sum, float* d_size, uint32_t S_half = 0,
+                             const std::function<int()>* after_first_half = nullptr) {
     const uint64_t N = m->ncols, D = m->nrows;
     LG_CUDA(ctx, cudaMemsetAsync(d_sum, 0, sizeof(float) * (size_t)D * S, ctx->stream));
     if (d_size) LG_CUDA(ctx, cudaMemsetAsync(d_size, 0, sizeof(float) * S, ctx->stream));
-    if (N == 0 || D == 0 || S == 0) return LG_OK;
+    if (N == 0 || D == 0 || S == 0) {  // an empty shard still takes its part in the caller's exchange
+        if (after_first_half) LG_TRY((*after_first_half)());
+        return LG_OK;
+    }
     LG_REQUIRE(ctx, N < 0xFFFFFFFFull, "collapse: more than 2^32-1 cells in one block; shard the cells");
     // stable sort of cells by label (cells stay ascending inside a label)
     uint32_t *d_cell_in, *d_cell_out, *d_lab_out;
@@ -250,24 +275,44 @@ static int collapse_by_label(lg_ctx* ctx, LgStage& st, const lg_csc* m, const ui
     LG_TRY(st.scratch(1, &d_next));
     const size_t smem_cap = ctx->smem_optin - 4096;
     const uint32_t Wmax = (uint32_t)(smem_cap / sizeof(float));
+    // two launches over the sorted positions (labels below S_half, then the rest) when a caller wants the first half early and
+    // the genes fit one pass; the position ranges stay on the device
+    const bool split = after_first_half && S_half > 0 && S_half < S && D <= Wmax;
+    uint32_t* d_range = nullptr;
+    if (split) {
+        LG_TRY(st.scratch(4, &d_range));
+        LG_LAUNCH(ctx, k_split_point, 1, 1, 0, d_lab_out, (uint32_t)N, S_half, d_range);
+    }
     for (uint64_t g0 = 0; g0 < D; g0 += Wmax) {
         const uint32_t W = (uint32_t)((D - g0) < Wmax ? (D - g0) : Wmax);
         const size_t smem = (size_t)W * sizeof(float);
-        LG_CUDA(ctx, cudaMemsetAsync(d_next, 0, sizeof(unsigned long long), ctx->stream));
         const bool vec = (((uintptr_t)m->indices | (uintptr_t)m->values) & 15) == 0;
+        for (int half = 0; half < (split ? 2 : 1); ++half) {
+            LG_CUDA(ctx, cudaMemsetAsync(d_next, 0, sizeof(unsigned long long), ctx->stream));
+            const uint32_t* rng = split ? d_range + 2 * half : nullptr;
 #define LG_COLLAPSE_LAUNCH(I, V)                                                                                                   \
     do {                                                                                                                           \
         LG_CUDA(ctx, cudaFuncSetAttribute(k_collapse_sorted<I, V>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));       \
         LG_LAUNCH(ctx, (k_collapse_sorted<I, V>), ctx->num_sms, COLLAPSE_THREADS, smem, m->indptr, m->indices, m->values, m->nnz, \
-                  d_lab_out, d_cell_out, N, d_mult, S, D, (uint32_t)g0, W, d_sum, d_size, d_next);                                  \
+                  d_lab_out, d_cell_out, N, d_mult, S, D, (uint32_t)g0, W, d_sum, d_size, d_next, rng);                             \
     } while (0)
-        if (use_int && vec) LG_COLLAPSE_LAUNCH(true, true);
-        else if (use_int) LG_COLLAPSE_LAUNCH(true, false);
-        else if (vec) LG_COLLAPSE_LAUNCH(false, true);
-        else LG_COLLAPSE_LAUNCH(false, false);
+            if (use_int && vec) LG_COLLAPSE_LAUNCH(true, true);
+            else if (use_int) LG_COLLAPSE_LAUNCH(true, false);
+            else if (vec) LG_COLLAPSE_LAUNCH(false, true);
+            else LG_COLLAPSE_LAUNCH(false, false);
 #undef LG_COLLAPSE_LAUNCH
+            if (split && half == 0) LG_TRY((*after_first_half)());
+        }
     }
+    if (after_first_half && !split) LG_TRY((*after_first_half)());  // nothing was split: the callback still runs once, before the caller's second step
     return LG_OK;
+}
+
+int lg_collapse_basic_split(lg_ctx* ctx, const lg_csc* m, const uint32_t* d_group, uint32_t S, uint32_t S_half, float* d_sum_ds,
+                            float* d_size_s, const std::function<int()>& after_first_half) {
+    LgStage st(ctx);
+    LG_TRY(collapse_by_label(ctx, st, m, d_group, nullptr, S, d_sum_ds, d_size_s, S_half, &after_first_half));
+    return st.finish();
 }
 
 extern "C" int lg_collapse_basic(lg_ctx* ctx, const lg_csc* m, const uint32_t* group_of_cell, const float* mult, uint32_t S,

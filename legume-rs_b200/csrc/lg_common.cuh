@@ -6,6 +6,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <functional>
 #include <string>
 #include <vector>
 
@@ -33,6 +34,10 @@ struct lg_ctx {
     void* comm = nullptr;
     int comm_rank = 0, comm_world = 1;
     std::vector<uint32_t> lut_keep;  // host copy of the last group table (outlives its asynchronous upload)
+    // second stream + two events of the sharded path: the all-reduce of the first half of the group sums runs there while the
+    // second half is still being collapsed (lg_comm.cu); created on first use
+    cudaStream_t side_stream = nullptr;
+    cudaEvent_t side_ev[2] = {nullptr, nullptr};
     // Large scratch (>= LG_CACHE_MIN bytes) is kept by the context and handed out again, smallest fitting block first:
     // every use is ordered on ctx->stream, so a block may be reused by the next call while the previous one's kernels
     // are still queued.  The driver's stream-ordered pool does this too, but with the path's mix of one 4 GB block and
@@ -263,6 +268,11 @@ __device__ __forceinline__ void lg_block_sums_stage2(const double* stage, int co
     __syncthreads();
 }
 
+// lg_collapse_basic on device pointers in two launches, groups below `S_half` first; `after_first_half` runs between them (the
+// sums of those groups are complete and queued on ctx->stream when it is called).  Internal: the sharded path overlaps the
+// all-reduce of the first half with the collapse of the second (lg_comm.cu).
+int lg_collapse_basic_split(lg_ctx* ctx, const lg_csc* m, const uint32_t* d_group, uint32_t S, uint32_t S_half, float* d_sum_ds,
+                            float* d_size_s, const std::function<int()>& after_first_half);
 // LG_OK when rows are strictly ascending and in range inside every column (checked once per block, cached)
 int lg_csc_require_canonical(lg_ctx* ctx, const lg_csc* m, const char* who);
 // rejects labels outside [0, bound) with LG_ERR_INVALID (one small kernel + a flag read-back)

@@ -64,6 +64,9 @@ extern "C" int lg_ctx_destroy(lg_ctx* c) {
     if (c->log1p_tab) cudaFree(c->log1p_tab);
     for (auto& b : c->cache) cudaFree(b.p);
     for (auto e : c->ring_ev) cudaEventDestroy(e);
+    for (auto e : c->side_ev)
+        if (e) cudaEventDestroy(e);
+    if (c->side_stream) cudaStreamDestroy(c->side_stream);
     delete c;
     return LG_OK;
 }
