@@ -1353,15 +1353,14 @@ class SparseIoVec:
         cell_to_pb = [np.asarray(p2g, np.uint32)[c2p] for p2g in p2g_levels]
         return dict(levels=outs, cell_to_pb_per_level=cell_to_pb, stats=stats)
 
-    def _refine_and_collect(self, proj_kn, nb, level_dims, codes_h, group, ng, params):
-        """refine_and_collect_single_layer (refine.rs:264-500).  refine_or_identity(num_batches >= 2, ..): with one batch
-        the refined assignment is the compacted hash partition of every level"""
-        layout, gene_sums = self._build_pb_samples(proj_kn, group, ng, nb)
+    def _refined_partition(self, proj_kn, nb, level_dims, codes_h, layout, gene_sums, params):
+        """every level's pb-sample -> group and group count: refine_or_identity(num_batches >= 2, ..) (refine.rs:126-147,
+        313-345) — with one batch the compacted hash partition, with more the BBKNN candidates + DC-Poisson sweeps"""
         c2p = np.asarray(layout.cell_to_pbsamp).astype(np.int64)
         first = np.full(layout.num_pb, len(c2p), np.int64)
         np.minimum.at(first, c2p, np.arange(len(c2p)))  # a pb-sample's first cell (pb_samples.rs:472-481)
         p2g = initial_per_level_from_hash(codes_h, first, level_dims)
-        if nb >= 2:  # refine_or_identity(num_batches >= 2, ..): BBKNN candidates + DC-Poisson sweeps (refine.rs:329-345)
+        if nb >= 2:
             matched, _ = per_batch_sc_neighbors(self.ctx, layout, proj_kn, self.col_to_batch, nb, params.knn_pb_samples)
             bbknn = np.asarray(matched.cpu() if _is_torch(matched) else matched)  # build_bbknn_neighbors (refine_multilevel.rs:60-83)
             offsets = build_reproject_offsets(codes_h, first, level_dims)
@@ -1369,8 +1368,36 @@ class SparseIoVec:
             self.refine_moves = moves
         else:
             p2g, k = zip(*(compact_labels(l) for l in p2g))
-        return self._collect_refined_levels(proj_kn, nb, layout, gene_sums, list(p2g), list(k), params,
-                                            params.output_calibration)
+        return list(p2g), list(k)
+
+    def _refine_and_collect(self, proj_kn, nb, level_dims, codes_h, group, ng, params):
+        """refine_and_collect_single_layer (refine.rs:264-500)"""
+        layout, gene_sums = self._build_pb_samples(proj_kn, group, ng, nb)
+        p2g, k = self._refined_partition(proj_kn, nb, level_dims, codes_h, layout, gene_sums, params)
+        return self._collect_refined_levels(proj_kn, nb, layout, gene_sums, p2g, k, params, params.output_calibration)
+
+    def _legacy_levels(self, proj_kn, nb, level_dims, codes_h, group, ng, params):
+        """the un-refined descent (mod.rs:943-1046): finest statistics from the hash groups, coarser levels by masked codes"""
+        ctx = self.ctx
+        fine_stat = CollapsedStat(self.num_rows(), ng, nb)
+        self.collect_basic_stat(fine_stat)
+        if nb >= 2:
+            self.collect_batch_stat(fine_stat)
+            layout, gene_sums = self._build_pb_samples(proj_kn, group, ng, nb)
+            matched = per_batch_sc_neighbors(ctx, layout, proj_kn, self.col_to_batch, nb, params.knn_pb_samples)
+            collect_matched_stat_coarse(ctx, layout, gene_sums, layout.pb_sample_to_group, matched, fine_stat)
+        if params.observe_panels:
+            self.attach_observability(fine_stat)
+        outs = [optimize(ctx, fine_stat, (1.0, 1.0), params.num_opt_iter, TARGET_ALL)]
+        stats = [fine_stat]
+        prev, prev_group, prev_n = fine_stat, group, ng
+        for dim in level_dims[1:]:
+            f2c, nc = compute_fine_to_coarse_mapping(ctx, codes_h, prev_group, prev_n, dim)
+            coarse = self._merge_level(prev, f2c, nc, nb)
+            outs.append(optimize(ctx, coarse, (1.0, 1.0), max(params.num_opt_iter // 2, 10), TARGET_ALL))
+            stats.append(coarse)
+            prev, prev_group, prev_n = coarse, f2c[prev_group], nc
+        return outs, stats
 
     def collapse_columns_multilevel_with_hierarchy(self, proj_kn, batch_membership, params: MultilevelParams):
         """collapse_data/mod.rs:534-607: the levels plus the per-level cell -> pb map; needs params.refine"""
@@ -1405,25 +1432,7 @@ class SparseIoVec:
         if params.refine is not None:  # mod.rs:914-941
             out = self._refine_and_collect(proj_kn, nb, level_dims, codes_h, group, ng, params)
             return out["levels"], out["stats"]
-        fine_stat = CollapsedStat(self.num_rows(), ng, nb)
-        self.collect_basic_stat(fine_stat)
-        if nb >= 2:
-            self.collect_batch_stat(fine_stat)
-            layout, gene_sums = self._build_pb_samples(proj_kn, group, ng, nb)
-            matched = per_batch_sc_neighbors(ctx, layout, proj_kn, self.col_to_batch, nb, params.knn_pb_samples)
-            collect_matched_stat_coarse(ctx, layout, gene_sums, layout.pb_sample_to_group, matched, fine_stat)
-        if params.observe_panels:
-            self.attach_observability(fine_stat)
-        outs = [optimize(ctx, fine_stat, (1.0, 1.0), params.num_opt_iter, TARGET_ALL)]
-        stats = [fine_stat]
-        prev, prev_group, prev_n = fine_stat, group, ng
-        for dim in level_dims[1:]:
-            f2c, nc = compute_fine_to_coarse_mapping(ctx, codes_h, prev_group, prev_n, dim)
-            coarse = self._merge_level(prev, f2c, nc, nb)
-            outs.append(optimize(ctx, coarse, (1.0, 1.0), max(params.num_opt_iter // 2, 10), TARGET_ALL))
-            stats.append(coarse)
-            prev, prev_group, prev_n = coarse, f2c[prev_group], nc
-        return outs, stats
+        return self._legacy_levels(proj_kn, nb, level_dims, codes_h, group, ng, params)
 
 
 # --------------------------------------------------------------------------------------------------
@@ -1485,6 +1494,43 @@ class SparseIoStack:
         for x in self.stack[1:]:
             x.binary_codes, x.col_to_group, x.group_keys = first.binary_codes, first.col_to_group, first.group_keys
         return out
+
+    def collapse_columns_multilevel_vec(self, proj_kn, batch_membership, params: "MultilevelParams"):
+        """MultilevelCollapsingOps for SparseIoStack (collapse_data/mod.rs:1050-1260, refine.rs:503-716): ONE partition for every
+        modality — the first layer owns the grouping decision (its gene sums drive the refinement) — and per level one
+        CollapsedOut per layer.  Returns (levels x layers of CollapsedOut, levels x layers of CollapsedStat).  Panels are not
+        observed on the stack path (mod.rs:1128) and anchor / bulk batches are refused there (:1116-1120)."""
+        import copy
+        first = self.stack[0]
+        proj_kn, nb, level_dims, codes_h, group, ng = first._multilevel_prologue(proj_kn, batch_membership, params)
+        for x in self.stack[1:]:
+            x.register_batch_membership(batch_membership)
+            if nb >= 2:
+                x.build_hnsw_per_batch(proj_kn, batch_membership)
+            x.col_to_group, x.binary_codes, x.group_keys = first.col_to_group, first.binary_codes, first.group_keys
+        p = copy.copy(params)
+        p.observe_panels = False
+        per_layer = []
+        if params.refine is not None:
+            layout, gs0 = first._build_pb_samples(proj_kn, group, ng, nb)
+            p2g, k = first._refined_partition(proj_kn, nb, level_dims, codes_h, layout, gs0, p)
+            for d, x in enumerate(self.stack):
+                gs = gs0 if d == 0 else x._build_pb_samples(proj_kn, group, ng, nb)[1]
+                out = x._collect_refined_levels(proj_kn, nb, layout, gs, p2g, k, p, p.output_calibration)
+                per_layer.append((out["levels"], out["stats"]))
+        else:
+            for x in self.stack:
+                per_layer.append(x._legacy_levels(proj_kn, nb, level_dims, codes_h, group, ng, p))
+        nlev = len(per_layer[0][0])
+        return ([[per_layer[d][0][l] for d in range(len(self.stack))] for l in range(nlev)],
+                [[per_layer[d][1][l] for d in range(len(self.stack))] for l in range(nlev)])
+
+    def collapse_columns_multilevel(self, proj_kn, batch_membership, params: "MultilevelParams"):
+        """the finest level only (mod.rs:1053-1068)"""
+        outs, _ = self.collapse_columns_multilevel_vec(proj_kn, batch_membership, params)
+        if not outs:
+            raise LegumeError(1, "no levels processed")
+        return outs[0]
 
     def project_columns_weighted(self, target_dim, block_size, batch_membership, row_weights, bases=None,
                                  seed=DEFAULT_PROJECTION_SEED):

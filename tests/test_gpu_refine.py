@@ -242,3 +242,45 @@ def test_vectorised_candidate_sets_equal_the_list_form(lg):
             got = [flat[ptr[e]:ptr[e + 1]].tolist() for e in range(n)]
             assert got == want
             assert got == orc.candidate_sets(orc.sibling_sets(refined[level], refined[1] if level == 0 else None, kk_), lists, refined[level])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("refine", [True, False])
+def test_stack_multilevel_collapse_first_layer_owns_the_partition(lg, ctx, refine):
+    """MultilevelCollapsingOps for SparseIoStack (collapse_data/mod.rs:1050-1260, refine.rs:503-716): the first modality's gene
+    sums drive the refinement, every modality is then collapsed on that one partition"""
+    N, B, K = 3000, 3, 20
+    ip0, ix0, v0, proj, batch, _ = make_case(41, 350, N, B, 4, K, clustered=True)
+    ip1, ix1, v1, _, _, _ = make_case(42, 220, N, B, 4, K)
+    layers = [(ip0, ix0, v0, 350), (ip1, ix1, v1, 220)]
+    stack = lg.SparseIoStack([lg.SparseIoVec.from_csc(ctx, ip, ix, v, D) for ip, ix, v, D in layers])
+    params = lg.MultilevelParams(K, knn_pb_samples=4, num_levels=2, sort_dim=8, num_opt_iter=12, refine="default" if refine else None)
+    outs, stats = stack.collapse_columns_multilevel_vec(proj, batch, params)
+    dims = orc.level_sort_dims(8, 2)
+    assert len(outs) == len(dims) and all(len(lv) == 2 for lv in outs)
+    codes = orc.binary_codes(proj, dims[0])
+    grp, S = orc.assign_groups(codes)
+    lay = orc.pb_layout(proj, grp, S, batch, B)
+    if refine:
+        cells = orc.pb_sample_to_cells(lay["cell_to_pb"], lay["num_pb"])
+        first = np.array([c[0] for c in cells])
+        init = orc.initial_per_level_from_hash(codes, cells, dims)
+        gs0, _ = orc.collapse_basic(ip0, ix0, v0, 350, lay["cell_to_pb"], lay["num_pb"])
+        mp, _ = orc.pb_match(proj, batch, B, lay, 4)
+        bbknn = [row[row != 0xFFFFFFFF].tolist() for row in mp]
+        p2g, k, _ = orc.refine_assignments(gs0, bbknn, init, lg.build_reproject_offsets(codes, first, dims), seed=42)
+        for d, (ip, ix, v, D) in enumerate(layers):
+            want, fine = _oracle_refined_levels(ip, ix, v, D, proj, batch, B, codes, dims, p2g, k, lay, 4, 12)
+            assert np.array_equal(np.asarray(stack.stack[d].col_to_group), fine)
+            for level in range(2):
+                st, w = stats[level][d], want[level]
+                assert np.array_equal(st.observed_sum_ds, w["obs"]) and np.array_equal(st.size_s, w["size"])
+                assert close(st.imputed_sum_ds, w["imp"], TOL) and close(st.residual_sum_ds, w["res"], TOL)
+                assert close(outs[level][d].mu_adjusted["mean"], w["fit"]["mu_adjusted"], 1e-4)
+    else:
+        for d, (ip, ix, v, D) in enumerate(layers):
+            assert np.array_equal(np.asarray(stack.stack[d].col_to_group), grp)
+            obs, size = orc.collapse_basic(ip, ix, v, D, grp, S)
+            assert np.array_equal(stats[0][d].observed_sum_ds, obs) and np.array_equal(stats[0][d].size_s, size)
+    finest = stack.collapse_columns_multilevel(proj, batch, params)
+    assert len(finest) == 2
