@@ -32,22 +32,64 @@ __global__ void k_all_integral(const float* __restrict__ v, uint64_t n, int* __r
     if (__any_sync(0xffffffffu, bad) && (threadIdx.x & 31) == 0) atomicOr(not_integral, 1);
 }
 
-// Accumulator element: u32 with native shared-memory ATOMS.ADD when the counts are integers
-// (exact, and a third of the shared-memory traffic of the f32 compare-and-swap loop), f32 otherwise.
+// Accumulator element.  Integer counts with unit multiplicity: u32 with native shared-memory ATOMS.ADD — exact, so the result
+// does not depend on the order in which warps and CTAs arrive.  Anything else (fractional multiplicities, non-integer values):
+// 64-bit FIXED POINT, `round(v * w * 2^e)` with e chosen per call so that no sum can overflow — integer adds again, so these
+// sums are also bit-identical run to run and for any sharding (section 8b "Determinism"); f32 atomics in arrival order were not.
+// They leave through a u64 twin of the output that one pass converts to f32 at the end.
 template <bool INT>
 struct Acc;
 template <>
 struct Acc<true> {
     using T = unsigned int;
-    static __device__ __forceinline__ void add(T* a, float v, float) { atomicAdd(a, (unsigned int)v); }
-    static __device__ __forceinline__ float get(T v) { return (float)v; }
+    static __device__ __forceinline__ void add(T* a, float v, float, float) { atomicAdd(a, (unsigned int)v); }
 };
 template <>
 struct Acc<false> {
-    using T = float;
-    static __device__ __forceinline__ void add(T* a, float v, float w) { atomicAdd(a, v * w); }
-    static __device__ __forceinline__ float get(T v) { return v; }
+    using T = unsigned long long;
+    static __device__ __forceinline__ void add(T* a, float v, float w, float scale) {
+        atomicAdd(a, (unsigned long long)__float2ll_rn(__fmul_rn(__fmul_rn(v, w), scale)));  // two's complement: negatives wrap and add up
+    }
 };
+
+// largest |x| of an array as float bits (non-negative floats order like their bit patterns)
+__global__ void k_max_abs_bits(const float* __restrict__ v, uint64_t n, unsigned int* __restrict__ out) {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    float m = 0.0f;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const float x = fabsf(__ldg(v + i));
+        if (x > m && x <= 3.0e38f) m = x;  // non-finite values do not size the scale
+    }
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, off));
+    if ((threadIdx.x & 31) == 0 && m > 0.0f) atomicMax(out, __float_as_uint(m));
+}
+
+// fixed-point twin -> f32 sums
+__global__ void k_fixed_to_f32(const unsigned long long* __restrict__ src, uint64_t n, double inv_scale, float* __restrict__ dst) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) dst[i] = (float)((double)(long long)src[i] * inv_scale);
+}
+
+// size_s[s] += w over the cells of group s in ascending cell order: the reference's own fold (stats.rs:126-131), one thread per
+// group over its segment of the sorted cells (used when multiplicities are registered; with unit weights the in-kernel adds are exact)
+__global__ void k_size_by_group(const uint32_t* __restrict__ sorted_label, const uint32_t* __restrict__ sorted_cell, uint32_t n,
+                                const float* __restrict__ mult, uint32_t S, float* __restrict__ size_s) {
+    const uint32_t sgrp = blockIdx.x * blockDim.x + threadIdx.x;
+    if (sgrp >= S) return;
+    auto lower = [&](uint32_t key) {
+        uint32_t lo = 0, hi = n;
+        while (lo < hi) {
+            const uint32_t mid = lo + (hi - lo) / 2;
+            if (sorted_label[mid] < key) lo = mid + 1;
+            else hi = mid;
+        }
+        return lo;
+    };
+    float acc = 0.0f;
+    for (uint32_t i = lower(sgrp), e = lower(sgrp + 1); i < e; ++i) acc = __fadd_rn(acc, mult[sorted_cell[i]]);
+    size_s[sgrp] = acc;
+}
 
 // window [g0, g0 + W) of the gene axis lives in shared memory
 // VEC: index / value arrays are 16-byte aligned, so a lane reads 4 consecutive nnz per 128-bit load (entries of the
@@ -57,7 +99,8 @@ __global__ void __launch_bounds__(COLLAPSE_THREADS, 1) k_collapse_sorted(
     const uint64_t* __restrict__ indptr, const uint32_t* __restrict__ indices, const float* __restrict__ values, uint64_t nnz_total,
     const uint32_t* __restrict__ sorted_label, const uint32_t* __restrict__ sorted_cell, uint64_t ncells,
     const float* __restrict__ mult, uint32_t S, uint64_t D, uint32_t g0, uint32_t W, float* __restrict__ sum_ds,
-    float* __restrict__ size_s, unsigned long long* __restrict__ next_chunk, const uint32_t* __restrict__ cell_range) {
+    float* __restrict__ size_s, unsigned long long* __restrict__ next_chunk, const uint32_t* __restrict__ cell_range,
+    unsigned long long* __restrict__ sum64, float scale) {
     using A = Acc<INT>;
     // cell_range (or NULL): this launch takes the sorted positions [cell_range[0], cell_range[1]) only — the sharded path
     // collapses the groups in two halves so that the first half's sums can be all-reduced while the second is summed
@@ -145,7 +188,7 @@ __global__ void __launch_bounds__(COLLAPSE_THREADS, 1) k_collapse_sorted(
                                 const float ve[4] = {vq[u].x, vq[u].y, vq[u].z, vq[u].w};
 #pragma unroll
                                 for (int e = 0; e < 4; ++e)
-                                    if (cu + e >= lo && cu + e < hi && ge[e] < W) A::add(&acc[ge[e]], ve[e], w);
+                                    if (cu + e >= lo && cu + e < hi && ge[e] < W) A::add(&acc[ge[e]], ve[e], w, scale);
                             }
                         }
                     } else {
@@ -160,7 +203,7 @@ __global__ void __launch_bounds__(COLLAPSE_THREADS, 1) k_collapse_sorted(
                         }
 #pragma unroll
                         for (int u = 0; u < COLLAPSE_UNROLL; ++u)
-                            if (gi[u] < W) A::add(&acc[gi[u]], vv[u], w);
+                            if (gi[u] < W) A::add(&acc[gi[u]], vv[u], w, scale);
                     }
                     for (; t + 96 < hi; t += 128) {  // lower tiers: keep several loads in flight for the ragged rest
                         uint32_t gi[4];
@@ -172,17 +215,17 @@ __global__ void __launch_bounds__(COLLAPSE_THREADS, 1) k_collapse_sorted(
                         }
 #pragma unroll
                         for (int u = 0; u < 4; ++u)
-                            if (gi[u] < W) A::add(&acc[gi[u]], vv[u], w);
+                            if (gi[u] < W) A::add(&acc[gi[u]], vv[u], w, scale);
                     }
                     for (; t + 32 < hi; t += 64) {
                         const uint32_t ga = __ldg(indices + t) - g0, gb = __ldg(indices + t + 32) - g0;
                         const float va = __ldg(values + t), vb = __ldg(values + t + 32);
-                        if (ga < W) A::add(&acc[ga], va, w);
-                        if (gb < W) A::add(&acc[gb], vb, w);
+                        if (ga < W) A::add(&acc[ga], va, w, scale);
+                        if (gb < W) A::add(&acc[gb], vb, w, scale);
                     }
                     for (; t < hi; t += 32) {
                         const uint32_t gi = __ldg(indices + t) - g0;
-                        if (gi < W) A::add(&acc[gi], __ldg(values + t), w);
+                        if (gi < W) A::add(&acc[gi], __ldg(values + t), w, scale);
                     }
                     }
                     wsum += (mult ? mult[cell] : 1.0f);
@@ -193,11 +236,11 @@ __global__ void __launch_bounds__(COLLAPSE_THREADS, 1) k_collapse_sorted(
                 }
                 if (lane == 0 && g0 == 0 && size_s && wsum != 0.0f) atomicAdd(&size_s[lab], wsum);
                 __syncthreads();
-                float* col = sum_ds + (size_t)lab * D + g0;
                 for (uint32_t g = threadIdx.x; g < W; g += COLLAPSE_THREADS) {
                     const typename A::T v = acc[g];
                     if (v != 0) {
-                        atomicAdd(col + g, A::get(v));
+                        if constexpr (INT) atomicAdd(sum_ds + (size_t)lab * D + g0 + g, (float)v);  // whole numbers: exact in any order
+                        else atomicAdd(sum64 + (size_t)lab * D + g0 + g, v);                          // fixed point: exact in any order
                         acc[g] = 0;
                     }
                 }
@@ -215,6 +258,15 @@ __global__ void k_count_bs(const uint32_t* __restrict__ group, const uint32_t* _
     if (j >= ncols) return;
     const uint32_t s = group[j], b = batch[j];
     if (s < S && b < B) atomicAdd(&n_bs[(size_t)s * B + b], mult ? mult[j] : 1.0f);
+}
+// the same with registered multiplicities: fixed point (integer adds: any arrival order gives the same bits), converted after
+__global__ void k_count_bs_fixed(const uint32_t* __restrict__ group, const uint32_t* __restrict__ batch,
+                                 const float* __restrict__ mult, uint64_t ncols, uint32_t S, uint32_t B, float scale,
+                                 unsigned long long* __restrict__ n64) {
+    const uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= ncols) return;
+    const uint32_t s = group[j], b = batch[j];
+    if (s < S && b < B) atomicAdd(&n64[(size_t)s * B + b], (unsigned long long)__float2ll_rn(__fmul_rn(mult[j], scale)));
 }
 
 // first sorted position whose label is >= split: out = {0, c, c, n} (the two position ranges of the split collapse)
@@ -274,10 +326,44 @@ static int collapse_by_label(lg_ctx* ctx, LgStage& st, const lg_csc* m, const ui
     unsigned long long* d_next;
     LG_TRY(st.scratch(1, &d_next));
     const size_t smem_cap = ctx->smem_optin - 4096;
-    const uint32_t Wmax = (uint32_t)(smem_cap / sizeof(float));
+    // the fixed-point path: scale 2^e with max|v| * max|w| * N * 2^e < 2^62 (a (gene, group) cell gets at most one entry per cell)
+    unsigned long long* d_sum64 = nullptr;
+    float scale = 1.0f;
+    double inv_scale = 1.0;
+    float* d_size_kernel = d_size;
+    if (!use_int) {
+        unsigned int* d_mx;
+        LG_TRY(st.scratch(2, &d_mx));
+        LG_CUDA(ctx, cudaMemsetAsync(d_mx, 0, 2 * sizeof(unsigned int), ctx->stream));
+        if (m->nnz) LG_LAUNCH(ctx, k_max_abs_bits, ctx->num_sms * 8, 256, 0, m->values, m->nnz, d_mx);
+        if (d_mult) LG_LAUNCH(ctx, k_max_abs_bits, ctx->num_sms * 2, 256, 0, d_mult, N, d_mx + 1);
+        unsigned int* h_mx = static_cast<unsigned int*>(ctx->pinned);
+        LG_CUDA(ctx, cudaMemcpyAsync(h_mx, d_mx, 2 * sizeof(unsigned int), cudaMemcpyDeviceToHost, ctx->stream));
+        LG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        float mv, mw = 1.0f;
+        memcpy(&mv, &h_mx[0], 4);
+        if (d_mult) memcpy(&mw, &h_mx[1], 4);
+        const double bound = (double)mv * (double)mw * (double)N;
+        int e = 24;
+        if (bound > 0.0) {
+            int be = 0;
+            frexp(bound, &be);  // bound < 2^be
+            e = 62 - be;
+        }
+        e = e > 100 ? 100 : (e < -100 ? -100 : e);
+        scale = ldexpf(1.0f, e);
+        inv_scale = ldexp(1.0, -e);
+        LG_TRY(st.scratch((size_t)D * S, &d_sum64));
+        LG_CUDA(ctx, cudaMemsetAsync(d_sum64, 0, sizeof(unsigned long long) * (size_t)D * S, ctx->stream));
+        if (d_mult && d_size) {  // the reference's serial fold over the group's cells instead of f32 atomics in arrival order
+            LG_LAUNCH(ctx, k_size_by_group, (S + 127) / 128, 128, 0, d_lab_out, d_cell_out, (uint32_t)N, d_mult, S, d_size);
+            d_size_kernel = nullptr;
+        }
+    }
+    const uint32_t Wmax = (uint32_t)(smem_cap / (use_int ? sizeof(unsigned int) : sizeof(unsigned long long)));
     // two launches over the sorted positions (labels below S_half, then the rest) when a caller wants the first half early and
     // the genes fit one pass; the position ranges stay on the device
-    const bool split = after_first_half && S_half > 0 && S_half < S && D <= Wmax;
+    const bool split = after_first_half && S_half > 0 && S_half < S && D <= Wmax && use_int;
     uint32_t* d_range = nullptr;
     if (split) {
         LG_TRY(st.scratch(4, &d_range));
@@ -285,7 +371,7 @@ static int collapse_by_label(lg_ctx* ctx, LgStage& st, const lg_csc* m, const ui
     }
     for (uint64_t g0 = 0; g0 < D; g0 += Wmax) {
         const uint32_t W = (uint32_t)((D - g0) < Wmax ? (D - g0) : Wmax);
-        const size_t smem = (size_t)W * sizeof(float);
+        const size_t smem = (size_t)W * (use_int ? sizeof(unsigned int) : sizeof(unsigned long long));
         const bool vec = (((uintptr_t)m->indices | (uintptr_t)m->values) & 15) == 0;
         for (int half = 0; half < (split ? 2 : 1); ++half) {
             LG_CUDA(ctx, cudaMemsetAsync(d_next, 0, sizeof(unsigned long long), ctx->stream));
@@ -294,7 +380,7 @@ static int collapse_by_label(lg_ctx* ctx, LgStage& st, const lg_csc* m, const ui
     do {                                                                                                                           \
         LG_CUDA(ctx, cudaFuncSetAttribute(k_collapse_sorted<I, V>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));       \
         LG_LAUNCH(ctx, (k_collapse_sorted<I, V>), ctx->num_sms, COLLAPSE_THREADS, smem, m->indptr, m->indices, m->values, m->nnz, \
-                  d_lab_out, d_cell_out, N, d_mult, S, D, (uint32_t)g0, W, d_sum, d_size, d_next, rng);                             \
+                  d_lab_out, d_cell_out, N, d_mult, S, D, (uint32_t)g0, W, d_sum, d_size_kernel, d_next, rng, d_sum64, scale);      \
     } while (0)
             if (use_int && vec) LG_COLLAPSE_LAUNCH(true, true);
             else if (use_int) LG_COLLAPSE_LAUNCH(true, false);
@@ -303,6 +389,10 @@ static int collapse_by_label(lg_ctx* ctx, LgStage& st, const lg_csc* m, const ui
 #undef LG_COLLAPSE_LAUNCH
             if (split && half == 0) LG_TRY((*after_first_half)());
         }
+    }
+    if (d_sum64) {
+        const uint64_t total = D * (uint64_t)S;
+        LG_LAUNCH(ctx, k_fixed_to_f32, (unsigned)((total + 255) / 256), 256, 0, d_sum64, total, inv_scale, d_sum);
     }
     if (after_first_half && !split) LG_TRY((*after_first_half)());  // nothing was split: the callback still runs once, before the caller's second step
     return LG_OK;
@@ -348,8 +438,31 @@ extern "C" int lg_collapse_batch(lg_ctx* ctx, const lg_csc* m, const uint32_t* g
     LG_TRY(st.out(out_n_bs, (size_t)B * S, &d_nbs));
     LG_TRY(collapse_by_label(ctx, st, m, d_batch, d_mult, B, d_sum, nullptr));
     LG_CUDA(ctx, cudaMemsetAsync(d_nbs, 0, sizeof(float) * (size_t)B * S, ctx->stream));
-    if (m->ncols)
+    if (m->ncols && !d_mult) {
         LG_LAUNCH(ctx, k_count_bs, (unsigned)((m->ncols + 255) / 256), 256, 0, d_group, d_batch, d_mult, m->ncols, S, B, d_nbs);
+    } else if (m->ncols) {
+        unsigned int* d_mx;
+        unsigned long long* d_n64;
+        LG_TRY(st.scratch(1, &d_mx));
+        LG_TRY(st.scratch((size_t)B * S, &d_n64));
+        LG_CUDA(ctx, cudaMemsetAsync(d_mx, 0, sizeof(unsigned int), ctx->stream));
+        LG_CUDA(ctx, cudaMemsetAsync(d_n64, 0, sizeof(unsigned long long) * (size_t)B * S, ctx->stream));
+        LG_LAUNCH(ctx, k_max_abs_bits, ctx->num_sms * 2, 256, 0, d_mult, m->ncols, d_mx);
+        unsigned int* h_mx = static_cast<unsigned int*>(ctx->pinned);
+        LG_CUDA(ctx, cudaMemcpyAsync(h_mx, d_mx, sizeof(unsigned int), cudaMemcpyDeviceToHost, ctx->stream));
+        LG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        float mw;
+        memcpy(&mw, h_mx, 4);
+        int e = 24, be = 0;
+        if (mw > 0.0f) {
+            frexp((double)mw * (double)m->ncols, &be);
+            e = 62 - be;
+        }
+        e = e > 100 ? 100 : (e < -100 ? -100 : e);
+        LG_LAUNCH(ctx, k_count_bs_fixed, (unsigned)((m->ncols + 255) / 256), 256, 0, d_group, d_batch, d_mult, m->ncols, S, B,
+                  ldexpf(1.0f, e), d_n64);
+        LG_LAUNCH(ctx, k_fixed_to_f32, (unsigned)(((size_t)B * S + 255) / 256), 256, 0, d_n64, (uint64_t)B * S, ldexp(1.0, -e), d_nbs);
+    }
     return st.finish();
 }
 

@@ -615,6 +615,36 @@ def test_collapse_batch_and_multiplicity(lg, ctx):
         data.register_column_multiplicity(np.zeros(N, np.float32))
 
 
+@pytest.mark.parametrize("D,N,S", [(800, 3000, 20), (70_000, 1500, 7)])
+def test_fractional_collapse_is_deterministic(lg, ctx, D, N, S):
+    """SURVEY section 8b "Determinism": with fractional multiplicities or non-integer values the sums go through 64-bit fixed
+    point (integer adds, any order), so they are bit-identical run to run, the sizes are the reference's own serial fold, and the
+    sums sit within 1e-5 of the reference's f32 folds; D = 70 000 exceeds one shared-memory window of the 64-bit accumulators"""
+    rng = np.random.default_rng(31)
+    ip, ix, v = random_csc(rng, D, N, 0.05 if D < 10_000 else 0.004)
+    grp = rng.integers(0, S, N).astype(np.uint32)
+    w = rng.uniform(1e-4, 3.0, N).astype(np.float32)
+    for values, mult in ((v, w), ((v * np.float32(0.37)).astype(np.float32), None), (-v * np.float32(1.5), w)):
+        data = lg.SparseIoVec.from_csc(ctx, ip, ix, values, D)
+        data.col_to_group = grp
+        if mult is not None:
+            data.register_column_multiplicity(mult)
+        runs = []
+        for _ in range(3):
+            stat = lg.CollapsedStat(D, S, 0)
+            data.collect_basic_stat(stat)
+            runs.append((np.asarray(stat.observed_sum_ds).copy(), np.asarray(stat.size_s).copy()))
+        assert all(r[0].tobytes() == runs[0][0].tobytes() and r[1].tobytes() == runs[0][1].tobytes() for r in runs[1:])
+        ws, wsz = orc.collapse_basic(ip, ix, values, D, grp, S, mult=mult)
+        assert close(runs[0][0], ws, TOL)
+        assert runs[0][1].tobytes() == wsz.tobytes()  # the serial fold over the group's cells, as the reference makes it
+        # and against exact arithmetic: the fixed-point sums are the better ones
+        cols = np.repeat(np.arange(N), np.diff(ip).astype(np.int64))
+        exact = np.zeros((S, D))
+        np.add.at(exact, (grp[cols], ix.astype(np.int64)), values.astype(np.float64) * (1.0 if mult is None else mult[cols].astype(np.float64)))
+        assert np.max(np.abs(runs[0][0] - exact) / (1 + np.abs(exact))) < 1e-6
+
+
 def test_weighted_columns_identity(lg, ctx):
     """data-beans-alg/tests/weighted_columns.rs:91-121"""
     D, M = 6, 20
