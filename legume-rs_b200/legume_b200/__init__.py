@@ -502,15 +502,16 @@ def compute_fine_to_coarse_mapping(ctx: Context, fine_codes, col_to_group, num_f
 class RefineParams:
     """dc_poisson.rs:71-117 `RefineParams::default()`: the BBKNN + Poisson refinement of the pb-sample partition.  With one batch
     the refinement is the identity (refine.rs:126-147); with two or more it runs the Jacobi sweeps of dc_poisson.rs:778-915
-    through lg_dcp_refine_level.  The sequential Gauss-Seidel sweeps (parallel = false) and the projected profile source
-    are outside the hot path and refused."""
+    through lg_dcp_refine_level.  profile_source = "Projected" scores on the pb-samples' summed projection columns instead of
+    their gene sums (Profiles::from_projection, dc_poisson.rs:164-195; feature weighting is then skipped, refine_multilevel.rs:
+    228-236).  The sequential Gauss-Seidel sweeps (parallel = false) are outside the hot path and refused."""
 
     def __init__(self, num_gibbs=20, num_greedy=10, feature_weighting="FisherInfoNb", seed=42, gibbs_stagnation=0.005,
                  profile_source="Raw", parallel=True):
         if feature_weighting not in ("None", "FisherInfoNb"):
             raise LegumeError(1, "RefineParams.feature_weighting is None or FisherInfoNb (dc_poisson.rs:54-66)")
-        if profile_source != "Raw":
-            raise LegumeError(1, "RefineParams.profile_source = Projected is outside the hot path (dc_poisson.rs:39-49)")
+        if profile_source not in ("Raw", "Projected"):
+            raise LegumeError(1, "RefineParams.profile_source is Raw or Projected (dc_poisson.rs:39-49)")
         if not parallel:
             raise LegumeError(1, "RefineParams.parallel = false (Gauss-Seidel sweeps, dc_poisson.rs:688-731) is outside the hot path")
         self.num_gibbs, self.num_greedy = int(num_gibbs), int(num_greedy)
@@ -680,7 +681,7 @@ def refine_assignments(ctx: Context, gene_sums, bbknn, initial_per_level, reproj
     dev = _is_torch(gs)
     prof = gs.clone() if dev else np.array(gs, np.float32, copy=True)
     w = None
-    if params.feature_weighting == "FisherInfoNb":
+    if params.feature_weighting == "FisherInfoNb" and params.profile_source == "Raw":
         w = ctx.empty((D,), np.float32, dev)
         ctx.check(lib.lg_dcp_fisher_weights(ctx.h, _ptr(prof), D, npb, _ptr(w)))
     sf = ctx.empty((npb,), np.float32, dev)
@@ -1364,11 +1365,27 @@ class SparseIoVec:
             matched, _ = per_batch_sc_neighbors(self.ctx, layout, proj_kn, self.col_to_batch, nb, params.knn_pb_samples)
             bbknn = np.asarray(matched.cpu() if _is_torch(matched) else matched)  # build_bbknn_neighbors (refine_multilevel.rs:60-83)
             offsets = build_reproject_offsets(codes_h, first, level_dims)
-            p2g, k, moves = refine_assignments(self.ctx, gene_sums, bbknn, p2g, offsets, params.refine)
+            profiles = gene_sums
+            if params.refine.profile_source == "Projected":  # Profiles::from_projection: a pb-sample's projection columns summed
+                profiles = self._projection_sums(proj_kn, layout)  # in ascending cell order (serial f32 folds, dc_poisson.rs:171-178)
+            p2g, k, moves = refine_assignments(self.ctx, profiles, bbknn, p2g, offsets, params.refine)
             self.refine_moves = moves
         else:
             p2g, k = zip(*(compact_labels(l) for l in p2g))
         return list(p2g), list(k)
+
+    def _projection_sums(self, proj_kn, layout):
+        """(npb, K): sum of every pb-sample's projection columns, cells ascending (lg_pb_centroid_fold on zeroed running sums)"""
+        import torch
+        n, K = proj_kn.shape
+        dev = torch.device("cuda", self.ctx.device)
+        dproj = proj_kn.to(dev) if _is_torch(proj_kn) else torch.from_numpy(np.ascontiguousarray(proj_kn, np.float32)).to(dev)
+        c2p = torch.from_numpy(np.asarray(layout.cell_to_pbsamp).astype(np.int32)).to(dev)
+        csum = torch.zeros((layout.num_pb, K), dtype=torch.float32, device=dev)
+        ccnt = torch.zeros(layout.num_pb, dtype=torch.float32, device=dev)
+        self.ctx.check(lib.lg_pb_centroid_fold(self.ctx.h, _ptr(dproj), K, n, _ptr(c2p), layout.num_pb, None, _ptr(csum), _ptr(ccnt)))
+        self.ctx.sync()
+        return csum.cpu().numpy()
 
     def _refine_and_collect(self, proj_kn, nb, level_dims, codes_h, group, ng, params):
         """refine_and_collect_single_layer (refine.rs:264-500)"""

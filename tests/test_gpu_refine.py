@@ -133,7 +133,7 @@ def test_refine_level_edge_cases(lg, ctx):
     with pytest.raises(lg.LegumeError):
         lg.RefineParams(parallel=False)
     with pytest.raises(lg.LegumeError):
-        lg.RefineParams(profile_source="Projected")
+        lg.RefineParams(profile_source="Spatial")
 
 
 @pytest.mark.gpu
@@ -284,3 +284,31 @@ def test_stack_multilevel_collapse_first_layer_owns_the_partition(lg, ctx, refin
             assert np.array_equal(stats[0][d].observed_sum_ds, obs) and np.array_equal(stats[0][d].size_s, size)
     finest = stack.collapse_columns_multilevel(proj, batch, params)
     assert len(finest) == 2
+
+
+@pytest.mark.gpu
+def test_multilevel_collapse_with_projected_profiles(lg, ctx):
+    """RefineParams.profile_source = Projected (dc_poisson.rs:39-49, 164-195): the refinement scores on the pb-samples' summed
+    projection columns (entries > 0 only, no feature weighting)"""
+    D, N, B, K = 300, 3000, 3, 16
+    ip, ix, v, proj, batch, _ = make_case(51, D, N, B, 4, K, clustered=True)
+    data = lg.SparseIoVec.from_csc(ctx, ip, ix, v, D)
+    rp = lg.RefineParams(num_gibbs=5, num_greedy=5, profile_source="Projected", seed=7)
+    params = lg.MultilevelParams(K, knn_pb_samples=4, num_levels=2, sort_dim=8, num_opt_iter=12, refine=rp, observe_panels=False)
+    out = data.collapse_columns_multilevel_with_hierarchy(proj, batch, params)
+    dims = orc.level_sort_dims(8, 2)
+    codes = orc.binary_codes(proj, dims[0])
+    grp, S = orc.assign_groups(codes)
+    lay = orc.pb_layout(proj, grp, S, batch, B)
+    cells = orc.pb_sample_to_cells(lay["cell_to_pb"], lay["num_pb"])
+    first = np.array([c[0] for c in cells])
+    prof = np.zeros((lay["num_pb"], K), np.float32)
+    np.add.at(prof, lay["cell_to_pb"].astype(np.int64), proj)  # unbuffered: one f32 add per cell, ascending — the reference's fold
+    mp, _ = orc.pb_match(proj, batch, B, lay, 4)
+    bbknn = [row[row != 0xFFFFFFFF].tolist() for row in mp]
+    init = orc.initial_per_level_from_hash(codes, cells, dims)
+    p2g, k, moves = orc.refine_assignments(prof, bbknn, init, lg.build_reproject_offsets(codes, first, dims), num_gibbs=5, num_greedy=5,
+                                           fisher=False, seed=7)
+    assert data.refine_moves == moves
+    for level in range(2):
+        assert np.array_equal(out["cell_to_pb_per_level"][level], p2g[level][lay["cell_to_pb"].astype(np.int64)])

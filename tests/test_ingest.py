@@ -133,3 +133,28 @@ def test_zarr_block_equals_direct_upload(tmp_path):
     assert got.shape == want.shape
     assert np.max(np.abs(got - want) / (1 + np.maximum(np.abs(got), np.abs(want)))) <= 1e-5
     be.close()
+
+
+def test_zarr_edge_shapes(tmp_path):
+    # a matrix without any stored entry, and ranges that end exactly on chunk boundaries
+    root = str(tmp_path / "empty.zarr")
+    write_store(root, np.zeros(6, np.uint64), np.zeros(0, np.uint64), np.zeros(0, np.float32), 9)
+    be = lg.SparseMtxData.open(root)
+    assert (be.num_rows(), be.num_columns(), be.num_non_zeros()) == (9, 5, 0)
+    ip, ix, v = be.read_columns_host()
+    assert np.array_equal(ip, np.zeros(6, np.uint64)) and len(ix) == 0 and len(v) == 0
+    ip, ix, v = be.read_columns_host(2, 4)
+    assert len(ip) == 3 and len(ix) == 0
+    be.close()
+    D, N = 64, 256
+    ip = np.arange(0, (N + 1) * 4, 4, dtype=np.uint64)           # 4 entries per column: column j ends at entry 4 (j + 1)
+    ix = np.tile(np.array([1, 7, 30, 63], np.uint64), N)
+    v = np.arange(1, 4 * N + 1, dtype=np.float32)
+    root = str(tmp_path / "aligned.zarr")
+    write_store(root, ip, ix, v, D, chunk=64)                     # 16 columns of entries per chunk, 64 indptr entries per chunk
+    be = lg.SparseMtxData.open(root)
+    for lo, hi in [(0, 16), (16, 32), (15, 17), (63, 64), (64, 128), (240, 256)]:
+        rip, rix, rv = be.read_columns_host(lo, hi)
+        assert np.array_equal(rip, ip[lo:hi + 1] - ip[lo])
+        assert np.array_equal(rix, ix[4 * lo:4 * hi]) and np.array_equal(rv, v[4 * lo:4 * hi])
+    be.close()
