@@ -385,6 +385,25 @@ def main():
                                                              out["size_s"].clone().data_ptr()))
         stages["collapse_kernel_only_ms"] = timed(local_only, reps)
         stages["collectives"] = "NCCL all-reduce(sum) of the D x S sums; all-gather of f64 block partials (K1 batch sums, K3 Gram, K3 means)"
+    # the six stages INSIDE the one-call path (lg_ctx_time_stages: events around each stage of lg_hotpath_run_sharded, outside
+    # the timed region): there K5 sums K1's 1-bit pattern instead of streaming the CSC arrays again, which the stand-alone
+    # lg_collapse_basic above cannot do
+    if not staged:
+        import ctypes as _C
+        lib.lg_ctx_time_stages(ctx.h, 1)
+        rows = []
+        pc0 = lib.lg_ctx_pattern_collapse_count(ctx.h)
+        for _ in range(3):
+            step()
+            buf = (_C.c_float * 6)()
+            if lib.lg_hotpath_last_stage_ms(ctx.h, buf) == 0:
+                rows.append([float(x) for x in buf])
+        lib.lg_ctx_time_stages(ctx.h, 0)
+        if rows:
+            med = np.median(np.asarray(rows), axis=0)
+            names = ("project", "codes", "groups", "collapse", "allreduce", "posterior")
+            stages["in_path_ms"] = {k: float(v) for k, v in zip(names, med)}
+            stages["in_path_collapse_from_pattern"] = bool(lib.lg_ctx_pattern_collapse_count(ctx.h) - pc0 == 3)
     peak, peak_src = measured_peak()
     k1_bytes = 8.0 * nnz_local + 8.0 * (n_local + 1) + 4.0 * K * n_local
     achieved = k1_bytes / (t_k1 * 1e-3) / 1e9
@@ -394,6 +413,10 @@ def main():
     if "collapse_ms" in stages:
         cb = 8.0 * nnz_local + 8.0 * (n_local + 1) + 4.0 * n_local + 4.0 * D * ngroups
         stages["collapse_GBps"] = cb / (stages["collapse_ms"] * 1e-3) / 1e9
+        if "in_path_ms" in stages:  # ALGORITHMIC bytes of the stage over its time in the path (the pattern form moves fewer)
+            ip = stages["in_path_ms"]
+            stages["in_path_collapse_GBps"] = cb / (ip["collapse"] * 1e-3) / 1e9
+            stages["in_path_project_plus_collapse_frac"] = (k1_bytes + cb) / ((ip["project"] + ip["collapse"]) * 1e-3) / 1e9 / peak
 
     # ---- K7 at the shape of BASELINE configs[2]: one batch's 125k cells as references, 250k queries, d = 50, k = 10 ----
     roofline_knn = None

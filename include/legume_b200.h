@@ -65,6 +65,15 @@ uint64_t lg_ctx_h2d_bytes(const lg_ctx* ctx);
  * stderr unless LG_QUIET=1.  Results are the same either way. */
 uint64_t lg_ctx_fallback_count(const lg_ctx* ctx);
 const char* lg_ctx_last_fallback(const lg_ctx* ctx);
+/* how many collapses summed the 1-bit pattern the projection of the same lg_hotpath_run_sharded call left behind instead of
+ * streaming the CSC arrays a second time (LG_COLLAPSE_PATTERN=0 turns that off; blocks with more than 32 768 genes, counts
+ * that are not whole numbers below 32 768 or a projection outside the tensor path take the CSC kernel; same sums either way) */
+uint64_t lg_ctx_pattern_collapse_count(const lg_ctx* ctx);
+/* lg_ctx_time_stages(ctx, 1): lg_hotpath_run_sharded brackets its six stages (projection, codes, groups, collapse,
+ * all-reduce, posterior) with events and synchronises at its end; lg_hotpath_last_stage_ms copies the last call's six device
+ * times in milliseconds (LG_ERR_INVALID when there is none).  Diagnostic: off by default. */
+void lg_ctx_time_stages(lg_ctx* ctx, int on);
+int lg_hotpath_last_stage_ms(const lg_ctx* ctx, float* out6);
 const char* lg_version(void);
 
 /* ---- data feed --------------------------------------------------------------------------

@@ -251,6 +251,186 @@ __global__ void __launch_bounds__(COLLAPSE_THREADS, 1) k_collapse_sorted(
     }
 }
 
+// ---- K5 from K1's pattern (lg_pattern, lg_common.cuh) ----------------------------------------------------------------
+// Inside one pass of the hot path the projection has already turned the CSC stream into a 1-bit pattern (3.75 KB per cell
+// against 11.3 KB of indices + values) and a short list of the counts != 1.  The sum of a group is then
+//     sum[g, s] = #{cells of s with bit g set}  +  sum over the listed entries (count - 1)
+// The first term is a VERTICAL count: thread t owns the 32-gene word t of every cell's row and adds the words of 16 cells
+// with a Harley-Seal carry-save tree (30 LOP3 per 16 cells) into nine bit planes; no index is ever decoded and no atomic is
+// issued for the 94 % of the entries that are ones.  The listed entries ride along in the same memory round trip (two warps
+// per cell of the round) and go to the D-long shared accumulator with ATOMS.ADD.  When the label changes (or the 256-cell
+// chunk ends) the planes are expanded into the accumulator — four genes per multiply through the 0x00204081 bit spread —
+// and the accumulator leaves with one RED.ADD.F32 per touched gene, exactly as in k_collapse_sorted.  Whole numbers
+// throughout: bit-identical to the CSC kernel and to the reference's serial fold.
+constexpr int CP_THREADS = 1024;
+constexpr int CP_CHUNK = 256;  // sorted cells per work item: the largest count nine planes have to hold
+constexpr int CP_ROUND = 16;   // cells per carry-save round
+
+// gene g lives at position cp_swz(g) of the accumulator: thread t's 32 genes then fall into 32 different banks for the 32
+// threads of a warp (they would all hit bank b otherwise), and a position run of 32 is still one 128-byte line of the output
+__device__ __forceinline__ uint32_t cp_swz(uint32_t g) { return (g & ~31u) | ((g + (g >> 5)) & 31u); }
+__device__ __forceinline__ uint32_t cp_unswz(uint32_t q) { return (q & ~31u) | ((q - (q >> 5)) & 31u); }
+// bits 0..3 of x to bit 0 of bytes 0..3
+__device__ __forceinline__ uint32_t cp_spread4(uint32_t x) { return ((x & 0xfu) * 0x00204081u) & 0x01010101u; }
+#define LG_CSA(h, l, a, b, c)                  \
+    do {                                       \
+        const uint32_t u__ = (a) ^ (b);        \
+        h = ((a) & (b)) | (u__ & (c));         \
+        l = u__ ^ (c);                         \
+    } while (0)
+
+__global__ void __launch_bounds__(CP_THREADS, 1) k_collapse_pattern(
+    const uint32_t* __restrict__ bm, uint32_t nchunks_g, const uint64_t* __restrict__ indptr, const uint32_t* __restrict__ exc,
+    const uint32_t* __restrict__ exc_cnt, const uint32_t* __restrict__ sorted_label, const uint32_t* __restrict__ sorted_cell,
+    uint64_t ncells, uint32_t S, uint64_t D, float* __restrict__ sum_ds, float* __restrict__ size_s,
+    unsigned long long* __restrict__ next_chunk) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const uint32_t Dpad = nchunks_g * LG_PAT_GC;
+    uint32_t* acc = reinterpret_cast<uint32_t*>(smem_raw);                      // Dpad swizzled accumulators
+    const char** s_base = reinterpret_cast<const char**>(acc + Dpad);           // the cell's bitmap row in chunk 0
+    uint64_t* s_e0 = reinterpret_cast<uint64_t*>(s_base + (CP_CHUNK + CP_ROUND));  // first list slot of the cell
+    uint32_t* s_cnt = reinterpret_cast<uint32_t*>(s_e0 + (CP_CHUNK + CP_ROUND));  // listed entries of the cell
+    uint32_t* s_label = s_cnt + (CP_CHUNK + CP_ROUND);
+    __shared__ unsigned long long s_chunk;
+    __shared__ uint32_t s_last[CP_CHUNK / 32 + 1];  // bit p: position p is the last of its label inside the chunk
+    const uint32_t t = threadIdx.x;
+    const int lane = t & 31, warp = t >> 5;
+    const bool active = (t >> 6) < nchunks_g;  // thread t owns bitmap word t & 63 of chunk t >> 6 = genes 32 t .. 32 t + 31
+    const uint64_t toff = ((uint64_t)(t >> 6) * (LG_PAT_CELLS * LG_PAT_STRIDE) + (t & 63u)) * 4;  // bytes from the row start to this thread's word
+    const uint64_t nchunks = (ncells + CP_CHUNK - 1) / CP_CHUNK;
+    for (uint32_t g = t; g < Dpad; g += CP_THREADS) acc[g] = 0;
+    auto add_listed = [&](uint32_t x) {
+        const uint32_t f = x >> 17;
+        atomicAdd(&acc[cp_swz(x & 0x1ffffu)], f == LG_PAT_ZERO ? 0xffffffffu : f);  // a stored zero takes its pattern bit back
+    };
+    while (true) {
+        __syncthreads();
+        if (t == 0) s_chunk = atomicAdd(next_chunk, 1ull);
+        __syncthreads();
+        const uint64_t chunk = s_chunk;
+        if (chunk >= nchunks) break;
+        const uint64_t p0 = chunk * CP_CHUNK;
+        const int np = (int)((p0 + CP_CHUNK) < ncells ? CP_CHUNK : (ncells - p0));
+        if ((int)t < np) {
+            const uint32_t cell = sorted_cell[p0 + t];
+            s_label[t] = sorted_label[p0 + t];
+            s_base[t] = reinterpret_cast<const char*>(bm + ((uint64_t)(cell >> 8) * nchunks_g) * (uint64_t)(LG_PAT_CELLS * LG_PAT_STRIDE) +
+                                                      (uint64_t)(cell & 255u) * LG_PAT_STRIDE);
+            s_e0[t] = (indptr[cell] >> 2) + cell;
+            s_cnt[t] = exc_cnt[cell];
+        }
+        __syncthreads();
+        if (t < CP_CHUNK) {
+            const bool last = (int)t < np && ((int)t == np - 1 || s_label[t + 1] != s_label[t]);
+            const unsigned mk = __ballot_sync(0xffffffffu, last);
+            if (lane == 0) s_last[warp] = mk;
+        }
+        __syncthreads();
+        int seg0 = 0;
+        while (seg0 < np) {
+            const uint32_t lab = s_label[seg0];
+            int seg1;
+            {
+                int w = seg0 >> 5;
+                uint32_t mk = s_last[w] & (0xffffffffu << (seg0 & 31));
+                while (!mk) mk = s_last[++w];  // position np - 1 is always marked
+                seg1 = (w << 5) + __ffs(mk);
+            }
+            if (lab < S) {
+                uint32_t ones = 0, twos = 0, fours = 0, eights = 0, h0 = 0, h1 = 0, h2 = 0, h3 = 0, h4 = 0;
+                for (int b = seg0; b < seg1; b += CP_ROUND) {
+                    uint32_t w[CP_ROUND];
+                    if (active && b + CP_ROUND <= seg1) {  // a full round: sixteen plain loads in flight
+#pragma unroll
+                        for (int u = 0; u < CP_ROUND; ++u) w[u] = __ldg(reinterpret_cast<const uint32_t*>(s_base[b + u] + toff));
+                    } else {
+#pragma unroll
+                        for (int u = 0; u < CP_ROUND; ++u) {
+                            w[u] = 0u;
+                            if (active && b + u < seg1) w[u] = __ldg(reinterpret_cast<const uint32_t*>(s_base[b + u] + toff));
+                        }
+                    }
+                    // the listed entries of cell b + (warp & 15): this half of the warp pair takes entries 32 half + lane (+ 64 i)
+                    const int pe = b + (warp & 15);
+                    uint32_t ecnt = 0;
+                    uint64_t ee0 = 0;
+                    if (pe < seg1) {
+                        ecnt = s_cnt[pe];
+                        ee0 = s_e0[pe];
+                    }
+                    const uint32_t k0 = ((uint32_t)(warp >> 4) << 5) + lane;
+                    uint32_t x0 = 0u, x1 = 0u;  // no packed word is 0 (field 0 would be a count of one)
+                    if (k0 < ecnt) x0 = __ldg(exc + ee0 + k0);
+                    if (k0 + 64 < ecnt) x1 = __ldg(exc + ee0 + k0 + 64);
+                    uint32_t ta, tb, fa, fb, ea, eb, sx;
+                    LG_CSA(ta, ones, ones, w[0], w[1]);
+                    LG_CSA(tb, ones, ones, w[2], w[3]);
+                    LG_CSA(fa, twos, twos, ta, tb);
+                    LG_CSA(ta, ones, ones, w[4], w[5]);
+                    LG_CSA(tb, ones, ones, w[6], w[7]);
+                    LG_CSA(fb, twos, twos, ta, tb);
+                    LG_CSA(ea, fours, fours, fa, fb);
+                    LG_CSA(ta, ones, ones, w[8], w[9]);
+                    LG_CSA(tb, ones, ones, w[10], w[11]);
+                    LG_CSA(fa, twos, twos, ta, tb);
+                    LG_CSA(ta, ones, ones, w[12], w[13]);
+                    LG_CSA(tb, ones, ones, w[14], w[15]);
+                    LG_CSA(fb, twos, twos, ta, tb);
+                    LG_CSA(eb, fours, fours, fa, fb);
+                    LG_CSA(sx, eights, eights, ea, eb);
+                    // the sixteens ripple into the upper planes
+                    uint32_t cy = sx, tt;
+                    tt = h0 & cy; h0 ^= cy; cy = tt;
+                    tt = h1 & cy; h1 ^= cy; cy = tt;
+                    tt = h2 & cy; h2 ^= cy; cy = tt;
+                    tt = h3 & cy; h3 ^= cy; cy = tt;
+                    h4 ^= cy;
+                    if (x0) add_listed(x0);
+                    if (x1) add_listed(x1);
+                    for (uint32_t k = k0 + 128; k < ecnt; k += 64) add_listed(__ldg(exc + ee0 + k));
+                }
+                __syncthreads();  // every listed entry is in
+                if (active) {
+                    const uint32_t gbase = t << 5;
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) {
+                        const int sh = 4 * q;
+                        uint32_t pk = cp_spread4(ones >> sh);
+                        pk += cp_spread4(twos >> sh) << 1;
+                        pk += cp_spread4(fours >> sh) << 2;
+                        pk += cp_spread4(eights >> sh) << 3;
+                        pk += cp_spread4(h0 >> sh) << 4;
+                        pk += cp_spread4(h1 >> sh) << 5;
+                        pk += cp_spread4(h2 >> sh) << 6;
+                        pk += cp_spread4(h3 >> sh) << 7;
+                        const uint32_t top = (h4 >> sh) & 0xfu;  // a gene present in all 256 cells
+                        if (pk | top) {
+#pragma unroll
+                            for (int i = 0; i < 4; ++i) {
+                                const uint32_t cnt = ((pk >> (8 * i)) & 255u) + (((top >> i) & 1u) << 8);
+                                if (cnt) acc[gbase + (((uint32_t)(sh + i) + t) & 31u)] += cnt;
+                            }
+                        }
+                    }
+                }
+                __syncthreads();
+                for (uint32_t q = t; q < Dpad; q += CP_THREADS) {
+                    const uint32_t v = acc[q];
+                    if (v != 0) {
+                        const uint32_t gene = cp_unswz(q);
+                        if (gene < D) atomicAdd(sum_ds + (size_t)lab * D + gene, (float)v);  // whole numbers: exact in any order
+                        acc[q] = 0;
+                    }
+                }
+                if (t == 0 && size_s) atomicAdd(&size_s[lab], (float)(seg1 - seg0));
+                __syncthreads();
+            }
+            seg0 = seg1;
+        }
+    }
+}
+#undef LG_CSA
+
 __global__ void k_count_bs(const uint32_t* __restrict__ group, const uint32_t* __restrict__ batch,
                            const float* __restrict__ mult, uint64_t ncols, uint32_t S, uint32_t B,
                            float* __restrict__ n_bs) {
@@ -396,6 +576,54 @@ static int collapse_by_label(lg_ctx* ctx, LgStage& st, const lg_csc* m, const ui
     }
     if (after_first_half && !split) LG_TRY((*after_first_half)());  // nothing was split: the callback still runs once, before the caller's second step
     return LG_OK;
+}
+
+// can k_collapse_pattern take this block?  (thread t of 1024 owns bitmap word t: at most 16 chunks of 2048 genes)
+bool lg_collapse_pattern_fits(const lg_ctx* ctx, uint64_t D, uint64_t N) {
+    const uint64_t nch = (D + LG_PAT_GC - 1) / LG_PAT_GC;
+    const size_t smem = (size_t)nch * LG_PAT_GC * 4 + (size_t)(CP_CHUNK + CP_ROUND) * 24;
+    return D > 0 && N > 0 && N < 0xFFFFFFFFull && nch * (LG_PAT_GC / 32) <= CP_THREADS && smem + 4096 <= ctx->smem_optin;
+}
+
+// lg_collapse_basic (unit multiplicities) from the pattern K1 left behind in this pass; the caller has checked pat->filled and
+// read pat->ovf as 0
+int lg_collapse_basic_pattern(lg_ctx* ctx, const lg_csc* m, const uint32_t* group_of_cell, uint32_t S, float* out_sum_ds,
+                              float* out_size_s, const lg_pattern* pat) {
+    LG_REQUIRE(ctx, m && group_of_cell && out_sum_ds && out_size_s && pat && pat->filled, "lg_collapse_basic_pattern: null argument");
+    const uint64_t N = m->ncols, D = m->nrows;
+    LG_REQUIRE(ctx, lg_collapse_pattern_fits(ctx, D, N) && pat->nchunks == (uint32_t)((D + LG_PAT_GC - 1) / LG_PAT_GC),
+               "lg_collapse_basic_pattern: block outside the pattern kernel's range");
+    LgStage st(ctx);
+    const uint32_t* d_label;
+    float *d_sum, *d_size;
+    LG_TRY(st.in(group_of_cell, (size_t)N, &d_label));
+    LG_TRY(st.out(out_sum_ds, (size_t)D * S, &d_sum));
+    LG_TRY(st.out(out_size_s, (size_t)S, &d_size));
+    LG_CUDA(ctx, cudaMemsetAsync(d_sum, 0, sizeof(float) * (size_t)D * S, ctx->stream));
+    LG_CUDA(ctx, cudaMemsetAsync(d_size, 0, sizeof(float) * S, ctx->stream));
+    if (S == 0) return st.finish();
+    uint32_t *d_cell_in, *d_cell_out, *d_lab_out;
+    LG_TRY(st.scratch(N, &d_cell_in));
+    LG_TRY(st.scratch(N, &d_cell_out));
+    LG_TRY(st.scratch(N, &d_lab_out));
+    LG_LAUNCH(ctx, k_iota_u32, (unsigned)((N + 255) / 256), 256, 0, d_cell_in, N);
+    size_t tmp_bytes = 0;
+    LG_CUDA(ctx, cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, d_label, d_lab_out, d_cell_in, d_cell_out, (int)N, 0, 32, ctx->stream));
+    char* d_tmp;
+    LG_TRY(st.scratch(tmp_bytes, &d_tmp));
+    LG_CUDA(ctx, cub::DeviceRadixSort::SortPairs(d_tmp, tmp_bytes, d_label, d_lab_out, d_cell_in, d_cell_out, (int)N, 0, 32, ctx->stream));
+    ctx->launches += 4;
+    unsigned long long* d_next;
+    LG_TRY(st.scratch(1, &d_next));
+    LG_CUDA(ctx, cudaMemsetAsync(d_next, 0, sizeof(unsigned long long), ctx->stream));
+    const size_t smem = (size_t)pat->nchunks * LG_PAT_GC * 4 + (size_t)(CP_CHUNK + CP_ROUND) * 24;
+    LG_CUDA(ctx, cudaFuncSetAttribute(k_collapse_pattern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const uint64_t nwork = (N + CP_CHUNK - 1) / CP_CHUNK;
+    const unsigned grid = (unsigned)(nwork < (uint64_t)ctx->num_sms ? nwork : (uint64_t)ctx->num_sms);
+    LG_LAUNCH(ctx, k_collapse_pattern, grid, CP_THREADS, smem, pat->bm, pat->nchunks, m->indptr, pat->exc, pat->exc_cnt, d_lab_out,
+              d_cell_out, N, S, D, d_sum, d_size, d_next);
+    ctx->pattern_collapses++;
+    return st.finish();
 }
 
 int lg_collapse_basic_split(lg_ctx* ctx, const lg_csc* m, const uint32_t* d_group, uint32_t S, uint32_t S_half, float* d_sum_ds,

@@ -184,9 +184,10 @@ extern "C" int lg_hotpath_run_sharded(lg_ctx* ctx, const lg_csc* m, const float*
     // LG_TRACE=1: device time of every stage of this call on stderr (diagnostic; synchronises at the end)
     const char* tr = getenv("LG_TRACE");
     const bool trace = tr && tr[0] == '1';
+    const bool timed = trace || ctx->time_stages;  // lg_ctx_time_stages: the same events, read back through lg_hotpath_last_stage_ms
     std::vector<cudaEvent_t> evs;
     auto mark = [&]() {
-        if (!trace) return;
+        if (!timed) return;
         cudaEvent_t e;
         cudaEventCreate(&e);
         cudaEventRecord(e, ctx->stream);
@@ -214,7 +215,30 @@ extern "C" int lg_hotpath_run_sharded(lg_ctx* ctx, const lg_csc* m, const float*
     }
     const uint64_t nblk = (n + LG_BLOCK_CELLS - 1) / LG_BLOCK_CELLS;
     // ---- K1 + K2 ----
-    LG_TRY(lg_project_raw(ctx, m, d_basis_kd, K, d_proj));
+    // lg_pattern: the scan of K1 leaves its 1-bit pattern and the counts != 1 in buffers this call owns, and K5 sums the groups
+    // from those (3.9 KB + ~0.35 KB per cell at configs[1]) instead of streaming the 8 bytes per non-zero of the CSC arrays a second time
+    // (LG_COLLAPSE_PATTERN=0 keeps the CSC kernel)
+    lg_pattern pat;
+    int* h_ovf = reinterpret_cast<int*>(static_cast<char*>(ctx->pinned) + 256);
+    {
+        const char* pz = getenv("LG_COLLAPSE_PATTERN");
+        if (!(pz && pz[0] == '0') && lg_collapse_pattern_fits(ctx, D, n)) {
+            const uint64_t nch = (D + LG_PAT_GC - 1) / LG_PAT_GC, nsup = (n + LG_PAT_CELLS - 1) / LG_PAT_CELLS;
+            LG_TRY(st.scratch((size_t)(nsup * nch) * (LG_PAT_CELLS * LG_PAT_STRIDE), &pat.bm));
+            LG_TRY(st.scratch((size_t)((m->nnz >> 2) + n + 1), &pat.exc));
+            LG_TRY(st.scratch((size_t)n, &pat.exc_cnt));
+            LG_TRY(st.scratch(1, &pat.ovf));
+            ctx->pat = &pat;
+        }
+    }
+    {
+        const int rc = lg_project_raw(ctx, m, d_basis_kd, K, d_proj);
+        ctx->pat = nullptr;
+        LG_TRY(rc);
+    }
+    *h_ovf = 1;
+    if (pat.filled)  // home long before the group table's read-back below waits on the stream
+        LG_CUDA(ctx, cudaMemcpyAsync(h_ovf, pat.ovf, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
     double* d_sums = nullptr;
     if (d_batch) {
         const uint32_t M = nbatch * (uint32_t)(K + 1);
@@ -314,7 +338,8 @@ extern "C" int lg_hotpath_run_sharded(lg_ctx* ctx, const lg_csc* m, const float*
         LG_NCCL(ctx, a->GroupEnd());
         LG_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->side_ev[1], 0));
     } else {
-        LG_TRY(lg_collapse_basic(ctx, m, d_group, nullptr, S, d_sum_ds, d_size_s));
+        if (pat.filled && *h_ovf == 0) LG_TRY(lg_collapse_basic_pattern(ctx, m, d_group, S, d_sum_ds, d_size_s, &pat));
+        else LG_TRY(lg_collapse_basic(ctx, m, d_group, nullptr, S, d_sum_ds, d_size_s));
         mark();
         LG_TRY(lg_allreduce_stats(ctx, d_sum_ds, d_size_s, nullptr, nullptr, D, S, 0));
     }
@@ -323,6 +348,11 @@ extern "C" int lg_hotpath_run_sharded(lg_ctx* ctx, const lg_csc* m, const float*
     if (d_mean || d_sd || d_log_mean || d_log_sd)
         LG_TRY(lg_optimize_single(ctx, d_sum_ds, d_size_s, D, S, 1.0f, 1.0f, target, d_mean, d_sd, d_log_mean, d_log_sd));
     mark();
+    if (timed && !trace && evs.size() == 7) {
+        cudaEventSynchronize(evs.back());
+        for (int i = 0; i < 6; ++i) cudaEventElapsedTime(&ctx->stage_ms[i], evs[i], evs[i + 1]);
+        ctx->stage_ms_valid = true;
+    }
     if (trace && evs.size() == 7) {
         static cudaEvent_t prev_end = nullptr;  // diagnostic only: the stream time between two consecutive calls
         cudaEventSynchronize(evs.back());

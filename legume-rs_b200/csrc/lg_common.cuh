@@ -12,6 +12,25 @@
 
 #include "../../include/legume_b200.h"
 
+// K1's by-product for K5 (lg_project_umma.cu writes it, lg_collapse.cu reads it back inside ONE pass of the hot path): the
+// 1-bit sparsity pattern the scan builds for the tensor kernel, tiled [N/256][D/2048][256 cells][66 words] with gene offset o
+// of a 32-gene word at bit o, plus the entries whose count is not 1 as packed words `gene | field << 17` (field = count - 1,
+// or 0x7fff for a stored zero) in the slots [(lo >> 2) + j, ...) of cell j (lo = indptr[j]; the slot count of a cell is
+// (hi >> 2) - (lo >> 2) + 1).  `ovf` is raised when a list did not fit its slots or a value is not a whole number in
+// [0, 32767]: the collapse then streams the CSC arrays as it always did.
+constexpr int LG_PAT_CELLS = 256;                    // cells per supertile
+constexpr int LG_PAT_GC = 2048;                      // genes per bitmap chunk
+constexpr int LG_PAT_STRIDE = LG_PAT_GC / 32 + 2;    // words per (cell, chunk) row
+constexpr uint32_t LG_PAT_ZERO = 0x7fffu;            // field of a stored zero
+struct lg_pattern {
+    uint32_t* bm = nullptr;       // device, nsuper * nchunks * 256 * 66 words
+    uint32_t* exc = nullptr;      // device, (nnz >> 2) + ncols + 1 words
+    uint32_t* exc_cnt = nullptr;  // device, ncols: entries with a count != 1 per cell
+    int* ovf = nullptr;           // device flag
+    uint32_t nchunks = 0;
+    bool filled = false;          // set by K1 when the tensor path ran and wrote all of the above
+};
+
 struct lg_ctx {
     int device = 0;
     int num_sms = 148;
@@ -50,6 +69,12 @@ struct lg_ctx {
     };
     std::vector<CacheBlk> cache;
     // tensor-core paths that could not take a call and handed it to the CUDA-core kernel (lg_note_fallback)
+    lg_pattern* pat = nullptr;  // set by the hot path around its K1 call: "keep the pattern for the collapse"
+    uint64_t pattern_collapses = 0;  // collapses that summed K1's pattern instead of the CSC arrays
+    // lg_ctx_time_stages: device time of the six stages of the last lg_hotpath_run_sharded call (events around each stage)
+    bool time_stages = false;
+    bool stage_ms_valid = false;
+    float stage_ms[6] = {0, 0, 0, 0, 0, 0};
     uint64_t fallbacks = 0;
     std::string last_fallback;
     std::vector<std::string> fallback_seen;
@@ -273,6 +298,10 @@ __device__ __forceinline__ void lg_block_sums_stage2(const double* stage, int co
 // all-reduce of the first half with the collapse of the second (lg_comm.cu).
 int lg_collapse_basic_split(lg_ctx* ctx, const lg_csc* m, const uint32_t* d_group, uint32_t S, uint32_t S_half, float* d_sum_ds,
                             float* d_size_s, const std::function<int()>& after_first_half);
+// K5 from the pattern K1 left behind in the same pass (lg_pattern; lg_collapse.cu)
+bool lg_collapse_pattern_fits(const lg_ctx* ctx, uint64_t D, uint64_t N);
+int lg_collapse_basic_pattern(lg_ctx* ctx, const lg_csc* m, const uint32_t* group_of_cell, uint32_t S, float* out_sum_ds,
+                              float* out_size_s, const lg_pattern* pat);
 // LG_OK when rows are strictly ascending and in range inside every column (checked once per block, cached)
 int lg_csc_require_canonical(lg_ctx* ctx, const lg_csc* m, const char* who);
 // rejects labels outside [0, bound) with LG_ERR_INVALID (one small kernel + a flag read-back)

@@ -97,6 +97,18 @@ extern "C" int lg_ctx_sync(lg_ctx* c) {
 extern "C" uint64_t lg_ctx_launch_count(const lg_ctx* c) { return c ? c->launches : 0; }
 extern "C" uint64_t lg_ctx_h2d_bytes(const lg_ctx* c) { return c ? c->h2d_bytes : 0; }
 extern "C" uint64_t lg_ctx_fallback_count(const lg_ctx* c) { return c ? c->fallbacks : 0; }
+extern "C" uint64_t lg_ctx_pattern_collapse_count(const lg_ctx* c) { return c ? c->pattern_collapses : 0; }
+extern "C" void lg_ctx_time_stages(lg_ctx* c, int on) {
+    if (c) {
+        c->time_stages = on != 0;
+        c->stage_ms_valid = false;
+    }
+}
+extern "C" int lg_hotpath_last_stage_ms(const lg_ctx* c, float* out6) {
+    if (!c || !out6 || !c->stage_ms_valid) return LG_ERR_INVALID;
+    for (int i = 0; i < 6; ++i) out6[i] = c->stage_ms[i];
+    return LG_OK;
+}
 extern "C" const char* lg_ctx_last_fallback(const lg_ctx* c) { return c ? c->last_fallback.c_str() : ""; }
 
 // ---- CSC container ----------------------------------------------------------------------------

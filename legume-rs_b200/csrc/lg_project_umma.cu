@@ -35,6 +35,7 @@ constexpr int CELLS = TILE_M * NT;   // cells per CTA pass
 constexpr int GS = 128;              // genes per pipeline stage (4 MMAs of K = 32)
 constexpr int GC = 2048;             // genes per bitmap chunk: K1b stores one 256-byte row piece per chunk (1024 costs it 1 ms)
 constexpr int BM_STRIDE = GC / 32 + 2;  // 66 words per cell row: 8-byte aligned, conflict-free LDS.64
+static_assert(CELLS == LG_PAT_CELLS && GC == LG_PAT_GC && BM_STRIDE == LG_PAT_STRIDE, "lg_pattern describes this layout to the collapse");
 constexpr int NBST = 4;              // B-operand ring depth (stages)
 constexpr int NBM = 2;               // bitmap chunks in flight
 constexpr int NAST = 3;              // A-operand ring depth in TMEM (stages per tile)
@@ -145,7 +146,9 @@ __global__ void __launch_bounds__(PREP_WARPS * 32, 4) k_project_prep(const uint6
                                                                      const float* __restrict__ values, uint64_t ncols,
                                                                      const float* __restrict__ basis_kd, int K, uint32_t nchunks,
                                                                      uint32_t* __restrict__ bm_global, float* __restrict__ out,
-                                                                     float* __restrict__ scale, float csn) {
+                                                                     float* __restrict__ scale, float csn,
+                                                                     uint32_t* __restrict__ exc, uint32_t* __restrict__ exc_cnt,
+                                                                     int* __restrict__ exc_ovf) {
     extern __shared__ __align__(16) uint32_t rows[];  // PREP_WARPS bitmap rows, then the exception queues
     __shared__ float lut_x[PREP_LUT];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -166,6 +169,8 @@ __global__ void __launch_bounds__(PREP_WARPS * 32, 4) k_project_prep(const uint6
         const uint32_t n = (uint32_t)(indptr[j + 1] - lo);
         const uint32_t* ip = indices + lo + lane;
         const float* vp = values + lo + lane;
+        // lg_pattern: the cell's counts != 1 also leave as packed words for the collapse (exc != NULL only in projection mode)
+        // in the slots [(lo >> 2) + j, ((lo + n) >> 2) + j] (recomputed in the drain: nothing extra stays live across the scan)
         float acc[HALF2 ? 4 : NACC];
 #pragma unroll
         for (int a = 0; a < (HALF2 ? 4 : NACC); ++a) acc[a] = 0.0f;
@@ -204,6 +209,14 @@ __global__ void __launch_bounds__(PREP_WARPS * 32, 4) k_project_prep(const uint6
                     x = (val == (float)vi && vi >= 0 && vi < PREP_LUT) ? lut_x[vi] : log1pf(val);
                     nsq = fmaf(x, x, nsq);
                     w = x - base_x;
+                    if (exc) {
+                        const uint32_t idx = qhead + lane;  // qhead counts the cell's entries drained so far
+                        const uint64_t e0 = (lo >> 2) + j;
+                        if (val == (float)vi && vi >= 0 && vi <= 32767 && e0 + idx <= ((lo + n) >> 2) + j)
+                            exc[e0 + idx] = g | ((vi == 0 ? LG_PAT_ZERO : (uint32_t)(vi - 1)) << 17);
+                        else
+                            *exc_ovf = 1;  // the collapse falls back to the CSC arrays
+                    }
                 }
             }
             if constexpr (HALF2) {
@@ -442,7 +455,10 @@ __global__ void __launch_bounds__(PREP_WARPS * 32, 4) k_project_prep(const uint6
                 if (k < K) out[(size_t)j * K + k] = acc[a] / denom;
             }
         }
-        if (lane == 0) scale[j] = pat_scale;
+        if (lane == 0) {
+            scale[j] = pat_scale;
+            if (exc) exc_cnt[j] = qtail;
+        }
         __syncwarp();
     }
 }
@@ -1246,7 +1262,21 @@ int lg_project_raw_umma(lg_ctx* ctx, const lg_csc* m, const float* d_basis, int 
     const uint32_t nchunks = (uint32_t)((D + GC - 1) / GC);
     const uint64_t nsuper = (m->ncols + CELLS - 1) / CELLS;
     uint32_t* d_bm;
-    LG_TRY(st.scratch((size_t)nsuper * nchunks * CELLS * BM_STRIDE, &d_bm));
+    // the hot path asks for the pattern to outlive this call (lg_pattern): it owns the buffers then
+    lg_pattern* pat = (mode == 0) ? ctx->pat : nullptr;
+    uint32_t *d_exc = nullptr, *d_exc_cnt = nullptr;
+    int* d_exc_ovf = nullptr;
+    if (pat) {
+        pat->filled = false;
+        pat->nchunks = nchunks;
+        d_bm = pat->bm;
+        d_exc = pat->exc;
+        d_exc_cnt = pat->exc_cnt;
+        d_exc_ovf = pat->ovf;
+        LG_CUDA(ctx, cudaMemsetAsync(d_exc_ovf, 0, sizeof(int), ctx->stream));
+    } else {
+        LG_TRY(st.scratch((size_t)nsuper * nchunks * CELLS * BM_STRIDE, &d_bm));
+    }
     if (m->ncols % CELLS)  // rows of the ragged last supertile that no cell writes must read as empty
         LG_CUDA(ctx, cudaMemsetAsync(d_bm + (nsuper - 1) * nchunks * (size_t)(CELLS * BM_STRIDE), 0,
                                      (size_t)nchunks * BM_CHUNK_BYTES, ctx->stream));
@@ -1264,7 +1294,7 @@ int lg_project_raw_umma(lg_ctx* ctx, const lg_csc* m, const float* d_basis, int 
     do {                                                                                                                              \
         LG_CUDA(ctx, cudaFuncSetAttribute(k_project_prep<NA, H2, V, M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psmem));    \
         LG_LAUNCH(ctx, (k_project_prep<NA, H2, V, M>), (unsigned)blocks, PREP_WARPS * 32, psmem, m->indptr, m->indices, m->values,  \
-                  m->ncols, d_basis, K, nchunks, d_bm, d_out, d_scale, csn);                                                          \
+                  m->ncols, d_basis, K, nchunks, d_bm, d_out, d_scale, csn, d_exc, d_exc_cnt, d_exc_ovf);                             \
     } while (0)
 #define LG_PREP_LAUNCH(NA, H2, V)                 \
     do {                                          \
@@ -1307,6 +1337,7 @@ int lg_project_raw_umma(lg_ctx* ctx, const lg_csc* m, const float* d_basis, int 
         fprintf(stderr, "[lg_project] prep %.3f ms, umma %.3f ms\n", a, b);
         for (int i = 0; i < 3; ++i) cudaEventDestroy(ev[i]);
     }
+    if (pat) pat->filled = true;
     *used = 1;
     return LG_OK;
 }

@@ -125,6 +125,12 @@ lib.lg_ctx_h2d_bytes.argtypes = [_vp]
 lib.lg_ctx_h2d_bytes.restype = C.c_uint64
 lib.lg_ctx_fallback_count.argtypes = [_vp]
 lib.lg_ctx_fallback_count.restype = C.c_uint64
+lib.lg_ctx_pattern_collapse_count.argtypes = [_vp]
+lib.lg_ctx_pattern_collapse_count.restype = C.c_uint64
+lib.lg_ctx_time_stages.argtypes = [_vp, C.c_int]
+lib.lg_ctx_time_stages.restype = None
+lib.lg_hotpath_last_stage_ms.argtypes = [_vp, _vp]
+lib.lg_hotpath_last_stage_ms.restype = C.c_int
 lib.lg_ctx_last_fallback.argtypes = [_vp]
 lib.lg_ctx_last_fallback.restype = C.c_char_p
 lib.lg_zarr_close.argtypes = [_vp]
@@ -135,4 +141,4 @@ lib.lg_version.argtypes = []
 lib.lg_version.restype = C.c_char_p
 
 EXPORTED = sorted(list(_sig) + ["lg_last_error", "lg_ctx_launch_count", "lg_ctx_h2d_bytes", "lg_ctx_fallback_count", "lg_ctx_last_fallback",
-                          "lg_version", "lg_zarr_close", "lg_zarr_last_error"])
+                          "lg_ctx_pattern_collapse_count", "lg_ctx_time_stages", "lg_hotpath_last_stage_ms", "lg_version", "lg_zarr_close", "lg_zarr_last_error"])

@@ -2,6 +2,7 @@
 inputs.  Bit-exact for codes, groups, sums and neighbour sets; 1e-5 (the reference's mixed abs/rel
 form) for projections and posteriors.  Run on the B200 box: pytest -m gpu."""
 import ctypes as C
+import os
 
 import numpy as np
 import pytest
@@ -437,6 +438,86 @@ def test_hotpath_run_sharded_one_rank_equals_staged_path(lg, ctx):
     s = a["sum_ds"].clone()
     ctx.check(lg.lib.lg_allreduce_stats(ctx.h, lg._ptr(s), None, None, None, D, a["num_groups"], 0))
     assert torch.equal(s, a["sum_ds"])
+
+
+def _pattern_case(rng, D, N, density, p_geom, max_count, zeros=0, always=(), empty_every=0):
+    ip, ix, v = random_csc(rng, D, N, density, max_count=max_count, empty_every=empty_every)
+    ip, ix, v = ip.astype(np.int64), ix.astype(np.int64), v.copy()
+    v[:] = np.minimum(rng.geometric(p_geom, size=v.size), max_count).astype(np.float32)
+    if zeros:
+        v[rng.choice(v.size, size=zeros, replace=False)] = 0.0  # stored zeros: bit set, count 0
+    if len(always):  # genes present in every non-empty cell: a chunk of 256 cells of one group counts to 256 (the ninth plane)
+        cols = []
+        for j in range(N):
+            rows, vals = ix[ip[j]:ip[j + 1]], v[ip[j]:ip[j + 1]]
+            if rows.size:
+                extra = np.setdiff1d(np.asarray(always), rows)
+                rows = np.concatenate([rows, extra])
+                vals = np.concatenate([vals, np.ones(extra.size, np.float32)])
+                o = np.argsort(rows, kind="stable")
+                rows, vals = rows[o], vals[o]
+            cols.append((rows, vals))
+        ip = np.concatenate([[0], np.cumsum([c[0].size for c in cols])])
+        ix = np.concatenate([c[0] for c in cols])
+        v = np.concatenate([c[1] for c in cols]).astype(np.float32)
+    return ip.astype(np.uint64), ix.astype(np.uint64), v
+
+
+@pytest.mark.parametrize("case", ["ones_mostly", "many_listed", "stored_zeros", "huge_count", "too_many_genes", "fractional"])
+def test_collapse_from_the_projection_pattern_equals_the_csc_collapse(lg, ctx, case):
+    """Inside lg_hotpath_run_sharded K5 sums the groups from the 1-bit pattern + list of counts != 1 that K1's scan left
+    behind (k_collapse_pattern, lg_collapse.cu) instead of streaming the CSC arrays again.  Whole-number sums: they must
+    equal the CSC kernel's (the staged path) bit for bit — ragged cell / gene counts, empty cells, a gene present in all 256
+    cells of a chunk, cells with more than 128 listed entries, stored zeros — and a block the pattern cannot express
+    (a count above 32 767, a fractional value, more than 32 768 genes) must quietly take the CSC kernel."""
+    import torch
+    from legume_b200.pipeline import HotPath
+    rng = np.random.default_rng(77)
+    K = 50
+    if case == "ones_mostly":
+        D, N, kk = 5000, 1300, 1
+        ip, ix, v = _pattern_case(rng, D, N, 0.08, 0.92, 9, always=(7, 4999), empty_every=17)
+    elif case == "many_listed":
+        D, N, kk = 4100, 700, 6
+        ip, ix, v = _pattern_case(rng, D, N, 0.2, 0.3, 40)
+    elif case == "stored_zeros":
+        D, N, kk = 2048, 513, 3
+        ip, ix, v = _pattern_case(rng, D, N, 0.1, 0.8, 5, zeros=900)
+    elif case == "huge_count":
+        D, N, kk = 3000, 600, 4
+        ip, ix, v = _pattern_case(rng, D, N, 0.05, 0.8, 5)
+        v[v.size // 2] = 40000.0
+    elif case == "fractional":
+        D, N, kk = 3000, 600, 4
+        ip, ix, v = _pattern_case(rng, D, N, 0.05, 0.8, 5)
+        v[v.size // 3] = 2.5
+    else:
+        D, N, kk = 33000, 300, 3
+        ip, ix, v = _pattern_case(rng, D, N, 0.01, 0.8, 5)
+    blk = lg.CscBlock.upload(ctx, ip, ix, v, D)
+    basis = torch.from_numpy(basis_for(D, K, 5)).cuda()
+    hp = HotPath(ctx)
+    before = lg.lib.lg_ctx_pattern_collapse_count(ctx.h)
+    c = hp.run_native(blk, basis, None, 0, kk)
+    took = lg.lib.lg_ctx_pattern_collapse_count(ctx.h) - before
+    assert took == (0 if case in ("huge_count", "too_many_genes", "fractional") else 1)
+    a = hp.run(blk, basis, None, 0, kk)  # staged calls: lg_collapse_basic on the CSC arrays
+    assert a["num_groups"] == c["num_groups"]
+    for key in ("proj", "group", "sum_ds", "size_s"):
+        assert torch.equal(a[key], c[key]), key
+    # and against the arrays themselves
+    dense = np.zeros((c["num_groups"], D), np.float64)
+    g = c["group"].cpu().numpy()
+    for j in range(N):
+        np.add.at(dense[g[j]], ix[ip[j]:ip[j + 1]].astype(np.int64), v[ip[j]:ip[j + 1]])
+    assert np.array_equal(c["sum_ds"].cpu().numpy().astype(np.float64), dense)
+    os.environ["LG_COLLAPSE_PATTERN"] = "0"
+    try:
+        off = hp.run_native(blk, basis, None, 0, kk)
+    finally:
+        del os.environ["LG_COLLAPSE_PATTERN"]
+    assert lg.lib.lg_ctx_pattern_collapse_count(ctx.h) - before == took
+    assert torch.equal(off["sum_ds"], c["sum_ds"]) and torch.equal(off["size_s"], c["size_s"])
 
 
 def test_sparse_io_stack_projects_every_modality_and_stacks(lg, ctx):
