@@ -316,7 +316,7 @@ __global__ void __launch_bounds__(CP_THREADS, 1) k_collapse_pattern(
             s_label[t] = sorted_label[p0 + t];
             s_base[t] = reinterpret_cast<const char*>(bm + ((uint64_t)(cell >> 8) * nchunks_g) * (uint64_t)(LG_PAT_CELLS * LG_PAT_STRIDE) +
                                                       (uint64_t)(cell & 255u) * LG_PAT_STRIDE);
-            s_e0[t] = (indptr[cell] >> 2) + cell;
+            s_e0[t] = (indptr[cell] >> 1) + cell;
             s_cnt[t] = exc_cnt[cell];
         }
         __syncthreads();

@@ -225,7 +225,7 @@ extern "C" int lg_hotpath_run_sharded(lg_ctx* ctx, const lg_csc* m, const float*
         if (!(pz && pz[0] == '0') && lg_collapse_pattern_fits(ctx, D, n)) {
             const uint64_t nch = (D + LG_PAT_GC - 1) / LG_PAT_GC, nsup = (n + LG_PAT_CELLS - 1) / LG_PAT_CELLS;
             LG_TRY(st.scratch((size_t)(nsup * nch) * (LG_PAT_CELLS * LG_PAT_STRIDE), &pat.bm));
-            LG_TRY(st.scratch((size_t)((m->nnz >> 2) + n + 1), &pat.exc));
+            LG_TRY(st.scratch((size_t)((m->nnz >> 1) + n + 1), &pat.exc));
             LG_TRY(st.scratch((size_t)n, &pat.exc_cnt));
             LG_TRY(st.scratch(1, &pat.ovf));
             ctx->pat = &pat;

@@ -15,8 +15,8 @@
 // K1's by-product for K5 (lg_project_umma.cu writes it, lg_collapse.cu reads it back inside ONE pass of the hot path): the
 // 1-bit sparsity pattern the scan builds for the tensor kernel, tiled [N/256][D/2048][256 cells][66 words] with gene offset o
 // of a 32-gene word at bit o, plus the entries whose count is not 1 as packed words `gene | field << 17` (field = count - 1,
-// or 0x7fff for a stored zero) in the slots [(lo >> 2) + j, ...) of cell j (lo = indptr[j]; the slot count of a cell is
-// (hi >> 2) - (lo >> 2) + 1).  `ovf` is raised when a list did not fit its slots or a value is not a whole number in
+// or 0x7fff for a stored zero) in the slots [(lo >> 1) + j, ...) of cell j (lo = indptr[j]; the slot count of a cell is
+// (hi >> 1) - (lo >> 1) + 1: half of its entries may differ from one).  `ovf` is raised when a list did not fit its slots or a value is not a whole number in
 // [0, 32767]: the collapse then streams the CSC arrays as it always did.
 constexpr int LG_PAT_CELLS = 256;                    // cells per supertile
 constexpr int LG_PAT_GC = 2048;                      // genes per bitmap chunk
@@ -24,7 +24,7 @@ constexpr int LG_PAT_STRIDE = LG_PAT_GC / 32 + 2;    // words per (cell, chunk) 
 constexpr uint32_t LG_PAT_ZERO = 0x7fffu;            // field of a stored zero
 struct lg_pattern {
     uint32_t* bm = nullptr;       // device, nsuper * nchunks * 256 * 66 words
-    uint32_t* exc = nullptr;      // device, (nnz >> 2) + ncols + 1 words
+    uint32_t* exc = nullptr;      // device, (nnz >> 1) + ncols + 1 words
     uint32_t* exc_cnt = nullptr;  // device, ncols: entries with a count != 1 per cell
     int* ovf = nullptr;           // device flag
     uint32_t nchunks = 0;

@@ -170,7 +170,7 @@ __global__ void __launch_bounds__(PREP_WARPS * 32, 4) k_project_prep(const uint6
         const uint32_t* ip = indices + lo + lane;
         const float* vp = values + lo + lane;
         // lg_pattern: the cell's counts != 1 also leave as packed words for the collapse (exc != NULL only in projection mode)
-        // in the slots [(lo >> 2) + j, ((lo + n) >> 2) + j] (recomputed in the drain: nothing extra stays live across the scan)
+        // in the slots [(lo >> 1) + j, ((lo + n) >> 1) + j] (recomputed in the drain: nothing extra stays live across the scan)
         float acc[HALF2 ? 4 : NACC];
 #pragma unroll
         for (int a = 0; a < (HALF2 ? 4 : NACC); ++a) acc[a] = 0.0f;
@@ -211,8 +211,8 @@ __global__ void __launch_bounds__(PREP_WARPS * 32, 4) k_project_prep(const uint6
                     w = x - base_x;
                     if (exc) {
                         const uint32_t idx = qhead + lane;  // qhead counts the cell's entries drained so far
-                        const uint64_t e0 = (lo >> 2) + j;
-                        if (val == (float)vi && vi >= 0 && vi <= 32767 && e0 + idx <= ((lo + n) >> 2) + j)
+                        const uint64_t e0 = (lo >> 1) + j;
+                        if (val == (float)vi && vi >= 0 && vi <= 32767 && e0 + idx <= ((lo + n) >> 1) + j)
                             exc[e0 + idx] = g | ((vi == 0 ? LG_PAT_ZERO : (uint32_t)(vi - 1)) << 17);
                         else
                             *exc_ovf = 1;  // the collapse falls back to the CSC arrays

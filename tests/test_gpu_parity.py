@@ -463,13 +463,14 @@ def _pattern_case(rng, D, N, density, p_geom, max_count, zeros=0, always=(), emp
     return ip.astype(np.uint64), ix.astype(np.uint64), v
 
 
-@pytest.mark.parametrize("case", ["ones_mostly", "many_listed", "stored_zeros", "huge_count", "too_many_genes", "fractional"])
+@pytest.mark.parametrize("case", ["ones_mostly", "many_listed", "stored_zeros", "huge_count", "too_many_genes", "fractional", "list_overflows"])
 def test_collapse_from_the_projection_pattern_equals_the_csc_collapse(lg, ctx, case):
     """Inside lg_hotpath_run_sharded K5 sums the groups from the 1-bit pattern + list of counts != 1 that K1's scan left
     behind (k_collapse_pattern, lg_collapse.cu) instead of streaming the CSC arrays again.  Whole-number sums: they must
     equal the CSC kernel's (the staged path) bit for bit — ragged cell / gene counts, empty cells, a gene present in all 256
     cells of a chunk, cells with more than 128 listed entries, stored zeros — and a block the pattern cannot express
-    (a count above 32 767, a fractional value, more than 32 768 genes) must quietly take the CSC kernel."""
+    (a count above 32 767, a fractional value, more than 32 768 genes, more than half of a cell's entries not ones)
+    must quietly take the CSC kernel."""
     import torch
     from legume_b200.pipeline import HotPath
     rng = np.random.default_rng(77)
@@ -479,7 +480,10 @@ def test_collapse_from_the_projection_pattern_equals_the_csc_collapse(lg, ctx, c
         ip, ix, v = _pattern_case(rng, D, N, 0.08, 0.92, 9, always=(7, 4999), empty_every=17)
     elif case == "many_listed":
         D, N, kk = 4100, 700, 6
-        ip, ix, v = _pattern_case(rng, D, N, 0.2, 0.3, 40)
+        ip, ix, v = _pattern_case(rng, D, N, 0.2, 0.75, 40)  # ~820 entries per cell, ~205 of them listed (room for 411)
+    elif case == "list_overflows":
+        D, N, kk = 4100, 700, 6
+        ip, ix, v = _pattern_case(rng, D, N, 0.2, 0.3, 40)  # 70 % of the entries are not ones: the lists (half a cell's entries) do not fit
     elif case == "stored_zeros":
         D, N, kk = 2048, 513, 3
         ip, ix, v = _pattern_case(rng, D, N, 0.1, 0.8, 5, zeros=900)
@@ -500,7 +504,7 @@ def test_collapse_from_the_projection_pattern_equals_the_csc_collapse(lg, ctx, c
     before = lg.lib.lg_ctx_pattern_collapse_count(ctx.h)
     c = hp.run_native(blk, basis, None, 0, kk)
     took = lg.lib.lg_ctx_pattern_collapse_count(ctx.h) - before
-    assert took == (0 if case in ("huge_count", "too_many_genes", "fractional") else 1)
+    assert took == (0 if case in ("huge_count", "too_many_genes", "fractional", "list_overflows") else 1)
     a = hp.run(blk, basis, None, 0, kk)  # staged calls: lg_collapse_basic on the CSC arrays
     assert a["num_groups"] == c["num_groups"]
     for key in ("proj", "group", "sum_ds", "size_s"):
