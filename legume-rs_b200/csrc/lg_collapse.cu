@@ -264,7 +264,9 @@ __global__ void __launch_bounds__(COLLAPSE_THREADS, 1) k_collapse_sorted(
 // throughout: bit-identical to the CSC kernel and to the reference's serial fold.
 constexpr int CP_THREADS = 1024;
 constexpr int CP_CHUNK = 256;  // sorted cells per work item: the largest count nine planes have to hold
-constexpr int CP_ROUND = 16;   // cells per carry-save round
+constexpr int CP_ROUND = 16;   // cells per carry-save round (a double-buffered 8-cell form measured slower: 1.40 against 1.23 ms)
+constexpr int CP_PAD = CP_CHUNK + CP_ROUND;
+constexpr size_t CP_META_BYTES = (size_t)CP_PAD * (8 + 8 + 4 + 4) + (size_t)CP_CHUNK * (4 + 4 + 8 + 4);
 
 // gene g lives at position cp_swz(g) of the accumulator: thread t's 32 genes then fall into 32 different banks for the 32
 // threads of a warp (they would all hit bank b otherwise), and a position run of 32 is still one 128-byte line of the output
@@ -272,6 +274,13 @@ __device__ __forceinline__ uint32_t cp_swz(uint32_t g) { return (g & ~31u) | ((g
 __device__ __forceinline__ uint32_t cp_unswz(uint32_t q) { return (q & ~31u) | ((q - (q >> 5)) & 31u); }
 // bits 0..3 of x to bit 0 of bytes 0..3
 __device__ __forceinline__ uint32_t cp_spread4(uint32_t x) { return ((x & 0xfu) * 0x00204081u) & 0x01010101u; }
+__device__ __forceinline__ void cp_async4(void* dst_smem, const void* src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(dst_smem)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async8(void* dst_smem, const void* src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((uint32_t)__cvta_generic_to_shared(dst_smem)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 #define LG_CSA(h, l, a, b, c)                  \
     do {                                       \
         const uint32_t u__ = (a) ^ (b);        \
@@ -288,10 +297,15 @@ __global__ void __launch_bounds__(CP_THREADS, 1) k_collapse_pattern(
     const uint32_t Dpad = nchunks_g * LG_PAT_GC;
     uint32_t* acc = reinterpret_cast<uint32_t*>(smem_raw);                      // Dpad swizzled accumulators
     const char** s_base = reinterpret_cast<const char**>(acc + Dpad);           // the cell's bitmap row in chunk 0
-    uint64_t* s_e0 = reinterpret_cast<uint64_t*>(s_base + (CP_CHUNK + CP_ROUND));  // first list slot of the cell
-    uint32_t* s_cnt = reinterpret_cast<uint32_t*>(s_e0 + (CP_CHUNK + CP_ROUND));  // listed entries of the cell
-    uint32_t* s_label = s_cnt + (CP_CHUNK + CP_ROUND);
-    __shared__ unsigned long long s_chunk;
+    uint64_t* s_e0 = reinterpret_cast<uint64_t*>(s_base + CP_PAD);              // first list slot of the cell
+    uint32_t* s_cnt = reinterpret_cast<uint32_t*>(s_e0 + CP_PAD);               // listed entries of the cell
+    uint32_t* s_label = s_cnt + CP_PAD;
+    // the NEXT chunk's metadata, brought in by cp.async while this chunk is summed (element t is written and read by thread t only)
+    uint64_t* r_lo = reinterpret_cast<uint64_t*>(s_label + CP_PAD);
+    uint32_t* r_cell = reinterpret_cast<uint32_t*>(r_lo + CP_CHUNK);
+    uint32_t* r_label = r_cell + CP_CHUNK;
+    uint32_t* r_cnt = r_label + CP_CHUNK;
+    __shared__ unsigned long long s_chunk[2];
     __shared__ uint32_t s_last[CP_CHUNK / 32 + 1];  // bit p: position p is the last of its label inside the chunk
     const uint32_t t = threadIdx.x;
     const int lane = t & 31, warp = t >> 5;
@@ -303,23 +317,42 @@ __global__ void __launch_bounds__(CP_THREADS, 1) k_collapse_pattern(
         const uint32_t f = x >> 17;
         atomicAdd(&acc[cp_swz(x & 0x1ffffu)], f == LG_PAT_ZERO ? 0xffffffffu : f);  // a stored zero takes its pattern bit back
     };
-    while (true) {
-        __syncthreads();
-        if (t == 0) s_chunk = atomicAdd(next_chunk, 1ull);
-        __syncthreads();
-        const uint64_t chunk = s_chunk;
-        if (chunk >= nchunks) break;
-        const uint64_t p0 = chunk * CP_CHUNK;
-        const int np = (int)((p0 + CP_CHUNK) < ncells ? CP_CHUNK : (ncells - p0));
-        if ((int)t < np) {
-            const uint32_t cell = sorted_cell[p0 + t];
-            s_label[t] = sorted_label[p0 + t];
+    auto cells_of = [&](uint64_t c) { return (int)((c * CP_CHUNK + CP_CHUNK) < ncells ? CP_CHUNK : (ncells - c * CP_CHUNK)); };
+    auto meta_level1 = [&](uint64_t c) {  // which cells, which labels
+        if (c < nchunks && (int)t < cells_of(c)) {
+            cp_async4(&r_cell[t], sorted_cell + c * CP_CHUNK + t);
+            cp_async4(&r_label[t], sorted_label + c * CP_CHUNK + t);
+        }
+    };
+    auto meta_level2 = [&](uint64_t c) {  // after this thread's level-1 copies have landed: the cell's extent and list length
+        if (c < nchunks && (int)t < cells_of(c)) {
+            const uint32_t cell = r_cell[t];
+            cp_async8(&r_lo[t], indptr + cell);
+            cp_async4(&r_cnt[t], exc_cnt + cell);
+        }
+    };
+    if (t == 0) s_chunk[0] = atomicAdd(next_chunk, 1ull);
+    __syncthreads();
+    uint64_t chunk = s_chunk[0];
+    meta_level1(chunk);
+    cp_async_wait_all();
+    meta_level2(chunk);
+    cp_async_wait_all();
+    for (int it = 0; chunk < nchunks; ++it) {
+        const int np = cells_of(chunk);
+        if ((int)t < np) {  // this chunk's metadata out of the landing zone (own elements: no barrier needed before)
+            const uint32_t cell = r_cell[t];
+            s_label[t] = r_label[t];
             s_base[t] = reinterpret_cast<const char*>(bm + ((uint64_t)(cell >> 8) * nchunks_g) * (uint64_t)(LG_PAT_CELLS * LG_PAT_STRIDE) +
                                                       (uint64_t)(cell & 255u) * LG_PAT_STRIDE);
-            s_e0[t] = (indptr[cell] >> 1) + cell;
-            s_cnt[t] = exc_cnt[cell];
+            s_e0[t] = (r_lo[t] >> 1) + cell;
+            s_cnt[t] = r_cnt[t];
         }
+        if (t == 0) s_chunk[(it + 1) & 1] = atomicAdd(next_chunk, 1ull);
         __syncthreads();
+        const uint64_t nxt = s_chunk[(it + 1) & 1];
+        meta_level1(nxt);
+        bool level2_done = false;
         if (t < CP_CHUNK) {
             const bool last = (int)t < np && ((int)t == np - 1 || s_label[t + 1] != s_label[t]);
             const unsigned mk = __ballot_sync(0xffffffffu, last);
@@ -338,6 +371,8 @@ __global__ void __launch_bounds__(CP_THREADS, 1) k_collapse_pattern(
             }
             if (lab < S) {
                 uint32_t ones = 0, twos = 0, fours = 0, eights = 0, h0 = 0, h1 = 0, h2 = 0, h3 = 0, h4 = 0;
+                // the listed entries of cell b + (warp & 15) of a round: this half of the warp pair takes entries 32 half + lane (+ 64 i)
+                const uint32_t k0 = ((uint32_t)(warp >> 4) << 5) + lane;
                 for (int b = seg0; b < seg1; b += CP_ROUND) {
                     uint32_t w[CP_ROUND];
                     if (active && b + CP_ROUND <= seg1) {  // a full round: sixteen plain loads in flight
@@ -350,7 +385,6 @@ __global__ void __launch_bounds__(CP_THREADS, 1) k_collapse_pattern(
                             if (active && b + u < seg1) w[u] = __ldg(reinterpret_cast<const uint32_t*>(s_base[b + u] + toff));
                         }
                     }
-                    // the listed entries of cell b + (warp & 15): this half of the warp pair takes entries 32 half + lane (+ 64 i)
                     const int pe = b + (warp & 15);
                     uint32_t ecnt = 0;
                     uint64_t ee0 = 0;
@@ -358,7 +392,6 @@ __global__ void __launch_bounds__(CP_THREADS, 1) k_collapse_pattern(
                         ecnt = s_cnt[pe];
                         ee0 = s_e0[pe];
                     }
-                    const uint32_t k0 = ((uint32_t)(warp >> 4) << 5) + lane;
                     uint32_t x0 = 0u, x1 = 0u;  // no packed word is 0 (field 0 would be a count of one)
                     if (k0 < ecnt) x0 = __ldg(exc + ee0 + k0);
                     if (k0 + 64 < ecnt) x1 = __ldg(exc + ee0 + k0 + 64);
@@ -388,6 +421,11 @@ __global__ void __launch_bounds__(CP_THREADS, 1) k_collapse_pattern(
                     if (x0) add_listed(x0);
                     if (x1) add_listed(x1);
                     for (uint32_t k = k0 + 128; k < ecnt; k += 64) add_listed(__ldg(exc + ee0 + k));
+                }
+                if (!level2_done) {  // the next chunk's cells are known by now: ask for their extents (lands during the flushes)
+                    cp_async_wait_all();
+                    meta_level2(nxt);
+                    level2_done = true;
                 }
                 __syncthreads();  // every listed entry is in
                 if (active) {
@@ -427,6 +465,13 @@ __global__ void __launch_bounds__(CP_THREADS, 1) k_collapse_pattern(
             }
             seg0 = seg1;
         }
+        cp_async_wait_all();
+        if (!level2_done) {  // a chunk whose labels were all out of range
+            meta_level2(nxt);
+            cp_async_wait_all();
+        }
+        __syncthreads();  // everybody is done with this chunk's tables before the next chunk's are written
+        chunk = nxt;
     }
 }
 #undef LG_CSA
@@ -581,7 +626,7 @@ static int collapse_by_label(lg_ctx* ctx, LgStage& st, const lg_csc* m, const ui
 // can k_collapse_pattern take this block?  (thread t of 1024 owns bitmap word t: at most 16 chunks of 2048 genes)
 bool lg_collapse_pattern_fits(const lg_ctx* ctx, uint64_t D, uint64_t N) {
     const uint64_t nch = (D + LG_PAT_GC - 1) / LG_PAT_GC;
-    const size_t smem = (size_t)nch * LG_PAT_GC * 4 + (size_t)(CP_CHUNK + CP_ROUND) * 24;
+    const size_t smem = (size_t)nch * LG_PAT_GC * 4 + CP_META_BYTES;
     return D > 0 && N > 0 && N < 0xFFFFFFFFull && nch * (LG_PAT_GC / 32) <= CP_THREADS && smem + 4096 <= ctx->smem_optin;
 }
 
@@ -616,7 +661,7 @@ int lg_collapse_basic_pattern(lg_ctx* ctx, const lg_csc* m, const uint32_t* grou
     unsigned long long* d_next;
     LG_TRY(st.scratch(1, &d_next));
     LG_CUDA(ctx, cudaMemsetAsync(d_next, 0, sizeof(unsigned long long), ctx->stream));
-    const size_t smem = (size_t)pat->nchunks * LG_PAT_GC * 4 + (size_t)(CP_CHUNK + CP_ROUND) * 24;
+    const size_t smem = (size_t)pat->nchunks * LG_PAT_GC * 4 + CP_META_BYTES;
     LG_CUDA(ctx, cudaFuncSetAttribute(k_collapse_pattern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const uint64_t nwork = (N + CP_CHUNK - 1) / CP_CHUNK;
     const unsigned grid = (unsigned)(nwork < (uint64_t)ctx->num_sms ? nwork : (uint64_t)ctx->num_sms);
