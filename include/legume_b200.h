@@ -104,6 +104,15 @@ int lg_csc_concat(lg_ctx* ctx, const lg_csc* const* parts, uint32_t nparts, lg_c
 int lg_csc_wrap_device(lg_ctx* ctx, const uint64_t* d_indptr, const uint32_t* d_indices,
                        const float* d_values, uint64_t nrows, uint64_t ncols, uint64_t nnz,
                        lg_csc** out);
+/* on != 0: the block gets buffers of its own (about 3.9 KB per cell + 2 bytes per non-zero) into which every projection of it
+ * (lg_project / lg_project_raw on the tensor path) leaves the 1-bit sparsity pattern and the list of counts != 1 that its scan
+ * builds anyway; lg_collapse_basic / lg_collapse_batch with unit multiplicities then sum that pattern instead of streaming the
+ * arrays a second (third, ...) time — the multilevel collapse sums the same block once per level.  Same sums, bit for bit.
+ * No effect for blocks the pattern kernel cannot take (more than 32 768 genes); a block whose counts are not whole numbers below
+ * 32 768, or with more than half of a cell's entries != 1, keeps the CSC kernel.  on == 2: only if the buffers fit four times
+ * into the free device memory and LG_KEEP_PATTERN is not 0 (what the SparseIoVec mirrors ask for).  on == 0 releases the buffers
+ * (lg_csc_free does too).  lg_hotpath_run_sharded does this on its own for the length of one call. */
+int lg_csc_keep_pattern(lg_ctx* ctx, lg_csc* m, int on);
 int lg_csc_free(lg_ctx* ctx, lg_csc* m);
 int lg_csc_shape(const lg_csc* m, uint64_t* nrows, uint64_t* ncols, uint64_t* nnz);
 /* raw device pointers of a block (for torch interop / tests) */

@@ -503,6 +503,7 @@ class SparseIoVec {
         : ctx_(ctx) {
         if (indptr.empty()) throw Error(LG_ERR_INVALID, "empty indptr");
         ctx_.check(lg_csc_upload(ctx_.get(), indptr.data(), indices.data(), data.data(), nrows, 0, indptr.size() - 1, nullptr, &csc_));
+        ctx_.check(lg_csc_keep_pattern(ctx_.get(), csc_, 2));  // one projection, then one collapse per level: keep the pattern if memory allows
         uint64_t r, c, z;
         lg_csc_shape(csc_, &r, &c, &z);
         nrows_ = r;
@@ -521,6 +522,7 @@ class SparseIoVec {
         rc = lg_zarr_read_columns(ctx_.get(), z, col_lo, col_hi, &csc_);
         lg_zarr_close(z);
         ctx_.check(rc);
+        ctx_.check(lg_csc_keep_pattern(ctx_.get(), csc_, 2));
         lg_csc_shape(csc_, &r, &c, &nz);
         nrows_ = r;
         ncols_ = c;
@@ -532,6 +534,9 @@ class SparseIoVec {
     uint64_t refine_moves() const { return refine_moves_; }  // accepted DC-Poisson moves of the last multilevel collapse
     size_t num_columns() const { return ncols_; }
     const lg_csc* block() const { return csc_; }
+    // lg_csc_keep_pattern: projections of this block leave their 1-bit pattern + list of counts != 1 behind, and the collapses
+    // that follow (one per level of the multilevel scheme) sum those instead of streaming the arrays again; same sums
+    void keep_pattern(bool on = true) { ctx_.check(lg_csc_keep_pattern(ctx_.get(), csc_, on ? 1 : 0)); }
 
     // ---- batch.rs:259-336 ----
     template <typename T>

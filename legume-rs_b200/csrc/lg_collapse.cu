@@ -508,11 +508,20 @@ __global__ void k_split_point(const uint32_t* __restrict__ sorted_label, uint32_
     out[3] = n;
 }
 
+static int collapse_by_label_pattern(lg_ctx* ctx, LgStage& st, const lg_csc* m, const uint32_t* d_label, uint32_t S, float* d_sum,
+                                     float* d_size, const lg_pattern* pat);
+static int twin_usable(lg_ctx* ctx, const lg_csc* m, bool* yes);
+
 // generic "sum columns by label" driver shared by the basic (label = group) and batch (label = batch) stats
 static int collapse_by_label(lg_ctx* ctx, LgStage& st, const lg_csc* m, const uint32_t* d_label, const float* d_mult,
                              uint32_t S, float* d_sum, float* d_size, uint32_t S_half = 0,
                              const std::function<int()>* after_first_half = nullptr) {
     const uint64_t N = m->ncols, D = m->nrows;
+    if (!d_mult && !after_first_half && N && D && S) {  // the block keeps a pattern and a projection has filled it
+        bool yes = false;
+        LG_TRY(twin_usable(ctx, m, &yes));
+        if (yes) return collapse_by_label_pattern(ctx, st, m, d_label, S, d_sum, d_size, m->twin);
+    }
     LG_CUDA(ctx, cudaMemsetAsync(d_sum, 0, sizeof(float) * (size_t)D * S, ctx->stream));
     if (d_size) LG_CUDA(ctx, cudaMemsetAsync(d_size, 0, sizeof(float) * S, ctx->stream));
     if (N == 0 || D == 0 || S == 0) {  // an empty shard still takes its part in the caller's exchange
@@ -630,23 +639,15 @@ bool lg_collapse_pattern_fits(const lg_ctx* ctx, uint64_t D, uint64_t N) {
     return D > 0 && N > 0 && N < 0xFFFFFFFFull && nch * (LG_PAT_GC / 32) <= CP_THREADS && smem + 4096 <= ctx->smem_optin;
 }
 
-// lg_collapse_basic (unit multiplicities) from the pattern K1 left behind in this pass; the caller has checked pat->filled and
-// read pat->ovf as 0
-int lg_collapse_basic_pattern(lg_ctx* ctx, const lg_csc* m, const uint32_t* group_of_cell, uint32_t S, float* out_sum_ds,
-                              float* out_size_s, const lg_pattern* pat) {
-    LG_REQUIRE(ctx, m && group_of_cell && out_sum_ds && out_size_s && pat && pat->filled, "lg_collapse_basic_pattern: null argument");
+// sums by label (unit multiplicities) from a filled pattern whose flag the caller has read as 0; device pointers
+static int collapse_by_label_pattern(lg_ctx* ctx, LgStage& st, const lg_csc* m, const uint32_t* d_label, uint32_t S, float* d_sum,
+                                     float* d_size, const lg_pattern* pat) {
     const uint64_t N = m->ncols, D = m->nrows;
     LG_REQUIRE(ctx, lg_collapse_pattern_fits(ctx, D, N) && pat->nchunks == (uint32_t)((D + LG_PAT_GC - 1) / LG_PAT_GC),
-               "lg_collapse_basic_pattern: block outside the pattern kernel's range");
-    LgStage st(ctx);
-    const uint32_t* d_label;
-    float *d_sum, *d_size;
-    LG_TRY(st.in(group_of_cell, (size_t)N, &d_label));
-    LG_TRY(st.out(out_sum_ds, (size_t)D * S, &d_sum));
-    LG_TRY(st.out(out_size_s, (size_t)S, &d_size));
+               "collapse: block outside the pattern kernel's range");
     LG_CUDA(ctx, cudaMemsetAsync(d_sum, 0, sizeof(float) * (size_t)D * S, ctx->stream));
-    LG_CUDA(ctx, cudaMemsetAsync(d_size, 0, sizeof(float) * S, ctx->stream));
-    if (S == 0) return st.finish();
+    if (d_size) LG_CUDA(ctx, cudaMemsetAsync(d_size, 0, sizeof(float) * S, ctx->stream));
+    if (S == 0) return LG_OK;
     uint32_t *d_cell_in, *d_cell_out, *d_lab_out;
     LG_TRY(st.scratch(N, &d_cell_in));
     LG_TRY(st.scratch(N, &d_cell_out));
@@ -668,7 +669,37 @@ int lg_collapse_basic_pattern(lg_ctx* ctx, const lg_csc* m, const uint32_t* grou
     LG_LAUNCH(ctx, k_collapse_pattern, grid, CP_THREADS, smem, pat->bm, pat->nchunks, m->indptr, pat->exc, pat->exc_cnt, d_lab_out,
               d_cell_out, N, S, D, d_sum, d_size, d_next);
     ctx->pattern_collapses++;
+    return LG_OK;
+}
+
+// lg_collapse_basic (unit multiplicities) from the pattern K1 left behind in this pass; the caller has checked pat->filled and
+// read pat->ovf as 0
+int lg_collapse_basic_pattern(lg_ctx* ctx, const lg_csc* m, const uint32_t* group_of_cell, uint32_t S, float* out_sum_ds,
+                              float* out_size_s, const lg_pattern* pat) {
+    LG_REQUIRE(ctx, m && group_of_cell && out_sum_ds && out_size_s && pat && pat->filled, "lg_collapse_basic_pattern: null argument");
+    LgStage st(ctx);
+    const uint32_t* d_label;
+    float *d_sum, *d_size;
+    LG_TRY(st.in(group_of_cell, (size_t)m->ncols, &d_label));
+    LG_TRY(st.out(out_sum_ds, (size_t)m->nrows * S, &d_sum));
+    LG_TRY(st.out(out_size_s, (size_t)S, &d_size));
+    LG_TRY(collapse_by_label_pattern(ctx, st, m, d_label, S, d_sum, d_size, pat));
     return st.finish();
+}
+
+// the block's own pattern (lg_csc_keep_pattern), if a projection has filled it and it can express the block: 1, else 0
+static int twin_usable(lg_ctx* ctx, const lg_csc* m, bool* yes) {
+    *yes = false;
+    const char* pz = getenv("LG_COLLAPSE_PATTERN");
+    if (!m->twin || !m->twin->filled || (pz && pz[0] == '0')) return LG_OK;
+    if (m->twin_ovf < 0) {  // once per projection
+        int* h = reinterpret_cast<int*>(static_cast<char*>(ctx->pinned) + 256);
+        LG_CUDA(ctx, cudaMemcpyAsync(h, m->twin->ovf, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+        LG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        m->twin_ovf = *h ? 1 : 0;
+    }
+    *yes = m->twin_ovf == 0;
+    return LG_OK;
 }
 
 int lg_collapse_basic_split(lg_ctx* ctx, const lg_csc* m, const uint32_t* d_group, uint32_t S, uint32_t S_half, float* d_sum_ds,

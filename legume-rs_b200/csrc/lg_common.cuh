@@ -91,6 +91,11 @@ struct lg_csc {
     mutable int int_valued = -1;
     // cached "rows strictly ascending and in range inside every column" (-1 unknown): see lg_csc_require_canonical
     mutable int canonical = -1;
+    // lg_csc_keep_pattern: buffers owned by the block into which every projection of it leaves its pattern (lg_pattern), so
+    // that the collapses that follow (lg_collapse_basic / lg_collapse_batch with unit multiplicities) sum the pattern instead
+    // of streaming the arrays again; twin_ovf caches the device flag on the host (-1 = not read since the last projection)
+    mutable lg_pattern* twin = nullptr;
+    mutable int twin_ovf = -1;
 };
 
 constexpr size_t LG_CACHE_MIN = 1u << 20;

@@ -1029,8 +1029,58 @@ extern "C" int lg_csc_wrap_device(lg_ctx* ctx, const uint64_t* d_indptr, const u
     return LG_OK;
 }
 
+static void free_twin(lg_ctx* ctx, lg_csc* m) {
+    if (!m->twin) return;
+    if (ctx) {
+        cudaSetDevice(ctx->device);
+        cudaStreamSynchronize(ctx->stream);
+    }
+    if (m->twin->bm) cudaFree(m->twin->bm);
+    if (m->twin->exc) cudaFree(m->twin->exc);
+    if (m->twin->exc_cnt) cudaFree(m->twin->exc_cnt);
+    if (m->twin->ovf) cudaFree(m->twin->ovf);
+    delete m->twin;
+    m->twin = nullptr;
+    m->twin_ovf = -1;
+}
+
+extern "C" int lg_csc_keep_pattern(lg_ctx* ctx, lg_csc* m, int on) {
+    if (!ctx) return LG_ERR_INVALID;
+    LG_REQUIRE(ctx, m, "lg_csc_keep_pattern: null block");
+    cudaSetDevice(ctx->device);
+    if (!on) {
+        free_twin(ctx, m);
+        return LG_OK;
+    }
+    if (m->twin || !lg_collapse_pattern_fits(ctx, m->nrows, m->ncols)) return LG_OK;  // already there / outside the kernel's range
+    const uint64_t nch = (m->nrows + LG_PAT_GC - 1) / LG_PAT_GC, nsup = (m->ncols + LG_PAT_CELLS - 1) / LG_PAT_CELLS;
+    if (on == 2) {  // "if memory is plentiful": the buffers must fit four times into what is free
+        const char* kz = getenv("LG_KEEP_PATTERN");
+        if (kz && kz[0] == '0') return LG_OK;
+        size_t fr = 0, tot = 0;
+        const size_t need = ((size_t)(nsup * nch) * (LG_PAT_CELLS * LG_PAT_STRIDE) + (size_t)(m->nnz >> 1) + 2 * (size_t)m->ncols + 2) * 4;
+        if (cudaMemGetInfo(&fr, &tot) != cudaSuccess || need * 4 > fr) {
+            cudaGetLastError();
+            return LG_OK;
+        }
+    }
+    lg_pattern* t = new lg_pattern();
+    cudaError_t e = cudaMalloc(&t->bm, (size_t)(nsup * nch) * (LG_PAT_CELLS * LG_PAT_STRIDE) * sizeof(uint32_t));
+    if (e == cudaSuccess) e = cudaMalloc(&t->exc, (size_t)((m->nnz >> 1) + m->ncols + 1) * sizeof(uint32_t));
+    if (e == cudaSuccess) e = cudaMalloc(&t->exc_cnt, (size_t)m->ncols * sizeof(uint32_t));
+    if (e == cudaSuccess) e = cudaMalloc(&t->ovf, sizeof(int));
+    m->twin = t;
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        free_twin(ctx, m);
+        return lg_fail(ctx, e == cudaErrorMemoryAllocation ? LG_ERR_NOMEM : LG_ERR_CUDA, std::string("lg_csc_keep_pattern: ") + cudaGetErrorString(e));
+    }
+    return LG_OK;
+}
+
 extern "C" int lg_csc_free(lg_ctx* ctx, lg_csc* m) {
     if (!m) return LG_OK;
+    free_twin(ctx, m);
     if (m->owned) {
         if (ctx) {
             cudaSetDevice(ctx->device);

@@ -1263,7 +1263,8 @@ int lg_project_raw_umma(lg_ctx* ctx, const lg_csc* m, const float* d_basis, int 
     const uint64_t nsuper = (m->ncols + CELLS - 1) / CELLS;
     uint32_t* d_bm;
     // the hot path asks for the pattern to outlive this call (lg_pattern): it owns the buffers then
-    lg_pattern* pat = (mode == 0) ? ctx->pat : nullptr;
+    lg_pattern* pat = (mode == 0) ? (ctx->pat ? ctx->pat : m->twin) : nullptr;
+    if (pat && pat == m->twin) m->twin_ovf = -1;
     uint32_t *d_exc = nullptr, *d_exc_cnt = nullptr;
     int* d_exc_ovf = nullptr;
     if (pat) {

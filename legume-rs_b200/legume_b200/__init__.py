@@ -184,6 +184,13 @@ class CscBlock:
         self.ctx.check(lib.lg_csc_download(self.ctx.h, self.h, _ptr(indptr), _ptr(indices), _ptr(data)))
         return indptr, indices, data
 
+    def keep_pattern(self, on: bool = True):
+        """lg_csc_keep_pattern: every projection of this block leaves its 1-bit sparsity pattern + the list of counts != 1 in
+        buffers owned by the block, and the collapses that follow (unit multiplicities) sum those instead of streaming the
+        arrays again — one projection, then one collapse per level of the multilevel scheme.  Same sums, bit for bit."""
+        self.ctx.check(lib.lg_csc_keep_pattern(self.ctx.h, self.h, 1 if on else 0))
+        return self
+
     def free(self):
         if self.h:
             lib.lg_csc_free(self.ctx.h if self.ctx.h else None, self.h)
@@ -993,6 +1000,11 @@ class SparseIoVec:
 
     def __init__(self, ctx: Context, block: CscBlock):
         self.ctx, self.block = ctx, block
+        # the reference's flow is one projection and then one collapse per level (and per label kind): the block keeps the
+        # projection's 1-bit pattern for them (lg_csc_keep_pattern; same sums) unless LG_KEEP_PATTERN=0 or memory is short —
+        # the buffers take about half of what the block itself does
+        if block.ncols:
+            ctx.check(lib.lg_csc_keep_pattern(ctx.h, block.h, 2))
         self.col_to_group = None      # uint32[N]
         self.group_keys = None
         self.col_to_batch = None      # uint32[N]

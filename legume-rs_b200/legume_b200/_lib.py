@@ -42,6 +42,7 @@ _sig = {
     "lg_csc_concat": [_vp, _vp, _u32, C.POINTER(_vp)],
     "lg_csc_wrap_device": [_vp, _vp, _vp, _vp, _u64, _u64, _u64, C.POINTER(_vp)],
     "lg_csc_free": [_vp, _vp],
+    "lg_csc_keep_pattern": [_vp, _vp, _i],
     "lg_csc_shape": [_vp, C.POINTER(_u64), C.POINTER(_u64), C.POINTER(_u64)],
     "lg_csc_device_arrays": [_vp, C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp)],
     "lg_csc_download": [_vp, _vp, _vp, _vp, _vp],

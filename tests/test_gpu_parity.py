@@ -524,6 +524,47 @@ def test_collapse_from_the_projection_pattern_equals_the_csc_collapse(lg, ctx, c
     assert torch.equal(off["sum_ds"], c["sum_ds"]) and torch.equal(off["size_s"], c["size_s"])
 
 
+def test_block_that_keeps_its_pattern_collapses_from_it(lg, ctx):
+    """lg_csc_keep_pattern: after a projection of the block, lg_collapse_basic and lg_collapse_batch (unit multiplicities) sum
+    the pattern; with multiplicities, before any projection, after an exact-order projection (no scan ran) or once the
+    buffers are released they stream the arrays.  The sums are the same bits every time."""
+    import torch
+    from legume_b200.pipeline import HotPath
+    rng = np.random.default_rng(5)
+    D, N, K, kk, B = 4500, 1100, 50, 5, 3
+    ip, ix, v = _pattern_case(rng, D, N, 0.07, 0.9, 12, zeros=40, empty_every=23)
+    blk = lg.CscBlock.upload(ctx, ip, ix, v, D)
+    basis = torch.from_numpy(basis_for(D, K, 6)).cuda()
+    batch = torch.from_numpy(rng.integers(0, B, N).astype(np.int32)).cuda()
+    hp = HotPath(ctx)
+    count = lambda: lg.lib.lg_ctx_pattern_collapse_count(ctx.h)
+    ref = hp.run(blk, basis, batch, B, kk)  # no pattern kept: the CSC kernels
+    ref_db, ref_nbs = hp.collapse_batch(blk, ref["group"], batch, ref["num_groups"], B)
+    blk.keep_pattern()
+    c0 = count()
+    s0, z0 = hp.collapse_basic(blk, ref["group"], ref["num_groups"])  # nothing projected yet: arrays
+    assert count() == c0 and torch.equal(s0, ref["sum_ds"]) and torch.equal(z0, ref["size_s"])
+    got = hp.run(blk, basis, batch, B, kk)  # projection fills the pattern, the collapse of the same pass sums it
+    assert count() == c0 + 1
+    for key in ("proj", "group", "sum_ds", "size_s"):
+        assert torch.equal(got[key], ref[key]), key
+    db, nbs = hp.collapse_batch(blk, ref["group"], batch, ref["num_groups"], B)  # label = batch
+    assert count() == c0 + 2 and torch.equal(db, ref_db) and torch.equal(nbs, ref_nbs)
+    coarse = (ref["group"] // 4).contiguous()  # another level of the multilevel scheme: same block, coarser labels
+    ng = int(coarse.max().item()) + 1
+    s1, z1 = hp.collapse_basic(blk, coarse, ng)
+    assert count() == c0 + 3
+    dense = np.zeros((ng, D), np.float64)
+    g = coarse.cpu().numpy()
+    for j in range(N):
+        np.add.at(dense[g[j]], ix[ip[j]:ip[j + 1]].astype(np.int64), v[ip[j]:ip[j + 1]])
+    assert np.array_equal(s1.cpu().numpy().astype(np.float64), dense)
+    assert np.array_equal(z1.cpu().numpy(), np.bincount(g, minlength=ng).astype(np.float32))
+    blk.keep_pattern(False)
+    s2, _ = hp.collapse_basic(blk, coarse, ng)
+    assert count() == c0 + 3 and torch.equal(s2, s1)
+
+
 def test_sparse_io_stack_projects_every_modality_and_stacks(lg, ctx):
     """RandProjOps for SparseIoStack (random_projection.rs:200-340): per-modality projection with its own basis, vertical
     concatenation of bases (rows) and projections (dims); batch labels cut to the shared column count; one set of codes"""

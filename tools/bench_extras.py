@@ -40,6 +40,7 @@ def c3_adjust(ctx, hp, N=1_000_000, B=8, D=30000, K=50, kk=10, knn=10, reps=2, p
     dev = hp.dev
     tabs = sim.make_tables(D, ntopic=8, nbatch=B, depth=1500, pve_batch=0.3, seed=42)
     blk, _, batch_h = sim.sim_block(ctx, tabs, 0, N)
+    blk.keep_pattern(True)  # as the SparseIoVec mirrors do: the three collapses below sum the projection's pattern
     batch = torch.from_numpy(batch_h.astype(np.int32)).to(dev)
     basis = torch.from_numpy(np.random.default_rng(0).standard_normal((D, K)).astype(np.float32)).to(dev)
     t = {}
