@@ -416,7 +416,9 @@ int lg_dcp_refine_level(lg_ctx* ctx, const float* profiles, const float* size_fa
  *   preload_columns + csc_column_arrays over a column range            zarr.rs:573-587, 982-994   -> lg_zarr_read_columns_host
  *   read_columns_csc (the block handed to the visitors)                sparse_io_vector/read.rs:172-285 -> lg_zarr_read_columns
  * Chunks are inflated on the host cores (libzstd bound at run time with dlopen; LG_INGEST_THREADS, default all cores up to
- * 32) and the block goes through lg_csc_upload.  The hdf5 twin, the /by_row copy and `.zarr.zip` stores are not read.
+ * 32) and the block goes through lg_csc_upload.  A path ending in `.zip` is opened as an archive of such a
+ * directory (zarr_io.rs:30-85: entries under `<stem>/`, `<stem>.zarr/` or bare; stored or deflated; ZIP64) and read in place.  The hdf5 twin and
+ * the /by_row copy are not read.
  * lg_zarr_open reports through `err` (it has no context yet); the other calls through lg_zarr_last_error. */
 typedef struct lg_zarr lg_zarr;
 int lg_zarr_open(const char* path, lg_zarr** out, char* err, size_t err_len);

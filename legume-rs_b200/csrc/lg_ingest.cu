@@ -13,10 +13,15 @@
 //
 // This file reads a column range the way SparseIo::read_columns_csc / csc_column_arrays do (zarr.rs:573-587, 982-994): the
 // range's indptr slice, then the chunks of indices / data that hold its entries, inflated on the host cores (libzstd is
-// bound at run time with dlopen, like NCCL: no link-time dependency) and handed to lg_csc_upload.  The hdf5 twin
-// (hdf5.rs, blosc) and the zip store are not read.  No reference-written file exists in this environment, so the layout is
+// bound at run time with dlopen, like NCCL: no link-time dependency) and handed to lg_csc_upload.  A `.zarr.zip` archive of
+// such a directory (zarr_io.rs:30-85: zarrs' ZipStorageAdapter; written by common_io.rs:591-640 with STORED entries under the
+// prefix `<stem>/`, formerly `<stem>.zarr/`) is read in place through its central directory (ZIP64 included; deflated entries
+// through libz, also bound at run time).  The hdf5 twin (hdf5.rs, blosc) is not read.  No reference-written file exists in this environment, so the layout is
 // held to the Zarr V3 specification and zarrs' documented defaults: parity unpinned for this row.
 #include <dlfcn.h>
+#include <fcntl.h>
+#include <unistd.h>
+#include <zlib.h>  // the z_stream layout only: libz itself is bound with dlopen when a deflated entry is met
 
 #include <atomic>
 #include <cerrno>
@@ -27,6 +32,7 @@
 #include <mutex>
 #include <sstream>
 #include <thread>
+#include <unordered_map>
 
 #include "lg_common.cuh"
 
@@ -205,8 +211,226 @@ bool read_file(const std::string& path, std::string* out) {
     return true;
 }
 
+// ---- libz, bound at run time (deflated zip entries only) ----------------------------------------
+struct ZlibApi {
+    void* handle = nullptr;
+    int (*inflate_init2)(z_streamp, int, const char*, int) = nullptr;
+    int (*inflate_fn)(z_streamp, int) = nullptr;
+    int (*inflate_end)(z_streamp) = nullptr;
+    std::string err;
+};
+ZlibApi* zlib_api() {
+    static ZlibApi api;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        for (const char* n : {"libz.so.1", "libz.so"}) {
+            api.handle = dlopen(n, RTLD_NOW | RTLD_LOCAL);
+            if (api.handle) break;
+        }
+        if (!api.handle) {
+            api.err = "libz not found (dlopen libz.so.1): a deflated zip entry cannot be read";
+            return;
+        }
+        api.inflate_init2 = reinterpret_cast<decltype(api.inflate_init2)>(dlsym(api.handle, "inflateInit2_"));
+        api.inflate_fn = reinterpret_cast<decltype(api.inflate_fn)>(dlsym(api.handle, "inflate"));
+        api.inflate_end = reinterpret_cast<decltype(api.inflate_end)>(dlsym(api.handle, "inflateEnd"));
+        if (!api.inflate_init2 || !api.inflate_fn || !api.inflate_end) api.err = "libz: symbol missing";
+    });
+    return &api;
+}
+
+// ---- a store: a directory, or a zip archive of one ------------------------------------------------
+struct ZipEntry {
+    uint64_t off = 0, csize = 0, usize = 0;  // local header offset, stored and inflated sizes
+    uint16_t method = 0;                     // 0 stored, 8 deflated
+};
+struct ZStore {
+    std::string root;  // the directory, or the archive
+    bool zip = false;
+    int fd = -1;
+    std::string prefix;  // the archive's entries sit under `<stem>/` (or `<stem>.zarr/`, or nothing): zarr_io.rs:30-50
+    std::unordered_map<std::string, ZipEntry> entries;
+    ~ZStore() {
+        if (fd >= 0) close(fd);
+    }
+};
+inline uint16_t le16(const unsigned char* p) { return (uint16_t)(p[0] | (p[1] << 8)); }
+inline uint32_t le32(const unsigned char* p) { return (uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16) | ((uint32_t)p[3] << 24); }
+inline uint64_t le64(const unsigned char* p) { return (uint64_t)le32(p) | ((uint64_t)le32(p + 4) << 32); }
+bool pread_all(int fd, void* dst, size_t n, uint64_t off) {
+    char* d = static_cast<char*>(dst);
+    while (n) {
+        const ssize_t g = pread(fd, d, n, (off_t)off);
+        if (g <= 0) return false;
+        d += g;
+        off += (uint64_t)g;
+        n -= (size_t)g;
+    }
+    return true;
+}
+// the central directory of the archive -> entries (names as stored)
+bool zip_open(const std::string& path, ZStore* st, std::string* err) {
+    st->fd = open(path.c_str(), O_RDONLY | O_CLOEXEC);
+    if (st->fd < 0) {
+        *err = "cannot open " + path;
+        return false;
+    }
+    const off_t fsize = lseek(st->fd, 0, SEEK_END);
+    if (fsize < 22) {
+        *err = path + ": not a zip archive";
+        return false;
+    }
+    const size_t tail = (size_t)std::min<off_t>(fsize, 65536 + 22 + 20);
+    std::vector<unsigned char> buf(tail);
+    if (!pread_all(st->fd, buf.data(), tail, (uint64_t)(fsize - (off_t)tail))) {
+        *err = path + ": read error";
+        return false;
+    }
+    ssize_t e = -1;
+    for (ssize_t i = (ssize_t)tail - 22; i >= 0; --i)
+        if (le32(&buf[i]) == 0x06054b50u) {
+            e = i;
+            break;
+        }
+    if (e < 0) {
+        *err = path + ": no end-of-central-directory record (not a zip archive)";
+        return false;
+    }
+    uint64_t nent = le16(&buf[e + 10]), cd_size = le32(&buf[e + 12]), cd_off = le32(&buf[e + 16]);
+    if (nent == 0xffffu || cd_size == 0xffffffffu || cd_off == 0xffffffffu) {  // ZIP64: locator just before the record
+        if (e < 20 || le32(&buf[e - 20]) != 0x07064b50u) {
+            *err = path + ": ZIP64 locator missing";
+            return false;
+        }
+        const uint64_t r64 = le64(&buf[e - 20 + 8]);
+        unsigned char rec[56];
+        if (!pread_all(st->fd, rec, sizeof rec, r64) || le32(rec) != 0x06064b50u) {
+            *err = path + ": ZIP64 end-of-central-directory record unreadable";
+            return false;
+        }
+        nent = le64(rec + 32);
+        cd_size = le64(rec + 40);
+        cd_off = le64(rec + 48);
+    }
+    if (cd_off + cd_size > (uint64_t)fsize) {
+        *err = path + ": central directory outside the file";
+        return false;
+    }
+    std::vector<unsigned char> cd((size_t)cd_size);
+    if (cd_size && !pread_all(st->fd, cd.data(), (size_t)cd_size, cd_off)) {
+        *err = path + ": central directory unreadable";
+        return false;
+    }
+    size_t p = 0;
+    for (uint64_t i = 0; i < nent; ++i) {
+        if (p + 46 > cd.size() || le32(&cd[p]) != 0x02014b50u) {
+            *err = path + ": central directory entry " + std::to_string(i) + " is malformed";
+            return false;
+        }
+        ZipEntry ze;
+        ze.method = le16(&cd[p + 10]);
+        ze.csize = le32(&cd[p + 20]);
+        ze.usize = le32(&cd[p + 24]);
+        const size_t nlen = le16(&cd[p + 28]), xlen = le16(&cd[p + 30]), clen = le16(&cd[p + 32]);
+        ze.off = le32(&cd[p + 42]);
+        if (p + 46 + nlen + xlen + clen > cd.size()) {
+            *err = path + ": central directory entry overruns the directory";
+            return false;
+        }
+        const std::string name(reinterpret_cast<const char*>(&cd[p + 46]), nlen);
+        // ZIP64 extended information: the 64-bit values of the fields that read 0xffffffff, in this order
+        size_t x = p + 46 + nlen;
+        const size_t xend = x + xlen;
+        while (x + 4 <= xend) {
+            const uint16_t id = le16(&cd[x]), sz = le16(&cd[x + 2]);
+            if (id == 0x0001) {
+                size_t q = x + 4;
+                if (ze.usize == 0xffffffffu && q + 8 <= xend) {
+                    ze.usize = le64(&cd[q]);
+                    q += 8;
+                }
+                if (ze.csize == 0xffffffffu && q + 8 <= xend) {
+                    ze.csize = le64(&cd[q]);
+                    q += 8;
+                }
+                if (ze.off == 0xffffffffu && q + 8 <= xend) ze.off = le64(&cd[q]);
+            }
+            x += 4 + sz;
+        }
+        if (!name.empty() && name.back() != '/') st->entries.emplace(name, ze);
+        p += 46 + nlen + xlen + clen;
+    }
+    // where the hierarchy starts inside the archive (detect_zip_zarr_prefix, zarr_io.rs:30-50)
+    std::string file = path.substr(path.find_last_of('/') == std::string::npos ? 0 : path.find_last_of('/') + 1);
+    auto strip = [](std::string v, const std::string& suf) {
+        if (v.size() >= suf.size() && v.compare(v.size() - suf.size(), suf.size(), suf) == 0) v.resize(v.size() - suf.size());
+        return v;
+    };
+    const std::string stem = strip(file, ".zip");
+    const std::string new_prefix = strip(stem, ".zarr") + "/", legacy_prefix = stem + "/";
+    auto any_under = [&](const std::string& pre) {
+        for (const auto& kv : st->entries)
+            if (kv.first.compare(0, pre.size(), pre) == 0) return true;
+        return false;
+    };
+    st->prefix = any_under(new_prefix) ? new_prefix : (new_prefix != legacy_prefix && any_under(legacy_prefix) ? legacy_prefix : "");
+    st->zip = true;
+    return true;
+}
+// the bytes under `key` (a path relative to the root of the hierarchy): 1 read, 0 absent, -1 error (*err set)
+int store_read(const ZStore& st, const std::string& key, std::string* out, std::string* err) {
+    if (!st.zip) return read_file(st.root + "/" + key, out) ? 1 : 0;
+    const auto it = st.entries.find(st.prefix + key);
+    if (it == st.entries.end()) return 0;
+    const ZipEntry& ze = it->second;
+    unsigned char lh[30];
+    if (!pread_all(st.fd, lh, sizeof lh, ze.off) || le32(lh) != 0x04034b50u) {
+        *err = st.root + ": local header of " + key + " unreadable";
+        return -1;
+    }
+    const uint64_t data_off = ze.off + 30 + le16(lh + 26) + le16(lh + 28);
+    std::string comp((size_t)ze.csize, '\0');
+    if (ze.csize && !pread_all(st.fd, &comp[0], (size_t)ze.csize, data_off)) {
+        *err = st.root + ": " + key + " is truncated";
+        return -1;
+    }
+    if (ze.method == 0) {
+        out->swap(comp);
+        return 1;
+    }
+    if (ze.method != 8) {
+        *err = st.root + ": " + key + " uses zip compression method " + std::to_string(ze.method) + " (stored and deflated entries are read)";
+        return -1;
+    }
+    ZlibApi* z = zlib_api();
+    if (!z->err.empty()) {
+        *err = z->err;
+        return -1;
+    }
+    out->assign((size_t)ze.usize, '\0');
+    z_stream zs;
+    memset(&zs, 0, sizeof zs);
+    if (z->inflate_init2(&zs, -15, ZLIB_VERSION, (int)sizeof(z_stream)) != Z_OK) {  // raw deflate stream
+        *err = "libz: inflateInit2 failed";
+        return -1;
+    }
+    zs.next_in = reinterpret_cast<Bytef*>(&comp[0]);
+    zs.avail_in = (uInt)comp.size();
+    zs.next_out = reinterpret_cast<Bytef*>(&(*out)[0]);
+    zs.avail_out = (uInt)out->size();
+    const int rc = z->inflate_fn(&zs, Z_FINISH);
+    const bool ok = rc == Z_STREAM_END && zs.total_out == ze.usize;
+    z->inflate_end(&zs);
+    if (!ok) {
+        *err = st.root + ": " + key + " does not inflate to its recorded size";
+        return -1;
+    }
+    return 1;
+}
+
 struct ZArray {
-    std::string dir;       // .../by_column/<name>
+    const ZStore* store = nullptr;
+    std::string dir;       // key of the array inside the store: by_column/<name>
     uint64_t n = 0, chunk = 0;
     int elem = 0;          // bytes per element
     bool is_float = false;
@@ -218,6 +442,7 @@ struct ZArray {
 }  // namespace
 
 struct lg_zarr {
+    ZStore store;
     std::string root, err;
     uint64_t nrows = 0, ncols = 0, nnz = 0;
     ZArray indptr, indices, data;
@@ -236,10 +461,10 @@ int zfail(lg_zarr* z, int code, const std::string& msg) {
 }
 
 // zarr.json of one array -> ZArray; `want_float` / `want_bytes`: what the reference writes there
-bool open_array(const std::string& dir, bool want_float, int want_bytes, ZArray* a, std::string* err) {
+bool open_array(const ZStore& st, const std::string& dir, bool want_float, int want_bytes, ZArray* a, std::string* err) {
     std::string txt;
-    if (!read_file(dir + "/zarr.json", &txt)) {
-        *err = "cannot read " + dir + "/zarr.json";
+    if (store_read(st, dir + "/zarr.json", &txt, err) != 1) {
+        if (err->empty()) *err = "cannot read " + dir + "/zarr.json in " + st.root;
         return false;
     }
     JParser p(txt);
@@ -320,6 +545,7 @@ bool open_array(const std::string& dir, bool want_float, int want_bytes, ZArray*
         return false;
     }
     a->dir = dir;
+    a->store = &st;
     return true;
 }
 
@@ -348,7 +574,14 @@ bool read_range(const ZArray& a, uint64_t e0, uint64_t e1, void* dst, int nthrea
             const std::string path = a.dir + "/c" + a.sep + std::to_string(c);
             const uint64_t lo = std::max<uint64_t>(e0, c * a.chunk), hi = std::min<uint64_t>(e1, (c + 1) * a.chunk);
             char* out = static_cast<char*>(dst) + (size_t)(lo - e0) * a.elem;
-            if (!read_file(path, &comp)) {  // an absent chunk is the fill value (Zarr V3)
+            std::string rerr;
+            const int got_chunk = store_read(*a.store, path, &comp, &rerr);
+            if (got_chunk < 0) {
+                std::lock_guard<std::mutex> g(mu);
+                if (first_err.empty()) first_err = rerr;
+                continue;
+            }
+            if (got_chunk == 0) {  // an absent chunk is the fill value (Zarr V3)
                 if (a.is_float) {
                     const float f = (float)a.fill;
                     for (uint64_t i = 0; i < hi - lo; ++i) memcpy(out + i * 4, &f, 4);
@@ -407,13 +640,20 @@ extern "C" int lg_zarr_open(const char* path, lg_zarr** out, char* err, size_t e
     *out = nullptr;
     std::string root(path);
     while (root.size() > 1 && root.back() == '/') root.pop_back();
+    std::unique_ptr<lg_zarr> zz(new lg_zarr());
+    zz->store.root = root;
+    const bool is_zip = root.size() > 4 && root.compare(root.size() - 4, 4, ".zip") == 0;  // zarr_io.rs:59: by extension
+    std::string serr;
+    if (is_zip && !zip_open(root, &zz->store, &serr)) return say("lg_zarr_open: " + serr);
     std::string txt;
-    if (!read_file(root + "/zarr.json", &txt)) return say("lg_zarr_open: cannot read " + root + "/zarr.json (a Zarr V3 directory store is expected)");
+    if (store_read(zz->store, "zarr.json", &txt, &serr) != 1)
+        return say(serr.empty() ? "lg_zarr_open: cannot read " + root + "/zarr.json (a Zarr V3 directory store or a .zarr.zip of one is expected)"
+                                : "lg_zarr_open: " + serr);
     JParser p(txt);
     const JVal g = p.value();
     const JVal* node = g.get("node_type");
     if (!p.ok || !node || node->str != "group") return say("lg_zarr_open: " + root + "/zarr.json is not a Zarr V3 group");
-    lg_zarr* z = new lg_zarr();
+    lg_zarr* z = zz.release();
     z->root = root;
     const JVal* at = g.get("attributes");
     auto attr = [&](const char* k, uint64_t* v) {
@@ -424,8 +664,8 @@ extern "C" int lg_zarr_open(const char* path, lg_zarr** out, char* err, size_t e
     };
     std::string e;
     const bool have_shape = attr("nrow", &z->nrows) && attr("ncol", &z->ncols);
-    if (!open_array(root + "/by_column/indptr", false, 8, &z->indptr, &e) || !open_array(root + "/by_column/indices", false, 8, &z->indices, &e) ||
-        !open_array(root + "/by_column/data", true, 4, &z->data, &e)) {
+    if (!open_array(z->store, "by_column/indptr", false, 8, &z->indptr, &e) || !open_array(z->store, "by_column/indices", false, 8, &z->indices, &e) ||
+        !open_array(z->store, "by_column/data", true, 4, &z->data, &e)) {
         delete z;
         return say("lg_zarr_open: " + e);
     }

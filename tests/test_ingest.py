@@ -54,6 +54,60 @@ def test_zarr_host_read_round_trip(tmp_path, compress):
     be.close()
 
 
+def _zip_store(root, zip_path, prefix, method, pad_entries=0):
+    """the archive common_io.rs:591-640 writes from a store directory: entries sorted, directories included, under `prefix`"""
+    import zipfile
+    with zipfile.ZipFile(zip_path, "w", compression=method) as zf:
+        for dirpath, dirnames, filenames in sorted(os.walk(root)):
+            rel = os.path.relpath(dirpath, root)
+            rel = "" if rel == "." else rel + "/"
+            if rel:
+                zf.writestr(prefix + rel, b"")  # add_directory
+            for fn in sorted(filenames):
+                zf.write(os.path.join(dirpath, fn), prefix + rel + fn)
+        for i in range(pad_entries):  # more than 65 535 entries: the ZIP64 end-of-central-directory record
+            zf.writestr(f"{prefix}pad/{i:06d}", b"")
+
+
+@pytest.mark.parametrize("form", ["stem_stored", "legacy_deflated", "bare_stored", "zip64"])
+def test_zarr_zip_store_reads_in_place(tmp_path, form):
+    """`.zarr.zip` (zarr_io.rs:30-85: the reference opens the archive in place through zarrs' ZipStorageAdapter, entries
+    under `<stem>/`, formerly `<stem>.zarr/`, or bare): the same arrays as the directory it was zipped from — stored
+    entries as the reference writes them, deflated ones, and an archive large enough for the ZIP64 records"""
+    import zipfile
+    D, N = 300, 400
+    ip, ix, v = random_csc(D, N, 0.06, 7)
+    root = str(tmp_path / "m.zarr")
+    write_store(root, ip, ix, v, D, chunk=500)
+    zpath = str(tmp_path / "m.zarr.zip")
+    prefix, method, pad = {"stem_stored": ("m/", zipfile.ZIP_STORED, 0), "legacy_deflated": ("m.zarr/", zipfile.ZIP_DEFLATED, 0),
+                           "bare_stored": ("", zipfile.ZIP_STORED, 0), "zip64": ("m/", zipfile.ZIP_STORED, 66000)}[form]
+    _zip_store(root, zpath, prefix, method, pad)
+    import shutil
+    shutil.rmtree(root)  # finalize_zarr_output removes the directory: only the archive is left
+    be = lg.SparseMtxData.open(zpath)
+    assert (be.num_rows(), be.num_columns(), be.num_non_zeros()) == (D, N, len(v))
+    gip, gix, gv = be.read_columns_host()
+    assert np.array_equal(gip, ip) and np.array_equal(gix, ix) and gv.tobytes() == v.tobytes()
+    rip, rix, rv = be.read_columns_host(33, 257)
+    a, b = int(ip[33]), int(ip[257])
+    assert np.array_equal(rip, ip[33:258] - ip[33]) and np.array_equal(rix, ix[a:b]) and rv.tobytes() == v[a:b].tobytes()
+    be.close()
+
+
+def test_zarr_zip_errors(tmp_path):
+    bad = tmp_path / "x.zarr.zip"
+    bad.write_bytes(b"this is not an archive, only a file whose name ends in .zip")
+    with pytest.raises(lg.LegumeError, match="zip"):
+        lg.SparseMtxData.open(str(bad))
+    import zipfile
+    empty = str(tmp_path / "e.zarr.zip")
+    with zipfile.ZipFile(empty, "w") as zf:
+        zf.writestr("e/readme.txt", b"no hierarchy here")
+    with pytest.raises(lg.LegumeError, match="zarr.json"):
+        lg.SparseMtxData.open(empty)
+
+
 def test_zarr_default_chunking_and_missing_chunk(tmp_path):
     # the reference's own chunk size (the whole array when it is below 1 MiB); an absent chunk reads as the fill value
     D, N = 300, 400
